@@ -1,0 +1,420 @@
+"""Host-side mirror of retrofire-core's render API over the C ABI (include/retrofire_b200.h).
+
+Mirrors, name for name where Python allows:
+
+* `render(prims, verts, shader, uniform, to_screen, target, ctx)`  core/src/render.rs:134-147
+* `Batch` (builder, `.render()`)                                   core/src/render/batch.rs:31-147
+* `Context` (+ `FaceCull`, depth test, write masks, `stats`)       core/src/render/ctx.rs:11-127
+* `Stats` / `Throughput`                                           core/src/render/stats.rs:16-40
+* `shader.new(vs, fs)` -> a (vertex, fragment) catalogue pair      core/src/render/shader.rs:78-126
+* `Texture`                                                        core/src/render/tex.rs:33-37
+* `Framebuf` / `Colorbuf` targets (device-resident)                core/src/render/target.rs:35-58
+* `Frame.clear`                                                    front/src/lib.rs:103-120
+
+User closures cannot cross the FFI, so shaders are (vs_id, fs_id) pairs from the fixed
+catalogue. Everything here is thin marshalling: the work happens in
+librf_b200.so. There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import RfDraw, RfStats
+
+
+class RetrofireError(RuntimeError):
+    """A non-zero rf_status (the reference panics in these cases)."""
+
+    def __init__(self, status: int, msg: str = ""):
+        self.status = status
+        super().__init__(f"{_ffi.STATUS_NAMES.get(status, status)}: {msg}")
+
+
+# ---- Stats (render/stats.rs) ------------------------------------------------------------
+@dataclass
+class Throughput:
+    i: int = 0
+    o: int = 0
+
+    def __iadd__(self, other: "Throughput"):
+        self.i += other.i
+        self.o += other.o
+        return self
+
+
+@dataclass
+class Stats:
+    time: float = 0.0  # seconds
+    calls: float = 0.0
+    frames: float = 0.0
+    objs: Throughput = field(default_factory=Throughput)
+    prims: Throughput = field(default_factory=Throughput)
+    verts: Throughput = field(default_factory=Throughput)
+    frags: Throughput = field(default_factory=Throughput)
+
+    def __iadd__(self, o: "Stats"):  # stats.rs:199-208
+        self.time += o.time
+        self.calls += o.calls
+        self.frames += o.frames
+        self.objs += o.objs
+        self.prims += o.prims
+        self.verts += o.verts
+        self.frags += o.frags
+        return self
+
+    @staticmethod
+    def from_c(s: RfStats) -> "Stats":
+        return Stats(time=s.time_ns * 1e-9, calls=float(s.calls),
+                     prims=Throughput(s.prims_i, s.prims_o), verts=Throughput(s.verts_i, s.verts_o),
+                     frags=Throughput(s.frags_i, s.frags_o))
+
+    def counters(self) -> tuple:
+        return (int(self.calls), self.prims.i, self.prims.o, self.verts.i, self.verts.o, self.frags.i, self.frags.o)
+
+
+# ---- Context (render/ctx.rs) ------------------------------------------------------------
+class FaceCull:
+    Front = _ffi.CULL_FRONT
+    Back = _ffi.CULL_BACK
+
+
+class Ordering:  # core::cmp::Ordering as used by Context.depth_test
+    Less = _ffi.DEPTH_LESS
+    Equal = _ffi.DEPTH_EQUAL
+    Greater = _ffi.DEPTH_GREATER
+
+
+@dataclass
+class Context:
+    color_clear: Optional[tuple] = (0, 0, 0, 0xFF)
+    depth_clear: Optional[float] = float("inf")
+    face_cull: Optional[int] = FaceCull.Back
+    depth_sort: Optional[int] = None
+    depth_test: Optional[int] = Ordering.Less
+    color_write: bool = True
+    depth_write: bool = True
+    stats: Stats = field(default_factory=Stats)
+
+
+# ---- shaders (render/shader.rs; catalogue SURVEY §8a-11) ---------------------------------
+_FS_LANES = {  # fs id -> (lanes, persp_mask) implied by the varying's Rust type
+    _ffi.FS_COLOR3F: (3, 0b000), _ffi.FS_COLOR3F_SRGB: (3, 0b000), _ffi.FS_COLOR4F: (4, 0b0000),
+    _ffi.FS_CHECKER: (2, 0b11), _ffi.FS_TEX_CLAMP_LIT: (5, 0b11111), _ffi.FS_TEX_CLAMP: (2, 0b11),
+    _ffi.FS_TEX_REPEAT_POT: (2, 0b11), _ffi.FS_SPRITE_DISC: (2, 0b11), _ffi.FS_NORMAL_VIS: (3, 0b111),
+}
+
+
+@dataclass
+class Shader:
+    vs: int
+    fs: int
+    lanes: int
+    persp_mask: int
+    fs_uniform: Sequence[float] = ()
+    texture: Optional["Texture"] = None
+
+
+class shader:  # namespace mirroring `render::shader`
+    @staticmethod
+    def new(vs: int, fs: int, *, fs_uniform: Sequence[float] = (), texture: "Texture" = None,
+            lanes: int = None, persp_mask: int = None) -> Shader:
+        dl, dm = _FS_LANES[fs]
+        return Shader(vs, fs, dl if lanes is None else lanes, dm if persp_mask is None else persp_mask,
+                      tuple(fs_uniform), texture)
+
+
+# ---- Texture (render/tex.rs:33-37) --------------------------------------------------------
+class Texture:
+    """Host texel data (h, w, 3|4) uint8; uploaded lazily per Device."""
+
+    def __init__(self, data: np.ndarray):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        assert data.ndim == 3 and data.shape[2] in (3, 4)
+        self.data = data
+        self.h, self.w = data.shape[:2]
+        self.fmt = _ffi.TEXEL_RGB888 if data.shape[2] == 3 else _ffi.TEXEL_RGBA8888
+        self._dev = {}
+
+    def handle(self, dev: "Device") -> int:
+        h = self._dev.get(id(dev))
+        if h is None:
+            out = C.c_void_p()
+            dev._check(dev.lib.rf_texture_create(dev.h, self.w, self.h, self.fmt, self.data.ctypes.data, self.w, C.byref(out)))
+            h = out.value
+            self._dev[id(dev)] = h
+            dev._textures.append(h)
+        return h
+
+
+# ---- one render() call, marshalled ---------------------------------------------------------
+def _flatten_uniform(uniform) -> np.ndarray:
+    if isinstance(uniform, (tuple, list)):
+        flat = np.concatenate([np.asarray(u, dtype=np.float32).reshape(-1) for u in uniform])
+    else:
+        flat = np.asarray(uniform, dtype=np.float32).reshape(-1)
+    assert flat.size <= _ffi.RF_VS_UNIFORM_F32
+    out = np.zeros(_ffi.RF_VS_UNIFORM_F32, dtype=np.float32)
+    out[: flat.size] = flat
+    return out
+
+
+@dataclass
+class DrawCall:
+    """Arguments of one `render()` call in ABI form. Keeps the numpy buffers alive."""
+    prims: np.ndarray      # (n,3) uint32
+    verts: np.ndarray      # (n, stride) float32 : [x,y,z,a0..]
+    shader: Shader
+    uniform: np.ndarray    # 32 f32
+    viewport: np.ndarray   # 4x4 f32
+    face_cull: int = _ffi.CULL_BACK
+    depth_test: int = _ffi.DEPTH_LESS
+    color_write: bool = True
+    depth_write: bool = True
+    depth_sort: int = 0
+    mesh: Optional["Mesh"] = None
+
+    @staticmethod
+    def make(prims, verts, shd: Shader, uniform, to_screen, ctx: Context = None, mesh: "Mesh" = None) -> "DrawCall":
+        ctx = ctx or Context()
+        if mesh is None:
+            prims = np.ascontiguousarray(np.asarray(prims, dtype=np.uint32).reshape(-1, 3))
+            verts = np.ascontiguousarray(np.asarray(verts, dtype=np.float32))
+            assert verts.ndim == 2 and verts.shape[1] >= 3 + shd.lanes, (verts.shape, shd.lanes)
+        return DrawCall(prims, verts, shd, _flatten_uniform(uniform), np.asarray(to_screen, dtype=np.float32).reshape(4, 4),
+                        face_cull=ctx.face_cull or 0, depth_test=ctx.depth_test or 0,
+                        color_write=bool(ctx.color_write), depth_write=bool(ctx.depth_write),
+                        depth_sort=0 if ctx.depth_sort is None else int(ctx.depth_sort), mesh=mesh)
+
+    def to_struct(self, texture_handle: int = None, mesh_handle: int = None) -> RfDraw:
+        d = RfDraw()
+        if self.mesh is None:
+            d.indices = self.prims.ctypes.data_as(C.POINTER(C.c_uint32))
+            d.n_prims = self.prims.shape[0]
+            d.verts = self.verts.ctypes.data_as(C.POINTER(C.c_float))
+            d.n_verts = self.verts.shape[0]
+            d.vert_stride_f32 = self.verts.shape[1]
+        else:
+            d.mesh = mesh_handle
+        d.n_attr_lanes = self.shader.lanes
+        d.persp_mask = self.shader.persp_mask
+        d.vs, d.fs = self.shader.vs, self.shader.fs
+        C.memmove(d.vs_uniform, self.uniform.ctypes.data, 4 * _ffi.RF_VS_UNIFORM_F32)
+        fu = np.zeros(_ffi.RF_FS_UNIFORM_F32, dtype=np.float32)
+        fu[: len(self.shader.fs_uniform)] = np.asarray(self.shader.fs_uniform, dtype=np.float32)
+        C.memmove(d.fs_uniform, fu.ctypes.data, 4 * _ffi.RF_FS_UNIFORM_F32)
+        d.texture = texture_handle
+        vp = np.ascontiguousarray(self.viewport, dtype=np.float32)
+        C.memmove(d.viewport, vp.ctypes.data, 64)
+        d.face_cull, d.depth_test = self.face_cull, self.depth_test
+        d.color_write, d.depth_write, d.depth_sort = int(self.color_write), int(self.depth_write), self.depth_sort
+        return d
+
+
+# ---- device objects -----------------------------------------------------------------------
+class Device:
+    """One rf_ctx (one GPU, one stream)."""
+
+    def __init__(self, device: int = 0, stream: int = None):
+        self.lib = _ffi.load()
+        out = C.c_void_p()
+        st = self.lib.rf_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(out))
+        if st != _ffi.RF_OK:
+            raise RetrofireError(st, "rf_ctx_create failed (is an sm_100 GPU visible?)")
+        self.h = out.value
+        self._textures = []
+        self._targets = []
+        self._meshes = []
+
+    def _check(self, st: int):
+        if st != _ffi.RF_OK:
+            msg = self.lib.rf_last_error(self.h)
+            raise RetrofireError(st, msg.decode() if msg else "")
+
+    def close(self):
+        if self.h:
+            for t in self._targets:
+                t._destroy()
+            for m in self._meshes:
+                m._destroy()
+            for t in self._textures:
+                self.lib.rf_texture_destroy(t)
+            self.lib.rf_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_row_band(self, y0: int, y1: int):
+        self._check(self.lib.rf_ctx_set_row_band(self.h, y0, y1))
+
+    def flush(self):
+        self._check(self.lib.rf_flush(self.h))
+
+    def sync(self):
+        self._check(self.lib.rf_sync(self.h))
+
+    def stats(self, reset: bool = False) -> Stats:
+        s = RfStats()
+        self._check(self.lib.rf_ctx_stats(self.h, C.byref(s), int(reset)))
+        return Stats.from_c(s)
+
+    def last_pass(self):
+        t, n = C.c_uint64(), C.c_uint32()
+        self._check(self.lib.rf_ctx_last_pass(self.h, C.byref(t), C.byref(n)))
+        return t.value, n.value
+
+    def framebuf(self, w: int, h: int, fmt: int = _ffi.FMT_RGBA8888, depth: bool = True) -> "Framebuf":
+        return Framebuf(self, w, h, fmt, depth)
+
+    def mesh(self, prims, verts) -> "Mesh":
+        return Mesh(self, prims, verts)
+
+    # -- the hot path
+    def render(self, call: DrawCall, target: "Framebuf", want_stats: bool = False) -> Optional[Stats]:
+        tex = call.shader.texture.handle(self) if call.shader.texture is not None else None
+        d = call.to_struct(tex, call.mesh.h if call.mesh is not None else None)
+        if want_stats:
+            s = RfStats()
+            self._check(self.lib.rf_render(self.h, target.h, C.byref(d), C.byref(s)))
+            return Stats.from_c(s)
+        self._check(self.lib.rf_render(self.h, target.h, C.byref(d), None))
+        return None
+
+    def render_frames(self, call: DrawCall, targets: Sequence["Framebuf"], uniforms: np.ndarray):
+        """Frame batch: draw i -> targets[i] with vs_uniform uniforms[i] (n, 32) f32."""
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float32).reshape(len(targets), _ffi.RF_VS_UNIFORM_F32)
+        tex = call.shader.texture.handle(self) if call.shader.texture is not None else None
+        d = call.to_struct(tex, call.mesh.h if call.mesh is not None else None)
+        arr = (C.c_void_p * len(targets))(*[t.h for t in targets])
+        self._check(self.lib.rf_render_frames(self.h, arr, len(targets), C.byref(d), uniforms.ctypes.data))
+
+
+class Mesh:
+    """Persistent device copy of (prims, verts) — avoids Batch's per-call clones (batch.rs:62-84)."""
+
+    def __init__(self, dev: Device, prims, verts):
+        self.dev = dev
+        prims = np.ascontiguousarray(np.asarray(prims, dtype=np.uint32).reshape(-1, 3))
+        verts = np.ascontiguousarray(np.asarray(verts, dtype=np.float32))
+        self.n_prims, self.n_verts, self.stride = prims.shape[0], verts.shape[0], verts.shape[1]
+        out = C.c_void_p()
+        dev._check(dev.lib.rf_mesh_create(dev.h, verts.ctypes.data, self.n_verts, self.stride, prims.ctypes.data,
+                                          self.n_prims, C.byref(out)))
+        self.h = out.value
+        dev._meshes.append(self)
+
+    def _destroy(self):
+        if self.h:
+            self.dev.lib.rf_mesh_destroy(self.h)
+            self.h = None
+
+
+_HOST_DTYPE = {_ffi.FMT_RGBA8888: (np.uint8, 4), _ffi.FMT_XRGB8888: (np.uint32, 1), _ffi.FMT_ARGB8888: (np.uint8, 4),
+               _ffi.FMT_BGRA8888: (np.uint8, 4), _ffi.FMT_RGB888: (np.uint8, 3), _ffi.FMT_RGB565: (np.uint8, 2),
+               _ffi.FMT_RGBA4444: (np.uint8, 2)}
+
+
+class Framebuf:
+    """Device-resident `Framebuf<Colorbuf<_, Fmt>, Buf2<f32>>` (or a bare colour buffer if depth=False)."""
+
+    def __init__(self, dev: Device, w: int, h: int, fmt: int, depth: bool):
+        self.dev, self.w, self.h_px, self.fmt, self.has_depth = dev, w, h, fmt, depth
+        out = C.c_void_p()
+        dev._check(dev.lib.rf_target_create(dev.h, w, h, fmt, int(depth), C.byref(out)))
+        self.h = out.value
+        dev._targets.append(self)
+
+    def _destroy(self):
+        if self.h:
+            self.dev.lib.rf_target_destroy(self.h)
+            self.h = None
+
+    def clear(self, ctx: Context = None):
+        """Frame::clear (front/src/lib.rs:103-120): depth is filled with 1/depth_clear."""
+        ctx = ctx or Context()
+        rgba = (C.c_uint8 * 4)(*ctx.color_clear) if ctx.color_clear is not None else None
+        z = None
+        if ctx.depth_clear is not None and self.has_depth:
+            z = C.c_float(float(np.float32(1.0) / np.float32(ctx.depth_clear)))
+        self.dev._check(self.dev.lib.rf_target_clear(self.dev.h, self.h, rgba, C.byref(z) if z is not None else None))
+
+    def _host_shape(self):
+        dt, ch = _HOST_DTYPE[self.fmt]
+        return (dt, (self.h_px, self.w) if ch == 1 else (self.h_px, self.w, ch))
+
+    def download_color(self) -> np.ndarray:
+        dt, shape = self._host_shape()
+        out = np.empty(shape, dtype=dt)
+        self.dev._check(self.dev.lib.rf_target_download_color(self.dev.h, self.h, out.ctypes.data, self.w))
+        return out
+
+    def upload_color(self, buf: np.ndarray):
+        dt, shape = self._host_shape()
+        buf = np.ascontiguousarray(buf, dtype=dt).reshape(shape)
+        self.dev._check(self.dev.lib.rf_target_upload_color(self.dev.h, self.h, buf.ctypes.data, self.w))
+
+    def download_depth(self) -> np.ndarray:
+        out = np.empty((self.h_px, self.w), dtype=np.float32)
+        self.dev._check(self.dev.lib.rf_target_download_depth(self.dev.h, self.h, out.ctypes.data, self.w))
+        return out
+
+    def upload_depth(self, buf: np.ndarray):
+        buf = np.ascontiguousarray(buf, dtype=np.float32).reshape(self.h_px, self.w)
+        self.dev._check(self.dev.lib.rf_target_upload_depth(self.dev.h, self.h, buf.ctypes.data, self.w))
+
+    def color_devptr(self) -> int:
+        return self.dev.lib.rf_target_color_devptr(self.h)
+
+    def depth_devptr(self) -> int:
+        return self.dev.lib.rf_target_depth_devptr(self.h)
+
+
+# ---- render() and Batch ----------------------------------------------------------------------
+def render(prims, verts, shd: Shader, uniform, to_screen, target: Framebuf, ctx: Context, *, sync_stats: bool = True):
+    """`retrofire_core::render::render` (render.rs:134-207).
+
+    With sync_stats=True (default, the reference's observable behaviour) the call returns
+    after the draw has executed and `ctx.stats` has been updated (render.rs:206). With
+    sync_stats=False the draw is only queued; stats accumulate in the Device (`Device.stats`).
+    """
+    call = DrawCall.make(prims, verts, shd, uniform, to_screen, ctx)
+    s = target.dev.render(call, target, want_stats=sync_stats)
+    if s is not None:
+        ctx.stats += s
+
+
+@dataclass
+class Batch:
+    """`render::Batch` (batch.rs:31-147): builder whose `.render()` calls `render()`."""
+    prims: np.ndarray = None
+    verts: np.ndarray = None
+    uniform_: object = None
+    shader_: Shader = None
+    viewport_: np.ndarray = None
+    target_: Framebuf = None
+    ctx: Context = field(default_factory=Context)
+
+    def _upd(self, **kw) -> "Batch":
+        return dataclasses.replace(self, **kw)
+
+    def primitives(self, prims): return self._upd(prims=np.array(prims, dtype=np.uint32).reshape(-1, 3))
+    def vertices(self, verts): return self._upd(verts=np.array(verts, dtype=np.float32))
+    def mesh(self, m): return self._upd(prims=np.array(m[0], dtype=np.uint32).reshape(-1, 3), verts=np.array(m[1], dtype=np.float32))
+    def uniform(self, u): return self._upd(uniform_=u)
+    def shader(self, s): return self._upd(shader_=s)
+    def viewport(self, v): return self._upd(viewport_=v)
+    def target(self, t): return self._upd(target_=t)
+    def context(self, c): return self._upd(ctx=c)
+    def clone(self): return self._upd()
+
+    def render(self, *, sync_stats: bool = True):
+        render(self.prims, self.verts, self.shader_, self.uniform_, self.viewport_, self.target_, self.ctx, sync_stats=sync_stats)
