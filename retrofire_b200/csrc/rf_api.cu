@@ -1,0 +1,792 @@
+// rf_api.cu — C ABI (include/retrofire_b200.h) and pass orchestration for the sm_100a kernels.
+//
+// A "pass" is every draw queued between two flush points, executed in submission order by
+// one chain of kernels:
+//   k_vertex -> k_prim -> k_span_count -> k_bin_alloc -> k_piece_fill -> k_bin_sort -> k_raster
+// Passes are launched asynchronously on the ctx stream and validated lazily (capacity overflow
+// or device-detected errors) at the next synchronisation point; an overflowing pass poisons
+// the ctx on the device so that later passes become no-ops until the host has grown the
+// arenas and replayed them in order.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -prec-div=true
+//        -prec-sqrt=true -ftz=false -shared -Xcompiler -fPIC   (see __graft_entry__.build()).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rf_device.cuh"
+#include "rf_geometry.cuh"
+#include "rf_raster.cuh"
+
+namespace {
+
+constexpr int kSlots = 3;          // passes that may be in flight before the oldest is validated
+constexpr uint32_t kMaxTargetDim = 32768;
+
+struct PinnedBuf {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  bool reserve(size_t n) {
+    if (n <= cap) return true;
+    size_t nc = std::max(n, cap * 2);
+    uint8_t* q = nullptr;
+    if (cudaHostAlloc(&q, nc, cudaHostAllocDefault) != cudaSuccess) return false;
+    if (p) { std::memcpy(q, p, cap); cudaFreeHost(p); }
+    p = q; cap = nc;
+    return true;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool reserve(size_t n) {  // contents are NOT preserved
+    if (n <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    if (cudaMalloc(&p, n) != cudaSuccess) return false;
+    cap = n;
+    return true;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct QueuedDraw {
+  DrawDesc desc;        // verts/indices/tex resolved to device pointers at launch
+  rf_target* target;
+  size_t verts_off;     // into geometry staging, or SIZE_MAX when the draw uses an rf_mesh
+  size_t idx_off;
+};
+
+struct HostStatus {     // pinned, one per slot
+  PassStatus status;
+};
+
+struct QueuedClear {  // Frame::clear recorded at the head of a pass (replayed with it)
+  rf_target* target;
+  bool has_color, has_depth;
+  uint32_t color, zbits;
+};
+
+struct PassSlot {
+  bool in_flight = false;
+  std::vector<QueuedClear> clears;
+  std::vector<QueuedDraw> draws;
+  std::vector<rf_target*> targets;
+  PinnedBuf geom;       // pinned copy of host-pointer geometry
+  size_t geom_len = 0;
+  PinnedBuf table;      // pinned [DrawDesc x n][vbase][pbase][TargetDesc x nt]
+  DevBuf d_geom, d_table, d_dstats, d_status;
+  PinnedBuf h_dstats;
+  HostStatus* h_status = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  uint32_t NV = 0, NP = 0, n_tiles = 0, lt = 0;
+  uint32_t n_launches = 0;
+};
+
+}  // namespace
+
+struct rf_target {
+  rf_ctx* ctx;
+  uint32_t w, h, fmt;
+  bool has_depth;
+  uint32_t* d_color;
+  float* d_depth;
+};
+struct rf_texture {
+  rf_ctx* ctx;
+  uint32_t w, h;
+  uint32_t* d_data;
+};
+struct rf_mesh {
+  rf_ctx* ctx;
+  float* d_verts;
+  uint32_t* d_idx;
+  uint32_t n_verts, stride, n_prims;
+};
+
+struct rf_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string err;
+  uint32_t band_y0 = 0, band_y1 = 0xFFFFFFFFu;
+
+  PassSlot slots[kSlots];
+  int cur = 0;                 // slot collecting queued draws
+  std::vector<int> flight;     // slots launched and not yet validated, oldest first
+
+  // scratch arenas shared by all passes (stream order makes reuse safe)
+  DevBuf cv, spans, halves, pieces, order, tiles, cursors;
+  size_t cap_spans = 0, cap_halves = 0, cap_pieces = 0;
+  CtxStatus* d_cstatus = nullptr;
+  DevBuf bounce;               // upload/download staging on the device
+  PinnedBuf h_bounce;
+
+  rf_stats accum{};
+  rf_stats last_draw{};        // stats of the last draw of the last validated pass
+  uint64_t last_pass_ns = 0;
+  uint32_t last_pass_launches = 0;
+};
+
+namespace {
+
+rf_status fail(rf_ctx* c, rf_status st, const char* fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    c->err = buf;
+  }
+  return st;
+}
+
+#define RF_CUDA(c, expr)                                                                       \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess) return fail((c), RF_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+int lt_for(uint32_t L) { return L <= 3 ? 3 : (L <= 5 ? 5 : 8); }
+
+template <int LT> struct Sizes {
+  static size_t cv(size_t n) { return n * Rec<LT>::CVS * 4; }
+};
+size_t words_cv(int lt) { return lt == 3 ? Rec<3>::CVS : lt == 5 ? Rec<5>::CVS : Rec<8>::CVS; }
+size_t words_span(int lt) { return lt == 3 ? Rec<3>::SW : lt == 5 ? Rec<5>::SW : Rec<8>::SW; }
+size_t words_half(int lt) { return lt == 3 ? Rec<3>::HW : lt == 5 ? Rec<5>::HW : Rec<8>::HW; }
+size_t words_piece(int lt) { return lt == 3 ? Rec<3>::PW : lt == 5 ? Rec<5>::PW : Rec<8>::PW; }
+
+// ---- small utility kernels --------------------------------------------------------------------
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n, const CtxStatus* cs) {
+  if (cs->poison) return;
+  const size_t n4 = n >> 2;
+  uint4* p4 = reinterpret_cast<uint4*>(p);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p4[i] = make_uint4(v, v, v, v);
+  for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// host layouts of 3- and 2-byte formats <-> uint32 containers
+__global__ void k_pack_small(const uint32_t* c, uint8_t* out, size_t n, int bytes) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t v = c[i];
+    for (int b = 0; b < bytes; b++) out[i * bytes + b] = (uint8_t)(v >> (8 * b));
+  }
+}
+__global__ void k_unpack_small(const uint8_t* in, uint32_t* c, size_t n, int bytes) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    for (int b = 0; b < bytes; b++) v |= (uint32_t)in[i * bytes + b] << (8 * b);
+    c[i] = v;
+  }
+}
+__global__ void k_expand_rgb(const uint8_t* in, uint32_t* out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = in[3 * i] | in[3 * i + 1] << 8 | in[3 * i + 2] << 16 | 0xFF000000u;  // Color3::to_rgba
+}
+
+int host_bytes(uint32_t fmt) { return fmt <= RF_FMT_BGRA8888 ? 4 : (fmt == RF_FMT_RGB888 ? 3 : 2); }
+
+uint32_t pack_pixel_host(uint32_t fmt, const uint8_t c[4]) {
+  const uint32_t r = c[0], g = c[1], b = c[2], a = c[3];
+  switch (fmt) {
+    case RF_FMT_RGBA8888: return r | g << 8 | b << 16 | a << 24;
+    case RF_FMT_XRGB8888: return r << 16 | g << 8 | b;
+    case RF_FMT_ARGB8888: return a | r << 8 | g << 16 | b << 24;
+    case RF_FMT_BGRA8888: return b | g << 8 | r << 16 | a << 24;
+    case RF_FMT_RGB888: return r | g << 8 | b << 16;
+    case RF_FMT_RGB565: return ((r >> 3) & 0x1Fu) << 11 | ((g >> 2) & 0x3Fu) << 5 | ((b >> 3) & 0x1Fu);
+    default: return (r >> 4) << 12 | (g >> 4) << 8 | (b >> 4) << 4 | (a >> 4);
+  }
+}
+
+// ---- pass launch ----------------------------------------------------------------------------------
+template <int LT>
+void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
+  const int sm = c->sm_count;
+  cudaStream_t st = c->stream;
+  auto blocks = [&](size_t n, int bs, int per_sm) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + bs - 1) / bs, (size_t)sm * per_sm)); };
+  k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
+  k_prim<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+  k_span_count<LT><<<sm * 8, 256, 0, st>>>(P);
+  k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, st>>>(P);
+  k_piece_fill<LT><<<sm * 8, 256, 0, st>>>(P);
+  k_bin_sort<LT, RF_SORT_SMALL><<<sm * 8, 256, RF_SORT_SMALL * 8, st>>>(P, 0);
+  k_bin_sort<LT, RF_SORT_BIG><<<sm, 256, RF_SORT_BIG * 8, st>>>(P, 1);
+  k_raster<LT><<<sm * 6, RF_RASTER_WARPS * 32, 0, st>>>(P);
+  s.n_launches += 8;
+}
+
+rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, size_t want_spans, size_t want_halves, size_t want_pieces) {
+  // Any growth frees memory that in-flight kernels might still use -> callers guarantee idleness.
+  if (!c->cv.reserve(nv * words_cv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "clip-vertex arena");
+  // capacities are kept in units of the widest record so that an LT switch never shrinks them
+  if (want_spans > c->cap_spans) { if (!c->spans.reserve(want_spans * Rec<8>::SW * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->cap_spans = want_spans; }
+  if (want_halves > c->cap_halves) { if (!c->halves.reserve(want_halves * Rec<8>::HW * 4)) return fail(c, RF_E_NOMEM, "half arena"); c->cap_halves = want_halves; }
+  if (want_pieces > c->cap_pieces) {
+    if (!c->pieces.reserve(want_pieces * Rec<8>::PW * 4)) return fail(c, RF_E_NOMEM, "piece arena");
+    if (!c->order.reserve(want_pieces * 4)) return fail(c, RF_E_NOMEM, "order arena");
+    c->cap_pieces = want_pieces;
+  }
+  if (!c->tiles.reserve(n_tiles * 5 * 4 + 64)) return fail(c, RF_E_NOMEM, "tile arrays");
+  if (!c->cursors.reserve(64)) return fail(c, RF_E_NOMEM, "cursors");
+  return RF_OK;
+}
+
+rf_status wait_idle(rf_ctx* c) {
+  RF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RF_OK;
+}
+
+// Launch (or re-launch) the pass stored in slot `si`.
+rf_status launch_pass(rf_ctx* c, int si) {
+  PassSlot& s = c->slots[si];
+  const size_t nd = s.draws.size();
+  // ---- targets and tiles
+  s.targets.clear();
+  for (auto& q : s.draws) {
+    auto it = std::find(s.targets.begin(), s.targets.end(), q.target);
+    if (it == s.targets.end()) { s.targets.push_back(q.target); q.desc.target = (uint32_t)s.targets.size() - 1; }
+    else q.desc.target = (uint32_t)(it - s.targets.begin());
+  }
+  const size_t nt = s.targets.size();
+  uint32_t maxL = 0;
+  for (auto& q : s.draws) maxL = std::max(maxL, q.desc.L);
+  const int lt = lt_for(maxL);
+  s.lt = lt;
+
+  const size_t table_bytes = nd * sizeof(DrawDesc) + 2 * (nd + 1) * 4 + nt * sizeof(TargetDesc) + 64;
+  if (!s.table.reserve(table_bytes)) return fail(c, RF_E_NOMEM, "pinned table");
+  // idle device needed before any reallocation of buffers a previous launch of this slot used
+  bool need_idle = s.d_table.cap < table_bytes || s.d_geom.cap < s.geom_len || s.d_dstats.cap < nd * sizeof(DrawStats);
+  uint32_t nv = 0, np = 0, ntiles = 0;
+  for (auto& q : s.draws) { nv += q.desc.n_verts; np += q.desc.n_prims; }
+  for (auto* t : s.targets) ntiles += ((t->w + RF_TILE - 1) / RF_TILE) * ((t->h + RF_TILE - 1) / RF_TILE);
+  s.NV = nv; s.NP = np; s.n_tiles = ntiles;
+  const size_t want_spans = std::max<size_t>(c->cap_spans, 1u << 20);
+  const size_t want_halves = std::max<size_t>(c->cap_halves, 1u << 19);
+  const size_t want_pieces = std::max<size_t>(c->cap_pieces, 1u << 20);
+  need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 20 + 64 ||
+              want_spans > c->cap_spans || want_halves > c->cap_halves || want_pieces > c->cap_pieces || c->cursors.cap < 64;
+  if (need_idle) { rf_status st = wait_idle(c); if (st) return st; }
+  if (!s.d_table.reserve(table_bytes) || !s.d_geom.reserve(std::max<size_t>(s.geom_len, 16)) ||
+      !s.d_dstats.reserve(std::max<size_t>(nd * sizeof(DrawStats), 16)) || !s.d_status.reserve(sizeof(PassStatus)) ||
+      !s.h_dstats.reserve(std::max<size_t>(nd * sizeof(DrawStats), 16)))
+    return fail(c, RF_E_NOMEM, "pass buffers");
+  { rf_status st = ensure_arenas(c, lt, nv, ntiles, want_spans, want_halves, want_pieces); if (st) return st; }
+
+  // ---- build the table
+  uint8_t* tb = s.table.p;
+  DrawDesc* h_draws = reinterpret_cast<DrawDesc*>(tb);
+  uint32_t* h_vbase = reinterpret_cast<uint32_t*>(tb + nd * sizeof(DrawDesc));
+  uint32_t* h_pbase = h_vbase + (nd + 1);
+  size_t toff = nd * sizeof(DrawDesc) + 2 * (nd + 1) * 4;
+  toff = (toff + 15) & ~size_t(15);
+  TargetDesc* h_targets = reinterpret_cast<TargetDesc*>(tb + toff);
+  uint32_t vb = 0, pb = 0;
+  for (size_t i = 0; i < nd; i++) {
+    QueuedDraw& q = s.draws[i];
+    DrawDesc d = q.desc;
+    if (q.verts_off != SIZE_MAX) {
+      d.verts = reinterpret_cast<const float*>(static_cast<uint8_t*>(s.d_geom.p) + q.verts_off);
+      d.indices = reinterpret_cast<const uint32_t*>(static_cast<uint8_t*>(s.d_geom.p) + q.idx_off);
+    }
+    h_draws[i] = d;
+    h_vbase[i] = vb; h_pbase[i] = pb;
+    vb += d.n_verts; pb += d.n_prims;
+  }
+  h_vbase[nd] = vb; h_pbase[nd] = pb;
+  uint32_t tile_base = 0;
+  for (size_t i = 0; i < nt; i++) {
+    rf_target* t = s.targets[i];
+    TargetDesc& T = h_targets[i];
+    T.color = t->d_color; T.depth = t->has_depth ? t->d_depth : nullptr;
+    T.w = t->w; T.h = t->h; T.fmt = t->fmt;
+    T.tiles_x = (t->w + RF_TILE - 1) / RF_TILE; T.tiles_y = (t->h + RF_TILE - 1) / RF_TILE;
+    T.tile_base = tile_base; tile_base += T.tiles_x * T.tiles_y;
+    T.band_y0 = std::min(c->band_y0, t->h); T.band_y1 = std::min(c->band_y1, t->h);
+  }
+
+  cudaStream_t st = c->stream;
+  RF_CUDA(c, cudaEventRecord(s.ev_start, st));
+  s.n_launches = 0;
+  for (const QueuedClear& qc : s.clears) {
+    const size_t n = (size_t)qc.target->w * qc.target->h;
+    if (qc.has_color) { k_fill_u32<<<c->sm_count * 4, 256, 0, st>>>(qc.target->d_color, qc.color, n, c->d_cstatus); s.n_launches++; }
+    if (qc.has_depth) { k_fill_u32<<<c->sm_count * 4, 256, 0, st>>>(reinterpret_cast<uint32_t*>(qc.target->d_depth), qc.zbits, n, c->d_cstatus); s.n_launches++; }
+  }
+  if (nd == 0) {
+    RF_CUDA(c, cudaMemsetAsync(s.d_status.p, 0, sizeof(PassStatus), st));
+    RF_CUDA(c, cudaMemcpyAsync(&s.h_status->status, s.d_status.p, sizeof(PassStatus), cudaMemcpyDeviceToHost, st));
+    RF_CUDA(c, cudaEventRecord(s.ev_stop, st));
+    s.in_flight = true;
+    return RF_OK;
+  }
+  RF_CUDA(c, cudaMemcpyAsync(s.d_table.p, tb, toff + nt * sizeof(TargetDesc), cudaMemcpyHostToDevice, st));
+  if (s.geom_len) RF_CUDA(c, cudaMemcpyAsync(s.d_geom.p, s.geom.p, s.geom_len, cudaMemcpyHostToDevice, st));
+  RF_CUDA(c, cudaMemsetAsync(s.d_status.p, 0, sizeof(PassStatus), st));
+  RF_CUDA(c, cudaMemsetAsync(s.d_dstats.p, 0, std::max<size_t>(nd * sizeof(DrawStats), 16), st));
+  RF_CUDA(c, cudaMemsetAsync(c->tiles.p, 0, (size_t)ntiles * 20, st));
+  RF_CUDA(c, cudaMemsetAsync(c->cursors.p, 0, 64, st));
+
+  PassParams P{};
+  uint8_t* dt = static_cast<uint8_t*>(s.d_table.p);
+  P.draws = reinterpret_cast<const DrawDesc*>(dt);
+  P.vbase = reinterpret_cast<const uint32_t*>(dt + nd * sizeof(DrawDesc));
+  P.pbase = P.vbase + (nd + 1);
+  P.targets = reinterpret_cast<const TargetDesc*>(dt + toff);
+  P.n_draws = (uint32_t)nd; P.n_targets = (uint32_t)nt; P.NV = nv; P.NP = np; P.n_tiles = ntiles;
+  P.cv = static_cast<float*>(c->cv.p);
+  P.spans = static_cast<uint32_t*>(c->spans.p);
+  P.halves = static_cast<uint32_t*>(c->halves.p);
+  P.pieces = static_cast<uint32_t*>(c->pieces.p);
+  P.order = static_cast<uint32_t*>(c->order.p);
+  // capacities in records of THIS pass's width (arenas are sized for the widest record)
+  P.cap_spans = (uint32_t)std::min<size_t>(c->cap_spans * Rec<8>::SW / words_span(lt), 0xFFFFFFF0u);
+  P.cap_halves = (uint32_t)std::min<size_t>(c->cap_halves * Rec<8>::HW / words_half(lt), 0xFFFFFFF0u);
+  P.cap_pieces = (uint32_t)std::min<size_t>(c->cap_pieces, 0xFFFFFFF0u);
+  uint32_t* ta = static_cast<uint32_t*>(c->tiles.p);
+  P.tile_cnt = ta; P.tile_off = ta + ntiles; P.tile_fill = ta + 2 * (size_t)ntiles;
+  P.worklist = ta + 3 * (size_t)ntiles; P.worklist_big = ta + 4 * (size_t)ntiles;
+  P.cursors = static_cast<uint32_t*>(c->cursors.p);
+  P.dstats = static_cast<DrawStats*>(s.d_dstats.p);
+  P.status = static_cast<PassStatus*>(s.d_status.p);
+  P.cstatus = c->d_cstatus;
+
+  if (lt == 3) launch_kernels<3>(c, s, P);
+  else if (lt == 5) launch_kernels<5>(c, s, P);
+  else launch_kernels<8>(c, s, P);
+  RF_CUDA(c, cudaGetLastError());
+
+  RF_CUDA(c, cudaMemcpyAsync(&s.h_status->status, s.d_status.p, sizeof(PassStatus), cudaMemcpyDeviceToHost, st));
+  if (nd) RF_CUDA(c, cudaMemcpyAsync(s.h_dstats.p, s.d_dstats.p, nd * sizeof(DrawStats), cudaMemcpyDeviceToHost, st));
+  RF_CUDA(c, cudaEventRecord(s.ev_stop, st));
+  s.in_flight = true;
+  return RF_OK;
+}
+
+void reset_slot(PassSlot& s) {
+  s.clears.clear();
+  s.draws.clear();
+  s.geom_len = 0;
+  s.in_flight = false;
+}
+
+// Wait for every pass in flight, replay overflowed ones with larger arenas, fold Stats.
+rf_status validate_all(rf_ctx* c) {
+  rf_status result = RF_OK;
+  while (!c->flight.empty()) {
+    const int si = c->flight.front();
+    PassSlot& s = c->slots[si];
+    RF_CUDA(c, cudaEventSynchronize(s.ev_stop));
+    const PassStatus ps = s.h_status->status;
+    if (ps.overflow) {
+      // Every later pass in flight was a no-op (device poison). Grow and replay from here, in order.
+      { rf_status st = wait_idle(c); if (st) return st; }
+      const int lt = (int)s.lt;
+      const size_t ws = (size_t)((ps.spans_needed * words_span(lt) + Rec<8>::SW - 1) / Rec<8>::SW);
+      const size_t wh = (size_t)((ps.halves_needed * words_half(lt) + Rec<8>::HW - 1) / Rec<8>::HW);
+      const size_t wp = (size_t)ps.pieces_needed;
+      const size_t ns = std::max(c->cap_spans, ws + ws / 8 + 1024), nh = std::max(c->cap_halves, wh + wh / 8 + 1024);
+      // pieces_needed is only known once spans fit; guess from spans if it did not get that far
+      const size_t np = std::max(c->cap_pieces, std::max(wp + wp / 8, ws + ws / 4) + 1024);
+      { rf_status st = ensure_arenas(c, lt, s.NV, s.n_tiles, ns, nh, np); if (st) return st; }
+      RF_CUDA(c, cudaMemsetAsync(c->d_cstatus, 0, sizeof(CtxStatus), c->stream));
+      std::vector<int> replay = c->flight;
+      for (int r : replay) { rf_status st = launch_pass(c, r); if (st) return st; }
+      continue;  // re-validate the same front slot
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s.ev_start, s.ev_stop);
+    const uint64_t ns = (uint64_t)(ms * 1e6);
+    c->last_pass_ns = ns;
+    c->last_pass_launches = s.n_launches;
+    if (ps.error) {
+      if (ps.error & RF_ERRBIT_INDEX_OOB) result = fail(c, RF_E_INDEX_OOB, "vertex index out of bounds (render/prim.rs:17-19 panics)");
+      else if (ps.error & RF_ERRBIT_TARGET_OOB) result = fail(c, RF_E_TARGET_OOB, "scanline outside the render target (render/target.rs:148,173 panics)");
+      else result = fail(c, RF_E_NOMEM, "a 32x32 tile holds more than %u span pieces (max_bin=%u)", RF_SORT_BIG, ps.max_bin);
+    } else {
+      const DrawStats* ds = reinterpret_cast<const DrawStats*>(s.h_dstats.p);
+      for (size_t i = 0; i < s.draws.size(); i++) {
+        rf_stats d{};
+        d.calls = 1;
+        d.prims_i = s.draws[i].desc.n_prims; d.verts_i = s.draws[i].desc.n_verts;
+        d.prims_o = ds[i].prims_o; d.verts_o = 3 * ds[i].prims_o;
+        d.frags_i = ds[i].frags_i; d.frags_o = ds[i].frags_o;
+        c->accum.calls += 1;
+        c->accum.prims_i += d.prims_i; c->accum.prims_o += d.prims_o;
+        c->accum.verts_i += d.verts_i; c->accum.verts_o += d.verts_o;
+        c->accum.frags_i += d.frags_i; c->accum.frags_o += d.frags_o;
+        if (i + 1 == s.draws.size()) { d.time_ns = ns; c->last_draw = d; }
+      }
+      c->accum.time_ns += ns;
+    }
+    reset_slot(s);
+    c->flight.erase(c->flight.begin());
+  }
+  return result;
+}
+
+rf_status flush_impl(rf_ctx* c) {
+  PassSlot& s = c->slots[c->cur];
+  if (s.draws.empty() && s.clears.empty()) return RF_OK;
+  const int si = c->cur;
+  rf_status st = launch_pass(c, si);
+  if (st) { reset_slot(s); return st; }
+  c->flight.push_back(si);
+  // pick the next collecting slot; if none is free, validate (blocks on the oldest pass)
+  int next = -1;
+  for (int k = 0; k < kSlots; k++) if (!c->slots[k].in_flight && c->slots[k].draws.empty() && c->slots[k].clears.empty()) { next = k; break; }
+  if (next < 0) {
+    st = validate_all(c);
+    next = 0;
+    for (int k = 0; k < kSlots; k++) if (!c->slots[k].in_flight) { next = k; break; }
+  }
+  c->cur = next;
+  return st;
+}
+
+rf_status sync_impl(rf_ctx* c) {
+  rf_status st = flush_impl(c);
+  rf_status sv = validate_all(c);
+  if (st == RF_OK) st = sv;
+  if (st == RF_OK) RF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return st;
+}
+
+bool fs_needs_tex(uint32_t fs) { return fs == RF_FS_TEX_CLAMP_LIT || fs == RF_FS_TEX_CLAMP || fs == RF_FS_TEX_REPEAT_POT; }
+uint32_t fs_min_lanes(uint32_t fs) {
+  switch (fs) {
+    case RF_FS_COLOR3F: case RF_FS_COLOR3F_SRGB: case RF_FS_NORMAL_VIS: return 3;
+    case RF_FS_COLOR4F: return 4;
+    case RF_FS_TEX_CLAMP_LIT: return 5;
+    default: return 2;
+  }
+}
+
+rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float* vs_uniform_override) {
+  if (!c || !target || !d) return fail(c, RF_E_INVALID, "null argument");
+  if (target->ctx != c) return fail(c, RF_E_INVALID, "target belongs to another ctx");
+  if (d->depth_sort) return fail(c, RF_E_UNSUPPORTED, "Context::depth_sort is outside the hot path (SURVEY 8f-3)");
+  if (d->vs > RF_VS_SPRITE || d->fs > RF_FS_NORMAL_VIS) return fail(c, RF_E_UNSUPPORTED_SHADER, "shader id not in the catalogue");
+  if (d->n_attr_lanes > RF_MAX_ATTR_LANES || d->n_attr_lanes < fs_min_lanes(d->fs))
+    return fail(c, RF_E_UNSUPPORTED_SHADER, "fragment shader %u needs >= %u varying lanes, got %u", d->fs, fs_min_lanes(d->fs), d->n_attr_lanes);
+  if ((d->vs == RF_VS_SOLIDS && d->n_attr_lanes < 3) || (d->vs == RF_VS_SPRITE && d->n_attr_lanes < 2))
+    return fail(c, RF_E_UNSUPPORTED_SHADER, "vertex shader %u lanes", d->vs);
+  if (d->face_cull > RF_CULL_FRONT || d->depth_test > RF_DEPTH_GREATER) return fail(c, RF_E_INVALID, "bad Context flag");
+  if (fs_needs_tex(d->fs)) {
+    if (!d->texture) return fail(c, RF_E_INVALID, "fragment shader needs a texture");
+    if (d->fs == RF_FS_TEX_REPEAT_POT) {
+      const uint32_t w = d->texture->w, h = d->texture->h;
+      if (!w || !h || (w & (w - 1)) || (h & (h - 1))) return fail(c, RF_E_BAD_TEXTURE, "SamplerRepeatPot needs power-of-two dims, got %ux%u (render/tex.rs:230-231)", w, h);
+    }
+  }
+  QueuedDraw q{};
+  DrawDesc& D = q.desc;
+  PassSlot& s = c->slots[c->cur];
+  if (d->mesh) {
+    if (d->verts || d->indices) return fail(c, RF_E_INVALID, "give either mesh or host pointers");
+    if (d->mesh->stride < 3 + d->n_attr_lanes) return fail(c, RF_E_INVALID, "mesh stride too small");
+    D.verts = d->mesh->d_verts; D.indices = d->mesh->d_idx;
+    D.vstride = d->mesh->stride; D.n_verts = d->mesh->n_verts; D.n_prims = d->mesh->n_prims;
+    q.verts_off = q.idx_off = SIZE_MAX;
+  } else {
+    if ((d->n_prims && !d->indices) || (d->n_verts && !d->verts)) return fail(c, RF_E_INVALID, "null geometry");
+    if (d->vert_stride_f32 < 3 + d->n_attr_lanes) return fail(c, RF_E_INVALID, "vert_stride_f32 < 3 + n_attr_lanes");
+    const size_t vb = (size_t)d->n_verts * d->vert_stride_f32 * 4, ib = (size_t)d->n_prims * 12;
+    const size_t off = (s.geom_len + 15) & ~size_t(15);
+    const size_t ioff = (off + vb + 15) & ~size_t(15);
+    if (!s.geom.reserve(ioff + ib + 16)) return fail(c, RF_E_NOMEM, "pinned geometry staging");
+    if (vb) std::memcpy(s.geom.p + off, d->verts, vb);
+    if (ib) std::memcpy(s.geom.p + ioff, d->indices, ib);
+    s.geom_len = ioff + ib;
+    q.verts_off = off; q.idx_off = ioff;
+    D.vstride = d->vert_stride_f32; D.n_verts = d->n_verts; D.n_prims = d->n_prims;
+  }
+  D.L = d->n_attr_lanes; D.persp_mask = d->persp_mask; D.vs = d->vs; D.fs = d->fs;
+  D.flags = (uint32_t)d->face_cull | (uint32_t)d->depth_test << RF_F_DTEST_SHIFT | (d->color_write ? RF_F_CWRITE : 0u) | (d->depth_write ? RF_F_DWRITE : 0u);
+  D.tex = d->texture ? d->texture->d_data : nullptr;
+  D.tex_w = d->texture ? d->texture->w : 0; D.tex_h = d->texture ? d->texture->h : 0;
+  std::memcpy(D.vs_u, vs_uniform_override ? vs_uniform_override : d->vs_uniform, sizeof D.vs_u);
+  std::memcpy(D.fs_u, d->fs_uniform, sizeof D.fs_u);
+  std::memcpy(D.vp, d->viewport, sizeof D.vp);
+  q.target = target;
+  // a pass addresses targets with 16 bits and prims with 29 (key = prim*8 + fan index)
+  uint64_t np = D.n_prims;
+  for (auto& e : s.draws) np += e.desc.n_prims;
+  if (np >= (1u << 29) || s.draws.size() >= 60000) {
+    rf_status st = flush_impl(c);
+    if (st) return st;
+    return queue_draw(c, target, d, vs_uniform_override);
+  }
+  s.draws.push_back(q);
+  return RF_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+uint32_t rf_abi_version(void) { return RF_ABI_VERSION; }
+
+rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
+  if (!out) return RF_E_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return RF_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return RF_E_CUDA;
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RF_E_CUDA;
+  if (prop.major != 10) return RF_E_CUDA;  // sm_100a SASS only; no fallback path
+  rf_ctx* c = new rf_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (stream) c->stream = static_cast<cudaStream_t>(stream);
+  else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RF_E_CUDA; }
+    c->own_stream = true;
+  }
+  bool ok = cudaMalloc(&c->d_cstatus, sizeof(CtxStatus)) == cudaSuccess && cudaMemset(c->d_cstatus, 0, sizeof(CtxStatus)) == cudaSuccess;
+  for (int k = 0; k < kSlots && ok; k++) {
+    PassSlot& s = c->slots[k];
+    ok = ok && cudaEventCreate(&s.ev_start) == cudaSuccess && cudaEventCreate(&s.ev_stop) == cudaSuccess;
+    ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_status), sizeof(HostStatus), cudaHostAllocDefault) == cudaSuccess;
+  }
+  ok = ok && cudaFuncSetAttribute(k_bin_sort<3, RF_SORT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_bin_sort<5, RF_SORT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_bin_sort<8, RF_SORT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
+  if (!ok) { rf_ctx_destroy(c); return RF_E_CUDA; }
+  *out = c;
+  return RF_OK;
+}
+
+void rf_ctx_destroy(rf_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int k = 0; k < kSlots; k++) {
+    PassSlot& s = c->slots[k];
+    s.geom.release(); s.table.release(); s.h_dstats.release();
+    s.d_geom.release(); s.d_table.release(); s.d_dstats.release(); s.d_status.release();
+    if (s.h_status) cudaFreeHost(s.h_status);
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
+    if (s.ev_stop) cudaEventDestroy(s.ev_stop);
+  }
+  c->cv.release(); c->spans.release(); c->halves.release(); c->pieces.release(); c->order.release();
+  c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
+  if (c->d_cstatus) cudaFree(c->d_cstatus);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* rf_last_error(const rf_ctx* c) { return c ? c->err.c_str() : "no context"; }
+
+rf_status rf_ctx_set_row_band(rf_ctx* c, uint32_t y0, uint32_t y1) {
+  if (!c || y0 > y1) return fail(c, RF_E_INVALID, "bad band");
+  rf_status st = flush_impl(c);
+  c->band_y0 = y0; c->band_y1 = y1;
+  return st;
+}
+
+rf_status rf_target_create(rf_ctx* c, uint32_t w, uint32_t h, uint32_t fmt, int has_depth, rf_target** out) {
+  if (!c || !out || !w || !h || fmt > RF_FMT_RGBA4444) return fail(c, RF_E_INVALID, "bad target arguments");
+  if (w > kMaxTargetDim || h > kMaxTargetDim) return fail(c, RF_E_INVALID, "target larger than %ux%u", kMaxTargetDim, kMaxTargetDim);
+  cudaSetDevice(c->device);
+  rf_target* t = new rf_target{c, w, h, fmt, has_depth != 0, nullptr, nullptr};
+  const size_t n = (size_t)w * h;
+  if (cudaMalloc(&t->d_color, n * 4) != cudaSuccess) { delete t; return fail(c, RF_E_NOMEM, "colour buffer"); }
+  if (has_depth && cudaMalloc(&t->d_depth, n * 4) != cudaSuccess) { cudaFree(t->d_color); delete t; return fail(c, RF_E_NOMEM, "depth buffer"); }
+  cudaMemsetAsync(t->d_color, 0, n * 4, c->stream);  // Buf2::new zero-fills (util/buf.rs:155-161)
+  if (has_depth) cudaMemsetAsync(t->d_depth, 0, n * 4, c->stream);
+  *out = t;
+  return RF_OK;
+}
+
+void rf_target_destroy(rf_target* t) {
+  if (!t) return;
+  sync_impl(t->ctx);
+  cudaFree(t->d_color);
+  if (t->d_depth) cudaFree(t->d_depth);
+  delete t;
+}
+
+rf_status rf_target_clear(rf_ctx* c, rf_target* t, const uint8_t* rgba, const float* depth_recip) {
+  if (!c || !t) return fail(c, RF_E_INVALID, "null argument");
+  if (t->ctx != c) return fail(c, RF_E_INVALID, "target belongs to another ctx");
+  // A clear is recorded at the head of a pass so that it is ordered with, and replayed with, its draws.
+  if (!c->slots[c->cur].draws.empty()) { rf_status st = flush_impl(c); if (st) return st; }
+  QueuedClear qc{t, rgba != nullptr, depth_recip != nullptr && t->has_depth, 0u, 0u};
+  if (rgba) qc.color = pack_pixel_host(t->fmt, rgba);
+  if (qc.has_depth) std::memcpy(&qc.zbits, depth_recip, 4);
+  if (qc.has_color || qc.has_depth) c->slots[c->cur].clears.push_back(qc);
+  return RF_OK;
+}
+
+rf_status rf_target_upload_color(rf_ctx* c, rf_target* t, const void* host, size_t stride) {
+  if (!c || !t || !host || stride < t->w) return fail(c, RF_E_INVALID, "bad upload arguments");
+  rf_status st = sync_impl(c);
+  if (st) return st;
+  const int hb = host_bytes(t->fmt);
+  if (hb == 4) {
+    RF_CUDA(c, cudaMemcpy2DAsync(t->d_color, (size_t)t->w * 4, host, stride * 4, (size_t)t->w * 4, t->h, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    const size_t n = (size_t)t->w * t->h;
+    if (!c->bounce.reserve(n * hb)) return fail(c, RF_E_NOMEM, "bounce");
+    RF_CUDA(c, cudaMemcpy2DAsync(c->bounce.p, (size_t)t->w * hb, host, stride * hb, (size_t)t->w * hb, t->h, cudaMemcpyHostToDevice, c->stream));
+    k_unpack_small<<<c->sm_count * 4, 256, 0, c->stream>>>(static_cast<const uint8_t*>(c->bounce.p), t->d_color, n, hb);
+  }
+  RF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RF_OK;
+}
+
+rf_status rf_target_download_color(rf_ctx* c, rf_target* t, void* host, size_t stride) {
+  if (!c || !t || !host || stride < t->w) return fail(c, RF_E_INVALID, "bad download arguments");
+  rf_status st = sync_impl(c);
+  if (st) return st;
+  const int hb = host_bytes(t->fmt);
+  if (hb == 4) {
+    RF_CUDA(c, cudaMemcpy2DAsync(host, stride * 4, t->d_color, (size_t)t->w * 4, (size_t)t->w * 4, t->h, cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    const size_t n = (size_t)t->w * t->h;
+    if (!c->bounce.reserve(n * hb)) return fail(c, RF_E_NOMEM, "bounce");
+    k_pack_small<<<c->sm_count * 4, 256, 0, c->stream>>>(t->d_color, static_cast<uint8_t*>(c->bounce.p), n, hb);
+    RF_CUDA(c, cudaMemcpy2DAsync(host, stride * hb, c->bounce.p, (size_t)t->w * hb, (size_t)t->w * hb, t->h, cudaMemcpyDeviceToHost, c->stream));
+  }
+  RF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RF_OK;
+}
+
+rf_status rf_target_upload_depth(rf_ctx* c, rf_target* t, const float* host, size_t stride) {
+  if (!c || !t || !host || stride < t->w || !t->has_depth) return fail(c, RF_E_INVALID, "bad upload arguments");
+  rf_status st = sync_impl(c);
+  if (st) return st;
+  RF_CUDA(c, cudaMemcpy2DAsync(t->d_depth, (size_t)t->w * 4, host, stride * 4, (size_t)t->w * 4, t->h, cudaMemcpyHostToDevice, c->stream));
+  RF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RF_OK;
+}
+
+rf_status rf_target_download_depth(rf_ctx* c, rf_target* t, float* host, size_t stride) {
+  if (!c || !t || !host || stride < t->w || !t->has_depth) return fail(c, RF_E_INVALID, "bad download arguments");
+  rf_status st = sync_impl(c);
+  if (st) return st;
+  RF_CUDA(c, cudaMemcpy2DAsync(host, stride * 4, t->d_depth, (size_t)t->w * 4, (size_t)t->w * 4, t->h, cudaMemcpyDeviceToHost, c->stream));
+  RF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RF_OK;
+}
+
+void* rf_target_color_devptr(rf_target* t) { return t ? t->d_color : nullptr; }
+void* rf_target_depth_devptr(rf_target* t) { return t ? t->d_depth : nullptr; }
+
+rf_status rf_texture_create(rf_ctx* c, uint32_t w, uint32_t h, uint32_t fmt, const void* data, size_t stride, rf_texture** out) {
+  if (!c || !out || !data || !w || !h || fmt > RF_TEXEL_RGBA8888 || stride < w) return fail(c, RF_E_INVALID, "bad texture arguments");
+  cudaSetDevice(c->device);
+  const size_t n = (size_t)w * h;
+  const int bpp = fmt == RF_TEXEL_RGB888 ? 3 : 4;
+  rf_texture* t = new rf_texture{c, w, h, nullptr};
+  if (cudaMalloc(&t->d_data, n * 4) != cudaSuccess) { delete t; return fail(c, RF_E_NOMEM, "texture"); }
+  rf_status st = sync_impl(c);
+  if (st) { cudaFree(t->d_data); delete t; return st; }
+  if (bpp == 4) {
+    RF_CUDA(c, cudaMemcpy2DAsync(t->d_data, (size_t)w * 4, data, stride * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    if (!c->bounce.reserve(n * 3)) return fail(c, RF_E_NOMEM, "bounce");
+    RF_CUDA(c, cudaMemcpy2DAsync(c->bounce.p, (size_t)w * 3, data, stride * 3, (size_t)w * 3, h, cudaMemcpyHostToDevice, c->stream));
+    k_expand_rgb<<<c->sm_count, 256, 0, c->stream>>>(static_cast<const uint8_t*>(c->bounce.p), t->d_data, n);
+  }
+  RF_CUDA(c, cudaStreamSynchronize(c->stream));
+  *out = t;
+  return RF_OK;
+}
+
+void rf_texture_destroy(rf_texture* t) {
+  if (!t) return;
+  sync_impl(t->ctx);
+  cudaFree(t->d_data);
+  delete t;
+}
+
+rf_status rf_mesh_create(rf_ctx* c, const float* verts, uint32_t n_verts, uint32_t stride, const uint32_t* indices, uint32_t n_prims, rf_mesh** out) {
+  if (!c || !out || !verts || !indices || stride < 3) return fail(c, RF_E_INVALID, "bad mesh arguments");
+  cudaSetDevice(c->device);
+  rf_mesh* m = new rf_mesh{c, nullptr, nullptr, n_verts, stride, n_prims};
+  const size_t vb = std::max<size_t>((size_t)n_verts * stride * 4, 16), ib = std::max<size_t>((size_t)n_prims * 12, 16);
+  if (cudaMalloc(&m->d_verts, vb) != cudaSuccess || cudaMalloc(&m->d_idx, ib) != cudaSuccess) {
+    if (m->d_verts) cudaFree(m->d_verts);
+    delete m;
+    return fail(c, RF_E_NOMEM, "mesh");
+  }
+  RF_CUDA(c, cudaMemcpyAsync(m->d_verts, verts, (size_t)n_verts * stride * 4, cudaMemcpyHostToDevice, c->stream));
+  RF_CUDA(c, cudaMemcpyAsync(m->d_idx, indices, (size_t)n_prims * 12, cudaMemcpyHostToDevice, c->stream));
+  RF_CUDA(c, cudaStreamSynchronize(c->stream));
+  *out = m;
+  return RF_OK;
+}
+
+void rf_mesh_destroy(rf_mesh* m) {
+  if (!m) return;
+  sync_impl(m->ctx);
+  cudaFree(m->d_verts);
+  cudaFree(m->d_idx);
+  delete m;
+}
+
+rf_status rf_render(rf_ctx* c, rf_target* target, const rf_draw* draw, rf_stats* stats_out) {
+  if (c) cudaSetDevice(c->device);
+  rf_status st = queue_draw(c, target, draw, nullptr);
+  if (st) return st;
+  if (stats_out) {
+    st = sync_impl(c);
+    if (st) return st;
+    *stats_out = c->last_draw;
+  }
+  return RF_OK;
+}
+
+rf_status rf_render_frames(rf_ctx* c, rf_target* const* targets, uint32_t n_frames, const rf_draw* draw, const float* vs_uniforms) {
+  if (!c || !targets || !draw || !vs_uniforms) return fail(c, RF_E_INVALID, "null argument");
+  cudaSetDevice(c->device);
+  for (uint32_t i = 0; i < n_frames; i++) {
+    rf_status st = queue_draw(c, targets[i], draw, vs_uniforms + (size_t)i * RF_VS_UNIFORM_F32);
+    if (st) return st;
+  }
+  return RF_OK;
+}
+
+rf_status rf_flush(rf_ctx* c) {
+  if (!c) return RF_E_INVALID;
+  cudaSetDevice(c->device);
+  return flush_impl(c);
+}
+
+rf_status rf_sync(rf_ctx* c) {
+  if (!c) return RF_E_INVALID;
+  cudaSetDevice(c->device);
+  return sync_impl(c);
+}
+
+rf_status rf_ctx_stats(rf_ctx* c, rf_stats* out, int reset) {
+  if (!c || !out) return fail(c, RF_E_INVALID, "null argument");
+  rf_status st = sync_impl(c);
+  *out = c->accum;
+  if (reset) c->accum = rf_stats{};
+  return st;
+}
+
+rf_status rf_ctx_last_pass(rf_ctx* c, uint64_t* time_ns, uint32_t* n_launches) {
+  if (!c) return RF_E_INVALID;
+  rf_status st = sync_impl(c);
+  if (time_ns) *time_ns = c->last_pass_ns;
+  if (n_launches) *n_launches = c->last_pass_launches;
+  return st;
+}
+
+}  // extern "C"

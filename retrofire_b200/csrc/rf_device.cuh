@@ -1,0 +1,184 @@
+// rf_device.cuh — device-side structures and exact-arithmetic helpers shared by the kernels.
+//
+// NUMERICS CONTRACT: every + - * / is one IEEE binary32 operation,
+// round-to-nearest-even, never fused. This translation unit MUST be compiled with
+//   -fmad=false -prec-div=true -prec-sqrt=true -ftz=false      (never --use_fast_math)
+// Interpolation is by *sequential* accumulation (val = val + step), never closed form.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/retrofire_b200.h"
+
+#define RF_TILE 32          // framebuffer tile: RF_TILE rows x RF_TILE columns, one warp owns one tile
+#define RF_TILE_SHIFT 5
+#define RF_TILE_PITCH 33    // smem row pitch in words (bank = (row + col) % 32)
+#define RF_MAX_ROWS (1u << 20)
+
+// per-draw flag bits
+#define RF_F_CULL_MASK 0x3u
+#define RF_F_DTEST_SHIFT 2
+#define RF_F_DTEST_MASK 0x3u
+#define RF_F_CWRITE 0x10u
+#define RF_F_DWRITE 0x20u
+
+// device error bits (PassStatus::error)
+#define RF_ERRBIT_INDEX_OOB 0x1u
+#define RF_ERRBIT_TARGET_OOB 0x2u
+#define RF_ERRBIT_BIN_TOO_DEEP 0x4u
+
+struct DrawDesc {
+  const float* verts;       // [n_verts][vstride]
+  const uint32_t* indices;  // [n_prims][3]
+  const uint32_t* tex;      // RGBA8 texels (device copy is always 4 B/texel), row-major, pitch = tex_w
+  uint32_t vstride, n_verts, n_prims;
+  uint32_t L, persp_mask, vs, fs;
+  uint32_t target;          // index into the pass's TargetDesc table
+  uint32_t flags;           // RF_F_*
+  uint32_t tex_w, tex_h;
+  float vs_u[RF_VS_UNIFORM_F32];
+  float fs_u[RF_FS_UNIFORM_F32];
+  float vp[12];             // rows 0..2 of the viewport matrix
+};
+
+struct TargetDesc {
+  uint32_t* color;  // uint32 containers, pitch = w
+  float* depth;     // or nullptr
+  uint32_t w, h, fmt;
+  uint32_t tiles_x, tiles_y, tile_base;
+  uint32_t band_y0, band_y1;
+};
+
+struct DrawStats {
+  unsigned long long prims_o, frags_i, frags_o;
+};
+
+// zeroed before every pass; read back after it
+struct PassStatus {
+  unsigned long long spans_needed;   // total span records the pass wants
+  unsigned long long halves_needed;  // total half records
+  unsigned long long pieces_needed;  // total piece records
+  uint32_t error;                    // RF_ERRBIT_*
+  uint32_t overflow;                 // a capacity was exceeded: nothing was rasterised
+  uint32_t n_work;                   // non-empty tiles
+  uint32_t n_work_big;               // tiles whose bin needs the large-smem sort
+  uint32_t max_bin;
+  uint32_t _pad;
+};
+
+// persistent across passes: once set, every later pass is a no-op until the host clears it
+struct CtxStatus {
+  uint32_t poison;
+};
+
+struct PassParams {
+  const DrawDesc* draws;
+  const uint32_t* vbase;  // [n_draws+1] prefix of n_verts
+  const uint32_t* pbase;  // [n_draws+1] prefix of n_prims
+  const TargetDesc* targets;
+  uint32_t n_draws, n_targets, NV, NP, n_tiles;
+  float* cv;              // clip verts [NV][CVS]
+  uint32_t* spans;        // [cap_spans][SW]
+  uint32_t* halves;       // [cap_halves][HW]
+  uint32_t* pieces;       // [cap_pieces][PW]
+  uint32_t* order;        // [cap_pieces] sorted local piece index per tile bin
+  uint32_t cap_spans, cap_halves, cap_pieces;
+  uint32_t* tile_cnt;     // [n_tiles]
+  uint32_t* tile_off;     // [n_tiles]
+  uint32_t* tile_fill;    // [n_tiles]
+  uint32_t* worklist;     // [n_tiles] non-empty tiles
+  uint32_t* worklist_big; // [n_tiles]
+  uint32_t* cursors;      // [0] piece cursor, [1] raster work cursor, [2] sort cursor, [3] big sort cursor
+  DrawStats* dstats;      // [n_draws]
+  PassStatus* status;
+  CtxStatus* cstatus;
+};
+
+// record strides in 32-bit words, as a function of the compile-time lane count LT
+template <int LT> struct Rec {
+  static constexpr int CVS = (5 + LT + 3) & ~3;  // clip vert: pos4, oc, attr[LT]
+  static constexpr int SW = (5 + LT + 3) & ~3;   // span: Y, X0, n, half, z, attr[LT]
+  static constexpr int HW = (3 + LT + 3) & ~3;   // half: key, draw, dz, dattr[LT]
+  static constexpr int PW = (4 + LT + 3) & ~3;   // piece: key, yxn, half, z, attr[LT]
+};
+
+// ---- Rust `as` casts (saturating, NaN -> 0). PTX cvt.rzi.{u32,s32}.f32 clamps and maps NaN to 0.
+__device__ __forceinline__ uint32_t sat_u32(float f) { return __float2uint_rz(f); }
+__device__ __forceinline__ int32_t sat_i32(float f) { return __float2int_rz(f); }
+__device__ __forceinline__ uint32_t sat_u8(float f) { return min(__float2uint_rz(f), 255u); }
+
+// math/vec.rs:231-238: left fold from 0.0
+__device__ __forceinline__ float dot4(float a0, float a1, float a2, float a3, float b0, float b1, float b2, float b3) {
+  float acc = 0.0f;
+  acc = acc + a0 * b0;
+  acc = acc + a1 * b1;
+  acc = acc + a2 * b2;
+  acc = acc + a3 * b3;
+  return acc;
+}
+__device__ __forceinline__ float dot4p(const float* __restrict__ m, float b0, float b1, float b2, float b3) {
+  return dot4(m[0], m[1], m[2], m[3], b0, b1, b2, b3);
+}
+
+// render/clip.rs:215-222,240-242. Plane vectors are (n, -1); dot keeps the zero terms, as the reference does.
+__device__ __forceinline__ float plane_dist(int p, float x, float y, float z, float w) {
+  switch (p) {
+    case 0: return dot4(0.0f, 0.0f, -1.0f, -1.0f, x, y, z, w);
+    case 1: return dot4(0.0f, 0.0f, 1.0f, -1.0f, x, y, z, w);
+    case 2: return dot4(-1.0f, 0.0f, 0.0f, -1.0f, x, y, z, w);
+    case 3: return dot4(1.0f, 0.0f, 0.0f, -1.0f, x, y, z, w);
+    case 4: return dot4(0.0f, -1.0f, 0.0f, -1.0f, x, y, z, w);
+    default: return dot4(0.0f, 1.0f, 0.0f, -1.0f, x, y, z, w);
+  }
+}
+__device__ __forceinline__ uint32_t outcode(float x, float y, float z, float w) {
+  uint32_t oc = 0;
+#pragma unroll
+  for (int p = 0; p < 6; p++) oc |= (plane_dist(p, x, y, z, w) > 0.0f) ? (1u << p) : 0u;
+  return oc;
+}
+
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return a + (b - a) * t; }  // math.rs:196-198
+__device__ __forceinline__ float round_up_to_half(float x) { return floorf(x + 0.5f) + 0.5f; }  // raster.rs:304-307
+
+// f32::total_cmp key (stable sort of the three vertices by y, raster.rs:191)
+__device__ __forceinline__ int32_t total_key(float f) {
+  int32_t b = __float_as_int(f);
+  return b ^ (int32_t)(((uint32_t)(b >> 31)) >> 1);
+}
+
+// util/pixfmt.rs:45-142: Color4 -> uint32 container
+__device__ __forceinline__ uint32_t pack_pixel(uint32_t fmt, uint32_t r, uint32_t g, uint32_t b, uint32_t a) {
+  switch (fmt) {
+    case RF_FMT_RGBA8888: return r | g << 8 | b << 16 | a << 24;
+    case RF_FMT_XRGB8888: return r << 16 | g << 8 | b;
+    case RF_FMT_ARGB8888: return a | r << 8 | g << 16 | b << 24;
+    case RF_FMT_BGRA8888: return b | g << 8 | r << 16 | a << 24;
+    case RF_FMT_RGB888: return r | g << 8 | b << 16;
+    case RF_FMT_RGB565: return ((r >> 3) & 0x1Fu) << 11 | ((g >> 2) & 0x3Fu) << 5 | ((b >> 3) & 0x1Fu);
+    default: return (r >> 4) << 12 | (g >> 4) << 8 | (b >> 4) << 4 | (a >> 4);  // RGBA4444
+  }
+}
+
+// binary search: largest d with base[d] <= i   (base has n+1 entries, base[0] = 0)
+__device__ __forceinline__ uint32_t find_draw(const uint32_t* __restrict__ base, uint32_t n, uint32_t i) {
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(base + mid) <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() { return (1u << lane_id()) - 1u; }
+
+// inclusive warp scan
+__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+    if ((int)lane_id() >= o) v += t;
+  }
+  return v;
+}

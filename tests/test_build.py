@@ -1,0 +1,56 @@
+"""CPU-only checks of the native build: the library exists, exports the whole ABI, and the
+coverage/depth kernels contain no fused multiply-adds (SURVEY §7 hard part 3)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from retrofire_b200 import _ffi
+from retrofire_b200 import build as rfbuild
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    rfbuild.build()
+    lib = _ffi.load()
+    header = open(os.path.join(ROOT, "include", "retrofire_b200.h")).read()
+    declared = set(re.findall(r"^(?:rf_status|void\*?|const char\*|uint32_t)\s+(rf_[a-z_0-9]+)\s*\(", header, re.M))
+    assert declared == set(_ffi.SYMBOLS), declared ^ set(_ffi.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.rf_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import retrofire_b200 as rf
+    with pytest.raises(rf.RetrofireError):
+        rf.Device(0)
+
+
+def test_ptx_has_no_fma_on_coverage_and_depth_chains(tmp_path):
+    """User arithmetic must not be contracted: in PTX, fma.rn.f32 may appear only inside the powf
+    expansion (19 per call) of the sRGB shaders; k_prim / k_piece_fill / k_span_count have none."""
+    ptx = open(rfbuild.ptx(str(tmp_path / "rf.ptx"))).read()
+    counts, cur = {}, None
+    for line in ptx.splitlines():
+        m = re.search(r"\.entry\s+(\w+)", line)
+        if m:
+            cur = m.group(1)
+        if "fma.rn.f32" in line and cur:
+            counts[cur] = counts.get(cur, 0) + 1
+    for name, n in counts.items():
+        assert "k_prim" not in name and "k_piece_fill" not in name and "k_span_count" not in name, (name, n)
+        if "k_raster" in name:
+            assert n == 3 * 19, (name, n)   # powf(c, 1/2.2) x3 in FS_COLOR3F_SRGB only
+    assert "--use_fast_math" not in " ".join(rfbuild.NVCC_FLAGS)
+    assert "-fmad=false" in rfbuild.NVCC_FLAGS
+
+
+def test_sass_is_sm_100a():
+    out = subprocess.run(["cuobjdump", "-lelf", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out

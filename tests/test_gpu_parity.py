@@ -1,0 +1,165 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on identical
+inputs. Bit-exact depth (so coverage and depth-test winners are exact), bit-exact colour except
+where a shader uses powf (±1 LSB), equal Stats counters."""
+import os
+
+import numpy as np
+import pytest
+
+import retrofire_b200 as rf
+from retrofire_b200 import scenes
+from tests.parity import assert_parity, run_gpu, run_oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def check(device, oracle, sc, **kw):
+    assert_parity(run_gpu(device, sc), run_oracle(oracle, sc), name=sc.name, **kw)
+
+
+def test_hello_tri(device, oracle):
+    """BASELINE config 1 (core/examples/hello_tri.rs), non-fp shaders: bit-exact."""
+    sc = scenes.hello_tri(fp=False)
+    got = run_gpu(device, sc)
+    assert tuple(got[0][240, 320]) == (114, 102, 128, 255)
+    assert_parity(got, run_oracle(oracle, sc), name=sc.name)
+
+
+def test_hello_tri_fp_and_golden(device, oracle):
+    """fp shaders use powf: coverage exact, colour within 1 LSB of oracle and of core/triangle.ppm."""
+    sc = scenes.hello_tri(fp=True)
+    got = run_gpu(device, sc)
+    assert_parity(got, run_oracle(oracle, sc), name=sc.name, color_tol=1)
+    gold = np.load(os.path.join(GOLD, "triangle_fp.npz"))["rgb"]
+    assert np.array_equal(got[0][:, :, 3] != 0, gold.any(axis=2))
+    assert np.abs(got[0][:, :, :3].astype(int) - gold.astype(int)).max() <= 1
+    assert np.abs(got[0][240, 320].astype(int) - np.array([151, 128, 187, 255])).max() <= 1
+
+
+def test_textured_quad_golden(device, oracle):
+    """core/tests/rendering.rs: whole frame equals textured_quad.ppm."""
+    sc = scenes.textured_quad()
+    got = run_gpu(device, sc)
+    gold = np.load(os.path.join(GOLD, "textured_quad.npz"))["rgb"]
+    assert np.array_equal(got[0], gold)
+    assert_parity(got, run_oracle(oracle, sc), name=sc.name)
+
+
+@pytest.mark.parametrize("kind", ["color3", "uv", "disc", "lit"])
+@pytest.mark.parametrize("big", [False, True])
+def test_random_soup(device, oracle, kind, big):
+    """Random triangles crossing all six frustum planes; small and screen-filling; every lane layout."""
+    for seed in (1, 2):
+        sc = scenes.random_soup(3000 if not big else 400, 640, 360, seed=seed, lanes_kind=kind, big=big)
+        check(device, oracle, sc)
+
+
+def test_odd_sized_target(device, oracle):
+    """Width/height not multiples of the tile or of 4 (scalar tile I/O path)."""
+    sc = scenes.random_soup(500, 333, 211, seed=5, lanes_kind="color3", big=True)
+    check(device, oracle, sc)
+
+
+@pytest.mark.parametrize("ctxkw", [
+    dict(face_cull=None), dict(face_cull=rf.FaceCull.Front), dict(depth_test=None),
+    dict(depth_test=rf.Ordering.Greater), dict(depth_test=rf.Ordering.Equal),
+    dict(color_write=False), dict(depth_write=False), dict(depth_test=None, depth_write=False),
+])
+def test_context_flags(device, oracle, ctxkw):
+    """Context fields consumed by the path (render/ctx.rs:11-101); no reference test pins these."""
+    ctx = rf.Context(**ctxkw)
+    if ctxkw.get("depth_test") in (rf.Ordering.Greater, rf.Ordering.Equal):
+        ctx.depth_clear = 0.001  # 1/depth_clear = 1000: 'Greater' passes when curr > new
+    sc = scenes.random_soup(1500, 400, 300, seed=11, lanes_kind="color3", big=True, ctx=ctx)
+    check(device, oracle, sc)
+
+
+def test_multi_draw_frame_and_per_draw_stats(device, oracle):
+    """Several render() calls into one target (front/src/minifb.rs frame loop), mixed shaders."""
+    a = scenes.random_soup(800, 512, 384, seed=21, lanes_kind="lit", big=True)
+    b = scenes.random_soup(800, 512, 384, seed=22, lanes_kind="color3", big=False)
+    c = scenes.random_soup(800, 512, 384, seed=23, lanes_kind="disc", big=True)
+    a.draws += b.draws + c.draws
+    a.name = "multi"
+    want = run_oracle(oracle, a)
+    assert_parity(run_gpu(device, a), want, name="multi-queued")
+    assert_parity(run_gpu(device, a, per_draw_sync=True), want, name="multi-sync")
+
+
+@pytest.mark.parametrize("fmt", [rf.FMT_RGBA8888, rf.FMT_XRGB8888, rf.FMT_ARGB8888, rf.FMT_BGRA8888, rf.FMT_RGB888,
+                                 rf.FMT_RGB565, rf.FMT_RGBA4444])
+def test_pixel_formats(device, oracle, fmt):
+    """util/pixfmt.rs conversions at write time and in download."""
+    sc = scenes.random_soup(300, 256, 128, seed=3, lanes_kind="color3", big=True)
+    sc.fmt = fmt
+    check(device, oracle, sc)
+
+
+def test_bunny_native(device, oracle):
+    """BASELINE config 2 at the reference asset's size (4,968 tris), 1920x1080."""
+    check(device, oracle, scenes.bunny(subdiv=0))
+
+
+def test_bunny_x16(device, oracle):
+    """BASELINE config 2: ~79k triangles."""
+    check(device, oracle, scenes.bunny(subdiv=2))
+
+
+def test_sprites(device, oracle):
+    """BASELINE config 4 (reduced count for CPU time): discard + heavy overdraw."""
+    check(device, oracle, scenes.sprites(count=3000))
+
+
+def test_crates_169_reduced(device, oracle):
+    """BASELINE config 3, reference layout, 1920x1080: 170 draws, long perspective-correct spans."""
+    check(device, oracle, scenes.crates("169", w=1920, h=1080))
+
+
+def test_empty_and_degenerate(device, oracle):
+    """Empty draws, zero-area and all-outside triangles."""
+    sc = scenes.hello_tri()
+    d = sc.draws[0]
+    empty = rf.DrawCall.make(np.zeros((0, 3), np.uint32), d.verts, d.shader, d.uniform[:16].reshape(4, 4), d.viewport)
+    degenerate = rf.DrawCall.make([[0, 0, 1], [0, 1, 1], [2, 2, 2]], d.verts, d.shader, d.uniform[:16].reshape(4, 4), d.viewport)
+    sc.draws = [empty, degenerate, d]
+    check(device, oracle, sc)
+
+
+def test_index_out_of_bounds_is_an_error(device):
+    """render/prim.rs:17-19 panics; the ABI returns RF_E_INDEX_OOB and leaves the target untouched."""
+    sc = scenes.hello_tri()
+    d = sc.draws[0]
+    bad = rf.DrawCall.make([[0, 1, 7]], d.verts, d.shader, d.uniform[:16].reshape(4, 4), d.viewport)
+    fb = device.framebuf(sc.w, sc.h, sc.fmt, False)
+    with pytest.raises(rf.RetrofireError) as e:
+        device.render(bad, fb, want_stats=True)
+    assert e.value.status == rf.RF_E_INDEX_OOB
+    assert not fb.download_color().any()
+
+
+def test_target_out_of_bounds_is_an_error(device):
+    """A viewport larger than the target makes spans index outside it (render/target.rs:148,173 panics)."""
+    sc = scenes.hello_tri()
+    d = sc.draws[0]
+    fb = device.framebuf(320, 240, sc.fmt, False)
+    with pytest.raises(rf.RetrofireError) as e:
+        device.render(d, fb, want_stats=True)
+    assert e.value.status == rf.RF_E_TARGET_OOB
+
+
+def test_arena_growth_replays_the_pass(device, oracle):
+    """A pass that overflows the span/piece arenas is replayed transparently after growth."""
+    sc = scenes.random_soup(6000, 1920, 1080, seed=31, lanes_kind="lit", big=True)
+    check(device, oracle, sc)
+
+
+def test_row_band_sharding_matches_oracle_band(device, oracle):
+    """Sort-first sharding: a ctx restricted to a row band renders exactly those rows."""
+    sc = scenes.random_soup(1000, 512, 384, seed=41, lanes_kind="color3", big=True)
+    device.set_row_band(100, 260)
+    try:
+        got = run_gpu(device, sc)
+    finally:
+        device.set_row_band(0, 0xFFFFFFFF)
+    assert_parity(got, run_oracle(oracle, sc, band=(100, 260)), name="band")
