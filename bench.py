@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the render() hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload bunny|crates|sprites]
+
+Workload (BASELINE.json configs[1]): the Stanford bunny, 2x midpoint-subdivided to 79,488
+triangles, Gouraud-shaded (VS_SOLIDS/FS_COLOR3F) with depth test at 1920x1080, Xrgb8888 + f32
+depth. One "step" is one frame batch: F frames (theta = 2*pi*f/F), each cleared and drawn into
+its own device-resident target — the frame-sharded batch of SURVEY §8e. With N GPUs every rank
+renders its own F frames (weak scaling, no data-path collective).
+
+`value`   : Mfragments/s (Stats.frags.i per second) with geometry resident in HBM (rf_mesh).
+`e2e`     : same metric through the reference-facing call with HOST vertex/index buffers every
+            frame (H2D inside the timed region) and the colour buffer of every frame downloaded.
+`roofline`: k_raster, algorithmic bytes 4*frags.i + 8*frags.o per launch over its
+            CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth.
+`cpu_baseline`: the CPU oracle (1 thread, like the single-threaded reference) on a bounded
+            sample of the same frames.
+`--impl reference`: the oracle port on all host cores (frames are independent), same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import retrofire_b200 as rf  # noqa: E402
+from retrofire_b200 import scenes  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="bunny", choices=["bunny", "crates", "sprites"])
+    ap.add_argument("--frames", type=int, default=32, help="frames per step (frame batch)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ---- workload ------------------------------------------------------------------------------------
+def make_workload(name: str, frames: int):
+    """Returns (scene template, list of per-frame DrawCall lists)."""
+    if name == "bunny":
+        base = scenes.bunny(subdiv=2)
+        per_frame = []
+        for f in range(frames):
+            th = 2.0 * math.pi * f / frames + 1.0
+            sc = scenes.bunny(subdiv=2, theta=th)
+            per_frame.append(sc.draws)
+        desc = {"workload": "bunny_x16 79,488 tris Gouraud+depth 1920x1080 Xrgb8888, frame batch", "frames_per_step": frames,
+                "resolution": [base.w, base.h]}
+        return base, per_frame, desc
+    if name == "crates":
+        base = scenes.crates("1089")
+        per_frame = [base.draws for _ in range(frames)]
+        desc = {"workload": "crates 1,089 textured cubes + floor 3840x2160 Rgba8888, one draw per cube", "frames_per_step": frames,
+                "resolution": [base.w, base.h]}
+        return base, per_frame, desc
+    base = scenes.sprites(10000)
+    per_frame = [scenes.sprites(10000, theta=1.0 + 0.1 * f).draws for f in range(frames)]
+    desc = {"workload": "sprites 10k discs 1920x1080", "frames_per_step": frames, "resolution": [base.w, base.h]}
+    return base, per_frame, desc
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- reference arm / cpu baseline -------------------------------------------------------------------
+def oracle_frames(base, per_frame, idx, threads: int):
+    """Render frames `idx` with the CPU oracle; returns (seconds, frags_i, prims_i, frames)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import rfo
+    rfo.load()
+
+    def one(f):
+        tgt = rfo.HostTarget(base.w, base.h, base.fmt, base.has_depth)
+        tgt.clear(base.ctx.color_clear, base.ctx.depth_clear)
+        fi = pi = 0
+        for d in per_frame[f]:
+            s = rfo.render(d, tgt)
+            fi += s.frags.i
+            pi += s.prims.i
+        return fi, pi
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        res = [one(f) for f in idx]
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            res = list(ex.map(one, idx))
+    dt = time.perf_counter() - t0
+    return dt, sum(r[0] for r in res), sum(r[1] for r in res), len(idx)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, per_frame, desc = make_workload(args.workload, args.frames)
+    cores = os.cpu_count() or 1
+    # bounded sample per step: at most `cores` frames x 1 so a step stays around a second
+    sample = list(range(min(args.frames, max(cores, 8))))
+    for _ in range(max(args.warmup, 1)):
+        oracle_frames(base, per_frame, sample[: max(1, len(sample) // 4)], cores)
+    tot_t = tot_f = tot_p = tot_n = 0
+    for _ in range(args.steps):
+        dt, fi, pi, n = oracle_frames(base, per_frame, sample, cores)
+        tot_t += dt; tot_f += fi; tot_p += pi; tot_n += n
+    val = tot_f / tot_t / 1e6
+    line = {
+        "impl": "reference", "metric": "Mfragments/s", "value": val, "unit": "Mfragments/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": desc,
+        "frames_per_s": tot_n / tot_t, "Mtriangles_per_s": tot_p / tot_t / 1e6,
+        "cpu_baseline": {"value": val, "unit": "Mfragments/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(sample)} of {args.frames} frames per step, frames spread over {cores} host threads (oracle port; the Rust reference cannot be built here)"},
+        "e2e": {"value": val, "unit": "Mfragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- B200 arm ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream(device=local)
+
+    base, per_frame, desc = make_workload(args.workload, args.frames)
+    F = args.frames
+    dev = rf.Device(local, stream=stream.cuda_stream)
+    targets = [dev.framebuf(base.w, base.h, base.fmt, base.has_depth) for _ in range(F)]
+    # resident geometry: one rf_mesh per distinct (prims, verts) pair
+    mesh_cache = {}
+
+    def resident(d: rf.DrawCall) -> rf.DrawCall:
+        key = (d.prims.ctypes.data, d.verts.ctypes.data)
+        if key not in mesh_cache:
+            mesh_cache[key] = dev.mesh(d.prims, d.verts)
+        import dataclasses
+        return dataclasses.replace(d, mesh=mesh_cache[key])
+
+    res_frames = [[resident(d) for d in draws] for draws in per_frame]
+    single = all(len(dr) == 1 for dr in res_frames)
+    uniforms = np.stack([dr[0].uniform for dr in res_frames]) if single else None
+
+    def step_resident():
+        for t in targets:
+            t.clear(base.ctx)
+        if single:
+            dev.render_frames(res_frames[0][0], targets, uniforms)
+        else:
+            for t, draws in zip(targets, res_frames):
+                for d in draws:
+                    dev.render(d, t)
+        dev.flush()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also grows the arenas so the timed region never replays a pass)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    dev.sync()
+    dev.stats(reset=True)
+    dev.profile(True)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record(stream)
+    dev.sync()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    sampler.stop_flag.set()
+    st = dev.stats(reset=True)
+    ktimes = dev.kernel_times()
+    dev.profile(False)
+    _, launches_per_pass = dev.last_pass()
+
+    # ---- end to end: host geometry in, colour buffers out, every frame
+    Fe = min(F, 8)
+    host_color = [np.empty((base.h, base.w), dtype=np.uint32) if base.fmt == rf.FMT_XRGB8888 else None for _ in range(Fe)]
+
+    def step_e2e():
+        for f in range(Fe):
+            targets[f].clear(base.ctx)
+            for d in per_frame[f]:
+                dev.render(d, targets[f])          # host pointers: copied H2D inside the call/flush
+        dev.flush()
+        outs = []
+        for f in range(Fe):
+            outs.append(targets[f].download_color())  # D2H of the step's result
+        return outs
+
+    for _ in range(2):
+        step_e2e()
+    dev.stats(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    e_steps = max(2, min(args.steps, 5))
+    for _ in range(e_steps):
+        step_e2e()
+    barrier()
+    e_dt = time.perf_counter() - t0
+    e_st = dev.stats(reset=True)
+    h2d = sum(d.verts.nbytes + d.prims.nbytes for f in range(Fe) for d in per_frame[f])
+    d2h = Fe * base.w * base.h * 4
+
+    # ---- reduce over ranks
+    t_ms, e_s = ms, e_dt
+    frags_i, frags_o, prims_i = st.frags.i, st.frags.o, st.prims.i
+    e_frags = e_st.frags.i
+    if world > 1:
+        tt = torch.tensor([ms, e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms, e_s = float(tt[0]), float(tt[1])
+        cc = torch.tensor([frags_i, frags_o, prims_i, e_frags], device="cuda", dtype=torch.int64)
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        frags_i, frags_o, prims_i, e_frags = (int(x) for x in cc)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        r_ns, r_n = ktimes["k_raster"]
+        # rank-0 kernel: algorithmic bytes of ITS launches
+        alg_bytes_launch = (4 * st.frags.i + 8 * st.frags.o) / max(r_n, 1)
+        r_avg_s = r_ns * 1e-9 / max(r_n, 1)
+        achieved = alg_bytes_launch / r_avg_s / 1e9 if r_avg_s > 0 else 0.0
+        kshare = {k: round(v[0] / max(sum(x[0] for x in ktimes.values()), 1), 4) for k, v in ktimes.items()}
+        # whole-frame algorithmic bytes (SURVEY §8d B_alg) over the whole step time, for context
+        geom = base.geometry_bytes() if single else sum(d.verts.shape[0] * 4 * (3 + d.shader.lanes) + d.prims.shape[0] * 12 for d in per_frame[0])
+        b_alg_step = F * (geom + 8 * base.w * base.h) + (4 * st.frags.i + 8 * st.frags.o) / args.steps
+        line = {
+            "metric": "Mfragments/s", "value": frags_i / (t_ms * 1e-3) / 1e6, "unit": "Mfragments/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(desc, l2="inputs larger than L2: %d targets x %.1f MB colour+depth per step" % (F, base.w * base.h * 8 / 1e6),
+                           parallelism=f"frame-sharded x{world}"),
+            "frames_per_s": world * F * args.steps / (t_ms * 1e-3), "Mtriangles_per_s": prims_i / (t_ms * 1e-3) / 1e6,
+            "frags_i_per_step": frags_i // args.steps, "frags_o_per_step": frags_o // args.steps,
+            "e2e": {"value": e_frags / e_s / 1e6, "unit": "Mfragments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "frames_per_step": Fe, "frames_per_s": world * Fe * e_steps / e_s},
+            "gpu_launches": int(args.steps * (launches_per_pass)),
+            "roofline": {"bound": "hbm", "kernel": "k_raster", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms_avg": r_avg_s * 1e3,
+                         "alg_bytes_per_launch": alg_bytes_launch, "kernel_time_share": kshare,
+                         "pass_alg_GBps": b_alg_step / (t_ms * 1e-3 / args.steps) / 1e9},
+            "clocks": sampler.summary(),
+        }
+        if world == 1:
+            # CPU baseline: oracle, 1 thread (the reference is single-threaded), bounded sample
+            n = 0
+            t_used = fi_tot = 0.0
+            while n < F and t_used < args.cpu_seconds:
+                dt, fi, _, _ = oracle_frames(base, per_frame, [n], 1)
+                t_used += dt; fi_tot += fi; n += 1
+            line["cpu_baseline"] = {"value": fi_tot / t_used / 1e6, "unit": "Mfragments/s", "cores": 1, "kind": "port",
+                                    "sample": f"first {n} of {F} frames of the step, CPU oracle single-threaded, {t_used:.1f} s",
+                                    "frames_per_s": n / t_used}
+        print(json.dumps(line), flush=True)
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

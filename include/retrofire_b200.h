@@ -194,6 +194,15 @@ rf_status rf_ctx_stats(rf_ctx* ctx, rf_stats* out, int reset);
 /* Device time in ns of the most recent executed pass, and the number of kernels it launched. */
 rf_status rf_ctx_last_pass(rf_ctx* ctx, uint64_t* time_ns, uint32_t* n_launches);
 
+
+/* ---- measurement (Stats::start/finish analogue, render/stats.rs:57-78, per kernel) ----------- */
+#define RF_N_KERNELS 8 /* kernels launched by one pass, in order; see rf_kernel_name */
+/* enable=1: record CUDA events between the pass kernels (on the ctx stream). Resets the sums. */
+rf_status rf_ctx_profile(rf_ctx* ctx, int enable);
+/* Device time (ns) and launch count per kernel accumulated since the last call; resets them. */
+rf_status rf_ctx_kernel_times(rf_ctx* ctx, uint64_t* ns /*[RF_N_KERNELS]*/, uint64_t* launches /*[RF_N_KERNELS]*/);
+const char* rf_kernel_name(uint32_t i);
+
 #ifdef __cplusplus
 }
 #endif

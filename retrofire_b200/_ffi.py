@@ -99,7 +99,11 @@ SYMBOLS = {
     "rf_sync": (C.c_int, [_P]),
     "rf_ctx_stats": (C.c_int, [_P, C.POINTER(RfStats), C.c_int]),
     "rf_ctx_last_pass": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "rf_ctx_profile": (C.c_int, [_P, C.c_int]),
+    "rf_ctx_kernel_times": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "rf_kernel_name": (C.c_char_p, [C.c_uint32]),
 }
+RF_N_KERNELS = 8
 
 _lib = None
 

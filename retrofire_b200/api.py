@@ -272,6 +272,16 @@ class Device:
         self._check(self.lib.rf_ctx_last_pass(self.h, C.byref(t), C.byref(n)))
         return t.value, n.value
 
+    def profile(self, enable: bool = True):
+        self._check(self.lib.rf_ctx_profile(self.h, int(enable)))
+
+    def kernel_times(self) -> dict:
+        """{kernel: (total_ns, launches)} since the last call (profiling mode)."""
+        ns = (C.c_uint64 * _ffi.RF_N_KERNELS)()
+        ln = (C.c_uint64 * _ffi.RF_N_KERNELS)()
+        self._check(self.lib.rf_ctx_kernel_times(self.h, ns, ln))
+        return {self.lib.rf_kernel_name(i).decode(): (int(ns[i]), int(ln[i])) for i in range(_ffi.RF_N_KERNELS)}
+
     def framebuf(self, w: int, h: int, fmt: int = _ffi.FMT_RGBA8888, depth: bool = True) -> "Framebuf":
         return Framebuf(self, w, h, fmt, depth)
 

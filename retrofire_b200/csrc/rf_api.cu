@@ -86,6 +86,8 @@ struct PassSlot {
   PinnedBuf h_dstats;
   HostStatus* h_status = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  cudaEvent_t ev_k[RF_N_KERNELS + 1] = {};  // boundaries between the pass kernels (profiling mode)
+  bool profiled = false;
   uint32_t NV = 0, NP = 0, n_tiles = 0, lt = 0;
   uint32_t n_launches = 0;
 };
@@ -134,6 +136,9 @@ struct rf_ctx {
   rf_stats last_draw{};        // stats of the last draw of the last validated pass
   uint64_t last_pass_ns = 0;
   uint32_t last_pass_launches = 0;
+  bool profile = false;
+  uint64_t kernel_ns[RF_N_KERNELS] = {};      // accumulated since the last query
+  uint64_t kernel_launches[RF_N_KERNELS] = {};
 };
 
 namespace {
@@ -214,15 +219,28 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   const int sm = c->sm_count;
   cudaStream_t st = c->stream;
   auto blocks = [&](size_t n, int bs, int per_sm) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + bs - 1) / bs, (size_t)sm * per_sm)); };
+  const bool prof = c->profile;
+  s.profiled = prof;
+  int ek = 0;
+  auto mark = [&]() { if (prof) cudaEventRecord(s.ev_k[ek++], st); };
+  mark();
   k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
+  mark();
   k_prim<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+  mark();
   k_span_count<LT><<<sm * 8, 256, 0, st>>>(P);
+  mark();
   k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, st>>>(P);
+  mark();
   k_piece_fill<LT><<<sm * 8, 256, 0, st>>>(P);
+  mark();
   k_bin_sort<LT, RF_SORT_SMALL><<<sm * 8, 256, RF_SORT_SMALL * 8, st>>>(P, 0);
+  mark();
   k_bin_sort<LT, RF_SORT_BIG><<<sm, 256, RF_SORT_BIG * 8, st>>>(P, 1);
+  mark();
   k_raster<LT><<<sm * 6, RF_RASTER_WARPS * 32, 0, st>>>(P);
-  s.n_launches += 8;
+  mark();
+  s.n_launches += RF_N_KERNELS;
 }
 
 rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, size_t want_spans, size_t want_halves, size_t want_pieces) {
@@ -406,6 +424,12 @@ rf_status validate_all(rf_ctx* c) {
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s.ev_start, s.ev_stop);
+    if (s.profiled && !s.draws.empty()) {
+      for (int k = 0; k < RF_N_KERNELS; k++) {
+        float kms = 0.f;
+        if (cudaEventElapsedTime(&kms, s.ev_k[k], s.ev_k[k + 1]) == cudaSuccess) { c->kernel_ns[k] += (uint64_t)(kms * 1e6); c->kernel_launches[k] += 1; }
+      }
+    }
     const uint64_t ns = (uint64_t)(ms * 1e6);
     c->last_pass_ns = ns;
     c->last_pass_launches = s.n_launches;
@@ -559,6 +583,7 @@ rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
   for (int k = 0; k < kSlots && ok; k++) {
     PassSlot& s = c->slots[k];
     ok = ok && cudaEventCreate(&s.ev_start) == cudaSuccess && cudaEventCreate(&s.ev_stop) == cudaSuccess;
+    for (int e = 0; e <= RF_N_KERNELS && ok; e++) ok = cudaEventCreate(&s.ev_k[e]) == cudaSuccess;
     ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_status), sizeof(HostStatus), cudaHostAllocDefault) == cudaSuccess;
   }
   ok = ok && cudaFuncSetAttribute(k_bin_sort<3, RF_SORT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
@@ -580,6 +605,7 @@ void rf_ctx_destroy(rf_ctx* c) {
     if (s.h_status) cudaFreeHost(s.h_status);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
+    for (int e = 0; e <= RF_N_KERNELS; e++) if (s.ev_k[e]) cudaEventDestroy(s.ev_k[e]);
   }
   c->cv.release(); c->spans.release(); c->halves.release(); c->pieces.release(); c->order.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
@@ -787,6 +813,30 @@ rf_status rf_ctx_last_pass(rf_ctx* c, uint64_t* time_ns, uint32_t* n_launches) {
   if (time_ns) *time_ns = c->last_pass_ns;
   if (n_launches) *n_launches = c->last_pass_launches;
   return st;
+}
+
+rf_status rf_ctx_profile(rf_ctx* c, int enable) {
+  if (!c) return RF_E_INVALID;
+  rf_status st = sync_impl(c);
+  c->profile = enable != 0;
+  std::memset(c->kernel_ns, 0, sizeof c->kernel_ns);
+  std::memset(c->kernel_launches, 0, sizeof c->kernel_launches);
+  return st;
+}
+
+rf_status rf_ctx_kernel_times(rf_ctx* c, uint64_t* ns, uint64_t* launches) {
+  if (!c || !ns || !launches) return fail(c, RF_E_INVALID, "null argument");
+  rf_status st = sync_impl(c);
+  std::memcpy(ns, c->kernel_ns, sizeof c->kernel_ns);
+  std::memcpy(launches, c->kernel_launches, sizeof c->kernel_launches);
+  std::memset(c->kernel_ns, 0, sizeof c->kernel_ns);
+  std::memset(c->kernel_launches, 0, sizeof c->kernel_launches);
+  return st;
+}
+
+const char* rf_kernel_name(uint32_t i) {
+  static const char* names[RF_N_KERNELS] = {"k_vertex", "k_prim", "k_span_count", "k_bin_alloc", "k_piece_fill", "k_bin_sort", "k_bin_sort_big", "k_raster"};
+  return i < RF_N_KERNELS ? names[i] : "";
 }
 
 }  // extern "C"
