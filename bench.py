@@ -41,12 +41,13 @@ from retrofire_b200 import scenes  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="bunny", choices=["bunny", "crates", "sprites"])
     ap.add_argument("--frames", type=int, default=32, help="frames per step (frame batch)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and cpu_baseline legs (for ncu runs)")
     return ap.parse_args()
 
 
@@ -93,7 +94,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([s.strip() for s in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.1)
 
     def summary(self):
         if not self.rows:
@@ -216,9 +217,10 @@ def run_b200(args):
     # ---- warm-up (also grows the arenas so the timed region never replays a pass)
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    dev.sync()
+        dev.sync()
     dev.stats(reset=True)
     dev.profile(True)
+    torch.cuda.cudart().cudaProfilerStart()  # ncu --profile-from-start off: capture only the timed region
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -230,6 +232,7 @@ def run_b200(args):
     ev1.record(stream)
     dev.sync()
     barrier()
+    torch.cuda.cudart().cudaProfilerStop()
     ms = ev0.elapsed_time(ev1)
     sampler.stop_flag.set()
     st = dev.stats(reset=True)
@@ -252,16 +255,16 @@ def run_b200(args):
             outs.append(targets[f].download_color())  # D2H of the step's result
         return outs
 
-    for _ in range(2):
+    e_steps = 0 if args.kernel_only else max(2, min(args.steps, 5))
+    for _ in range(2 if e_steps else 0):
         step_e2e()
     dev.stats(reset=True)
     barrier()
     t0 = time.perf_counter()
-    e_steps = max(2, min(args.steps, 5))
     for _ in range(e_steps):
         step_e2e()
     barrier()
-    e_dt = time.perf_counter() - t0
+    e_dt = max(time.perf_counter() - t0, 1e-9)
     e_st = dev.stats(reset=True)
     h2d = sum(d.verts.nbytes + d.prims.nbytes for f in range(Fe) for d in per_frame[f])
     d2h = Fe * base.w * base.h * 4
@@ -306,15 +309,15 @@ def run_b200(args):
                          "pass_alg_GBps": b_alg_step / (t_ms * 1e-3 / args.steps) / 1e9},
             "clocks": sampler.summary(),
         }
-        if world == 1:
+        if world == 1 and not args.kernel_only:
             # CPU baseline: oracle, 1 thread (the reference is single-threaded), bounded sample
             n = 0
             t_used = fi_tot = 0.0
-            while n < F and t_used < args.cpu_seconds:
-                dt, fi, _, _ = oracle_frames(base, per_frame, [n], 1)
+            while t_used < args.cpu_seconds and n < 100000:
+                dt, fi, _, _ = oracle_frames(base, per_frame, [n % F], 1)
                 t_used += dt; fi_tot += fi; n += 1
             line["cpu_baseline"] = {"value": fi_tot / t_used / 1e6, "unit": "Mfragments/s", "cores": 1, "kind": "port",
-                                    "sample": f"first {n} of {F} frames of the step, CPU oracle single-threaded, {t_used:.1f} s",
+                                    "sample": f"{n} frames (cycling the step's {F}), CPU oracle single-threaded, {t_used:.1f} s",
                                     "frames_per_s": n / t_used}
         print(json.dumps(line), flush=True)
     dev.close()
