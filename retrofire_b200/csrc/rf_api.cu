@@ -2,7 +2,7 @@
 //
 // A "pass" is every draw queued between two flush points, executed in submission order by
 // one chain of kernels:
-//   k_vertex -> k_prim -> k_span_count -> k_bin_alloc -> k_piece_fill -> k_bin_sort -> k_raster
+//   [k_clear_multi] -> k_vertex -> k_prim -> k_bin_alloc -> k_bin_scatter -> k_ckpt -> k_bin_sort_* -> k_raster
 // Passes are launched asynchronously on the ctx stream and validated lazily (capacity overflow
 // or device-detected errors) at the next synchronisation point; an overflowing pass poisons
 // the ctx on the device so that later passes become no-ops until the host has grown the
@@ -126,8 +126,10 @@ struct rf_ctx {
   std::vector<int> flight;     // slots launched and not yet validated, oldest first
 
   // scratch arenas shared by all passes (stream order makes reuse safe)
-  DevBuf cv, spans, halves, pieces, order, tiles, cursors;
-  size_t cap_spans = 0, cap_halves = 0, cap_pieces = 0;
+  DevBuf cv, spans, tris, entries, bins, longlist, ckpts, tiles, cursors;
+  // capacities: spans/tris/ckpts in 32-bit WORDS (record width depends on the pass's lane count),
+  // entries and long spans in records
+  size_t capw_spans = 0, capw_tris = 0, capw_ckpts = 0, cap_entries = 0, cap_long = 0;
   CtxStatus* d_cstatus = nullptr;
   DevBuf bounce;               // upload/download staging on the device
   PinnedBuf h_bounce;
@@ -163,13 +165,10 @@ rf_status fail(rf_ctx* c, rf_status st, const char* fmt, ...) {
 
 int lt_for(uint32_t L) { return L <= 3 ? 3 : (L <= 5 ? 5 : 8); }
 
-template <int LT> struct Sizes {
-  static size_t cv(size_t n) { return n * Rec<LT>::CVS * 4; }
-};
 size_t words_cv(int lt) { return lt == 3 ? Rec<3>::CVS : lt == 5 ? Rec<5>::CVS : Rec<8>::CVS; }
 size_t words_span(int lt) { return lt == 3 ? Rec<3>::SW : lt == 5 ? Rec<5>::SW : Rec<8>::SW; }
-size_t words_half(int lt) { return lt == 3 ? Rec<3>::HW : lt == 5 ? Rec<5>::HW : Rec<8>::HW; }
-size_t words_piece(int lt) { return lt == 3 ? Rec<3>::PW : lt == 5 ? Rec<5>::PW : Rec<8>::PW; }
+size_t words_tri(int lt) { return lt == 3 ? Rec<3>::TW : lt == 5 ? Rec<5>::TW : Rec<8>::TW; }
+size_t words_ckpt(int lt) { return lt == 3 ? Rec<3>::KW : lt == 5 ? Rec<5>::KW : Rec<8>::KW; }
 
 // ---- small utility kernels --------------------------------------------------------------------
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n, const CtxStatus* cs) {
@@ -228,32 +227,33 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   mark();
   k_prim<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
   mark();
-  k_span_count<LT><<<sm * 8, 256, 0, st>>>(P);
-  mark();
   k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, st>>>(P);
   mark();
-  k_piece_fill<LT><<<sm * 8, 256, 0, st>>>(P);
+  k_bin_scatter<<<sm * 8, 256, 0, st>>>(P);
   mark();
-  k_bin_sort<LT, RF_SORT_SMALL><<<sm * 8, 256, RF_SORT_SMALL * 8, st>>>(P, 0);
+  k_ckpt<LT><<<sm * 8, 256, 0, st>>>(P);
   mark();
-  k_bin_sort<LT, RF_SORT_BIG><<<sm, 256, RF_SORT_BIG * 8, st>>>(P, 1);
+  k_bin_sort_warp<<<sm * 8, RF_SORT_WARPS * 32, 0, st>>>(P);
+  mark();
+  k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, st>>>(P);
   mark();
   k_raster<LT><<<sm * 6, RF_RASTER_WARPS * 32, 0, st>>>(P);
   mark();
   s.n_launches += RF_N_KERNELS;
 }
 
-rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, size_t want_spans, size_t want_halves, size_t want_pieces) {
-  // Any growth frees memory that in-flight kernels might still use -> callers guarantee idleness.
+// Any growth frees memory that in-flight kernels might still use -> callers guarantee idleness.
+rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, size_t ww_spans, size_t ww_tris, size_t ww_ckpts, size_t w_entries,
+                        size_t w_long) {
   if (!c->cv.reserve(nv * words_cv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "clip-vertex arena");
-  // capacities are kept in units of the widest record so that an LT switch never shrinks them
-  if (want_spans > c->cap_spans) { if (!c->spans.reserve(want_spans * Rec<8>::SW * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->cap_spans = want_spans; }
-  if (want_halves > c->cap_halves) { if (!c->halves.reserve(want_halves * Rec<8>::HW * 4)) return fail(c, RF_E_NOMEM, "half arena"); c->cap_halves = want_halves; }
-  if (want_pieces > c->cap_pieces) {
-    if (!c->pieces.reserve(want_pieces * Rec<8>::PW * 4)) return fail(c, RF_E_NOMEM, "piece arena");
-    if (!c->order.reserve(want_pieces * 4)) return fail(c, RF_E_NOMEM, "order arena");
-    c->cap_pieces = want_pieces;
+  if (ww_spans > c->capw_spans) { if (!c->spans.reserve(ww_spans * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->capw_spans = ww_spans; }
+  if (ww_tris > c->capw_tris) { if (!c->tris.reserve(ww_tris * 4)) return fail(c, RF_E_NOMEM, "triangle arena"); c->capw_tris = ww_tris; }
+  if (ww_ckpts > c->capw_ckpts) { if (!c->ckpts.reserve(ww_ckpts * 4)) return fail(c, RF_E_NOMEM, "checkpoint arena"); c->capw_ckpts = ww_ckpts; }
+  if (w_entries > c->cap_entries) {
+    if (!c->entries.reserve(w_entries * 16) || !c->bins.reserve(w_entries * 8)) return fail(c, RF_E_NOMEM, "bin arena");
+    c->cap_entries = w_entries;
   }
+  if (w_long > c->cap_long) { if (!c->longlist.reserve(w_long * 8)) return fail(c, RF_E_NOMEM, "long-span list"); c->cap_long = w_long; }
   if (!c->tiles.reserve(n_tiles * 5 * 4 + 64)) return fail(c, RF_E_NOMEM, "tile arrays");
   if (!c->cursors.reserve(64)) return fail(c, RF_E_NOMEM, "cursors");
   return RF_OK;
@@ -281,7 +281,9 @@ rf_status launch_pass(rf_ctx* c, int si) {
   const int lt = lt_for(maxL);
   s.lt = lt;
 
-  const size_t table_bytes = nd * sizeof(DrawDesc) + 2 * (nd + 1) * 4 + nt * sizeof(TargetDesc) + 64;
+  size_t ncl = 0;
+  for (const QueuedClear& qc : s.clears) ncl += (qc.has_color ? 1 : 0) + (qc.has_depth ? 1 : 0);
+  const size_t table_bytes = nd * sizeof(DrawDesc) + 2 * (nd + 1) * 4 + nt * sizeof(TargetDesc) + ncl * sizeof(ClearDesc) + 64;
   if (!s.table.reserve(table_bytes)) return fail(c, RF_E_NOMEM, "pinned table");
   // idle device needed before any reallocation of buffers a previous launch of this slot used
   bool need_idle = s.d_table.cap < table_bytes || s.d_geom.cap < s.geom_len || s.d_dstats.cap < nd * sizeof(DrawStats);
@@ -289,17 +291,19 @@ rf_status launch_pass(rf_ctx* c, int si) {
   for (auto& q : s.draws) { nv += q.desc.n_verts; np += q.desc.n_prims; }
   for (auto* t : s.targets) ntiles += ((t->w + RF_TILE - 1) / RF_TILE) * ((t->h + RF_TILE - 1) / RF_TILE);
   s.NV = nv; s.NP = np; s.n_tiles = ntiles;
-  const size_t want_spans = std::max<size_t>(c->cap_spans, 1u << 20);
-  const size_t want_halves = std::max<size_t>(c->cap_halves, 1u << 19);
-  const size_t want_pieces = std::max<size_t>(c->cap_pieces, 1u << 20);
+  // initial arena sizes (grown on demand by validate_all after an overflowing pass)
+  const size_t ww_spans = std::max<size_t>(c->capw_spans, (size_t)8 << 20), ww_tris = std::max<size_t>(c->capw_tris, (size_t)4 << 20);
+  const size_t ww_ckpts = std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), w_entries = std::max<size_t>(c->cap_entries, (size_t)1 << 20);
+  const size_t w_long = std::max<size_t>(c->cap_long, (size_t)1 << 19);
   need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 20 + 64 ||
-              want_spans > c->cap_spans || want_halves > c->cap_halves || want_pieces > c->cap_pieces || c->cursors.cap < 64;
+              ww_spans > c->capw_spans || ww_tris > c->capw_tris || ww_ckpts > c->capw_ckpts || w_entries > c->cap_entries ||
+              w_long > c->cap_long || c->cursors.cap < 64;
   if (need_idle) { rf_status st = wait_idle(c); if (st) return st; }
   if (!s.d_table.reserve(table_bytes) || !s.d_geom.reserve(std::max<size_t>(s.geom_len, 16)) ||
       !s.d_dstats.reserve(std::max<size_t>(nd * sizeof(DrawStats), 16)) || !s.d_status.reserve(sizeof(PassStatus)) ||
       !s.h_dstats.reserve(std::max<size_t>(nd * sizeof(DrawStats), 16)))
     return fail(c, RF_E_NOMEM, "pass buffers");
-  { rf_status st = ensure_arenas(c, lt, nv, ntiles, want_spans, want_halves, want_pieces); if (st) return st; }
+  { rf_status st = ensure_arenas(c, lt, nv, ntiles, ww_spans, ww_tris, ww_ckpts, w_entries, w_long); if (st) return st; }
 
   // ---- build the table
   uint8_t* tb = s.table.p;
@@ -333,13 +337,25 @@ rf_status launch_pass(rf_ctx* c, int si) {
     T.band_y0 = std::min(c->band_y0, t->h); T.band_y1 = std::min(c->band_y1, t->h);
   }
 
+  const size_t coff = (toff + nt * sizeof(TargetDesc) + 15) & ~size_t(15);
+  ClearDesc* h_clears = reinterpret_cast<ClearDesc*>(tb + coff);
+  {
+    size_t k = 0;
+    for (const QueuedClear& qc : s.clears) {
+      const unsigned long long n = (unsigned long long)qc.target->w * qc.target->h;
+      if (qc.has_color) h_clears[k++] = ClearDesc{qc.target->d_color, n, qc.color, 0u};
+      if (qc.has_depth) h_clears[k++] = ClearDesc{reinterpret_cast<uint32_t*>(qc.target->d_depth), n, qc.zbits, 0u};
+    }
+  }
+
   cudaStream_t st = c->stream;
   RF_CUDA(c, cudaEventRecord(s.ev_start, st));
   s.n_launches = 0;
-  for (const QueuedClear& qc : s.clears) {
-    const size_t n = (size_t)qc.target->w * qc.target->h;
-    if (qc.has_color) { k_fill_u32<<<c->sm_count * 4, 256, 0, st>>>(qc.target->d_color, qc.color, n, c->d_cstatus); s.n_launches++; }
-    if (qc.has_depth) { k_fill_u32<<<c->sm_count * 4, 256, 0, st>>>(reinterpret_cast<uint32_t*>(qc.target->d_depth), qc.zbits, n, c->d_cstatus); s.n_launches++; }
+  RF_CUDA(c, cudaMemcpyAsync(s.d_table.p, tb, coff + ncl * sizeof(ClearDesc), cudaMemcpyHostToDevice, st));
+  if (ncl) {
+    const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)c->sm_count * 8 / ncl + 1, 1024));
+    k_clear_multi<<<dim3(gx, (unsigned)ncl), 256, 0, st>>>(reinterpret_cast<const ClearDesc*>(static_cast<uint8_t*>(s.d_table.p) + coff), c->d_cstatus);
+    s.n_launches++;
   }
   if (nd == 0) {
     RF_CUDA(c, cudaMemsetAsync(s.d_status.p, 0, sizeof(PassStatus), st));
@@ -348,7 +364,6 @@ rf_status launch_pass(rf_ctx* c, int si) {
     s.in_flight = true;
     return RF_OK;
   }
-  RF_CUDA(c, cudaMemcpyAsync(s.d_table.p, tb, toff + nt * sizeof(TargetDesc), cudaMemcpyHostToDevice, st));
   if (s.geom_len) RF_CUDA(c, cudaMemcpyAsync(s.d_geom.p, s.geom.p, s.geom_len, cudaMemcpyHostToDevice, st));
   RF_CUDA(c, cudaMemsetAsync(s.d_status.p, 0, sizeof(PassStatus), st));
   RF_CUDA(c, cudaMemsetAsync(s.d_dstats.p, 0, std::max<size_t>(nd * sizeof(DrawStats), 16), st));
@@ -364,13 +379,17 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.n_draws = (uint32_t)nd; P.n_targets = (uint32_t)nt; P.NV = nv; P.NP = np; P.n_tiles = ntiles;
   P.cv = static_cast<float*>(c->cv.p);
   P.spans = static_cast<uint32_t*>(c->spans.p);
-  P.halves = static_cast<uint32_t*>(c->halves.p);
-  P.pieces = static_cast<uint32_t*>(c->pieces.p);
-  P.order = static_cast<uint32_t*>(c->order.p);
-  // capacities in records of THIS pass's width (arenas are sized for the widest record)
-  P.cap_spans = (uint32_t)std::min<size_t>(c->cap_spans * Rec<8>::SW / words_span(lt), 0xFFFFFFF0u);
-  P.cap_halves = (uint32_t)std::min<size_t>(c->cap_halves * Rec<8>::HW / words_half(lt), 0xFFFFFFF0u);
-  P.cap_pieces = (uint32_t)std::min<size_t>(c->cap_pieces, 0xFFFFFFF0u);
+  P.tris = static_cast<uint32_t*>(c->tris.p);
+  P.entries = static_cast<uint4*>(c->entries.p);
+  P.bins = static_cast<unsigned long long*>(c->bins.p);
+  P.longlist = static_cast<uint2*>(c->longlist.p);
+  P.ckpts = static_cast<uint32_t*>(c->ckpts.p);
+  // capacities in records of THIS pass's width
+  P.cap_spans = (uint32_t)std::min<size_t>(c->capw_spans / words_span(lt), 0xFFFFFFF0u);
+  P.cap_tris = (uint32_t)std::min<size_t>(c->capw_tris / words_tri(lt), 0x7FFFFFF0u);
+  P.cap_ckpts = (uint32_t)std::min<size_t>(c->capw_ckpts / words_ckpt(lt), 0xFFFFFFF0u);
+  P.cap_entries = (uint32_t)std::min<size_t>(c->cap_entries, 0xFFFFFFF0u);
+  P.cap_long = (uint32_t)std::min<size_t>(c->cap_long, 0xFFFFFFF0u);
   uint32_t* ta = static_cast<uint32_t*>(c->tiles.p);
   P.tile_cnt = ta; P.tile_off = ta + ntiles; P.tile_fill = ta + 2 * (size_t)ntiles;
   P.worklist = ta + 3 * (size_t)ntiles; P.worklist_big = ta + 4 * (size_t)ntiles;
@@ -410,13 +429,14 @@ rf_status validate_all(rf_ctx* c) {
       // Every later pass in flight was a no-op (device poison). Grow and replay from here, in order.
       { rf_status st = wait_idle(c); if (st) return st; }
       const int lt = (int)s.lt;
-      const size_t ws = (size_t)((ps.spans_needed * words_span(lt) + Rec<8>::SW - 1) / Rec<8>::SW);
-      const size_t wh = (size_t)((ps.halves_needed * words_half(lt) + Rec<8>::HW - 1) / Rec<8>::HW);
-      const size_t wp = (size_t)ps.pieces_needed;
-      const size_t ns = std::max(c->cap_spans, ws + ws / 8 + 1024), nh = std::max(c->cap_halves, wh + wh / 8 + 1024);
-      // pieces_needed is only known once spans fit; guess from spans if it did not get that far
-      const size_t np = std::max(c->cap_pieces, std::max(wp + wp / 8, ws + ws / 4) + 1024);
-      { rf_status st = ensure_arenas(c, lt, s.NV, s.n_tiles, ns, nh, np); if (st) return st; }
+      auto grow = [](size_t cap, unsigned long long need) { return need > cap ? (size_t)(need + need / 4 + 4096) : cap; };
+      const size_t ws = grow(c->capw_spans, ps.spans_needed * words_span(lt));
+      const size_t wt = grow(c->capw_tris, ps.tris_needed * words_tri(lt));
+      const size_t we = grow(c->cap_entries, ps.entries_needed);
+      // long spans / checkpoints are only fully counted once the spans fit; guess from the spans otherwise
+      const size_t wl = grow(c->cap_long, std::max<unsigned long long>(ps.long_needed, ps.spans_needed > c->capw_spans / words_span(lt) ? ps.spans_needed / 8 : 0));
+      const size_t wk = grow(c->capw_ckpts, ps.ckpts_needed * words_ckpt(lt));
+      { rf_status st = ensure_arenas(c, lt, s.NV, s.n_tiles, ws, wt, wk, we, wl); if (st) return st; }
       RF_CUDA(c, cudaMemsetAsync(c->d_cstatus, 0, sizeof(CtxStatus), c->stream));
       std::vector<int> replay = c->flight;
       for (int r : replay) { rf_status st = launch_pass(c, r); if (st) return st; }
@@ -436,7 +456,9 @@ rf_status validate_all(rf_ctx* c) {
     if (ps.error) {
       if (ps.error & RF_ERRBIT_INDEX_OOB) result = fail(c, RF_E_INDEX_OOB, "vertex index out of bounds (render/prim.rs:17-19 panics)");
       else if (ps.error & RF_ERRBIT_TARGET_OOB) result = fail(c, RF_E_TARGET_OOB, "scanline outside the render target (render/target.rs:148,173 panics)");
-      else result = fail(c, RF_E_NOMEM, "a 32x32 tile holds more than %u span pieces (max_bin=%u)", RF_SORT_BIG, ps.max_bin);
+      else if (ps.error & RF_ERRBIT_NEG_ROW) result = fail(c, RF_E_TARGET_OOB, "scanline above the render target (viewport outside the target)");
+      else if (ps.error & RF_ERRBIT_INTERNAL) result = fail(c, RF_E_CUDA, "internal: span outside its triangle's tile bounding box");
+      else result = fail(c, RF_E_NOMEM, "a 32x32 tile is overlapped by more than %u triangles of one pass (max_bin=%u)", RF_SORT_BIG, ps.max_bin);
     } else {
       const DrawStats* ds = reinterpret_cast<const DrawStats*>(s.h_dstats.p);
       for (size_t i = 0; i < s.draws.size(); i++) {
@@ -586,9 +608,7 @@ rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
     for (int e = 0; e <= RF_N_KERNELS && ok; e++) ok = cudaEventCreate(&s.ev_k[e]) == cudaSuccess;
     ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_status), sizeof(HostStatus), cudaHostAllocDefault) == cudaSuccess;
   }
-  ok = ok && cudaFuncSetAttribute(k_bin_sort<3, RF_SORT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(k_bin_sort<5, RF_SORT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(k_bin_sort<8, RF_SORT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_bin_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
   if (!ok) { rf_ctx_destroy(c); return RF_E_CUDA; }
   *out = c;
   return RF_OK;
@@ -607,7 +627,7 @@ void rf_ctx_destroy(rf_ctx* c) {
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
     for (int e = 0; e <= RF_N_KERNELS; e++) if (s.ev_k[e]) cudaEventDestroy(s.ev_k[e]);
   }
-  c->cv.release(); c->spans.release(); c->halves.release(); c->pieces.release(); c->order.release();
+  c->cv.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->longlist.release(); c->ckpts.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
   if (c->d_cstatus) cudaFree(c->d_cstatus);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -835,7 +855,7 @@ rf_status rf_ctx_kernel_times(rf_ctx* c, uint64_t* ns, uint64_t* launches) {
 }
 
 const char* rf_kernel_name(uint32_t i) {
-  static const char* names[RF_N_KERNELS] = {"k_vertex", "k_prim", "k_span_count", "k_bin_alloc", "k_piece_fill", "k_bin_sort", "k_bin_sort_big", "k_raster"};
+  static const char* names[RF_N_KERNELS] = {"k_vertex", "k_prim", "k_bin_alloc", "k_bin_scatter", "k_ckpt", "k_bin_sort_warp", "k_bin_sort_big", "k_raster"};
   return i < RF_N_KERNELS ? names[i] : "";
 }
 

@@ -26,6 +26,8 @@
 #define RF_ERRBIT_INDEX_OOB 0x1u
 #define RF_ERRBIT_TARGET_OOB 0x2u
 #define RF_ERRBIT_BIN_TOO_DEEP 0x4u
+#define RF_ERRBIT_NEG_ROW 0x8u
+#define RF_ERRBIT_INTERNAL 0x10u
 
 struct DrawDesc {
   const float* verts;       // [n_verts][vstride]
@@ -55,13 +57,16 @@ struct DrawStats {
 
 // zeroed before every pass; read back after it
 struct PassStatus {
-  unsigned long long spans_needed;   // total span records the pass wants
-  unsigned long long halves_needed;  // total half records
-  unsigned long long pieces_needed;  // total piece records
-  uint32_t error;                    // RF_ERRBIT_*
-  uint32_t overflow;                 // a capacity was exceeded: nothing was rasterised
-  uint32_t n_work;                   // non-empty tiles
-  uint32_t n_work_big;               // tiles whose bin needs the large-smem sort
+  unsigned long long spans_needed;    // span records the pass wants (one per scanline of every drawn triangle)
+  unsigned long long tris_needed;     // triangle records
+  unsigned long long entries_needed;  // bin entry slots (triangle x bounding-box tile)
+  unsigned long long long_needed;     // spans that cross a tile-column boundary
+  unsigned long long ckpts_needed;    // checkpoint records for those spans
+  unsigned long long bins_needed;     // valid bin entries = total size of all tile bins
+  uint32_t error;                     // RF_ERRBIT_*
+  uint32_t overflow;                  // a capacity was exceeded: nothing was rasterised
+  uint32_t n_work;                    // non-empty tiles
+  uint32_t n_work_big;                // tiles whose bin needs the large-smem sort
   uint32_t max_bin;
   uint32_t _pad;
 };
@@ -71,6 +76,13 @@ struct CtxStatus {
   uint32_t poison;
 };
 
+struct ClearDesc {
+  uint32_t* ptr;
+  unsigned long long n;
+  uint32_t value;
+  uint32_t _pad;
+};
+
 struct PassParams {
   const DrawDesc* draws;
   const uint32_t* vbase;  // [n_draws+1] prefix of n_verts
@@ -78,28 +90,33 @@ struct PassParams {
   const TargetDesc* targets;
   uint32_t n_draws, n_targets, NV, NP, n_tiles;
   float* cv;              // clip verts [NV][CVS]
-  uint32_t* spans;        // [cap_spans][SW]
-  uint32_t* halves;       // [cap_halves][HW]
-  uint32_t* pieces;       // [cap_pieces][PW]
-  uint32_t* order;        // [cap_pieces] sorted local piece index per tile bin
-  uint32_t cap_spans, cap_halves, cap_pieces;
+  uint32_t* spans;        // [cap_spans][SW]   one per scanline, contiguous per triangle
+  uint32_t* tris;         // [cap_tris][TW]    per drawn triangle: key, draw, rows, dv/dx of both halves
+  uint4* entries;         // [cap_entries]     {tile | ~0, key, tri, 0}: triangle x bbox-tile slots
+  unsigned long long* bins;  // [cap_entries]  per-tile lists of (key << 32 | tri), sorted by k_bin_sort
+  uint2* longlist;        // [cap_long]        {span index, tri*2+half} of spans crossing a tile-column boundary
+  uint32_t* ckpts;        // [cap_ckpts][KW]   varyings of such spans at each later tile-column start
+  uint32_t cap_spans, cap_tris, cap_entries, cap_long, cap_ckpts;
   uint32_t* tile_cnt;     // [n_tiles]
   uint32_t* tile_off;     // [n_tiles]
   uint32_t* tile_fill;    // [n_tiles]
   uint32_t* worklist;     // [n_tiles] non-empty tiles
   uint32_t* worklist_big; // [n_tiles]
-  uint32_t* cursors;      // [0] piece cursor, [1] raster work cursor, [2] sort cursor, [3] big sort cursor
+  uint32_t* cursors;      // [1] raster work cursor
   DrawStats* dstats;      // [n_draws]
   PassStatus* status;
   CtxStatus* cstatus;
 };
 
+#define RF_NO_CKPT 0xFFFFFFFFu
+#define RF_NO_TILE 0xFFFFFFFFu
+
 // record strides in 32-bit words, as a function of the compile-time lane count LT
 template <int LT> struct Rec {
-  static constexpr int CVS = (5 + LT + 3) & ~3;  // clip vert: pos4, oc, attr[LT]
-  static constexpr int SW = (5 + LT + 3) & ~3;   // span: Y, X0, n, half, z, attr[LT]
-  static constexpr int HW = (3 + LT + 3) & ~3;   // half: key, draw, dz, dattr[LT]
-  static constexpr int PW = (4 + LT + 3) & ~3;   // piece: key, yxn, half, z, attr[LT]
+  static constexpr int CVS = (5 + LT + 3) & ~3;        // clip vert: pos4, oc, attr[LT]            (16 B aligned)
+  static constexpr int SW = (2 + 1 + LT + 1) & ~1;     // span: X0|n<<16, ckpt, z, attr[LT]         (8 B aligned)
+  static constexpr int TW = (6 + 2 * (1 + LT) + 3) & ~3;  // tri: key, draw, sbase, Y0, nU, nL|target<<16, dv[2][1+LT]
+  static constexpr int KW = (1 + LT + 1) & ~1;         // checkpoint: z, attr[LT]                   (8 B aligned)
 };
 
 // ---- Rust `as` casts (saturating, NaN -> 0). PTX cvt.rzi.{u32,s32}.f32 clamps and maps NaN to 0.
@@ -181,4 +198,15 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v) {
     if ((int)lane_id() >= o) v += t;
   }
   return v;
+}
+
+// Warp-aggregated increment usable from divergent code: the currently converged lanes elect a
+// leader that performs one atomic for the group; returns this lane's slot.
+__device__ __forceinline__ unsigned long long agg_atomic_inc(unsigned long long* ctr) {
+  const uint32_t mask = __activemask();
+  const int leader = __ffs(mask) - 1;
+  unsigned long long base = 0;
+  if ((int)lane_id() == leader) base = atomicAdd(ctr, (unsigned long long)__popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + __popc(mask & lanemask_lt());
 }

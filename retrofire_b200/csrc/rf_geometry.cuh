@@ -207,10 +207,90 @@ __device__ __forceinline__ void half_setup(float y0, float y1, const float* l0, 
   H.n = sat_u32(y1r - y0r);
 }
 
+// Walk one trapezoid half row by row (ScanlineIter::next, raster.rs:80-114): sequential adds down
+// both edges, one span record per row. Tracks the tile-column range touched in the current tile
+// row and flushes exact bin entries whenever the walk leaves a tile row.
+template <int LT> struct WalkState {
+  uint32_t sidx;        // next span record
+  uint32_t Y;           // current row
+  uint32_t cmin, cmax;  // tile columns touched in the current tile row (cmin > cmax: none)
+  unsigned long long frags_i;
+};
+
+template <int LT>
+__device__ __forceinline__ void flush_tile_row(const PassParams& P, const TargetDesc& T, WalkState<LT>& W, uint32_t trow, uint32_t tr0,
+                                               uint32_t c_lo, uint32_t ncols, uint32_t ebase, uint32_t key, uint32_t tri_idx) {
+  if (W.cmin <= W.cmax && (W.cmin < c_lo || W.cmax >= c_lo + ncols)) atomicOr(&P.status->error, RF_ERRBIT_INTERNAL);
+  uint4* e = P.entries + ebase + (size_t)(trow - tr0) * ncols;
+  const uint32_t tbase = T.tile_base + trow * T.tiles_x;
+  for (uint32_t c = 0; c < ncols; c++) {
+    const uint32_t col = c_lo + c;
+    const bool valid = col >= W.cmin && col <= W.cmax;
+    e[c] = make_uint4(valid ? tbase + col : RF_NO_TILE, key, tri_idx, 0u);
+    if (valid) atomicAdd(P.tile_cnt + tbase + col, 1u);
+  }
+  W.cmin = 0xFFFFFFFFu;
+  W.cmax = 0u;
+}
+
+template <int LT>
+__device__ __forceinline__ void walk_half(const PassParams& P, const TargetDesc& T, HalfSetup<LT>& H, WalkState<LT>& W, uint32_t rows_left_after,
+                                          uint32_t own, uint32_t tr0, uint32_t c_lo, uint32_t ncols, uint32_t ebase, uint32_t key, uint32_t tri_idx) {
+  constexpr int NL = 2 + LT;
+  constexpr int SW = Rec<LT>::SW;
+  float y = H.y;
+  for (uint32_t j = 0; j < H.n; j++) {
+    float v0[NL];
+#pragma unroll
+    for (int i = 0; i < NL; i++) { v0[i] = H.L[i]; H.L[i] = H.L[i] + H.dl[i]; }
+    const float x1 = H.R;
+    H.R = H.R + H.dr;
+    const float x0r = round_up_to_half(v0[0]), x1r = round_up_to_half(x1);
+    const float tx = x0r - v0[0];
+    uint32_t w[SW];
+#pragma unroll
+    for (int i = 1; i < NL; i++) w[2 + (i - 1)] = __float_as_uint(v0[i] + ((v0[i] + H.dv[i]) - v0[i]) * tx);
+#pragma unroll
+    for (int i = 2 + NL - 1; i < SW; i++) w[i] = 0u;
+    const uint32_t cnt = sat_u32(x1r - x0r);
+    const uint32_t Yf = sat_u32(y), X0 = sat_u32(x0r), X1 = max(sat_u32(x1r), X0);
+    uint32_t nn = min(cnt, X1 - X0);
+    if (Yf >= T.h || X1 > T.w) {  // target.rs:148,173-174 (slice index panics)
+      atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
+      nn = 0;
+    } else if (Yf < T.band_y0 || Yf >= T.band_y1) {
+      nn = 0;  // not this GPU's row band
+    } else {
+      W.frags_i += X1 - X0;
+    }
+    if (nn) {
+      const uint32_t ca = X0 >> RF_TILE_SHIFT, cb = (X0 + nn - 1) >> RF_TILE_SHIFT;
+      W.cmin = min(W.cmin, ca);
+      W.cmax = max(W.cmax, cb);
+      if (ca != cb) {  // crosses a tile-column boundary: k_ckpt will add checkpoints
+        const unsigned long long slot = agg_atomic_inc(&P.status->long_needed);
+        if (slot < P.cap_long) P.longlist[slot] = make_uint2(W.sidx, own);
+        else { P.status->overflow = 1; P.cstatus->poison = 1; }
+      }
+    }
+    w[0] = X0 | nn << 16;
+    w[1] = RF_NO_CKPT;
+    uint32_t* sr = P.spans + (size_t)W.sidx * SW;
+#pragma unroll
+    for (int q = 0; q < SW / 2; q++) *reinterpret_cast<uint2*>(sr + 2 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
+    W.sidx++;
+    const bool last = (j + 1 == H.n) && rows_left_after == 0;
+    if (last || ((W.Y + 1) >> RF_TILE_SHIFT) != (W.Y >> RF_TILE_SHIFT))
+      flush_tile_row<LT>(P, T, W, W.Y >> RF_TILE_SHIFT, tr0, c_lo, ncols, ebase, key, tri_idx);
+    W.Y++;
+    y = y + 1.0f;
+  }
+}
+
 template <int LT>
 __global__ void __launch_bounds__(128) k_prim(PassParams P) {
   constexpr int NL = 2 + LT;
-  constexpr int SW = Rec<LT>::SW, HW = Rec<LT>::HW;
+  constexpr int TW = Rec<LT>::TW;
   if (P.cstatus->poison) return;
   const uint32_t lane = lane_id();
   const uint32_t n_iter = (P.NP + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
@@ -254,7 +334,8 @@ __global__ void __launch_bounds__(128) k_prim(PassParams P) {
     for (uint32_t t = 0; t < max_tri; t++) {
       bool emit = false;
       HalfSetup<LT> H0, H1;
-      uint32_t tw = 0, th = 0, tgt = 0, by0 = 0, by1 = 0;
+      H0.n = H1.n = 0;
+      uint32_t tgt = 0, Y0 = 0, tr0 = 0, c_lo = 0, ncols = 0, nent = 0;
       if (t < ntri) {
         const DrawDesc& D = P.draws[d];
         SVert<LT> s[3];
@@ -276,8 +357,7 @@ __global__ void __launch_bounds__(128) k_prim(PassParams P) {
         const bool back = wz < 0.0f;
         const uint32_t cull = D.flags & RF_F_CULL_MASK;
         if (!((cull == RF_CULL_BACK && back) || (cull == RF_CULL_FRONT && !back))) {
-          emit = true;
-          my_prims_o++;
+          my_prims_o++;  // render.rs:195-196: counted before rasterisation, whatever it covers
           // tri_fill raster.rs:185-224: stable sort by y (total_cmp)
           int o0 = 0, o1 = 1, o2 = 2;
           {
@@ -308,91 +388,78 @@ __global__ void __launch_bounds__(128) k_prim(PassParams P) {
           half_setup<LT>(ty, my, top, left, top, right, H0);
           half_setup<LT>(my, by, left, bot, right, bot, H1);
           const TargetDesc& T = P.targets[D.target];
-          tgt = D.target; tw = T.w; th = T.h; by0 = T.band_y0; by1 = T.band_y1;
-          // Row-range sanity: a scanline at y >= h panics in the reference (target.rs:148,173).
-          // Also bounds the loop (RF_MAX_ROWS) against absurd coordinates.
-#pragma unroll
-          for (int hh = 0; hh < 2; hh++) {
-            HalfSetup<LT>& H = hh ? H1 : H0;
-            if (H.n != 0) {
-              const float ylast = H.y + (float)(H.n - 1);
-              if (H.n > RF_MAX_ROWS || sat_u32(ylast) >= th) {
-                atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
-                H.n = 0;
-              }
+          tgt = D.target;
+          // Row-range sanity. A scanline at y >= h panics in the reference (target.rs:148,173);
+          // RF_MAX_ROWS bounds the loop against absurd coordinates; a negative first row can only
+          // come from a viewport outside the target and is rejected (the reference would draw it at row 0).
+          uint32_t nrows = H0.n + H1.n;
+          if (nrows != 0) {
+            const float yfirst = H0.n ? H0.y : H1.y;
+            const float ylast = yfirst + (float)(nrows - 1);
+            if (H0.n > RF_MAX_ROWS || H1.n > RF_MAX_ROWS || sat_u32(ylast) >= T.h) {
+              atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
+              nrows = 0;
+            } else if (yfirst < 0.0f) {
+              atomicOr(&P.status->error, RF_ERRBIT_NEG_ROW);
+              nrows = 0;
+            }
+            if (nrows == 0) H0.n = H1.n = 0;
+            else {
+              emit = true;
+              Y0 = sat_u32(yfirst);
+              tr0 = Y0 >> RF_TILE_SHIFT;
+              const uint32_t tr1 = (Y0 + nrows - 1) >> RF_TILE_SHIFT;
+              const float xmin = fminf(s[0].x, fminf(s[1].x, s[2].x)), xmax = fmaxf(s[0].x, fmaxf(s[1].x, s[2].x));
+              c_lo = min(sat_u32(floorf(xmin) - 1.0f) >> RF_TILE_SHIFT, T.tiles_x - 1);
+              const uint32_t c_hi = min(sat_u32(floorf(xmax) + 1.0f) >> RF_TILE_SHIFT, T.tiles_x - 1);
+              ncols = (c_hi >= c_lo ? c_hi - c_lo : 0u) + 1u;
+              nent = (tr1 - tr0 + 1) * ncols;
             }
           }
         }
       }
-      // ---- warp-aggregated allocation of span and half records (warp prefix sum)
+      // ---- warp-aggregated allocation (warp prefix sums): span records, triangle records, bin slots
       const uint32_t nsp = emit ? (H0.n + H1.n) : 0u;
-      const uint32_t incl = warp_scan_incl(nsp);
-      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      const uint32_t incl_s = warp_scan_incl(nsp);
+      const uint32_t incl_e = warp_scan_incl(nent);
+      const uint32_t tot_s = __shfl_sync(0xFFFFFFFFu, incl_s, 31), tot_e = __shfl_sync(0xFFFFFFFFu, incl_e, 31);
       const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
-      uint32_t sbase = 0, hbase = 0;
+      unsigned long long sb = 0, tb = 0, eb = 0;
       if (lane == 0 && emask) {
-        sbase = (uint32_t)atomicAdd(&P.status->spans_needed, (unsigned long long)total);
-        hbase = (uint32_t)atomicAdd(&P.status->halves_needed, 2ull * __popc(emask));
+        sb = atomicAdd(&P.status->spans_needed, (unsigned long long)tot_s);
+        tb = atomicAdd(&P.status->tris_needed, (unsigned long long)__popc(emask));
+        eb = atomicAdd(&P.status->entries_needed, (unsigned long long)tot_e);
       }
-      sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
-      hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
-      const bool fits = (unsigned long long)sbase + total <= P.cap_spans && (unsigned long long)hbase + 2u * __popc(emask) <= P.cap_halves;
+      sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
+      tb = __shfl_sync(0xFFFFFFFFu, tb, 0);
+      eb = __shfl_sync(0xFFFFFFFFu, eb, 0);
+      const bool fits = sb + tot_s <= P.cap_spans && tb + __popc(emask) <= P.cap_tris && eb + tot_e <= P.cap_entries;
       if (!fits) {
         if (lane == 0 && emask) { P.status->overflow = 1; P.cstatus->poison = 1; }
         continue;  // keep counting what is needed, write nothing
       }
       if (!emit) continue;
-      uint32_t sidx = sbase + (incl - nsp);
-      const uint32_t hidx = hbase + 2u * __popc(emask & lanemask_lt());
+      const uint32_t sbase = (uint32_t)sb + (incl_s - nsp);
+      const uint32_t tri_idx = (uint32_t)tb + __popc(emask & lanemask_lt());
+      const uint32_t ebase = (uint32_t)eb + (incl_e - nent);
       const uint32_t key = gp * 8u + t;
-
+      {  // triangle record
+        uint32_t w[TW];
+        w[0] = key; w[1] = d; w[2] = sbase; w[3] = Y0; w[4] = H0.n; w[5] = H1.n | (tgt << 16);
 #pragma unroll
-      for (int hh = 0; hh < 2; hh++) {
-        HalfSetup<LT>& H = hh ? H1 : H0;
-        // half record: key, draw, dz/dx, dattr/dx
-        {
-          uint32_t* hr = P.halves + (size_t)(hidx + hh) * HW;
-          uint32_t w[HW];
-          w[0] = key; w[1] = d; w[2] = __float_as_uint(H.dv[1]);
+        for (int i = 0; i < 1 + LT; i++) { w[6 + i] = __float_as_uint(H0.dv[1 + i]); w[6 + (1 + LT) + i] = __float_as_uint(H1.dv[1 + i]); }
 #pragma unroll
-          for (int i = 0; i < HW - 3; i++) w[3 + i] = (i < LT) ? __float_as_uint(H.dv[2 + i]) : 0u;
+        for (int i = 6 + 2 * (1 + LT); i < TW; i++) w[i] = 0u;
+        uint32_t* tr = P.tris + (size_t)tri_idx * TW;
 #pragma unroll
-          for (int q = 0; q < HW / 4; q++) *reinterpret_cast<uint4*>(hr + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-        }
-        // ScanlineIter::next raster.rs:80-114 — sequential adds down both edges
-        float y = H.y;
-        for (uint32_t j = 0; j < H.n; j++) {
-          float v0[NL];
-#pragma unroll
-          for (int i = 0; i < NL; i++) { v0[i] = H.L[i]; H.L[i] = H.L[i] + H.dl[i]; }
-          const float x1 = H.R;
-          H.R = H.R + H.dr;
-          const float x0r = round_up_to_half(v0[0]), x1r = round_up_to_half(x1);
-          const float tx = x0r - v0[0];
-          uint32_t w[SW];
-#pragma unroll
-          for (int i = 1; i < NL; i++) w[4 + (i - 1)] = __float_as_uint(v0[i] + ((v0[i] + H.dv[i]) - v0[i]) * tx);
-#pragma unroll
-          for (int i = 4 + NL - 1; i < SW; i++) w[i] = 0u;
-          const uint32_t cnt = sat_u32(x1r - x0r);
-          const uint32_t Y = sat_u32(y), X0 = sat_u32(x0r), X1 = max(sat_u32(x1r), X0);
-          uint32_t nn = min(cnt, X1 - X0);
-          if (Y >= th || X1 > tw) {  // target.rs:148,173-174
-            atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
-            nn = 0;
-          } else if (Y < by0 || Y >= by1) {
-            nn = 0;  // not this GPU's row band
-          } else {
-            my_frags_i += X1 - X0;
-          }
-          w[0] = Y; w[1] = X0; w[2] = nn | (tgt << 16); w[3] = hidx + hh;
-          uint32_t* sr = P.spans + (size_t)sidx * SW;
-#pragma unroll
-          for (int q = 0; q < SW / 4; q++) *reinterpret_cast<uint4*>(sr + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-          sidx++;
-          y = y + 1.0f;
-        }
+        for (int q = 0; q < TW / 4; q++) *reinterpret_cast<uint4*>(tr + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
       }
+      const TargetDesc& T = P.targets[tgt];
+      WalkState<LT> W;
+      W.sidx = sbase; W.Y = Y0; W.cmin = 0xFFFFFFFFu; W.cmax = 0u; W.frags_i = 0;
+      walk_half<LT>(P, T, H0, W, H1.n, tri_idx * 2u, tr0, c_lo, ncols, ebase, key, tri_idx);
+      walk_half<LT>(P, T, H1, W, 0u, tri_idx * 2u + 1u, tr0, c_lo, ncols, ebase, key, tri_idx);
+      my_frags_i += W.frags_i;
     }
     // ---- per-draw stats: aggregate over the warp when every lane has the same draw
     {

@@ -1,35 +1,15 @@
-// rf_raster.cuh — binning of span pieces into 32x32 tiles, per-tile submission-order sort, and
-// the tile rasteriser (span fill, perspective-correct varyings, texture fetch, depth test,
+// rf_raster.cuh — tile binning of triangles, per-tile submission-order sort, span checkpoints,
+// and the tile rasteriser (span fill, perspective-correct varyings, texture fetch, depth test,
 // colour/depth writes). Reference path: raster.rs:60-69 (fragments), target.rs:138-198.
 #pragma once
 #include "rf_device.cuh"
 
 // =============================================================================================
-// K3a: count, per tile, the span pieces that fall into it. One thread per span.
+// K3: give every non-empty tile a contiguous bin (warp prefix sum + one atomic per warp) and
+// build the work lists. tile_cnt was accumulated by k_prim.
 // =============================================================================================
-template <int LT>
-__global__ void __launch_bounds__(256) k_span_count(PassParams P) {
-  constexpr int SW = Rec<LT>::SW;
-  if (P.cstatus->poison) return;
-  const uint32_t ns = (uint32_t)min(P.status->spans_needed, (unsigned long long)P.cap_spans);
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
-    const uint4 h = __ldg(reinterpret_cast<const uint4*>(P.spans + (size_t)s * SW));
-    const uint32_t n = h.z & 0xFFFFu;
-    if (n == 0) continue;
-    const TargetDesc& T = P.targets[h.z >> 16];
-    const uint32_t trow = h.x >> RF_TILE_SHIFT;
-    const uint32_t c0 = h.y >> RF_TILE_SHIFT, c1 = (h.y + n - 1) >> RF_TILE_SHIFT;
-    uint32_t* cnt = P.tile_cnt + T.tile_base + trow * T.tiles_x;
-    for (uint32_t c = c0; c <= c1; c++) atomicAdd(cnt + c, 1u);
-  }
-}
-
-// =============================================================================================
-// K3b: give every non-empty tile a contiguous bin in the piece buffer (warp prefix sum + one
-// atomic per warp) and build the work lists.
-// =============================================================================================
-#define RF_SORT_SMALL 2048u
-#define RF_SORT_BIG 16384u
+#define RF_SORT_SMALL 1024u   // per-warp shared-memory sort capacity (entries)
+#define RF_SORT_BIG 16384u    // per-block (large smem) sort capacity
 
 __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
   if (P.cstatus->poison) return;
@@ -44,17 +24,14 @@ __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
     const uint32_t big = __ballot_sync(0xFFFFFFFFu, c > RF_SORT_SMALL);
     uint32_t base = 0, wbase = 0, bbase = 0;
     if (lane == 0 && nz) {
-      base = (uint32_t)atomicAdd(&P.status->pieces_needed, (unsigned long long)total);
+      base = (uint32_t)atomicAdd(&P.status->bins_needed, (unsigned long long)total);
       wbase = atomicAdd(&P.status->n_work, (uint32_t)__popc(nz));
       if (big) bbase = atomicAdd(&P.status->n_work_big, (uint32_t)__popc(big));
     }
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
     bbase = __shfl_sync(0xFFFFFFFFu, bbase, 0);
-    if (nz && (unsigned long long)base + total > P.cap_pieces) {
-      if (lane == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
-      continue;
-    }
+    // valid entries <= entry slots <= cap_entries, so the bins always fit
     if (c != 0) {
       P.tile_off[t] = base + (incl - c);
       P.worklist[wbase + __popc(nz & lanemask_lt())] = t;
@@ -66,115 +43,179 @@ __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
 }
 
 // =============================================================================================
-// K3c: cut every span at tile-column boundaries into pieces, advancing the varyings to each
-// boundary by the reference's own sequential adds (vary.rs:146-154) — this is what lets tiles
-// run independently and still reproduce the running sums bit for bit. One thread per span.
+// K4: scatter the (triangle x tile) entries written by k_prim into the tile bins.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_bin_scatter(PassParams P) {
+  if (P.cstatus->poison) return;
+  const uint32_t ne = (uint32_t)min(P.status->entries_needed, (unsigned long long)P.cap_entries);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += gridDim.x * blockDim.x) {
+    const uint4 e = __ldg(P.entries + i);
+    if (e.x == RF_NO_TILE) continue;
+    const uint32_t slot = P.tile_off[e.x] + atomicAdd(P.tile_fill + e.x, 1u);
+    P.bins[slot] = (unsigned long long)e.y << 32 | e.z;
+  }
+}
+
+// =============================================================================================
+// K5: checkpoints. A span that crosses tile-column boundaries gets, for every later tile column
+// it touches, the varyings at that column's first pixel — produced by the reference's own
+// sequential adds (vary.rs:146-154), so tiles can start mid-span and still reproduce the running
+// sums bit for bit. One thread per such span.
 // =============================================================================================
 template <int LT>
-__global__ void __launch_bounds__(256) k_piece_fill(PassParams P) {
-  constexpr int SW = Rec<LT>::SW, HW = Rec<LT>::HW, PW = Rec<LT>::PW;
-  constexpr int NV = 1 + LT;  // z + attrs
+__global__ void __launch_bounds__(256) k_ckpt(PassParams P) {
+  constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW;
+  constexpr int NV = 1 + LT;
   if (P.cstatus->poison) return;
-  const uint32_t ns = (uint32_t)min(P.status->spans_needed, (unsigned long long)P.cap_spans);
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
-    const uint32_t* sp = P.spans + (size_t)s * SW;
-    uint32_t w[SW];
-#pragma unroll
-    for (int q = 0; q < SW / 4; q++) {
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(sp) + q);
-      w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+  const uint32_t nl = (uint32_t)min(P.status->long_needed, (unsigned long long)P.cap_long);
+  const uint32_t lane = lane_id();
+  const uint32_t n_iter = (nl + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
+  for (uint32_t it = 0; it < n_iter; it++) {
+    const uint32_t li = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool have = li < nl;
+    uint32_t s = 0, own = 0, X0 = 0, n = 0, nck = 0;
+    if (have) {
+      const uint2 le = P.longlist[li];
+      s = le.x; own = le.y;
+      const uint32_t h = P.spans[(size_t)s * SW];
+      X0 = h & 0xFFFFu; n = h >> 16;
+      nck = ((X0 + n - 1) >> RF_TILE_SHIFT) - (X0 >> RF_TILE_SHIFT);
     }
-    const uint32_t n = w[2] & 0xFFFFu;
-    if (n == 0) continue;
-    const uint32_t Y = w[0], X0 = w[1], half = w[3];
-    const TargetDesc& T = P.targets[w[2] >> 16];
+    const uint32_t incl = warp_scan_incl(nck);
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && total) base = atomicAdd(&P.status->ckpts_needed, (unsigned long long)total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base + total > P.cap_ckpts) {
+      if (lane == 0 && total) { P.status->overflow = 1; P.cstatus->poison = 1; }
+      continue;
+    }
+    if (!have || nck == 0) continue;
+    const uint32_t cbase = (uint32_t)base + (incl - nck);
+    uint32_t* sp = P.spans + (size_t)s * SW;
+    sp[1] = cbase;
     float v[NV], dv[NV];
 #pragma unroll
-    for (int i = 0; i < NV; i++) v[i] = __uint_as_float(w[4 + i]);
-    const uint32_t* hr = P.halves + (size_t)half * HW;
-    const uint32_t key = __ldg(hr);
-    const bool multi = ((X0 + n - 1) >> RF_TILE_SHIFT) != (X0 >> RF_TILE_SHIFT);
-    if (multi) {
+    for (int i = 0; i < NV; i++) v[i] = __uint_as_float(sp[2 + i]);
+    const uint32_t* tr = P.tris + (size_t)(own >> 1) * TW + 6 + (own & 1u) * NV;
 #pragma unroll
-      for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(__ldg(hr + 2 + i));
-    }
-    const uint32_t tile_row = T.tile_base + (Y >> RF_TILE_SHIFT) * T.tiles_x;
-    const uint32_t xe = X0 + n;
+    for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(__ldg(tr + i));
     uint32_t x = X0;
-    while (x < xe) {
-      const uint32_t c = x >> RF_TILE_SHIFT;
-      const uint32_t xend = min((c + 1) << RF_TILE_SHIFT, xe);
-      const uint32_t m = xend - x;
-      const uint32_t tile = tile_row + c;
-      const uint32_t slot = P.tile_off[tile] + atomicAdd(P.tile_fill + tile, 1u);
-      uint32_t o[PW];
-      o[0] = key;
-      o[1] = (Y & (RF_TILE - 1)) | (x & (RF_TILE - 1)) << 8 | m << 16;
-      o[2] = half;
+    const uint32_t xe = X0 + n;
+    uint32_t k = 0;
+    for (;;) {
+      const uint32_t xend = ((x >> RF_TILE_SHIFT) + 1) << RF_TILE_SHIFT;
+      if (xend >= xe) break;
+      for (; x < xend; x++) {
 #pragma unroll
-      for (int i = 0; i < NV; i++) o[3 + i] = __float_as_uint(v[i]);
-#pragma unroll
-      for (int i = 3 + NV; i < PW; i++) o[i] = 0u;
-      uint32_t* pp = P.pieces + (size_t)slot * PW;
-#pragma unroll
-      for (int q = 0; q < PW / 4; q++) *reinterpret_cast<uint4*>(pp + 4 * q) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-      if (xend < xe) {
-        for (uint32_t k = 0; k < m; k++) {
-#pragma unroll
-          for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
-        }
+        for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
       }
-      x = xend;
+      uint32_t* ck = P.ckpts + (size_t)(cbase + k) * KW;
+      uint32_t w[KW];
+#pragma unroll
+      for (int i = 0; i < KW; i++) w[i] = i < NV ? __float_as_uint(v[i]) : 0u;
+#pragma unroll
+      for (int q = 0; q < KW / 2; q++) *reinterpret_cast<uint2*>(ck + 2 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
+      k++;
     }
   }
 }
 
 // =============================================================================================
-// K4: per-tile sort of the bin by submission key, in shared memory (bitonic). Produces, for each
-// bin, the permutation `order[off + i]` = local index of the i-th piece in submission order.
-// Pieces of one triangle never share a pixel, so ties between equal keys need no order.
+// K6: per-tile sort of the bin by submission key (bitonic). Small bins: one WARP per tile, keys in
+// that warp's shared-memory slice (<= 32 entries: registers + shuffles only). Large bins: one
+// block per tile with a large shared-memory buffer.
 // =============================================================================================
-template <int LT, uint32_t CAP>
-__global__ void __launch_bounds__(256) k_bin_sort(PassParams P, int big) {
-  constexpr int PW = Rec<LT>::PW;
-  extern __shared__ unsigned long long sk[];
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+  return __shfl_xor_sync(0xFFFFFFFFu, v, m);
+}
+
+#define RF_SORT_WARPS 4
+__global__ void __launch_bounds__(RF_SORT_WARPS * 32) k_bin_sort_warp(PassParams P) {
+  __shared__ unsigned long long sk_all[RF_SORT_WARPS][RF_SORT_SMALL];
   if (P.cstatus->poison) return;
-  const uint32_t n_work = big ? P.status->n_work_big : P.status->n_work;
-  const uint32_t* wl = big ? P.worklist_big : P.worklist;
-  for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-    const uint32_t tile = wl[wi];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  unsigned long long* sk = sk_all[warp];
+  const uint32_t n_work = P.status->n_work;
+  const uint32_t gw = blockIdx.x * RF_SORT_WARPS + warp, nw = gridDim.x * RF_SORT_WARPS;
+  for (uint32_t wi = gw; wi < n_work; wi += nw) {
+    const uint32_t tile = P.worklist[wi];
     const uint32_t cnt = P.tile_cnt[tile], off = P.tile_off[tile];
-    if (!big && cnt > RF_SORT_SMALL) continue;  // the big pass handles it
-    if (cnt > CAP) continue;                    // flagged RF_ERRBIT_BIN_TOO_DEEP
+    if (cnt <= 1 || cnt > RF_SORT_SMALL) continue;
+    unsigned long long* bin = P.bins + off;
+    if (cnt <= 32) {
+      unsigned long long v = lane < cnt ? bin[lane] : ~0ull;
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const unsigned long long o = shfl_xor_u64(v, j);
+          const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+          const bool take_min = up == lower;
+          v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+        }
+      }
+      if (lane < cnt) bin[lane] = v;
+      continue;
+    }
+    uint32_t n2 = 64;
+    while (n2 < cnt) n2 <<= 1;
+    for (uint32_t i = lane; i < n2; i += 32) sk[i] = i < cnt ? bin[i] : ~0ull;
+    __syncwarp();
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t p = lane; p < (n2 >> 1); p += 32) {
+          const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1));  // index with bit j clear
+          const uint32_t l = i | j;
+          const unsigned long long a = sk[i], b = sk[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { sk[i] = b; sk[l] = a; }
+        }
+        __syncwarp();
+      }
+    }
+    for (uint32_t i = lane; i < cnt; i += 32) bin[i] = sk[i];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bin_sort_big(PassParams P) {
+  extern __shared__ unsigned long long skb[];
+  if (P.cstatus->poison) return;
+  const uint32_t n_work = P.status->n_work_big;
+  for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const uint32_t tile = P.worklist_big[wi];
+    const uint32_t cnt = P.tile_cnt[tile], off = P.tile_off[tile];
+    if (cnt > RF_SORT_BIG) continue;  // flagged RF_ERRBIT_BIN_TOO_DEEP
+    unsigned long long* bin = P.bins + off;
     uint32_t n2 = 1;
     while (n2 < cnt) n2 <<= 1;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x)
-      sk[i] = i < cnt ? ((unsigned long long)P.pieces[(size_t)(off + i) * PW] << 32 | i) : ~0ull;
+    for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) skb[i] = i < cnt ? bin[i] : ~0ull;
     __syncthreads();
     for (uint32_t k = 2; k <= n2; k <<= 1) {
       for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
-          const uint32_t l = i ^ j;
-          if (l > i) {
-            const unsigned long long a = sk[i], b = sk[l];
-            const bool up = (i & k) == 0;
-            if ((a > b) == up) { sk[i] = b; sk[l] = a; }
-          }
+        for (uint32_t p = threadIdx.x; p < (n2 >> 1); p += blockDim.x) {
+          const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+          const uint32_t l = i | j;
+          const unsigned long long a = skb[i], b = skb[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { skb[i] = b; skb[l] = a; }
         }
         __syncthreads();
       }
     }
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) P.order[off + i] = (uint32_t)sk[i];
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) bin[i] = skb[i];
   }
 }
 
 // =============================================================================================
-// K5: tile rasteriser. One warp owns one 32x32 tile: colour and depth are staged in shared
-// memory, the tile's pieces are consumed in submission order 32 at a time (one piece per lane,
-// each lane walking its piece pixel by pixel with the reference's sequential adds). Lanes whose
-// pieces overlap on a row are serialised in submission order, which preserves the reference's
-// depth-test and write semantics exactly (first-submitted wins ties, frags.o counts every write).
+// K7: tile rasteriser. One warp owns one 32x32 tile: colour and depth are staged in shared
+// memory; the tile's triangles are taken in submission order, 32 at a time, and expanded into
+// (triangle, row) items — one span piece per lane — each lane walking its piece pixel by pixel
+// with the reference's sequential adds. Lanes whose pieces overlap on a row are serialised in
+// submission order, which preserves the reference's depth-test and write semantics exactly
+// (first-submitted wins ties, frags.o counts every write).
 // =============================================================================================
 #define RF_RASTER_WARPS 4
 
@@ -263,7 +304,7 @@ __device__ __forceinline__ bool shade_fragment(const DrawDesc& D, const float* v
 
 template <int LT>
 __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
-  constexpr int HW = Rec<LT>::HW, PW = Rec<LT>::PW;
+  constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW;
   constexpr int NV = 1 + LT;
   __shared__ uint32_t s_color[RF_RASTER_WARPS][RF_TILE * RF_TILE_PITCH];
   __shared__ float s_depth[RF_RASTER_WARPS][RF_TILE * RF_TILE_PITCH];
@@ -322,106 +363,146 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
     uint32_t acc_draw = 0xFFFFFFFFu;  // warp-uniform draw id of the pending frags.o partial sums
     uint32_t acc_o = 0;               // per-lane partial
 
-    for (uint32_t b0 = 0; b0 < cnt; b0 += 32) {
-      const bool valid = b0 + lane < cnt;
-      uint32_t py = 32 + lane, pxs = 0, pn = 0, draw = 0;
-      float v[NV], dv[NV];
-#pragma unroll
-      for (int i = 0; i < NV; i++) { v[i] = 0.0f; dv[i] = 0.0f; }
-      if (valid) {
-        const uint32_t li = P.order[off + b0 + lane];
-        const uint32_t* pp = P.pieces + (size_t)(off + li) * PW;
-        uint32_t w[PW];
-#pragma unroll
-        for (int q = 0; q < PW / 4; q++) {
-          const uint4 t = __ldg(reinterpret_cast<const uint4*>(pp) + q);
-          w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-        }
-        py = w[1] & 0xFFu; pxs = (w[1] >> 8) & 0xFFu; pn = w[1] >> 16;
-#pragma unroll
-        for (int i = 0; i < NV; i++) v[i] = __uint_as_float(w[3 + i]);
-        const uint32_t* hr = P.halves + (size_t)w[2] * HW;
-        uint32_t hw[HW];
-#pragma unroll
-        for (int q = 0; q < HW / 4; q++) {
-          const uint4 t = __ldg(reinterpret_cast<const uint4*>(hr) + q);
-          hw[4 * q] = t.x; hw[4 * q + 1] = t.y; hw[4 * q + 2] = t.z; hw[4 * q + 3] = t.w;
-        }
-        draw = hw[1];
-#pragma unroll
-        for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(hw[2 + i]);
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+      // ---- lane t: one triangle of this chunk (sorted by submission key)
+      uint32_t t_tri = 0, t_sbase = 0, t_Y0 = 0, t_nU = 0, t_ra = 0, t_rows = 0, t_draw = 0;
+      if (c0 + lane < cnt) {
+        t_tri = (uint32_t)P.bins[off + c0 + lane];
+        const uint32_t* tr = P.tris + (size_t)t_tri * TW;
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(tr));
+        const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(tr + 4));
+        t_draw = h0.y; t_sbase = h0.z; t_Y0 = h0.w; t_nU = h1.x;
+        const uint32_t nrows = h1.x + (h1.y & 0xFFFFu);
+        t_ra = max(t_Y0, py0);
+        const uint32_t rb = min(t_Y0 + nrows, py0 + th);
+        t_rows = rb > t_ra ? rb - t_ra : 0u;
       }
-      // ---- dependencies: earlier lanes on the same row whose x-range overlaps mine
-      uint32_t dep = 0;
-      {
-        uint32_t m = __match_any_sync(0xFFFFFFFFu, py) & lanemask_lt();
-        while (__any_sync(0xFFFFFFFFu, m != 0)) {
-          const int j = m ? (__ffs(m) - 1) : (int)lane;
-          const uint32_t ox = __shfl_sync(0xFFFFFFFFu, pxs, j), on = __shfl_sync(0xFFFFFFFFu, pn, j);
-          if (m) {
-            if (pxs < ox + on && ox < pxs + pn) dep |= 1u << j;
-            m &= m - 1;
+      const uint32_t t_incl = warp_scan_incl(t_rows);
+      const uint32_t n_items = __shfl_sync(0xFFFFFFFFu, t_incl, 31);
+
+      for (uint32_t ib = 0; ib < n_items; ib += 32) {
+        const uint32_t item = ib + lane;
+        bool valid = item < n_items;
+        // owner triangle lane: number of lanes whose inclusive end <= item
+        uint32_t ot = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const uint32_t cand = ot + step;
+          const uint32_t e = __shfl_sync(0xFFFFFFFFu, t_incl, (cand - 1) & 31);
+          if (cand <= 32 && e <= item) ot = cand;
+        }
+        ot &= 31u;
+        const uint32_t o_incl = __shfl_sync(0xFFFFFFFFu, t_incl, ot), o_rows = __shfl_sync(0xFFFFFFFFu, t_rows, ot);
+        const uint32_t o_ra = __shfl_sync(0xFFFFFFFFu, t_ra, ot), o_Y0 = __shfl_sync(0xFFFFFFFFu, t_Y0, ot);
+        const uint32_t o_sbase = __shfl_sync(0xFFFFFFFFu, t_sbase, ot), o_nU = __shfl_sync(0xFFFFFFFFu, t_nU, ot);
+        const uint32_t o_tri = __shfl_sync(0xFFFFFFFFu, t_tri, ot), o_draw = __shfl_sync(0xFFFFFFFFu, t_draw, ot);
+
+        uint32_t py = 32 + lane, pxs = 0, pn = 0, draw = 0;
+        float v[NV], dv[NV];
+#pragma unroll
+        for (int i = 0; i < NV; i++) { v[i] = 0.0f; dv[i] = 0.0f; }
+        if (valid) {
+          const uint32_t Y = o_ra + (item - (o_incl - o_rows));
+          const uint32_t j = Y - o_Y0;
+          const uint32_t* sp = P.spans + (size_t)(o_sbase + j) * SW;
+          uint32_t w[SW];
+#pragma unroll
+          for (int q = 0; q < SW / 2; q++) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp) + q);
+            w[2 * q] = t.x; w[2 * q + 1] = t.y;
           }
-        }
-      }
-      // ---- frags.o bookkeeping: flush partial sums when the draw changes
-      const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, draw, __ffs(__ballot_sync(0xFFFFFFFFu, valid)) - 1);
-      const bool uni = __all_sync(0xFFFFFFFFu, !valid || draw == d0);
-      if (!uni || d0 != acc_draw) {
-        if (acc_draw != 0xFFFFFFFFu) {
-          uint32_t s = acc_o;
+          const uint32_t X0 = w[0] & 0xFFFFu, n = w[0] >> 16;
+          const uint32_t xs = max(X0, px0), xe = min(X0 + n, px0 + tw);
+          if (n == 0 || xs >= xe) valid = false;
+          else {
+            py = Y - py0; pxs = xs - px0; pn = xe - xs; draw = o_draw;
+            if (xs > X0) {  // the span started in an earlier tile column: take the checkpoint at this column
+              const uint32_t* ck = P.ckpts + (size_t)(w[1] + (tx - (X0 >> RF_TILE_SHIFT) - 1)) * KW;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-          if (lane == 0 && s) atomicAdd(&P.dstats[acc_draw].frags_o, (unsigned long long)s);
-        }
-        acc_o = 0;
-        acc_draw = uni ? d0 : 0xFFFFFFFFu;
-      }
-      uint32_t my_o = 0;
-
-      const DrawDesc& D = P.draws[draw];
-      const uint32_t flags = valid ? D.flags : 0u;
-      const uint32_t pmask = valid ? D.persp_mask : 0u;
-      const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
-      const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
-
-      uint32_t done = ~__ballot_sync(0xFFFFFFFFu, valid);
-      bool pending = valid;
-      while (done != 0xFFFFFFFFu) {
-        const bool ready = pending && (dep & ~done) == 0;
-        uint32_t maxn = ready ? pn : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xFFFFFFFFu, maxn, o));
-        if (ready) {
-          const uint32_t base = py * RF_TILE_PITCH + pxs;
-          for (uint32_t k = 0; k < pn; k++) {
-            const float z = v[0];
-            bool pass = true;  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
-            if (dtest != RF_DEPTH_NONE) {
-              const float curr = sz[base + k];
-              pass = dtest == RF_DEPTH_LESS ? (curr < z) : (dtest == RF_DEPTH_EQUAL ? (curr == z) : (curr > z));
-            }
-            if (pass) {
-              float var[LT];
-#pragma unroll
-              for (int i = 0; i < LT; i++) var[i] = ((pmask >> i) & 1u) ? v[1 + i] / z : v[1 + i];  // raster.rs:60-69
-              uint32_t r = 0, g = 0, bl = 0, a = 0;
-              if (shade_fragment<LT>(D, var, r, g, bl, a)) {
-                if (cwrite) { my_o++; sc[base + k] = pack_pixel(T.fmt, r, g, bl, a); }
-                if (dwrite) sz[base + k] = z;
+              for (int q = 0; q < KW / 2; q++) {
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(ck) + q);
+                if (2 * q < NV) v[2 * q] = __uint_as_float(t.x);
+                if (2 * q + 1 < NV) v[2 * q + 1] = __uint_as_float(t.y);
               }
-            }
+            } else {
 #pragma unroll
-            for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
+              for (int i = 0; i < NV; i++) v[i] = __uint_as_float(w[2 + i]);
+            }
+            const uint32_t* dp = P.tris + (size_t)o_tri * TW + 6 + (j >= o_nU ? NV : 0);
+#pragma unroll
+            for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(__ldg(dp + i));
           }
         }
-        (void)maxn;
-        __syncwarp();
-        done |= __ballot_sync(0xFFFFFFFFu, ready);
-        if (ready) pending = false;
+        const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (vmask == 0) continue;
+        // ---- dependencies: earlier lanes on the same row whose x-range overlaps mine
+        uint32_t dep = 0;
+        {
+          uint32_t m = __match_any_sync(0xFFFFFFFFu, py) & lanemask_lt();
+          while (__any_sync(0xFFFFFFFFu, m != 0)) {
+            const int jj = m ? (__ffs(m) - 1) : (int)lane;
+            const uint32_t ox = __shfl_sync(0xFFFFFFFFu, pxs, jj), on = __shfl_sync(0xFFFFFFFFu, pn, jj);
+            if (m) {
+              if (pxs < ox + on && ox < pxs + pn) dep |= 1u << jj;
+              m &= m - 1;
+            }
+          }
+        }
+        // ---- frags.o bookkeeping: flush partial sums when the draw changes
+        const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, draw, __ffs(vmask) - 1);
+        const bool uni = __all_sync(0xFFFFFFFFu, !valid || draw == d0);
+        if (!uni || d0 != acc_draw) {
+          if (acc_draw != 0xFFFFFFFFu) {
+            uint32_t s = acc_o;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+            if (lane == 0 && s) atomicAdd(&P.dstats[acc_draw].frags_o, (unsigned long long)s);
+          }
+          acc_o = 0;
+          acc_draw = uni ? d0 : 0xFFFFFFFFu;
+        }
+        uint32_t my_o = 0;
+
+        const DrawDesc& D = P.draws[draw];
+        const uint32_t flags = valid ? D.flags : 0u;
+        const uint32_t pmask = valid ? D.persp_mask : 0u;
+        const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
+        const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
+
+        uint32_t done = ~vmask;
+        bool pending = valid;
+        while (done != 0xFFFFFFFFu) {
+          const bool ready = pending && (dep & ~done) == 0;
+          if (ready) {
+            const uint32_t base = py * RF_TILE_PITCH + pxs;
+            for (uint32_t k = 0; k < pn; k++) {
+              const float z = v[0];
+              bool pass = true;  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
+              if (dtest != RF_DEPTH_NONE) {
+                const float curr = sz[base + k];
+                pass = dtest == RF_DEPTH_LESS ? (curr < z) : (dtest == RF_DEPTH_EQUAL ? (curr == z) : (curr > z));
+              }
+              if (pass) {
+                float var[LT];
+#pragma unroll
+                for (int i = 0; i < LT; i++) var[i] = ((pmask >> i) & 1u) ? v[1 + i] / z : v[1 + i];  // raster.rs:60-69
+                uint32_t r = 0, g = 0, bl = 0, a = 0;
+                if (shade_fragment<LT>(D, var, r, g, bl, a)) {
+                  if (cwrite) { my_o++; sc[base + k] = pack_pixel(T.fmt, r, g, bl, a); }
+                  if (dwrite) sz[base + k] = z;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
+            }
+          }
+          __syncwarp();
+          done |= __ballot_sync(0xFFFFFFFFu, ready);
+          if (ready) pending = false;
+        }
+        if (uni) acc_o += my_o;
+        else if (my_o) atomicAdd(&P.dstats[draw].frags_o, (unsigned long long)my_o);
       }
-      if (uni) acc_o += my_o;
-      else if (my_o) atomicAdd(&P.dstats[draw].frags_o, (unsigned long long)my_o);
     }
     if (acc_draw != 0xFFFFFFFFu) {
       uint32_t s = acc_o;
@@ -453,4 +534,18 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
     }
     __syncwarp();
   }
+}
+
+// =============================================================================================
+// Frame::clear (front/src/lib.rs:103-120) for every target cleared at the head of a pass, in one
+// launch: blockIdx.y selects the buffer, 128-bit stores.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_clear_multi(const ClearDesc* __restrict__ cl, const CtxStatus* cs) {
+  if (cs->poison) return;
+  const ClearDesc c = cl[blockIdx.y];
+  const size_t n4 = c.n >> 2;
+  uint4* p4 = reinterpret_cast<uint4*>(c.ptr);
+  const uint4 v4 = make_uint4(c.value, c.value, c.value, c.value);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p4[i] = v4;
+  for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < c.n; i += (size_t)gridDim.x * blockDim.x) c.ptr[i] = c.value;
 }
