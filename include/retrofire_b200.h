@@ -196,7 +196,7 @@ rf_status rf_ctx_last_pass(rf_ctx* ctx, uint64_t* time_ns, uint32_t* n_launches)
 
 
 /* ---- measurement (Stats::start/finish analogue, render/stats.rs:57-78, per kernel) ----------- */
-#define RF_N_KERNELS 8 /* kernels launched by one pass, in order; see rf_kernel_name */
+#define RF_N_KERNELS 10 /* kernels launched by one pass, in order; see rf_kernel_name */
 /* enable=1: record CUDA events between the pass kernels (on the ctx stream). Resets the sums. */
 rf_status rf_ctx_profile(rf_ctx* ctx, int enable);
 /* Device time (ns) and launch count per kernel accumulated since the last call; resets them. */

@@ -2,7 +2,7 @@
 //
 // A "pass" is every draw queued between two flush points, executed in submission order by
 // one chain of kernels:
-//   [k_clear_multi] -> k_vertex -> k_prim -> k_bin_alloc -> k_bin_scatter -> k_ckpt -> k_bin_sort_* -> k_raster
+//   [k_clear_multi] -> k_vertex -> k_setup -> k_edge_ckpt -> k_walk -> k_bin_alloc -> k_bin_scatter -> k_ckpt -> k_bin_sort_* -> k_raster
 // Passes are launched asynchronously on the ctx stream and validated lazily (capacity overflow
 // or device-detected errors) at the next synchronisation point; an overflowing pass poisons
 // the ctx on the device so that later passes become no-ops until the host has grown the
@@ -126,10 +126,10 @@ struct rf_ctx {
   std::vector<int> flight;     // slots launched and not yet validated, oldest first
 
   // scratch arenas shared by all passes (stream order makes reuse safe)
-  DevBuf cv, spans, tris, entries, bins, longlist, ckpts, tiles, cursors;
+  DevBuf cv, spans, tris, entries, bins, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
   // capacities: spans/tris/ckpts in 32-bit WORDS (record width depends on the pass's lane count),
   // entries and long spans in records
-  size_t capw_spans = 0, capw_tris = 0, capw_ckpts = 0, cap_entries = 0, cap_long = 0;
+  size_t capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
   CtxStatus* d_cstatus = nullptr;
   DevBuf bounce;               // upload/download staging on the device
   PinnedBuf h_bounce;
@@ -169,6 +169,11 @@ size_t words_cv(int lt) { return lt == 3 ? Rec<3>::CVS : lt == 5 ? Rec<5>::CVS :
 size_t words_span(int lt) { return lt == 3 ? Rec<3>::SW : lt == 5 ? Rec<5>::SW : Rec<8>::SW; }
 size_t words_tri(int lt) { return lt == 3 ? Rec<3>::TW : lt == 5 ? Rec<5>::TW : Rec<8>::TW; }
 size_t words_ckpt(int lt) { return lt == 3 ? Rec<3>::KW : lt == 5 ? Rec<5>::KW : Rec<8>::KW; }
+size_t words_eck(int lt) { return lt == 3 ? Rec<3>::EW : lt == 5 ? Rec<5>::EW : Rec<8>::EW; }
+
+struct ArenaWants {  // spans/tris/ckpts/ecks in words, the rest in records
+  size_t w_spans, w_tris, w_ckpts, w_ecks, entries, longs, chunks, tall;
+};
 
 // ---- small utility kernels --------------------------------------------------------------------
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n, const CtxStatus* cs) {
@@ -225,7 +230,11 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   mark();
   k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
   mark();
-  k_prim<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+  k_setup<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+  mark();
+  k_edge_ckpt<LT><<<sm * 4, 128, 0, st>>>(P);
+  mark();
+  k_walk<LT><<<sm * 12, 128, 0, st>>>(P);
   mark();
   k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, st>>>(P);
   mark();
@@ -243,20 +252,27 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
 }
 
 // Any growth frees memory that in-flight kernels might still use -> callers guarantee idleness.
-rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, size_t ww_spans, size_t ww_tris, size_t ww_ckpts, size_t w_entries,
-                        size_t w_long) {
+rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const ArenaWants& w) {
   if (!c->cv.reserve(nv * words_cv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "clip-vertex arena");
-  if (ww_spans > c->capw_spans) { if (!c->spans.reserve(ww_spans * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->capw_spans = ww_spans; }
-  if (ww_tris > c->capw_tris) { if (!c->tris.reserve(ww_tris * 4)) return fail(c, RF_E_NOMEM, "triangle arena"); c->capw_tris = ww_tris; }
-  if (ww_ckpts > c->capw_ckpts) { if (!c->ckpts.reserve(ww_ckpts * 4)) return fail(c, RF_E_NOMEM, "checkpoint arena"); c->capw_ckpts = ww_ckpts; }
-  if (w_entries > c->cap_entries) {
-    if (!c->entries.reserve(w_entries * 16) || !c->bins.reserve(w_entries * 8)) return fail(c, RF_E_NOMEM, "bin arena");
-    c->cap_entries = w_entries;
+  if (w.w_spans > c->capw_spans) { if (!c->spans.reserve(w.w_spans * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->capw_spans = w.w_spans; }
+  if (w.w_tris > c->capw_tris) { if (!c->tris.reserve(w.w_tris * 4)) return fail(c, RF_E_NOMEM, "triangle arena"); c->capw_tris = w.w_tris; }
+  if (w.w_ckpts > c->capw_ckpts) { if (!c->ckpts.reserve(w.w_ckpts * 4)) return fail(c, RF_E_NOMEM, "checkpoint arena"); c->capw_ckpts = w.w_ckpts; }
+  if (w.w_ecks > c->capw_ecks) { if (!c->ecks.reserve(w.w_ecks * 4)) return fail(c, RF_E_NOMEM, "edge checkpoint arena"); c->capw_ecks = w.w_ecks; }
+  if (w.entries > c->cap_entries) {
+    if (!c->entries.reserve(w.entries * 16) || !c->bins.reserve(w.entries * 8)) return fail(c, RF_E_NOMEM, "bin arena");
+    c->cap_entries = w.entries;
   }
-  if (w_long > c->cap_long) { if (!c->longlist.reserve(w_long * 8)) return fail(c, RF_E_NOMEM, "long-span list"); c->cap_long = w_long; }
+  if (w.longs > c->cap_long) { if (!c->longlist.reserve(w.longs * 8)) return fail(c, RF_E_NOMEM, "long-span list"); c->cap_long = w.longs; }
+  if (w.chunks > c->cap_chunks) { if (!c->chunks.reserve(w.chunks * 8)) return fail(c, RF_E_NOMEM, "chunk list"); c->cap_chunks = w.chunks; }
+  if (w.tall > c->cap_tall) { if (!c->talllist.reserve(w.tall * 4)) return fail(c, RF_E_NOMEM, "tall list"); c->cap_tall = w.tall; }
   if (!c->tiles.reserve(n_tiles * 5 * 4 + 64)) return fail(c, RF_E_NOMEM, "tile arrays");
   if (!c->cursors.reserve(64)) return fail(c, RF_E_NOMEM, "cursors");
   return RF_OK;
+}
+
+bool arenas_cover(const rf_ctx* c, const ArenaWants& w) {
+  return w.w_spans <= c->capw_spans && w.w_tris <= c->capw_tris && w.w_ckpts <= c->capw_ckpts && w.w_ecks <= c->capw_ecks &&
+         w.entries <= c->cap_entries && w.longs <= c->cap_long && w.chunks <= c->cap_chunks && w.tall <= c->cap_tall;
 }
 
 rf_status wait_idle(rf_ctx* c) {
@@ -292,18 +308,18 @@ rf_status launch_pass(rf_ctx* c, int si) {
   for (auto* t : s.targets) ntiles += ((t->w + RF_TILE - 1) / RF_TILE) * ((t->h + RF_TILE - 1) / RF_TILE);
   s.NV = nv; s.NP = np; s.n_tiles = ntiles;
   // initial arena sizes (grown on demand by validate_all after an overflowing pass)
-  const size_t ww_spans = std::max<size_t>(c->capw_spans, (size_t)8 << 20), ww_tris = std::max<size_t>(c->capw_tris, (size_t)4 << 20);
-  const size_t ww_ckpts = std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), w_entries = std::max<size_t>(c->cap_entries, (size_t)1 << 20);
-  const size_t w_long = std::max<size_t>(c->cap_long, (size_t)1 << 19);
+  ArenaWants want{std::max<size_t>(c->capw_spans, (size_t)8 << 20), std::max<size_t>(c->capw_tris, (size_t)8 << 20),
+                  std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), std::max<size_t>(c->capw_ecks, (size_t)1 << 20),
+                  std::max<size_t>(c->cap_entries, (size_t)1 << 20), std::max<size_t>(c->cap_long, (size_t)1 << 19),
+                  std::max<size_t>(c->cap_chunks, (size_t)1 << 20), std::max<size_t>(c->cap_tall, (size_t)1 << 18)};
   need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 20 + 64 ||
-              ww_spans > c->capw_spans || ww_tris > c->capw_tris || ww_ckpts > c->capw_ckpts || w_entries > c->cap_entries ||
-              w_long > c->cap_long || c->cursors.cap < 64;
+              !arenas_cover(c, want) || c->cursors.cap < 64;
   if (need_idle) { rf_status st = wait_idle(c); if (st) return st; }
   if (!s.d_table.reserve(table_bytes) || !s.d_geom.reserve(std::max<size_t>(s.geom_len, 16)) ||
       !s.d_dstats.reserve(std::max<size_t>(nd * sizeof(DrawStats), 16)) || !s.d_status.reserve(sizeof(PassStatus)) ||
       !s.h_dstats.reserve(std::max<size_t>(nd * sizeof(DrawStats), 16)))
     return fail(c, RF_E_NOMEM, "pass buffers");
-  { rf_status st = ensure_arenas(c, lt, nv, ntiles, ww_spans, ww_tris, ww_ckpts, w_entries, w_long); if (st) return st; }
+  { rf_status st = ensure_arenas(c, lt, nv, ntiles, want); if (st) return st; }
 
   // ---- build the table
   uint8_t* tb = s.table.p;
@@ -390,6 +406,12 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.cap_ckpts = (uint32_t)std::min<size_t>(c->capw_ckpts / words_ckpt(lt), 0xFFFFFFF0u);
   P.cap_entries = (uint32_t)std::min<size_t>(c->cap_entries, 0xFFFFFFF0u);
   P.cap_long = (uint32_t)std::min<size_t>(c->cap_long, 0xFFFFFFF0u);
+  P.chunks = static_cast<uint2*>(c->chunks.p);
+  P.talllist = static_cast<uint32_t*>(c->talllist.p);
+  P.ecks = static_cast<uint32_t*>(c->ecks.p);
+  P.cap_chunks = (uint32_t)std::min<size_t>(c->cap_chunks, 0xFFFFFFF0u);
+  P.cap_tall = (uint32_t)std::min<size_t>(c->cap_tall, 0xFFFFFFF0u);
+  P.cap_ecks = (uint32_t)std::min<size_t>(c->capw_ecks / words_eck(lt), 0xFFFFFFF0u);
   uint32_t* ta = static_cast<uint32_t*>(c->tiles.p);
   P.tile_cnt = ta; P.tile_off = ta + ntiles; P.tile_fill = ta + 2 * (size_t)ntiles;
   P.worklist = ta + 3 * (size_t)ntiles; P.worklist_big = ta + 4 * (size_t)ntiles;
@@ -430,13 +452,15 @@ rf_status validate_all(rf_ctx* c) {
       { rf_status st = wait_idle(c); if (st) return st; }
       const int lt = (int)s.lt;
       auto grow = [](size_t cap, unsigned long long need) { return need > cap ? (size_t)(need + need / 4 + 4096) : cap; };
-      const size_t ws = grow(c->capw_spans, ps.spans_needed * words_span(lt));
-      const size_t wt = grow(c->capw_tris, ps.tris_needed * words_tri(lt));
-      const size_t we = grow(c->cap_entries, ps.entries_needed);
-      // long spans / checkpoints are only fully counted once the spans fit; guess from the spans otherwise
-      const size_t wl = grow(c->cap_long, std::max<unsigned long long>(ps.long_needed, ps.spans_needed > c->capw_spans / words_span(lt) ? ps.spans_needed / 8 : 0));
-      const size_t wk = grow(c->capw_ckpts, ps.ckpts_needed * words_ckpt(lt));
-      { rf_status st = ensure_arenas(c, lt, s.NV, s.n_tiles, ws, wt, wk, we, wl); if (st) return st; }
+      // counters downstream of an overflowed stage are incomplete: guess them from the span count
+      const bool early = ps.spans_needed * words_span(lt) > c->capw_spans || ps.tris_needed * words_tri(lt) > c->capw_tris ||
+                         ps.chunks_needed > c->cap_chunks || ps.entries_needed > c->cap_entries;
+      ArenaWants w{grow(c->capw_spans, ps.spans_needed * words_span(lt)), grow(c->capw_tris, ps.tris_needed * words_tri(lt)),
+                   grow(c->capw_ckpts, std::max<unsigned long long>(ps.ckpts_needed, early ? ps.spans_needed / 8 : 0) * words_ckpt(lt)),
+                   grow(c->capw_ecks, ps.ecks_needed * words_eck(lt)), grow(c->cap_entries, ps.entries_needed),
+                   grow(c->cap_long, std::max<unsigned long long>(ps.long_needed, early ? ps.spans_needed / 8 : 0)),
+                   grow(c->cap_chunks, ps.chunks_needed), grow(c->cap_tall, ps.tall_needed)};
+      { rf_status st = ensure_arenas(c, lt, s.NV, s.n_tiles, w); if (st) return st; }
       RF_CUDA(c, cudaMemsetAsync(c->d_cstatus, 0, sizeof(CtxStatus), c->stream));
       std::vector<int> replay = c->flight;
       for (int r : replay) { rf_status st = launch_pass(c, r); if (st) return st; }
@@ -627,7 +651,7 @@ void rf_ctx_destroy(rf_ctx* c) {
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
     for (int e = 0; e <= RF_N_KERNELS; e++) if (s.ev_k[e]) cudaEventDestroy(s.ev_k[e]);
   }
-  c->cv.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->longlist.release(); c->ckpts.release();
+  c->cv.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
   if (c->d_cstatus) cudaFree(c->d_cstatus);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -855,7 +879,7 @@ rf_status rf_ctx_kernel_times(rf_ctx* c, uint64_t* ns, uint64_t* launches) {
 }
 
 const char* rf_kernel_name(uint32_t i) {
-  static const char* names[RF_N_KERNELS] = {"k_vertex", "k_prim", "k_bin_alloc", "k_bin_scatter", "k_ckpt", "k_bin_sort_warp", "k_bin_sort_big", "k_raster"};
+  static const char* names[RF_N_KERNELS] = {"k_vertex", "k_setup", "k_edge_ckpt", "k_walk", "k_bin_alloc", "k_bin_scatter", "k_ckpt", "k_bin_sort_warp", "k_bin_sort_big", "k_raster"};
   return i < RF_N_KERNELS ? names[i] : "";
 }
 

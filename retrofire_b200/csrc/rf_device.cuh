@@ -60,6 +60,9 @@ struct PassStatus {
   unsigned long long spans_needed;    // span records the pass wants (one per scanline of every drawn triangle)
   unsigned long long tris_needed;     // triangle records
   unsigned long long entries_needed;  // bin entry slots (triangle x bounding-box tile)
+  unsigned long long chunks_needed;   // walk chunks (<= 32 rows of one trapezoid half)
+  unsigned long long tall_needed;     // halves with more than one chunk
+  unsigned long long ecks_needed;     // edge checkpoints (state of both edges at each later chunk start)
   unsigned long long long_needed;     // spans that cross a tile-column boundary
   unsigned long long ckpts_needed;    // checkpoint records for those spans
   unsigned long long bins_needed;     // valid bin entries = total size of all tile bins
@@ -92,8 +95,12 @@ struct PassParams {
   float* cv;              // clip verts [NV][CVS]
   uint32_t* spans;        // [cap_spans][SW]   one per scanline, contiguous per triangle
   uint32_t* tris;         // [cap_tris][TW]    per drawn triangle: key, draw, rows, dv/dx of both halves
-  uint4* entries;         // [cap_entries]     {tile | ~0, key, tri, 0}: triangle x bbox-tile slots
+  uint4* entries;         // [cap_entries]     {tile, key, tri, 0}: one per (triangle, overlapped tile)
   unsigned long long* bins;  // [cap_entries]  per-tile lists of (key << 32 | tri), sorted by k_bin_sort
+  uint2* chunks;          // [cap_chunks]      {tri*2+half, chunk index}
+  uint32_t* talllist;     // [cap_tall]        tri*2+half of halves with more than one chunk
+  uint32_t* ecks;         // [cap_ecks][EW]    edge state at the start of chunk 1.. of tall halves
+  uint32_t cap_chunks, cap_tall, cap_ecks;
   uint2* longlist;        // [cap_long]        {span index, tri*2+half} of spans crossing a tile-column boundary
   uint32_t* ckpts;        // [cap_ckpts][KW]   varyings of such spans at each later tile-column start
   uint32_t cap_spans, cap_tris, cap_entries, cap_long, cap_ckpts;
@@ -115,7 +122,9 @@ struct PassParams {
 template <int LT> struct Rec {
   static constexpr int CVS = (5 + LT + 3) & ~3;        // clip vert: pos4, oc, attr[LT]            (16 B aligned)
   static constexpr int SW = (2 + 1 + LT + 1) & ~1;     // span: X0|n<<16, ckpt, z, attr[LT]         (8 B aligned)
-  static constexpr int TW = (6 + 2 * (1 + LT) + 3) & ~3;  // tri: key, draw, sbase, Y0, nU, nL|target<<16, dv[2][1+LT]
+  static constexpr int HS = (3 * LT + 8 + 3) & ~3;      // half setup: dv[1+LT], L[2+LT], dl[2+LT], R, dr, y    (16 B aligned)
+  static constexpr int TW = 8 + 2 * HS;                // tri: 8 header words + two half setups (see TriRec)
+  static constexpr int EW = (2 + LT + 1 + 1) & ~1;     // edge checkpoint: L[2+LT], R                        (8 B aligned)
   static constexpr int KW = (1 + LT + 1) & ~1;         // checkpoint: z, attr[LT]                   (8 B aligned)
 };
 

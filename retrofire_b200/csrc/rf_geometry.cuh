@@ -207,90 +207,54 @@ __device__ __forceinline__ void half_setup(float y0, float y1, const float* l0, 
   H.n = sat_u32(y1r - y0r);
 }
 
-// Walk one trapezoid half row by row (ScanlineIter::next, raster.rs:80-114): sequential adds down
-// both edges, one span record per row. Tracks the tile-column range touched in the current tile
-// row and flushes exact bin entries whenever the walk leaves a tile row.
-template <int LT> struct WalkState {
-  uint32_t sidx;        // next span record
-  uint32_t Y;           // current row
-  uint32_t cmin, cmax;  // tile columns touched in the current tile row (cmin > cmax: none)
-  unsigned long long frags_i;
+// ---------------------------------------------------------------------------------------------
+// Triangle record (Rec<LT>::TW words), written by k_setup, read by k_edge_ckpt, k_walk, k_ckpt, k_raster:
+//   [0] key  [1] draw  [2] sbase  [3] Y0  [4] nU  [5] nL | target << 16  [6] eck base half 0  [7] eck base half 1
+//   [8 + h*HS ...] half h: dv[1+LT] (dz/dx, dattr/dx), L[2+LT], dl[2+LT], R, dr, y
+// ---------------------------------------------------------------------------------------------
+template <int LT> struct TriRec {
+  static constexpr int NL = 2 + LT, NV = 1 + LT;
+  static constexpr int HS = Rec<LT>::HS;
+  static constexpr int O_DV = 0, O_L = NV, O_DL = NV + NL, O_R = NV + 2 * NL, O_DR = O_R + 1, O_Y = O_R + 2;
 };
 
+// Conservative tile-column range of a triangle in one tile row, from the closed-form edge lines
+// widened by a margin that bounds the drift of the reference's running sums (|sum_j - (x0 + j*dx)|
+// <= j * 2^-24 * max|x|) plus the half-pixel rounding of round_up_to_half.
 template <int LT>
-__device__ __forceinline__ void flush_tile_row(const PassParams& P, const TargetDesc& T, WalkState<LT>& W, uint32_t trow, uint32_t tr0,
-                                               uint32_t c_lo, uint32_t ncols, uint32_t ebase, uint32_t key, uint32_t tri_idx) {
-  if (W.cmin <= W.cmax && (W.cmin < c_lo || W.cmax >= c_lo + ncols)) atomicOr(&P.status->error, RF_ERRBIT_INTERNAL);
-  uint4* e = P.entries + ebase + (size_t)(trow - tr0) * ncols;
-  const uint32_t tbase = T.tile_base + trow * T.tiles_x;
-  for (uint32_t c = 0; c < ncols; c++) {
-    const uint32_t col = c_lo + c;
-    const bool valid = col >= W.cmin && col <= W.cmax;
-    e[c] = make_uint4(valid ? tbase + col : RF_NO_TILE, key, tri_idx, 0u);
-    if (valid) atomicAdd(P.tile_cnt + tbase + col, 1u);
+__device__ __forceinline__ void tile_row_cols(const HalfSetup<LT>& H0, const HalfSetup<LT>& H1, uint32_t Y0, uint32_t nrows, uint32_t trow,
+                                              float margin, uint32_t tiles_x, uint32_t& ca, uint32_t& cb) {
+  const uint32_t Ya = max(Y0, trow << RF_TILE_SHIFT), Yb = min(Y0 + nrows - 1, (trow << RF_TILE_SHIFT) + RF_TILE - 1);
+  float lo = 3.0e38f, hi = -3.0e38f;
+  const uint32_t nU = H0.n;
+  if (Ya < Y0 + nU) {  // rows of the upper half
+    const float ja = (float)(Ya - Y0), jb = (float)(min(Yb, Y0 + nU - 1) - Y0);
+    lo = fminf(lo, fminf(H0.L[0] + H0.dl[0] * ja, H0.L[0] + H0.dl[0] * jb));
+    hi = fmaxf(hi, fmaxf(H0.R + H0.dr * ja, H0.R + H0.dr * jb));
   }
-  W.cmin = 0xFFFFFFFFu;
-  W.cmax = 0u;
+  if (Yb >= Y0 + nU) {  // rows of the lower half
+    const float ja = (float)(max(Ya, Y0 + nU) - (Y0 + nU)), jb = (float)(Yb - (Y0 + nU));
+    lo = fminf(lo, fminf(H1.L[0] + H1.dl[0] * ja, H1.L[0] + H1.dl[0] * jb));
+    hi = fmaxf(hi, fmaxf(H1.R + H1.dr * ja, H1.R + H1.dr * jb));
+  }
+  const float fa = floorf(lo - 0.5f - margin), fb = floorf(hi + 0.5f + margin);
+  if (!(fa <= fb) || !(fabsf(fa) < 1.0e9f) || !(fabsf(fb) < 1.0e9f)) { ca = 0; cb = tiles_x - 1; return; }  // NaN/inf: whole row
+  ca = min(sat_u32(fa) >> RF_TILE_SHIFT, tiles_x - 1);
+  cb = min(sat_u32(fb) >> RF_TILE_SHIFT, tiles_x - 1);
 }
 
-template <int LT>
-__device__ __forceinline__ void walk_half(const PassParams& P, const TargetDesc& T, HalfSetup<LT>& H, WalkState<LT>& W, uint32_t rows_left_after,
-                                          uint32_t own, uint32_t tr0, uint32_t c_lo, uint32_t ncols, uint32_t ebase, uint32_t key, uint32_t tri_idx) {
-  constexpr int NL = 2 + LT;
-  constexpr int SW = Rec<LT>::SW;
-  float y = H.y;
-  for (uint32_t j = 0; j < H.n; j++) {
-    float v0[NL];
-#pragma unroll
-    for (int i = 0; i < NL; i++) { v0[i] = H.L[i]; H.L[i] = H.L[i] + H.dl[i]; }
-    const float x1 = H.R;
-    H.R = H.R + H.dr;
-    const float x0r = round_up_to_half(v0[0]), x1r = round_up_to_half(x1);
-    const float tx = x0r - v0[0];
-    uint32_t w[SW];
-#pragma unroll
-    for (int i = 1; i < NL; i++) w[2 + (i - 1)] = __float_as_uint(v0[i] + ((v0[i] + H.dv[i]) - v0[i]) * tx);
-#pragma unroll
-    for (int i = 2 + NL - 1; i < SW; i++) w[i] = 0u;
-    const uint32_t cnt = sat_u32(x1r - x0r);
-    const uint32_t Yf = sat_u32(y), X0 = sat_u32(x0r), X1 = max(sat_u32(x1r), X0);
-    uint32_t nn = min(cnt, X1 - X0);
-    if (Yf >= T.h || X1 > T.w) {  // target.rs:148,173-174 (slice index panics)
-      atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
-      nn = 0;
-    } else if (Yf < T.band_y0 || Yf >= T.band_y1) {
-      nn = 0;  // not this GPU's row band
-    } else {
-      W.frags_i += X1 - X0;
-    }
-    if (nn) {
-      const uint32_t ca = X0 >> RF_TILE_SHIFT, cb = (X0 + nn - 1) >> RF_TILE_SHIFT;
-      W.cmin = min(W.cmin, ca);
-      W.cmax = max(W.cmax, cb);
-      if (ca != cb) {  // crosses a tile-column boundary: k_ckpt will add checkpoints
-        const unsigned long long slot = agg_atomic_inc(&P.status->long_needed);
-        if (slot < P.cap_long) P.longlist[slot] = make_uint2(W.sidx, own);
-        else { P.status->overflow = 1; P.cstatus->poison = 1; }
-      }
-    }
-    w[0] = X0 | nn << 16;
-    w[1] = RF_NO_CKPT;
-    uint32_t* sr = P.spans + (size_t)W.sidx * SW;
-#pragma unroll
-    for (int q = 0; q < SW / 2; q++) *reinterpret_cast<uint2*>(sr + 2 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
-    W.sidx++;
-    const bool last = (j + 1 == H.n) && rows_left_after == 0;
-    if (last || ((W.Y + 1) >> RF_TILE_SHIFT) != (W.Y >> RF_TILE_SHIFT))
-      flush_tile_row<LT>(P, T, W, W.Y >> RF_TILE_SHIFT, tr0, c_lo, ncols, ebase, key, tri_idx);
-    W.Y++;
-    y = y + 1.0f;
-  }
-}
+// =============================================================================================
+// K2a k_setup: one thread per input primitive — assembly, clip, to_screen, cull, triangle setup.
+// Emits, with warp-aggregated allocation (warp prefix sums): a triangle record, its span range,
+// its (triangle x tile) bin entries, and its walk chunks (<= 32 rows each).
+// =============================================================================================
+#define RF_CHUNK 32u
 
 template <int LT>
-__global__ void __launch_bounds__(128) k_prim(PassParams P) {
-  constexpr int NL = 2 + LT;
-  constexpr int TW = Rec<LT>::TW;
+__global__ void __launch_bounds__(128) k_setup(PassParams P) {
+  constexpr int NL = 2 + LT, NV = 1 + LT;
+  constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS;
+  using TR = TriRec<LT>;
   if (P.cstatus->poison) return;
   const uint32_t lane = lane_id();
   const uint32_t n_iter = (P.NP + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
@@ -328,14 +292,14 @@ __global__ void __launch_bounds__(128) k_prim(PassParams P) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) max_tri = max(max_tri, __shfl_xor_sync(0xFFFFFFFFu, max_tri, o));
 
-    unsigned long long my_frags_i = 0;
     uint32_t my_prims_o = 0;
 
     for (uint32_t t = 0; t < max_tri; t++) {
       bool emit = false;
       HalfSetup<LT> H0, H1;
       H0.n = H1.n = 0;
-      uint32_t tgt = 0, Y0 = 0, tr0 = 0, c_lo = 0, ncols = 0, nent = 0;
+      uint32_t tgt = 0, Y0 = 0, tr0 = 0, tr1 = 0, tiles_x = 1, nent = 0, nchunk = 0, neck = 0, by0 = 0, by1 = 0;
+      float margin = 0.0f;
       if (t < ntri) {
         const DrawDesc& D = P.draws[d];
         SVert<LT> s[3];
@@ -388,9 +352,9 @@ __global__ void __launch_bounds__(128) k_prim(PassParams P) {
           half_setup<LT>(ty, my, top, left, top, right, H0);
           half_setup<LT>(my, by, left, bot, right, bot, H1);
           const TargetDesc& T = P.targets[D.target];
-          tgt = D.target;
+          tgt = D.target; tiles_x = T.tiles_x; by0 = T.band_y0; by1 = T.band_y1;
           // Row-range sanity. A scanline at y >= h panics in the reference (target.rs:148,173);
-          // RF_MAX_ROWS bounds the loop against absurd coordinates; a negative first row can only
+          // RF_MAX_ROWS bounds the work against absurd coordinates; a negative first row can only
           // come from a viewport outside the target and is rejected (the reference would draw it at row 0).
           uint32_t nrows = H0.n + H1.n;
           if (nrows != 0) {
@@ -407,33 +371,46 @@ __global__ void __launch_bounds__(128) k_prim(PassParams P) {
             else {
               emit = true;
               Y0 = sat_u32(yfirst);
-              tr0 = Y0 >> RF_TILE_SHIFT;
-              const uint32_t tr1 = (Y0 + nrows - 1) >> RF_TILE_SHIFT;
-              const float xmin = fminf(s[0].x, fminf(s[1].x, s[2].x)), xmax = fmaxf(s[0].x, fmaxf(s[1].x, s[2].x));
-              c_lo = min(sat_u32(floorf(xmin) - 1.0f) >> RF_TILE_SHIFT, T.tiles_x - 1);
-              const uint32_t c_hi = min(sat_u32(floorf(xmax) + 1.0f) >> RF_TILE_SHIFT, T.tiles_x - 1);
-              ncols = (c_hi >= c_lo ? c_hi - c_lo : 0u) + 1u;
-              nent = (tr1 - tr0 + 1) * ncols;
+              // only tile rows inside this GPU's row band get bin entries
+              const uint32_t Ya = max(Y0, by0), Yb = min(Y0 + nrows, by1);
+              const float xabs = fmaxf(fmaxf(fabsf(s[0].x), fabsf(s[1].x)), fabsf(s[2].x));
+              margin = 1.0f + (float)nrows * xabs * 1.2e-7f;
+              if (Ya < Yb) {
+                tr0 = Ya >> RF_TILE_SHIFT; tr1 = (Yb - 1) >> RF_TILE_SHIFT;
+                for (uint32_t tr = tr0; tr <= tr1; tr++) {
+                  uint32_t ca, cb;
+                  tile_row_cols<LT>(H0, H1, Y0, nrows, tr, margin, tiles_x, ca, cb);
+                  nent += cb - ca + 1;
+                }
+              } else { tr0 = 1; tr1 = 0; }
+              const uint32_t ch0 = (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = (H1.n + RF_CHUNK - 1) / RF_CHUNK;
+              nchunk = ch0 + ch1;
+              neck = (ch0 ? ch0 - 1 : 0) + (ch1 ? ch1 - 1 : 0);
             }
           }
         }
       }
-      // ---- warp-aggregated allocation (warp prefix sums): span records, triangle records, bin slots
+      // ---- warp-aggregated allocation (warp prefix sums)
       const uint32_t nsp = emit ? (H0.n + H1.n) : 0u;
-      const uint32_t incl_s = warp_scan_incl(nsp);
-      const uint32_t incl_e = warp_scan_incl(nent);
+      const uint32_t incl_s = warp_scan_incl(nsp), incl_e = warp_scan_incl(nent), incl_c = warp_scan_incl(nchunk), incl_k = warp_scan_incl(neck);
       const uint32_t tot_s = __shfl_sync(0xFFFFFFFFu, incl_s, 31), tot_e = __shfl_sync(0xFFFFFFFFu, incl_e, 31);
+      const uint32_t tot_c = __shfl_sync(0xFFFFFFFFu, incl_c, 31), tot_k = __shfl_sync(0xFFFFFFFFu, incl_k, 31);
       const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
-      unsigned long long sb = 0, tb = 0, eb = 0;
+      unsigned long long sb = 0, tb = 0, eb = 0, cb_ = 0, kb = 0;
       if (lane == 0 && emask) {
         sb = atomicAdd(&P.status->spans_needed, (unsigned long long)tot_s);
         tb = atomicAdd(&P.status->tris_needed, (unsigned long long)__popc(emask));
-        eb = atomicAdd(&P.status->entries_needed, (unsigned long long)tot_e);
+        if (tot_e) eb = atomicAdd(&P.status->entries_needed, (unsigned long long)tot_e);
+        cb_ = atomicAdd(&P.status->chunks_needed, (unsigned long long)tot_c);
+        if (tot_k) kb = atomicAdd(&P.status->ecks_needed, (unsigned long long)tot_k);
       }
       sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
       tb = __shfl_sync(0xFFFFFFFFu, tb, 0);
       eb = __shfl_sync(0xFFFFFFFFu, eb, 0);
-      const bool fits = sb + tot_s <= P.cap_spans && tb + __popc(emask) <= P.cap_tris && eb + tot_e <= P.cap_entries;
+      cb_ = __shfl_sync(0xFFFFFFFFu, cb_, 0);
+      kb = __shfl_sync(0xFFFFFFFFu, kb, 0);
+      const bool fits = sb + tot_s <= P.cap_spans && tb + __popc(emask) <= P.cap_tris && eb + tot_e <= P.cap_entries &&
+                        cb_ + tot_c <= P.cap_chunks && kb + tot_k <= P.cap_ecks;
       if (!fits) {
         if (lane == 0 && emask) { P.status->overflow = 1; P.cstatus->poison = 1; }
         continue;  // keep counting what is needed, write nothing
@@ -441,45 +418,250 @@ __global__ void __launch_bounds__(128) k_prim(PassParams P) {
       if (!emit) continue;
       const uint32_t sbase = (uint32_t)sb + (incl_s - nsp);
       const uint32_t tri_idx = (uint32_t)tb + __popc(emask & lanemask_lt());
-      const uint32_t ebase = (uint32_t)eb + (incl_e - nent);
+      uint32_t eidx = (uint32_t)eb + (incl_e - nent);
+      uint32_t cidx = (uint32_t)cb_ + (incl_c - nchunk);
+      const uint32_t kbase = (uint32_t)kb + (incl_k - neck);
       const uint32_t key = gp * 8u + t;
+      const uint32_t ch0 = (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = (H1.n + RF_CHUNK - 1) / RF_CHUNK;
+      const uint32_t eck0 = kbase, eck1 = kbase + (ch0 ? ch0 - 1 : 0);
       {  // triangle record
-        uint32_t w[TW];
-        w[0] = key; w[1] = d; w[2] = sbase; w[3] = Y0; w[4] = H0.n; w[5] = H1.n | (tgt << 16);
-#pragma unroll
-        for (int i = 0; i < 1 + LT; i++) { w[6 + i] = __float_as_uint(H0.dv[1 + i]); w[6 + (1 + LT) + i] = __float_as_uint(H1.dv[1 + i]); }
-#pragma unroll
-        for (int i = 6 + 2 * (1 + LT); i < TW; i++) w[i] = 0u;
         uint32_t* tr = P.tris + (size_t)tri_idx * TW;
+        *reinterpret_cast<uint4*>(tr) = make_uint4(key, d, sbase, Y0);
+        *reinterpret_cast<uint4*>(tr + 4) = make_uint4(H0.n, H1.n | (tgt << 16), eck0, eck1);
 #pragma unroll
-        for (int q = 0; q < TW / 4; q++) *reinterpret_cast<uint4*>(tr + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        for (int hh = 0; hh < 2; hh++) {
+          const HalfSetup<LT>& H = hh ? H1 : H0;
+          uint32_t w[HS];
+#pragma unroll
+          for (int i = 0; i < HS; i++) w[i] = 0u;
+#pragma unroll
+          for (int i = 0; i < NV; i++) w[TR::O_DV + i] = __float_as_uint(H.dv[1 + i]);
+#pragma unroll
+          for (int i = 0; i < NL; i++) { w[TR::O_L + i] = __float_as_uint(H.L[i]); w[TR::O_DL + i] = __float_as_uint(H.dl[i]); }
+          w[TR::O_R] = __float_as_uint(H.R); w[TR::O_DR] = __float_as_uint(H.dr); w[TR::O_Y] = __float_as_uint(H.y);
+          // lane 0 of dv (dx/dx) is needed by the walk's x-alignment of... nothing: alignment uses dv of every other lane only
+#pragma unroll
+          for (int q = 0; q < HS / 4; q++) *reinterpret_cast<uint4*>(tr + 8 + hh * HS + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        }
       }
-      const TargetDesc& T = P.targets[tgt];
-      WalkState<LT> W;
-      W.sidx = sbase; W.Y = Y0; W.cmin = 0xFFFFFFFFu; W.cmax = 0u; W.frags_i = 0;
-      walk_half<LT>(P, T, H0, W, H1.n, tri_idx * 2u, tr0, c_lo, ncols, ebase, key, tri_idx);
-      walk_half<LT>(P, T, H1, W, 0u, tri_idx * 2u + 1u, tr0, c_lo, ncols, ebase, key, tri_idx);
-      my_frags_i += W.frags_i;
+      // bin entries: every tile of the conservative per-tile-row column range
+      if (nent) {
+        const TargetDesc& T = P.targets[tgt];
+        for (uint32_t tr = tr0; tr <= tr1; tr++) {
+          uint32_t ca, cb;
+          tile_row_cols<LT>(H0, H1, Y0, H0.n + H1.n, tr, margin, tiles_x, ca, cb);
+          const uint32_t tbase = T.tile_base + tr * tiles_x;
+          for (uint32_t c = ca; c <= cb; c++) {
+            P.entries[eidx++] = make_uint4(tbase + c, key, tri_idx, 0u);
+            atomicAdd(P.tile_cnt + tbase + c, 1u);
+          }
+        }
+      }
+      // walk chunks (and the list of tall halves that need edge checkpoints)
+      for (uint32_t c = 0; c < ch0; c++) P.chunks[cidx++] = make_uint2(tri_idx * 2u, c);
+      for (uint32_t c = 0; c < ch1; c++) P.chunks[cidx++] = make_uint2(tri_idx * 2u + 1u, c);
+      if (ch0 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
+      if (ch1 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u + 1u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
     }
-    // ---- per-draw stats: aggregate over the warp when every lane has the same draw
+    // ---- per-draw prims.o: aggregate over the warp when every lane has the same draw
     {
       const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d, 0);
       const bool uniform = __all_sync(0xFFFFFFFFu, !have || d == d0);
       if (uniform) {
-        unsigned long long fi = my_frags_i;
         uint32_t po = my_prims_o;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          fi += __shfl_xor_sync(0xFFFFFFFFu, fi, o);
-          po += __shfl_xor_sync(0xFFFFFFFFu, po, o);
+        for (int o = 16; o > 0; o >>= 1) po += __shfl_xor_sync(0xFFFFFFFFu, po, o);
+        if (lane == 0 && po) atomicAdd(&P.dstats[d0].prims_o, (unsigned long long)po);
+      } else if (have && my_prims_o) {
+        atomicAdd(&P.dstats[d].prims_o, (unsigned long long)my_prims_o);
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// K2b k_edge_ckpt: for halves taller than one chunk, walk ONLY the running sums of both edges
+// (the reference's sequential adds, raster.rs:88-104) and store the state at every chunk start,
+// so that k_walk can process all chunks of a tall triangle in parallel. One thread per tall half.
+// =============================================================================================
+template <int LT>
+__global__ void __launch_bounds__(128) k_edge_ckpt(PassParams P) {
+  constexpr int NL = 2 + LT;
+  constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS, EW = Rec<LT>::EW;
+  using TR = TriRec<LT>;
+  if (P.cstatus->poison) return;
+  const uint32_t nt = (uint32_t)min(P.status->tall_needed, (unsigned long long)P.cap_tall);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) {
+    const uint32_t own = P.talllist[i];
+    const uint32_t* tr = P.tris + (size_t)(own >> 1) * TW;
+    const uint32_t hh = own & 1u;
+    const uint32_t n = hh ? (tr[5] & 0xFFFFu) : tr[4];
+    const uint32_t ebase = tr[6 + hh];
+    const uint32_t* hs = tr + 8 + hh * HS;
+    float L[NL], dl[NL];
+#pragma unroll
+    for (int k = 0; k < NL; k++) { L[k] = __uint_as_float(hs[TR::O_L + k]); dl[k] = __uint_as_float(hs[TR::O_DL + k]); }
+    float R = __uint_as_float(hs[TR::O_R]);
+    const float dr = __uint_as_float(hs[TR::O_DR]);
+    uint32_t c = 0;
+    for (uint32_t j = 0; j + RF_CHUNK < n; j += RF_CHUNK) {
+      for (uint32_t r = 0; r < RF_CHUNK; r++) {
+#pragma unroll
+        for (int k = 0; k < NL; k++) L[k] = L[k] + dl[k];
+        R = R + dr;
+      }
+      uint32_t* e = P.ecks + (size_t)(ebase + c) * EW;
+      uint32_t w[EW];
+#pragma unroll
+      for (int k = 0; k < EW; k++) w[k] = k < NL ? __float_as_uint(L[k]) : (k == NL ? __float_as_uint(R) : 0u);
+#pragma unroll
+      for (int q = 0; q < EW / 2; q++) *reinterpret_cast<uint2*>(e + 2 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
+      c++;
+    }
+  }
+}
+
+// =============================================================================================
+// K2c k_walk: ScanlineIter::next (raster.rs:80-114) for every row of every drawn triangle, one ROW
+// per lane. A warp takes 32 chunks (<= 32 rows each), expands them to rows with a warp prefix sum,
+// and every lane brings its row's edge state up to date with r sequential adds from the chunk
+// start (r < 32) — the same additions, in the same order, as the reference's running sums.
+// Emits one span record per row; spans crossing a tile column go to the long list for k_ckpt.
+// =============================================================================================
+template <int LT>
+__global__ void __launch_bounds__(128) k_walk(PassParams P) {
+  constexpr int NL = 2 + LT;
+  constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS, EW = Rec<LT>::EW, SW = Rec<LT>::SW;
+  using TR = TriRec<LT>;
+  if (P.cstatus->poison) return;
+  const uint32_t lane = lane_id();
+  const uint32_t nch = (uint32_t)min(P.status->chunks_needed, (unsigned long long)P.cap_chunks);
+  const uint32_t wpb = blockDim.x >> 5;
+  const uint32_t n_warps = gridDim.x * wpb;
+  for (uint32_t cb = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 32u; cb < nch; cb += n_warps * 32u) {
+    // lane c: one chunk
+    uint32_t c_own = 0, c_idx = 0, c_rows = 0, c_sidx = 0, c_Y = 0, c_draw = 0, c_tgt = 0, c_eck = 0;
+    if (cb + lane < nch) {
+      const uint2 ch = __ldg(P.chunks + cb + lane);
+      c_own = ch.x; c_idx = ch.y;
+      const uint32_t* tr = P.tris + (size_t)(c_own >> 1) * TW;
+      const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(tr));
+      const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(tr + 4));
+      const uint32_t hh = c_own & 1u, nU = h1.x, nL = h1.y & 0xFFFFu;
+      const uint32_t n = hh ? nL : nU;
+      c_rows = min(RF_CHUNK, n - c_idx * RF_CHUNK);
+      const uint32_t row0 = (hh ? nU : 0u) + c_idx * RF_CHUNK;  // row index inside the triangle
+      c_sidx = h0.z + row0; c_Y = h0.w + row0; c_draw = h0.y; c_tgt = h1.y >> 16;
+      c_eck = (hh ? h1.w : h1.z) + c_idx - 1;  // valid when c_idx > 0
+    }
+    const uint32_t incl = warp_scan_incl(c_rows);
+    const uint32_t n_items = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long my_frags_i = 0;
+    uint32_t my_draw = 0xFFFFFFFFu;
+    for (uint32_t ib = 0; ib < n_items; ib += 32) {
+      const uint32_t item = ib + lane;
+      const bool valid = item < n_items;
+      uint32_t oc = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t cand = oc + step;
+        const uint32_t e = __shfl_sync(0xFFFFFFFFu, incl, (cand - 1) & 31);
+        if (cand <= 32 && e <= item) oc = cand;
+      }
+      oc &= 31u;
+      const uint32_t o_incl = __shfl_sync(0xFFFFFFFFu, incl, oc), o_rows = __shfl_sync(0xFFFFFFFFu, c_rows, oc);
+      const uint32_t o_own = __shfl_sync(0xFFFFFFFFu, c_own, oc), o_idx = __shfl_sync(0xFFFFFFFFu, c_idx, oc);
+      const uint32_t o_sidx = __shfl_sync(0xFFFFFFFFu, c_sidx, oc), o_Y = __shfl_sync(0xFFFFFFFFu, c_Y, oc);
+      const uint32_t o_draw = __shfl_sync(0xFFFFFFFFu, c_draw, oc), o_tgt = __shfl_sync(0xFFFFFFFFu, c_tgt, oc);
+      const uint32_t o_eck = __shfl_sync(0xFFFFFFFFu, c_eck, oc);
+      const uint32_t r = valid ? item - (o_incl - o_rows) : 0u;  // row inside the chunk = number of adds
+      float L[NL], dl[NL], dv[NL], R = 0.0f, dr = 0.0f, y = 0.0f;
+#pragma unroll
+      for (int k = 0; k < NL; k++) { L[k] = 0.0f; dl[k] = 0.0f; dv[k] = 0.0f; }
+      if (valid) {
+        const uint32_t* hs = P.tris + (size_t)(o_own >> 1) * TW + 8 + (o_own & 1u) * HS;
+        float buf[HS];
+#pragma unroll
+        for (int q = 0; q < HS / 4; q++) {
+          const uint4 t = __ldg(reinterpret_cast<const uint4*>(hs) + q);
+          buf[4 * q] = __uint_as_float(t.x); buf[4 * q + 1] = __uint_as_float(t.y); buf[4 * q + 2] = __uint_as_float(t.z); buf[4 * q + 3] = __uint_as_float(t.w);
         }
-        if (lane == 0) {
-          if (po) atomicAdd(&P.dstats[d0].prims_o, (unsigned long long)po);
-          if (fi) atomicAdd(&P.dstats[d0].frags_i, fi);
+#pragma unroll
+        for (int k = 0; k < NL; k++) { L[k] = buf[TR::O_L + k]; dl[k] = buf[TR::O_DL + k]; }
+#pragma unroll
+        for (int k = 1; k < NL; k++) dv[k] = buf[TR::O_DV + k - 1];
+        R = buf[TR::O_R]; dr = buf[TR::O_DR];
+        y = buf[TR::O_Y] + (float)(o_idx * RF_CHUNK + r);  // exact: row centres are k + 0.5 below 2^24
+        if (o_idx > 0) {  // chunk start state from the edge checkpoints
+          const uint32_t* e = P.ecks + (size_t)o_eck * EW;
+#pragma unroll
+          for (int q = 0; q < EW / 2; q++) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(e) + q);
+            if (2 * q < NL) L[2 * q] = __uint_as_float(t.x); else if (2 * q == NL) R = __uint_as_float(t.x);
+            if (2 * q + 1 < NL) L[2 * q + 1] = __uint_as_float(t.y); else if (2 * q + 1 == NL) R = __uint_as_float(t.y);
+          }
         }
-      } else if (have) {
-        if (my_prims_o) atomicAdd(&P.dstats[d].prims_o, (unsigned long long)my_prims_o);
-        if (my_frags_i) atomicAdd(&P.dstats[d].frags_i, my_frags_i);
+      }
+      uint32_t maxr = r;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) maxr = max(maxr, __shfl_xor_sync(0xFFFFFFFFu, maxr, o));
+      for (uint32_t j = 0; j < maxr; j++) {  // r sequential adds down both edges
+        if (j < r) {
+#pragma unroll
+          for (int k = 0; k < NL; k++) L[k] = L[k] + dl[k];
+          R = R + dr;
+        }
+      }
+      if (valid) {
+        const TargetDesc& T = P.targets[o_tgt];
+        const float x0r = round_up_to_half(L[0]), x1r = round_up_to_half(R);
+        const float tx = x0r - L[0];
+        uint32_t w[SW];
+#pragma unroll
+        for (int k = 1; k < NL; k++) w[2 + (k - 1)] = __float_as_uint(L[k] + ((L[k] + dv[k]) - L[k]) * tx);
+#pragma unroll
+        for (int k = 2 + NL - 1; k < SW; k++) w[k] = 0u;
+        const uint32_t cnt = sat_u32(x1r - x0r);
+        const uint32_t Yf = sat_u32(y), X0 = sat_u32(x0r), X1 = max(sat_u32(x1r), X0);
+        uint32_t nn = min(cnt, X1 - X0);
+        if (Yf >= T.h || X1 > T.w) {  // target.rs:148,173-174 (slice index panics)
+          atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
+          nn = 0;
+        } else if (Yf < T.band_y0 || Yf >= T.band_y1) {
+          nn = 0;  // not this GPU's row band
+        } else {
+          if (my_draw != o_draw) {
+            if (my_frags_i) atomicAdd(&P.dstats[my_draw].frags_i, my_frags_i);
+            my_frags_i = 0; my_draw = o_draw;
+          }
+          my_frags_i += X1 - X0;
+        }
+        const uint32_t sidx = o_sidx + r;
+        if (nn && ((X0 + nn - 1) >> RF_TILE_SHIFT) != (X0 >> RF_TILE_SHIFT)) {  // crosses a tile column: k_ckpt adds checkpoints
+          const unsigned long long slot = agg_atomic_inc(&P.status->long_needed);
+          if (slot < P.cap_long) P.longlist[slot] = make_uint2(sidx, o_own);
+          else { P.status->overflow = 1; P.cstatus->poison = 1; }
+        }
+        w[0] = X0 | nn << 16;
+        w[1] = RF_NO_CKPT;
+        uint32_t* sr = P.spans + (size_t)sidx * SW;
+#pragma unroll
+        for (int q = 0; q < SW / 2; q++) *reinterpret_cast<uint2*>(sr + 2 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
+        (void)o_Y;
+      }
+    }
+    // ---- frags.i: one atomic per warp when the whole warp worked on one draw
+    {
+      const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, my_draw, 0);
+      const bool uniform = __all_sync(0xFFFFFFFFu, my_draw == d0 || my_frags_i == 0);
+      if (uniform) {
+        unsigned long long fi = my_frags_i;
+        uint32_t dd = my_frags_i ? my_draw : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { fi += __shfl_xor_sync(0xFFFFFFFFu, fi, o); dd = max(dd, __shfl_xor_sync(0xFFFFFFFFu, dd, o)); }
+        if (lane == 0 && fi) atomicAdd(&P.dstats[dd].frags_i, fi);
+      } else if (my_frags_i) {
+        atomicAdd(&P.dstats[my_draw].frags_i, my_frags_i);
       }
     }
   }

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) k_ckpt(PassParams P) {
     float v[NV], dv[NV];
 #pragma unroll
     for (int i = 0; i < NV; i++) v[i] = __uint_as_float(sp[2 + i]);
-    const uint32_t* tr = P.tris + (size_t)(own >> 1) * TW + 6 + (own & 1u) * NV;
+    const uint32_t* tr = P.tris + (size_t)(own >> 1) * TW + 8 + (own & 1u) * Rec<LT>::HS;
 #pragma unroll
     for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(__ldg(tr + i));
     uint32_t x = X0;
@@ -302,6 +302,31 @@ __device__ __forceinline__ bool shade_fragment(const DrawDesc& D, const float* v
   }
 }
 
+// One fragment (target.rs:163-198): depth test -> fragment shader -> colour/depth write.
+// v[0] = interpolated 1/w (the depth value), v[1..] = interpolated varyings. Returns 1 if colour was written.
+template <int LT>
+__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fmt, uint32_t* sc, float* sz, uint32_t idx, const float* v,
+                                                     uint32_t pmask, uint32_t dtest, bool cwrite, bool dwrite) {
+  const float z = v[0];
+  if (dtest != RF_DEPTH_NONE) {  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
+    const float curr = sz[idx];
+    const bool pass = dtest == RF_DEPTH_LESS ? (curr < z) : (dtest == RF_DEPTH_EQUAL ? (curr == z) : (curr > z));
+    if (!pass) return 0u;
+  }
+  float var[LT];
+#pragma unroll
+  for (int i = 0; i < LT; i++) var[i] = ((pmask >> i) & 1u) ? v[1 + i] / z : v[1 + i];  // raster.rs:60-69
+  uint32_t r = 0, g = 0, bl = 0, a = 0;
+  if (!shade_fragment<LT>(D, var, r, g, bl, a)) return 0u;  // discard: no writes at all
+  if (dwrite) sz[idx] = z;
+  if (cwrite) { sc[idx] = pack_pixel(fmt, r, g, bl, a); return 1u; }
+  return 0u;
+}
+
+// Average piece length (pixels) above which a batch of pieces is walked one piece per lane;
+// below it the batch is expanded to one FRAGMENT per lane (each lane does k sequential adds).
+#define RF_SPAN_MODE_MIN_AVG 10u
+
 template <int LT>
 __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
   constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW;
@@ -370,7 +395,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
         t_tri = (uint32_t)P.bins[off + c0 + lane];
         const uint32_t* tr = P.tris + (size_t)t_tri * TW;
         const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(tr));
-        const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(tr + 4));
+        const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(tr + 4));  // nU, nL | target << 16
         t_draw = h0.y; t_sbase = h0.z; t_Y0 = h0.w; t_nU = h1.x;
         const uint32_t nrows = h1.x + (h1.y & 0xFFFFu);
         t_ra = max(t_Y0, py0);
@@ -428,26 +453,13 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
 #pragma unroll
               for (int i = 0; i < NV; i++) v[i] = __uint_as_float(w[2 + i]);
             }
-            const uint32_t* dp = P.tris + (size_t)o_tri * TW + 6 + (j >= o_nU ? NV : 0);
+            const uint32_t* dp = P.tris + (size_t)o_tri * TW + 8 + (j >= o_nU ? Rec<LT>::HS : 0);
 #pragma unroll
             for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(__ldg(dp + i));
           }
         }
         const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
         if (vmask == 0) continue;
-        // ---- dependencies: earlier lanes on the same row whose x-range overlaps mine
-        uint32_t dep = 0;
-        {
-          uint32_t m = __match_any_sync(0xFFFFFFFFu, py) & lanemask_lt();
-          while (__any_sync(0xFFFFFFFFu, m != 0)) {
-            const int jj = m ? (__ffs(m) - 1) : (int)lane;
-            const uint32_t ox = __shfl_sync(0xFFFFFFFFu, pxs, jj), on = __shfl_sync(0xFFFFFFFFu, pn, jj);
-            if (m) {
-              if (pxs < ox + on && ox < pxs + pn) dep |= 1u << jj;
-              m &= m - 1;
-            }
-          }
-        }
         // ---- frags.o bookkeeping: flush partial sums when the draw changes
         const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, draw, __ffs(vmask) - 1);
         const bool uni = __all_sync(0xFFFFFFFFu, !valid || draw == d0);
@@ -463,45 +475,97 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
         }
         uint32_t my_o = 0;
 
-        const DrawDesc& D = P.draws[draw];
-        const uint32_t flags = valid ? D.flags : 0u;
-        const uint32_t pmask = valid ? D.persp_mask : 0u;
-        const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
-        const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
+        const uint32_t f_incl = warp_scan_incl(pn);
+        const uint32_t n_frags = __shfl_sync(0xFFFFFFFFu, f_incl, 31);
 
-        uint32_t done = ~vmask;
-        bool pending = valid;
-        while (done != 0xFFFFFFFFu) {
-          const bool ready = pending && (dep & ~done) == 0;
-          if (ready) {
-            const uint32_t base = py * RF_TILE_PITCH + pxs;
-            for (uint32_t k = 0; k < pn; k++) {
-              const float z = v[0];
-              bool pass = true;  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
-              if (dtest != RF_DEPTH_NONE) {
-                const float curr = sz[base + k];
-                pass = dtest == RF_DEPTH_LESS ? (curr < z) : (dtest == RF_DEPTH_EQUAL ? (curr == z) : (curr > z));
+        if (n_frags >= RF_SPAN_MODE_MIN_AVG * (uint32_t)__popc(vmask)) {
+          // ================= span mode: one piece per lane, walked serially =================
+          // dependencies: earlier lanes on the same row whose x-range overlaps mine
+          uint32_t dep = 0;
+          {
+            uint32_t m = __match_any_sync(0xFFFFFFFFu, py) & lanemask_lt();
+            while (__any_sync(0xFFFFFFFFu, m != 0)) {
+              const int jj = m ? (__ffs(m) - 1) : (int)lane;
+              const uint32_t ox = __shfl_sync(0xFFFFFFFFu, pxs, jj), on = __shfl_sync(0xFFFFFFFFu, pn, jj);
+              if (m) {
+                if (pxs < ox + on && ox < pxs + pn) dep |= 1u << jj;
+                m &= m - 1;
               }
-              if (pass) {
-                float var[LT];
-#pragma unroll
-                for (int i = 0; i < LT; i++) var[i] = ((pmask >> i) & 1u) ? v[1 + i] / z : v[1 + i];  // raster.rs:60-69
-                uint32_t r = 0, g = 0, bl = 0, a = 0;
-                if (shade_fragment<LT>(D, var, r, g, bl, a)) {
-                  if (cwrite) { my_o++; sc[base + k] = pack_pixel(T.fmt, r, g, bl, a); }
-                  if (dwrite) sz[base + k] = z;
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
             }
           }
-          __syncwarp();
-          done |= __ballot_sync(0xFFFFFFFFu, ready);
-          if (ready) pending = false;
+          const DrawDesc& D = P.draws[draw];
+          const uint32_t flags = valid ? D.flags : 0u;
+          const uint32_t pmask = valid ? D.persp_mask : 0u;
+          const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
+          const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
+          uint32_t done = ~vmask;
+          bool pending = valid;
+          while (done != 0xFFFFFFFFu) {
+            const bool ready = pending && (dep & ~done) == 0;
+            if (ready) {
+              const uint32_t base = py * RF_TILE_PITCH + pxs;
+              for (uint32_t k = 0; k < pn; k++) {
+                my_o += process_fragment<LT>(D, T.fmt, sc, sz, base + k, v, pmask, dtest, cwrite, dwrite);
+#pragma unroll
+                for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
+              }
+            }
+            __syncwarp();
+            done |= __ballot_sync(0xFFFFFFFFu, ready);
+            if (ready) pending = false;
+          }
+          if (uni) acc_o += my_o;
+          else if (my_o) atomicAdd(&P.dstats[draw].frags_o, (unsigned long long)my_o);
+        } else {
+          // ================= fragment mode: one fragment per lane =================
+          for (uint32_t fb = 0; fb < n_frags; fb += 32) {
+            const uint32_t f = fb + lane;
+            const bool fvalid = f < n_frags;
+            uint32_t oi = 0;  // owner piece lane: number of lanes whose inclusive end <= f
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+              const uint32_t cand = oi + step;
+              const uint32_t e = __shfl_sync(0xFFFFFFFFu, f_incl, (cand - 1) & 31);
+              if (cand <= 32 && e <= f) oi = cand;
+            }
+            oi &= 31u;
+            const uint32_t o_end = __shfl_sync(0xFFFFFFFFu, f_incl, oi), o_pn = __shfl_sync(0xFFFFFFFFu, pn, oi);
+            const uint32_t o_py = __shfl_sync(0xFFFFFFFFu, py, oi), o_px = __shfl_sync(0xFFFFFFFFu, pxs, oi);
+            const uint32_t fdraw = __shfl_sync(0xFFFFFFFFu, draw, oi);
+            float fv[NV], fd[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) { fv[i] = __shfl_sync(0xFFFFFFFFu, v[i], oi); fd[i] = __shfl_sync(0xFFFFFFFFu, dv[i], oi); }
+            const uint32_t k = fvalid ? f - (o_end - o_pn) : 0u;
+            uint32_t maxk = k;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxk = max(maxk, __shfl_xor_sync(0xFFFFFFFFu, maxk, o));
+            for (uint32_t j = 0; j < maxk; j++) {  // k sequential adds (vary.rs:146-154)
+              if (j < k) {
+#pragma unroll
+                for (int i = 0; i < NV; i++) fv[i] = fv[i] + fd[i];
+              }
+            }
+            const uint32_t pix = fvalid ? (o_py * RF_TILE_PITCH + o_px + k) : (0x10000u + lane);
+            const uint32_t earlier = __match_any_sync(0xFFFFFFFFu, pix) & lanemask_lt();  // same pixel, submitted before me
+            const DrawDesc& D = P.draws[fdraw];
+            const uint32_t flags = fvalid ? D.flags : 0u;
+            const uint32_t pmask = fvalid ? D.persp_mask : 0u;
+            const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
+            const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
+            uint32_t done = ~__ballot_sync(0xFFFFFFFFu, fvalid);
+            bool pending = fvalid;
+            uint32_t wrote = 0;
+            while (done != 0xFFFFFFFFu) {
+              const bool ready = pending && (earlier & ~done) == 0;
+              if (ready) wrote = process_fragment<LT>(D, T.fmt, sc, sz, pix, fv, pmask, dtest, cwrite, dwrite);
+              __syncwarp();
+              done |= __ballot_sync(0xFFFFFFFFu, ready);
+              if (ready) pending = false;
+            }
+            if (uni) acc_o += wrote;
+            else if (wrote) atomicAdd(&P.dstats[fdraw].frags_o, 1ull);
+          }
         }
-        if (uni) acc_o += my_o;
-        else if (my_o) atomicAdd(&P.dstats[draw].frags_o, (unsigned long long)my_o);
       }
     }
     if (acc_draw != 0xFFFFFFFFu) {
