@@ -162,6 +162,13 @@ rf_status rf_target_upload_color(rf_ctx* ctx, rf_target* t, const void* host, si
 rf_status rf_target_download_color(rf_ctx* ctx, rf_target* t, void* host, size_t stride_elems);
 rf_status rf_target_upload_depth(rf_ctx* ctx, rf_target* t, const float* host, size_t stride_elems);
 rf_status rf_target_download_depth(rf_ctx* ctx, rf_target* t, float* host, size_t stride_elems);
+/* Pinned host memory for Buf2 storage, so that uploads/downloads DMA directly (no staging copy). */
+rf_status rf_host_alloc(size_t bytes, void** out);
+void rf_host_free(void* p);
+/* Asynchronous download (4-byte formats): ordered after the queued draws on the ctx stream; the
+ * pixels are valid after the next rf_sync(). A replayed (arena-overflow) pass re-issues nothing:
+ * callers that use this must have warmed the arenas up, or use the synchronous download. */
+rf_status rf_target_download_color_async(rf_ctx* ctx, rf_target* t, void* host, size_t stride_elems);
 /* Device pointers of the uint32 colour containers / float depth (row-major, stride = w),
  * for NCCL gathers done by the host layer. */
 void* rf_target_color_devptr(rf_target* t);

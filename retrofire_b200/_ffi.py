@@ -87,6 +87,9 @@ SYMBOLS = {
     "rf_target_download_color": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "rf_target_upload_depth": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "rf_target_download_depth": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "rf_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "rf_host_free": (None, [_P]),
+    "rf_target_download_color_async": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "rf_target_color_devptr": (_P, [_P]),
     "rf_target_depth_devptr": (_P, [_P]),
     "rf_texture_create": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_size_t, C.POINTER(_P)]),

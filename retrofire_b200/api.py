@@ -191,6 +191,14 @@ class DrawCall:
                         color_write=bool(ctx.color_write), depth_write=bool(ctx.depth_write),
                         depth_sort=0 if ctx.depth_sort is None else int(ctx.depth_sort), mesh=mesh)
 
+    def cached_struct(self, key, texture_handle, mesh_handle) -> RfDraw:
+        """to_struct() memoised per device: the marshalling costs more than the rf_render call."""
+        c = self.__dict__.setdefault("_cache", {})
+        st = c.get(key)
+        if st is None:
+            st = c[key] = self.to_struct(texture_handle, mesh_handle)
+        return st
+
     def to_struct(self, texture_handle: int = None, mesh_handle: int = None) -> RfDraw:
         d = RfDraw()
         if self.mesh is None:
@@ -230,6 +238,7 @@ class Device:
         self._textures = []
         self._targets = []
         self._meshes = []
+        self._pinned = []
 
     def _check(self, st: int):
         if st != _ffi.RF_OK:
@@ -245,6 +254,9 @@ class Device:
             for t in self._textures:
                 self.lib.rf_texture_destroy(t)
             self.lib.rf_ctx_destroy(self.h)
+            for p in self._pinned:
+                self.lib.rf_host_free(p)
+            self._pinned = []
             self.h = None
 
     def __enter__(self):
@@ -282,6 +294,17 @@ class Device:
         self._check(self.lib.rf_ctx_kernel_times(self.h, ns, ln))
         return {self.lib.rf_kernel_name(i).decode(): (int(ns[i]), int(ln[i])) for i in range(_ffi.RF_N_KERNELS)}
 
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array over rf_host_alloc'ed (page-locked) memory; freed with the Device."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        st = self.lib.rf_host_alloc(n, C.byref(p))
+        if st != _ffi.RF_OK:
+            raise RetrofireError(st, "rf_host_alloc")
+        self._pinned.append(p.value)
+        buf = (C.c_uint8 * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
     def framebuf(self, w: int, h: int, fmt: int = _ffi.FMT_RGBA8888, depth: bool = True) -> "Framebuf":
         return Framebuf(self, w, h, fmt, depth)
 
@@ -291,7 +314,7 @@ class Device:
     # -- the hot path
     def render(self, call: DrawCall, target: "Framebuf", want_stats: bool = False) -> Optional[Stats]:
         tex = call.shader.texture.handle(self) if call.shader.texture is not None else None
-        d = call.to_struct(tex, call.mesh.h if call.mesh is not None else None)
+        d = call.cached_struct(id(self), tex, call.mesh.h if call.mesh is not None else None)
         if want_stats:
             s = RfStats()
             self._check(self.lib.rf_render(self.h, target.h, C.byref(d), C.byref(s)))
@@ -371,6 +394,10 @@ class Framebuf:
         dt, shape = self._host_shape()
         buf = np.ascontiguousarray(buf, dtype=dt).reshape(shape)
         self.dev._check(self.dev.lib.rf_target_upload_color(self.dev.h, self.h, buf.ctypes.data, self.w))
+
+    def download_color_async(self, out: np.ndarray):
+        """Queue a D2H copy into `out` (ideally from Device.pinned_empty); valid after Device.sync()."""
+        self.dev._check(self.dev.lib.rf_target_download_color_async(self.dev.h, self.h, out.ctypes.data, self.w))
 
     def download_depth(self) -> np.ndarray:
         out = np.empty((self.h_px, self.w), dtype=np.float32)

@@ -724,7 +724,20 @@ rf_status rf_target_download_color(rf_ctx* c, rf_target* t, void* host, size_t s
   if (st) return st;
   const int hb = host_bytes(t->fmt);
   if (hb == 4) {
-    RF_CUDA(c, cudaMemcpy2DAsync(host, stride * 4, t->d_color, (size_t)t->w * 4, (size_t)t->w * 4, t->h, cudaMemcpyDeviceToHost, c->stream));
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+      RF_CUDA(c, cudaMemcpy2DAsync(host, stride * 4, t->d_color, (size_t)t->w * 4, (size_t)t->w * 4, t->h, cudaMemcpyDeviceToHost, c->stream));
+    } else {  // pageable destination: DMA into the pinned bounce buffer, then one host copy
+      const size_t row = (size_t)t->w * 4;
+      if (!c->h_bounce.reserve(row * t->h)) return fail(c, RF_E_NOMEM, "pinned bounce");
+      RF_CUDA(c, cudaMemcpyAsync(c->h_bounce.p, t->d_color, row * t->h, cudaMemcpyDeviceToHost, c->stream));
+      RF_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (stride == t->w) std::memcpy(host, c->h_bounce.p, row * t->h);
+      else for (uint32_t y = 0; y < t->h; y++) std::memcpy(static_cast<uint8_t*>(host) + (size_t)y * stride * 4, c->h_bounce.p + (size_t)y * row, row);
+      return RF_OK;
+    }
   } else {
     const size_t n = (size_t)t->w * t->h;
     if (!c->bounce.reserve(n * hb)) return fail(c, RF_E_NOMEM, "bounce");
@@ -857,6 +870,26 @@ rf_status rf_ctx_last_pass(rf_ctx* c, uint64_t* time_ns, uint32_t* n_launches) {
   if (time_ns) *time_ns = c->last_pass_ns;
   if (n_launches) *n_launches = c->last_pass_launches;
   return st;
+}
+
+// ---- pinned host memory for Buf2 storage: lets uploads/downloads DMA straight into caller memory
+rf_status rf_host_alloc(size_t bytes, void** out) {
+  if (!out || !bytes) return RF_E_INVALID;
+  return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? RF_OK : RF_E_NOMEM;
+}
+void rf_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// Asynchronous variant of rf_target_download_color for 4-byte formats: enqueues the copy after the
+// queued draws; the pixels are in `host` after the next rf_sync(). `host` should come from rf_host_alloc.
+rf_status rf_target_download_color_async(rf_ctx* c, rf_target* t, void* host, size_t stride) {
+  if (!c || !t || !host || stride < t->w) return fail(c, RF_E_INVALID, "bad download arguments");
+  if (host_bytes(t->fmt) != 4) return fail(c, RF_E_UNSUPPORTED, "async download needs a 4-byte pixel format");
+  rf_status st = flush_impl(c);
+  if (st) return st;
+  RF_CUDA(c, cudaMemcpy2DAsync(host, stride * 4, t->d_color, (size_t)t->w * 4, (size_t)t->w * 4, t->h, cudaMemcpyDeviceToHost, c->stream));
+  return RF_OK;
 }
 
 rf_status rf_ctx_profile(rf_ctx* c, int enable) {
