@@ -54,3 +54,25 @@ def test_ptx_has_no_fma_on_coverage_and_depth_chains(tmp_path):
 def test_sass_is_sm_100a():
     out = subprocess.run(["cuobjdump", "-lelf", _ffi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out
+
+
+def _compile_cpp_smoke(out):
+    src = os.path.join(ROOT, "tests", "cpp_host_smoke.cpp")
+    libdir = os.path.join(ROOT, "retrofire_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-o", out, src, f"-L{libdir}", "-lrf_b200", f"-Wl,-rpath,{libdir}", "-L/usr/local/cuda/lib64", "-lcudart"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+def test_cpp_host_mirror_compiles_against_the_c_abi(tmp_path):
+    """include/retrofire_b200.hpp (the compiled-language host mirror) builds and links with librf_b200.so."""
+    rfbuild.build()
+    assert os.path.exists(_compile_cpp_smoke(str(tmp_path / "cpp_host_smoke")))
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_renders_hello_tri(tmp_path):
+    """hello_tri through re::render(): centre pixel (114,102,128,255), 51,200 fragments (hello_tri.rs:47-53)."""
+    exe = _compile_cpp_smoke(str(tmp_path / "cpp_host_smoke"))
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
