@@ -246,7 +246,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   mark();
   k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, st>>>(P);
   mark();
-  k_raster<LT><<<sm * 6, RF_RASTER_WARPS * 32, 0, st>>>(P);
+  k_raster<LT><<<sm * 4, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
   mark();
   s.n_launches += RF_N_KERNELS;
 }
@@ -257,13 +257,15 @@ rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const Aren
   if (w.w_spans > c->capw_spans) { if (!c->spans.reserve(w.w_spans * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->capw_spans = w.w_spans; }
   if (w.w_tris > c->capw_tris) { if (!c->tris.reserve(w.w_tris * 4)) return fail(c, RF_E_NOMEM, "triangle arena"); c->capw_tris = w.w_tris; }
   if (w.w_ckpts > c->capw_ckpts) { if (!c->ckpts.reserve(w.w_ckpts * 4)) return fail(c, RF_E_NOMEM, "checkpoint arena"); c->capw_ckpts = w.w_ckpts; }
-  if (w.w_ecks > c->capw_ecks) { if (!c->ecks.reserve(w.w_ecks * 4)) return fail(c, RF_E_NOMEM, "edge checkpoint arena"); c->capw_ecks = w.w_ecks; }
   if (w.entries > c->cap_entries) {
     if (!c->entries.reserve(w.entries * 16) || !c->bins.reserve(w.entries * 8)) return fail(c, RF_E_NOMEM, "bin arena");
     c->cap_entries = w.entries;
   }
   if (w.longs > c->cap_long) { if (!c->longlist.reserve(w.longs * 8)) return fail(c, RF_E_NOMEM, "long-span list"); c->cap_long = w.longs; }
-  if (w.chunks > c->cap_chunks) { if (!c->chunks.reserve(w.chunks * 8)) return fail(c, RF_E_NOMEM, "chunk list"); c->cap_chunks = w.chunks; }
+  if (w.chunks > c->cap_chunks) {
+    if (!c->chunks.reserve(w.chunks * 16) || !c->ecks.reserve(w.chunks * Rec<8>::EW * 4)) return fail(c, RF_E_NOMEM, "chunk list");
+    c->cap_chunks = w.chunks;
+  }
   if (w.tall > c->cap_tall) { if (!c->talllist.reserve(w.tall * 4)) return fail(c, RF_E_NOMEM, "tall list"); c->cap_tall = w.tall; }
   if (!c->tiles.reserve(n_tiles * 5 * 4 + 64)) return fail(c, RF_E_NOMEM, "tile arrays");
   if (!c->cursors.reserve(64)) return fail(c, RF_E_NOMEM, "cursors");
@@ -271,7 +273,7 @@ rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const Aren
 }
 
 bool arenas_cover(const rf_ctx* c, const ArenaWants& w) {
-  return w.w_spans <= c->capw_spans && w.w_tris <= c->capw_tris && w.w_ckpts <= c->capw_ckpts && w.w_ecks <= c->capw_ecks &&
+  return w.w_spans <= c->capw_spans && w.w_tris <= c->capw_tris && w.w_ckpts <= c->capw_ckpts &&
          w.entries <= c->cap_entries && w.longs <= c->cap_long && w.chunks <= c->cap_chunks && w.tall <= c->cap_tall;
 }
 
@@ -309,7 +311,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   s.NV = nv; s.NP = np; s.n_tiles = ntiles;
   // initial arena sizes (grown on demand by validate_all after an overflowing pass)
   ArenaWants want{std::max<size_t>(c->capw_spans, (size_t)8 << 20), std::max<size_t>(c->capw_tris, (size_t)8 << 20),
-                  std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), std::max<size_t>(c->capw_ecks, (size_t)1 << 20),
+                  std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), 0,
                   std::max<size_t>(c->cap_entries, (size_t)1 << 20), std::max<size_t>(c->cap_long, (size_t)1 << 19),
                   std::max<size_t>(c->cap_chunks, (size_t)1 << 20), std::max<size_t>(c->cap_tall, (size_t)1 << 18)};
   need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 20 + 64 ||
@@ -406,12 +408,12 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.cap_ckpts = (uint32_t)std::min<size_t>(c->capw_ckpts / words_ckpt(lt), 0xFFFFFFF0u);
   P.cap_entries = (uint32_t)std::min<size_t>(c->cap_entries, 0xFFFFFFF0u);
   P.cap_long = (uint32_t)std::min<size_t>(c->cap_long, 0xFFFFFFF0u);
-  P.chunks = static_cast<uint2*>(c->chunks.p);
+  P.chunks = static_cast<uint4*>(c->chunks.p);
   P.talllist = static_cast<uint32_t*>(c->talllist.p);
   P.ecks = static_cast<uint32_t*>(c->ecks.p);
   P.cap_chunks = (uint32_t)std::min<size_t>(c->cap_chunks, 0xFFFFFFF0u);
   P.cap_tall = (uint32_t)std::min<size_t>(c->cap_tall, 0xFFFFFFF0u);
-  P.cap_ecks = (uint32_t)std::min<size_t>(c->capw_ecks / words_eck(lt), 0xFFFFFFF0u);
+  P.cap_ecks = P.cap_chunks;
   uint32_t* ta = static_cast<uint32_t*>(c->tiles.p);
   P.tile_cnt = ta; P.tile_off = ta + ntiles; P.tile_fill = ta + 2 * (size_t)ntiles;
   P.worklist = ta + 3 * (size_t)ntiles; P.worklist_big = ta + 4 * (size_t)ntiles;
@@ -457,7 +459,7 @@ rf_status validate_all(rf_ctx* c) {
                          ps.chunks_needed > c->cap_chunks || ps.entries_needed > c->cap_entries;
       ArenaWants w{grow(c->capw_spans, ps.spans_needed * words_span(lt)), grow(c->capw_tris, ps.tris_needed * words_tri(lt)),
                    grow(c->capw_ckpts, std::max<unsigned long long>(ps.ckpts_needed, early ? ps.spans_needed / 8 : 0) * words_ckpt(lt)),
-                   grow(c->capw_ecks, ps.ecks_needed * words_eck(lt)), grow(c->cap_entries, ps.entries_needed),
+                   0, grow(c->cap_entries, ps.entries_needed),
                    grow(c->cap_long, std::max<unsigned long long>(ps.long_needed, early ? ps.spans_needed / 8 : 0)),
                    grow(c->cap_chunks, ps.chunks_needed), grow(c->cap_tall, ps.tall_needed)};
       { rf_status st = ensure_arenas(c, lt, s.NV, s.n_tiles, w); if (st) return st; }
@@ -633,6 +635,9 @@ rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
     ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_status), sizeof(HostStatus), cudaHostAllocDefault) == cudaSuccess;
   }
   ok = ok && cudaFuncSetAttribute(k_bin_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_raster<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<3>::BYTES) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_raster<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<5>::BYTES) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_raster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<8>::BYTES) == cudaSuccess;
   if (!ok) { rf_ctx_destroy(c); return RF_E_CUDA; }
   *out = c;
   return RF_OK;

@@ -97,9 +97,9 @@ struct PassParams {
   uint32_t* tris;         // [cap_tris][TW]    per drawn triangle: key, draw, rows, dv/dx of both halves
   uint4* entries;         // [cap_entries]     {tile, key, tri, 0}: one per (triangle, overlapped tile)
   unsigned long long* bins;  // [cap_entries]  per-tile lists of (key << 32 | tri), sorted by k_bin_sort
-  uint2* chunks;          // [cap_chunks]      {tri*2+half, chunk index}
+  uint4* chunks;          // [cap_chunks]      {tri*2+half, chunk | rows << 16, first span, draw | target << 16}
   uint32_t* talllist;     // [cap_tall]        tri*2+half of halves with more than one chunk
-  uint32_t* ecks;         // [cap_ecks][EW]    edge state at the start of chunk 1.. of tall halves
+  uint32_t* ecks;         // [cap_chunks][EW]  edge state at the start of a chunk (indexed by chunk position; chunk 0 unused)
   uint32_t cap_chunks, cap_tall, cap_ecks;
   uint2* longlist;        // [cap_long]        {span index, tri*2+half} of spans crossing a tile-column boundary
   uint32_t* ckpts;        // [cap_ckpts][KW]   varyings of such spans at each later tile-column start

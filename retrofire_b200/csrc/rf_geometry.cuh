@@ -209,7 +209,7 @@ __device__ __forceinline__ void half_setup(float y0, float y1, const float* l0, 
 
 // ---------------------------------------------------------------------------------------------
 // Triangle record (Rec<LT>::TW words), written by k_setup, read by k_edge_ckpt, k_walk, k_ckpt, k_raster:
-//   [0] key  [1] draw  [2] sbase  [3] Y0  [4] nU  [5] nL | target << 16  [6] eck base half 0  [7] eck base half 1
+//   [0] key  [1] draw  [2] sbase  [3] Y0  [4] nU  [5] nL | target << 16  [6] chunk position of half 0  [7] of half 1
 //   [8 + h*HS ...] half h: dv[1+LT] (dz/dx, dattr/dx), L[2+LT], dl[2+LT], R, dr, y
 // ---------------------------------------------------------------------------------------------
 template <int LT> struct TriRec {
@@ -249,6 +249,7 @@ __device__ __forceinline__ void tile_row_cols(const HalfSetup<LT>& H0, const Hal
 // its (triangle x tile) bin entries, and its walk chunks (<= 32 rows each).
 // =============================================================================================
 #define RF_CHUNK 32u
+#define RF_LONG_BLOCK 256u
 
 template <int LT>
 __global__ void __launch_bounds__(128) k_setup(PassParams P) {
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(128) k_setup(PassParams P) {
       bool emit = false;
       HalfSetup<LT> H0, H1;
       H0.n = H1.n = 0;
-      uint32_t tgt = 0, Y0 = 0, tr0 = 0, tr1 = 0, tiles_x = 1, nent = 0, nchunk = 0, neck = 0, by0 = 0, by1 = 0;
+      uint32_t tgt = 0, Y0 = 0, tr0 = 0, tr1 = 0, tiles_x = 1, nent = 0, nchunk = 0, by0 = 0, by1 = 0;
       float margin = 0.0f;
       if (t < ntri) {
         const DrawDesc& D = P.draws[d];
@@ -385,32 +386,29 @@ __global__ void __launch_bounds__(128) k_setup(PassParams P) {
               } else { tr0 = 1; tr1 = 0; }
               const uint32_t ch0 = (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = (H1.n + RF_CHUNK - 1) / RF_CHUNK;
               nchunk = ch0 + ch1;
-              neck = (ch0 ? ch0 - 1 : 0) + (ch1 ? ch1 - 1 : 0);
             }
           }
         }
       }
       // ---- warp-aggregated allocation (warp prefix sums)
       const uint32_t nsp = emit ? (H0.n + H1.n) : 0u;
-      const uint32_t incl_s = warp_scan_incl(nsp), incl_e = warp_scan_incl(nent), incl_c = warp_scan_incl(nchunk), incl_k = warp_scan_incl(neck);
+      const uint32_t incl_s = warp_scan_incl(nsp), incl_e = warp_scan_incl(nent), incl_c = warp_scan_incl(nchunk);
       const uint32_t tot_s = __shfl_sync(0xFFFFFFFFu, incl_s, 31), tot_e = __shfl_sync(0xFFFFFFFFu, incl_e, 31);
-      const uint32_t tot_c = __shfl_sync(0xFFFFFFFFu, incl_c, 31), tot_k = __shfl_sync(0xFFFFFFFFu, incl_k, 31);
+      const uint32_t tot_c = __shfl_sync(0xFFFFFFFFu, incl_c, 31);
       const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
-      unsigned long long sb = 0, tb = 0, eb = 0, cb_ = 0, kb = 0;
+      unsigned long long sb = 0, tb = 0, eb = 0, cb_ = 0;
       if (lane == 0 && emask) {
         sb = atomicAdd(&P.status->spans_needed, (unsigned long long)tot_s);
         tb = atomicAdd(&P.status->tris_needed, (unsigned long long)__popc(emask));
         if (tot_e) eb = atomicAdd(&P.status->entries_needed, (unsigned long long)tot_e);
         cb_ = atomicAdd(&P.status->chunks_needed, (unsigned long long)tot_c);
-        if (tot_k) kb = atomicAdd(&P.status->ecks_needed, (unsigned long long)tot_k);
       }
       sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
       tb = __shfl_sync(0xFFFFFFFFu, tb, 0);
       eb = __shfl_sync(0xFFFFFFFFu, eb, 0);
       cb_ = __shfl_sync(0xFFFFFFFFu, cb_, 0);
-      kb = __shfl_sync(0xFFFFFFFFu, kb, 0);
       const bool fits = sb + tot_s <= P.cap_spans && tb + __popc(emask) <= P.cap_tris && eb + tot_e <= P.cap_entries &&
-                        cb_ + tot_c <= P.cap_chunks && kb + tot_k <= P.cap_ecks;
+                        cb_ + tot_c <= P.cap_chunks;
       if (!fits) {
         if (lane == 0 && emask) { P.status->overflow = 1; P.cstatus->poison = 1; }
         continue;  // keep counting what is needed, write nothing
@@ -420,10 +418,9 @@ __global__ void __launch_bounds__(128) k_setup(PassParams P) {
       const uint32_t tri_idx = (uint32_t)tb + __popc(emask & lanemask_lt());
       uint32_t eidx = (uint32_t)eb + (incl_e - nent);
       uint32_t cidx = (uint32_t)cb_ + (incl_c - nchunk);
-      const uint32_t kbase = (uint32_t)kb + (incl_k - neck);
       const uint32_t key = gp * 8u + t;
       const uint32_t ch0 = (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = (H1.n + RF_CHUNK - 1) / RF_CHUNK;
-      const uint32_t eck0 = kbase, eck1 = kbase + (ch0 ? ch0 - 1 : 0);
+      const uint32_t eck0 = cidx, eck1 = cidx + ch0;  // edge checkpoints are indexed by chunk position
       {  // triangle record
         uint32_t* tr = P.tris + (size_t)tri_idx * TW;
         *reinterpret_cast<uint4*>(tr) = make_uint4(key, d, sbase, Y0);
@@ -458,8 +455,11 @@ __global__ void __launch_bounds__(128) k_setup(PassParams P) {
         }
       }
       // walk chunks (and the list of tall halves that need edge checkpoints)
-      for (uint32_t c = 0; c < ch0; c++) P.chunks[cidx++] = make_uint2(tri_idx * 2u, c);
-      for (uint32_t c = 0; c < ch1; c++) P.chunks[cidx++] = make_uint2(tri_idx * 2u + 1u, c);
+      // chunk record: {tri*2+half, chunk | rows << 16, first span index, draw | target << 16}
+      for (uint32_t c = 0; c < ch0; c++)
+        P.chunks[cidx++] = make_uint4(tri_idx * 2u, c | min(RF_CHUNK, H0.n - c * RF_CHUNK) << 16, sbase + c * RF_CHUNK, d | tgt << 16);
+      for (uint32_t c = 0; c < ch1; c++)
+        P.chunks[cidx++] = make_uint4(tri_idx * 2u + 1u, c | min(RF_CHUNK, H1.n - c * RF_CHUNK) << 16, sbase + H0.n + c * RF_CHUNK, d | tgt << 16);
       if (ch0 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
       if (ch1 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u + 1u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
     }
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(128) k_edge_ckpt(PassParams P) {
         for (int k = 0; k < NL; k++) L[k] = L[k] + dl[k];
         R = R + dr;
       }
-      uint32_t* e = P.ecks + (size_t)(ebase + c) * EW;
+      uint32_t* e = P.ecks + (size_t)(ebase + c + 1) * EW;  // state at the start of chunk c+1
       uint32_t w[EW];
 #pragma unroll
       for (int k = 0; k < EW; k++) w[k] = k < NL ? __float_as_uint(L[k]) : (k == NL ? __float_as_uint(R) : 0u);
@@ -537,30 +537,34 @@ __global__ void __launch_bounds__(128) k_walk(PassParams P) {
   const uint32_t lane = lane_id();
   const uint32_t nch = (uint32_t)min(P.status->chunks_needed, (unsigned long long)P.cap_chunks);
   const uint32_t wpb = blockDim.x >> 5;
-  const uint32_t n_warps = gridDim.x * wpb;
-  for (uint32_t cb = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 32u; cb < nch; cb += n_warps * 32u) {
-    // lane c: one chunk
-    uint32_t c_own = 0, c_idx = 0, c_rows = 0, c_sidx = 0, c_Y = 0, c_draw = 0, c_tgt = 0, c_eck = 0;
-    if (cb + lane < nch) {
-      const uint2 ch = __ldg(P.chunks + cb + lane);
-      c_own = ch.x; c_idx = ch.y;
-      const uint32_t* tr = P.tris + (size_t)(c_own >> 1) * TW;
-      const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(tr));
-      const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(tr + 4));
-      const uint32_t hh = c_own & 1u, nU = h1.x, nL = h1.y & 0xFFFFu;
-      const uint32_t n = hh ? nL : nU;
-      c_rows = min(RF_CHUNK, n - c_idx * RF_CHUNK);
-      const uint32_t row0 = (hh ? nU : 0u) + c_idx * RF_CHUNK;  // row index inside the triangle
-      c_sidx = h0.z + row0; c_Y = h0.w + row0; c_draw = h0.y; c_tgt = h1.y >> 16;
-      c_eck = (hh ? h1.w : h1.z) + c_idx - 1;  // valid when c_idx > 0
-    }
+  const uint32_t stride = gridDim.x * wpb * 32u;
+  uint32_t cb = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 32u;
+  // software pipeline over chunk batches: the records of batch n+1 are requested while batch n is walked
+  uint4 ch_next = make_uint4(0u, 0u, 0u, 0u);
+  if (cb + lane < nch) ch_next = __ldg(P.chunks + cb + lane);
+  // Long-list slots are reserved RF_LONG_BLOCK at a time per warp: one same-address atomic per block
+  // instead of one per row batch. Unused slots of a block are left as {~0, ~0} for k_ckpt to skip.
+  unsigned long long ll_next = 0, ll_end = 0;  // warp-uniform
+  for (; cb < nch; cb += stride) {
+    const uint4 ch = ch_next;
+    const bool c_have = cb + lane < nch;
+    ch_next = make_uint4(0u, 0u, 0u, 0u);
+    if (cb + stride + lane < nch) ch_next = __ldg(P.chunks + cb + stride + lane);
+    const uint32_t c_rows = c_have ? (ch.y >> 16) : 0u;
     const uint32_t incl = warp_scan_incl(c_rows);
     const uint32_t n_items = __shfl_sync(0xFFFFFFFFu, incl, 31);
     unsigned long long my_frags_i = 0;
     uint32_t my_draw = 0xFFFFFFFFu;
-    for (uint32_t ib = 0; ib < n_items; ib += 32) {
+
+    struct Pre {
+      bool valid;
+      uint32_t r, own, cidx, sidx, dt, cpos;
+      uint32_t buf[HS];
+      uint32_t eck[EW];
+    };
+    auto fetch = [&](uint32_t ib, Pre& p) {
       const uint32_t item = ib + lane;
-      const bool valid = item < n_items;
+      p.valid = item < n_items;
       uint32_t oc = 0;
 #pragma unroll
       for (int step = 16; step > 0; step >>= 1) {
@@ -570,36 +574,50 @@ __global__ void __launch_bounds__(128) k_walk(PassParams P) {
       }
       oc &= 31u;
       const uint32_t o_incl = __shfl_sync(0xFFFFFFFFu, incl, oc), o_rows = __shfl_sync(0xFFFFFFFFu, c_rows, oc);
-      const uint32_t o_own = __shfl_sync(0xFFFFFFFFu, c_own, oc), o_idx = __shfl_sync(0xFFFFFFFFu, c_idx, oc);
-      const uint32_t o_sidx = __shfl_sync(0xFFFFFFFFu, c_sidx, oc), o_Y = __shfl_sync(0xFFFFFFFFu, c_Y, oc);
-      const uint32_t o_draw = __shfl_sync(0xFFFFFFFFu, c_draw, oc), o_tgt = __shfl_sync(0xFFFFFFFFu, c_tgt, oc);
-      const uint32_t o_eck = __shfl_sync(0xFFFFFFFFu, c_eck, oc);
-      const uint32_t r = valid ? item - (o_incl - o_rows) : 0u;  // row inside the chunk = number of adds
+      p.own = __shfl_sync(0xFFFFFFFFu, ch.x, oc);
+      p.cidx = __shfl_sync(0xFFFFFFFFu, ch.y, oc) & 0xFFFFu;
+      p.sidx = __shfl_sync(0xFFFFFFFFu, ch.z, oc);
+      p.dt = __shfl_sync(0xFFFFFFFFu, ch.w, oc);
+      p.cpos = cb + oc;
+      p.r = p.valid ? item - (o_incl - o_rows) : 0u;  // row inside the chunk = number of adds
+      if (p.valid) {
+        const uint32_t* hs = P.tris + (size_t)(p.own >> 1) * TW + 8 + (p.own & 1u) * HS;
+#pragma unroll
+        for (int q = 0; q < HS / 4; q++) {
+          const uint4 t = __ldg(reinterpret_cast<const uint4*>(hs) + q);
+          p.buf[4 * q] = t.x; p.buf[4 * q + 1] = t.y; p.buf[4 * q + 2] = t.z; p.buf[4 * q + 3] = t.w;
+        }
+        if (p.cidx > 0) {  // chunk start state from the edge checkpoints
+          const uint32_t* e = P.ecks + (size_t)p.cpos * EW;
+#pragma unroll
+          for (int q = 0; q < EW / 2; q++) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(e) + q);
+            p.eck[2 * q] = t.x; p.eck[2 * q + 1] = t.y;
+          }
+        }
+      }
+    };
+    Pre cur, nxt;
+    fetch(0, cur);
+    for (uint32_t ib = 0; ib < n_items; ib += 32, cur = nxt) {
+      nxt.valid = false;
+      if (ib + 32 < n_items) fetch(ib + 32, nxt);
+      const bool valid = cur.valid;
+      const uint32_t r = cur.r;
       float L[NL], dl[NL], dv[NL], R = 0.0f, dr = 0.0f, y = 0.0f;
 #pragma unroll
       for (int k = 0; k < NL; k++) { L[k] = 0.0f; dl[k] = 0.0f; dv[k] = 0.0f; }
       if (valid) {
-        const uint32_t* hs = P.tris + (size_t)(o_own >> 1) * TW + 8 + (o_own & 1u) * HS;
-        float buf[HS];
 #pragma unroll
-        for (int q = 0; q < HS / 4; q++) {
-          const uint4 t = __ldg(reinterpret_cast<const uint4*>(hs) + q);
-          buf[4 * q] = __uint_as_float(t.x); buf[4 * q + 1] = __uint_as_float(t.y); buf[4 * q + 2] = __uint_as_float(t.z); buf[4 * q + 3] = __uint_as_float(t.w);
-        }
+        for (int k = 0; k < NL; k++) { L[k] = __uint_as_float(cur.buf[TR::O_L + k]); dl[k] = __uint_as_float(cur.buf[TR::O_DL + k]); }
 #pragma unroll
-        for (int k = 0; k < NL; k++) { L[k] = buf[TR::O_L + k]; dl[k] = buf[TR::O_DL + k]; }
+        for (int k = 1; k < NL; k++) dv[k] = __uint_as_float(cur.buf[TR::O_DV + k - 1]);
+        R = __uint_as_float(cur.buf[TR::O_R]); dr = __uint_as_float(cur.buf[TR::O_DR]);
+        y = __uint_as_float(cur.buf[TR::O_Y]) + (float)(cur.cidx * RF_CHUNK + r);  // exact: row centres are k + 0.5 below 2^24
+        if (cur.cidx > 0) {
 #pragma unroll
-        for (int k = 1; k < NL; k++) dv[k] = buf[TR::O_DV + k - 1];
-        R = buf[TR::O_R]; dr = buf[TR::O_DR];
-        y = buf[TR::O_Y] + (float)(o_idx * RF_CHUNK + r);  // exact: row centres are k + 0.5 below 2^24
-        if (o_idx > 0) {  // chunk start state from the edge checkpoints
-          const uint32_t* e = P.ecks + (size_t)o_eck * EW;
-#pragma unroll
-          for (int q = 0; q < EW / 2; q++) {
-            const uint2 t = __ldg(reinterpret_cast<const uint2*>(e) + q);
-            if (2 * q < NL) L[2 * q] = __uint_as_float(t.x); else if (2 * q == NL) R = __uint_as_float(t.x);
-            if (2 * q + 1 < NL) L[2 * q + 1] = __uint_as_float(t.y); else if (2 * q + 1 == NL) R = __uint_as_float(t.y);
-          }
+          for (int k = 0; k < NL; k++) L[k] = __uint_as_float(cur.eck[k]);
+          R = __uint_as_float(cur.eck[NL]);
         }
       }
       uint32_t maxr = r;
@@ -612,8 +630,11 @@ __global__ void __launch_bounds__(128) k_walk(PassParams P) {
           R = R + dr;
         }
       }
+      bool is_long = false;
+      uint32_t long_sidx = 0;
       if (valid) {
-        const TargetDesc& T = P.targets[o_tgt];
+        const uint32_t o_draw = cur.dt & 0xFFFFu;
+        const TargetDesc& T = P.targets[cur.dt >> 16];
         const float x0r = round_up_to_half(L[0]), x1r = round_up_to_half(R);
         const float tx = x0r - L[0];
         uint32_t w[SW];
@@ -636,18 +657,37 @@ __global__ void __launch_bounds__(128) k_walk(PassParams P) {
           }
           my_frags_i += X1 - X0;
         }
-        const uint32_t sidx = o_sidx + r;
-        if (nn && ((X0 + nn - 1) >> RF_TILE_SHIFT) != (X0 >> RF_TILE_SHIFT)) {  // crosses a tile column: k_ckpt adds checkpoints
-          const unsigned long long slot = agg_atomic_inc(&P.status->long_needed);
-          if (slot < P.cap_long) P.longlist[slot] = make_uint2(sidx, o_own);
-          else { P.status->overflow = 1; P.cstatus->poison = 1; }
-        }
+        const uint32_t sidx = cur.sidx + r;
+        is_long = nn && ((X0 + nn - 1) >> RF_TILE_SHIFT) != (X0 >> RF_TILE_SHIFT);  // crosses a tile column: k_ckpt adds checkpoints
+        long_sidx = sidx;
         w[0] = X0 | nn << 16;
         w[1] = RF_NO_CKPT;
         uint32_t* sr = P.spans + (size_t)sidx * SW;
 #pragma unroll
         for (int q = 0; q < SW / 2; q++) *reinterpret_cast<uint2*>(sr + 2 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
-        (void)o_Y;
+      }
+      {  // long-list append from warp-private reserved blocks
+        const uint32_t lm = __ballot_sync(0xFFFFFFFFu, is_long);
+        if (lm) {
+          const uint32_t nl = __popc(lm);
+          if (ll_next + nl > ll_end) {  // reserve a fresh block (the tail of the old one stays marked unused)
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&P.status->long_needed, (unsigned long long)RF_LONG_BLOCK);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base + RF_LONG_BLOCK <= P.cap_long) {
+              for (uint32_t q = lane; q < RF_LONG_BLOCK; q += 32) P.longlist[base + q] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+              __syncwarp();
+              ll_next = base; ll_end = base + RF_LONG_BLOCK;
+            } else {
+              if (lane == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
+              ll_next = ll_end = 0;
+            }
+          }
+          if (ll_next + nl <= ll_end) {
+            if (is_long) P.longlist[ll_next + __popc(lm & lanemask_lt())] = make_uint2(long_sidx, cur.own);
+            ll_next += nl;
+          }
+        }
       }
     }
     // ---- frags.i: one atomic per warp when the whole warp worked on one draw

@@ -2,6 +2,8 @@
 // and the tile rasteriser (span fill, perspective-correct varyings, texture fetch, depth test,
 // colour/depth writes). Reference path: raster.rs:60-69 (fragments), target.rs:138-198.
 #pragma once
+#include <type_traits>
+
 #include "rf_device.cuh"
 
 // =============================================================================================
@@ -77,9 +79,11 @@ __global__ void __launch_bounds__(256) k_ckpt(PassParams P) {
     if (have) {
       const uint2 le = P.longlist[li];
       s = le.x; own = le.y;
-      const uint32_t h = P.spans[(size_t)s * SW];
-      X0 = h & 0xFFFFu; n = h >> 16;
-      nck = ((X0 + n - 1) >> RF_TILE_SHIFT) - (X0 >> RF_TILE_SHIFT);
+      if (s != 0xFFFFFFFFu) {  // unused slot of a reserved block
+        const uint32_t h = P.spans[(size_t)s * SW];
+        X0 = h & 0xFFFFu; n = h >> 16;
+        nck = ((X0 + n - 1) >> RF_TILE_SHIFT) - (X0 >> RF_TILE_SHIFT);
+      }
     }
     const uint32_t incl = warp_scan_incl(nck);
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
@@ -227,9 +231,9 @@ __device__ __forceinline__ float rust_clampf(float x, float lo, float hi) {
 
 // Catalogue fragment shaders. var[] already perspective-corrected. false = discard.
 template <int LT>
-__device__ __forceinline__ bool shade_fragment(const DrawDesc& D, const float* var, uint32_t& r, uint32_t& g, uint32_t& b, uint32_t& a) {
+__device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, const float* var, uint32_t& r, uint32_t& g, uint32_t& b, uint32_t& a) {
   a = 0xFFu;
-  switch (D.fs) {
+  switch (fs) {
     case RF_FS_COLOR3F:  // color.rs:246-263
       if (LT >= 3) { r = sat_u8(256.0f * var[0]); g = sat_u8(256.0f * var[1]); b = sat_u8(256.0f * var[2]); }
       return true;
@@ -305,7 +309,7 @@ __device__ __forceinline__ bool shade_fragment(const DrawDesc& D, const float* v
 // One fragment (target.rs:163-198): depth test -> fragment shader -> colour/depth write.
 // v[0] = interpolated 1/w (the depth value), v[1..] = interpolated varyings. Returns 1 if colour was written.
 template <int LT>
-__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fmt, uint32_t* sc, float* sz, uint32_t idx, const float* v,
+__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t* sc, float* sz, uint32_t idx, const float* v,
                                                      uint32_t pmask, uint32_t dtest, bool cwrite, bool dwrite) {
   const float z = v[0];
   if (dtest != RF_DEPTH_NONE) {  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
@@ -315,28 +319,57 @@ __device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t
   }
   float var[LT];
 #pragma unroll
-  for (int i = 0; i < LT; i++) var[i] = ((pmask >> i) & 1u) ? v[1 + i] / z : v[1 + i];  // raster.rs:60-69
+  for (int i = 0; i < LT; i++) var[i] = v[1 + i];
+  if (pmask != 0) {  // Scanline::fragments: var.z_div(pos.z) on the lanes whose type divides (raster.rs:60-69)
+#pragma unroll
+    for (int i = 0; i < LT; i++)
+      if ((pmask >> i) & 1u) var[i] = v[1 + i] / z;
+  }
   uint32_t r = 0, g = 0, bl = 0, a = 0;
-  if (!shade_fragment<LT>(D, var, r, g, bl, a)) return 0u;  // discard: no writes at all
+  if (!shade_fragment<LT>(D, fs, var, r, g, bl, a)) return 0u;  // discard: no writes at all
   if (dwrite) sz[idx] = z;
   if (cwrite) { sc[idx] = pack_pixel(fmt, r, g, bl, a); return 1u; }
   return 0u;
 }
 
+// Specialisation for the default Context (depth test Less, colour and depth writes on, ctx.rs:104-127) and a
+// compile-time fragment shader / perspective mask: straight-line code, no state decoding.
+template <int LT, int FS, uint32_t PMASK>
+__device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, uint32_t fmt, uint32_t* sc, float* sz, uint32_t idx, const float* v) {
+  const float z = v[0];
+  if (!(sz[idx] < z)) return 0u;
+  float var[LT];
+#pragma unroll
+  for (int i = 0; i < LT; i++) var[i] = ((PMASK >> i) & 1u) ? v[1 + i] / z : v[1 + i];
+  uint32_t r = 0, g = 0, bl = 0, a = 0;
+  if (!shade_fragment<LT>(D, (uint32_t)FS, var, r, g, bl, a)) return 0u;
+  sz[idx] = z;
+  sc[idx] = pack_pixel(fmt, r, g, bl, a);
+  return 1u;
+}
+
 // Average piece length (pixels) above which a batch of pieces is walked one piece per lane;
 // below it the batch is expanded to one FRAGMENT per lane (each lane does k sequential adds).
-#define RF_SPAN_MODE_MIN_AVG 10u
+#define RF_SPAN_MODE_MIN_AVG 6u
+#define RF_FRAG_QUEUE (RF_SPAN_MODE_MIN_AVG * 32u)  // fragment-mode batches hold fewer fragments than this
+
+template <int LT> struct RasterSmem {
+  static constexpr int TILE_WORDS = RF_TILE * RF_TILE_PITCH;
+  static constexpr int WARP_WORDS = 2 * TILE_WORDS + (2 + LT) * (int)RF_FRAG_QUEUE;  // colour, depth, queue {z, attr[LT], pix}
+  static constexpr size_t BYTES = (size_t)RF_RASTER_WARPS * WARP_WORDS * 4;
+};
 
 template <int LT>
 __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
   constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW;
   constexpr int NV = 1 + LT;
-  __shared__ uint32_t s_color[RF_RASTER_WARPS][RF_TILE * RF_TILE_PITCH];
-  __shared__ float s_depth[RF_RASTER_WARPS][RF_TILE * RF_TILE_PITCH];
+  extern __shared__ uint32_t s_raster[];
   if (P.cstatus->poison || P.status->error) return;
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  uint32_t* sc = s_color[warp];
-  float* sz = s_depth[warp];
+  uint32_t* sc = s_raster + (size_t)warp * RasterSmem<LT>::WARP_WORDS;
+  float* sz = reinterpret_cast<float*>(sc + RasterSmem<LT>::TILE_WORDS);
+  float* qv = sz + RasterSmem<LT>::TILE_WORDS;                                  // [1+LT][RF_FRAG_QUEUE]
+  uint32_t* qp = reinterpret_cast<uint32_t*>(qv + (1 + LT) * RF_FRAG_QUEUE);    // [RF_FRAG_QUEUE] pixel index | owner lane << 16
   const uint32_t n_work = P.status->n_work;
 
   for (;;) {
@@ -405,9 +438,17 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
       const uint32_t t_incl = warp_scan_incl(t_rows);
       const uint32_t n_items = __shfl_sync(0xFFFFFFFFu, t_incl, 31);
 
-      for (uint32_t ib = 0; ib < n_items; ib += 32) {
+      // Software pipeline: the span record and dv/dx of batch n+1 are requested before batch n is
+      // processed, so their (L2/HBM) latency overlaps the fragment work.
+      struct Pre {
+        bool valid;
+        uint32_t Y, draw;
+        uint32_t w[SW];
+        uint32_t dvw[NV];
+      };
+      auto fetch = [&](uint32_t ib, Pre& p) {
         const uint32_t item = ib + lane;
-        bool valid = item < n_items;
+        p.valid = item < n_items;
         // owner triangle lane: number of lanes whose inclusive end <= item
         uint32_t ot = 0;
 #pragma unroll
@@ -420,29 +461,41 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
         const uint32_t o_incl = __shfl_sync(0xFFFFFFFFu, t_incl, ot), o_rows = __shfl_sync(0xFFFFFFFFu, t_rows, ot);
         const uint32_t o_ra = __shfl_sync(0xFFFFFFFFu, t_ra, ot), o_Y0 = __shfl_sync(0xFFFFFFFFu, t_Y0, ot);
         const uint32_t o_sbase = __shfl_sync(0xFFFFFFFFu, t_sbase, ot), o_nU = __shfl_sync(0xFFFFFFFFu, t_nU, ot);
-        const uint32_t o_tri = __shfl_sync(0xFFFFFFFFu, t_tri, ot), o_draw = __shfl_sync(0xFFFFFFFFu, t_draw, ot);
-
+        const uint32_t o_tri = __shfl_sync(0xFFFFFFFFu, t_tri, ot);
+        p.draw = __shfl_sync(0xFFFFFFFFu, t_draw, ot);
+        p.Y = 0;
+        if (p.valid) {
+          p.Y = o_ra + (item - (o_incl - o_rows));
+          const uint32_t j = p.Y - o_Y0;
+          const uint32_t* sp = P.spans + (size_t)(o_sbase + j) * SW;
+#pragma unroll
+          for (int q = 0; q < SW / 2; q++) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp) + q);
+            p.w[2 * q] = t.x; p.w[2 * q + 1] = t.y;
+          }
+          const uint32_t* dp = P.tris + (size_t)o_tri * TW + 8 + (j >= o_nU ? Rec<LT>::HS : 0);
+#pragma unroll
+          for (int i = 0; i < NV; i++) p.dvw[i] = __ldg(dp + i);
+        }
+      };
+      Pre cur, nxt;
+      fetch(0, cur);
+      for (uint32_t ib = 0; ib < n_items; ib += 32, cur = nxt) {
+        nxt.valid = false;
+        if (ib + 32 < n_items) fetch(ib + 32, nxt);
+        bool valid = cur.valid;
         uint32_t py = 32 + lane, pxs = 0, pn = 0, draw = 0;
         float v[NV], dv[NV];
 #pragma unroll
         for (int i = 0; i < NV; i++) { v[i] = 0.0f; dv[i] = 0.0f; }
         if (valid) {
-          const uint32_t Y = o_ra + (item - (o_incl - o_rows));
-          const uint32_t j = Y - o_Y0;
-          const uint32_t* sp = P.spans + (size_t)(o_sbase + j) * SW;
-          uint32_t w[SW];
-#pragma unroll
-          for (int q = 0; q < SW / 2; q++) {
-            const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp) + q);
-            w[2 * q] = t.x; w[2 * q + 1] = t.y;
-          }
-          const uint32_t X0 = w[0] & 0xFFFFu, n = w[0] >> 16;
+          const uint32_t X0 = cur.w[0] & 0xFFFFu, n = cur.w[0] >> 16;
           const uint32_t xs = max(X0, px0), xe = min(X0 + n, px0 + tw);
           if (n == 0 || xs >= xe) valid = false;
           else {
-            py = Y - py0; pxs = xs - px0; pn = xe - xs; draw = o_draw;
+            py = cur.Y - py0; pxs = xs - px0; pn = xe - xs; draw = cur.draw;
             if (xs > X0) {  // the span started in an earlier tile column: take the checkpoint at this column
-              const uint32_t* ck = P.ckpts + (size_t)(w[1] + (tx - (X0 >> RF_TILE_SHIFT) - 1)) * KW;
+              const uint32_t* ck = P.ckpts + (size_t)(cur.w[1] + (tx - (X0 >> RF_TILE_SHIFT) - 1)) * KW;
 #pragma unroll
               for (int q = 0; q < KW / 2; q++) {
                 const uint2 t = __ldg(reinterpret_cast<const uint2*>(ck) + q);
@@ -451,11 +504,10 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < NV; i++) v[i] = __uint_as_float(w[2 + i]);
+              for (int i = 0; i < NV; i++) v[i] = __uint_as_float(cur.w[2 + i]);
             }
-            const uint32_t* dp = P.tris + (size_t)o_tri * TW + 8 + (j >= o_nU ? Rec<LT>::HS : 0);
 #pragma unroll
-            for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(__ldg(dp + i));
+            for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(cur.dvw[i]);
           }
         }
         const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
@@ -496,18 +548,42 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
           const DrawDesc& D = P.draws[draw];
           const uint32_t flags = valid ? D.flags : 0u;
           const uint32_t pmask = valid ? D.persp_mask : 0u;
+          const uint32_t fs = D.fs;
           const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
           const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
+          // warp-uniform specialisation selector (0 = generic)
+          int smode = 0;
+          if (uni) {
+            const DrawDesc& Dq = P.draws[d0];
+            const uint32_t dflt = RF_DEPTH_LESS << RF_F_DTEST_SHIFT | RF_F_CWRITE | RF_F_DWRITE;
+            const bool is_default = has_depth && (Dq.flags & ~RF_F_CULL_MASK) == dflt;
+            if (is_default && Dq.fs == RF_FS_TEX_CLAMP_LIT && Dq.persp_mask == 0x1Fu && LT >= 5) smode = 4;
+            else if (is_default && Dq.fs == RF_FS_COLOR3F && Dq.persp_mask == 0u && LT >= 3) smode = 2;
+          }
           uint32_t done = ~vmask;
           bool pending = valid;
           while (done != 0xFFFFFFFFu) {
             const bool ready = pending && (dep & ~done) == 0;
             if (ready) {
               const uint32_t base = py * RF_TILE_PITCH + pxs;
-              for (uint32_t k = 0; k < pn; k++) {
-                my_o += process_fragment<LT>(D, T.fmt, sc, sz, base + k, v, pmask, dtest, cwrite, dwrite);
+              if (smode == 4) {  // default Context + FS_TEX_CLAMP_LIT (crates): straight-line fragment code
+                for (uint32_t k = 0; k < pn; k++) {
+                  my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, sc, sz, base + k, v);
 #pragma unroll
-                for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
+                  for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
+                }
+              } else if (smode == 2) {
+                for (uint32_t k = 0; k < pn; k++) {
+                  my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, sc, sz, base + k, v);
+#pragma unroll
+                  for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
+                }
+              } else {
+                for (uint32_t k = 0; k < pn; k++) {
+                  my_o += process_fragment<LT>(D, fs, T.fmt, sc, sz, base + k, v, pmask, dtest, cwrite, dwrite);
+#pragma unroll
+                  for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
+                }
               }
             }
             __syncwarp();
@@ -518,53 +594,95 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
           else if (my_o) atomicAdd(&P.dstats[draw].frags_o, (unsigned long long)my_o);
         } else {
           // ================= fragment mode: one fragment per lane =================
-          for (uint32_t fb = 0; fb < n_frags; fb += 32) {
-            const uint32_t f = fb + lane;
-            const bool fvalid = f < n_frags;
-            uint32_t oi = 0;  // owner piece lane: number of lanes whose inclusive end <= f
+          // Phase A: every piece lane walks its piece (sequential adds, vary.rs:146-154) and queues one
+          // record per fragment in shared memory; phase B: 32 fragments at a time, one per lane.
+          {
+            const uint32_t qstart = f_incl - pn;
+            uint32_t maxn = pn;
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-              const uint32_t cand = oi + step;
-              const uint32_t e = __shfl_sync(0xFFFFFFFFu, f_incl, (cand - 1) & 31);
-              if (cand <= 32 && e <= f) oi = cand;
-            }
-            oi &= 31u;
-            const uint32_t o_end = __shfl_sync(0xFFFFFFFFu, f_incl, oi), o_pn = __shfl_sync(0xFFFFFFFFu, pn, oi);
-            const uint32_t o_py = __shfl_sync(0xFFFFFFFFu, py, oi), o_px = __shfl_sync(0xFFFFFFFFu, pxs, oi);
-            const uint32_t fdraw = __shfl_sync(0xFFFFFFFFu, draw, oi);
-            float fv[NV], fd[NV];
+            for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xFFFFFFFFu, maxn, o));
+            const uint32_t pix0 = py * RF_TILE_PITCH + pxs;
+            for (uint32_t k = 0; k < maxn; k++) {
+              if (k < pn) {
+                const uint32_t q = qstart + k;
 #pragma unroll
-            for (int i = 0; i < NV; i++) { fv[i] = __shfl_sync(0xFFFFFFFFu, v[i], oi); fd[i] = __shfl_sync(0xFFFFFFFFu, dv[i], oi); }
-            const uint32_t k = fvalid ? f - (o_end - o_pn) : 0u;
-            uint32_t maxk = k;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) maxk = max(maxk, __shfl_xor_sync(0xFFFFFFFFu, maxk, o));
-            for (uint32_t j = 0; j < maxk; j++) {  // k sequential adds (vary.rs:146-154)
-              if (j < k) {
-#pragma unroll
-                for (int i = 0; i < NV; i++) fv[i] = fv[i] + fd[i];
+                for (int i = 0; i < NV; i++) { qv[i * RF_FRAG_QUEUE + q] = v[i]; v[i] = v[i] + dv[i]; }
+                qp[q] = (pix0 + k) | lane << 16;
               }
             }
-            const uint32_t pix = fvalid ? (o_py * RF_TILE_PITCH + o_px + k) : (0x10000u + lane);
-            const uint32_t earlier = __match_any_sync(0xFFFFFFFFu, pix) & lanemask_lt();  // same pixel, submitted before me
-            const DrawDesc& D = P.draws[fdraw];
-            const uint32_t flags = fvalid ? D.flags : 0u;
-            const uint32_t pmask = fvalid ? D.persp_mask : 0u;
-            const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
-            const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
-            uint32_t done = ~__ballot_sync(0xFFFFFFFFu, fvalid);
-            bool pending = fvalid;
-            uint32_t wrote = 0;
-            while (done != 0xFFFFFFFFu) {
-              const bool ready = pending && (earlier & ~done) == 0;
-              if (ready) wrote = process_fragment<LT>(D, T.fmt, sc, sz, pix, fv, pmask, dtest, cwrite, dwrite);
-              __syncwarp();
-              done |= __ballot_sync(0xFFFFFFFFu, ready);
-              if (ready) pending = false;
-            }
-            if (uni) acc_o += wrote;
-            else if (wrote) atomicAdd(&P.dstats[fdraw].frags_o, 1ull);
           }
+          __syncwarp();
+          // Phase B. When the whole batch belongs to one draw (the common case) the draw state is
+          // warp-uniform and hoisted out of the loop; otherwise every fragment looks its draw up.
+          auto frag_loop = [&](auto mode_tag) {
+            // MODE 0: per-lane draw state; 1: warp-uniform state; 2..4: warp-uniform default state with a fixed shader
+            constexpr int MODE = decltype(mode_tag)::value;
+            constexpr bool UNI = MODE >= 1;
+            const DrawDesc& Du = P.draws[d0];
+            const uint32_t u_flags = Du.flags, u_pmask = Du.persp_mask, u_fs = Du.fs;
+            const uint32_t u_dtest = has_depth ? ((u_flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
+            const bool u_cwrite = (u_flags & RF_F_CWRITE) != 0, u_dwrite = has_depth && (u_flags & RF_F_DWRITE) != 0;
+            for (uint32_t fb = 0; fb < n_frags; fb += 32) {
+              const uint32_t f = fb + lane;
+              const bool fvalid = f < n_frags;
+              float fv[NV];
+              uint32_t pw = 0;
+              if (fvalid) {
+#pragma unroll
+                for (int i = 0; i < NV; i++) fv[i] = qv[i * RF_FRAG_QUEUE + f];
+                pw = qp[f];
+              } else {
+#pragma unroll
+                for (int i = 0; i < NV; i++) fv[i] = 0.0f;
+              }
+              const uint32_t pix = fvalid ? (pw & 0xFFFFu) : (0x10000u + lane);
+              const uint32_t earlier = __match_any_sync(0xFFFFFFFFu, pix) & lanemask_lt();  // same pixel, submitted before me
+              uint32_t fdraw = d0, pmask = u_pmask, fs = u_fs, dtest = u_dtest;
+              bool cwrite = u_cwrite, dwrite = u_dwrite;
+              if (!UNI) {
+                fdraw = __shfl_sync(0xFFFFFFFFu, draw, (pw >> 16) & 31u);
+                const DrawDesc& Dl = P.draws[fdraw];
+                const uint32_t flags = Dl.flags;
+                pmask = Dl.persp_mask; fs = Dl.fs;
+                dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
+                cwrite = (flags & RF_F_CWRITE) != 0; dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
+              }
+              const DrawDesc& D = UNI ? Du : P.draws[fdraw];
+              uint32_t wrote = 0;
+              auto one = [&]() -> uint32_t {
+                if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, sc, sz, pix, fv);
+                if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, T.fmt, sc, sz, pix, fv);
+                if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, sc, sz, pix, fv);
+                return process_fragment<LT>(D, fs, T.fmt, sc, sz, pix, fv, pmask, dtest, cwrite, dwrite);
+              };
+              if (__all_sync(0xFFFFFFFFu, earlier == 0)) {
+                if (fvalid) wrote = one();
+              } else {
+                uint32_t done = ~__ballot_sync(0xFFFFFFFFu, fvalid);
+                bool pending = fvalid;
+                while (done != 0xFFFFFFFFu) {
+                  const bool ready = pending && (earlier & ~done) == 0;
+                  if (ready) wrote = one();
+                  __syncwarp();
+                  done |= __ballot_sync(0xFFFFFFFFu, ready);
+                  if (ready) pending = false;
+                }
+              }
+              if (UNI) acc_o += wrote;
+              else if (wrote) atomicAdd(&P.dstats[fdraw].frags_o, 1ull);
+            }
+          };
+          if (!uni) frag_loop(std::integral_constant<int, 0>{});
+          else {
+            const DrawDesc& Dq = P.draws[d0];
+            const uint32_t dflt = RF_DEPTH_LESS << RF_F_DTEST_SHIFT | RF_F_CWRITE | RF_F_DWRITE;
+            const bool is_default = has_depth && (Dq.flags & ~RF_F_CULL_MASK) == dflt;
+            if (is_default && Dq.fs == RF_FS_COLOR3F && Dq.persp_mask == 0u && LT >= 3) frag_loop(std::integral_constant<int, 2>{});
+            else if (is_default && Dq.fs == RF_FS_SPRITE_DISC && Dq.persp_mask == 0x3u) frag_loop(std::integral_constant<int, 3>{});
+            else if (is_default && Dq.fs == RF_FS_TEX_CLAMP_LIT && Dq.persp_mask == 0x1Fu && LT >= 5) frag_loop(std::integral_constant<int, 4>{});
+            else frag_loop(std::integral_constant<int, 1>{});
+          }
+          __syncwarp();
         }
       }
     }
