@@ -246,7 +246,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   mark();
   k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, st>>>(P);
   mark();
-  k_raster<LT><<<sm * 4, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
+  k_raster<LT><<<sm * 7, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
   mark();
   s.n_launches += RF_N_KERNELS;
 }

@@ -308,8 +308,14 @@ __device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, c
 
 // One fragment (target.rs:163-198): depth test -> fragment shader -> colour/depth write.
 // v[0] = interpolated 1/w (the depth value), v[1..] = interpolated varyings. Returns 1 if colour was written.
+// colour pixel of tile-local index idx (= row * RF_TILE_PITCH + col) in the framebuffer
+__device__ __forceinline__ uint32_t* color_px(uint32_t* gc, uint32_t gw, uint32_t idx) {
+  const uint32_t row = idx / RF_TILE_PITCH;
+  return gc + (size_t)row * gw + (idx - row * RF_TILE_PITCH);
+}
+
 template <int LT>
-__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t* sc, float* sz, uint32_t idx, const float* v,
+__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t* gc, uint32_t gw, float* sz, uint32_t idx, const float* v,
                                                      uint32_t pmask, uint32_t dtest, bool cwrite, bool dwrite) {
   const float z = v[0];
   if (dtest != RF_DEPTH_NONE) {  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
@@ -328,14 +334,14 @@ __device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t
   uint32_t r = 0, g = 0, bl = 0, a = 0;
   if (!shade_fragment<LT>(D, fs, var, r, g, bl, a)) return 0u;  // discard: no writes at all
   if (dwrite) sz[idx] = z;
-  if (cwrite) { sc[idx] = pack_pixel(fmt, r, g, bl, a); return 1u; }
+  if (cwrite) { *color_px(gc, gw, idx) = pack_pixel(fmt, r, g, bl, a); return 1u; }
   return 0u;
 }
 
 // Specialisation for the default Context (depth test Less, colour and depth writes on, ctx.rs:104-127) and a
 // compile-time fragment shader / perspective mask: straight-line code, no state decoding.
 template <int LT, int FS, uint32_t PMASK>
-__device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, uint32_t fmt, uint32_t* sc, float* sz, uint32_t idx, const float* v) {
+__device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, uint32_t fmt, uint32_t* gc, uint32_t gw, float* sz, uint32_t idx, const float* v) {
   const float z = v[0];
   if (!(sz[idx] < z)) return 0u;
   float var[LT];
@@ -344,7 +350,7 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
   uint32_t r = 0, g = 0, bl = 0, a = 0;
   if (!shade_fragment<LT>(D, (uint32_t)FS, var, r, g, bl, a)) return 0u;
   sz[idx] = z;
-  sc[idx] = pack_pixel(fmt, r, g, bl, a);
+  *color_px(gc, gw, idx) = pack_pixel(fmt, r, g, bl, a);
   return 1u;
 }
 
@@ -355,7 +361,7 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
 
 template <int LT> struct RasterSmem {
   static constexpr int TILE_WORDS = RF_TILE * RF_TILE_PITCH;
-  static constexpr int WARP_WORDS = 2 * TILE_WORDS + (2 + LT) * (int)RF_FRAG_QUEUE;  // colour, depth, queue {z, attr[LT], pix}
+  static constexpr int WARP_WORDS = TILE_WORDS + (2 + LT) * (int)RF_FRAG_QUEUE;  // depth tile, queue {z, attr[LT], pix}
   static constexpr size_t BYTES = (size_t)RF_RASTER_WARPS * WARP_WORDS * 4;
 };
 
@@ -366,8 +372,10 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
   extern __shared__ uint32_t s_raster[];
   if (P.cstatus->poison || P.status->error) return;
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  uint32_t* sc = s_raster + (size_t)warp * RasterSmem<LT>::WARP_WORDS;
-  float* sz = reinterpret_cast<float*>(sc + RasterSmem<LT>::TILE_WORDS);
+  // Only DEPTH is staged in shared memory: colour is write-only on this path (no blending, target.rs:187-189),
+  // so passing fragments store their pixel straight to the framebuffer. __syncwarp() between dependency
+  // rounds orders two writes to one pixel; untouched pixels are never read or written.
+  float* sz = reinterpret_cast<float*>(s_raster + (size_t)warp * RasterSmem<LT>::WARP_WORDS);
   float* qv = sz + RasterSmem<LT>::TILE_WORDS;                                  // [1+LT][RF_FRAG_QUEUE]
   uint32_t* qp = reinterpret_cast<uint32_t*>(qv + (1 + LT) * RF_FRAG_QUEUE);    // [RF_FRAG_QUEUE] pixel index | owner lane << 16
   const uint32_t n_work = P.status->n_work;
@@ -394,27 +402,20 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
     const bool has_depth = T.depth != nullptr;
     const bool vec = (T.w & 3u) == 0 && tw == RF_TILE;
 
-    // ---- stage the tile: 128-bit coalesced loads, 8 lanes per row, 4 rows per instruction
-    if (vec) {
-      const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
-      for (uint32_t r = rsub; r < th; r += 4) {
-        const size_t g = (size_t)(py0 + r) * T.w + px0 + c4;
-        const uint4 c = *reinterpret_cast<const uint4*>(T.color + g);
-        uint32_t* d = sc + r * RF_TILE_PITCH + c4;
-        d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
-        if (has_depth) {
-          const float4 z = *reinterpret_cast<const float4*>(T.depth + g);
+    uint32_t* gc = T.color + (size_t)py0 * T.w + px0;  // framebuffer address of the tile's first pixel
+    // ---- stage the depth tile: 128-bit coalesced loads, 8 lanes per row, 4 rows per instruction
+    if (has_depth) {
+      if (vec) {
+        const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
+        for (uint32_t r = rsub; r < th; r += 4) {
+          const float4 z = *reinterpret_cast<const float4*>(T.depth + (size_t)(py0 + r) * T.w + px0 + c4);
           float* e = sz + r * RF_TILE_PITCH + c4;
           e[0] = z.x; e[1] = z.y; e[2] = z.z; e[3] = z.w;
         }
+      } else {
+        for (uint32_t r = 0; r < th; r++)
+          if (lane < tw) sz[r * RF_TILE_PITCH + lane] = T.depth[(size_t)(py0 + r) * T.w + px0 + lane];
       }
-    } else {
-      for (uint32_t r = 0; r < th; r++)
-        if (lane < tw) {
-          const size_t g = (size_t)(py0 + r) * T.w + px0 + lane;
-          sc[r * RF_TILE_PITCH + lane] = T.color[g];
-          if (has_depth) sz[r * RF_TILE_PITCH + lane] = T.depth[g];
-        }
     }
     __syncwarp();
 
@@ -568,19 +569,19 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
               const uint32_t base = py * RF_TILE_PITCH + pxs;
               if (smode == 4) {  // default Context + FS_TEX_CLAMP_LIT (crates): straight-line fragment code
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, sc, sz, base + k, v);
+                  my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, gc, T.w, sz, base + k, v);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                 }
               } else if (smode == 2) {
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, sc, sz, base + k, v);
+                  my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, sz, base + k, v);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                 }
               } else {
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment<LT>(D, fs, T.fmt, sc, sz, base + k, v, pmask, dtest, cwrite, dwrite);
+                  my_o += process_fragment<LT>(D, fs, T.fmt, gc, T.w, sz, base + k, v, pmask, dtest, cwrite, dwrite);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
                 }
@@ -650,10 +651,10 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
               const DrawDesc& D = UNI ? Du : P.draws[fdraw];
               uint32_t wrote = 0;
               auto one = [&]() -> uint32_t {
-                if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, sc, sz, pix, fv);
-                if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, T.fmt, sc, sz, pix, fv);
-                if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, sc, sz, pix, fv);
-                return process_fragment<LT>(D, fs, T.fmt, sc, sz, pix, fv, pmask, dtest, cwrite, dwrite);
+                if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, sz, pix, fv);
+                if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, T.fmt, gc, T.w, sz, pix, fv);
+                if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, gc, T.w, sz, pix, fv);
+                return process_fragment<LT>(D, fs, T.fmt, gc, T.w, sz, pix, fv, pmask, dtest, cwrite, dwrite);
               };
               if (__all_sync(0xFFFFFFFFu, earlier == 0)) {
                 if (fvalid) wrote = one();
@@ -694,25 +695,18 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
     }
     __syncwarp();
 
-    // ---- write the tile back: 128-bit coalesced stores
-    if (vec) {
-      const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
-      for (uint32_t r = rsub; r < th; r += 4) {
-        const size_t g = (size_t)(py0 + r) * T.w + px0 + c4;
-        const uint32_t* d = sc + r * RF_TILE_PITCH + c4;
-        *reinterpret_cast<uint4*>(T.color + g) = make_uint4(d[0], d[1], d[2], d[3]);
-        if (has_depth) {
+    // ---- write the depth tile back: 128-bit coalesced stores
+    if (has_depth) {
+      if (vec) {
+        const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
+        for (uint32_t r = rsub; r < th; r += 4) {
           const float* e = sz + r * RF_TILE_PITCH + c4;
-          *reinterpret_cast<float4*>(T.depth + g) = make_float4(e[0], e[1], e[2], e[3]);
+          *reinterpret_cast<float4*>(T.depth + (size_t)(py0 + r) * T.w + px0 + c4) = make_float4(e[0], e[1], e[2], e[3]);
         }
+      } else {
+        for (uint32_t r = 0; r < th; r++)
+          if (lane < tw) T.depth[(size_t)(py0 + r) * T.w + px0 + lane] = sz[r * RF_TILE_PITCH + lane];
       }
-    } else {
-      for (uint32_t r = 0; r < th; r++)
-        if (lane < tw) {
-          const size_t g = (size_t)(py0 + r) * T.w + px0 + lane;
-          T.color[g] = sc[r * RF_TILE_PITCH + lane];
-          if (has_depth) T.depth[g] = sz[r * RF_TILE_PITCH + lane];
-        }
     }
     __syncwarp();
   }
