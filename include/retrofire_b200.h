@@ -204,8 +204,9 @@ rf_status rf_ctx_last_pass(rf_ctx* ctx, uint64_t* time_ns, uint32_t* n_launches)
 
 /* ---- measurement (Stats::start/finish analogue, render/stats.rs:57-78, per kernel) ----------- */
 #define RF_N_KERNELS 10 /* kernels launched by one pass, in order; see rf_kernel_name */
-/* enable=1: record CUDA events between the pass kernels (on the ctx stream). Resets the sums. */
-rf_status rf_ctx_profile(rf_ctx* ctx, int enable);
+/* level 0: off. 1: CUDA events around k_raster only (the pass keeps its two-stream overlap).
+ * 2: events between all pass kernels, which are then serialised on the ctx stream. Resets the sums. */
+rf_status rf_ctx_profile(rf_ctx* ctx, int level);
 /* Device time (ns) and launch count per kernel accumulated since the last call; resets them. */
 rf_status rf_ctx_kernel_times(rf_ctx* ctx, uint64_t* ns /*[RF_N_KERNELS]*/, uint64_t* launches /*[RF_N_KERNELS]*/);
 const char* rf_kernel_name(uint32_t i);

@@ -284,8 +284,9 @@ class Device:
         self._check(self.lib.rf_ctx_last_pass(self.h, C.byref(t), C.byref(n)))
         return t.value, n.value
 
-    def profile(self, enable: bool = True):
-        self._check(self.lib.rf_ctx_profile(self.h, int(enable)))
+    def profile(self, level: int = 2):
+        """0 off; 1 time k_raster only (pass keeps its stream overlap); 2 time every kernel (serialised)."""
+        self._check(self.lib.rf_ctx_profile(self.h, int(level)))
 
     def kernel_times(self) -> dict:
         """{kernel: (total_ns, launches)} since the last call (profiling mode)."""

@@ -87,7 +87,8 @@ struct PassSlot {
   HostStatus* h_status = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   cudaEvent_t ev_k[RF_N_KERNELS + 1] = {};  // boundaries between the pass kernels (profiling mode)
-  bool profiled = false;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // binning chain runs on the ctx's side stream
+  int profiled = 0;
   uint32_t NV = 0, NP = 0, n_tiles = 0, lt = 0;
   uint32_t n_launches = 0;
 };
@@ -116,6 +117,7 @@ struct rf_mesh {
 struct rf_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;   // binning chain (k_bin_alloc/scatter/sort) overlaps the span chain (k_edge_ckpt/k_walk/k_ckpt)
   bool own_stream = false;
   int sm_count = 148;
   std::string err;
@@ -138,7 +140,7 @@ struct rf_ctx {
   rf_stats last_draw{};        // stats of the last draw of the last validated pass
   uint64_t last_pass_ns = 0;
   uint32_t last_pass_launches = 0;
-  bool profile = false;
+  int profile = 0;               // 0 off, 1 k_raster only (keeps the two-stream overlap), 2 every kernel (serialised)
   uint64_t kernel_ns[RF_N_KERNELS] = {};      // accumulated since the last query
   uint64_t kernel_launches[RF_N_KERNELS] = {};
 };
@@ -223,31 +225,43 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   const int sm = c->sm_count;
   cudaStream_t st = c->stream;
   auto blocks = [&](size_t n, int bs, int per_sm) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + bs - 1) / bs, (size_t)sm * per_sm)); };
-  const bool prof = c->profile;
+  const int prof = c->profile;
   s.profiled = prof;
-  int ek = 0;
-  auto mark = [&]() { if (prof) cudaEventRecord(s.ev_k[ek++], st); };
-  mark();
-  k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
-  mark();
-  k_setup<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
-  mark();
-  k_edge_ckpt<LT><<<sm * 4, 128, 0, st>>>(P);
-  mark();
-  k_walk<LT><<<sm * 12, 128, 0, st>>>(P);
-  mark();
-  k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, st>>>(P);
-  mark();
-  k_bin_scatter<<<sm * 8, 256, 0, st>>>(P);
-  mark();
-  k_ckpt<LT><<<sm * 8, 256, 0, st>>>(P);
-  mark();
-  k_bin_sort_warp<<<sm * 8, RF_SORT_WARPS * 32, 0, st>>>(P);
-  mark();
-  k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, st>>>(P);
-  mark();
-  k_raster<LT><<<sm * 7, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
-  mark();
+  const unsigned raster_blocks = sm * 7;
+  if (prof == 2) {  // serialised on one stream, an event between every pair of kernels
+    int ek = 0;
+    auto mark = [&]() { cudaEventRecord(s.ev_k[ek++], st); };
+    mark(); k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
+    mark(); k_setup<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+    mark(); k_edge_ckpt<LT><<<sm * 4, 128, 0, st>>>(P);
+    mark(); k_walk<LT><<<sm * 12, 128, 0, st>>>(P);
+    mark(); k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, st>>>(P);
+    mark(); k_bin_scatter<<<sm * 8, 256, 0, st>>>(P);
+    mark(); k_ckpt<LT><<<sm * 8, 256, 0, st>>>(P);
+    mark(); k_bin_sort_warp<<<sm * 8, RF_SORT_WARPS * 32, 0, st>>>(P);
+    mark(); k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, st>>>(P);
+    mark(); k_raster<LT><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
+    mark();
+  } else {
+    // two dependent chains after k_setup: spans (main stream) and bins (side stream), joined before k_raster
+    cudaStream_t sd = c->side;
+    k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
+    k_setup<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+    cudaEventRecord(s.ev_fork, st);
+    cudaStreamWaitEvent(sd, s.ev_fork, 0);
+    k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, sd>>>(P);
+    k_bin_scatter<<<sm * 4, 256, 0, sd>>>(P);
+    k_bin_sort_warp<<<sm * 4, RF_SORT_WARPS * 32, 0, sd>>>(P);
+    k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, sd>>>(P);
+    cudaEventRecord(s.ev_join, sd);
+    k_edge_ckpt<LT><<<sm * 4, 128, 0, st>>>(P);
+    k_walk<LT><<<sm * 12, 128, 0, st>>>(P);
+    k_ckpt<LT><<<sm * 8, 256, 0, st>>>(P);
+    cudaStreamWaitEvent(st, s.ev_join, 0);
+    if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS - 1], st);
+    k_raster<LT><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
+    if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS], st);
+  }
   s.n_launches += RF_N_KERNELS;
 }
 
@@ -471,7 +485,7 @@ rf_status validate_all(rf_ctx* c) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s.ev_start, s.ev_stop);
     if (s.profiled && !s.draws.empty()) {
-      for (int k = 0; k < RF_N_KERNELS; k++) {
+      for (int k = (s.profiled == 2 ? 0 : RF_N_KERNELS - 1); k < RF_N_KERNELS; k++) {
         float kms = 0.f;
         if (cudaEventElapsedTime(&kms, s.ev_k[k], s.ev_k[k + 1]) == cudaSuccess) { c->kernel_ns[k] += (uint64_t)(kms * 1e6); c->kernel_launches[k] += 1; }
       }
@@ -627,11 +641,13 @@ rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RF_E_CUDA; }
     c->own_stream = true;
   }
+  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) { rf_ctx_destroy(c); return RF_E_CUDA; }
   bool ok = cudaMalloc(&c->d_cstatus, sizeof(CtxStatus)) == cudaSuccess && cudaMemset(c->d_cstatus, 0, sizeof(CtxStatus)) == cudaSuccess;
   for (int k = 0; k < kSlots && ok; k++) {
     PassSlot& s = c->slots[k];
     ok = ok && cudaEventCreate(&s.ev_start) == cudaSuccess && cudaEventCreate(&s.ev_stop) == cudaSuccess;
     for (int e = 0; e <= RF_N_KERNELS && ok; e++) ok = cudaEventCreate(&s.ev_k[e]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_status), sizeof(HostStatus), cudaHostAllocDefault) == cudaSuccess;
   }
   ok = ok && cudaFuncSetAttribute(k_bin_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
@@ -655,10 +671,13 @@ void rf_ctx_destroy(rf_ctx* c) {
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
     for (int e = 0; e <= RF_N_KERNELS; e++) if (s.ev_k[e]) cudaEventDestroy(s.ev_k[e]);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    if (s.ev_join) cudaEventDestroy(s.ev_join);
   }
   c->cv.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
   if (c->d_cstatus) cudaFree(c->d_cstatus);
+  if (c->side) cudaStreamDestroy(c->side);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -900,7 +919,7 @@ rf_status rf_target_download_color_async(rf_ctx* c, rf_target* t, void* host, si
 rf_status rf_ctx_profile(rf_ctx* c, int enable) {
   if (!c) return RF_E_INVALID;
   rf_status st = sync_impl(c);
-  c->profile = enable != 0;
+  c->profile = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   std::memset(c->kernel_ns, 0, sizeof c->kernel_ns);
   std::memset(c->kernel_launches, 0, sizeof c->kernel_launches);
   return st;
