@@ -243,6 +243,56 @@ __device__ __forceinline__ void tile_row_cols(const HalfSetup<LT>& H0, const Hal
   cb = min(sat_u32(fb) >> RF_TILE_SHIFT, tiles_x - 1);
 }
 
+// Serial walk of one trapezoid half by the thread that set it up (ScanlineIter::next, raster.rs:80-114).
+// Used for triangles with few rows, where a separate row-parallel kernel costs more than it saves.
+template <int LT>
+__device__ __forceinline__ void walk_half_inline(const PassParams& P, const TargetDesc& T, HalfSetup<LT>& H, uint32_t& sidx, uint32_t own,
+                                                 unsigned long long& frags_i) {
+  constexpr int NL = 2 + LT;
+  constexpr int SW = Rec<LT>::SW;
+  float y = H.y;
+  for (uint32_t j = 0; j < H.n; j++) {
+    float v0[NL];
+#pragma unroll
+    for (int i = 0; i < NL; i++) { v0[i] = H.L[i]; H.L[i] = H.L[i] + H.dl[i]; }
+    const float x1 = H.R;
+    H.R = H.R + H.dr;
+    const float x0r = round_up_to_half(v0[0]), x1r = round_up_to_half(x1);
+    const float tx = x0r - v0[0];
+    uint32_t w[SW];
+#pragma unroll
+    for (int i = 1; i < NL; i++) w[2 + (i - 1)] = __float_as_uint(v0[i] + ((v0[i] + H.dv[i]) - v0[i]) * tx);
+#pragma unroll
+    for (int i = 2 + NL - 1; i < SW; i++) w[i] = 0u;
+    const uint32_t cnt = sat_u32(x1r - x0r);
+    const uint32_t Yf = sat_u32(y), X0 = sat_u32(x0r), X1 = max(sat_u32(x1r), X0);
+    uint32_t nn = min(cnt, X1 - X0);
+    if (Yf >= T.h || X1 > T.w) {  // target.rs:148,173-174 (slice index panics)
+      atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
+      nn = 0;
+    } else if (Yf < T.band_y0 || Yf >= T.band_y1) {
+      nn = 0;  // not this GPU's row band
+    } else {
+      frags_i += X1 - X0;
+    }
+    if (nn && ((X0 + nn - 1) >> RF_TILE_SHIFT) != (X0 >> RF_TILE_SHIFT)) {  // crosses a tile column: k_ckpt adds checkpoints
+      const unsigned long long slot = agg_atomic_inc(&P.status->long_needed);
+      if (slot < P.cap_long) P.longlist[slot] = make_uint2(sidx, own);
+      else { P.status->overflow = 1; P.cstatus->poison = 1; }
+    }
+    w[0] = X0 | nn << 16;
+    w[1] = RF_NO_CKPT;
+    uint32_t* sr = P.spans + (size_t)sidx * SW;
+#pragma unroll
+    for (int q = 0; q < SW / 2; q++) *reinterpret_cast<uint2*>(sr + 2 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
+    sidx++;
+    y = y + 1.0f;
+  }
+}
+
+// Triangles with at most this many scanlines are walked inline by k_setup; taller ones go to k_walk in chunks.
+#define RF_INLINE_ROWS 12u
+
 // =============================================================================================
 // K2a k_setup: one thread per input primitive — assembly, clip, to_screen, cull, triangle setup.
 // Emits, with warp-aggregated allocation (warp prefix sums): a triangle record, its span range,
@@ -252,7 +302,7 @@ __device__ __forceinline__ void tile_row_cols(const HalfSetup<LT>& H0, const Hal
 #define RF_LONG_BLOCK 256u
 
 template <int LT>
-__global__ void __launch_bounds__(128) k_setup(PassParams P) {
+__global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
   constexpr int NL = 2 + LT, NV = 1 + LT;
   constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS;
   using TR = TriRec<LT>;
@@ -294,6 +344,7 @@ __global__ void __launch_bounds__(128) k_setup(PassParams P) {
     for (int o = 16; o > 0; o >>= 1) max_tri = max(max_tri, __shfl_xor_sync(0xFFFFFFFFu, max_tri, o));
 
     uint32_t my_prims_o = 0;
+    unsigned long long my_frags_i = 0;
 
     for (uint32_t t = 0; t < max_tri; t++) {
       bool emit = false;
@@ -384,8 +435,7 @@ __global__ void __launch_bounds__(128) k_setup(PassParams P) {
                   nent += cb - ca + 1;
                 }
               } else { tr0 = 1; tr1 = 0; }
-              const uint32_t ch0 = (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = (H1.n + RF_CHUNK - 1) / RF_CHUNK;
-              nchunk = ch0 + ch1;
+              if (nrows > RF_INLINE_ROWS) nchunk = (H0.n + RF_CHUNK - 1) / RF_CHUNK + (H1.n + RF_CHUNK - 1) / RF_CHUNK;
             }
           }
         }
@@ -419,7 +469,8 @@ __global__ void __launch_bounds__(128) k_setup(PassParams P) {
       uint32_t eidx = (uint32_t)eb + (incl_e - nent);
       uint32_t cidx = (uint32_t)cb_ + (incl_c - nchunk);
       const uint32_t key = gp * 8u + t;
-      const uint32_t ch0 = (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = (H1.n + RF_CHUNK - 1) / RF_CHUNK;
+      const bool inline_walk = H0.n + H1.n <= RF_INLINE_ROWS;
+      const uint32_t ch0 = inline_walk ? 0u : (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = inline_walk ? 0u : (H1.n + RF_CHUNK - 1) / RF_CHUNK;
       const uint32_t eck0 = cidx, eck1 = cidx + ch0;  // edge checkpoints are indexed by chunk position
       {  // triangle record
         uint32_t* tr = P.tris + (size_t)tri_idx * TW;
@@ -460,6 +511,12 @@ __global__ void __launch_bounds__(128) k_setup(PassParams P) {
         P.chunks[cidx++] = make_uint4(tri_idx * 2u, c | min(RF_CHUNK, H0.n - c * RF_CHUNK) << 16, sbase + c * RF_CHUNK, d | tgt << 16);
       for (uint32_t c = 0; c < ch1; c++)
         P.chunks[cidx++] = make_uint4(tri_idx * 2u + 1u, c | min(RF_CHUNK, H1.n - c * RF_CHUNK) << 16, sbase + H0.n + c * RF_CHUNK, d | tgt << 16);
+      if (inline_walk) {  // few rows: walk them here, serially (sequential adds down both edges)
+        const TargetDesc& T = P.targets[tgt];
+        uint32_t sidx = sbase;
+        walk_half_inline<LT>(P, T, H0, sidx, tri_idx * 2u, my_frags_i);
+        walk_half_inline<LT>(P, T, H1, sidx, tri_idx * 2u + 1u, my_frags_i);
+      }
       if (ch0 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
       if (ch1 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u + 1u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
     }
@@ -469,11 +526,14 @@ __global__ void __launch_bounds__(128) k_setup(PassParams P) {
       const bool uniform = __all_sync(0xFFFFFFFFu, !have || d == d0);
       if (uniform) {
         uint32_t po = my_prims_o;
+        unsigned long long fi = my_frags_i;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) po += __shfl_xor_sync(0xFFFFFFFFu, po, o);
+        for (int o = 16; o > 0; o >>= 1) { po += __shfl_xor_sync(0xFFFFFFFFu, po, o); fi += __shfl_xor_sync(0xFFFFFFFFu, fi, o); }
         if (lane == 0 && po) atomicAdd(&P.dstats[d0].prims_o, (unsigned long long)po);
-      } else if (have && my_prims_o) {
-        atomicAdd(&P.dstats[d].prims_o, (unsigned long long)my_prims_o);
+        if (lane == 0 && fi) atomicAdd(&P.dstats[d0].frags_i, fi);
+      } else if (have) {
+        if (my_prims_o) atomicAdd(&P.dstats[d].prims_o, (unsigned long long)my_prims_o);
+        if (my_frags_i) atomicAdd(&P.dstats[d].frags_i, my_frags_i);
       }
     }
   }

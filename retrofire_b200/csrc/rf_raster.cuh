@@ -366,7 +366,7 @@ template <int LT> struct RasterSmem {
 };
 
 template <int LT>
-__global__ void __launch_bounds__(RF_RASTER_WARPS * 32) k_raster(PassParams P) {
+__global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raster(PassParams P) {
   constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW;
   constexpr int NV = 1 + LT;
   extern __shared__ uint32_t s_raster[];
