@@ -355,6 +355,24 @@ def random_soup(n: int, w: int, h: int, seed: int, *, lanes_kind: str = "color3"
         attr = np.concatenate([nrm, g.uniform(-0.2, 1.2, (n, 3, 2)).astype(f32)], 2).astype(f32)
         tex = g.integers(0, 256, (32, 32, 3), dtype=np.uint8)
         shd = shader.new(_ffi.VS_MVP, _ffi.FS_TEX_CLAMP_LIT, fs_uniform=mx.normalize([-2.0, 1.0, -4.0]), texture=Texture(tex))
+    elif lanes_kind == "color4":
+        attr = g.uniform(-0.1, 1.1, (n, 3, 4)).astype(f32)
+        shd = shader.new(_ffi.VS_MVP, _ffi.FS_COLOR4F)
+    elif lanes_kind == "checker":
+        attr = g.uniform(-0.5, 1.5, (n, 3, 2)).astype(f32)
+        shd = shader.new(_ffi.VS_MVP, _ffi.FS_CHECKER)
+    elif lanes_kind == "normal":
+        attr = g.normal(size=(n, 3, 3)).astype(f32)
+        shd = shader.new(_ffi.VS_MVP, _ffi.FS_NORMAL_VIS)
+    elif lanes_kind == "texclamp":
+        attr = g.uniform(-0.5, 1.5, (n, 3, 2)).astype(f32)
+        tex = g.integers(0, 256, (13, 7, 4), dtype=np.uint8)   # non-power-of-two RGBA texture
+        shd = shader.new(_ffi.VS_MVP, _ffi.FS_TEX_CLAMP, texture=Texture(tex))
+    elif lanes_kind == "lanes8":
+        # 8 varying lanes (the widest kernel instantiation); the colour shader reads the first three,
+        # two of which are declared perspective-divided to exercise z_div on a colour shader
+        attr = g.uniform(0.05, 1, (n, 3, 8)).astype(f32)
+        shd = shader.new(_ffi.VS_MVP, _ffi.FS_COLOR3F, lanes=8, persp_mask=0b10100101)
     else:
         raise ValueError(lanes_kind)
     verts = np.concatenate([pos, attr], 2).reshape(3 * n, -1).astype(f32)

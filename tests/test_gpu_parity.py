@@ -55,6 +55,72 @@ def test_random_soup(device, oracle, kind, big):
         check(device, oracle, sc)
 
 
+@pytest.mark.parametrize("kind", ["color4", "checker", "normal", "texclamp", "lanes8"])
+def test_remaining_catalogue_shaders_and_widest_lanes(device, oracle, kind):
+    """FS_COLOR4F, FS_CHECKER, FS_NORMAL_VIS, FS_TEX_CLAMP on a non-POT RGBA texture, and 8 varying lanes."""
+    for big in (False, True):
+        check(device, oracle, scenes.random_soup(1200 if not big else 300, 512, 300, seed=13, lanes_kind=kind, big=big))
+
+
+def test_non_pot_texture_with_repeat_sampler_is_an_error(device):
+    """SamplerRepeatPot::new asserts power-of-two dimensions (render/tex.rs:230-231)."""
+    sc = scenes.random_soup(10, 64, 64, seed=1, lanes_kind="uv")
+    d = sc.draws[0]
+    d.shader.texture = rf.Texture(np.zeros((12, 10, 3), np.uint8))
+    fb = device.framebuf(64, 64, sc.fmt, True)
+    with pytest.raises(rf.RetrofireError) as e:
+        device.render(d, fb, want_stats=True)
+    assert e.value.status == rf.RF_E_BAD_TEXTURE
+
+
+def test_unsupported_options_are_reported(device):
+    """depth_sort is outside the path; a fragment shader with too few lanes is rejected."""
+    sc = scenes.hello_tri()
+    d = sc.draws[0]
+    fb = device.framebuf(sc.w, sc.h, sc.fmt, False)
+    import dataclasses
+    with pytest.raises(rf.RetrofireError) as e:
+        device.render(dataclasses.replace(d, depth_sort=1), fb, want_stats=True)
+    assert e.value.status == rf.RF_E_UNSUPPORTED
+    bad = dataclasses.replace(d, shader=rf.shader.new(rf.VS_MVP, rf.FS_TEX_CLAMP_LIT, lanes=3, persp_mask=0))
+    with pytest.raises(rf.RetrofireError) as e:
+        device.render(bad, fb, want_stats=True)
+    assert e.value.status in (rf.RF_E_UNSUPPORTED_SHADER, rf.RF_E_INVALID)
+
+
+def test_many_small_draws_one_pass(device, oracle):
+    """Hundreds of tiny render() calls queued into one pass (the crates demo pattern, crates.rs:114-131)."""
+    base = scenes.random_soup(900, 400, 300, seed=77, lanes_kind="lit", big=False)
+    d = base.draws[0]
+    import dataclasses
+    draws = []
+    for k in range(300):
+        draws.append(dataclasses.replace(d, prims=np.ascontiguousarray(d.prims[3 * k: 3 * k + 3])))
+    base.draws = draws
+    check(device, oracle, base)
+
+
+def test_frame_batch_render_frames(device, oracle):
+    """rf_render_frames: one mesh, per-frame uniforms, per-frame targets (SURVEY 8e frame sharding)."""
+    verts, faces = scenes.bunny_mesh(0)
+    frames = [scenes.bunny(subdiv=0, theta=0.5 * f, w=640, h=360) for f in range(4)]
+    mesh = device.mesh(faces, verts)
+    import dataclasses
+    call = dataclasses.replace(frames[0].draws[0], mesh=mesh)
+    targets = [device.framebuf(640, 360, frames[0].fmt, True) for _ in frames]
+    for t in targets:
+        t.clear(frames[0].ctx)
+    device.stats(reset=True)
+    device.render_frames(call, targets, np.stack([f.draws[0].uniform for f in frames]))
+    got_stats = device.stats(reset=True)
+    want_total = rf.Stats()
+    for f, t in zip(frames, targets):
+        wc, wd, ws = run_oracle(oracle, f)
+        want_total += ws
+        assert np.array_equal(t.download_color(), wc) and np.array_equal(t.download_depth().view(np.uint32), wd.view(np.uint32))
+    assert got_stats.counters() == want_total.counters()
+
+
 def test_odd_sized_target(device, oracle):
     """Width/height not multiples of the tile or of 4 (scalar tile I/O path)."""
     sc = scenes.random_soup(500, 333, 211, seed=5, lanes_kind="color3", big=True)
@@ -114,6 +180,42 @@ def test_sprites(device, oracle):
 def test_crates_169_reduced(device, oracle):
     """BASELINE config 3, reference layout, 1920x1080: 170 draws, long perspective-correct spans."""
     check(device, oracle, scenes.crates("169", w=1920, h=1080))
+
+
+def test_crates_1089_full_4k(device, oracle):
+    """BASELINE config 3 at full size: 3840x2160, one draw per cube + floor, perspective-correct textured."""
+    check(device, oracle, scenes.crates("1089"))
+
+
+def test_sprites_10k_full(device, oracle):
+    """BASELINE config 4 at full size: 10,000 sphere sprites (20,000 tris), discard + overdraw, 1920x1080."""
+    check(device, oracle, scenes.sprites(10000))
+
+
+def test_small_tris_1m_8k(device, oracle):
+    """BASELINE config 5(i) at full size: 1,000,000 small triangles at 7680x4320."""
+    check(device, oracle, scenes.small_tris(1_000_000))
+
+
+def test_small_tris_8k_row_bands_cover_the_frame(device, oracle):
+    """Sort-first property at full size: rendering the 8 row bands separately and stacking them
+    equals the unsharded frame; frags counters add up."""
+    from retrofire_b200 import shard
+    sc = scenes.small_tris(200_000)
+    full_c, full_d, full_s = run_gpu(device, sc)
+    acc_c, acc_d = np.zeros_like(full_c), np.zeros_like(full_d)
+    fi = fo = 0
+    for (y0, y1) in shard.row_bands(sc.h, 8):
+        device.set_row_band(y0, y1)
+        try:
+            c, d, st = run_gpu(device, sc)
+        finally:
+            device.set_row_band(0, 0xFFFFFFFF)
+        acc_c[y0:y1], acc_d[y0:y1] = c[y0:y1], d[y0:y1]
+        fi += st.frags.i
+        fo += st.frags.o
+    assert np.array_equal(acc_c, full_c) and np.array_equal(acc_d.view(np.uint32), full_d.view(np.uint32))
+    assert (fi, fo) == (full_s.frags.i, full_s.frags.o)
 
 
 def test_empty_and_degenerate(device, oracle):
