@@ -101,6 +101,8 @@ struct rf_target {
   bool has_depth;
   uint32_t* d_color;
   float* d_depth;
+  cudaEvent_t dl_done = nullptr;  // completion of the last asynchronous download (copy stream)
+  bool dl_pending = false;
 };
 struct rf_texture {
   rf_ctx* ctx;
@@ -117,6 +119,8 @@ struct rf_mesh {
 struct rf_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy = nullptr;   // asynchronous downloads: D2H overlaps the next pass
+  cudaEvent_t ev_copy = nullptr;
   cudaStream_t side = nullptr;   // binning chain (k_bin_alloc/scatter/sort) overlaps the span chain (k_edge_ckpt/k_walk/k_ckpt)
   bool own_stream = false;
   int sm_count = 148;
@@ -381,6 +385,9 @@ rf_status launch_pass(rf_ctx* c, int si) {
   }
 
   cudaStream_t st = c->stream;
+  // a target that is still being downloaded on the copy stream must not be overwritten yet
+  for (rf_target* t : s.targets) if (t->dl_pending) { RF_CUDA(c, cudaStreamWaitEvent(st, t->dl_done, 0)); t->dl_pending = false; }
+  for (const QueuedClear& qc : s.clears) if (qc.target->dl_pending) { RF_CUDA(c, cudaStreamWaitEvent(st, qc.target->dl_done, 0)); qc.target->dl_pending = false; }
   RF_CUDA(c, cudaEventRecord(s.ev_start, st));
   s.n_launches = 0;
   RF_CUDA(c, cudaMemcpyAsync(s.d_table.p, tb, coff + ncl * sizeof(ClearDesc), cudaMemcpyHostToDevice, st));
@@ -545,6 +552,7 @@ rf_status sync_impl(rf_ctx* c) {
   rf_status sv = validate_all(c);
   if (st == RF_OK) st = sv;
   if (st == RF_OK) RF_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (st == RF_OK) RF_CUDA(c, cudaStreamSynchronize(c->copy));
   return st;
 }
 
@@ -641,7 +649,8 @@ rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RF_E_CUDA; }
     c->own_stream = true;
   }
-  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) { rf_ctx_destroy(c); return RF_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) { rf_ctx_destroy(c); return RF_E_CUDA; }
   bool ok = cudaMalloc(&c->d_cstatus, sizeof(CtxStatus)) == cudaSuccess && cudaMemset(c->d_cstatus, 0, sizeof(CtxStatus)) == cudaSuccess;
   for (int k = 0; k < kSlots && ok; k++) {
     PassSlot& s = c->slots[k];
@@ -678,6 +687,8 @@ void rf_ctx_destroy(rf_ctx* c) {
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
   if (c->d_cstatus) cudaFree(c->d_cstatus);
   if (c->side) cudaStreamDestroy(c->side);
+  if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -695,7 +706,7 @@ rf_status rf_target_create(rf_ctx* c, uint32_t w, uint32_t h, uint32_t fmt, int 
   if (!c || !out || !w || !h || fmt > RF_FMT_RGBA4444) return fail(c, RF_E_INVALID, "bad target arguments");
   if (w > kMaxTargetDim || h > kMaxTargetDim) return fail(c, RF_E_INVALID, "target larger than %ux%u", kMaxTargetDim, kMaxTargetDim);
   cudaSetDevice(c->device);
-  rf_target* t = new rf_target{c, w, h, fmt, has_depth != 0, nullptr, nullptr};
+  rf_target* t = new rf_target{c, w, h, fmt, has_depth != 0, nullptr, nullptr, nullptr, false};
   const size_t n = (size_t)w * h;
   if (cudaMalloc(&t->d_color, n * 4) != cudaSuccess) { delete t; return fail(c, RF_E_NOMEM, "colour buffer"); }
   if (has_depth && cudaMalloc(&t->d_depth, n * 4) != cudaSuccess) { cudaFree(t->d_color); delete t; return fail(c, RF_E_NOMEM, "depth buffer"); }
@@ -708,6 +719,7 @@ rf_status rf_target_create(rf_ctx* c, uint32_t w, uint32_t h, uint32_t fmt, int 
 void rf_target_destroy(rf_target* t) {
   if (!t) return;
   sync_impl(t->ctx);
+  if (t->dl_done) cudaEventDestroy(t->dl_done);
   cudaFree(t->d_color);
   if (t->d_depth) cudaFree(t->d_depth);
   delete t;
@@ -912,7 +924,13 @@ rf_status rf_target_download_color_async(rf_ctx* c, rf_target* t, void* host, si
   if (host_bytes(t->fmt) != 4) return fail(c, RF_E_UNSUPPORTED, "async download needs a 4-byte pixel format");
   rf_status st = flush_impl(c);
   if (st) return st;
-  RF_CUDA(c, cudaMemcpy2DAsync(host, stride * 4, t->d_color, (size_t)t->w * 4, (size_t)t->w * 4, t->h, cudaMemcpyDeviceToHost, c->stream));
+  // the copy runs on its own stream, after everything queued so far, and overlaps later passes
+  RF_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
+  RF_CUDA(c, cudaStreamWaitEvent(c->copy, c->ev_copy, 0));
+  RF_CUDA(c, cudaMemcpy2DAsync(host, stride * 4, t->d_color, (size_t)t->w * 4, (size_t)t->w * 4, t->h, cudaMemcpyDeviceToHost, c->copy));
+  if (!t->dl_done) RF_CUDA(c, cudaEventCreateWithFlags(&t->dl_done, cudaEventDisableTiming));
+  RF_CUDA(c, cudaEventRecord(t->dl_done, c->copy));
+  t->dl_pending = true;
   return RF_OK;
 }
 
