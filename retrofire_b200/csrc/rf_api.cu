@@ -2,7 +2,7 @@
 //
 // A "pass" is every draw queued between two flush points, executed in submission order by
 // one chain of kernels:
-//   [k_clear_multi] -> k_vertex -> k_setup -> k_edge_ckpt -> k_walk -> k_bin_alloc -> k_bin_scatter -> k_ckpt -> k_bin_sort_* -> k_raster
+//   [k_clear_multi] -> k_vertex -> k_assemble -> k_setup -> k_edge_ckpt -> k_walk -> k_bin_alloc -> k_bin_scatter -> k_ckpt -> k_bin_sort_* -> k_raster
 // Passes are launched asynchronously on the ctx stream and validated lazily (capacity overflow
 // or device-detected errors) at the next synchronisation point; an overflowing pass poisons
 // the ctx on the device so that later passes become no-ops until the host has grown the
@@ -132,10 +132,10 @@ struct rf_ctx {
   std::vector<int> flight;     // slots launched and not yet validated, oldest first
 
   // scratch arenas shared by all passes (stream order makes reuse safe)
-  DevBuf cv, spans, tris, entries, bins, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
+  DevBuf cv, stris, spans, tris, entries, bins, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
   // capacities: spans/tris/ckpts in 32-bit WORDS (record width depends on the pass's lane count),
   // entries and long spans in records
-  size_t capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
+  size_t capw_stris = 0, capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
   CtxStatus* d_cstatus = nullptr;
   DevBuf bounce;               // upload/download staging on the device
   PinnedBuf h_bounce;
@@ -175,10 +175,11 @@ size_t words_cv(int lt) { return lt == 3 ? Rec<3>::CVS : lt == 5 ? Rec<5>::CVS :
 size_t words_span(int lt) { return lt == 3 ? Rec<3>::SW : lt == 5 ? Rec<5>::SW : Rec<8>::SW; }
 size_t words_tri(int lt) { return lt == 3 ? Rec<3>::TW : lt == 5 ? Rec<5>::TW : Rec<8>::TW; }
 size_t words_ckpt(int lt) { return lt == 3 ? Rec<3>::KW : lt == 5 ? Rec<5>::KW : Rec<8>::KW; }
+size_t words_stri(int lt) { return lt == 3 ? Rec<3>::QW : lt == 5 ? Rec<5>::QW : Rec<8>::QW; }
 size_t words_eck(int lt) { return lt == 3 ? Rec<3>::EW : lt == 5 ? Rec<5>::EW : Rec<8>::EW; }
 
 struct ArenaWants {  // spans/tris/ckpts/ecks in words, the rest in records
-  size_t w_spans, w_tris, w_ckpts, w_ecks, entries, longs, chunks, tall;
+  size_t w_spans, w_tris, w_ckpts, w_stris, entries, longs, chunks, tall;
 };
 
 // ---- small utility kernels --------------------------------------------------------------------
@@ -236,7 +237,8 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     int ek = 0;
     auto mark = [&]() { cudaEventRecord(s.ev_k[ek++], st); };
     mark(); k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
-    mark(); k_setup<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+    mark(); k_assemble<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+    mark(); k_setup<LT><<<sm * 8, 128, 0, st>>>(P);
     mark(); k_edge_ckpt<LT><<<sm * 4, 128, 0, st>>>(P);
     mark(); k_walk<LT><<<sm * 12, 128, 0, st>>>(P);
     mark(); k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, st>>>(P);
@@ -250,7 +252,8 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     // two dependent chains after k_setup: spans (main stream) and bins (side stream), joined before k_raster
     cudaStream_t sd = c->side;
     k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
-    k_setup<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+    k_assemble<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+    k_setup<LT><<<sm * 8, 128, 0, st>>>(P);
     cudaEventRecord(s.ev_fork, st);
     cudaStreamWaitEvent(sd, s.ev_fork, 0);
     k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, sd>>>(P);
@@ -272,6 +275,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
 // Any growth frees memory that in-flight kernels might still use -> callers guarantee idleness.
 rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const ArenaWants& w) {
   if (!c->cv.reserve(nv * words_cv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "clip-vertex arena");
+  if (w.w_stris > c->capw_stris) { if (!c->stris.reserve(w.w_stris * 4)) return fail(c, RF_E_NOMEM, "screen-triangle arena"); c->capw_stris = w.w_stris; }
   if (w.w_spans > c->capw_spans) { if (!c->spans.reserve(w.w_spans * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->capw_spans = w.w_spans; }
   if (w.w_tris > c->capw_tris) { if (!c->tris.reserve(w.w_tris * 4)) return fail(c, RF_E_NOMEM, "triangle arena"); c->capw_tris = w.w_tris; }
   if (w.w_ckpts > c->capw_ckpts) { if (!c->ckpts.reserve(w.w_ckpts * 4)) return fail(c, RF_E_NOMEM, "checkpoint arena"); c->capw_ckpts = w.w_ckpts; }
@@ -291,7 +295,7 @@ rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const Aren
 }
 
 bool arenas_cover(const rf_ctx* c, const ArenaWants& w) {
-  return w.w_spans <= c->capw_spans && w.w_tris <= c->capw_tris && w.w_ckpts <= c->capw_ckpts &&
+  return w.w_stris <= c->capw_stris && w.w_spans <= c->capw_spans && w.w_tris <= c->capw_tris && w.w_ckpts <= c->capw_ckpts &&
          w.entries <= c->cap_entries && w.longs <= c->cap_long && w.chunks <= c->cap_chunks && w.tall <= c->cap_tall;
 }
 
@@ -329,7 +333,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   s.NV = nv; s.NP = np; s.n_tiles = ntiles;
   // initial arena sizes (grown on demand by validate_all after an overflowing pass)
   ArenaWants want{std::max<size_t>(c->capw_spans, (size_t)8 << 20), std::max<size_t>(c->capw_tris, (size_t)8 << 20),
-                  std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), 0,
+                  std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), std::max<size_t>(c->capw_stris, (size_t)8 << 20),
                   std::max<size_t>(c->cap_entries, (size_t)1 << 20), std::max<size_t>(c->cap_long, (size_t)1 << 19),
                   std::max<size_t>(c->cap_chunks, (size_t)1 << 20), std::max<size_t>(c->cap_tall, (size_t)1 << 18)};
   need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 20 + 64 ||
@@ -417,6 +421,8 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.targets = reinterpret_cast<const TargetDesc*>(dt + toff);
   P.n_draws = (uint32_t)nd; P.n_targets = (uint32_t)nt; P.NV = nv; P.NP = np; P.n_tiles = ntiles;
   P.cv = static_cast<float*>(c->cv.p);
+  P.stris = static_cast<uint32_t*>(c->stris.p);
+  P.cap_stris = (uint32_t)std::min<size_t>(c->capw_stris / words_stri(lt), 0x1FFFFFF0u);
   P.spans = static_cast<uint32_t*>(c->spans.p);
   P.tris = static_cast<uint32_t*>(c->tris.p);
   P.entries = static_cast<uint4*>(c->entries.p);
@@ -476,11 +482,11 @@ rf_status validate_all(rf_ctx* c) {
       const int lt = (int)s.lt;
       auto grow = [](size_t cap, unsigned long long need) { return need > cap ? (size_t)(need + need / 4 + 4096) : cap; };
       // counters downstream of an overflowed stage are incomplete: guess them from the span count
-      const bool early = ps.spans_needed * words_span(lt) > c->capw_spans || ps.tris_needed * words_tri(lt) > c->capw_tris ||
+      const bool early = ps.stris_needed * words_stri(lt) > c->capw_stris || ps.spans_needed * words_span(lt) > c->capw_spans || ps.tris_needed * words_tri(lt) > c->capw_tris ||
                          ps.chunks_needed > c->cap_chunks || ps.entries_needed > c->cap_entries;
       ArenaWants w{grow(c->capw_spans, ps.spans_needed * words_span(lt)), grow(c->capw_tris, ps.tris_needed * words_tri(lt)),
                    grow(c->capw_ckpts, std::max<unsigned long long>(ps.ckpts_needed, early ? ps.spans_needed / 8 : 0) * words_ckpt(lt)),
-                   0, grow(c->cap_entries, ps.entries_needed),
+                   grow(c->capw_stris, ps.stris_needed * words_stri(lt)), grow(c->cap_entries, ps.entries_needed),
                    grow(c->cap_long, std::max<unsigned long long>(ps.long_needed, early ? ps.spans_needed / 8 : 0)),
                    grow(c->cap_chunks, ps.chunks_needed), grow(c->cap_tall, ps.tall_needed)};
       { rf_status st = ensure_arenas(c, lt, s.NV, s.n_tiles, w); if (st) return st; }
@@ -683,7 +689,7 @@ void rf_ctx_destroy(rf_ctx* c) {
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
   }
-  c->cv.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
+  c->cv.release(); c->stris.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
   if (c->d_cstatus) cudaFree(c->d_cstatus);
   if (c->side) cudaStreamDestroy(c->side);
@@ -954,7 +960,7 @@ rf_status rf_ctx_kernel_times(rf_ctx* c, uint64_t* ns, uint64_t* launches) {
 }
 
 const char* rf_kernel_name(uint32_t i) {
-  static const char* names[RF_N_KERNELS] = {"k_vertex", "k_setup", "k_edge_ckpt", "k_walk", "k_bin_alloc", "k_bin_scatter", "k_ckpt", "k_bin_sort_warp", "k_bin_sort_big", "k_raster"};
+  static const char* names[RF_N_KERNELS] = {"k_vertex", "k_assemble", "k_setup", "k_edge_ckpt", "k_walk", "k_bin_alloc", "k_bin_scatter", "k_ckpt", "k_bin_sort_warp", "k_bin_sort_big", "k_raster"};
   return i < RF_N_KERNELS ? names[i] : "";
 }
 

@@ -55,21 +55,30 @@ struct DrawStats {
   unsigned long long prims_o, frags_i, frags_o;
 };
 
-// zeroed before every pass; read back after it
+// zeroed before every pass; read back after it.
+// Every allocation counter sits in its own 128-byte line: they are hit by one atomic per warp from
+// thousands of warps, and atomics on one line serialise in a single L2 slice.
+struct alignas(128) PaddedCounter {
+  unsigned long long v;
+  unsigned long long _pad[15];
+  __host__ __device__ operator unsigned long long() const { return v; }
+};
+__device__ __forceinline__ unsigned long long atomicAdd(PaddedCounter* c, unsigned long long n) { return atomicAdd(&c->v, n); }
+
 struct PassStatus {
-  unsigned long long spans_needed;    // span records the pass wants (one per scanline of every drawn triangle)
-  unsigned long long tris_needed;     // triangle records
-  unsigned long long entries_needed;  // bin entry slots (triangle x bounding-box tile)
-  unsigned long long chunks_needed;   // walk chunks (<= 32 rows of one trapezoid half)
-  unsigned long long tall_needed;     // halves with more than one chunk
-  unsigned long long ecks_needed;     // edge checkpoints (state of both edges at each later chunk start)
-  unsigned long long long_needed;     // spans that cross a tile-column boundary
-  unsigned long long ckpts_needed;    // checkpoint records for those spans
-  unsigned long long bins_needed;     // valid bin entries = total size of all tile bins
-  uint32_t error;                     // RF_ERRBIT_*
-  uint32_t overflow;                  // a capacity was exceeded: nothing was rasterised
-  uint32_t n_work;                    // non-empty tiles
-  uint32_t n_work_big;                // tiles whose bin needs the large-smem sort
+  PaddedCounter stris_needed;    // screen triangles surviving clip + cull
+  PaddedCounter spans_needed;    // span records the pass wants (one per scanline of every drawn triangle)
+  PaddedCounter tris_needed;     // triangle records
+  PaddedCounter entries_needed;  // bin entries (triangle x overlapped tile)
+  PaddedCounter chunks_needed;   // walk chunks (<= 32 rows of one trapezoid half)
+  PaddedCounter tall_needed;     // halves with more than one chunk
+  PaddedCounter long_needed;     // spans that cross a tile-column boundary
+  PaddedCounter ckpts_needed;    // checkpoint records for those spans
+  PaddedCounter bins_needed;     // total size of all tile bins
+  uint32_t error;                // RF_ERRBIT_*
+  uint32_t overflow;             // a capacity was exceeded: nothing was rasterised
+  uint32_t n_work;               // non-empty tiles
+  uint32_t n_work_big;           // tiles whose bin needs the large-smem sort
   uint32_t max_bin;
   uint32_t _pad;
 };
@@ -93,6 +102,8 @@ struct PassParams {
   const TargetDesc* targets;
   uint32_t n_draws, n_targets, NV, NP, n_tiles;
   float* cv;              // clip verts [NV][CVS]
+  uint32_t* stris;        // [cap_stris][QW]   compacted screen triangles (k_assemble -> k_setup)
+  uint32_t cap_stris;
   uint32_t* spans;        // [cap_spans][SW]   one per scanline, contiguous per triangle
   uint32_t* tris;         // [cap_tris][TW]    per drawn triangle: key, draw, rows, dv/dx of both halves
   uint4* entries;         // [cap_entries]     {tile, key, tri, 0}: one per (triangle, overlapped tile)
@@ -126,6 +137,7 @@ template <int LT> struct Rec {
   static constexpr int TW = 8 + 2 * HS;                // tri: 8 header words + two half setups (see TriRec)
   static constexpr int EW = (2 + LT + 1 + 1) & ~1;     // edge checkpoint: L[2+LT], R                        (8 B aligned)
   static constexpr int KW = (1 + LT + 1) & ~1;         // checkpoint: z, attr[LT]                   (8 B aligned)
+  static constexpr int QW = (2 + 3 * (3 + LT) + 3) & ~3;  // screen triangle: key, draw, 3 x (x,y,z,attr[LT]) (16 B aligned)
 };
 
 // ---- Rust `as` casts (saturating, NaN -> 0). PTX cvt.rzi.{u32,s32}.f32 clamps and maps NaN to 0.
@@ -211,7 +223,7 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v) {
 
 // Warp-aggregated increment usable from divergent code: the currently converged lanes elect a
 // leader that performs one atomic for the group; returns this lane's slot.
-__device__ __forceinline__ unsigned long long agg_atomic_inc(unsigned long long* ctr) {
+__device__ __forceinline__ unsigned long long agg_atomic_inc(PaddedCounter* ctr) {
   const uint32_t mask = __activemask();
   const int leader = __ffs(mask) - 1;
   unsigned long long base = 0;

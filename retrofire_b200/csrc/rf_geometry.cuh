@@ -246,8 +246,8 @@ __device__ __forceinline__ void tile_row_cols(const HalfSetup<LT>& H0, const Hal
 // Serial walk of one trapezoid half by the thread that set it up (ScanlineIter::next, raster.rs:80-114).
 // Used for triangles with few rows, where a separate row-parallel kernel costs more than it saves.
 template <int LT>
-__device__ __forceinline__ void walk_half_inline(const PassParams& P, const TargetDesc& T, HalfSetup<LT>& H, uint32_t& sidx, uint32_t own,
-                                                 unsigned long long& frags_i) {
+__device__ __forceinline__ void walk_half_inline(const PassParams& P, uint32_t th, uint32_t tw, uint32_t by0, uint32_t by1, HalfSetup<LT>& H,
+                                                 uint32_t& sidx, uint32_t& row, uint32_t& long_rows, unsigned long long& frags_i, bool& oob) {
   constexpr int NL = 2 + LT;
   constexpr int SW = Rec<LT>::SW;
   float y = H.y;
@@ -267,25 +267,23 @@ __device__ __forceinline__ void walk_half_inline(const PassParams& P, const Targ
     const uint32_t cnt = sat_u32(x1r - x0r);
     const uint32_t Yf = sat_u32(y), X0 = sat_u32(x0r), X1 = max(sat_u32(x1r), X0);
     uint32_t nn = min(cnt, X1 - X0);
-    if (Yf >= T.h || X1 > T.w) {  // target.rs:148,173-174 (slice index panics)
-      atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
+    if (Yf >= th || X1 > tw) {  // target.rs:148,173-174 (slice index panics)
+      oob = true;
       nn = 0;
-    } else if (Yf < T.band_y0 || Yf >= T.band_y1) {
+    } else if (Yf < by0 || Yf >= by1) {
       nn = 0;  // not this GPU's row band
     } else {
       frags_i += X1 - X0;
     }
-    if (nn && ((X0 + nn - 1) >> RF_TILE_SHIFT) != (X0 >> RF_TILE_SHIFT)) {  // crosses a tile column: k_ckpt adds checkpoints
-      const unsigned long long slot = agg_atomic_inc(&P.status->long_needed);
-      if (slot < P.cap_long) P.longlist[slot] = make_uint2(sidx, own);
-      else { P.status->overflow = 1; P.cstatus->poison = 1; }
-    }
+    // crosses a tile column: remembered in a bit mask (row <= RF_INLINE_ROWS), appended to the long list after the walk
+    if (nn && ((X0 + nn - 1) >> RF_TILE_SHIFT) != (X0 >> RF_TILE_SHIFT)) long_rows |= 1u << row;
     w[0] = X0 | nn << 16;
     w[1] = RF_NO_CKPT;
     uint32_t* sr = P.spans + (size_t)sidx * SW;
 #pragma unroll
     for (int q = 0; q < SW / 2; q++) *reinterpret_cast<uint2*>(sr + 2 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
     sidx++;
+    row++;
     y = y + 1.0f;
   }
 }
@@ -294,18 +292,18 @@ __device__ __forceinline__ void walk_half_inline(const PassParams& P, const Targ
 #define RF_INLINE_ROWS 12u
 
 // =============================================================================================
-// K2a k_setup: one thread per input primitive — assembly, clip, to_screen, cull, triangle setup.
-// Emits, with warp-aggregated allocation (warp prefix sums): a triangle record, its span range,
-// its (triangle x tile) bin entries, and its walk chunks (<= 32 rows each).
+// K2a k_assemble: one thread per input primitive — assembly (render.rs:168-172), status / Sutherland–
+// Hodgman clip (clip.rs:350-400), to_screen (prim.rs:62-88), winding + face cull (ctx.rs:95-101).
+// The surviving screen-space triangles are appended to a COMPACT buffer with one atomic per warp
+// (warp ballot / prefix sum), so the setup kernel that follows runs with every lane busy.
+// Screen triangle record (Rec<LT>::QW words): key, draw, then 3 x (x, y, z, attr[LT]).
 // =============================================================================================
 #define RF_CHUNK 32u
 #define RF_LONG_BLOCK 256u
 
 template <int LT>
-__global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
-  constexpr int NL = 2 + LT, NV = 1 + LT;
-  constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS;
-  using TR = TriRec<LT>;
+__global__ void __launch_bounds__(128) k_assemble(PassParams P) {
+  constexpr int QW = Rec<LT>::QW;
   if (P.cstatus->poison) return;
   const uint32_t lane = lane_id();
   const uint32_t n_iter = (P.NP + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
@@ -342,19 +340,12 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
     uint32_t max_tri = ntri;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) max_tri = max(max_tri, __shfl_xor_sync(0xFFFFFFFFu, max_tri, o));
-
     uint32_t my_prims_o = 0;
-    unsigned long long my_frags_i = 0;
-
     for (uint32_t t = 0; t < max_tri; t++) {
       bool emit = false;
-      HalfSetup<LT> H0, H1;
-      H0.n = H1.n = 0;
-      uint32_t tgt = 0, Y0 = 0, tr0 = 0, tr1 = 0, tiles_x = 1, nent = 0, nchunk = 0, by0 = 0, by1 = 0;
-      float margin = 0.0f;
+      SVert<LT> s[3];
       if (t < ntri) {
         const DrawDesc& D = P.draws[d];
-        SVert<LT> s[3];
         if (clipped) {
           to_screen<LT>(poly[0], D.vp, D.persp_mask, s[0]);
           to_screen<LT>(poly[t + 1], D.vp, D.persp_mask, s[1]);
@@ -372,103 +363,182 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
         wz = wz + abx * acy;
         const bool back = wz < 0.0f;
         const uint32_t cull = D.flags & RF_F_CULL_MASK;
-        if (!((cull == RF_CULL_BACK && back) || (cull == RF_CULL_FRONT && !back))) {
-          my_prims_o++;  // render.rs:195-196: counted before rasterisation, whatever it covers
-          // tri_fill raster.rs:185-224: stable sort by y (total_cmp)
-          int o0 = 0, o1 = 1, o2 = 2;
-          {
-            const int32_t k0 = total_key(s[0].y), k1 = total_key(s[1].y), k2 = total_key(s[2].y);
-            int32_t ka = k0, kb = k1, kc = k2;
-            if (kb < ka) { int ti = o0; o0 = o1; o1 = ti; int32_t tk = ka; ka = kb; kb = tk; }
-            if (kc < kb) { int ti = o1; o1 = o2; o2 = ti; int32_t tk = kb; kb = kc; kc = tk; }
-            if (kb < ka) { int ti = o0; o0 = o1; o1 = ti; }
-          }
-          float top[NL], mid0[NL], bot[NL], mid1[NL];
-          float ty, my, by;
-#define RF_PICK(dst, yy, idx)                                            \
-  {                                                                      \
-    const SVert<LT>& q = (idx == 0) ? s[0] : ((idx == 1) ? s[1] : s[2]); \
-    dst[0] = q.x; dst[1] = q.z; yy = q.y;                                \
-    _Pragma("unroll") for (int i = 0; i < LT; i++) dst[2 + i] = q.a[i];  \
-  }
-          RF_PICK(top, ty, o0)
-          RF_PICK(mid0, my, o1)
-          RF_PICK(bot, by, o2)
-#undef RF_PICK
-          const float tt = (my - ty) / (by - ty);
+        emit = !((cull == RF_CULL_BACK && back) || (cull == RF_CULL_FRONT && !back));
+        if (emit) my_prims_o++;  // render.rs:195-196: counted before rasterisation, whatever it covers
+      }
+      const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
+      if (emask == 0) continue;
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&P.status->stris_needed, (unsigned long long)__popc(emask));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (base + __popc(emask) > P.cap_stris) {
+        if (lane == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
+        continue;
+      }
+      if (emit) {
+        uint32_t* q = P.stris + (size_t)((uint32_t)base + __popc(emask & lanemask_lt())) * QW;
+        uint32_t w[QW];
+        w[0] = gp * 8u + t; w[1] = d;
 #pragma unroll
-          for (int i = 0; i < NL; i++) mid1[i] = lerpf(top[i], bot[i], tt);
-          const bool m0left = mid0[0] < mid1[0];
-          const float* left = m0left ? mid0 : mid1;
-          const float* right = m0left ? mid1 : mid0;
-          half_setup<LT>(ty, my, top, left, top, right, H0);
-          half_setup<LT>(my, by, left, bot, right, bot, H1);
-          const TargetDesc& T = P.targets[D.target];
-          tgt = D.target; tiles_x = T.tiles_x; by0 = T.band_y0; by1 = T.band_y1;
-          // Row-range sanity. A scanline at y >= h panics in the reference (target.rs:148,173);
-          // RF_MAX_ROWS bounds the work against absurd coordinates; a negative first row can only
-          // come from a viewport outside the target and is rejected (the reference would draw it at row 0).
-          uint32_t nrows = H0.n + H1.n;
-          if (nrows != 0) {
-            const float yfirst = H0.n ? H0.y : H1.y;
-            const float ylast = yfirst + (float)(nrows - 1);
-            if (H0.n > RF_MAX_ROWS || H1.n > RF_MAX_ROWS || sat_u32(ylast) >= T.h) {
-              atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
-              nrows = 0;
-            } else if (yfirst < 0.0f) {
-              atomicOr(&P.status->error, RF_ERRBIT_NEG_ROW);
-              nrows = 0;
+        for (int k = 0; k < 3; k++) {
+          w[2 + k * (3 + LT)] = __float_as_uint(s[k].x); w[3 + k * (3 + LT)] = __float_as_uint(s[k].y); w[4 + k * (3 + LT)] = __float_as_uint(s[k].z);
+#pragma unroll
+          for (int i = 0; i < LT; i++) w[5 + k * (3 + LT) + i] = __float_as_uint(s[k].a[i]);
+        }
+#pragma unroll
+        for (int i = 2 + 3 * (3 + LT); i < QW; i++) w[i] = 0u;
+#pragma unroll
+        for (int qd = 0; qd < QW / 4; qd++) *reinterpret_cast<uint4*>(q + 4 * qd) = make_uint4(w[4 * qd], w[4 * qd + 1], w[4 * qd + 2], w[4 * qd + 3]);
+      }
+    }
+    // ---- per-draw prims.o: aggregate over the warp when every lane has the same draw
+    {
+      const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d, 0);
+      const bool uniform = __all_sync(0xFFFFFFFFu, !have || d == d0);
+      if (uniform) {
+        uint32_t po = my_prims_o;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) po += __shfl_xor_sync(0xFFFFFFFFu, po, o);
+        if (lane == 0 && po) atomicAdd(&P.dstats[d0].prims_o, (unsigned long long)po);
+      } else if (have && my_prims_o) {
+        atomicAdd(&P.dstats[d].prims_o, (unsigned long long)my_prims_o);
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// K2a' k_setup: one thread per surviving screen triangle — tri_fill's y-sort and the `scan` setup of
+// both trapezoid halves (raster.rs:185-302). Emits, with warp-aggregated allocation (warp prefix
+// sums): a triangle record, its span range, its (triangle x tile) bin entries, and either walks
+// its scanlines inline (few rows) or cuts them into <= 32-row chunks for k_walk.
+// =============================================================================================
+template <int LT>
+__global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
+  constexpr int NL = 2 + LT, NV = 1 + LT;
+  constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS, QW = Rec<LT>::QW;
+  using TR = TriRec<LT>;
+  if (P.cstatus->poison) return;
+  const uint32_t lane = lane_id();
+  const uint32_t NT = (uint32_t)min(P.status->stris_needed, (unsigned long long)P.cap_stris);
+  const uint32_t n_iter = (NT + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
+  for (uint32_t it = 0; it < n_iter; it++) {
+    const uint32_t ti = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool have = ti < NT;
+    bool emit = false;
+    HalfSetup<LT> H0, H1;
+    H0.n = H1.n = 0;
+    uint32_t key = 0, d = 0, tgt = 0, Y0 = 0, tr0 = 0, tr1 = 0, tiles_x = 1, nent = 0, nchunk = 0;
+    float margin = 0.0f;
+    unsigned long long my_frags_i = 0;
+    uint32_t long_rows = 0, long_sbase = 0, long_tri = 0, long_nU = 0;  // inline-walked rows that cross a tile column
+    uint32_t t_h = 0, t_w = 0, t_by0 = 0, t_by1 = 0;
+    if (have) {
+      const uint32_t* q = P.stris + (size_t)ti * QW;
+      uint32_t w[QW];
+#pragma unroll
+      for (int qd = 0; qd < QW / 4; qd++) {
+        const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(q) + qd);
+        w[4 * qd] = t4.x; w[4 * qd + 1] = t4.y; w[4 * qd + 2] = t4.z; w[4 * qd + 3] = t4.w;
+      }
+      key = w[0]; d = w[1];
+      const DrawDesc& D = P.draws[d];
+      // tri_fill raster.rs:185-224: stable sort by y (total_cmp)
+      int o0 = 0, o1 = 1, o2 = 2;
+      {
+        const int32_t k0 = total_key(__uint_as_float(w[3])), k1 = total_key(__uint_as_float(w[3 + (3 + LT)])), k2 = total_key(__uint_as_float(w[3 + 2 * (3 + LT)]));
+        int32_t ka = k0, kb = k1, kc = k2;
+        if (kb < ka) { int t_ = o0; o0 = o1; o1 = t_; int32_t tk = ka; ka = kb; kb = tk; }
+        if (kc < kb) { int t_ = o1; o1 = o2; o2 = t_; int32_t tk = kb; kb = kc; kc = tk; }
+        if (kb < ka) { int t_ = o0; o0 = o1; o1 = t_; }
+      }
+      float top[NL], mid0[NL], bot[NL], mid1[NL];
+      float ty, my, by;
+#define RF_PICK(dst, yy, idx)                                                                      \
+  {                                                                                                \
+    _Pragma("unroll") for (int k = 0; k < 3; k++) if (k == idx) {                                  \
+      dst[0] = __uint_as_float(w[2 + k * (3 + LT)]); yy = __uint_as_float(w[3 + k * (3 + LT)]);    \
+      dst[1] = __uint_as_float(w[4 + k * (3 + LT)]);                                               \
+      _Pragma("unroll") for (int i = 0; i < LT; i++) dst[2 + i] = __uint_as_float(w[5 + k * (3 + LT) + i]); \
+    }                                                                                              \
+  }
+      RF_PICK(top, ty, o0)
+      RF_PICK(mid0, my, o1)
+      RF_PICK(bot, by, o2)
+#undef RF_PICK
+      const float tt = (my - ty) / (by - ty);
+#pragma unroll
+      for (int i = 0; i < NL; i++) mid1[i] = lerpf(top[i], bot[i], tt);
+      const bool m0left = mid0[0] < mid1[0];
+      const float* left = m0left ? mid0 : mid1;
+      const float* right = m0left ? mid1 : mid0;
+      half_setup<LT>(ty, my, top, left, top, right, H0);
+      half_setup<LT>(my, by, left, bot, right, bot, H1);
+      const TargetDesc& T = P.targets[D.target];
+      tgt = D.target; tiles_x = T.tiles_x;
+      t_h = T.h; t_w = T.w; t_by0 = T.band_y0; t_by1 = T.band_y1;
+      // Row-range sanity. A scanline at y >= h panics in the reference (target.rs:148,173);
+      // RF_MAX_ROWS bounds the work against absurd coordinates; a negative first row can only
+      // come from a viewport outside the target and is rejected (the reference would draw it at row 0).
+      uint32_t nrows = H0.n + H1.n;
+      if (nrows != 0) {
+        const float yfirst = H0.n ? H0.y : H1.y;
+        const float ylast = yfirst + (float)(nrows - 1);
+        if (H0.n > RF_MAX_ROWS || H1.n > RF_MAX_ROWS || sat_u32(ylast) >= T.h) {
+          atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
+          nrows = 0;
+        } else if (yfirst < 0.0f) {
+          atomicOr(&P.status->error, RF_ERRBIT_NEG_ROW);
+          nrows = 0;
+        }
+        if (nrows == 0) H0.n = H1.n = 0;
+        else {
+          emit = true;
+          Y0 = sat_u32(yfirst);
+          // only tile rows inside this GPU's row band get bin entries
+          const uint32_t Ya = max(Y0, T.band_y0), Yb = min(Y0 + nrows, T.band_y1);
+          const float xabs = fmaxf(fmaxf(fabsf(top[0]), fabsf(mid0[0])), fabsf(bot[0]));
+          margin = 1.0f + (float)nrows * xabs * 1.2e-7f;
+          if (Ya < Yb) {
+            tr0 = Ya >> RF_TILE_SHIFT; tr1 = (Yb - 1) >> RF_TILE_SHIFT;
+            for (uint32_t tr = tr0; tr <= tr1; tr++) {
+              uint32_t ca, cb;
+              tile_row_cols<LT>(H0, H1, Y0, nrows, tr, margin, tiles_x, ca, cb);
+              nent += cb - ca + 1;
             }
-            if (nrows == 0) H0.n = H1.n = 0;
-            else {
-              emit = true;
-              Y0 = sat_u32(yfirst);
-              // only tile rows inside this GPU's row band get bin entries
-              const uint32_t Ya = max(Y0, by0), Yb = min(Y0 + nrows, by1);
-              const float xabs = fmaxf(fmaxf(fabsf(s[0].x), fabsf(s[1].x)), fabsf(s[2].x));
-              margin = 1.0f + (float)nrows * xabs * 1.2e-7f;
-              if (Ya < Yb) {
-                tr0 = Ya >> RF_TILE_SHIFT; tr1 = (Yb - 1) >> RF_TILE_SHIFT;
-                for (uint32_t tr = tr0; tr <= tr1; tr++) {
-                  uint32_t ca, cb;
-                  tile_row_cols<LT>(H0, H1, Y0, nrows, tr, margin, tiles_x, ca, cb);
-                  nent += cb - ca + 1;
-                }
-              } else { tr0 = 1; tr1 = 0; }
-              if (nrows > RF_INLINE_ROWS) nchunk = (H0.n + RF_CHUNK - 1) / RF_CHUNK + (H1.n + RF_CHUNK - 1) / RF_CHUNK;
-            }
-          }
+          } else { tr0 = 1; tr1 = 0; }
+          if (nrows > RF_INLINE_ROWS) nchunk = (H0.n + RF_CHUNK - 1) / RF_CHUNK + (H1.n + RF_CHUNK - 1) / RF_CHUNK;
         }
       }
-      // ---- warp-aggregated allocation (warp prefix sums)
-      const uint32_t nsp = emit ? (H0.n + H1.n) : 0u;
-      const uint32_t incl_s = warp_scan_incl(nsp), incl_e = warp_scan_incl(nent), incl_c = warp_scan_incl(nchunk);
-      const uint32_t tot_s = __shfl_sync(0xFFFFFFFFu, incl_s, 31), tot_e = __shfl_sync(0xFFFFFFFFu, incl_e, 31);
-      const uint32_t tot_c = __shfl_sync(0xFFFFFFFFu, incl_c, 31);
-      const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
-      unsigned long long sb = 0, tb = 0, eb = 0, cb_ = 0;
-      if (lane == 0 && emask) {
-        sb = atomicAdd(&P.status->spans_needed, (unsigned long long)tot_s);
-        tb = atomicAdd(&P.status->tris_needed, (unsigned long long)__popc(emask));
-        if (tot_e) eb = atomicAdd(&P.status->entries_needed, (unsigned long long)tot_e);
-        cb_ = atomicAdd(&P.status->chunks_needed, (unsigned long long)tot_c);
-      }
-      sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
-      tb = __shfl_sync(0xFFFFFFFFu, tb, 0);
-      eb = __shfl_sync(0xFFFFFFFFu, eb, 0);
-      cb_ = __shfl_sync(0xFFFFFFFFu, cb_, 0);
-      const bool fits = sb + tot_s <= P.cap_spans && tb + __popc(emask) <= P.cap_tris && eb + tot_e <= P.cap_entries &&
-                        cb_ + tot_c <= P.cap_chunks;
-      if (!fits) {
-        if (lane == 0 && emask) { P.status->overflow = 1; P.cstatus->poison = 1; }
-        continue;  // keep counting what is needed, write nothing
-      }
-      if (!emit) continue;
+    }
+    // ---- warp-aggregated allocation (warp prefix sums)
+    const uint32_t nsp = emit ? (H0.n + H1.n) : 0u;
+    const uint32_t incl_s = warp_scan_incl(nsp), incl_e = warp_scan_incl(nent), incl_c = warp_scan_incl(nchunk);
+    const uint32_t tot_s = __shfl_sync(0xFFFFFFFFu, incl_s, 31), tot_e = __shfl_sync(0xFFFFFFFFu, incl_e, 31);
+    const uint32_t tot_c = __shfl_sync(0xFFFFFFFFu, incl_c, 31);
+    const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
+    unsigned long long sb = 0, tb = 0, eb = 0, cb_ = 0;
+    if (lane == 0 && emask) {
+      sb = atomicAdd(&P.status->spans_needed, (unsigned long long)tot_s);
+      tb = atomicAdd(&P.status->tris_needed, (unsigned long long)__popc(emask));
+      if (tot_e) eb = atomicAdd(&P.status->entries_needed, (unsigned long long)tot_e);
+      if (tot_c) cb_ = atomicAdd(&P.status->chunks_needed, (unsigned long long)tot_c);
+    }
+    sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
+    tb = __shfl_sync(0xFFFFFFFFu, tb, 0);
+    eb = __shfl_sync(0xFFFFFFFFu, eb, 0);
+    cb_ = __shfl_sync(0xFFFFFFFFu, cb_, 0);
+    const bool fits = sb + tot_s <= P.cap_spans && tb + __popc(emask) <= P.cap_tris && eb + tot_e <= P.cap_entries &&
+                      cb_ + tot_c <= P.cap_chunks;
+    if (!fits) {
+      if (lane == 0 && emask) { P.status->overflow = 1; P.cstatus->poison = 1; }
+      continue;  // keep counting what is needed, write nothing
+    }
+    if (emit) {
       const uint32_t sbase = (uint32_t)sb + (incl_s - nsp);
       const uint32_t tri_idx = (uint32_t)tb + __popc(emask & lanemask_lt());
       uint32_t eidx = (uint32_t)eb + (incl_e - nent);
       uint32_t cidx = (uint32_t)cb_ + (incl_c - nchunk);
-      const uint32_t key = gp * 8u + t;
       const bool inline_walk = H0.n + H1.n <= RF_INLINE_ROWS;
       const uint32_t ch0 = inline_walk ? 0u : (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = inline_walk ? 0u : (H1.n + RF_CHUNK - 1) / RF_CHUNK;
       const uint32_t eck0 = cidx, eck1 = cidx + ch0;  // edge checkpoints are indexed by chunk position
@@ -487,7 +557,6 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
 #pragma unroll
           for (int i = 0; i < NL; i++) { w[TR::O_L + i] = __float_as_uint(H.L[i]); w[TR::O_DL + i] = __float_as_uint(H.dl[i]); }
           w[TR::O_R] = __float_as_uint(H.R); w[TR::O_DR] = __float_as_uint(H.dr); w[TR::O_Y] = __float_as_uint(H.y);
-          // lane 0 of dv (dx/dx) is needed by the walk's x-alignment of... nothing: alignment uses dv of every other lane only
 #pragma unroll
           for (int q = 0; q < HS / 4; q++) *reinterpret_cast<uint4*>(tr + 8 + hh * HS + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
         }
@@ -505,35 +574,54 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
           }
         }
       }
-      // walk chunks (and the list of tall halves that need edge checkpoints)
       // chunk record: {tri*2+half, chunk | rows << 16, first span index, draw | target << 16}
       for (uint32_t c = 0; c < ch0; c++)
         P.chunks[cidx++] = make_uint4(tri_idx * 2u, c | min(RF_CHUNK, H0.n - c * RF_CHUNK) << 16, sbase + c * RF_CHUNK, d | tgt << 16);
       for (uint32_t c = 0; c < ch1; c++)
         P.chunks[cidx++] = make_uint4(tri_idx * 2u + 1u, c | min(RF_CHUNK, H1.n - c * RF_CHUNK) << 16, sbase + H0.n + c * RF_CHUNK, d | tgt << 16);
       if (inline_walk) {  // few rows: walk them here, serially (sequential adds down both edges)
-        const TargetDesc& T = P.targets[tgt];
-        uint32_t sidx = sbase;
-        walk_half_inline<LT>(P, T, H0, sidx, tri_idx * 2u, my_frags_i);
-        walk_half_inline<LT>(P, T, H1, sidx, tri_idx * 2u + 1u, my_frags_i);
+        uint32_t sidx = sbase, row = 0;
+        bool oob = false;
+        const uint32_t nU = H0.n;
+        walk_half_inline<LT>(P, t_h, t_w, t_by0, t_by1, H0, sidx, row, long_rows, my_frags_i, oob);
+        walk_half_inline<LT>(P, t_h, t_w, t_by0, t_by1, H1, sidx, row, long_rows, my_frags_i, oob);
+        if (oob) atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
+        long_sbase = sbase; long_tri = tri_idx; long_nU = nU;
       }
       if (ch0 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
       if (ch1 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u + 1u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
     }
-    // ---- per-draw prims.o: aggregate over the warp when every lane has the same draw
+    // ---- long list of the inline walks: one warp-aggregated allocation (warp prefix sum) for all lanes
+    {
+      const uint32_t nl = __popc(long_rows);
+      const uint32_t incl_l = warp_scan_incl(nl);
+      const uint32_t tot_l = __shfl_sync(0xFFFFFFFFu, incl_l, 31);
+      if (tot_l) {
+        unsigned long long lb = 0;
+        if (lane == 0) lb = atomicAdd(&P.status->long_needed, (unsigned long long)tot_l);
+        lb = __shfl_sync(0xFFFFFFFFu, lb, 0);
+        if (lb + tot_l <= P.cap_long) {
+          unsigned long long slot = lb + (incl_l - nl);
+          uint32_t m = long_rows;
+          while (m) {
+            const uint32_t r = __ffs(m) - 1;
+            m &= m - 1;
+            P.longlist[slot++] = make_uint2(long_sbase + r, long_tri * 2u + (r >= long_nU ? 1u : 0u));
+          }
+        } else if (lane == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
+      }
+    }
+    // ---- per-draw frags.i of the inline walks
     {
       const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d, 0);
       const bool uniform = __all_sync(0xFFFFFFFFu, !have || d == d0);
       if (uniform) {
-        uint32_t po = my_prims_o;
         unsigned long long fi = my_frags_i;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { po += __shfl_xor_sync(0xFFFFFFFFu, po, o); fi += __shfl_xor_sync(0xFFFFFFFFu, fi, o); }
-        if (lane == 0 && po) atomicAdd(&P.dstats[d0].prims_o, (unsigned long long)po);
+        for (int o = 16; o > 0; o >>= 1) fi += __shfl_xor_sync(0xFFFFFFFFu, fi, o);
         if (lane == 0 && fi) atomicAdd(&P.dstats[d0].frags_i, fi);
-      } else if (have) {
-        if (my_prims_o) atomicAdd(&P.dstats[d].prims_o, (unsigned long long)my_prims_o);
-        if (my_frags_i) atomicAdd(&P.dstats[d].frags_i, my_frags_i);
+      } else if (have && my_frags_i) {
+        atomicAdd(&P.dstats[d].frags_i, my_frags_i);
       }
     }
   }

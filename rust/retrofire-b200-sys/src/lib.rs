@@ -6,7 +6,7 @@ use core::ffi::{c_char, c_int, c_void};
 pub const RF_MAX_ATTR_LANES: usize = 8;
 pub const RF_VS_UNIFORM_F32: usize = 32;
 pub const RF_FS_UNIFORM_F32: usize = 8;
-pub const RF_N_KERNELS: usize = 10;
+pub const RF_N_KERNELS: usize = 11;
 
 #[repr(C)] pub struct rf_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct rf_target { _p: [u8; 0] }

@@ -44,7 +44,7 @@ def test_ptx_has_no_fma_on_coverage_and_depth_chains(tmp_path):
         if "fma.rn.f32" in line and cur:
             counts[cur] = counts.get(cur, 0) + 1
     for name, n in counts.items():
-        assert "k_setup" not in name and "k_walk" not in name and "k_ckpt" not in name, (name, n)
+        assert all(k not in name for k in ("k_assemble", "k_setup", "k_walk", "k_ckpt")), (name, n)
         if "k_raster" in name:
             assert n % (3 * 19) == 0, (name, n)   # powf(c, 1/2.2) x3 in FS_COLOR3F_SRGB, once per inlined copy
     assert "--use_fast_math" not in " ".join(rfbuild.NVCC_FLAGS)
