@@ -418,6 +418,9 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
   constexpr int NL = 2 + LT, NV = 1 + LT;
   constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS, QW = Rec<LT>::QW;
   using TR = TriRec<LT>;
+  __shared__ uint32_t s_tot[4][4];
+  __shared__ unsigned long long s_base[4];
+  __shared__ uint32_t s_fit[4];
   if (P.cstatus->poison) return;
   const uint32_t lane = lane_id();
   const uint32_t NT = (uint32_t)min(P.status->stris_needed, (unsigned long long)P.cap_stris);
@@ -511,27 +514,32 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
         }
       }
     }
-    // ---- warp-aggregated allocation (warp prefix sums)
+    // ---- block-aggregated allocation: warp prefix sums, then ONE atomic per counter per block
     const uint32_t nsp = emit ? (H0.n + H1.n) : 0u;
     const uint32_t incl_s = warp_scan_incl(nsp), incl_e = warp_scan_incl(nent), incl_c = warp_scan_incl(nchunk);
-    const uint32_t tot_s = __shfl_sync(0xFFFFFFFFu, incl_s, 31), tot_e = __shfl_sync(0xFFFFFFFFu, incl_e, 31);
-    const uint32_t tot_c = __shfl_sync(0xFFFFFFFFu, incl_c, 31);
     const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
-    unsigned long long sb = 0, tb = 0, eb = 0, cb_ = 0;
-    if (lane == 0 && emask) {
-      sb = atomicAdd(&P.status->spans_needed, (unsigned long long)tot_s);
-      tb = atomicAdd(&P.status->tris_needed, (unsigned long long)__popc(emask));
-      if (tot_e) eb = atomicAdd(&P.status->entries_needed, (unsigned long long)tot_e);
-      if (tot_c) cb_ = atomicAdd(&P.status->chunks_needed, (unsigned long long)tot_c);
+    const uint32_t wid = threadIdx.x >> 5;
+    if (lane == 31) { s_tot[wid][0] = incl_s; s_tot[wid][1] = __popc(emask); s_tot[wid][2] = incl_e; s_tot[wid][3] = incl_c; }
+    __syncthreads();
+    if (threadIdx.x < 4) {  // thread k allocates counter k for the whole block
+      uint32_t tot = 0;
+#pragma unroll
+      for (int w = 0; w < 4; w++) tot += s_tot[w][threadIdx.x];
+      PaddedCounter* ctr = threadIdx.x == 0 ? &P.status->spans_needed : threadIdx.x == 1 ? &P.status->tris_needed
+                         : threadIdx.x == 2 ? &P.status->entries_needed : &P.status->chunks_needed;
+      const uint32_t cap = threadIdx.x == 0 ? P.cap_spans : threadIdx.x == 1 ? P.cap_tris : threadIdx.x == 2 ? P.cap_entries : P.cap_chunks;
+      unsigned long long base = 0;
+      if (tot) base = atomicAdd(ctr, (unsigned long long)tot);
+      s_base[threadIdx.x] = base;
+      s_fit[threadIdx.x] = base + tot <= cap ? 1u : 0u;
     }
-    sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
-    tb = __shfl_sync(0xFFFFFFFFu, tb, 0);
-    eb = __shfl_sync(0xFFFFFFFFu, eb, 0);
-    cb_ = __shfl_sync(0xFFFFFFFFu, cb_, 0);
-    const bool fits = sb + tot_s <= P.cap_spans && tb + __popc(emask) <= P.cap_tris && eb + tot_e <= P.cap_entries &&
-                      cb_ + tot_c <= P.cap_chunks;
+    __syncthreads();
+    const bool fits = s_fit[0] && s_fit[1] && s_fit[2] && s_fit[3];
+    unsigned long long sb = s_base[0], tb = s_base[1], eb = s_base[2], cb_ = s_base[3];
+    for (uint32_t w = 0; w < wid; w++) { sb += s_tot[w][0]; tb += s_tot[w][1]; eb += s_tot[w][2]; cb_ += s_tot[w][3]; }
+    __syncthreads();  // s_tot / s_base are reused by the next iteration
     if (!fits) {
-      if (lane == 0 && emask) { P.status->overflow = 1; P.cstatus->poison = 1; }
+      if (threadIdx.x == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
       continue;  // keep counting what is needed, write nothing
     }
     if (emit) {
