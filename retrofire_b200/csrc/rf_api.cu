@@ -289,7 +289,7 @@ rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const Aren
     c->cap_chunks = w.chunks;
   }
   if (w.tall > c->cap_tall) { if (!c->talllist.reserve(w.tall * 4)) return fail(c, RF_E_NOMEM, "tall list"); c->cap_tall = w.tall; }
-  if (!c->tiles.reserve(n_tiles * 5 * 4 + 64)) return fail(c, RF_E_NOMEM, "tile arrays");
+  if (!c->tiles.reserve(n_tiles * 6 * 4 + 64)) return fail(c, RF_E_NOMEM, "tile arrays");
   if (!c->cursors.reserve(64)) return fail(c, RF_E_NOMEM, "cursors");
   return RF_OK;
 }
@@ -336,7 +336,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
                   std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), std::max<size_t>(c->capw_stris, (size_t)8 << 20),
                   std::max<size_t>(c->cap_entries, (size_t)1 << 20), std::max<size_t>(c->cap_long, (size_t)1 << 19),
                   std::max<size_t>(c->cap_chunks, (size_t)1 << 20), std::max<size_t>(c->cap_tall, (size_t)1 << 18)};
-  need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 20 + 64 ||
+  need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 24 + 64 ||
               !arenas_cover(c, want) || c->cursors.cap < 64;
   if (need_idle) { rf_status st = wait_idle(c); if (st) return st; }
   if (!s.d_table.reserve(table_bytes) || !s.d_geom.reserve(std::max<size_t>(s.geom_len, 16)) ||
@@ -443,7 +443,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.cap_ecks = P.cap_chunks;
   uint32_t* ta = static_cast<uint32_t*>(c->tiles.p);
   P.tile_cnt = ta; P.tile_off = ta + ntiles; P.tile_fill = ta + 2 * (size_t)ntiles;
-  P.worklist = ta + 3 * (size_t)ntiles; P.worklist_big = ta + 4 * (size_t)ntiles;
+  P.worklist = ta + 3 * (size_t)ntiles; P.worklist_big = ta + 4 * (size_t)ntiles; P.worklist_heavy = ta + 5 * (size_t)ntiles;
   P.cursors = static_cast<uint32_t*>(c->cursors.p);
   P.dstats = static_cast<DrawStats*>(s.d_dstats.p);
   P.status = static_cast<PassStatus*>(s.d_status.p);

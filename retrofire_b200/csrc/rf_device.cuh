@@ -80,7 +80,7 @@ struct PassStatus {
   uint32_t n_work;               // non-empty tiles
   uint32_t n_work_big;           // tiles whose bin needs the large-smem sort
   uint32_t max_bin;
-  uint32_t _pad;
+  uint32_t n_work_heavy;         // tiles with >= RF_HEAVY_BIN triangles
 };
 
 // persistent across passes: once set, every later pass is a no-op until the host clears it
@@ -120,6 +120,7 @@ struct PassParams {
   uint32_t* tile_fill;    // [n_tiles]
   uint32_t* worklist;     // [n_tiles] non-empty tiles
   uint32_t* worklist_big; // [n_tiles]
+  uint32_t* worklist_heavy; // [n_tiles] tiles rasterised first
   uint32_t* cursors;      // [1] raster work cursor
   DrawStats* dstats;      // [n_draws]
   PassStatus* status;
