@@ -81,6 +81,8 @@ struct PassStatus {
   uint32_t n_work_big;           // tiles whose bin needs the large-smem sort
   uint32_t max_bin;
   uint32_t n_work_heavy;         // tiles with >= RF_HEAVY_BIN triangles
+  uint32_t n_work_heaviest;      // tiles with >= RF_HEAVIEST_BIN triangles
+  uint32_t _pad;
 };
 
 // persistent across passes: once set, every later pass is a no-op until the host clears it

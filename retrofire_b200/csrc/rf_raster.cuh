@@ -12,7 +12,8 @@
 // =============================================================================================
 #define RF_SORT_SMALL 1024u   // per-warp shared-memory sort capacity (entries)
 #define RF_SORT_BIG 16384u    // per-block (large smem) sort capacity
-#define RF_HEAVY_BIN 96u      // tiles with at least this many triangles are rasterised first (longest-first scheduling)
+#define RF_HEAVY_BIN 64u      // tiles are rasterised longest-first in three classes: >= RF_HEAVIEST_BIN, >= RF_HEAVY_BIN, rest
+#define RF_HEAVIEST_BIN 160u
 
 __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
   if (P.cstatus->poison) return;
@@ -25,24 +26,29 @@ __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
     const uint32_t nz = __ballot_sync(0xFFFFFFFFu, c != 0);
     const uint32_t big = __ballot_sync(0xFFFFFFFFu, c > RF_SORT_SMALL);
-    const uint32_t heavy = __ballot_sync(0xFFFFFFFFu, c >= RF_HEAVY_BIN);
-    uint32_t base = 0, wbase = 0, bbase = 0, hbase = 0;
+    const uint32_t heavy = __ballot_sync(0xFFFFFFFFu, c >= RF_HEAVY_BIN && c < RF_HEAVIEST_BIN);
+    const uint32_t heaviest = __ballot_sync(0xFFFFFFFFu, c >= RF_HEAVIEST_BIN);
+    uint32_t base = 0, wbase = 0, bbase = 0, hbase = 0, hhbase = 0;
     if (lane == 0 && nz) {
       base = (uint32_t)atomicAdd(&P.status->bins_needed, (unsigned long long)total);
       wbase = atomicAdd(&P.status->n_work, (uint32_t)__popc(nz));
       if (big) bbase = atomicAdd(&P.status->n_work_big, (uint32_t)__popc(big));
       if (heavy) hbase = atomicAdd(&P.status->n_work_heavy, (uint32_t)__popc(heavy));
+      if (heaviest) hhbase = atomicAdd(&P.status->n_work_heaviest, (uint32_t)__popc(heaviest));
     }
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
     bbase = __shfl_sync(0xFFFFFFFFu, bbase, 0);
     hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
+    hhbase = __shfl_sync(0xFFFFFFFFu, hhbase, 0);
     // valid entries <= entry slots <= cap_entries, so the bins always fit
     if (c != 0) {
       P.tile_off[t] = base + (incl - c);
       P.worklist[wbase + __popc(nz & lanemask_lt())] = t;
       if (c > RF_SORT_SMALL) P.worklist_big[bbase + __popc(big & lanemask_lt())] = t;
-      if (c >= RF_HEAVY_BIN) P.worklist_heavy[hbase + __popc(heavy & lanemask_lt())] = t;
+      // heaviest tiles from the front of the array, heavy ones from its back
+      if (c >= RF_HEAVIEST_BIN) P.worklist_heavy[hhbase + __popc(heaviest & lanemask_lt())] = t;
+      else if (c >= RF_HEAVY_BIN) P.worklist_heavy[P.n_tiles - 1 - (hbase + __popc(heavy & lanemask_lt()))] = t;
       if (c > RF_SORT_BIG) atomicOr(&P.status->error, RF_ERRBIT_BIN_TOO_DEEP);
       atomicMax(&P.status->max_bin, c);
     }
@@ -383,14 +389,14 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
   float* sz = reinterpret_cast<float*>(s_raster + (size_t)warp * RasterSmem<LT>::WARP_WORDS);
   float* qv = sz + RasterSmem<LT>::TILE_WORDS;                                  // [1+LT][RF_FRAG_QUEUE]
   uint32_t* qp = reinterpret_cast<uint32_t*>(qv + (1 + LT) * RF_FRAG_QUEUE);    // [RF_FRAG_QUEUE] pixel index | owner lane << 16
-  const uint32_t n_work = P.status->n_work, n_heavy = P.status->n_work_heavy;
+  const uint32_t n_work = P.status->n_work, n_heaviest = P.status->n_work_heaviest, n_heavy = n_heaviest + P.status->n_work_heavy;
 
   for (;;) {
     uint32_t wi = 0;
     if (lane == 0) wi = atomicAdd(P.cursors + 1, 1u);
     wi = __shfl_sync(0xFFFFFFFFu, wi, 0);
     if (wi >= n_work + n_heavy) break;
-    const uint32_t tile = wi < n_heavy ? P.worklist_heavy[wi] : P.worklist[wi - n_heavy];
+    const uint32_t tile = wi < n_heaviest ? P.worklist_heavy[wi] : (wi < n_heavy ? P.worklist_heavy[P.n_tiles - 1 - (wi - n_heaviest)] : P.worklist[wi - n_heavy]);
     const uint32_t cnt = P.tile_cnt[tile], off = P.tile_off[tile];
     if (wi >= n_heavy && cnt >= RF_HEAVY_BIN) continue;  // already done from the heavy list
     // which target / tile coordinates
