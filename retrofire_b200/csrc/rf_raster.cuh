@@ -14,6 +14,7 @@
 #define RF_SORT_BIG 16384u    // per-block (large smem) sort capacity
 #define RF_HEAVY_BIN 64u      // tiles are rasterised longest-first in three classes: >= RF_HEAVIEST_BIN, >= RF_HEAVY_BIN, rest
 #define RF_HEAVIEST_BIN 160u
+#define RF_SLICES 4u          // row slices of a heaviest tile (RF_TILE / RF_SLICES rows each); task word = tile | (slice+1) << 28
 
 __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
   if (P.cstatus->poison) return;
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
       wbase = atomicAdd(&P.status->n_work, (uint32_t)__popc(nz));
       if (big) bbase = atomicAdd(&P.status->n_work_big, (uint32_t)__popc(big));
       if (heavy) hbase = atomicAdd(&P.status->n_work_heavy, (uint32_t)__popc(heavy));
-      if (heaviest) hhbase = atomicAdd(&P.status->n_work_heaviest, (uint32_t)__popc(heaviest));
+      if (heaviest) hhbase = atomicAdd(&P.status->n_work_heaviest, (uint32_t)__popc(heaviest) * RF_SLICES);
     }
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
@@ -47,7 +48,11 @@ __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
       P.worklist[wbase + __popc(nz & lanemask_lt())] = t;
       if (c > RF_SORT_SMALL) P.worklist_big[bbase + __popc(big & lanemask_lt())] = t;
       // heaviest tiles from the front of the array, heavy ones from its back
-      if (c >= RF_HEAVIEST_BIN) P.worklist_heavy[hhbase + __popc(heaviest & lanemask_lt())] = t;
+      if (c >= RF_HEAVIEST_BIN) {  // split into RF_SLICES row slices, each rasterised by its own warp
+        const uint32_t b = hhbase + __popc(heaviest & lanemask_lt()) * RF_SLICES;
+#pragma unroll
+        for (uint32_t sl = 0; sl < RF_SLICES; sl++) P.worklist_heavy[b + sl] = t | (sl + 1u) << 28;
+      }
       else if (c >= RF_HEAVY_BIN) P.worklist_heavy[P.n_tiles - 1 - (hbase + __popc(heavy & lanemask_lt()))] = t;
       if (c > RF_SORT_BIG) atomicOr(&P.status->error, RF_ERRBIT_BIN_TOO_DEEP);
       atomicMax(&P.status->max_bin, c);
@@ -396,7 +401,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
     if (lane == 0) wi = atomicAdd(P.cursors + 1, 1u);
     wi = __shfl_sync(0xFFFFFFFFu, wi, 0);
     if (wi >= n_work + n_heavy) break;
-    const uint32_t tile = wi < n_heaviest ? P.worklist_heavy[wi] : (wi < n_heavy ? P.worklist_heavy[P.n_tiles - 1 - (wi - n_heaviest)] : P.worklist[wi - n_heavy]);
+    const uint32_t task = wi < n_heaviest ? P.worklist_heavy[wi] : (wi < n_heavy ? P.worklist_heavy[P.n_tiles - 1 - (wi - n_heaviest)] : P.worklist[wi - n_heavy]);
+    const uint32_t tile = task & 0x0FFFFFFFu, slice = task >> 28;  // slice 0: whole tile; k+1: rows [k, k+1) * RF_TILE / RF_SLICES
     const uint32_t cnt = P.tile_cnt[tile], off = P.tile_off[tile];
     if (wi >= n_heavy && cnt >= RF_HEAVY_BIN) continue;  // already done from the heavy list
     // which target / tile coordinates
@@ -413,19 +419,22 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
     const uint32_t tw = min((uint32_t)RF_TILE, T.w - px0), th = min((uint32_t)RF_TILE, T.h - py0);
     const bool has_depth = T.depth != nullptr;
     const bool vec = (T.w & 3u) == 0 && tw == RF_TILE;
+    // tile rows this task owns (a heaviest tile is shared by RF_SLICES warps, each owning whole rows)
+    const uint32_t r0 = slice ? min(th, (slice - 1u) * (RF_TILE / RF_SLICES)) : 0u;
+    const uint32_t r1 = slice ? min(th, slice * (RF_TILE / RF_SLICES)) : th;
 
     uint32_t* gc = T.color + (size_t)py0 * T.w + px0;  // framebuffer address of the tile's first pixel
     // ---- stage the depth tile: 128-bit coalesced loads, 8 lanes per row, 4 rows per instruction
     if (has_depth) {
       if (vec) {
         const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
-        for (uint32_t r = rsub; r < th; r += 4) {
+        for (uint32_t r = r0 + rsub; r < r1; r += 4) {
           const float4 z = *reinterpret_cast<const float4*>(T.depth + (size_t)(py0 + r) * T.w + px0 + c4);
           float* e = sz + r * RF_TILE_PITCH + c4;
           e[0] = z.x; e[1] = z.y; e[2] = z.z; e[3] = z.w;
         }
       } else {
-        for (uint32_t r = 0; r < th; r++)
+        for (uint32_t r = r0; r < r1; r++)
           if (lane < tw) sz[r * RF_TILE_PITCH + lane] = T.depth[(size_t)(py0 + r) * T.w + px0 + lane];
       }
     }
@@ -444,8 +453,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
         const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(tr + 4));  // nU, nL | target << 16
         t_draw = h0.y; t_sbase = h0.z; t_Y0 = h0.w; t_nU = h1.x;
         const uint32_t nrows = h1.x + (h1.y & 0xFFFFu);
-        t_ra = max(t_Y0, py0);
-        const uint32_t rb = min(t_Y0 + nrows, py0 + th);
+        t_ra = max(t_Y0, py0 + r0);
+        const uint32_t rb = min(t_Y0 + nrows, py0 + r1);
         t_rows = rb > t_ra ? rb - t_ra : 0u;
       }
       const uint32_t t_incl = warp_scan_incl(t_rows);
@@ -711,12 +720,12 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
     if (has_depth) {
       if (vec) {
         const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
-        for (uint32_t r = rsub; r < th; r += 4) {
+        for (uint32_t r = r0 + rsub; r < r1; r += 4) {
           const float* e = sz + r * RF_TILE_PITCH + c4;
           *reinterpret_cast<float4*>(T.depth + (size_t)(py0 + r) * T.w + px0 + c4) = make_float4(e[0], e[1], e[2], e[3]);
         }
       } else {
-        for (uint32_t r = 0; r < th; r++)
+        for (uint32_t r = r0; r < r1; r++)
           if (lane < tw) T.depth[(size_t)(py0 + r) * T.w + px0 + lane] = sz[r * RF_TILE_PITCH + lane];
       }
     }
