@@ -333,6 +333,12 @@ def run_b200(args):
         # whole-frame algorithmic bytes (SURVEY §8d B_alg) over the whole step time, for context
         geom = base.geometry_bytes() if single else sum(d.verts.shape[0] * 4 * (3 + d.shader.lanes) + d.prims.shape[0] * 12 for d in per_frame[0])
         b_alg_step = F * (geom + 8 * base.w * base.h) + (4 * st.frags.i + 8 * st.frags.o) / args.steps
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_raster_traffic.json")
+        if os.path.exists(tp):  # dram bytes of one k_raster launch from the committed ncu --set full capture of this command
+            tj = json.load(open(tp))
+            if tj.get("workload") == args.workload and tj.get("frames_per_pass") == F:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         line = {
             "metric": "Mfragments/s", "value": frags_i / (t_ms * 1e-3) / 1e6, "unit": "Mfragments/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True,
@@ -345,7 +351,7 @@ def run_b200(args):
                     "frames_per_step": Fe, "frames_per_s": world * Fe * e_steps / e_s},
             "gpu_launches": int(args.steps * (launches_per_pass)),
             "roofline": {"bound": "hbm", "kernel": "k_raster", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms_avg": r_avg_s * 1e3,
+                         "traffic": traffic, "peak_source": peak_src, "kernel_ms_avg": r_avg_s * 1e3,
                          "alg_bytes_per_launch": alg_bytes_launch, "kernel_time_share": kshare,
                          "pass_alg_GBps": b_alg_step / (t_ms * 1e-3 / args.steps) / 1e9},
             "clocks": sampler.summary(),
