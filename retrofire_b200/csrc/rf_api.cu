@@ -396,8 +396,16 @@ rf_status launch_pass(rf_ctx* c, int si) {
   s.n_launches = 0;
   RF_CUDA(c, cudaMemcpyAsync(s.d_table.p, tb, coff + ncl * sizeof(ClearDesc), cudaMemcpyHostToDevice, st));
   if (ncl) {
+    // The clears are only needed by k_raster: with draws in the pass (and not in the serialised profiling mode) they run on
+    // the side stream, concurrently with the latency-bound geometry kernels, and are joined with the binning chain.
+    const bool overlap = nd != 0 && c->profile != 2;
+    cudaStream_t cs = overlap ? c->side : st;
+    if (overlap) {
+      RF_CUDA(c, cudaEventRecord(s.ev_fork, st));        // after the table upload and everything earlier on the ctx stream
+      RF_CUDA(c, cudaStreamWaitEvent(cs, s.ev_fork, 0));
+    }
     const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)c->sm_count * 8 / ncl + 1, 1024));
-    k_clear_multi<<<dim3(gx, (unsigned)ncl), 256, 0, st>>>(reinterpret_cast<const ClearDesc*>(static_cast<uint8_t*>(s.d_table.p) + coff), c->d_cstatus);
+    k_clear_multi<<<dim3(gx, (unsigned)ncl), 256, 0, cs>>>(reinterpret_cast<const ClearDesc*>(static_cast<uint8_t*>(s.d_table.p) + coff), c->d_cstatus);
     s.n_launches++;
   }
   if (nd == 0) {
