@@ -62,6 +62,7 @@ struct QueuedDraw {
   rf_target* target;
   size_t verts_off;     // into geometry staging, or SIZE_MAX when the draw uses an rf_mesh
   size_t idx_off;
+  bool direct;          // offsets are into the slot's d_direct buffer (page-locked caller memory, DMA'd during rf_render)
 };
 
 struct HostStatus {     // pinned, one per slot
@@ -81,6 +82,8 @@ struct PassSlot {
   std::vector<rf_target*> targets;
   PinnedBuf geom;       // pinned copy of host-pointer geometry
   size_t geom_len = 0;
+  DevBuf d_direct;      // geometry DMA'd straight from page-locked caller memory
+  size_t direct_len = 0;
   PinnedBuf table;      // pinned [DrawDesc x n][vbase][pbase][TargetDesc x nt]
   DevBuf d_geom, d_table, d_dstats, d_status;
   PinnedBuf h_dstats;
@@ -119,6 +122,7 @@ struct rf_mesh {
 struct rf_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_in = nullptr; // H2D of page-locked caller geometry during rf_render
   cudaStream_t copy = nullptr;   // asynchronous downloads: D2H overlaps the next pass
   cudaEvent_t ev_copy = nullptr;
   cudaStream_t side = nullptr;   // binning chain (k_bin_alloc/scatter/sort) overlaps the span chain (k_edge_ckpt/k_walk/k_ckpt)
@@ -358,8 +362,9 @@ rf_status launch_pass(rf_ctx* c, int si) {
     QueuedDraw& q = s.draws[i];
     DrawDesc d = q.desc;
     if (q.verts_off != SIZE_MAX) {
-      d.verts = reinterpret_cast<const float*>(static_cast<uint8_t*>(s.d_geom.p) + q.verts_off);
-      d.indices = reinterpret_cast<const uint32_t*>(static_cast<uint8_t*>(s.d_geom.p) + q.idx_off);
+      uint8_t* gbase = static_cast<uint8_t*>(q.direct ? s.d_direct.p : s.d_geom.p);
+      d.verts = reinterpret_cast<const float*>(gbase + q.verts_off);
+      d.indices = reinterpret_cast<const uint32_t*>(gbase + q.idx_off);
     }
     h_draws[i] = d;
     h_vbase[i] = vb; h_pbase[i] = pb;
@@ -473,6 +478,7 @@ void reset_slot(PassSlot& s) {
   s.clears.clear();
   s.draws.clear();
   s.geom_len = 0;
+  s.direct_len = 0;
   s.in_flight = false;
 }
 
@@ -605,18 +611,47 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
     if (d->mesh->stride < 3 + d->n_attr_lanes) return fail(c, RF_E_INVALID, "mesh stride too small");
     D.verts = d->mesh->d_verts; D.indices = d->mesh->d_idx;
     D.vstride = d->mesh->stride; D.n_verts = d->mesh->n_verts; D.n_prims = d->mesh->n_prims;
-    q.verts_off = q.idx_off = SIZE_MAX;
+    q.verts_off = q.idx_off = SIZE_MAX; q.direct = false;
   } else {
     if ((d->n_prims && !d->indices) || (d->n_verts && !d->verts)) return fail(c, RF_E_INVALID, "null geometry");
     if (d->vert_stride_f32 < 3 + d->n_attr_lanes) return fail(c, RF_E_INVALID, "vert_stride_f32 < 3 + n_attr_lanes");
     const size_t vb = (size_t)d->n_verts * d->vert_stride_f32 * 4, ib = (size_t)d->n_prims * 12;
-    const size_t off = (s.geom_len + 15) & ~size_t(15);
-    const size_t ioff = (off + vb + 15) & ~size_t(15);
-    if (!s.geom.reserve(ioff + ib + 16)) return fail(c, RF_E_NOMEM, "pinned geometry staging");
-    if (vb) std::memcpy(s.geom.p + off, d->verts, vb);
-    if (ib) std::memcpy(s.geom.p + ioff, d->indices, ib);
-    s.geom_len = ioff + ib;
-    q.verts_off = off; q.idx_off = ioff;
+    // Page-locked caller memory (rf_host_alloc) is DMA'd to the device right here, on the copy-in stream, and the
+    // call waits for it: the borrow ends at return, as in the reference, but without a staging memcpy. Pageable
+    // memory is copied into pinned staging instead and uploaded with the pass.
+    bool pinned_src = vb + ib >= (64u << 10);
+    if (pinned_src) {
+      cudaPointerAttributes av{}, ai{};
+      pinned_src = cudaPointerGetAttributes(&av, d->verts) == cudaSuccess && av.type == cudaMemoryTypeHost &&
+                   cudaPointerGetAttributes(&ai, d->indices) == cudaSuccess && ai.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+    }
+    if (pinned_src) {
+      const size_t off = (s.direct_len + 15) & ~size_t(15);
+      const size_t ioff = (off + vb + 15) & ~size_t(15);
+      if (ioff + ib + 16 > s.d_direct.cap) {  // grow, preserving what earlier draws of this pass uploaded
+        DevBuf nb;
+        if (!nb.reserve(std::max<size_t>((ioff + ib + 16) * 2, 8u << 20))) return fail(c, RF_E_NOMEM, "direct geometry buffer");
+        if (s.direct_len) RF_CUDA(c, cudaMemcpyAsync(nb.p, s.d_direct.p, s.direct_len, cudaMemcpyDeviceToDevice, c->copy_in));
+        RF_CUDA(c, cudaStreamSynchronize(c->copy_in));
+        s.d_direct.release();
+        s.d_direct = nb;
+      }
+      uint8_t* db = static_cast<uint8_t*>(s.d_direct.p);
+      if (vb) RF_CUDA(c, cudaMemcpyAsync(db + off, d->verts, vb, cudaMemcpyHostToDevice, c->copy_in));
+      if (ib) RF_CUDA(c, cudaMemcpyAsync(db + ioff, d->indices, ib, cudaMemcpyHostToDevice, c->copy_in));
+      RF_CUDA(c, cudaStreamSynchronize(c->copy_in));
+      s.direct_len = ioff + ib;
+      q.verts_off = off; q.idx_off = ioff; q.direct = true;
+    } else {
+      const size_t off = (s.geom_len + 15) & ~size_t(15);
+      const size_t ioff = (off + vb + 15) & ~size_t(15);
+      if (!s.geom.reserve(ioff + ib + 16)) return fail(c, RF_E_NOMEM, "pinned geometry staging");
+      if (vb) std::memcpy(s.geom.p + off, d->verts, vb);
+      if (ib) std::memcpy(s.geom.p + ioff, d->indices, ib);
+      s.geom_len = ioff + ib;
+      q.verts_off = off; q.idx_off = ioff; q.direct = false;
+    }
     D.vstride = d->vert_stride_f32; D.n_verts = d->n_verts; D.n_prims = d->n_prims;
   }
   D.L = d->n_attr_lanes; D.persp_mask = d->persp_mask; D.vs = d->vs; D.fs = d->fs;
@@ -664,6 +699,7 @@ rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
     c->own_stream = true;
   }
   if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) { rf_ctx_destroy(c); return RF_E_CUDA; }
   bool ok = cudaMalloc(&c->d_cstatus, sizeof(CtxStatus)) == cudaSuccess && cudaMemset(c->d_cstatus, 0, sizeof(CtxStatus)) == cudaSuccess;
   for (int k = 0; k < kSlots && ok; k++) {
@@ -689,7 +725,7 @@ void rf_ctx_destroy(rf_ctx* c) {
   for (int k = 0; k < kSlots; k++) {
     PassSlot& s = c->slots[k];
     s.geom.release(); s.table.release(); s.h_dstats.release();
-    s.d_geom.release(); s.d_table.release(); s.d_dstats.release(); s.d_status.release();
+    s.d_geom.release(); s.d_direct.release(); s.d_table.release(); s.d_dstats.release(); s.d_status.release();
     if (s.h_status) cudaFreeHost(s.h_status);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
@@ -702,6 +738,7 @@ void rf_ctx_destroy(rf_ctx* c) {
   if (c->d_cstatus) cudaFree(c->d_cstatus);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+  if (c->copy_in) cudaStreamDestroy(c->copy_in);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -742,8 +779,14 @@ void rf_target_destroy(rf_target* t) {
 rf_status rf_target_clear(rf_ctx* c, rf_target* t, const uint8_t* rgba, const float* depth_recip) {
   if (!c || !t) return fail(c, RF_E_INVALID, "null argument");
   if (t->ctx != c) return fail(c, RF_E_INVALID, "target belongs to another ctx");
-  // A clear is recorded at the head of a pass so that it is ordered with, and replayed with, its draws.
-  if (!c->slots[c->cur].draws.empty()) { rf_status st = flush_impl(c); if (st) return st; }
+  // A clear is recorded at the head of a pass so that it is ordered with, and replayed with, its draws. Only draws
+  // into THIS target order against it: clears of other targets join the pass being collected (clear A, draw A,
+  // clear B, draw B ... is one pass).
+  {
+    bool touched = false;
+    for (const QueuedDraw& q : c->slots[c->cur].draws) touched = touched || q.target == t;
+    if (touched) { rf_status st = flush_impl(c); if (st) return st; }
+  }
   QueuedClear qc{t, rgba != nullptr, depth_recip != nullptr && t->has_depth, 0u, 0u};
   if (rgba) qc.color = pack_pixel_host(t->fmt, rgba);
   if (qc.has_depth) std::memcpy(&qc.zbits, depth_recip, 4);

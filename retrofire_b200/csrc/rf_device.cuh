@@ -211,26 +211,32 @@ __device__ __forceinline__ uint32_t find_draw(const uint32_t* __restrict__ base,
   return lo;
 }
 
-__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
-__device__ __forceinline__ uint32_t lanemask_lt() { return (1u << lane_id()) - 1u; }
+// Lane index, read ONCE per kernel. The asm is volatile on purpose: otherwise the compiler prefers to
+// re-read the special register (S2R, a slow XU-pipe instruction) inside hot loops instead of keeping
+// the value in a register; kernels pass `lane` (and the lanes-below mask `lt`) to the helpers below.
+__device__ __forceinline__ uint32_t lane_id() {
+  uint32_t l;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l;
+}
 
 // inclusive warp scan
-__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v) {
+__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
-    if ((int)lane_id() >= o) v += t;
+    if ((int)lane >= o) v += t;
   }
   return v;
 }
 
 // Warp-aggregated increment usable from divergent code: the currently converged lanes elect a
 // leader that performs one atomic for the group; returns this lane's slot.
-__device__ __forceinline__ unsigned long long agg_atomic_inc(PaddedCounter* ctr) {
+__device__ __forceinline__ unsigned long long agg_atomic_inc(PaddedCounter* ctr, uint32_t lane) {
   const uint32_t mask = __activemask();
   const int leader = __ffs(mask) - 1;
   unsigned long long base = 0;
-  if ((int)lane_id() == leader) base = atomicAdd(ctr, (unsigned long long)__popc(mask));
+  if ((int)lane == leader) base = atomicAdd(ctr, (unsigned long long)__popc(mask));
   base = __shfl_sync(mask, base, leader);
-  return base + __popc(mask & lanemask_lt());
+  return base + __popc(mask & ((1u << lane) - 1u));
 }

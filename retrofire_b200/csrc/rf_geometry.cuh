@@ -305,7 +305,7 @@ template <int LT>
 __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
   constexpr int QW = Rec<LT>::QW;
   if (P.cstatus->poison) return;
-  const uint32_t lane = lane_id();
+  const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t n_iter = (P.NP + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
   for (uint32_t it = 0; it < n_iter; it++) {
     const uint32_t gp = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
         continue;
       }
       if (emit) {
-        uint32_t* q = P.stris + (size_t)((uint32_t)base + __popc(emask & lanemask_lt())) * QW;
+        uint32_t* q = P.stris + (size_t)((uint32_t)base + __popc(emask & lt)) * QW;
         uint32_t w[QW];
         w[0] = gp * 8u + t; w[1] = d;
 #pragma unroll
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
   __shared__ unsigned long long s_base[4];
   __shared__ uint32_t s_fit[4];
   if (P.cstatus->poison) return;
-  const uint32_t lane = lane_id();
+  const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t NT = (uint32_t)min(P.status->stris_needed, (unsigned long long)P.cap_stris);
   const uint32_t n_iter = (NT + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
   for (uint32_t it = 0; it < n_iter; it++) {
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
     }
     // ---- block-aggregated allocation: warp prefix sums, then ONE atomic per counter per block
     const uint32_t nsp = emit ? (H0.n + H1.n) : 0u;
-    const uint32_t incl_s = warp_scan_incl(nsp), incl_e = warp_scan_incl(nent), incl_c = warp_scan_incl(nchunk);
+    const uint32_t incl_s = warp_scan_incl(nsp, lane), incl_e = warp_scan_incl(nent, lane), incl_c = warp_scan_incl(nchunk, lane);
     const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
     const uint32_t wid = threadIdx.x >> 5;
     if (lane == 31) { s_tot[wid][0] = incl_s; s_tot[wid][1] = __popc(emask); s_tot[wid][2] = incl_e; s_tot[wid][3] = incl_c; }
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
     }
     if (emit) {
       const uint32_t sbase = (uint32_t)sb + (incl_s - nsp);
-      const uint32_t tri_idx = (uint32_t)tb + __popc(emask & lanemask_lt());
+      const uint32_t tri_idx = (uint32_t)tb + __popc(emask & lt);
       uint32_t eidx = (uint32_t)eb + (incl_e - nent);
       uint32_t cidx = (uint32_t)cb_ + (incl_c - nchunk);
       const bool inline_walk = H0.n + H1.n <= RF_INLINE_ROWS;
@@ -596,13 +596,13 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
         if (oob) atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
         long_sbase = sbase; long_tri = tri_idx; long_nU = nU;
       }
-      if (ch0 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
-      if (ch1 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u + 1u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
+      if (ch0 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed, lane); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
+      if (ch1 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed, lane); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u + 1u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
     }
     // ---- long list of the inline walks: one warp-aggregated allocation (warp prefix sum) for all lanes
     {
       const uint32_t nl = __popc(long_rows);
-      const uint32_t incl_l = warp_scan_incl(nl);
+      const uint32_t incl_l = warp_scan_incl(nl, lane);
       const uint32_t tot_l = __shfl_sync(0xFFFFFFFFu, incl_l, 31);
       if (tot_l) {
         unsigned long long lb = 0;
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(128) k_walk(PassParams P) {
   constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS, EW = Rec<LT>::EW, SW = Rec<LT>::SW;
   using TR = TriRec<LT>;
   if (P.cstatus->poison) return;
-  const uint32_t lane = lane_id();
+  const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t nch = (uint32_t)min(P.status->chunks_needed, (unsigned long long)P.cap_chunks);
   const uint32_t wpb = blockDim.x >> 5;
   const uint32_t stride = gridDim.x * wpb * 32u;
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(128) k_walk(PassParams P) {
     ch_next = make_uint4(0u, 0u, 0u, 0u);
     if (cb + stride + lane < nch) ch_next = __ldg(P.chunks + cb + stride + lane);
     const uint32_t c_rows = c_have ? (ch.y >> 16) : 0u;
-    const uint32_t incl = warp_scan_incl(c_rows);
+    const uint32_t incl = warp_scan_incl(c_rows, lane);
     const uint32_t n_items = __shfl_sync(0xFFFFFFFFu, incl, 31);
     unsigned long long my_frags_i = 0;
     uint32_t my_draw = 0xFFFFFFFFu;
@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(128) k_walk(PassParams P) {
             }
           }
           if (ll_next + nl <= ll_end) {
-            if (is_long) P.longlist[ll_next + __popc(lm & lanemask_lt())] = make_uint2(long_sidx, cur.own);
+            if (is_long) P.longlist[ll_next + __popc(lm & lt)] = make_uint2(long_sidx, cur.own);
             ll_next += nl;
           }
         }

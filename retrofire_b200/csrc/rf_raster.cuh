@@ -18,12 +18,12 @@
 
 __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
   if (P.cstatus->poison) return;
-  const uint32_t lane = lane_id();
+  const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t n_iter = (P.n_tiles + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
   for (uint32_t it = 0; it < n_iter; it++) {
     const uint32_t t = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     const uint32_t c = t < P.n_tiles ? P.tile_cnt[t] : 0u;
-    const uint32_t incl = warp_scan_incl(c);
+    const uint32_t incl = warp_scan_incl(c, lane);
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
     const uint32_t nz = __ballot_sync(0xFFFFFFFFu, c != 0);
     const uint32_t big = __ballot_sync(0xFFFFFFFFu, c > RF_SORT_SMALL);
@@ -45,15 +45,15 @@ __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
     // valid entries <= entry slots <= cap_entries, so the bins always fit
     if (c != 0) {
       P.tile_off[t] = base + (incl - c);
-      P.worklist[wbase + __popc(nz & lanemask_lt())] = t;
-      if (c > RF_SORT_SMALL) P.worklist_big[bbase + __popc(big & lanemask_lt())] = t;
+      P.worklist[wbase + __popc(nz & lt)] = t;
+      if (c > RF_SORT_SMALL) P.worklist_big[bbase + __popc(big & lt)] = t;
       // heaviest tiles from the front of the array, heavy ones from its back
       if (c >= RF_HEAVIEST_BIN) {  // split into RF_SLICES row slices, each rasterised by its own warp
-        const uint32_t b = hhbase + __popc(heaviest & lanemask_lt()) * RF_SLICES;
+        const uint32_t b = hhbase + __popc(heaviest & lt) * RF_SLICES;
 #pragma unroll
         for (uint32_t sl = 0; sl < RF_SLICES; sl++) P.worklist_heavy[b + sl] = t | (sl + 1u) << 28;
       }
-      else if (c >= RF_HEAVY_BIN) P.worklist_heavy[P.n_tiles - 1 - (hbase + __popc(heavy & lanemask_lt()))] = t;
+      else if (c >= RF_HEAVY_BIN) P.worklist_heavy[P.n_tiles - 1 - (hbase + __popc(heavy & lt))] = t;
       if (c > RF_SORT_BIG) atomicOr(&P.status->error, RF_ERRBIT_BIN_TOO_DEEP);
       atomicMax(&P.status->max_bin, c);
     }
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_ckpt(PassParams P) {
   constexpr int NV = 1 + LT;
   if (P.cstatus->poison) return;
   const uint32_t nl = (uint32_t)min(P.status->long_needed, (unsigned long long)P.cap_long);
-  const uint32_t lane = lane_id();
+  const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t n_iter = (nl + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
   for (uint32_t it = 0; it < n_iter; it++) {
     const uint32_t li = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_ckpt(PassParams P) {
         nck = ((X0 + n - 1) >> RF_TILE_SHIFT) - (X0 >> RF_TILE_SHIFT);
       }
     }
-    const uint32_t incl = warp_scan_incl(nck);
+    const uint32_t incl = warp_scan_incl(nck, lane);
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
     unsigned long long base = 0;
     if (lane == 0 && total) base = atomicAdd(&P.status->ckpts_needed, (unsigned long long)total);
@@ -154,7 +154,7 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 __global__ void __launch_bounds__(RF_SORT_WARPS * 32) k_bin_sort_warp(PassParams P) {
   __shared__ unsigned long long sk_all[RF_SORT_WARPS][RF_SORT_SMALL];
   if (P.cstatus->poison) return;
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id(), lt = (1u << lane) - 1u, warp = threadIdx.x >> 5;
   unsigned long long* sk = sk_all[warp];
   const uint32_t n_work = P.status->n_work;
   const uint32_t gw = blockIdx.x * RF_SORT_WARPS + warp, nw = gridDim.x * RF_SORT_WARPS;
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
   constexpr int NV = 1 + LT;
   extern __shared__ uint32_t s_raster[];
   if (P.cstatus->poison || P.status->error) return;
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id(), lt = (1u << lane) - 1u, warp = threadIdx.x >> 5;
   // Only DEPTH is staged in shared memory: colour is write-only on this path (no blending, target.rs:187-189),
   // so passing fragments store their pixel straight to the framebuffer. __syncwarp() between dependency
   // rounds orders two writes to one pixel; untouched pixels are never read or written.
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
         const uint32_t rb = min(t_Y0 + nrows, py0 + r1);
         t_rows = rb > t_ra ? rb - t_ra : 0u;
       }
-      const uint32_t t_incl = warp_scan_incl(t_rows);
+      const uint32_t t_incl = warp_scan_incl(t_rows, lane);
       const uint32_t n_items = __shfl_sync(0xFFFFFFFFu, t_incl, 31);
 
       // Software pipeline: the span record and dv/dx of batch n+1 are requested before batch n is
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
         }
         uint32_t my_o = 0;
 
-        const uint32_t f_incl = warp_scan_incl(pn);
+        const uint32_t f_incl = warp_scan_incl(pn, lane);
         const uint32_t n_frags = __shfl_sync(0xFFFFFFFFu, f_incl, 31);
 
         if (n_frags >= RF_SPAN_MODE_MIN_AVG * (uint32_t)__popc(vmask)) {
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
           // dependencies: earlier lanes on the same row whose x-range overlaps mine
           uint32_t dep = 0;
           {
-            uint32_t m = __match_any_sync(0xFFFFFFFFu, py) & lanemask_lt();
+            uint32_t m = __match_any_sync(0xFFFFFFFFu, py) & lt;
             while (__any_sync(0xFFFFFFFFu, m != 0)) {
               const int jj = m ? (__ffs(m) - 1) : (int)lane;
               const uint32_t ox = __shfl_sync(0xFFFFFFFFu, pxs, jj), on = __shfl_sync(0xFFFFFFFFu, pn, jj);
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
                 for (int i = 0; i < NV; i++) fv[i] = 0.0f;
               }
               const uint32_t pix = fvalid ? (pw & 0xFFFFu) : (0x10000u + lane);
-              const uint32_t earlier = __match_any_sync(0xFFFFFFFFu, pix) & lanemask_lt();  // same pixel, submitted before me
+              const uint32_t earlier = __match_any_sync(0xFFFFFFFFu, pix) & lt;  // same pixel, submitted before me
               uint32_t fdraw = d0, pmask = u_pmask, fs = u_fs, dtest = u_dtest;
               bool cwrite = u_cwrite, dwrite = u_dwrite;
               if (!UNI) {

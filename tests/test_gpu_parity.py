@@ -121,6 +121,27 @@ def test_frame_batch_render_frames(device, oracle):
     assert got_stats.counters() == want_total.counters()
 
 
+def test_page_locked_geometry_is_dmad_directly(device, oracle):
+    """Vertex/index arrays in rf_host_alloc memory take the direct-DMA path of rf_render (several draws per pass,
+    mixed with pageable draws that go through pinned staging); results are identical."""
+    import dataclasses
+    a = scenes.random_soup(4000, 640, 360, seed=51, lanes_kind="lit", big=False)
+    b = scenes.random_soup(4000, 640, 360, seed=52, lanes_kind="color3", big=True)
+    c = scenes.random_soup(4000, 640, 360, seed=53, lanes_kind="lit", big=True)
+    want = a
+    want.draws = a.draws + b.draws + c.draws
+
+    def pin(x):
+        y = device.pinned_empty(x.shape, x.dtype)
+        y[...] = x
+        return y
+
+    got_scene = dataclasses.replace(want, draws=[dataclasses.replace(want.draws[0], prims=pin(want.draws[0].prims), verts=pin(want.draws[0].verts)),
+                                                  want.draws[1],
+                                                  dataclasses.replace(want.draws[2], prims=pin(want.draws[2].prims), verts=pin(want.draws[2].verts))])
+    assert_parity(run_gpu(device, got_scene), run_oracle(oracle, want), name="direct-dma")
+
+
 def test_odd_sized_target(device, oracle):
     """Width/height not multiples of the tile or of 4 (scalar tile I/O path)."""
     sc = scenes.random_soup(500, 333, 211, seed=5, lanes_kind="color3", big=True)
