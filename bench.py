@@ -44,7 +44,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="bunny", choices=["bunny", "crates", "sprites"])
+    ap.add_argument("--workload", default="bunny", choices=["bunny", "crates", "sprites", "small_tris"])
+    ap.add_argument("--sharding", default="frames", choices=["frames", "tiles"],
+                    help="frames: every rank renders its own frame batch (weak scaling); tiles: sort-first row bands of ONE large frame "
+                         "per step + NCCL all_gather of the finished bands (strong scaling, SURVEY 8e)")
     ap.add_argument("--frames", type=int, default=32, help="frames per step (frame batch)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and cpu_baseline legs (for ncu runs)")
@@ -68,6 +71,12 @@ def make_workload(name: str, frames: int):
         base = scenes.crates("1089")
         per_frame = [base.draws for _ in range(frames)]
         desc = {"workload": "crates 1,089 textured cubes + floor 3840x2160 Rgba8888, one draw per cube", "frames_per_step": frames,
+                "resolution": [base.w, base.h]}
+        return base, per_frame, desc
+    if name == "small_tris":
+        base = scenes.small_tris(1_000_000)
+        per_frame = [base.draws for _ in range(frames)]
+        desc = {"workload": "1,000,000 small triangles (circumradius 1-8 px) 7680x4320 Rgba8888+depth", "frames_per_step": frames,
                 "resolution": [base.w, base.h]}
         return base, per_frame, desc
     base = scenes.sprites(10000)
@@ -245,6 +254,21 @@ def run_b200(args):
     dev.profile(0)
     _, launches_per_pass = dev.last_pass()
 
+    # ---- single-frame latency, reported separately: clear + draw + wait, one frame per pass
+    lat_ms = None
+    if not args.kernel_only:
+        one = res_frames[0]
+        ts = []
+        for k in range(30):
+            dev.sync()
+            t0 = time.perf_counter()
+            targets[0].clear(base.ctx)
+            for d in one:
+                dev.render(d, targets[0])
+            dev.sync()
+            ts.append(time.perf_counter() - t0)
+        lat_ms = 1e3 * sorted(ts[5:])[len(ts[5:]) // 2]
+
     # ---- end to end: host geometry in (rf_render with host pointers: staged through pinned memory and
     # copied H2D inside the timed region), colour buffer of every frame out (D2H into page-locked Buf2 storage)
     Fe = min(F, 8)
@@ -376,6 +400,8 @@ def run_b200(args):
         }
         if crates_info is not None:
             line["crates_4k"] = crates_info
+        if lat_ms is not None:
+            line["single_frame_latency_ms"] = lat_ms  # wall clock of clear + render + sync for ONE frame (not batched)
         if world == 1 and not args.kernel_only:
             # CPU baseline: oracle, 1 thread (the reference is single-threaded), bounded sample
             n = 0
@@ -392,10 +418,82 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_tiles(args):
+    """Sort-first: geometry replicated, rank r rasterises its row band of one large frame, bands gathered with NCCL."""
+    import torch
+    import torch.distributed as dist
+    from retrofire_b200 import shard
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream(device=local)
+    base, per_frame, desc = make_workload(args.workload, 1)
+    dev = rf.Device(local, stream=stream.cuda_stream)
+    bands = shard.row_bands(base.h, world)
+    dev.set_row_band(*bands[rank])
+    fb = dev.framebuf(base.w, base.h, base.fmt, base.has_depth)
+    import dataclasses
+    draws = [dataclasses.replace(d, mesh=dev.mesh(d.prims, d.verts)) for d in per_frame[0]]
+    color = shard.target_tensor(fb)
+
+    def step():
+        fb.clear(base.ctx)
+        for d in draws:
+            dev.render(d, fb)
+        dev.flush()
+        if world > 1:
+            with torch.cuda.stream(stream):
+                shard.gather_bands(color, bands, rank)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+        dev.sync()
+    dev.stats(reset=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    dev.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    st = dev.stats(reset=True)
+    fi, pi = st.frags.i, st.prims.i
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt[0])
+        cc = torch.tensor([fi], device="cuda", dtype=torch.int64)
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        fi = int(cc[0])
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Mfragments/s", "value": fi / (ms * 1e-3) / 1e6, "unit": "Mfragments/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(desc, parallelism=f"sort-first row bands x{world} + NCCL all_gather of finished bands", bands=bands,
+                           l2="inputs larger than L2: 265 MB colour+depth target + 84 MB geometry per step"),
+            "frames_per_s": args.steps / (ms * 1e-3), "Mtriangles_per_s": pi / (ms * 1e-3) / 1e6,
+            "gather_bytes_per_step": 0 if world == 1 else base.w * base.h * 4 * (world - 1) // world}), flush=True)
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.sharding == "tiles":
+        run_tiles(args)
     else:
         run_b200(args)
 

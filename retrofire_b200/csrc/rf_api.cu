@@ -387,9 +387,12 @@ rf_status launch_pass(rf_ctx* c, int si) {
   {
     size_t k = 0;
     for (const QueuedClear& qc : s.clears) {
-      const unsigned long long n = (unsigned long long)qc.target->w * qc.target->h;
-      if (qc.has_color) h_clears[k++] = ClearDesc{qc.target->d_color, n, qc.color, 0u};
-      if (qc.has_depth) h_clears[k++] = ClearDesc{reinterpret_cast<uint32_t*>(qc.target->d_depth), n, qc.zbits, 0u};
+      // under sort-first sharding only the rows of this GPU's band are cleared (the others are never rasterised here)
+      const uint32_t y0 = std::min(c->band_y0, qc.target->h), y1 = std::min(c->band_y1, qc.target->h);
+      const size_t first = (size_t)y0 * qc.target->w;
+      const unsigned long long n = (unsigned long long)(y1 > y0 ? y1 - y0 : 0) * qc.target->w;
+      if (qc.has_color) h_clears[k++] = ClearDesc{qc.target->d_color + first, n, qc.color, 0u};
+      if (qc.has_depth) h_clears[k++] = ClearDesc{reinterpret_cast<uint32_t*>(qc.target->d_depth) + first, n, qc.zbits, 0u};
     }
   }
 

@@ -509,8 +509,12 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
               tile_row_cols<LT>(H0, H1, Y0, nrows, tr, margin, tiles_x, ca, cb);
               nent += cb - ca + 1;
             }
-          } else { tr0 = 1; tr1 = 0; }
-          if (nrows > RF_INLINE_ROWS) nchunk = (H0.n + RF_CHUNK - 1) / RF_CHUNK + (H1.n + RF_CHUNK - 1) / RF_CHUNK;
+          } else {
+            // sort-first sharding: no scanline of this triangle is in this GPU's row band -> nothing to walk or rasterise
+            // (its x-extent can no longer raise RF_E_TARGET_OOB here; the rank that owns the rows reports it)
+            emit = false; H0.n = H1.n = 0; tr0 = 1; tr1 = 0;
+          }
+          if (emit && nrows > RF_INLINE_ROWS) nchunk = (H0.n + RF_CHUNK - 1) / RF_CHUNK + (H1.n + RF_CHUNK - 1) / RF_CHUNK;
         }
       }
     }

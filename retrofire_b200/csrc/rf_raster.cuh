@@ -740,9 +740,14 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
 __global__ void __launch_bounds__(256) k_clear_multi(const ClearDesc* __restrict__ cl, const CtxStatus* cs) {
   if (cs->poison) return;
   const ClearDesc c = cl[blockIdx.y];
-  const size_t n4 = c.n >> 2;
-  uint4* p4 = reinterpret_cast<uint4*>(c.ptr);
+  // scalar head up to 16-byte alignment (a row band may start at any row of an odd-width target), 128-bit body, scalar tail
+  const size_t head = min((size_t)c.n, (size_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(c.ptr) & 15u)) & 15u) >> 2);
+  uint32_t* body = c.ptr + head;
+  const size_t nb = c.n - head, n4 = nb >> 2;
+  uint4* p4 = reinterpret_cast<uint4*>(body);
   const uint4 v4 = make_uint4(c.value, c.value, c.value, c.value);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p4[i] = v4;
-  for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < c.n; i += (size_t)gridDim.x * blockDim.x) c.ptr[i] = c.value;
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  if (tid < head) c.ptr[tid] = c.value;
+  for (size_t i = tid; i < n4; i += nth) p4[i] = v4;
+  for (size_t i = (n4 << 2) + tid; i < nb; i += nth) body[i] = c.value;
 }

@@ -21,7 +21,12 @@ TILE = 32
 
 
 def row_bands(h: int, world: int, tile: int = TILE) -> List[Tuple[int, int]]:
-    """Contiguous row bands covering [0, h), one per rank, in whole tile rows (last may be short or empty)."""
+    """Contiguous row bands covering [0, h), one per rank: equal bands when h divides evenly, else whole tile rows."""
+    if h % world == 0:
+        # equal bands gather in place with one all_gather. They need not be tile aligned: a tile that straddles two bands is
+        # rasterised by both owners, each producing only its own rows (the others are replaced by the gather).
+        step = h // world
+        return [(r * step, (r + 1) * step) for r in range(world)]
     tiles = (h + tile - 1) // tile
     per, extra = divmod(tiles, world)
     out, t0 = [], 0
@@ -61,6 +66,12 @@ def gather_bands(buf, bands: Sequence[Tuple[int, int]], rank: int, group=None):
     import torch.distributed as dist
     world = len(bands)
     h, w = buf.shape
+    sizes = {b[1] - b[0] for b in bands}
+    if len(sizes) == 1 and buf.is_cuda and buf.is_contiguous() and hasattr(dist, "all_gather_into_tensor"):
+        # equal bands: in-place all-gather straight into the framebuffer (input is the rank's own slice of the output)
+        y0, y1 = bands[rank]
+        dist.all_gather_into_tensor(buf.view(-1), buf[y0:y1].reshape(-1), group=group)
+        return buf
     rows = max(b[1] - b[0] for b in bands)
     send = torch.zeros((rows, w), dtype=buf.dtype, device=buf.device)
     y0, y1 = bands[rank]
