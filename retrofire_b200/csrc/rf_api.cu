@@ -136,7 +136,7 @@ struct rf_ctx {
   std::vector<int> flight;     // slots launched and not yet validated, oldest first
 
   // scratch arenas shared by all passes (stream order makes reuse safe)
-  DevBuf cv, stris, spans, tris, entries, bins, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
+  DevBuf cv, stris, spans, tris, entries, bins, bins2, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
   // capacities: spans/tris/ckpts in 32-bit WORDS (record width depends on the pass's lane count),
   // entries and long spans in records
   size_t capw_stris = 0, capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
@@ -284,7 +284,7 @@ rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const Aren
   if (w.w_tris > c->capw_tris) { if (!c->tris.reserve(w.w_tris * 4)) return fail(c, RF_E_NOMEM, "triangle arena"); c->capw_tris = w.w_tris; }
   if (w.w_ckpts > c->capw_ckpts) { if (!c->ckpts.reserve(w.w_ckpts * 4)) return fail(c, RF_E_NOMEM, "checkpoint arena"); c->capw_ckpts = w.w_ckpts; }
   if (w.entries > c->cap_entries) {
-    if (!c->entries.reserve(w.entries * 16) || !c->bins.reserve(w.entries * 8)) return fail(c, RF_E_NOMEM, "bin arena");
+    if (!c->entries.reserve(w.entries * 16) || !c->bins.reserve(w.entries * 8) || !c->bins2.reserve(w.entries * 8)) return fail(c, RF_E_NOMEM, "bin arena");
     c->cap_entries = w.entries;
   }
   if (w.longs > c->cap_long) { if (!c->longlist.reserve(w.longs * 8)) return fail(c, RF_E_NOMEM, "long-span list"); c->cap_long = w.longs; }
@@ -443,6 +443,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.tris = static_cast<uint32_t*>(c->tris.p);
   P.entries = static_cast<uint4*>(c->entries.p);
   P.bins = static_cast<unsigned long long*>(c->bins.p);
+  P.bins2 = static_cast<unsigned long long*>(c->bins2.p);
   P.longlist = static_cast<uint2*>(c->longlist.p);
   P.ckpts = static_cast<uint32_t*>(c->ckpts.p);
   // capacities in records of THIS pass's width
@@ -736,7 +737,7 @@ void rf_ctx_destroy(rf_ctx* c) {
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
   }
-  c->cv.release(); c->stris.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
+  c->cv.release(); c->stris.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->bins2.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
   if (c->d_cstatus) cudaFree(c->d_cstatus);
   if (c->side) cudaStreamDestroy(c->side);

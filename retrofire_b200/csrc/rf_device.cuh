@@ -110,6 +110,7 @@ struct PassParams {
   uint32_t* tris;         // [cap_tris][TW]    per drawn triangle: key, draw, rows, dv/dx of both halves
   uint4* entries;         // [cap_entries]     {tile, key, tri, 0}: one per (triangle, overlapped tile)
   unsigned long long* bins;  // [cap_entries]  per-tile lists of (key << 32 | tri), sorted by k_bin_sort
+  unsigned long long* bins2; // [cap_entries]  merge scratch for bins deeper than one shared-memory run
   uint4* chunks;          // [cap_chunks]      {tri*2+half, chunk | rows << 16, first span, draw | target << 16}
   uint32_t* talllist;     // [cap_tall]        tri*2+half of halves with more than one chunk
   uint32_t* ecks;         // [cap_chunks][EW]  edge state at the start of a chunk (indexed by chunk position; chunk 0 unused)

@@ -11,7 +11,7 @@
 // build the work lists. tile_cnt was accumulated by k_prim.
 // =============================================================================================
 #define RF_SORT_SMALL 1024u   // per-warp shared-memory sort capacity (entries)
-#define RF_SORT_BIG 16384u    // per-block (large smem) sort capacity
+#define RF_SORT_BIG 16384u    // per-block (large smem) sort run; deeper bins are merged from runs of this size
 #define RF_HEAVY_BIN 64u      // tiles are rasterised longest-first in three classes: >= RF_HEAVIEST_BIN, >= RF_HEAVY_BIN, rest
 #define RF_HEAVIEST_BIN 160u
 #define RF_SLICES 4u          // row slices of a heaviest tile (RF_TILE / RF_SLICES rows each); task word = tile | (slice+1) << 28
@@ -54,7 +54,6 @@ __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
         for (uint32_t sl = 0; sl < RF_SLICES; sl++) P.worklist_heavy[b + sl] = t | (sl + 1u) << 28;
       }
       else if (c >= RF_HEAVY_BIN) P.worklist_heavy[P.n_tiles - 1 - (hbase + __popc(heavy & lt))] = t;
-      if (c > RF_SORT_BIG) atomicOr(&P.status->error, RF_ERRBIT_BIN_TOO_DEEP);
       atomicMax(&P.status->max_bin, c);
     }
   }
@@ -199,6 +198,25 @@ __global__ void __launch_bounds__(RF_SORT_WARPS * 32) k_bin_sort_warp(PassParams
   }
 }
 
+// bitonic sort of n2 (power of two) keys in shared memory by one block
+__device__ __forceinline__ void block_bitonic(unsigned long long* sk, uint32_t n2) {
+  for (uint32_t k = 2; k <= n2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t p = threadIdx.x; p < (n2 >> 1); p += blockDim.x) {
+        const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const uint32_t l = i | j;
+        const unsigned long long a = sk[i], b = sk[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { sk[i] = b; sk[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Bins larger than the per-warp sorter: one block per tile. Up to RF_SORT_BIG entries are sorted in shared memory;
+// deeper bins are sorted in runs of RF_SORT_BIG and the runs merged pairwise through a global scratch buffer
+// (every element finds its output slot by binary search in the other run), so there is no depth limit.
 __global__ void __launch_bounds__(256) k_bin_sort_big(PassParams P) {
   extern __shared__ unsigned long long skb[];
   if (P.cstatus->poison) return;
@@ -206,26 +224,44 @@ __global__ void __launch_bounds__(256) k_bin_sort_big(PassParams P) {
   for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
     const uint32_t tile = P.worklist_big[wi];
     const uint32_t cnt = P.tile_cnt[tile], off = P.tile_off[tile];
-    if (cnt > RF_SORT_BIG) continue;  // flagged RF_ERRBIT_BIN_TOO_DEEP
     unsigned long long* bin = P.bins + off;
-    uint32_t n2 = 1;
-    while (n2 < cnt) n2 <<= 1;
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) skb[i] = i < cnt ? bin[i] : ~0ull;
-    __syncthreads();
-    for (uint32_t k = 2; k <= n2; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t p = threadIdx.x; p < (n2 >> 1); p += blockDim.x) {
-          const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-          const uint32_t l = i | j;
-          const unsigned long long a = skb[i], b = skb[l];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) { skb[i] = b; skb[l] = a; }
-        }
-        __syncthreads();
-      }
+    for (uint32_t r0 = 0; r0 < cnt; r0 += RF_SORT_BIG) {  // sorted runs
+      const uint32_t rn = min(RF_SORT_BIG, cnt - r0);
+      uint32_t n2 = 1;
+      while (n2 < rn) n2 <<= 1;
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) skb[i] = i < rn ? bin[r0 + i] : ~0ull;
+      __syncthreads();
+      block_bitonic(skb, n2);
+      for (uint32_t i = threadIdx.x; i < rn; i += blockDim.x) bin[r0 + i] = skb[i];
     }
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) bin[i] = skb[i];
+    if (cnt <= RF_SORT_BIG) continue;
+    unsigned long long* src = bin;
+    unsigned long long* dst = P.bins2 + off;
+    for (uint32_t width = RF_SORT_BIG; width < cnt; width <<= 1) {
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint32_t pair0 = i / (2 * width) * (2 * width);
+        const uint32_t a0 = pair0, a1 = min(cnt, pair0 + width), b1 = min(cnt, pair0 + 2 * width);
+        const unsigned long long v = src[i];
+        uint32_t lo, hi, pos;
+        if (i < a1) {  // element of run A: rank among B = lower_bound
+          lo = a1; hi = b1;
+          while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (src[mid] < v) lo = mid + 1; else hi = mid; }
+          pos = (i - a0) + (lo - a1);
+        } else {       // element of run B: rank among A = upper_bound
+          lo = a0; hi = a1;
+          while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (src[mid] <= v) lo = mid + 1; else hi = mid; }
+          pos = (i - a1) + (lo - a0);
+        }
+        dst[pair0 + pos] = v;
+      }
+      __threadfence_block();
+      unsigned long long* t = src; src = dst; dst = t;
+    }
+    __syncthreads();
+    if (src != bin)
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) bin[i] = src[i];
   }
 }
 

@@ -142,6 +142,26 @@ def test_page_locked_geometry_is_dmad_directly(device, oracle):
     assert_parity(run_gpu(device, got_scene), run_oracle(oracle, want), name="direct-dma")
 
 
+def test_very_deep_tile_bin(device, oracle):
+    """40,000 triangles stacked on the same few tiles: bins deeper than one shared-memory sort run (16,384)
+    are merged from sorted runs; submission order must still be exact (depth ties, frags.o)."""
+    from retrofire_b200 import mathx as mx
+    g = np.random.default_rng(5)
+    n, w, h = 40000, 256, 192
+    z = g.choice(np.array([2.0, 3.0, 4.0], dtype=np.float32), (n, 1))          # many exact depth ties
+    c = g.uniform(-0.05, 0.05, (n, 1, 2)).astype(np.float32) * z[:, :, None]
+    xy = c + g.uniform(-0.04, 0.04, (n, 3, 2)).astype(np.float32) * z[:, :, None]
+    pos = np.concatenate([xy, np.repeat(z[:, :, None], 3, 1)], 2)
+    col = g.uniform(0, 1, (n, 3, 3)).astype(np.float32)
+    verts = np.concatenate([pos, col], 2).reshape(3 * n, 6).astype(np.float32)
+    tris = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    ctx = rf.Context(face_cull=None)
+    sc = scenes.Scene("deep_bin", w, h, rf.FMT_RGBA8888, True, ctx,
+                      [rf.DrawCall.make(tris, verts, rf.shader.new(rf.VS_MVP, rf.FS_COLOR3F), mx.perspective(1.0, w / h, 0.5, 50.0),
+                                        mx.viewport((0, h), (w, 0)), ctx)])
+    check(device, oracle, sc)
+
+
 def test_odd_sized_target(device, oracle):
     """Width/height not multiples of the tile or of 4 (scalar tile I/O path)."""
     sc = scenes.random_soup(500, 333, 211, seed=5, lanes_kind="color3", big=True)
