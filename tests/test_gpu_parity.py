@@ -162,6 +162,26 @@ def test_very_deep_tile_bin(device, oracle):
     check(device, oracle, sc)
 
 
+def test_nan_and_inf_vertices_behave_like_the_reference(device, oracle):
+    """NaN / infinite positions and attributes: outcodes treat NaN as inside (`d > 0.0` is false), saturating
+    casts map NaN to 0 rows — the CUDA path must make exactly the oracle's decisions."""
+    sc = scenes.random_soup(2000, 320, 240, seed=61, lanes_kind="color3", big=True)
+    v = sc.draws[0].verts
+    g = np.random.default_rng(3)
+    for k, val in enumerate((np.nan, np.inf, -np.inf)):
+        rows = g.choice(v.shape[0], 40, replace=False)
+        cols = g.integers(0, v.shape[1], 40)
+        v[rows, cols] = val
+    try:
+        want = run_oracle(oracle, sc)
+    except rf.RetrofireError as e:      # the reference would panic (span outside the target): the ABI must report the same
+        with pytest.raises(rf.RetrofireError) as ge:
+            run_gpu(device, sc)
+        assert ge.value.status == e.status
+        return
+    assert_parity(run_gpu(device, sc), want, name="nan-inf")
+
+
 def test_odd_sized_target(device, oracle):
     """Width/height not multiples of the tile or of 4 (scalar tile I/O path)."""
     sc = scenes.random_soup(500, 333, 211, seed=5, lanes_kind="color3", big=True)
