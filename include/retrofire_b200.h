@@ -98,6 +98,7 @@ typedef enum rf_texel_fmt {
   RF_TEXEL_RGBA8888 = 1 /* Color4, 4 B/texel */
 } rf_texel_fmt;
 
+enum { RF_PRIM_TRIS = 0, RF_PRIM_EDGES = 1 };
 enum { RF_CULL_NONE = 0, RF_CULL_BACK = 1, RF_CULL_FRONT = 2 };                /* ctx.rs:74-78 */
 enum { RF_DEPTH_NONE = 0, RF_DEPTH_LESS = 1, RF_DEPTH_EQUAL = 2, RF_DEPTH_GREATER = 3 }; /* ctx.rs:42-48,86-89 */
 
@@ -105,7 +106,7 @@ enum { RF_DEPTH_NONE = 0, RF_DEPTH_LESS = 1, RF_DEPTH_EQUAL = 2, RF_DEPTH_GREATE
  * (copied during the call, as the reference borrows them only for the call) or from a
  * persistent rf_mesh (then verts/indices must be NULL). */
 typedef struct rf_draw {
-  const uint32_t* indices;  /* 3 per primitive (Tri<usize>, geom/prim.rs:31-33)               */
+  const uint32_t* indices;  /* 3 per primitive (Tri<usize>, geom/prim.rs:31-33), 2 for RF_PRIM_EDGES */
   uint32_t n_prims;
   const float* verts;       /* n_verts records of vert_stride_f32 floats: [x,y,z,a0..a(L-1)]  */
   uint32_t n_verts;
@@ -126,7 +127,9 @@ typedef struct rf_draw {
   uint8_t color_write;      /* default 1                                                      */
   uint8_t depth_write;      /* default 1                                                      */
   uint8_t depth_sort;       /* 0 = None (default). Non-zero -> RF_E_UNSUPPORTED */
-  uint8_t _pad[3];
+  uint8_t prim_kind;        /* RF_PRIM_TRIS: 3 indices per primitive (Tri<usize>); RF_PRIM_EDGES: 2 indices per
+                               primitive (Edge<usize>: render/prim.rs:41-60, clip.rs:311-348, raster.rs:122-177) */
+  uint8_t _pad[2];
 } rf_draw;
 
 /* render/stats.rs:16-40. time_ns is device time of the pass(es) (CUDA events). */

@@ -391,6 +391,37 @@ struct Raster {
     }
   }
 
+  // raster.rs:122-177 — one-pixel-thick line: every pixel carries v0's position and attributes
+  void line(Lanes v0, Lanes v1) {
+    if (v0.v[1] > v1.v[1]) std::swap(v0, v1);
+    const float dx = v1.v[0] - v0.v[0], dy = v1.v[1] - v0.v[1];
+    Lanes zero;
+    for (int i = 0; i < 3 + MAXL; i++) zero.v[i] = 0.0f;  // vary_to(vs, vs, 1): step = (vs - vs) * 1
+    if (fabsf(dx) > dy) {  // more wide than tall
+      if (dx < 0.0f) std::swap(v0, v1);  // always draw from left to right (dx, dy keep their old values)
+      const float x0 = round_up_to_half(v0.v[0]), x1 = round_up_to_half(v1.v[0]);
+      const float dy_dx = dy / dx;
+      float y = v0.v[1] + dy_dx * (x0 - v0.v[0]);
+      const uint64_t xa = sat_usize(x0), xb = sat_usize(x1);
+      for (uint64_t x = xa; x < xb; x++) {
+        scanline(sat_usize(y), x, x + 1, 1, v0, zero);
+        if (oob) return;
+        y = y + dy_dx;
+      }
+    } else {  // more tall than wide
+      const float y0 = round_up_to_half(v0.v[1]), y1 = round_up_to_half(v1.v[1]);
+      const float dx_dy = dx / dy;
+      float x = v0.v[0] + dx_dy * (y0 - v0.v[1]);
+      const uint64_t ya = sat_usize(y0), yb = sat_usize(y1);
+      for (uint64_t yy = ya; yy < yb; yy++) {
+        const uint64_t xi = sat_usize(x);
+        scanline(yy, xi, xi + 1, 1, v0, zero);
+        if (oob) return;
+        x = x + dx_dy;
+      }
+    }
+  }
+
   // raster.rs:185-224
   void tri_fill(const Lanes in[3]) {
     Lanes s[3] = {in[0], in[1], in[2]};
@@ -457,6 +488,62 @@ int rfo_render(const rf_draw* dp, const rfo_texture* texp, rfo_target* tp, rf_st
   std::vector<ClipVert> cvs(d.n_verts);
   for (uint32_t i = 0; i < d.n_verts; i++) shade_vertex(d, d.verts + (size_t)i * d.vert_stride_f32, cvs[i]);
 
+  Target tg{tp->w, tp->h, tp->fmt, tp->color, tp->depth, tp->band_y0, tp->band_y1};
+  Raster R{d, texp ? &tex : nullptr, tg, s, 3 + L};
+  const float* VP = d.viewport;
+  int status = RF_OK;
+  auto screen = [&](const ClipVert& cv, Lanes& out) {  // prim.rs:62-88
+    float w = cv.pos[3];
+    float p[4] = {cv.pos[0] / w, cv.pos[1] / w, 1.0f / w, 1.0f};  // pt3(x,y,1).z_div(w)
+    for (int r = 0; r < 3; r++) out.v[r] = dot4(VP + 4 * r, p);   // mat.rs:945-949
+    for (int i = 0; i < L; i++) out.v[3 + i] = ((d.persp_mask >> i) & 1) ? cv.attr[i] / w : cv.attr[i];
+    for (int i = L; i < MAXL; i++) out.v[3 + i] = 0.0f;
+  };
+
+  if (d.prim_kind == RF_PRIM_EDGES) {
+    // Render for Edge<usize> (prim.rs:41-60) + Clip for [Edge] (clip.rs:311-348) + raster::line
+    struct CEdge { ClipVert a, b; };
+    std::vector<CEdge> clipped;
+    for (uint32_t p = 0; p < d.n_prims; p++) {
+      const uint32_t* idx = d.indices + 2 * (size_t)p;
+      if (idx[0] >= d.n_verts || idx[1] >= d.n_verts) return RF_E_INDEX_OOB;
+      ClipVert a = cvs[idx[0]], b = cvs[idx[1]];
+      if ((a.oc & b.oc) != 0) continue;                                    // both outside one plane
+      if ((a.oc | b.oc) == 0) { clipped.push_back(CEdge{a, b}); continue; }  // neither outside
+      bool keep = true;
+      for (int pl = 0; pl < 6 && keep; pl++) {
+        const uint8_t bit = (uint8_t)(1u << pl);
+        const bool a_in = (a.oc & bit) == 0, b_in = (b.oc & bit) == 0;
+        if (!a_in && !b_in) { keep = false; break; }
+        ClipVert x;
+        if (intersect(pl, a, b, L, x)) {
+          if (a_in) b = x;
+          else if (b_in) a = x;
+        }
+      }
+      if (keep) clipped.push_back(CEdge{a, b});
+    }
+    for (const CEdge& e : clipped) {
+      Lanes sa, sb;
+      screen(e.a, sa);
+      screen(e.b, sb);
+      // Render::is_backface defaults to false (render.rs:72-74): only FaceCull::Front culls an edge (ctx.rs:95-101)
+      if (d.face_cull == RF_CULL_FRONT) continue;
+      s.prims_o += 1;
+      s.verts_o += 3;  // render.rs:196 adds 3 whatever the primitive
+      R.line(sa, sb);
+      if (R.oob) { status = RF_E_TARGET_OOB; break; }
+    }
+    auto t1e = std::chrono::steady_clock::now();
+    s.time_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1e - t0).count();
+    st->calls += s.calls;
+    st->prims_i += s.prims_i; st->prims_o += s.prims_o;
+    st->verts_i += s.verts_i; st->verts_o += s.verts_o;
+    st->frags_i += s.frags_i; st->frags_o += s.frags_o;
+    st->time_ns += s.time_ns;
+    return status;
+  }
+
   // 2+3. assembly and clipping     render.rs:168-177; clip.rs:350-400
   struct CTri { ClipVert v[3]; };
   std::vector<CTri> clipped;
@@ -475,20 +562,9 @@ int rfo_render(const rf_draw* dp, const rfo_texture* texp, rfo_target* tp, rf_st
   }
 
   // 4. per primitive: to_screen, cull, rasterise     render.rs:185-205
-  Target tg{tp->w, tp->h, tp->fmt, tp->color, tp->depth, tp->band_y0, tp->band_y1};
-  Raster R{d, texp ? &tex : nullptr, tg, s, 3 + L};
-  const float* VP = d.viewport;
-  int status = RF_OK;
   for (const CTri& t : clipped) {
     Lanes scr[3];
-    for (int k = 0; k < 3; k++) {  // prim.rs:62-88
-      const ClipVert& cv = t.v[k];
-      float w = cv.pos[3];
-      float p[4] = {cv.pos[0] / w, cv.pos[1] / w, 1.0f / w, 1.0f};  // pt3(x,y,1).z_div(w)
-      for (int r = 0; r < 3; r++) scr[k].v[r] = dot4(VP + 4 * r, p);  // mat.rs:945-949
-      for (int i = 0; i < L; i++) scr[k].v[3 + i] = ((d.persp_mask >> i) & 1) ? cv.attr[i] / w : cv.attr[i];
-      for (int i = L; i < MAXL; i++) scr[k].v[3 + i] = 0.0f;
-    }
+    for (int k = 0; k < 3; k++) screen(t.v[k], scr[k]);
     // geom/prim.rs:150-156,288-294 ; vec.rs:443-445,480-482
     float abx = scr[1].v[0] - scr[0].v[0], aby = scr[1].v[1] - scr[0].v[1];
     float acx = scr[2].v[0] - scr[0].v[0], acy = scr[2].v[1] - scr[0].v[1];

@@ -33,6 +33,7 @@ FMT_RGBA8888, FMT_XRGB8888, FMT_ARGB8888, FMT_BGRA8888, FMT_RGB888, FMT_RGB565, 
 FMT_HOST_BYTES = {0: 4, 1: 4, 2: 4, 3: 4, 4: 3, 5: 2, 6: 2}
 TEXEL_RGB888, TEXEL_RGBA8888 = 0, 1
 
+PRIM_TRIS, PRIM_EDGES = 0, 1
 CULL_NONE, CULL_BACK, CULL_FRONT = 0, 1, 2
 DEPTH_NONE, DEPTH_LESS, DEPTH_EQUAL, DEPTH_GREATER = 0, 1, 2, 3
 
@@ -58,7 +59,8 @@ class RfDraw(C.Structure):
         ("color_write", C.c_uint8),
         ("depth_write", C.c_uint8),
         ("depth_sort", C.c_uint8),
-        ("_pad", C.c_uint8 * 3),
+        ("prim_kind", C.c_uint8),
+        ("_pad", C.c_uint8 * 2),
     ]
 
 

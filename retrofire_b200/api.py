@@ -178,18 +178,20 @@ class DrawCall:
     depth_write: bool = True
     depth_sort: int = 0
     mesh: Optional["Mesh"] = None
+    prim_kind: int = _ffi.PRIM_TRIS   # PRIM_EDGES: prims is (n,2) — `Edge<usize>` line primitives
 
     @staticmethod
-    def make(prims, verts, shd: Shader, uniform, to_screen, ctx: Context = None, mesh: "Mesh" = None) -> "DrawCall":
+    def make(prims, verts, shd: Shader, uniform, to_screen, ctx: Context = None, mesh: "Mesh" = None, edges: bool = False) -> "DrawCall":
         ctx = ctx or Context()
         if mesh is None:
-            prims = np.ascontiguousarray(np.asarray(prims, dtype=np.uint32).reshape(-1, 3))
+            prims = np.ascontiguousarray(np.asarray(prims, dtype=np.uint32).reshape(-1, 2 if edges else 3))
             verts = np.ascontiguousarray(np.asarray(verts, dtype=np.float32))
             assert verts.ndim == 2 and verts.shape[1] >= 3 + shd.lanes, (verts.shape, shd.lanes)
         return DrawCall(prims, verts, shd, _flatten_uniform(uniform), np.asarray(to_screen, dtype=np.float32).reshape(4, 4),
                         face_cull=ctx.face_cull or 0, depth_test=ctx.depth_test or 0,
                         color_write=bool(ctx.color_write), depth_write=bool(ctx.depth_write),
-                        depth_sort=0 if ctx.depth_sort is None else int(ctx.depth_sort), mesh=mesh)
+                        depth_sort=0 if ctx.depth_sort is None else int(ctx.depth_sort), mesh=mesh,
+                        prim_kind=_ffi.PRIM_EDGES if edges else _ffi.PRIM_TRIS)
 
     def cached_struct(self, key, texture_handle, mesh_handle) -> RfDraw:
         """to_struct() memoised per device: the marshalling costs more than the rf_render call."""
@@ -221,6 +223,7 @@ class DrawCall:
         C.memmove(d.viewport, vp.ctypes.data, 64)
         d.face_cull, d.depth_test = self.face_cull, self.depth_test
         d.color_write, d.depth_write, d.depth_sort = int(self.color_write), int(self.depth_write), self.depth_sort
+        d.prim_kind = self.prim_kind
         return d
 
 

@@ -599,7 +599,7 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
     return fail(c, RF_E_UNSUPPORTED_SHADER, "fragment shader %u needs >= %u varying lanes, got %u", d->fs, fs_min_lanes(d->fs), d->n_attr_lanes);
   if ((d->vs == RF_VS_SOLIDS && d->n_attr_lanes < 3) || (d->vs == RF_VS_SPRITE && d->n_attr_lanes < 2))
     return fail(c, RF_E_UNSUPPORTED_SHADER, "vertex shader %u lanes", d->vs);
-  if (d->face_cull > RF_CULL_FRONT || d->depth_test > RF_DEPTH_GREATER) return fail(c, RF_E_INVALID, "bad Context flag");
+  if (d->face_cull > RF_CULL_FRONT || d->depth_test > RF_DEPTH_GREATER || d->prim_kind > RF_PRIM_EDGES) return fail(c, RF_E_INVALID, "bad Context flag or primitive kind");
   if (fs_needs_tex(d->fs)) {
     if (!d->texture) return fail(c, RF_E_INVALID, "fragment shader needs a texture");
     if (d->fs == RF_FS_TEX_REPEAT_POT) {
@@ -619,7 +619,7 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
   } else {
     if ((d->n_prims && !d->indices) || (d->n_verts && !d->verts)) return fail(c, RF_E_INVALID, "null geometry");
     if (d->vert_stride_f32 < 3 + d->n_attr_lanes) return fail(c, RF_E_INVALID, "vert_stride_f32 < 3 + n_attr_lanes");
-    const size_t vb = (size_t)d->n_verts * d->vert_stride_f32 * 4, ib = (size_t)d->n_prims * 12;
+    const size_t vb = (size_t)d->n_verts * d->vert_stride_f32 * 4, ib = (size_t)d->n_prims * (d->prim_kind == RF_PRIM_EDGES ? 8 : 12);
     // Page-locked caller memory (rf_host_alloc) is DMA'd to the device right here, on the copy-in stream, and the
     // call waits for it: the borrow ends at return, as in the reference, but without a staging memcpy. Pageable
     // memory is copied into pinned staging instead and uploaded with the pass.
@@ -659,6 +659,7 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
     D.vstride = d->vert_stride_f32; D.n_verts = d->n_verts; D.n_prims = d->n_prims;
   }
   D.L = d->n_attr_lanes; D.persp_mask = d->persp_mask; D.vs = d->vs; D.fs = d->fs;
+  D.prim_kind = d->prim_kind;
   D.flags = (uint32_t)d->face_cull | (uint32_t)d->depth_test << RF_F_DTEST_SHIFT | (d->color_write ? RF_F_CWRITE : 0u) | (d->depth_write ? RF_F_DWRITE : 0u);
   D.tex = d->texture ? d->texture->d_data : nullptr;
   D.tex_w = d->texture ? d->texture->w : 0; D.tex_h = d->texture ? d->texture->h : 0;

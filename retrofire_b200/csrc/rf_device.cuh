@@ -35,6 +35,7 @@ struct DrawDesc {
   const uint32_t* tex;      // RGBA8 texels (device copy is always 4 B/texel), row-major, pitch = tex_w
   uint32_t vstride, n_verts, n_prims;
   uint32_t L, persp_mask, vs, fs;
+  uint32_t prim_kind;       // RF_PRIM_TRIS / RF_PRIM_EDGES
   uint32_t target;          // index into the pass's TargetDesc table
   uint32_t flags;           // RF_F_*
   uint32_t tex_w, tex_h;
@@ -131,6 +132,7 @@ struct PassParams {
 };
 
 #define RF_NO_CKPT 0xFFFFFFFFu
+#define RF_STRI_LINE 0x80000000u  // flag in the draw word of a screen-triangle record: the record is an Edge (2 vertices)
 #define RF_NO_TILE 0xFFFFFFFFu
 
 // record strides in 32-bit words, as a function of the compile-time lane count LT

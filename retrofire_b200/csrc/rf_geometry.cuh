@@ -288,6 +288,80 @@ __device__ __forceinline__ void walk_half_inline(const PassParams& P, uint32_t t
   }
 }
 
+// raster::line (raster.rs:122-177): a one-pixel-thick line, every pixel carrying v0's position and varyings. The
+// pixels of one framebuffer row are consecutive, so the line is stored like a triangle: one span record per row
+// with zero dv/dx. PASS 0 measures (row range, bin entries), PASS 1 writes span records and bin entries.
+struct LineGeom {
+  bool wide;
+  float start, step;   // wide: y at the first pixel centre and dy/dx; tall: x at the first row centre and dx/dy
+  uint32_t ia, ib;     // wide: pixel columns [ia, ib); tall: rows [ia, ib)
+};
+struct LineMeasure {
+  uint32_t ymin, ymax, nent;
+  bool oob;
+};
+
+template <int LT, int PASS>
+__device__ __forceinline__ void line_walk(const PassParams& P, const TargetDesc& T, const LineGeom& G, LineMeasure& M, uint32_t lane,
+                                          uint32_t sbase, uint32_t ebase, uint32_t key, uint32_t tri_idx, const float* lanes /*z, attr*/,
+                                          unsigned long long& frags_i) {
+  constexpr int SW = Rec<LT>::SW;
+  float acc = G.start;
+  uint32_t run_y = 0xFFFFFFFFu, run_x0 = 0, run_n = 0;  // current row run
+  uint32_t trow = 0xFFFFFFFFu, cmin = 0xFFFFFFFFu, cmax = 0;
+  uint32_t eidx = ebase;
+  auto flush_tile_row = [&]() {
+    if (trow != 0xFFFFFFFFu && cmin <= cmax) {
+      if (PASS == 0) M.nent += cmax - cmin + 1;
+      else {
+        const uint32_t tbase = T.tile_base + trow * T.tiles_x;
+        for (uint32_t c = cmin; c <= cmax; c++) { P.entries[eidx++] = make_uint4(tbase + c, key, tri_idx, 0u); atomicAdd(P.tile_cnt + tbase + c, 1u); }
+      }
+    }
+    cmin = 0xFFFFFFFFu; cmax = 0;
+  };
+  auto flush_run = [&]() {
+    if (run_n == 0) return;
+    const bool in_band = run_y >= T.band_y0 && run_y < T.band_y1;
+    if (PASS == 0) { M.ymin = min(M.ymin, run_y); M.ymax = max(M.ymax, run_y); }
+    if (in_band) {
+      if ((run_y >> RF_TILE_SHIFT) != trow) { flush_tile_row(); trow = run_y >> RF_TILE_SHIFT; }
+      cmin = min(cmin, run_x0 >> RF_TILE_SHIFT);
+      cmax = max(cmax, (run_x0 + run_n - 1) >> RF_TILE_SHIFT);
+    }
+    if (PASS == 1) {
+      const uint32_t nn = in_band ? run_n : 0u;
+      if (in_band) frags_i += run_n;
+      const uint32_t sidx = sbase + (run_y - M.ymin);
+      uint32_t w[SW];
+      w[0] = run_x0 | nn << 16; w[1] = RF_NO_CKPT;
+#pragma unroll
+      for (int i = 0; i < 1 + LT; i++) w[2 + i] = __float_as_uint(lanes[i]);
+#pragma unroll
+      for (int i = 3 + LT; i < SW; i++) w[i] = 0u;
+      uint32_t* sr = P.spans + (size_t)sidx * SW;
+#pragma unroll
+      for (int q = 0; q < SW / 2; q++) *reinterpret_cast<uint2*>(sr + 2 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
+      if (nn && ((run_x0 + nn - 1) >> RF_TILE_SHIFT) != (run_x0 >> RF_TILE_SHIFT)) {
+        const unsigned long long slot = agg_atomic_inc(&P.status->long_needed, lane);
+        if (slot < P.cap_long) P.longlist[slot] = make_uint2(sidx, tri_idx * 2u);
+        else { P.status->overflow = 1; P.cstatus->poison = 1; }
+      }
+    }
+    run_n = 0;
+  };
+  for (uint32_t i = G.ia; i < G.ib; i++) {
+    const uint32_t py = G.wide ? sat_u32(acc) : i;
+    const uint32_t px = G.wide ? i : sat_u32(acc);
+    if (py >= T.h || px + 1 > T.w) { M.oob = true; break; }  // target.rs:148,173-174
+    if (py != run_y || px != run_x0 + run_n) { flush_run(); run_y = py; run_x0 = px; }
+    run_n++;
+    acc = acc + G.step;
+  }
+  flush_run();
+  flush_tile_row();
+}
+
 // Triangles with at most this many scanlines are walked inline by k_setup; taller ones go to k_walk in chunks.
 #define RF_INLINE_ROWS 12u
 
@@ -314,8 +388,41 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
     CVert<LT> c0, c1, c2;
     CVert<LT> poly[10], tmp[10];
     bool clipped = false;
+    bool is_edge = false;
     if (have) {
       d = find_draw(P.pbase, P.n_draws, gp);
+      const DrawDesc& D = P.draws[d];
+      is_edge = D.prim_kind == RF_PRIM_EDGES;
+    }
+    if (have && is_edge) {
+      // Render for Edge<usize> (prim.rs:41-60): inline two vertices, Clip for [Edge] (clip.rs:311-348)
+      const DrawDesc& D = P.draws[d];
+      const uint32_t* ip = D.indices + 2 * (size_t)(gp - __ldg(P.pbase + d));
+      const uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1);
+      if (i0 >= D.n_verts || i1 >= D.n_verts) {
+        atomicOr(&P.status->error, RF_ERRBIT_INDEX_OOB);
+      } else {
+        const uint32_t vb = __ldg(P.vbase + d);
+        load_cv<LT>(P.cv, vb + i0, c0);
+        load_cv<LT>(P.cv, vb + i1, c1);
+        if ((c0.oc & c1.oc) != 0) ntri = 0;       // both outside one plane
+        else if ((c0.oc | c1.oc) == 0) ntri = 1;  // neither outside
+        else {
+          ntri = 1;
+          for (int pl = 0; pl < 6; pl++) {
+            const uint32_t bit = 1u << pl;
+            const bool a_in = (c0.oc & bit) == 0, b_in = (c1.oc & bit) == 0;
+            if (!a_in && !b_in) { ntri = 0; break; }
+            CVert<LT> x;
+            if (clip_intersect<LT>(pl, c0, c1, x)) {
+              if (a_in) c1 = x;
+              else if (b_in) c0 = x;
+            }
+          }
+        }
+        c2 = c0;  // unused third vertex
+      }
+    } else if (have) {
       const DrawDesc& D = P.draws[d];
       const uint32_t* ip = D.indices + 3 * (size_t)(gp - __ldg(P.pbase + d));
       const uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
@@ -361,7 +468,7 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
         float wz = 0.0f;
         wz = wz + (-aby) * acx;
         wz = wz + abx * acy;
-        const bool back = wz < 0.0f;
+        const bool back = is_edge ? false : wz < 0.0f;  // Render::is_backface defaults to false for edges (render.rs:72-74)
         const uint32_t cull = D.flags & RF_F_CULL_MASK;
         emit = !((cull == RF_CULL_BACK && back) || (cull == RF_CULL_FRONT && !back));
         if (emit) my_prims_o++;  // render.rs:195-196: counted before rasterisation, whatever it covers
@@ -378,7 +485,7 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
       if (emit) {
         uint32_t* q = P.stris + (size_t)((uint32_t)base + __popc(emask & lt)) * QW;
         uint32_t w[QW];
-        w[0] = gp * 8u + t; w[1] = d;
+        w[0] = gp * 8u + t; w[1] = is_edge ? (d | RF_STRI_LINE) : d;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
           w[2 + k * (3 + LT)] = __float_as_uint(s[k].x); w[3 + k * (3 + LT)] = __float_as_uint(s[k].y); w[4 + k * (3 + LT)] = __float_as_uint(s[k].z);
@@ -436,6 +543,10 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
     unsigned long long my_frags_i = 0;
     uint32_t long_rows = 0, long_sbase = 0, long_tri = 0, long_nU = 0;  // inline-walked rows that cross a tile column
     uint32_t t_h = 0, t_w = 0, t_by0 = 0, t_by1 = 0;
+    bool is_line = false;
+    LineGeom LG{};
+    LineMeasure LM{};
+    float line_lanes[1 + LT];
     if (have) {
       const uint32_t* q = P.stris + (size_t)ti * QW;
       uint32_t w[QW];
@@ -444,8 +555,50 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
         const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(q) + qd);
         w[4 * qd] = t4.x; w[4 * qd + 1] = t4.y; w[4 * qd + 2] = t4.z; w[4 * qd + 3] = t4.w;
       }
-      key = w[0]; d = w[1];
+      key = w[0]; d = w[1] & ~RF_STRI_LINE;
+      is_line = (w[1] & RF_STRI_LINE) != 0;
       const DrawDesc& D = P.draws[d];
+      if (is_line) {
+        // raster::line (raster.rs:122-177)
+        int a = 0, b = 1;
+        if (__uint_as_float(w[3]) > __uint_as_float(w[3 + (3 + LT)])) { a = 1; b = 0; }
+        const float ax = __uint_as_float(w[2 + a * (3 + LT)]), ay = __uint_as_float(w[3 + a * (3 + LT)]);
+        const float bx = __uint_as_float(w[2 + b * (3 + LT)]), by_ = __uint_as_float(w[3 + b * (3 + LT)]);
+        const float dx = bx - ax, dy = by_ - ay;
+        LG.wide = fabsf(dx) > dy;
+        int v0i = a;
+        if (LG.wide) {
+          float v0x = ax, v0y = ay, v1x = bx;
+          if (dx < 0.0f) { v0i = b; v0x = bx; v0y = by_; v1x = ax; }  // draw left to right; dx, dy keep their old values
+          const float x0 = round_up_to_half(v0x), x1 = round_up_to_half(v1x);
+          LG.step = dy / dx;
+          LG.start = v0y + LG.step * (x0 - v0x);
+          LG.ia = sat_u32(x0); LG.ib = sat_u32(x1);
+        } else {
+          const float y0 = round_up_to_half(ay), y1 = round_up_to_half(by_);
+          LG.step = dx / dy;
+          LG.start = ax + LG.step * (y0 - ay);
+          LG.ia = sat_u32(y0); LG.ib = sat_u32(y1);
+        }
+        line_lanes[0] = __uint_as_float(w[4 + v0i * (3 + LT)]);
+#pragma unroll
+        for (int i = 0; i < LT; i++) line_lanes[1 + i] = __uint_as_float(w[5 + v0i * (3 + LT) + i]);
+        const TargetDesc& T = P.targets[D.target];
+        tgt = D.target; tiles_x = T.tiles_x;
+        if (LG.ib > LG.ia && LG.ib - LG.ia > RF_MAX_ROWS) { atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB); LG.ib = LG.ia; }
+        LM.ymin = 0xFFFFFFFFu; LM.ymax = 0; LM.nent = 0; LM.oob = false;
+        line_walk<LT, 0>(P, T, LG, LM, lane, 0u, 0u, key, 0u, line_lanes, my_frags_i);
+        if (LM.oob) { atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB); }
+        else if (LM.ymin <= LM.ymax) {
+          emit = true;
+          Y0 = LM.ymin;
+          H0.n = LM.ymax - LM.ymin + 1; H1.n = 0;
+          nent = LM.nent;
+#pragma unroll
+          for (int i = 0; i < NL; i++) { H0.dv[i] = 0.0f; H0.L[i] = 0.0f; H0.dl[i] = 0.0f; H1.dv[i] = 0.0f; H1.L[i] = 0.0f; H1.dl[i] = 0.0f; }
+          H0.R = H0.dr = H0.y = 0.0f; H1.R = H1.dr = H1.y = 0.0f;
+        }
+      } else {
       // tri_fill raster.rs:185-224: stable sort by y (total_cmp)
       int o0 = 0, o1 = 1, o2 = 2;
       {
@@ -517,6 +670,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
           if (emit && nrows > RF_INLINE_ROWS) nchunk = (H0.n + RF_CHUNK - 1) / RF_CHUNK + (H1.n + RF_CHUNK - 1) / RF_CHUNK;
         }
       }
+      }  // triangle
     }
     // ---- block-aggregated allocation: warp prefix sums, then ONE atomic per counter per block
     const uint32_t nsp = emit ? (H0.n + H1.n) : 0u;
@@ -551,8 +705,8 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
       const uint32_t tri_idx = (uint32_t)tb + __popc(emask & lt);
       uint32_t eidx = (uint32_t)eb + (incl_e - nent);
       uint32_t cidx = (uint32_t)cb_ + (incl_c - nchunk);
-      const bool inline_walk = H0.n + H1.n <= RF_INLINE_ROWS;
-      const uint32_t ch0 = inline_walk ? 0u : (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = inline_walk ? 0u : (H1.n + RF_CHUNK - 1) / RF_CHUNK;
+      const bool inline_walk = !is_line && H0.n + H1.n <= RF_INLINE_ROWS;
+      const uint32_t ch0 = (inline_walk || is_line) ? 0u : (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = (inline_walk || is_line) ? 0u : (H1.n + RF_CHUNK - 1) / RF_CHUNK;
       const uint32_t eck0 = cidx, eck1 = cidx + ch0;  // edge checkpoints are indexed by chunk position
       {  // triangle record
         uint32_t* tr = P.tris + (size_t)tri_idx * TW;
@@ -573,8 +727,14 @@ __global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
           for (int q = 0; q < HS / 4; q++) *reinterpret_cast<uint4*>(tr + 8 + hh * HS + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
         }
       }
+      if (is_line) {  // spans (one run per row, rows without pixels in band keep n = 0) and exact bin entries
+        const TargetDesc& T = P.targets[tgt];
+        constexpr int SW_ = Rec<LT>::SW;
+        for (uint32_t r = 0; r < H0.n; r++) *reinterpret_cast<uint2*>(P.spans + (size_t)(sbase + r) * SW_) = make_uint2(0u, RF_NO_CKPT);
+        line_walk<LT, 1>(P, T, LG, LM, lane, sbase, eidx, key, tri_idx, line_lanes, my_frags_i);
+      }
       // bin entries: every tile of the conservative per-tile-row column range
-      if (nent) {
+      if (nent && !is_line) {
         const TargetDesc& T = P.targets[tgt];
         for (uint32_t tr = tr0; tr <= tr1; tr++) {
           uint32_t ca, cb;

@@ -380,3 +380,48 @@ def random_soup(n: int, w: int, h: int, seed: int, *, lanes_kind: str = "color3"
     mvp = mx.perspective(1.0, f32(w) / f32(h), 0.5, 50.0)
     vp = mx.viewport((0, h), (w, 0))
     return Scene(f"soup_{lanes_kind}_{n}_{seed}", w, h, _ffi.FMT_RGBA8888, True, ctx, [DrawCall.make(tris, verts, shd, mvp, vp, ctx)])
+
+
+# ---- Edge primitives (render/prim.rs:41-60, raster.rs:122-177): wireframes ---------------------------------------------
+def mesh_edges(faces: np.ndarray) -> np.ndarray:
+    """Unique undirected edges of a triangle mesh, as (n,2) uint32 (what render/debug.rs draws as a wireframe)."""
+    e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]]).astype(np.int64)
+    e = np.unique(np.sort(e, axis=1), axis=0)
+    return e.astype(np.uint32)
+
+
+def bunny_wireframe(subdiv: int = 0, theta: float = 1.0, w: int = 1920, h: int = 1080) -> Scene:
+    verts, faces = bunny_mesh(subdiv)
+    ctx = Context(color_clear=(0x33, 0x33, 0x33, 0xFF))
+    vp = mx.viewport((10, h - 10), (w - 10, 10))
+    shd = shader.new(_ffi.VS_SOLIDS, _ffi.FS_COLOR3F)
+    call = DrawCall.make(mesh_edges(faces), verts, shd, solids_uniform(theta, w, h), vp, ctx, edges=True)
+    return Scene(f"bunny_wire_x{4 ** subdiv}", w, h, _ffi.FMT_XRGB8888, True, ctx, [call])
+
+
+def random_lines(n: int, w: int, h: int, seed: int, ctx: Context = None, lanes_kind: str = "color3") -> Scene:
+    """Random line segments, many crossing the frustum planes; all slopes, including axis-aligned and degenerate ones."""
+    g = np.random.default_rng(seed)
+    ctx = ctx or Context()
+    z = g.uniform(-0.5, 30, (n, 1)).astype(f32)
+    c = g.uniform(-1.5, 1.5, (n, 1, 2)).astype(f32) * np.maximum(np.abs(z), 0.5)[:, :, None]
+    rad = g.uniform(0.0, 1.2, (n, 1, 1)).astype(f32) * np.maximum(np.abs(z), 0.5)[:, :, None]
+    xy = c + rad * g.uniform(-1, 1, (n, 2, 2)).astype(f32)
+    k = n // 10
+    xy[:k, 1, 1] = xy[:k, 0, 1]            # horizontal
+    xy[k:2 * k, 1, 0] = xy[k:2 * k, 0, 0]  # vertical
+    xy[2 * k:2 * k + 5, 1] = xy[2 * k:2 * k + 5, 0]  # zero length
+    zz = z[:, :, None] + g.uniform(-1, 1, (n, 2, 1)).astype(f32) * 2.0
+    pos = np.concatenate([xy, zz], 2).astype(f32)
+    if lanes_kind == "color3":
+        attr = g.uniform(0, 1, (n, 2, 3)).astype(f32)
+        shd = shader.new(_ffi.VS_MVP, _ffi.FS_COLOR3F)
+    else:
+        attr = g.uniform(-0.5, 1.5, (n, 2, 2)).astype(f32)
+        tex = g.integers(0, 256, (16, 16, 3), dtype=np.uint8)
+        shd = shader.new(_ffi.VS_MVP, _ffi.FS_TEX_REPEAT_POT, texture=Texture(tex))
+    verts = np.concatenate([pos, attr], 2).reshape(2 * n, -1).astype(f32)
+    edges = np.arange(2 * n, dtype=np.uint32).reshape(n, 2)
+    mvp = mx.perspective(1.0, f32(w) / f32(h), 0.5, 50.0)
+    vp = mx.viewport((0, h), (w, 0))
+    return Scene(f"lines_{lanes_kind}_{n}_{seed}", w, h, _ffi.FMT_RGBA8888, True, ctx, [DrawCall.make(edges, verts, shd, mvp, vp, ctx, edges=True)])

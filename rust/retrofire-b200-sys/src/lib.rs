@@ -47,7 +47,8 @@ pub struct rf_draw {
     pub color_write: u8,
     pub depth_write: u8,
     pub depth_sort: u8,
-    pub _pad: [u8; 3],
+    pub prim_kind: u8,
+    pub _pad: [u8; 2],
 }
 
 #[repr(C)]

@@ -182,6 +182,27 @@ def test_nan_and_inf_vertices_behave_like_the_reference(device, oracle):
     assert_parity(run_gpu(device, sc), want, name="nan-inf")
 
 
+@pytest.mark.parametrize("kind", ["color3", "uv"])
+def test_line_primitives(device, oracle, kind):
+    """Edge<usize> primitives (SURVEY 8f-2): Render for Edge, Clip for [Edge], raster::line — all slopes, clipped
+    against every frustum plane, axis-aligned and zero-length segments."""
+    for seed in (1, 2):
+        check(device, oracle, scenes.random_lines(3000, 640, 360, seed=seed, lanes_kind=kind))
+
+
+def test_wireframe_over_solid_and_front_cull(device, oracle):
+    """A wireframe pass over the solid mesh in one frame (lines + triangles, depth tested), and FaceCull::Front,
+    which culls every edge because Render::is_backface defaults to false (render.rs:72-74, ctx.rs:95-101)."""
+    solid = scenes.bunny(subdiv=0, w=960, h=540)
+    wire = scenes.bunny_wireframe(subdiv=0, w=960, h=540)
+    solid.draws = solid.draws + wire.draws
+    check(device, oracle, solid)
+    culled = scenes.random_lines(500, 320, 240, seed=3, ctx=rf.Context(face_cull=rf.FaceCull.Front))
+    got = run_gpu(device, culled)
+    assert got[2].prims.o == 0 and got[2].frags.i == 0
+    assert_parity(got, run_oracle(oracle, culled), name="front-cull-lines")
+
+
 def test_odd_sized_target(device, oracle):
     """Width/height not multiples of the tile or of 4 (scalar tile I/O path)."""
     sc = scenes.random_soup(500, 333, 211, seed=5, lanes_kind="color3", big=True)

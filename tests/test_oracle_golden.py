@@ -200,3 +200,30 @@ def test_pixfmt_kats(oracle):
     assert lib.rfo_pack_pixel(rf.FMT_RGBA4444, col) == 0x1234
     col = (C.c_uint8 * 4)(0x40, 0x20, 0x10, 0xFF)
     assert lib.rfo_pack_pixel(rf.FMT_RGB565, col) == 0b01000_001000_00010
+
+
+def test_line_primitives_restatement_sanity(oracle):
+    """raster::line (render/raster.rs:122-177) has no reference test: sanity of the restatement on axis-aligned and
+    diagonal lines drawn through the full edge path (Render for Edge, prim.rs:41-60). Pinned by restatement only."""
+    from retrofire_b200 import mathx as mx
+    w, h = 32, 24
+    ident = mx.identity()
+    vp = mx.viewport((0, 0), (w, h))            # NDC (-1,-1) -> (0,0), (1,1) -> (w,h)
+
+    def draw(p0, p1):
+        verts = np.array([[p0[0], p0[1], 0, 1, 0, 0], [p1[0], p1[1], 0, 0, 1, 0]], dtype=np.float32)
+        call = rf.DrawCall.make([[0, 1]], verts, rf.shader.new(rf.VS_MVP, rf.FS_COLOR3F), ident, vp, rf.Context(), edges=True)
+        tgt = oracle.HostTarget(w, h, rf.FMT_RGBA8888, True)
+        st = oracle.render(call, tgt)
+        return (tgt.color != 0), st
+
+    to_ndc = lambda x, y: (2 * x / w - 1, 2 * y / h - 1)
+    cov, st = draw(to_ndc(4.0, 10.2), to_ndc(20.0, 10.2))     # horizontal: pixel centres 4.5 .. 19.5 on row 10
+    assert st.prims.o == 1 and st.verts.o == 3 and st.frags.i == st.frags.o == 16
+    assert cov[10, 4:20].all() and cov.sum() == 16
+    cov, st = draw(to_ndc(7.3, 2.0), to_ndc(7.3, 12.0))       # vertical: rows 2 .. 11 in column 7
+    assert cov[2:12, 7].all() and cov.sum() == 10
+    cov, st = draw(to_ndc(2.0, 2.0), to_ndc(12.0, 12.0))      # diagonal: dx.abs() > dy is false -> tall branch, one pixel per row
+    assert cov.sum() == 10 and all(cov[y].sum() == 1 for y in range(2, 12))
+    cov, st = draw(to_ndc(5.0, 5.0), to_ndc(5.0, 5.0))        # zero length: nothing
+    assert cov.sum() == 0 and st.prims.o == 1
