@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--sharding", default="frames", choices=["frames", "tiles"],
                     help="frames: every rank renders its own frame batch (weak scaling); tiles: sort-first row bands of ONE large frame "
                          "per step + NCCL all_gather of the finished bands (strong scaling, SURVEY 8e)")
-    ap.add_argument("--frames", type=int, default=32, help="frames per step (frame batch)")
+    ap.add_argument("--frames", type=int, default=128,
+                    help="frames per step (frame batch); BASELINE config 5(ii) is a 1,024-frame batch over 8 GPUs = 128 per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and cpu_baseline legs (for ncu runs)")
     return ap.parse_args()
