@@ -52,7 +52,7 @@ typedef enum rf_status {
   RF_E_CUDA = 6,
   RF_E_NCCL = 7,
   RF_E_NOMEM = 8,
-  RF_E_UNSUPPORTED = 9         /* a Context option outside the path (depth_sort)              */
+  RF_E_UNSUPPORTED = 9         /* an option outside the path (e.g. async download of a non-32-bit format) */
 } rf_status;
 
 /* Vertex-shader catalogue. Input vertex = [x,y,z,a0..]; output = clip pos
@@ -99,6 +99,7 @@ typedef enum rf_texel_fmt {
 } rf_texel_fmt;
 
 enum { RF_PRIM_TRIS = 0, RF_PRIM_EDGES = 1 };
+enum { RF_SORT_NONE = 0, RF_SORT_FRONT_TO_BACK = 1, RF_SORT_BACK_TO_FRONT = 2 }; /* ctx.rs:39,67-72 */
 enum { RF_CULL_NONE = 0, RF_CULL_BACK = 1, RF_CULL_FRONT = 2 };                /* ctx.rs:74-78 */
 enum { RF_DEPTH_NONE = 0, RF_DEPTH_LESS = 1, RF_DEPTH_EQUAL = 2, RF_DEPTH_GREATER = 3 }; /* ctx.rs:42-48,86-89 */
 
@@ -126,7 +127,8 @@ typedef struct rf_draw {
   uint8_t depth_test;       /* RF_DEPTH_*   default LESS                                      */
   uint8_t color_write;      /* default 1                                                      */
   uint8_t depth_write;      /* default 1                                                      */
-  uint8_t depth_sort;       /* 0 = None (default). Non-zero -> RF_E_UNSUPPORTED */
+  uint8_t depth_sort;       /* RF_SORT_*    default NONE. Equal depths keep primitive order (the reference's
+                               sort_unstable_by leaves their order unspecified)  render.rs:180-182,209-219 */
   uint8_t prim_kind;        /* RF_PRIM_TRIS: 3 indices per primitive (Tri<usize>); RF_PRIM_EDGES: 2 indices per
                                primitive (Edge<usize>: render/prim.rs:41-60, clip.rs:311-348, raster.rs:122-177) */
   uint8_t _pad[2];

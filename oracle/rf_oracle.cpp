@@ -470,7 +470,7 @@ int rfo_render(const rf_draw* dp, const rfo_texture* texp, rfo_target* tp, rf_st
   const rf_draw& d = *dp;
   const int L = (int)d.n_attr_lanes;
   if (L > MAXL || d.vert_stride_f32 < 3u + (uint32_t)L) return RF_E_INVALID;
-  if (d.depth_sort) return RF_E_UNSUPPORTED;
+  if (d.depth_sort > RF_SORT_BACK_TO_FRONT) return RF_E_INVALID;
   Tex tex{};
   if (texp) tex = Tex{texp->w, texp->h, texp->fmt, texp->data, (size_t)texp->stride};
   const bool needs_tex = d.fs == RF_FS_TEX_CLAMP_LIT || d.fs == RF_FS_TEX_CLAMP || d.fs == RF_FS_TEX_REPEAT_POT;
@@ -559,6 +559,20 @@ int rfo_render(const rf_draw* dp, const rfo_texture* texp, rfo_target* tp, rf_st
     if (any == 0) { clipped.push_back(t); continue; }  // Visible
     clip_tri(t.v, L, vin, vout);
     for (size_t k = 1; k + 1 < vout.size(); k++) clipped.push_back(CTri{{vout[0], vout[k], vout[k + 1]}});
+  }
+
+  // Optional depth sort   render.rs:180-182, 209-219; Render::depth prim.rs:21-23.
+  // The reference's sort_unstable_by leaves the order of equal depths unspecified; this restatement
+  // (and the CUDA path) keep equal depths in primitive order. Edges all have depth +inf
+  // (render.rs:68-70), i.e. they keep their order, so the edge branch above has nothing to sort.
+  if (d.depth_sort) {
+    auto total_key = [](float f) { int32_t b; std::memcpy(&b, &f, 4); return b ^ (int32_t)(((uint32_t)(b >> 31)) >> 1); };  // f32::total_cmp
+    auto depth = [](const CTri& t) { return ((t.v[0].pos[2] + t.v[1].pos[2]) + t.v[2].pos[2]) / 3.0f; };
+    const bool f2b = d.depth_sort == RF_SORT_FRONT_TO_BACK;
+    std::stable_sort(clipped.begin(), clipped.end(), [&](const CTri& t, const CTri& u) {
+      const int32_t z = total_key(depth(t)), w = total_key(depth(u));
+      return f2b ? z < w : w < z;
+    });
   }
 
   // 4. per primitive: to_screen, cull, rasterise     render.rs:185-205

@@ -7,7 +7,7 @@ without a GPU raises.
 """
 from . import _ffi, mathx, scenes  # noqa: F401
 from ._ffi import *  # noqa: F401,F403  (enum constants)
-from .api import (Batch, Context, Device, DrawCall, FaceCull, Framebuf, Mesh, Ordering, RetrofireError, Shader, Stats,  # noqa: F401
+from .api import (Batch, Context, DepthSort, Device, DrawCall, FaceCull, Framebuf, Mesh, Ordering, RetrofireError, Shader, Stats,  # noqa: F401
                   Texture, Throughput, render, shader)
 
 __version__ = "0.1.0"

@@ -84,6 +84,11 @@ class FaceCull:
     Back = _ffi.CULL_BACK
 
 
+class DepthSort:  # render/ctx.rs:67-72
+    FrontToBack = 1
+    BackToFront = 2
+
+
 class Ordering:  # core::cmp::Ordering as used by Context.depth_test
     Less = _ffi.DEPTH_LESS
     Equal = _ffi.DEPTH_EQUAL

@@ -3,6 +3,7 @@
 // A "pass" is every draw queued between two flush points, executed in submission order by
 // one chain of kernels:
 //   [k_clear_multi] -> k_vertex -> k_assemble -> k_setup -> k_edge_ckpt -> k_walk -> k_bin_alloc -> k_bin_scatter -> k_ckpt -> k_bin_sort_* -> k_raster
+//   (+ the depth-sort ordering step of rf_order.cuh between k_assemble and k_setup for passes with Context::depth_sort)
 // Passes are launched asynchronously on the ctx stream and validated lazily (capacity overflow
 // or device-detected errors) at the next synchronisation point; an overflowing pass poisons
 // the ctx on the device so that later passes become no-ops until the host has grown the
@@ -22,6 +23,9 @@
 #include "rf_device.cuh"
 #include "rf_geometry.cuh"
 #include "rf_raster.cuh"
+#include "rf_order.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
 
 namespace {
 
@@ -94,6 +98,7 @@ struct PassSlot {
   int profiled = 0;
   uint32_t NV = 0, NP = 0, n_tiles = 0, lt = 0;
   uint32_t n_launches = 0;
+  uint32_t order_upper = 0;  // > 0: the pass holds a depth-sorted draw; bound on its screen triangles (rf_order.cuh)
 };
 
 }  // namespace
@@ -141,6 +146,7 @@ struct rf_ctx {
   // entries and long spans in records
   size_t capw_stris = 0, capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
   CtxStatus* d_cstatus = nullptr;
+  DevBuf sdepth, ord_k32[2], ord_v[2], ord_k64[2], ord_tmp;  // Context::depth_sort (rf_order.cuh), allocated on first use
   DevBuf bounce;               // upload/download staging on the device
   PinnedBuf h_bounce;
 
@@ -229,6 +235,25 @@ uint32_t pack_pixel_host(uint32_t fmt, const uint8_t c[4]) {
 }
 
 // ---- pass launch ----------------------------------------------------------------------------------
+// Context::depth_sort: replace the submission keys of the pass by ranks (rf_order.cuh). Runs between k_assemble and k_setup.
+void launch_order(rf_ctx* c, PassSlot& s, const PassParams& P, uint32_t QW, cudaStream_t st) {
+  const uint32_t n = s.order_upper;
+  const unsigned g = (unsigned)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 8));
+  uint32_t* k32[2] = {static_cast<uint32_t*>(c->ord_k32[0].p), static_cast<uint32_t*>(c->ord_k32[1].p)};
+  uint32_t* v[2] = {static_cast<uint32_t*>(c->ord_v[0].p), static_cast<uint32_t*>(c->ord_v[1].p)};
+  unsigned long long* k64[2] = {static_cast<unsigned long long*>(c->ord_k64[0].p), static_cast<unsigned long long*>(c->ord_k64[1].p)};
+  size_t tmp = c->ord_tmp.cap;
+  k_order_init<<<g, 256, 0, st>>>(P, QW, n, k32[0], v[0]);
+  cub::DeviceRadixSort::SortPairs(c->ord_tmp.p, tmp, k32[0], k32[1], v[0], v[1], (int)n, 0, 32, st);
+  k_order_keys<<<g, 256, 0, st>>>(P, QW, n, v[1], k64[0]);
+  int dbits = 1;
+  while ((1ull << dbits) <= P.n_draws) dbits++;  // the padding key (all ones) stays above every draw index
+  tmp = c->ord_tmp.cap;
+  cub::DeviceRadixSort::SortPairs(c->ord_tmp.p, tmp, k64[0], k64[1], v[1], v[0], (int)n, 0, 32 + dbits, st);
+  k_order_apply<<<g, 256, 0, st>>>(P, QW, n, v[0]);
+  s.n_launches += 3;  // plus CUB's own kernels
+}
+
 template <int LT>
 void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   const int sm = c->sm_count;
@@ -242,6 +267,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     auto mark = [&]() { cudaEventRecord(s.ev_k[ek++], st); };
     mark(); k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
     mark(); k_assemble<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+    if (s.order_upper) launch_order(c, s, P, Rec<LT>::QW, st);  // counted with k_assemble
     mark(); k_setup<LT><<<sm * 8, 128, 0, st>>>(P);
     mark(); k_edge_ckpt<LT><<<sm * 4, 128, 0, st>>>(P);
     mark(); k_walk<LT><<<sm * 12, 128, 0, st>>>(P);
@@ -257,6 +283,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     cudaStream_t sd = c->side;
     k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
     k_assemble<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+    if (s.order_upper) launch_order(c, s, P, Rec<LT>::QW, st);
     k_setup<LT><<<sm * 8, 128, 0, st>>>(P);
     cudaEventRecord(s.ev_fork, st);
     cudaStreamWaitEvent(sd, s.ev_fork, 0);
@@ -342,7 +369,30 @@ rf_status launch_pass(rf_ctx* c, int si) {
                   std::max<size_t>(c->cap_chunks, (size_t)1 << 20), std::max<size_t>(c->cap_tall, (size_t)1 << 18)};
   need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 24 + 64 ||
               !arenas_cover(c, want) || c->cursors.cap < 64;
+  // Context::depth_sort: bound on the pass's screen triangles (a clipped triangle fans into <= 7) and the sort buffers
+  uint64_t order_bound = 0;
+  bool any_sort = false;
+  for (auto& q : s.draws) {
+    order_bound += (uint64_t)q.desc.n_prims * (q.desc.prim_kind == RF_PRIM_EDGES ? 1 : 7);
+    any_sort = any_sort || ((q.desc.flags >> RF_F_DSORT_SHIFT) & RF_F_DSORT_MASK) != 0;
+  }
+  const size_t cap_stris_el = std::min<size_t>(std::max(want.w_stris, c->capw_stris) / words_stri(lt), 0x1FFFFFF0u);
+  const uint32_t order_upper = any_sort ? (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(order_bound, cap_stris_el)) : 0u;
+  size_t order_tmp = 0;
+  if (order_upper) {
+    size_t t32 = 0, t64 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t32, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)order_upper, 0, 32);
+    cub::DeviceRadixSort::SortPairs(nullptr, t64, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)order_upper, 0, 64);
+    order_tmp = std::max(t32, t64) + 256;
+    need_idle = need_idle || c->sdepth.cap < cap_stris_el * 4 || c->ord_k32[0].cap < (size_t)order_upper * 4 || c->ord_tmp.cap < order_tmp;
+  }
+  s.order_upper = order_upper;
   if (need_idle) { rf_status st = wait_idle(c); if (st) return st; }
+  if (order_upper) {
+    bool ok = c->sdepth.reserve(cap_stris_el * 4) && c->ord_tmp.reserve(order_tmp);
+    for (int k = 0; k < 2; k++) ok = ok && c->ord_k32[k].reserve((size_t)order_upper * 4) && c->ord_v[k].reserve((size_t)order_upper * 4) && c->ord_k64[k].reserve((size_t)order_upper * 8);
+    if (!ok) return fail(c, RF_E_NOMEM, "depth-sort buffers");
+  }
   if (!s.d_table.reserve(table_bytes) || !s.d_geom.reserve(std::max<size_t>(s.geom_len, 16)) ||
       !s.d_dstats.reserve(std::max<size_t>(nd * sizeof(DrawStats), 16)) || !s.d_status.reserve(sizeof(PassStatus)) ||
       !s.h_dstats.reserve(std::max<size_t>(nd * sizeof(DrawStats), 16)))
@@ -439,6 +489,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.cv = static_cast<float*>(c->cv.p);
   P.stris = static_cast<uint32_t*>(c->stris.p);
   P.cap_stris = (uint32_t)std::min<size_t>(c->capw_stris / words_stri(lt), 0x1FFFFFF0u);
+  P.sdepth = s.order_upper ? static_cast<uint32_t*>(c->sdepth.p) : nullptr;
   P.spans = static_cast<uint32_t*>(c->spans.p);
   P.tris = static_cast<uint32_t*>(c->tris.p);
   P.entries = static_cast<uint4*>(c->entries.p);
@@ -593,7 +644,7 @@ uint32_t fs_min_lanes(uint32_t fs) {
 rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float* vs_uniform_override) {
   if (!c || !target || !d) return fail(c, RF_E_INVALID, "null argument");
   if (target->ctx != c) return fail(c, RF_E_INVALID, "target belongs to another ctx");
-  if (d->depth_sort) return fail(c, RF_E_UNSUPPORTED, "Context::depth_sort is outside the hot path (SURVEY 8f-3)");
+  if (d->depth_sort > RF_SORT_BACK_TO_FRONT) return fail(c, RF_E_INVALID, "bad depth_sort");
   if (d->vs > RF_VS_SPRITE || d->fs > RF_FS_NORMAL_VIS) return fail(c, RF_E_UNSUPPORTED_SHADER, "shader id not in the catalogue");
   if (d->n_attr_lanes > RF_MAX_ATTR_LANES || d->n_attr_lanes < fs_min_lanes(d->fs))
     return fail(c, RF_E_UNSUPPORTED_SHADER, "fragment shader %u needs >= %u varying lanes, got %u", d->fs, fs_min_lanes(d->fs), d->n_attr_lanes);
@@ -660,7 +711,8 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
   }
   D.L = d->n_attr_lanes; D.persp_mask = d->persp_mask; D.vs = d->vs; D.fs = d->fs;
   D.prim_kind = d->prim_kind;
-  D.flags = (uint32_t)d->face_cull | (uint32_t)d->depth_test << RF_F_DTEST_SHIFT | (d->color_write ? RF_F_CWRITE : 0u) | (d->depth_write ? RF_F_DWRITE : 0u);
+  D.flags = (uint32_t)d->face_cull | (uint32_t)d->depth_test << RF_F_DTEST_SHIFT | (d->color_write ? RF_F_CWRITE : 0u) | (d->depth_write ? RF_F_DWRITE : 0u) |
+            (uint32_t)d->depth_sort << RF_F_DSORT_SHIFT;
   D.tex = d->texture ? d->texture->d_data : nullptr;
   D.tex_w = d->texture ? d->texture->w : 0; D.tex_h = d->texture ? d->texture->h : 0;
   std::memcpy(D.vs_u, vs_uniform_override ? vs_uniform_override : d->vs_uniform, sizeof D.vs_u);
@@ -740,6 +792,8 @@ void rf_ctx_destroy(rf_ctx* c) {
   }
   c->cv.release(); c->stris.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->bins2.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
+  c->sdepth.release(); c->ord_tmp.release();
+  for (int k = 0; k < 2; k++) { c->ord_k32[k].release(); c->ord_v[k].release(); c->ord_k64[k].release(); }
   if (c->d_cstatus) cudaFree(c->d_cstatus);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }

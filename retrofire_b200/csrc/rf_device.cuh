@@ -21,6 +21,10 @@
 #define RF_F_DTEST_MASK 0x3u
 #define RF_F_CWRITE 0x10u
 #define RF_F_DWRITE 0x20u
+#define RF_F_DSORT_SHIFT 6   // Context::depth_sort (ctx.rs:39): RF_SORT_*
+#define RF_F_DSORT_MASK 0x3u
+#define RF_SORT_FRONT_TO_BACK 1u
+#define RF_SORT_BACK_TO_FRONT 2u
 
 // device error bits (PassStatus::error)
 #define RF_ERRBIT_INDEX_OOB 0x1u
@@ -107,6 +111,7 @@ struct PassParams {
   float* cv;              // clip verts [NV][CVS]
   uint32_t* stris;        // [cap_stris][QW]   compacted screen triangles (k_assemble -> k_setup)
   uint32_t cap_stris;
+  uint32_t* sdepth;       // [cap_stris] total-order bits of Render::depth, or null when no draw of the pass is depth-sorted
   uint32_t* spans;        // [cap_spans][SW]   one per scanline, contiguous per triangle
   uint32_t* tris;         // [cap_tris][TW]    per drawn triangle: key, draw, rows, dv/dx of both halves
   uint4* entries;         // [cap_entries]     {tile, key, tri, 0}: one per (triangle, overlapped tile)

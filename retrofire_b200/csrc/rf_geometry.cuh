@@ -450,6 +450,7 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
     uint32_t my_prims_o = 0;
     for (uint32_t t = 0; t < max_tri; t++) {
       bool emit = false;
+      float depth = 0.0f;
       SVert<LT> s[3];
       if (t < ntri) {
         const DrawDesc& D = P.draws[d];
@@ -472,6 +473,12 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
         const uint32_t cull = D.flags & RF_F_CULL_MASK;
         emit = !((cull == RF_CULL_BACK && back) || (cull == RF_CULL_FRONT && !back));
         if (emit) my_prims_o++;  // render.rs:195-196: counted before rasterisation, whatever it covers
+        if (emit && P.sdepth != nullptr) {
+          // Render::depth: prim.rs:21-23 for triangles (clip-space z, left to right, then / 3.0); f32::INFINITY for edges
+          if (is_edge) depth = __int_as_float(0x7F800000);
+          else if (clipped) depth = ((poly[0].p[2] + poly[t + 1].p[2]) + poly[t + 2].p[2]) / 3.0f;
+          else depth = ((c0.p[2] + c1.p[2]) + c2.p[2]) / 3.0f;
+        }
       }
       const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
       if (emask == 0) continue;
@@ -484,6 +491,7 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
       }
       if (emit) {
         uint32_t* q = P.stris + (size_t)((uint32_t)base + __popc(emask & lt)) * QW;
+        if (P.sdepth != nullptr) P.sdepth[(uint32_t)base + __popc(emask & lt)] = (uint32_t)total_key(depth) ^ 0x80000000u;  // unsigned order == total_cmp
         uint32_t w[QW];
         w[0] = gp * 8u + t; w[1] = is_edge ? (d | RF_STRI_LINE) : d;
 #pragma unroll

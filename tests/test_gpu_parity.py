@@ -74,18 +74,67 @@ def test_non_pot_texture_with_repeat_sampler_is_an_error(device):
 
 
 def test_unsupported_options_are_reported(device):
-    """depth_sort is outside the path; a fragment shader with too few lanes is rejected."""
+    """An out-of-range depth_sort is invalid; a fragment shader with too few lanes is rejected."""
     sc = scenes.hello_tri()
     d = sc.draws[0]
     fb = device.framebuf(sc.w, sc.h, sc.fmt, False)
     import dataclasses
     with pytest.raises(rf.RetrofireError) as e:
-        device.render(dataclasses.replace(d, depth_sort=1), fb, want_stats=True)
-    assert e.value.status == rf.RF_E_UNSUPPORTED
+        device.render(dataclasses.replace(d, depth_sort=3), fb, want_stats=True)
+    assert e.value.status == rf.RF_E_INVALID
     bad = dataclasses.replace(d, shader=rf.shader.new(rf.VS_MVP, rf.FS_TEX_CLAMP_LIT, lanes=3, persp_mask=0))
     with pytest.raises(rf.RetrofireError) as e:
         device.render(bad, fb, want_stats=True)
     assert e.value.status in (rf.RF_E_UNSUPPORTED_SHADER, rf.RF_E_INVALID)
+
+
+@pytest.mark.parametrize("order", [rf.DepthSort.BackToFront, rf.DepthSort.FrontToBack])
+@pytest.mark.parametrize("dtest", [None, rf.Ordering.Less])
+def test_depth_sort(device, oracle, order, dtest):
+    """Context::depth_sort (SURVEY 8f-3; render.rs:180-182, 209-219): clipped primitives sorted by Render::depth before
+    rasterisation. Without a depth test (painter's algorithm) every overlap depends on the order; triangles crossing
+    the frustum planes are sorted by the depth of their clipped fan pieces."""
+    ctx = rf.Context(depth_sort=order, depth_test=dtest, face_cull=None)
+    for big in (False, True):
+        sc = scenes.random_soup(3000 if not big else 400, 640, 360, seed=31, lanes_kind="color3", big=big, ctx=ctx)
+        check(device, oracle, sc)
+        if dtest is None:   # the order matters in this scene: the unsorted submission paints something else
+            import dataclasses
+            plain = dataclasses.replace(sc, draws=[dataclasses.replace(sc.draws[0], depth_sort=0)])
+            assert (run_gpu(device, plain)[0] != run_gpu(device, sc)[0]).any()
+
+
+def test_depth_sort_mixed_pass_and_ties(device, oracle):
+    """One pass holding a back-to-front draw, an unsorted draw, a line draw (edges all have depth +inf and keep their
+    order) and a front-to-back draw, no depth test; then a stack of coplanar overlapping quads whose triangles all
+    have EQUAL depth: ties keep primitive order (the reference's sort_unstable_by leaves them unspecified)."""
+    import dataclasses
+    nod = dict(depth_test=None, face_cull=None)
+    a = scenes.random_soup(700, 512, 384, seed=41, lanes_kind="lit", big=True, ctx=rf.Context(depth_sort=rf.DepthSort.BackToFront, **nod))
+    b = scenes.random_soup(700, 512, 384, seed=42, lanes_kind="color3", big=True, ctx=rf.Context(**nod))
+    l = scenes.random_lines(600, 512, 384, seed=43, ctx=rf.Context(depth_sort=rf.DepthSort.BackToFront, **nod))
+    c = scenes.random_soup(700, 512, 384, seed=44, lanes_kind="disc", big=True, ctx=rf.Context(depth_sort=rf.DepthSort.FrontToBack, **nod))
+    a.draws += b.draws + l.draws + c.draws
+    a.name = "depth-sort-mixed"
+    want = run_oracle(oracle, a)
+    assert_parity(run_gpu(device, a), want, name="mixed-queued")
+    assert_parity(run_gpu(device, a, per_draw_sync=True), want, name="mixed-sync")
+
+    g = np.random.default_rng(9)
+    n = 200
+    quads, prims = [], []
+    for k in range(n):
+        cx, cy, r = g.uniform(-0.6, 0.6), g.uniform(-0.6, 0.6), g.uniform(0.1, 0.4)
+        col = g.uniform(0, 1, 3)
+        for dx, dy in ((-r, -r), (r, -r), (r, r), (-r, r)):
+            quads.append([cx + dx, cy + dy, 0.25, *col])
+        prims += [[4 * k, 4 * k + 1, 4 * k + 2], [4 * k, 4 * k + 2, 4 * k + 3]]
+    from retrofire_b200 import mathx as mx
+    for order in (rf.DepthSort.BackToFront, rf.DepthSort.FrontToBack):
+        ctx = rf.Context(depth_sort=order, **nod)
+        call = rf.DrawCall.make(np.array(prims, np.uint32), np.array(quads, np.float32), rf.shader.new(rf.VS_MVP, rf.FS_COLOR3F),
+                                mx.identity(), mx.viewport((0, 0), (256, 256)), ctx)
+        check(device, oracle, scenes.Scene("depth-sort-ties", 256, 256, rf.FMT_RGBA8888, True, ctx, [call]))
 
 
 def test_many_small_draws_one_pass(device, oracle):

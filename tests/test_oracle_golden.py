@@ -227,3 +227,46 @@ def test_line_primitives_restatement_sanity(oracle):
     assert cov.sum() == 10 and all(cov[y].sum() == 1 for y in range(2, 12))
     cov, st = draw(to_ndc(5.0, 5.0), to_ndc(5.0, 5.0))        # zero length: nothing
     assert cov.sum() == 0 and st.prims.o == 1
+
+
+@pytest.mark.parametrize("order", [rf.DepthSort.BackToFront, rf.DepthSort.FrontToBack])
+def test_depth_sort_restatement_equals_presorted_submission(oracle, order):
+    """Context::depth_sort (render.rs:180-182, 209-219) has no reference test. Without a depth test the painted result
+    depends on the order of every overlap: rendering with depth_sort must equal rendering the same triangles submitted
+    in an order computed independently here (numpy f32 restatement of Render::depth, prim.rs:21-23; stable on ties)."""
+    import dataclasses
+    from retrofire_b200 import scenes
+    f32 = np.float32
+    ctx = rf.Context(depth_test=None, face_cull=None)
+    sc = scenes.random_soup(600, 256, 192, seed=5, lanes_kind="color3", big=True, clipy=False, ctx=ctx)   # no triangle is clipped
+    d = sc.draws[0]
+    m = np.asarray(d.uniform, f32).ravel()[:16].reshape(4, 4)     # VS_MVP: row-major Mat4 in the first 16 uniform floats
+    v = d.verts[:, :3].astype(f32)
+    clip = []
+    for r in range(4):                                  # Mat4::apply: every row a left fold from 0.0, each step rounded to f32
+        acc = f32(0) + m[r, 0] * v[:, 0]
+        acc = acc + m[r, 1] * v[:, 1]
+        acc = acc + m[r, 2] * v[:, 2]
+        clip.append(acc + m[r, 3] * f32(1))
+    cx, cy, cz, cw = clip
+    inside = (np.abs(cx) < cw) & (np.abs(cy) < cw) & (np.abs(cz) < cw)
+    t = d.prims.reshape(-1, 3)
+    t = np.ascontiguousarray(t[inside[t].all(axis=1)])  # keep the triangles that are not clipped: their depth is that of the input
+    assert len(t) > 200
+    d = dataclasses.replace(d, prims=t)
+    depth = ((cz[t[:, 0]] + cz[t[:, 1]]) + cz[t[:, 2]]) / f32(3)
+    perm = np.argsort(depth if order == rf.DepthSort.FrontToBack else -depth, kind="stable")
+    assert (np.diff(perm) != 1).any()                   # the sort really reorders this scene
+
+    def paint(call):
+        tgt = oracle.HostTarget(sc.w, sc.h, sc.fmt, True)
+        tgt.clear(ctx.color_clear, ctx.depth_clear)
+        st = oracle.render(call, tgt)
+        return tgt.color.copy(), tgt.depth.copy(), st
+
+    c_sorted, z_sorted, st_sorted = paint(dataclasses.replace(d, depth_sort=int(order)))
+    c_manual, z_manual, st_manual = paint(dataclasses.replace(d, prims=np.ascontiguousarray(t[perm])))
+    c_plain, _, _ = paint(d)
+    assert (c_sorted == c_manual).all() and (z_sorted.view(np.uint32) == z_manual.view(np.uint32)).all()
+    assert st_sorted.counters() == st_manual.counters()
+    assert (c_sorted != c_plain).any()
