@@ -425,3 +425,34 @@ def random_lines(n: int, w: int, h: int, seed: int, ctx: Context = None, lanes_k
     mvp = mx.perspective(1.0, f32(w) / f32(h), 0.5, 50.0)
     vp = mx.viewport((0, h), (w, 0))
     return Scene(f"lines_{lanes_kind}_{n}_{seed}", w, h, _ffi.FMT_RGBA8888, True, ctx, [DrawCall.make(edges, verts, shd, mvp, vp, ctx, edges=True)])
+
+
+# ---- demos/src/bin/hello.rs: text as textured geometry (render/text.rs) ---------------------------------------------
+def synthetic_font(sub_dims=(16, 24), glyphs=256, seed=7) -> "text.Atlas":
+    """A 16-column grid atlas of black/white glyph cells (the demo's font is a PBM bitmap; this one is procedural:
+    every cell is a distinct blocky pattern with a one-texel dark border so neighbouring glyphs are distinguishable)."""
+    from . import text
+    gw, gh = sub_dims
+    cols = 16
+    rows = (glyphs + cols - 1) // cols
+    g = np.random.default_rng(seed)
+    tex = np.zeros((rows * gh, cols * gw, 3), np.uint8)
+    for i in range(glyphs):
+        cell = np.kron(g.integers(0, 2, ((gh - 2) // 2, (gw - 2) // 2)), np.ones((2, 2), np.int64))
+        y0, x0 = i // cols * gh, i % cols * gw
+        tex[y0 + 1:y0 + 1 + cell.shape[0], x0 + 1:x0 + 1 + cell.shape[1]] = (cell * 255)[:, :, None]
+    return text.Atlas(sub_dims, Texture(tex))
+
+
+def hello_text(secs: float = 0.7, msg: str = "   Hello,\nRetrocomputing\n     World!", w: int = 800, h: int = 600) -> Scene:
+    """hello.rs:13-73: the message as glyph quads, SamplerClamp into the font atlas, no face culling, viewport inset by 10."""
+    from . import text
+    t = text.Text(synthetic_font()).write(msg)
+    faces, verts = t.geom
+    vp_m = mx.then(mx.translate3(0, 0, 15.0), mx.perspective(1.0, f32(4.0) / f32(3.0), 0.1, 1000.0))
+    mvp = mx.then(mx.then(mx.then(mx.then(mx.scale3(0.1, 0.1, 0.1), mx.translate3(-10.0, -5.0, f32(5.0) * f32(math.sin(secs)))),
+                                  mx.rotate_y(f32(secs) * f32(0.59))), mx.rotate_z(f32(math.sin(secs * 1.13)))), vp_m)
+    ctx = Context(face_cull=None)
+    shd = shader.new(_ffi.VS_MVP, _ffi.FS_TEX_CLAMP, texture=t.font.texture)
+    call = DrawCall.make(faces, verts, shd, mvp, mx.viewport((10, 10), (w - 10, h - 10)), ctx)
+    return Scene("hello_text", w, h, _ffi.FMT_RGBA8888, True, ctx, [call])

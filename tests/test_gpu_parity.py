@@ -252,6 +252,15 @@ def test_wireframe_over_solid_and_front_cull(device, oracle):
     assert_parity(got, run_oracle(oracle, culled), name="front-cull-lines")
 
 
+def test_text_as_textured_geometry(device, oracle):
+    """render/text.rs + tex.rs Atlas: the hello.rs demo — glyph quads sampled with SamplerClamp from a font
+    atlas, swinging through the frustum (including frames where the text crosses the near plane and is clipped)."""
+    for secs in (0.0, 0.7, 2.3, 4.6):
+        check(device, oracle, scenes.hello_text(secs))
+    big = scenes.hello_text(1.1, msg="\n".join("".join(chr(32 + (r * 7 + c) % 90) for c in range(40)) for r in range(12)))
+    check(device, oracle, big)
+
+
 def test_odd_sized_target(device, oracle):
     """Width/height not multiples of the tile or of 4 (scalar tile I/O path)."""
     sc = scenes.random_soup(500, 333, 211, seed=5, lanes_kind="color3", big=True)
