@@ -131,7 +131,12 @@ typedef struct rf_draw {
                                sort_unstable_by leaves their order unspecified)  render.rs:180-182,209-219 */
   uint8_t prim_kind;        /* RF_PRIM_TRIS: 3 indices per primitive (Tri<usize>); RF_PRIM_EDGES: 2 indices per
                                primitive (Edge<usize>: render/prim.rs:41-60, clip.rs:311-348, raster.rs:122-177) */
-  uint8_t _pad[2];
+  uint8_t bbox_cull;        /* 1: scene-style object culling on the device (render/scene.rs:81-87, crates.rs:100-122):
+                               when BBox::visibility(vs_uniform[0..16]) of `bbox` is Hidden the draw is skipped as if
+                               render() had not been called (no Stats but objs.i). Needs a VS whose u[0..16] is the
+                               model-to-projection matrix (every catalogue VS except RF_VS_SPRITE). */
+  uint8_t _pad[1];
+  float bbox[6];            /* BBox<Model>: low x,y,z then upp x,y,z   scene.rs:22 */
 } rf_draw;
 
 /* render/stats.rs:16-40. time_ns is device time of the pass(es) (CUDA events). */
@@ -141,6 +146,7 @@ typedef struct rf_stats {
   uint64_t verts_i, verts_o;
   uint64_t frags_i, frags_o;
   uint64_t time_ns;
+  uint64_t objs_i, objs_o;  /* draws submitted with bbox_cull / those of them not Hidden (crates.rs:101,131) */
 } rf_stats;
 
 /* ---- context ------------------------------------------------------------------------- */

@@ -471,6 +471,21 @@ int rfo_render(const rf_draw* dp, const rfo_texture* texp, rfo_target* tp, rf_st
   const int L = (int)d.n_attr_lanes;
   if (L > MAXL || d.vert_stride_f32 < 3u + (uint32_t)L) return RF_E_INVALID;
   if (d.depth_sort > RF_SORT_BACK_TO_FRONT) return RF_E_INVALID;
+  if (d.bbox_cull) {
+    // The scene loop around render(): BBox::visibility (scene.rs:59-87) with the draw's model-to-projection matrix; a Hidden
+    // object is not rendered at all (crates.rs:100-122): only objs.i is counted (crates.rs:101,131).
+    if (d.bbox_cull > 1 || d.vs == RF_VS_SPRITE) return RF_E_INVALID;
+    st->objs_i += 1;
+    uint8_t all = 0x3F;
+    for (int k = 0; k < 8; k++) {  // BBox::verts scene.rs:62-69
+      const float p[3] = {d.bbox[(k & 4) ? 3 : 0], d.bbox[(k & 2) ? 4 : 1], d.bbox[(k & 1) ? 5 : 2]};
+      float pos[4];
+      apply_proj(d.vs_uniform, p, pos);
+      all &= outcode(pos);          // view_frustum::status clip.rs:245-267: Hidden <=> all corners outside one plane
+    }
+    if (all != 0) return RF_OK;
+    st->objs_o += 1;
+  }
   Tex tex{};
   if (texp) tex = Tex{texp->w, texp->h, texp->fmt, texp->data, (size_t)texp->stride};
   const bool needs_tex = d.fs == RF_FS_TEX_CLAMP_LIT || d.fs == RF_FS_TEX_CLAMP || d.fs == RF_FS_TEX_REPEAT_POT;

@@ -60,7 +60,9 @@ class RfDraw(C.Structure):
         ("depth_write", C.c_uint8),
         ("depth_sort", C.c_uint8),
         ("prim_kind", C.c_uint8),
-        ("_pad", C.c_uint8 * 2),
+        ("bbox_cull", C.c_uint8),
+        ("_pad", C.c_uint8 * 1),
+        ("bbox", C.c_float * 6),
     ]
 
 
@@ -71,6 +73,7 @@ class RfStats(C.Structure):
         ("verts_i", C.c_uint64), ("verts_o", C.c_uint64),
         ("frags_i", C.c_uint64), ("frags_o", C.c_uint64),
         ("time_ns", C.c_uint64),
+        ("objs_i", C.c_uint64), ("objs_o", C.c_uint64),
     ]
 
 

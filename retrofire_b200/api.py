@@ -70,7 +70,7 @@ class Stats:
 
     @staticmethod
     def from_c(s: RfStats) -> "Stats":
-        return Stats(time=s.time_ns * 1e-9, calls=float(s.calls),
+        return Stats(time=s.time_ns * 1e-9, calls=float(s.calls), objs=Throughput(s.objs_i, s.objs_o),
                      prims=Throughput(s.prims_i, s.prims_o), verts=Throughput(s.verts_i, s.verts_o),
                      frags=Throughput(s.frags_i, s.frags_o))
 
@@ -184,6 +184,7 @@ class DrawCall:
     depth_sort: int = 0
     mesh: Optional["Mesh"] = None
     prim_kind: int = _ffi.PRIM_TRIS   # PRIM_EDGES: prims is (n,2) — `Edge<usize>` line primitives
+    bbox: Optional[np.ndarray] = None  # (2,3) BBox<Model> low/upp: the draw is skipped when BBox::visibility(uniform) is Hidden
 
     @staticmethod
     def make(prims, verts, shd: Shader, uniform, to_screen, ctx: Context = None, mesh: "Mesh" = None, edges: bool = False) -> "DrawCall":
@@ -229,6 +230,10 @@ class DrawCall:
         d.face_cull, d.depth_test = self.face_cull, self.depth_test
         d.color_write, d.depth_write, d.depth_sort = int(self.color_write), int(self.depth_write), self.depth_sort
         d.prim_kind = self.prim_kind
+        if self.bbox is not None:
+            d.bbox_cull = 1
+            bb = np.ascontiguousarray(self.bbox, dtype=np.float32).reshape(6)
+            C.memmove(d.bbox, bb.ctypes.data, 24)
         return d
 
 

@@ -265,6 +265,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   if (prof == 2) {  // serialised on one stream, an event between every pair of kernels
     int ek = 0;
     auto mark = [&]() { cudaEventRecord(s.ev_k[ek++], st); };
+    if (P.any_bbox) { k_objects<<<blocks(P.n_draws, 128, 8), 128, 0, st>>>(P); s.n_launches++; }
     mark(); k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
     mark(); k_assemble<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
     if (s.order_upper) launch_order(c, s, P, Rec<LT>::QW, st);  // counted with k_assemble
@@ -281,6 +282,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   } else {
     // two dependent chains after k_setup: spans (main stream) and bins (side stream), joined before k_raster
     cudaStream_t sd = c->side;
+    if (P.any_bbox) { k_objects<<<blocks(P.n_draws, 128, 8), 128, 0, st>>>(P); s.n_launches++; }
     k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
     k_assemble<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
     if (s.order_upper) launch_order(c, s, P, Rec<LT>::QW, st);
@@ -486,6 +488,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.pbase = P.vbase + (nd + 1);
   P.targets = reinterpret_cast<const TargetDesc*>(dt + toff);
   P.n_draws = (uint32_t)nd; P.n_targets = (uint32_t)nt; P.NV = nv; P.NP = np; P.n_tiles = ntiles;
+  for (auto& q : s.draws) if (q.desc.flags & RF_F_BBOX) P.any_bbox = 1;
   P.cv = static_cast<float*>(c->cv.p);
   P.stris = static_cast<uint32_t*>(c->stris.p);
   P.cap_stris = (uint32_t)std::min<size_t>(c->capw_stris / words_stri(lt), 0x1FFFFFF0u);
@@ -584,7 +587,13 @@ rf_status validate_all(rf_ctx* c) {
     } else {
       const DrawStats* ds = reinterpret_cast<const DrawStats*>(s.h_dstats.p);
       for (size_t i = 0; i < s.draws.size(); i++) {
+        if (s.draws[i].desc.flags & RF_F_BBOX) {  // crates.rs:101,118-131: objs.i every object, objs.o the ones rendered
+          c->accum.objs_i += 1;
+          if (ds[i].hidden) { if (i + 1 == s.draws.size()) { c->last_draw = rf_stats{}; c->last_draw.objs_i = 1; } continue; }
+          c->accum.objs_o += 1;
+        }
         rf_stats d{};
+        if (s.draws[i].desc.flags & RF_F_BBOX) d.objs_i = d.objs_o = 1;
         d.calls = 1;
         d.prims_i = s.draws[i].desc.n_prims; d.verts_i = s.draws[i].desc.n_verts;
         d.prims_o = ds[i].prims_o; d.verts_o = 3 * ds[i].prims_o;
@@ -645,6 +654,7 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
   if (!c || !target || !d) return fail(c, RF_E_INVALID, "null argument");
   if (target->ctx != c) return fail(c, RF_E_INVALID, "target belongs to another ctx");
   if (d->depth_sort > RF_SORT_BACK_TO_FRONT) return fail(c, RF_E_INVALID, "bad depth_sort");
+  if (d->bbox_cull > 1 || (d->bbox_cull && d->vs == RF_VS_SPRITE)) return fail(c, RF_E_INVALID, "bbox_cull needs a vertex shader whose u[0..16] is the model-to-projection matrix");
   if (d->vs > RF_VS_SPRITE || d->fs > RF_FS_NORMAL_VIS) return fail(c, RF_E_UNSUPPORTED_SHADER, "shader id not in the catalogue");
   if (d->n_attr_lanes > RF_MAX_ATTR_LANES || d->n_attr_lanes < fs_min_lanes(d->fs))
     return fail(c, RF_E_UNSUPPORTED_SHADER, "fragment shader %u needs >= %u varying lanes, got %u", d->fs, fs_min_lanes(d->fs), d->n_attr_lanes);
@@ -712,7 +722,8 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
   D.L = d->n_attr_lanes; D.persp_mask = d->persp_mask; D.vs = d->vs; D.fs = d->fs;
   D.prim_kind = d->prim_kind;
   D.flags = (uint32_t)d->face_cull | (uint32_t)d->depth_test << RF_F_DTEST_SHIFT | (d->color_write ? RF_F_CWRITE : 0u) | (d->depth_write ? RF_F_DWRITE : 0u) |
-            (uint32_t)d->depth_sort << RF_F_DSORT_SHIFT;
+            (uint32_t)d->depth_sort << RF_F_DSORT_SHIFT | (d->bbox_cull ? RF_F_BBOX : 0u);
+  std::memcpy(D.bbox, d->bbox, sizeof D.bbox);
   D.tex = d->texture ? d->texture->d_data : nullptr;
   D.tex_w = d->texture ? d->texture->w : 0; D.tex_h = d->texture ? d->texture->h : 0;
   std::memcpy(D.vs_u, vs_uniform_override ? vs_uniform_override : d->vs_uniform, sizeof D.vs_u);

@@ -21,6 +21,7 @@
 #define RF_F_DTEST_MASK 0x3u
 #define RF_F_CWRITE 0x10u
 #define RF_F_DWRITE 0x20u
+#define RF_F_BBOX 0x100u    // skip the draw when its bounding box is Hidden (scene.rs:81-87)
 #define RF_F_DSORT_SHIFT 6   // Context::depth_sort (ctx.rs:39): RF_SORT_*
 #define RF_F_DSORT_MASK 0x3u
 #define RF_SORT_FRONT_TO_BACK 1u
@@ -46,6 +47,7 @@ struct DrawDesc {
   float vs_u[RF_VS_UNIFORM_F32];
   float fs_u[RF_FS_UNIFORM_F32];
   float vp[12];             // rows 0..2 of the viewport matrix
+  float bbox[6];            // BBox<Model> low, upp (RF_F_BBOX)
 };
 
 struct TargetDesc {
@@ -58,6 +60,7 @@ struct TargetDesc {
 
 struct DrawStats {
   unsigned long long prims_o, frags_i, frags_o;
+  unsigned long long hidden;  // k_objects: the draw's bounding box is outside the frustum -> the draw does not happen
 };
 
 // zeroed before every pass; read back after it.
@@ -108,6 +111,7 @@ struct PassParams {
   const uint32_t* pbase;  // [n_draws+1] prefix of n_prims
   const TargetDesc* targets;
   uint32_t n_draws, n_targets, NV, NP, n_tiles;
+  uint32_t any_bbox;      // some draw of the pass carries RF_F_BBOX (k_objects ran)
   float* cv;              // clip verts [NV][CVS]
   uint32_t* stris;        // [cap_stris][QW]   compacted screen triangles (k_assemble -> k_setup)
   uint32_t cap_stris;

@@ -10,12 +10,35 @@
 // K1: vertex shader (catalogue) + ClipVert::new outcode.  One thread per vertex of the pass.
 // render.rs:158-165; shader.rs:31-41; clip.rs:303-309
 // =============================================================================================
+// K0 k_objects: scene-style per-object culling (render/scene.rs:59-87; the loop of demos/src/bin/crates.rs:100-122).
+// One thread per draw that carries a bounding box: the 8 corners go through the draw's model-to-projection matrix
+// (ProjMat3::apply, mat.rs:968-972), get their outcodes (ClipVert::new, clip.rs:180-190) and the box is Hidden when all
+// corners are outside one plane (view_frustum::status, clip.rs:245-267). A hidden draw is skipped by k_vertex/k_assemble.
+__global__ void __launch_bounds__(128) k_objects(PassParams P) {
+  if (P.cstatus->poison) return;
+  for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < P.n_draws; d += gridDim.x * blockDim.x) {
+    const DrawDesc& D = P.draws[d];
+    if (!(D.flags & RF_F_BBOX)) continue;
+    uint32_t all = 0x3Fu;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {  // BBox::verts order (scene.rs:62-69); the order does not matter for the AND
+      const float x = D.bbox[(k & 4) ? 3 : 0], y = D.bbox[(k & 2) ? 4 : 1], z = D.bbox[(k & 1) ? 5 : 2];
+      float pos[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) pos[r] = dot4p(D.vs_u + 4 * r, x, y, z, 1.0f);
+      all &= outcode(pos[0], pos[1], pos[2], pos[3]);
+    }
+    if (all != 0) P.dstats[d].hidden = 1ull;
+  }
+}
+
 template <int LT>
 __global__ void __launch_bounds__(256) k_vertex(PassParams P) {
   constexpr int CVS = Rec<LT>::CVS;
   if (P.cstatus->poison) return;
   for (uint32_t gv = blockIdx.x * blockDim.x + threadIdx.x; gv < P.NV; gv += gridDim.x * blockDim.x) {
     const uint32_t d = find_draw(P.vbase, P.n_draws, gv);
+    if (P.any_bbox && P.dstats[d].hidden) continue;  // object culled: its clip vertices are never read
     const DrawDesc& D = P.draws[d];
     const float* __restrict__ in = D.verts + (size_t)(gv - __ldg(P.vbase + d)) * D.vstride;
     const uint32_t L = D.L;
@@ -394,7 +417,9 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
       const DrawDesc& D = P.draws[d];
       is_edge = D.prim_kind == RF_PRIM_EDGES;
     }
-    if (have && is_edge) {
+    const bool culled_obj = have && P.any_bbox && P.dstats[d].hidden != 0ull;  // k_objects: render() is not called at all
+    if (culled_obj) {
+    } else if (have && is_edge) {
       // Render for Edge<usize> (prim.rs:41-60): inline two vertices, Clip for [Edge] (clip.rs:311-348)
       const DrawDesc& D = P.draws[d];
       const uint32_t* ip = D.indices + 2 * (size_t)(gp - __ldg(P.pbase + d));

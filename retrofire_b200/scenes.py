@@ -221,8 +221,14 @@ def crate_texture() -> Texture:
     return Texture(read_ppm(os.path.join(ASSETS, "crate.ppm.gz")))
 
 
-def crates(grid: str = "1089", w: int = 3840, h: int = 2160, host_cull: bool = True) -> Scene:
-    """demos/src/bin/crates.rs. grid "169": reference layout (-30..=30 step 5); "1089": -48..=48 step 3."""
+def crates(grid: str = "1089", w: int = 3840, h: int = 2160, host_cull: bool = True, device_cull: bool = False) -> Scene:
+    """demos/src/bin/crates.rs. grid "169": reference layout (-30..=30 step 5); "1089": -48..=48 step 3.
+    host_cull: the demo's `bbox.visibility(..) == Hidden` test runs here and hidden objects are not submitted;
+    device_cull: EVERY object is submitted with its BBox<Model> and the test runs on the device (rf_draw.bbox_cull)."""
+    import dataclasses
+    if device_cull:
+        host_cull = False
+    with_bbox = lambda call, verts: dataclasses.replace(call, bbox=np.stack([verts[:, :3].min(0), verts[:, :3].max(0)])) if device_cull else call
     ctx = Context()
     vw, vh = w - 20, h - 20
     vp = mx.viewport((10, h - 10), (w - 10, 10))
@@ -238,7 +244,7 @@ def crates(grid: str = "1089", w: int = 3840, h: int = 2160, host_cull: bool = T
     fv, ff = floor_mesh(50)
     m2p = mx.then(mx.identity(), w2p)
     if not (host_cull and _bbox_hidden(fv, m2p)):
-        draws.append(DrawCall.make(ff, fv, floor_shd, m2p, vp, ctx))
+        draws.append(with_bbox(DrawCall.make(ff, fv, floor_shd, m2p, vp, ctx), fv))
     cv, cf = cube_mesh(2.0)
     rng = range(-30, 31, 5) if grid == "169" else range(-48, 49, 3)
     for i in rng:
@@ -246,7 +252,7 @@ def crates(grid: str = "1089", w: int = 3840, h: int = 2160, host_cull: bool = T
             m2p = mx.then(mx.translate3(i, 0, j), w2p)
             if host_cull and _bbox_hidden(cv, m2p):
                 continue
-            draws.append(DrawCall.make(cf, cv, crate_shd, m2p, vp, ctx))
+            draws.append(with_bbox(DrawCall.make(cf, cv, crate_shd, m2p, vp, ctx), cv))
     return Scene(f"crates_{grid}", w, h, _ffi.FMT_RGBA8888, True, ctx, draws)
 
 

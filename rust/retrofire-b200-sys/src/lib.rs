@@ -48,7 +48,9 @@ pub struct rf_draw {
     pub depth_write: u8,
     pub depth_sort: u8,
     pub prim_kind: u8,
-    pub _pad: [u8; 2],
+    pub bbox_cull: u8,
+    pub _pad: [u8; 1],
+    pub bbox: [f32; 6],
 }
 
 #[repr(C)]
@@ -59,6 +61,7 @@ pub struct rf_stats {
     pub verts_i: u64, pub verts_o: u64,
     pub frags_i: u64, pub frags_o: u64,
     pub time_ns: u64,
+    pub objs_i: u64, pub objs_o: u64,
 }
 
 unsafe extern "C" {

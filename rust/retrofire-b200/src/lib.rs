@@ -138,7 +138,7 @@ pub fn render<A, Uni: Copy, Shd>(
         face_cull: match ctx.face_cull { None => 0, Some(retrofire_core::render::ctx::FaceCull::Back) => 1, Some(_) => 2 },
         depth_test: match ctx.depth_test { None => 0, Some(core::cmp::Ordering::Less) => 1, Some(core::cmp::Ordering::Equal) => 2, Some(_) => 3 },
         color_write: ctx.color_write as u8, depth_write: ctx.depth_write as u8,
-        depth_sort: match ctx.depth_sort { None => 0, Some(DepthSort::FrontToBack) => 1, Some(DepthSort::BackToFront) => 2 }, prim_kind: 0, _pad: [0; 2],
+        depth_sort: match ctx.depth_sort { None => 0, Some(DepthSort::FrontToBack) => 1, Some(DepthSort::BackToFront) => 2 }, prim_kind: 0, bbox_cull: 0, _pad: [0; 1], bbox: [0.0; 6],
     };
     let mut st = sys::rf_stats::default();
     // stats_out != NULL: flush + wait, i.e. the reference's "done when render() returns" (render.rs:206)

@@ -252,6 +252,32 @@ def test_wireframe_over_solid_and_front_cull(device, oracle):
     assert_parity(got, run_oracle(oracle, culled), name="front-cull-lines")
 
 
+def test_object_culling_on_the_device(device, oracle):
+    """SURVEY 8f-3: the scene loop of crates.rs:100-131 with `BBox::visibility` (scene.rs:81-87) evaluated on the device.
+    All 170 objects are submitted with their bounding boxes; hidden ones are skipped as if render() had not been called
+    (Stats count only the rendered ones, objs.i/objs.o as the demo counts them), and the frame equals the host-culled one."""
+    dev_sc = scenes.crates("169", 960, 540, device_cull=True)
+    host_sc = scenes.crates("169", 960, 540)
+    assert len(dev_sc.draws) == 170 and len(host_sc.draws) < 100
+    got, want = run_gpu(device, dev_sc), run_oracle(oracle, dev_sc)
+    assert_parity(got, want, name="crates-device-cull")
+    assert (got[2].objs.i, got[2].objs.o) == (want[2].objs.i, want[2].objs.o) == (170, len(host_sc.draws))
+    host = run_gpu(device, host_sc)
+    assert (host[0] == got[0]).all() and host[2].counters() == got[2].counters()
+    assert_parity(run_gpu(device, dev_sc, per_draw_sync=True), want, name="crates-device-cull-sync")
+    # a bounding box that straddles a plane is not Hidden even when every triangle ends up clipped away
+    import dataclasses
+    d = dataclasses.replace(scenes.hello_tri().draws[0], bbox=np.array([[-50, -50, -1], [50, 50, 1]], np.float32))
+    sc = scenes.Scene("bbox-clipped", 640, 480, rf.FMT_RGBA8888, False, rf.Context(), [d], clear=False)
+    got = run_gpu(device, sc)
+    assert_parity(got, run_oracle(oracle, sc), name="bbox-clipped")
+    assert (got[2].objs.i, got[2].objs.o, int(got[2].calls)) == (1, 1, 1)
+    with pytest.raises(rf.RetrofireError) as e:   # the sprite VS has no model-to-projection matrix in u[0..16]
+        s = scenes.sprites(10)
+        device.render(dataclasses.replace(s.draws[0], bbox=np.zeros((2, 3), np.float32)), device.framebuf(s.w, s.h, s.fmt, True), want_stats=True)
+    assert e.value.status == rf.RF_E_INVALID
+
+
 def test_text_as_textured_geometry(device, oracle):
     """render/text.rs + tex.rs Atlas: the hello.rs demo — glyph quads sampled with SamplerClamp from a font
     atlas, swinging through the frustum (including frames where the text crosses the near plane and is clipped)."""
