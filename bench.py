@@ -272,7 +272,7 @@ def run_b200(args):
 
     # ---- end to end: host geometry in (rf_render with host pointers: staged through pinned memory and
     # copied H2D inside the timed region), colour buffer of every frame out (D2H into page-locked Buf2 storage)
-    Fe = min(F, 8)
+    Fe = min(F // 2, 16) if F >= 2 else 1   # frames per end-to-end step; two sets of device targets alternate (a swap chain)
     dt, shape = (np.uint32, (base.h, base.w)) if base.fmt == rf.FMT_XRGB8888 else (np.uint8, (base.h, base.w, 4))
     host_color = [[dev.pinned_empty(shape, dt) for _ in range(Fe)] for _ in range(2)]  # double-buffered Buf2 storage
 
@@ -294,12 +294,13 @@ def run_b200(args):
         """One step through the reference-facing calls: clear + render() with host geometry for every frame,
         then the colour buffer of every frame is read back. Downloads run on the library's copy stream and
         overlap the next step's rendering; dev.sync() at the end of the timed region waits for all of them."""
+        tg = targets[(k & 1) * Fe: (k & 1) * Fe + Fe] if F >= 2 * Fe else targets[:Fe]
         for f in range(Fe):
-            targets[f].clear(base.ctx)
+            tg[f].clear(base.ctx)
             for d in e2e_frames[f]:
-                dev.render(d, targets[f])
+                dev.render(d, tg[f])
         for f in range(Fe):
-            targets[f].download_color_async(host_color[k & 1][f])
+            tg[f].download_color_async(host_color[k & 1][f])
 
     e_steps = 0 if args.kernel_only else max(2, min(args.steps, 20))
     for k in range(2 if e_steps else 0):

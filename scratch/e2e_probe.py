@@ -3,11 +3,12 @@ sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 import retrofire_b200 as rf
 from retrofire_b200 import scenes
-F = 8
+F = 16
 base = scenes.bunny(subdiv=2)
 frames = [scenes.bunny(subdiv=2, theta=2*math.pi*f/32 + 1.0).draws for f in range(F)]
 dev = rf.Device(0)
-tg = [dev.framebuf(base.w, base.h, base.fmt, True) for _ in range(F)]
+tgs = [[dev.framebuf(base.w, base.h, base.fmt, True) for _ in range(F)] for _ in range(2)]
+tg = tgs[0]
 host = [[dev.pinned_empty((base.h, base.w), np.uint32) for _ in range(F)] for _ in range(2)]
 import dataclasses
 def pin(x):
@@ -23,6 +24,7 @@ t0 = time.perf_counter()
 for _ in range(200): tg[0].clear(base.ctx)
 print("clear call %.1f us" % ((time.perf_counter() - t0) / 200 * 1e6)); dev.sync()
 def step(k, t):
+    tg = tgs[k & 1]
     t0 = time.perf_counter()
     for f in range(F):
         tg[f].clear(base.ctx)
