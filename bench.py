@@ -469,6 +469,26 @@ def run_tiles(args):
     ms = ev0.elapsed_time(ev1)
     st = dev.stats(reset=True)
     fi, pi = st.frags.i, st.prims.i
+    # where the step goes (untimed extra steps): every kernel serialised and bracketed by events; the gather alone
+    dev.profile(2)
+    for _ in range(3):
+        step()
+    dev.sync()
+    kall = dev.kernel_times()
+    dev.profile(0)
+    kernel_ms = {k: round(v[0] * 1e-6 / max(v[1], 1), 4) for k, v in kall.items()}
+    gather_ms = 0.0
+    if world > 1:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            g0.record(stream)
+            for _ in range(5):
+                shard.gather_bands(color, bands, rank)
+            g1.record(stream)
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1) / 5
     if world > 1:
         tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -484,7 +504,8 @@ def run_tiles(args):
             "config": dict(desc, parallelism=f"sort-first row bands x{world} + NCCL all_gather of finished bands", bands=bands,
                            l2="inputs larger than L2: 265 MB colour+depth target + 84 MB geometry per step"),
             "frames_per_s": args.steps / (ms * 1e-3), "Mtriangles_per_s": pi / (ms * 1e-3) / 1e6,
-            "gather_bytes_per_step": 0 if world == 1 else base.w * base.h * 4 * (world - 1) // world}), flush=True)
+            "gather_bytes_per_step": 0 if world == 1 else base.w * base.h * 4 * (world - 1) // world,
+            "gather_ms": gather_ms, "kernel_ms_rank0": kernel_ms}), flush=True)
     dev.close()
     if world > 1:
         dist.destroy_process_group()

@@ -205,6 +205,25 @@ rf_status rf_render(rf_ctx* ctx, rf_target* target, const rf_draw* draw, rf_stat
  * vs_uniforms + i*RF_VS_UNIFORM_F32; everything else from `draw`. Queued like rf_render. */
 rf_status rf_render_frames(rf_ctx* ctx, rf_target* const* targets, uint32_t n_frames,
                            const rf_draw* draw, const float* vs_uniforms);
+/* ---- sort-first over NVLink peer memory --------------------------------------
+ * With peers attached, every colour store of this GPU's row band (rf_ctx_set_row_band) is also
+ * stored into the same pixel of the other GPUs' colour buffers (P2P over NVLink), inside the
+ * rasteriser: after rf_sync on every GPU each of them holds the whole frame, with no separate
+ * gather. Passes that draw into such a target run two cross-GPU barriers (after the clear, after
+ * rasterisation), so EVERY GPU must submit the same sequence of clears/draws/flushes for it, and
+ * rf_target_clear clears all rows of the colour buffer (depth: the band). Peers are named either
+ * by CUDA IPC handles (one process per GPU) or by raw device pointers (one process, several ctxs).
+ * Tables hold `world` entries in rank order; the entry of `rank` itself is ignored.
+ * If rf_ctx_replays grew on ANY GPU during a frame (a pass was re-run after arena growth), peers
+ * may have read the frame before the re-run's stores: render that frame again. */
+#define RF_IPC_HANDLE_BYTES 64
+#define RF_MAX_PEER_GPUS 8
+rf_status rf_ctx_peer_export(rf_ctx* ctx, uint8_t* ipc_handle_out /* 64 B or NULL */, void** devptr_out /* or NULL */);
+rf_status rf_ctx_peer_attach(rf_ctx* ctx, uint32_t world, uint32_t rank, const uint8_t* ipc_handles, void* const* devptrs);
+rf_status rf_target_peer_export(rf_ctx* ctx, rf_target* t, uint8_t* ipc_handle_out, void** devptr_out);
+rf_status rf_target_peer_attach(rf_ctx* ctx, rf_target* t, uint32_t world, uint32_t rank, const uint8_t* ipc_handles, void* const* devptrs);
+rf_status rf_ctx_replays(rf_ctx* ctx, uint64_t* out); /* passes re-launched after an arena overflow so far */
+
 rf_status rf_flush(rf_ctx* ctx); /* execute queued draws (asynchronous on the stream)       */
 rf_status rf_sync(rf_ctx* ctx);  /* flush + wait; reports deferred device-side errors        */
 /* Accumulated Stats of the ctx (flushes + waits); reset=1 zeroes them afterwards. */

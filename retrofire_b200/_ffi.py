@@ -101,6 +101,11 @@ SYMBOLS = {
     "rf_texture_destroy": (None, [_P]),
     "rf_mesh_create": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.POINTER(_P)]),
     "rf_mesh_destroy": (None, [_P]),
+    "rf_ctx_peer_export": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "rf_ctx_peer_attach": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.POINTER(_P)]),
+    "rf_target_peer_export": (C.c_int, [_P, _P, _P, C.POINTER(_P)]),
+    "rf_target_peer_attach": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, C.POINTER(_P)]),
+    "rf_ctx_replays": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "rf_render": (C.c_int, [_P, _P, C.POINTER(RfDraw), C.POINTER(RfStats)]),
     "rf_render_frames": (C.c_int, [_P, C.POINTER(_P), C.c_uint32, C.POINTER(RfDraw), _P]),
     "rf_flush": (C.c_int, [_P]),

@@ -237,6 +237,15 @@ class DrawCall:
         return d
 
 
+def _peer_call(fn, head, world, rank, table):
+    assert len(table) == world
+    if isinstance(table[rank], (bytes, bytearray)):
+        blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(bytes(t) for t in table))
+        return fn(*head, world, rank, blob, None)
+    ptrs = (C.c_void_p * world)(*[int(t) for t in table])
+    return fn(*head, world, rank, None, ptrs)
+
+
 # ---- device objects -----------------------------------------------------------------------
 class Device:
     """One rf_ctx (one GPU, one stream)."""
@@ -280,6 +289,22 @@ class Device:
 
     def set_row_band(self, y0: int, y1: int):
         self._check(self.lib.rf_ctx_set_row_band(self.h, y0, y1))
+
+    # ---- sort-first over NVLink peer memory (rf_ctx_peer_* / rf_target_peer_*) -------------------
+    def peer_export(self, ipc: bool = True):
+        """This GPU's barrier slots: a 64-byte CUDA IPC handle (other processes) or the raw device pointer (same process)."""
+        h, p = (C.c_uint8 * 64)(), C.c_void_p()
+        self._check(self.lib.rf_ctx_peer_export(self.h, h if ipc else None, C.byref(p)))
+        return bytes(h) if ipc else p.value
+
+    def peer_attach(self, world: int, rank: int, table):
+        """`table`: `world` IPC handles (bytes) or `world` device pointers (ints), in rank order."""
+        self._check(_peer_call(self.lib.rf_ctx_peer_attach, (self.h,), world, rank, table))
+
+    def replays(self) -> int:
+        n = C.c_uint64()
+        self._check(self.lib.rf_ctx_replays(self.h, C.byref(n)))
+        return n.value
 
     def flush(self):
         self._check(self.lib.rf_flush(self.h))
@@ -393,6 +418,15 @@ class Framebuf:
         if ctx.depth_clear is not None and self.has_depth:
             z = C.c_float(float(np.float32(1.0) / np.float32(ctx.depth_clear)))
         self.dev._check(self.dev.lib.rf_target_clear(self.dev.h, self.h, rgba, C.byref(z) if z is not None else None))
+
+    def peer_export(self, ipc: bool = True):
+        h, p = (C.c_uint8 * 64)(), C.c_void_p()
+        self.dev._check(self.dev.lib.rf_target_peer_export(self.dev.h, self.h, h if ipc else None, C.byref(p)))
+        return bytes(h) if ipc else p.value
+
+    def peer_attach(self, world: int, rank: int, table):
+        """Replicate this GPU's colour stores into the same target on the other GPUs (handles or pointers in rank order)."""
+        self.dev._check(_peer_call(self.dev.lib.rf_target_peer_attach, (self.dev.h, self.h), world, rank, table))
 
     def _host_shape(self):
         dt, ch = _HOST_DTYPE[self.fmt]

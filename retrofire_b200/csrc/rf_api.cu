@@ -24,6 +24,7 @@
 #include "rf_geometry.cuh"
 #include "rf_raster.cuh"
 #include "rf_order.cuh"
+#include "rf_peer.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -98,6 +99,9 @@ struct PassSlot {
   int profiled = 0;
   uint32_t NV = 0, NP = 0, n_tiles = 0, lt = 0;
   uint32_t n_launches = 0;
+  bool peer = false;         // some target of the pass replicates its colour stores into peer GPUs (rf_peer.cuh)
+  bool epochs_set = false;   // barrier epochs are assigned at the first launch and reused by replays
+  uint32_t epoch1 = 0, epoch2 = 0;
   uint32_t order_upper = 0;  // > 0: the pass holds a depth-sorted draw; bound on its screen triangles (rf_order.cuh)
 };
 
@@ -111,6 +115,9 @@ struct rf_target {
   float* d_depth;
   cudaEvent_t dl_done = nullptr;  // completion of the last asynchronous download (copy stream)
   bool dl_pending = false;
+  uint32_t n_peers = 0;           // rf_target_peer_attach: colour buffers of the same target on the other GPUs
+  uint32_t* peer_color[RF_MAX_PEERS] = {};
+  bool peer_ipc[RF_MAX_PEERS] = {};  // opened with cudaIpcOpenMemHandle (closed on destroy)
 };
 struct rf_texture {
   rf_ctx* ctx;
@@ -147,6 +154,11 @@ struct rf_ctx {
   size_t capw_stris = 0, capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
   CtxStatus* d_cstatus = nullptr;
   DevBuf sdepth, ord_k32[2], ord_v[2], ord_k64[2], ord_tmp;  // Context::depth_sort (rf_order.cuh), allocated on first use
+  DevBuf peer_flags;           // this GPU's barrier slots (rf_peer.cuh), written by the peers
+  PeerBarrier pb{};
+  bool pb_ipc[RF_MAX_PEERS + 1] = {};
+  uint32_t barrier_epoch = 0;
+  uint64_t replays = 0;        // passes re-launched after an arena overflow
   DevBuf bounce;               // upload/download staging on the device
   PinnedBuf h_bounce;
 
@@ -277,7 +289,15 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     mark(); k_ckpt<LT><<<sm * 8, 256, 0, st>>>(P);
     mark(); k_bin_sort_warp<<<sm * 8, RF_SORT_WARPS * 32, 0, st>>>(P);
     mark(); k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, st>>>(P);
-    mark(); k_raster<LT><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
+    mark();
+    if (s.peer) {
+      k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch1);
+      k_raster<LT, true><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
+      k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch2);
+      s.n_launches += 2;
+    } else {
+      k_raster<LT, false><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
+    }
     mark();
   } else {
     // two dependent chains after k_setup: spans (main stream) and bins (side stream), joined before k_raster
@@ -298,9 +318,12 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     k_walk<LT><<<sm * 12, 128, 0, st>>>(P);
     k_ckpt<LT><<<sm * 8, 256, 0, st>>>(P);
     cudaStreamWaitEvent(st, s.ev_join, 0);
+    if (s.peer) { k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch1); s.n_launches++; }  // every peer has cleared its copy of the frame
     if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS - 1], st);
-    k_raster<LT><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
+    if (s.peer) k_raster<LT, true><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
+    else k_raster<LT, false><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
     if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS], st);
+    if (s.peer) { k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch2); s.n_launches++; }  // every peer's stores into this GPU have landed
   }
   s.n_launches += RF_N_KERNELS;
 }
@@ -432,7 +455,11 @@ rf_status launch_pass(rf_ctx* c, int si) {
     T.tiles_x = (t->w + RF_TILE - 1) / RF_TILE; T.tiles_y = (t->h + RF_TILE - 1) / RF_TILE;
     T.tile_base = tile_base; tile_base += T.tiles_x * T.tiles_y;
     T.band_y0 = std::min(c->band_y0, t->h); T.band_y1 = std::min(c->band_y1, t->h);
+    T.n_peers = t->n_peers; T._pad = 0;
+    for (uint32_t p = 0; p < RF_MAX_PEERS; p++) T.peer_color[p] = p < t->n_peers ? t->peer_color[p] : nullptr;
+    if (t->n_peers && nd) s.peer = true;
   }
+  if (s.peer && !s.epochs_set) { s.epoch1 = ++c->barrier_epoch; s.epoch2 = ++c->barrier_epoch; s.epochs_set = true; }
 
   const size_t coff = (toff + nt * sizeof(TargetDesc) + 15) & ~size_t(15);
   ClearDesc* h_clears = reinterpret_cast<ClearDesc*>(tb + coff);
@@ -443,7 +470,9 @@ rf_status launch_pass(rf_ctx* c, int si) {
       const uint32_t y0 = std::min(c->band_y0, qc.target->h), y1 = std::min(c->band_y1, qc.target->h);
       const size_t first = (size_t)y0 * qc.target->w;
       const unsigned long long n = (unsigned long long)(y1 > y0 ? y1 - y0 : 0) * qc.target->w;
-      if (qc.has_color) h_clears[k++] = ClearDesc{qc.target->d_color + first, n, qc.color, 0u};
+      // with peers attached the other GPUs store THEIR bands into this buffer: the colour clear covers every row
+      if (qc.has_color && qc.target->n_peers) h_clears[k++] = ClearDesc{qc.target->d_color, (unsigned long long)qc.target->w * qc.target->h, qc.color, 0u};
+      else if (qc.has_color) h_clears[k++] = ClearDesc{qc.target->d_color + first, n, qc.color, 0u};
       if (qc.has_depth) h_clears[k++] = ClearDesc{reinterpret_cast<uint32_t*>(qc.target->d_depth) + first, n, qc.zbits, 0u};
     }
   }
@@ -538,6 +567,7 @@ void reset_slot(PassSlot& s) {
   s.geom_len = 0;
   s.direct_len = 0;
   s.in_flight = false;
+  s.peer = false; s.epochs_set = false;
 }
 
 // Wait for every pass in flight, replay overflowed ones with larger arenas, fold Stats.
@@ -564,6 +594,7 @@ rf_status validate_all(rf_ctx* c) {
       { rf_status st = ensure_arenas(c, lt, s.NV, s.n_tiles, w); if (st) return st; }
       RF_CUDA(c, cudaMemsetAsync(c->d_cstatus, 0, sizeof(CtxStatus), c->stream));
       std::vector<int> replay = c->flight;
+      c->replays += replay.size();
       for (int r : replay) { rf_status st = launch_pass(c, r); if (st) return st; }
       continue;  // re-validate the same front slot
     }
@@ -778,9 +809,12 @@ rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
     ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_status), sizeof(HostStatus), cudaHostAllocDefault) == cudaSuccess;
   }
   ok = ok && cudaFuncSetAttribute(k_bin_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(k_raster<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<3>::BYTES) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(k_raster<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<5>::BYTES) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(k_raster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<8>::BYTES) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_raster<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<3>::BYTES) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_raster<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<5>::BYTES) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_raster<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<8>::BYTES) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_raster<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<3>::BYTES) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_raster<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<5>::BYTES) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_raster<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RasterSmem<8>::BYTES) == cudaSuccess;
   if (!ok) { rf_ctx_destroy(c); return RF_E_CUDA; }
   *out = c;
   return RF_OK;
@@ -803,6 +837,8 @@ void rf_ctx_destroy(rf_ctx* c) {
   }
   c->cv.release(); c->stris.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->bins2.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
+  for (uint32_t r = 0; r < c->pb.world; r++) if (r != c->pb.self && c->pb_ipc[r]) cudaIpcCloseMemHandle(c->pb.flags[r]);
+  c->peer_flags.release();
   c->sdepth.release(); c->ord_tmp.release();
   for (int k = 0; k < 2; k++) { c->ord_k32[k].release(); c->ord_v[k].release(); c->ord_k64[k].release(); }
   if (c->d_cstatus) cudaFree(c->d_cstatus);
@@ -841,6 +877,7 @@ void rf_target_destroy(rf_target* t) {
   if (!t) return;
   sync_impl(t->ctx);
   if (t->dl_done) cudaEventDestroy(t->dl_done);
+  for (uint32_t p = 0; p < t->n_peers; p++) if (t->peer_ipc[p]) cudaIpcCloseMemHandle(t->peer_color[p]);
   cudaFree(t->d_color);
   if (t->d_depth) cudaFree(t->d_depth);
   delete t;
@@ -1083,6 +1120,104 @@ rf_status rf_ctx_kernel_times(rf_ctx* c, uint64_t* ns, uint64_t* launches) {
 const char* rf_kernel_name(uint32_t i) {
   static const char* names[RF_N_KERNELS] = {"k_vertex", "k_assemble", "k_setup", "k_edge_ckpt", "k_walk", "k_bin_alloc", "k_bin_scatter", "k_ckpt", "k_bin_sort_warp", "k_bin_sort_big", "k_raster"};
   return i < RF_N_KERNELS ? names[i] : "";
+}
+
+// ---- sort-first over NVLink peer memory (rf_peer.cuh) ---------------------------------------------------------
+namespace {
+rf_status ensure_peer_flags(rf_ctx* c) {
+  if (c->peer_flags.p) return RF_OK;
+  cudaSetDevice(c->device);
+  if (!c->peer_flags.reserve((RF_MAX_PEERS + 1) * RF_PEER_FLAG_STRIDE * 4)) return fail(c, RF_E_NOMEM, "peer barrier flags");
+  RF_CUDA(c, cudaMemset(c->peer_flags.p, 0, c->peer_flags.cap));
+  return RF_OK;
+}
+// resolve slot r of a peer table: an IPC handle (other process) or a raw device pointer (same process, maybe another GPU)
+rf_status open_peer(rf_ctx* c, const uint8_t* ipc_handles, void* const* devptrs, uint32_t r, void** out, bool* is_ipc) {
+  *is_ipc = false;
+  if (devptrs) {
+    *out = devptrs[r];
+    if (!*out) return fail(c, RF_E_INVALID, "null peer pointer");
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, *out) == cudaSuccess && a.type == cudaMemoryTypeDevice && a.device != c->device) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c, RF_E_CUDA, "no peer access from GPU %d to GPU %d", c->device, a.device);
+      cudaGetLastError();
+    }
+    return RF_OK;
+  }
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, ipc_handles + (size_t)r * RF_IPC_HANDLE_BYTES, sizeof h);
+  if (cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return fail(c, RF_E_CUDA, "cudaIpcOpenMemHandle failed for peer %u", r); }
+  *is_ipc = true;
+  return RF_OK;
+}
+}  // namespace
+
+rf_status rf_ctx_peer_export(rf_ctx* c, uint8_t* ipc_handle_out, void** devptr_out) {
+  if (!c) return RF_E_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == RF_IPC_HANDLE_BYTES, "handle size");
+  { rf_status st = ensure_peer_flags(c); if (st) return st; }
+  if (devptr_out) *devptr_out = c->peer_flags.p;
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    RF_CUDA(c, cudaIpcGetMemHandle(&h, c->peer_flags.p));
+    std::memcpy(ipc_handle_out, &h, sizeof h);
+  }
+  return RF_OK;
+}
+
+rf_status rf_ctx_peer_attach(rf_ctx* c, uint32_t world, uint32_t rank, const uint8_t* ipc_handles, void* const* devptrs) {
+  if (!c || world < 2 || world > RF_MAX_PEERS + 1 || rank >= world || (!ipc_handles == !devptrs)) return fail(c, RF_E_INVALID, "bad peer table");
+  { rf_status st = sync_impl(c); if (st) return st; }
+  { rf_status st = ensure_peer_flags(c); if (st) return st; }
+  cudaSetDevice(c->device);
+  PeerBarrier pb{};
+  pb.world = world; pb.self = rank;
+  for (uint32_t r = 0; r < world; r++) {
+    if (r == rank) { pb.flags[r] = static_cast<uint32_t*>(c->peer_flags.p); continue; }
+    void* p = nullptr;
+    rf_status st = open_peer(c, ipc_handles, devptrs, r, &p, &c->pb_ipc[r]);
+    if (st) return st;
+    pb.flags[r] = static_cast<uint32_t*>(p);
+  }
+  c->pb = pb;
+  return RF_OK;
+}
+
+rf_status rf_target_peer_export(rf_ctx* c, rf_target* t, uint8_t* ipc_handle_out, void** devptr_out) {
+  if (!c || !t || t->ctx != c) return fail(c, RF_E_INVALID, "bad target");
+  if (devptr_out) *devptr_out = t->d_color;
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    RF_CUDA(c, cudaIpcGetMemHandle(&h, t->d_color));
+    std::memcpy(ipc_handle_out, &h, sizeof h);
+  }
+  return RF_OK;
+}
+
+rf_status rf_target_peer_attach(rf_ctx* c, rf_target* t, uint32_t world, uint32_t rank, const uint8_t* ipc_handles, void* const* devptrs) {
+  if (!c || !t || t->ctx != c) return fail(c, RF_E_INVALID, "bad target");
+  if (c->pb.world != world || c->pb.self != rank) return fail(c, RF_E_INVALID, "rf_ctx_peer_attach must come first, with the same world and rank");
+  if (!ipc_handles == !devptrs) return fail(c, RF_E_INVALID, "give IPC handles or device pointers");
+  if (t->n_peers) return fail(c, RF_E_INVALID, "target already has peers");
+  { rf_status st = sync_impl(c); if (st) return st; }
+  cudaSetDevice(c->device);
+  uint32_t n = 0;
+  for (uint32_t r = 0; r < world; r++) {
+    if (r == rank) continue;
+    void* p = nullptr;
+    rf_status st = open_peer(c, ipc_handles, devptrs, r, &p, &t->peer_ipc[n]);
+    if (st) return st;
+    t->peer_color[n++] = static_cast<uint32_t*>(p);
+  }
+  t->n_peers = n;
+  return RF_OK;
+}
+
+rf_status rf_ctx_replays(rf_ctx* c, uint64_t* out) {
+  if (!c || !out) return RF_E_INVALID;
+  *out = c->replays;
+  return RF_OK;
 }
 
 }  // extern "C"

@@ -50,12 +50,17 @@ struct DrawDesc {
   float bbox[6];            // BBox<Model> low, upp (RF_F_BBOX)
 };
 
+#define RF_MAX_PEERS 7
 struct TargetDesc {
   uint32_t* color;  // uint32 containers, pitch = w
   float* depth;     // or nullptr
   uint32_t w, h, fmt;
   uint32_t tiles_x, tiles_y, tile_base;
   uint32_t band_y0, band_y1;
+  // Sort-first over NVLink peer memory: every colour store of this GPU's band is replicated into the colour buffers of
+  // the other GPUs (same layout), so each GPU ends the pass holding the whole frame without a separate gather.
+  uint32_t n_peers, _pad;
+  uint32_t* peer_color[RF_MAX_PEERS];
 };
 
 struct DrawStats {

@@ -7,9 +7,15 @@ which needs a collective on the data path:
 * sort-first sharding — geometry is replicated, rank r rasterises only the framebuffer rows of
   its band (`Device.set_row_band`), aligned to the 32-row tiles of the rasteriser.
 
-The ONLY exchange is the final gather of finished bands into one framebuffer
-(`gather_bands`): an all_gather of equal-sized (padded) row bands over NCCL/NVLink on GPUs, or
-gloo in the CPU tests. Stats are summed with an all_reduce (`reduce_stats`).
+The ONLY exchange is the final gather of finished bands into one framebuffer. Two forms:
+
+* `attach_peers` (GPUs): the exchange is fused into the rasteriser — every colour store of a rank's band is also
+  stored into the peers' framebuffers over NVLink (CUDA IPC peer memory), so after `Device.sync()` every rank holds
+  the whole frame and nothing else is moved (`render_frame_with_peers` adds the collective retry an arena-growth
+  replay needs);
+* `gather_bands`: an all_gather of equal-sized (padded) row bands over NCCL/NVLink on GPUs, or gloo in the CPU tests.
+
+Stats are summed with an all_reduce (`reduce_stats`).
 """
 from __future__ import annotations
 
@@ -96,3 +102,33 @@ def reduce_stats(counters: Sequence[int], device=None, group=None) -> List[int]:
     t = torch.tensor(list(counters), dtype=torch.int64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return [int(x) for x in t]
+
+
+# ---- sort-first with the exchange fused into the rasteriser (csrc/rf_peer.cuh) ------------------------------------
+def attach_peers(dev, framebufs, rank: int, world: int, group=None) -> None:
+    """One process per GPU: exchange CUDA IPC handles of the barrier slots and of every framebuffer's colour buffer with
+    torch.distributed and attach them. Every rank must call this with the same number of framebufs, in the same order."""
+    import torch.distributed as dist
+    mine = [dev.peer_export()] + [fb.peer_export() for fb in framebufs]
+    table = [None] * world
+    dist.all_gather_object(table, mine, group=group)
+    dev.peer_attach(world, rank, [t[0] for t in table])
+    for i, fb in enumerate(framebufs):
+        fb.peer_attach(world, rank, [t[1 + i] for t in table])
+
+
+def render_frame_with_peers(dev, draw_frame, group=None, max_tries: int = 4) -> int:
+    """Run `draw_frame()` (clear + draws of ONE frame into peer-attached targets) and wait for it on every rank. If any
+    rank had to re-run a pass after growing its arenas, peers may have seen the frame before those stores: the frame is
+    rendered again (arenas only grow, so this settles). Returns the number of attempts."""
+    import torch
+    import torch.distributed as dist
+    for attempt in range(1, max_tries + 1):
+        before = dev.replays()
+        draw_frame()
+        dev.sync()
+        grew = torch.tensor([dev.replays() - before], dtype=torch.int64, device="cuda" if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(grew, op=dist.ReduceOp.MAX, group=group)
+        if int(grew) == 0:
+            return attempt
+    raise RuntimeError("arenas kept growing")
