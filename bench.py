@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--sharding", default="frames", choices=["frames", "tiles"],
                     help="frames: every rank renders its own frame batch (weak scaling); tiles: sort-first row bands of ONE large frame "
                          "per step + NCCL all_gather of the finished bands (strong scaling, SURVEY 8e)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer-root", "nccl"],
+                    help="--sharding tiles: 'peer' fuses the exchange into the rasteriser (colour stores replicated into the peers over "
+                         "NVLink, csrc/rf_peer.cuh); 'nccl' rasterises first and all_gathers the finished bands")
     ap.add_argument("--frames", type=int, default=128,
                     help="frames per step (frame batch); BASELINE config 5(ii) is a 1,024-frame batch over 8 GPUs = 128 per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
@@ -440,13 +443,16 @@ def run_tiles(args):
     import dataclasses
     draws = [dataclasses.replace(d, mesh=dev.mesh(d.prims, d.verts)) for d in per_frame[0]]
     color = shard.target_tensor(fb)
+    peer = world > 1 and args.exchange.startswith("peer")
+    if peer:   # "peer": every rank ends with the whole frame; "peer-root": only rank 0 collects it
+        shard.attach_peers(dev, [fb], rank, world, root=0 if args.exchange == "peer-root" else None)
 
     def step():
         fb.clear(base.ctx)
         for d in draws:
             dev.render(d, fb)
         dev.flush()
-        if world > 1:
+        if world > 1 and not peer:
             with torch.cuda.stream(stream):
                 shard.gather_bands(color, bands, rank)
 
@@ -501,11 +507,13 @@ def run_tiles(args):
             "metric": "Mfragments/s", "value": fi / (ms * 1e-3) / 1e6, "unit": "Mfragments/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict(desc, parallelism=f"sort-first row bands x{world} + NCCL all_gather of finished bands", bands=bands,
+            "config": dict(desc, parallelism=f"sort-first row bands x{world}, " + ("colour stores replicated into the peers over NVLink inside k_raster"
+                                                                                   if peer else "NCCL all_gather of finished bands"), bands=bands,
                            l2="inputs larger than L2: 265 MB colour+depth target + 84 MB geometry per step"),
             "frames_per_s": args.steps / (ms * 1e-3), "Mtriangles_per_s": pi / (ms * 1e-3) / 1e6,
-            "gather_bytes_per_step": 0 if world == 1 else base.w * base.h * 4 * (world - 1) // world,
-            "gather_ms": gather_ms, "kernel_ms_rank0": kernel_ms}), flush=True)
+            "exchange": "none" if world == 1 else args.exchange,
+            "gather_bytes_per_step": 0 if world == 1 or peer else base.w * base.h * 4 * (world - 1) // world,
+            "nccl_gather_ms_alone": gather_ms, "kernel_ms_rank0": kernel_ms}), flush=True)
     dev.close()
     if world > 1:
         dist.destroy_process_group()

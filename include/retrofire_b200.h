@@ -213,7 +213,9 @@ rf_status rf_render_frames(rf_ctx* ctx, rf_target* const* targets, uint32_t n_fr
  * rasterisation), so EVERY GPU must submit the same sequence of clears/draws/flushes for it, and
  * rf_target_clear clears all rows of the colour buffer (depth: the band). Peers are named either
  * by CUDA IPC handles (one process per GPU) or by raw device pointers (one process, several ctxs).
- * Tables hold `world` entries in rank order; the entry of `rank` itself is ignored.
+ * Tables hold `world` entries in rank order; the entry of `rank` itself is ignored. In a target's
+ * table an all-zero handle / NULL pointer means "do not push into that rank": with only a root
+ * rank's entry set on the others (and an empty table on the root) the frame is gathered to root.
  * If rf_ctx_replays grew on ANY GPU during a frame (a pass was re-run after arena growth), peers
  * may have read the frame before the re-run's stores: render that frame again. */
 #define RF_IPC_HANDLE_BYTES 64

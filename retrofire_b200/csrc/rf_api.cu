@@ -115,7 +115,8 @@ struct rf_target {
   float* d_depth;
   cudaEvent_t dl_done = nullptr;  // completion of the last asynchronous download (copy stream)
   bool dl_pending = false;
-  uint32_t n_peers = 0;           // rf_target_peer_attach: colour buffers of the same target on the other GPUs
+  bool peer_mode = false;         // rf_target_peer_attach was called: passes drawing into it run the cross-GPU barriers
+  uint32_t n_peers = 0;           // colour buffers of the same target on the other GPUs that this GPU pushes its tiles into
   uint32_t* peer_color[RF_MAX_PEERS] = {};
   bool peer_ipc[RF_MAX_PEERS] = {};  // opened with cudaIpcOpenMemHandle (closed on destroy)
 };
@@ -457,7 +458,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
     T.band_y0 = std::min(c->band_y0, t->h); T.band_y1 = std::min(c->band_y1, t->h);
     T.n_peers = t->n_peers; T._pad = 0;
     for (uint32_t p = 0; p < RF_MAX_PEERS; p++) T.peer_color[p] = p < t->n_peers ? t->peer_color[p] : nullptr;
-    if (t->n_peers && nd) s.peer = true;
+    if (t->peer_mode && nd) s.peer = true;
   }
   if (s.peer && !s.epochs_set) { s.epoch1 = ++c->barrier_epoch; s.epoch2 = ++c->barrier_epoch; s.epochs_set = true; }
 
@@ -471,7 +472,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
       const size_t first = (size_t)y0 * qc.target->w;
       const unsigned long long n = (unsigned long long)(y1 > y0 ? y1 - y0 : 0) * qc.target->w;
       // with peers attached the other GPUs store THEIR bands into this buffer: the colour clear covers every row
-      if (qc.has_color && qc.target->n_peers) h_clears[k++] = ClearDesc{qc.target->d_color, (unsigned long long)qc.target->w * qc.target->h, qc.color, 0u};
+      if (qc.has_color && qc.target->peer_mode) h_clears[k++] = ClearDesc{qc.target->d_color, (unsigned long long)qc.target->w * qc.target->h, qc.color, 0u};
       else if (qc.has_color) h_clears[k++] = ClearDesc{qc.target->d_color + first, n, qc.color, 0u};
       if (qc.has_depth) h_clears[k++] = ClearDesc{reinterpret_cast<uint32_t*>(qc.target->d_depth) + first, n, qc.zbits, 0u};
     }
@@ -1199,18 +1200,21 @@ rf_status rf_target_peer_attach(rf_ctx* c, rf_target* t, uint32_t world, uint32_
   if (!c || !t || t->ctx != c) return fail(c, RF_E_INVALID, "bad target");
   if (c->pb.world != world || c->pb.self != rank) return fail(c, RF_E_INVALID, "rf_ctx_peer_attach must come first, with the same world and rank");
   if (!ipc_handles == !devptrs) return fail(c, RF_E_INVALID, "give IPC handles or device pointers");
-  if (t->n_peers) return fail(c, RF_E_INVALID, "target already has peers");
+  if (t->peer_mode) return fail(c, RF_E_INVALID, "target already has peers");
   { rf_status st = sync_impl(c); if (st) return st; }
   cudaSetDevice(c->device);
   uint32_t n = 0;
   for (uint32_t r = 0; r < world; r++) {
     if (r == rank) continue;
+    // an all-zero handle / null pointer: this GPU does not push into rank r (e.g. only a root rank collects the frame)
+    if (devptrs ? devptrs[r] == nullptr : std::all_of(ipc_handles + (size_t)r * RF_IPC_HANDLE_BYTES, ipc_handles + (size_t)(r + 1) * RF_IPC_HANDLE_BYTES, [](uint8_t b) { return b == 0; })) continue;
     void* p = nullptr;
     rf_status st = open_peer(c, ipc_handles, devptrs, r, &p, &t->peer_ipc[n]);
     if (st) return st;
     t->peer_color[n++] = static_cast<uint32_t*>(p);
   }
   t->n_peers = n;
+  t->peer_mode = true;
   return RF_OK;
 }
 

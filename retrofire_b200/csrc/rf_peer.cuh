@@ -1,8 +1,10 @@
 // rf_peer.cuh — sort-first sharding over NVLink peer memory: the exchange step fused into the rasteriser.
 //
-// Every GPU rasterises its row band and k_raster<LT, true> replicates each colour store into the colour buffers of
-// the other GPUs (TargetDesc::peer_color, P2P stores), so the pass ends with the whole frame on every GPU and there is
-// no separate gather: only pixels that were actually drawn cross NVLink, overlapped with rasterisation.
+// Every GPU rasterises its row band and k_raster<LT, true>, as soon as it has finished a tile, pushes that tile's
+// colour rows into the colour buffers of the other GPUs (TargetDesc::peer_color, 128-bit P2P stores), so the pass ends
+// with the whole frame on every GPU and there is no separate gather: only tiles that were actually drawn cross NVLink,
+// and the transfer overlaps the rasterisation of the other tiles. (Replicating every single colour store instead was
+// measured first and is slower: 4-byte remote stores waste NVLink packets, and overdraw multiplies them.)
 // Two cross-GPU barriers order the frame:
 //   clear (each GPU clears ALL rows of its own colour buffer) -> barrier 1 -> k_raster (remote stores) -> barrier 2
 // barrier 1: no GPU may store into a peer before that peer has cleared; barrier 2: the frame may only be read (or

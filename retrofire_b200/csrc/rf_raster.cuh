@@ -366,20 +366,8 @@ __device__ __forceinline__ uint32_t* color_px(uint32_t* gc, uint32_t gw, uint32_
   return gc + (size_t)row * gw + (idx - row * RF_TILE_PITCH);
 }
 
-// Colour store; with PEER also into the same pixel of every peer GPU's colour buffer (P2P stores over NVLink).
-template <bool PEER>
-__device__ __forceinline__ void store_color(const TargetDesc& T, uint32_t* gc, uint32_t gw, uint32_t idx, uint32_t px) {
-  uint32_t* lp = color_px(gc, gw, idx);
-  *lp = px;
-  if (PEER) {
-    const size_t eo = (size_t)(lp - T.color);
-    const uint32_t np = T.n_peers;
-    for (uint32_t p = 0; p < np; p++) T.peer_color[p][eo] = px;
-  }
-}
-
-template <int LT, bool PEER>
-__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, const TargetDesc& T, uint32_t fmt, uint32_t* gc, uint32_t gw, float* sz, uint32_t idx, const float* v,
+template <int LT>
+__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t* gc, uint32_t gw, float* sz, uint32_t idx, const float* v,
                                                      uint32_t pmask, uint32_t dtest, bool cwrite, bool dwrite) {
   const float z = v[0];
   if (dtest != RF_DEPTH_NONE) {  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
@@ -398,14 +386,14 @@ __device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t
   uint32_t r = 0, g = 0, bl = 0, a = 0;
   if (!shade_fragment<LT>(D, fs, var, r, g, bl, a)) return 0u;  // discard: no writes at all
   if (dwrite) sz[idx] = z;
-  if (cwrite) { store_color<PEER>(T, gc, gw, idx, pack_pixel(fmt, r, g, bl, a)); return 1u; }
+  if (cwrite) { *color_px(gc, gw, idx) = pack_pixel(fmt, r, g, bl, a); return 1u; }
   return 0u;
 }
 
 // Specialisation for the default Context (depth test Less, colour and depth writes on, ctx.rs:104-127) and a
 // compile-time fragment shader / perspective mask: straight-line code, no state decoding.
-template <int LT, int FS, uint32_t PMASK, bool PEER>
-__device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, const TargetDesc& T, uint32_t fmt, uint32_t* gc, uint32_t gw, float* sz, uint32_t idx, const float* v) {
+template <int LT, int FS, uint32_t PMASK>
+__device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, uint32_t fmt, uint32_t* gc, uint32_t gw, float* sz, uint32_t idx, const float* v) {
   const float z = v[0];
   if (!(sz[idx] < z)) return 0u;
   float var[LT];
@@ -414,7 +402,7 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, co
   uint32_t r = 0, g = 0, bl = 0, a = 0;
   if (!shade_fragment<LT>(D, (uint32_t)FS, var, r, g, bl, a)) return 0u;
   sz[idx] = z;
-  store_color<PEER>(T, gc, gw, idx, pack_pixel(fmt, r, g, bl, a));
+  *color_px(gc, gw, idx) = pack_pixel(fmt, r, g, bl, a);
   return 1u;
 }
 
@@ -638,19 +626,19 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
               const uint32_t base = py * RF_TILE_PITCH + pxs;
               if (smode == 4) {  // default Context + FS_TEX_CLAMP_LIT (crates): straight-line fragment code
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu, PEER>(D, T, T.fmt, gc, T.w, sz, base + k, v);
+                  my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, gc, T.w, sz, base + k, v);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                 }
               } else if (smode == 2) {
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u, PEER>(D, T, T.fmt, gc, T.w, sz, base + k, v);
+                  my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, sz, base + k, v);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                 }
               } else {
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment<LT, PEER>(D, fs, T, T.fmt, gc, T.w, sz, base + k, v, pmask, dtest, cwrite, dwrite);
+                  my_o += process_fragment<LT>(D, fs, T.fmt, gc, T.w, sz, base + k, v, pmask, dtest, cwrite, dwrite);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
                 }
@@ -720,10 +708,10 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
               const DrawDesc& D = UNI ? Du : P.draws[fdraw];
               uint32_t wrote = 0;
               auto one = [&]() -> uint32_t {
-                if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u, PEER>(D, T, T.fmt, gc, T.w, sz, pix, fv);
-                if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u, PEER>(D, T, T.fmt, gc, T.w, sz, pix, fv);
-                if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu, PEER>(D, T, T.fmt, gc, T.w, sz, pix, fv);
-                return process_fragment<LT, PEER>(D, fs, T, T.fmt, gc, T.w, sz, pix, fv, pmask, dtest, cwrite, dwrite);
+                if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, sz, pix, fv);
+                if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, T.fmt, gc, T.w, sz, pix, fv);
+                if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, gc, T.w, sz, pix, fv);
+                return process_fragment<LT>(D, fs, T.fmt, gc, T.w, sz, pix, fv, pmask, dtest, cwrite, dwrite);
               };
               if (__all_sync(0xFFFFFFFFu, earlier == 0)) {
                 if (fvalid) wrote = one();
@@ -778,6 +766,30 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
       }
     }
     __syncwarp();
+
+    // ---- sort-first over peer memory (rf_peer.cuh): push the finished colour rows of this tile that lie in this
+    // GPU's band into the same pixels of every peer's colour buffer — P2P stores over NVLink, whole 128-byte rows,
+    // once per tile whatever the overdraw, while other warps keep rasterising. The rows were just written by this
+    // warp (visible after the __syncwarp above) and are still in L2.
+    if (PEER) {
+      const uint32_t np = T.n_peers;
+      const uint32_t ya = max(py0 + r0, T.band_y0), yb = min(py0 + r1, T.band_y1);
+      if (vec) {
+        const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
+        for (uint32_t y = ya + rsub; y < yb; y += 4) {
+          const size_t eo = (size_t)y * T.w + px0 + c4;
+          const uint4 v = *reinterpret_cast<const uint4*>(T.color + eo);
+          for (uint32_t p = 0; p < np; p++) *reinterpret_cast<uint4*>(T.peer_color[p] + eo) = v;
+        }
+      } else {
+        for (uint32_t y = ya; y < yb; y++)
+          if (lane < tw) {
+            const size_t eo = (size_t)y * T.w + px0 + lane;
+            const uint32_t v = T.color[eo];
+            for (uint32_t p = 0; p < np; p++) T.peer_color[p][eo] = v;
+          }
+      }
+    }
   }
 }
 

@@ -105,16 +105,17 @@ def reduce_stats(counters: Sequence[int], device=None, group=None) -> List[int]:
 
 
 # ---- sort-first with the exchange fused into the rasteriser (csrc/rf_peer.cuh) ------------------------------------
-def attach_peers(dev, framebufs, rank: int, world: int, group=None) -> None:
+def attach_peers(dev, framebufs, rank: int, world: int, group=None, root: int = None) -> None:
     """One process per GPU: exchange CUDA IPC handles of the barrier slots and of every framebuffer's colour buffer with
-    torch.distributed and attach them. Every rank must call this with the same number of framebufs, in the same order."""
+    torch.distributed and attach them. Every rank must call this with the same number of framebufs, in the same order.
+    root=None: every rank ends with the whole frame (all-gather semantics); root=r: only rank r collects it (gather)."""
     import torch.distributed as dist
     mine = [dev.peer_export()] + [fb.peer_export() for fb in framebufs]
     table = [None] * world
     dist.all_gather_object(table, mine, group=group)
     dev.peer_attach(world, rank, [t[0] for t in table])
     for i, fb in enumerate(framebufs):
-        fb.peer_attach(world, rank, [t[1 + i] for t in table])
+        fb.peer_attach(world, rank, [t[1 + i] if root is None or r == root else bytes(64) for r, t in enumerate(table)])
 
 
 def render_frame_with_peers(dev, draw_frame, group=None, max_tries: int = 4) -> int:
