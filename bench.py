@@ -218,8 +218,7 @@ def run_b200(args):
             dev.render_frames(res_frames[0][0], targets, uniforms)
         else:
             for t, draws in zip(targets, res_frames):
-                for d in draws:
-                    dev.render(d, t)
+                dev.render_many(draws, t)    # the frame's render() calls in one crossing of the C ABI
         dev.flush()
 
     def barrier():
@@ -267,8 +266,7 @@ def run_b200(args):
             dev.sync()
             t0 = time.perf_counter()
             targets[0].clear(base.ctx)
-            for d in one:
-                dev.render(d, targets[0])
+            dev.render_many(one, targets[0])
             dev.sync()
             ts.append(time.perf_counter() - t0)
         lat_ms = 1e3 * sorted(ts[5:])[len(ts[5:]) // 2]
@@ -300,8 +298,7 @@ def run_b200(args):
         tg = targets[(k & 1) * Fe: (k & 1) * Fe + Fe] if F >= 2 * Fe else targets[:Fe]
         for f in range(Fe):
             tg[f].clear(base.ctx)
-            for d in e2e_frames[f]:
-                dev.render(d, tg[f])
+            dev.render_many(e2e_frames[f], tg[f])
         for f in range(Fe):
             tg[f].download_color_async(host_color[k & 1][f])
 
@@ -335,8 +332,7 @@ def run_b200(args):
         def step_crates():
             for t, draws in zip(ct, cres):
                 t.clear(cb.ctx)
-                for d in draws:
-                    dev.render(d, t)
+                dev.render_many(draws, t)
             dev.flush()
 
         for _ in range(3):

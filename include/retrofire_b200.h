@@ -203,6 +203,9 @@ void rf_mesh_destroy(rf_mesh* m);
 rf_status rf_render(rf_ctx* ctx, rf_target* target, const rf_draw* draw, rf_stats* stats_out);
 /* Frame batches: draw i goes to targets[i] with vs_uniform taken from
  * vs_uniforms + i*RF_VS_UNIFORM_F32; everything else from `draw`. Queued like rf_render. */
+/* A frame's list of render() calls into one target in ONE call (the loop of crates.rs:114-131,
+ * front/src/minifb.rs frame callbacks): same as n_draws rf_render(…, NULL) calls, in order. */
+rf_status rf_render_many(rf_ctx* ctx, rf_target* target, const rf_draw* draws, uint32_t n_draws);
 rf_status rf_render_frames(rf_ctx* ctx, rf_target* const* targets, uint32_t n_frames,
                            const rf_draw* draw, const float* vs_uniforms);
 /* ---- sort-first over NVLink peer memory --------------------------------------

@@ -101,6 +101,7 @@ SYMBOLS = {
     "rf_texture_destroy": (None, [_P]),
     "rf_mesh_create": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.POINTER(_P)]),
     "rf_mesh_destroy": (None, [_P]),
+    "rf_render_many": (C.c_int, [_P, _P, _P, C.c_uint32]),
     "rf_ctx_peer_export": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "rf_ctx_peer_attach": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.POINTER(_P)]),
     "rf_target_peer_export": (C.c_int, [_P, _P, _P, C.POINTER(_P)]),

@@ -261,6 +261,7 @@ class Device:
         self._targets = []
         self._meshes = []
         self._pinned = []
+        self._many = {}
 
     def _check(self, st: int):
         if st != _ffi.RF_OK:
@@ -360,6 +361,22 @@ class Device:
             return Stats.from_c(s)
         self._check(self.lib.rf_render(self.h, target.h, C.byref(d), None))
         return None
+
+    def render_many(self, calls: Sequence[DrawCall], target: "Framebuf"):
+        """All render() calls of one frame into one target with a single crossing of the C ABI (rf_render_many). The marshalled
+        array is memoised on the list object: a frame loop that re-submits the same list pays for the marshalling once."""
+        memo = self._many.get(id(calls))
+        if memo is None or memo[0] is not calls or memo[1] != len(calls) or any(a is not b for a, b in zip(memo[3], calls)):
+            arr = (RfDraw * len(calls))()
+            keep = []
+            for i, call in enumerate(calls):
+                tex = call.shader.texture.handle(self) if call.shader.texture is not None else None
+                d = call.to_struct(tex, call.mesh.h if call.mesh is not None else None)
+                C.memmove(C.byref(arr, i * C.sizeof(RfDraw)), C.byref(d), C.sizeof(RfDraw))
+                keep.append(call)
+            memo = (calls, len(calls), arr, keep)
+            self._many[id(calls)] = memo
+        self._check(self.lib.rf_render_many(self.h, target.h, memo[2], memo[1]))
 
     def render_frames(self, call: DrawCall, targets: Sequence["Framebuf"], uniforms: np.ndarray):
         """Frame batch: draw i -> targets[i] with vs_uniform uniforms[i] (n, 32) f32."""

@@ -1045,6 +1045,16 @@ rf_status rf_render_frames(rf_ctx* c, rf_target* const* targets, uint32_t n_fram
   return RF_OK;
 }
 
+rf_status rf_render_many(rf_ctx* c, rf_target* target, const rf_draw* draws, uint32_t n_draws) {
+  if (!c || !target || (n_draws && !draws)) return fail(c, RF_E_INVALID, "null argument");
+  cudaSetDevice(c->device);
+  for (uint32_t i = 0; i < n_draws; i++) {
+    rf_status st = queue_draw(c, target, draws + i, nullptr);
+    if (st) return st;
+  }
+  return RF_OK;
+}
+
 rf_status rf_flush(rf_ctx* c) {
   if (!c) return RF_E_INVALID;
   cudaSetDevice(c->device);

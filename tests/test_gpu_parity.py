@@ -149,6 +149,24 @@ def test_many_small_draws_one_pass(device, oracle):
     check(device, oracle, base)
 
 
+def test_render_many_equals_individual_calls(device, oracle):
+    """rf_render_many: a frame's list of render() calls in one crossing of the C ABI; re-submitting the same list reuses the
+    marshalled array, a changed list does not."""
+    sc = scenes.crates("169", 640, 360)
+    want = run_oracle(oracle, sc)
+    fb = device.framebuf(sc.w, sc.h, sc.fmt, True)
+    for rep in range(2):
+        fb.clear(sc.ctx)
+        device.stats(reset=True)
+        device.render_many(sc.draws, fb)
+        got = (fb.download_color(), fb.download_depth(), device.stats(reset=True))
+        assert_parity(got, want, name=f"render_many-{rep}")
+    sc.draws[-1], sc.draws[-2] = sc.draws[-2], sc.draws[-1]       # same list object, same length, different content
+    fb.clear(sc.ctx)
+    device.render_many(sc.draws, fb)
+    assert_parity((fb.download_color(), fb.download_depth(), device.stats(reset=True)), run_oracle(oracle, sc), name="render_many-changed")
+
+
 def test_frame_batch_render_frames(device, oracle):
     """rf_render_frames: one mesh, per-frame uniforms, per-frame targets (SURVEY 8e frame sharding)."""
     verts, faces = scenes.bunny_mesh(0)
