@@ -199,6 +199,14 @@ __device__ __forceinline__ uint32_t outcode(float x, float y, float z, float w) 
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return a + (b - a) * t; }  // math.rs:196-198
 __device__ __forceinline__ float round_up_to_half(float x) { return floorf(x + 0.5f) + 0.5f; }  // raster.rs:304-307
 
+// ZDiv for f32 (math/vary.rs:135-140): a / z, correctly rounded. An exactly-zero numerator (a component of an axis-aligned
+// normal, a uv on a texture edge) would send ptxas' div.rn sequence into its ~50-instruction slow path on every fragment
+// (FCHK flags zero operands); the quotient is then a zero with the sign of a XOR z whenever z is neither NaN nor zero.
+__device__ __forceinline__ float zdiv(float a, float z) {
+  if (a == 0.0f && z == z && z != 0.0f) return __uint_as_float((__float_as_uint(a) ^ __float_as_uint(z)) & 0x80000000u);
+  return a / z;
+}
+
 // f32::total_cmp key (stable sort of the three vertices by y, raster.rs:191)
 __device__ __forceinline__ int32_t total_key(float f) {
   int32_t b = __float_as_int(f);

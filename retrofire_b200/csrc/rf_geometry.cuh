@@ -185,7 +185,7 @@ __device__ __forceinline__ void to_screen(const CVert<LT>& c, const float* __res
   s.y = dot4p(vp + 4, px, py, pz, 1.0f);
   s.z = dot4p(vp + 8, px, py, pz, 1.0f);
 #pragma unroll
-  for (int i = 0; i < LT; i++) s.a[i] = ((persp_mask >> i) & 1u) ? c.a[i] / w : c.a[i];
+  for (int i = 0; i < LT; i++) s.a[i] = ((persp_mask >> i) & 1u) ? zdiv(c.a[i], w) : c.a[i];
 }
 
 // One trapezoid half: everything raster.rs:248-302 precomputes, minus the unused y lane.

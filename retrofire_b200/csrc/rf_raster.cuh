@@ -381,7 +381,7 @@ __device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t
   if (pmask != 0) {  // Scanline::fragments: var.z_div(pos.z) on the lanes whose type divides (raster.rs:60-69)
 #pragma unroll
     for (int i = 0; i < LT; i++)
-      if ((pmask >> i) & 1u) var[i] = v[1 + i] / z;
+      if ((pmask >> i) & 1u) var[i] = zdiv(v[1 + i], z);
   }
   uint32_t r = 0, g = 0, bl = 0, a = 0;
   if (!shade_fragment<LT>(D, fs, var, r, g, bl, a)) return 0u;  // discard: no writes at all
@@ -398,7 +398,7 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
   if (!(sz[idx] < z)) return 0u;
   float var[LT];
 #pragma unroll
-  for (int i = 0; i < LT; i++) var[i] = ((PMASK >> i) & 1u) ? v[1 + i] / z : v[1 + i];
+  for (int i = 0; i < LT; i++) var[i] = ((PMASK >> i) & 1u) ? zdiv(v[1 + i], z) : v[1 + i];
   uint32_t r = 0, g = 0, bl = 0, a = 0;
   if (!shade_fragment<LT>(D, (uint32_t)FS, var, r, g, bl, a)) return 0u;
   sz[idx] = z;
