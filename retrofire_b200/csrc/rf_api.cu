@@ -149,7 +149,7 @@ struct rf_ctx {
   std::vector<int> flight;     // slots launched and not yet validated, oldest first
 
   // scratch arenas shared by all passes (stream order makes reuse safe)
-  DevBuf cv, stris, spans, tris, entries, bins, bins2, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
+  DevBuf cv, sv, stris, spans, tris, entries, bins, bins2, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
   // capacities: spans/tris/ckpts in 32-bit WORDS (record width depends on the pass's lane count),
   // entries and long spans in records
   size_t capw_stris = 0, capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
@@ -195,6 +195,7 @@ rf_status fail(rf_ctx* c, rf_status st, const char* fmt, ...) {
 int lt_for(uint32_t L) { return L <= 3 ? 3 : (L <= 5 ? 5 : 8); }
 
 size_t words_cv(int lt) { return lt == 3 ? Rec<3>::CVS : lt == 5 ? Rec<5>::CVS : Rec<8>::CVS; }
+size_t words_sv(int lt) { return lt == 3 ? Rec<3>::SVS : lt == 5 ? Rec<5>::SVS : Rec<8>::SVS; }
 size_t words_span(int lt) { return lt == 3 ? Rec<3>::SW : lt == 5 ? Rec<5>::SW : Rec<8>::SW; }
 size_t words_tri(int lt) { return lt == 3 ? Rec<3>::TW : lt == 5 ? Rec<5>::TW : Rec<8>::TW; }
 size_t words_ckpt(int lt) { return lt == 3 ? Rec<3>::KW : lt == 5 ? Rec<5>::KW : Rec<8>::KW; }
@@ -280,7 +281,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     auto mark = [&]() { cudaEventRecord(s.ev_k[ek++], st); };
     if (P.any_bbox) { k_objects<<<blocks(P.n_draws, 128, 8), 128, 0, st>>>(P); s.n_launches++; }
     mark(); k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
-    mark(); k_assemble<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+    mark(); if (P.use_sv) k_assemble<LT, true><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P); else k_assemble<LT, false><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
     if (s.order_upper) launch_order(c, s, P, Rec<LT>::QW, st);  // counted with k_assemble
     mark(); k_setup<LT><<<sm * 8, 128, 0, st>>>(P);
     mark(); k_edge_ckpt<LT><<<sm * 4, 128, 0, st>>>(P);
@@ -305,7 +306,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     cudaStream_t sd = c->side;
     if (P.any_bbox) { k_objects<<<blocks(P.n_draws, 128, 8), 128, 0, st>>>(P); s.n_launches++; }
     k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
-    k_assemble<LT><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
+    if (P.use_sv) k_assemble<LT, true><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P); else k_assemble<LT, false><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
     if (s.order_upper) launch_order(c, s, P, Rec<LT>::QW, st);
     k_setup<LT><<<sm * 8, 128, 0, st>>>(P);
     cudaEventRecord(s.ev_fork, st);
@@ -332,6 +333,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
 // Any growth frees memory that in-flight kernels might still use -> callers guarantee idleness.
 rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const ArenaWants& w) {
   if (!c->cv.reserve(nv * words_cv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "clip-vertex arena");
+  if (!c->sv.reserve(nv * words_sv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "screen-vertex arena");
   if (w.w_stris > c->capw_stris) { if (!c->stris.reserve(w.w_stris * 4)) return fail(c, RF_E_NOMEM, "screen-triangle arena"); c->capw_stris = w.w_stris; }
   if (w.w_spans > c->capw_spans) { if (!c->spans.reserve(w.w_spans * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->capw_spans = w.w_spans; }
   if (w.w_tris > c->capw_tris) { if (!c->tris.reserve(w.w_tris * 4)) return fail(c, RF_E_NOMEM, "triangle arena"); c->capw_tris = w.w_tris; }
@@ -393,7 +395,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
                   std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), std::max<size_t>(c->capw_stris, (size_t)8 << 20),
                   std::max<size_t>(c->cap_entries, (size_t)1 << 20), std::max<size_t>(c->cap_long, (size_t)1 << 19),
                   std::max<size_t>(c->cap_chunks, (size_t)1 << 20), std::max<size_t>(c->cap_tall, (size_t)1 << 18)};
-  need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 24 + 64 ||
+  need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->sv.cap < (size_t)nv * words_sv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 24 + 64 ||
               !arenas_cover(c, want) || c->cursors.cap < 64;
   // Context::depth_sort: bound on the pass's screen triangles (a clipped triangle fans into <= 7) and the sort buffers
   uint64_t order_bound = 0;
@@ -519,7 +521,10 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.targets = reinterpret_cast<const TargetDesc*>(dt + toff);
   P.n_draws = (uint32_t)nd; P.n_targets = (uint32_t)nt; P.NV = nv; P.NP = np; P.n_tiles = ntiles;
   for (auto& q : s.draws) if (q.desc.flags & RF_F_BBOX) P.any_bbox = 1;
+  P.use_sv = 1;
+  for (auto& q : s.draws) if (!(q.desc.flags & RF_F_SV)) P.use_sv = 0;
   P.cv = static_cast<float*>(c->cv.p);
+  P.sv = static_cast<float*>(c->sv.p);
   P.stris = static_cast<uint32_t*>(c->stris.p);
   P.cap_stris = (uint32_t)std::min<size_t>(c->capw_stris / words_stri(lt), 0x1FFFFFF0u);
   P.sdepth = s.order_upper ? static_cast<uint32_t*>(c->sdepth.p) : nullptr;
@@ -756,6 +761,8 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
   D.flags = (uint32_t)d->face_cull | (uint32_t)d->depth_test << RF_F_DTEST_SHIFT | (d->color_write ? RF_F_CWRITE : 0u) | (d->depth_write ? RF_F_DWRITE : 0u) |
             (uint32_t)d->depth_sort << RF_F_DSORT_SHIFT | (d->bbox_cull ? RF_F_BBOX : 0u);
   std::memcpy(D.bbox, d->bbox, sizeof D.bbox);
+  // an indexed mesh uses each vertex several times: transform it to screen space once (k_vertex) instead of once per use
+  if ((uint64_t)D.n_prims * (d->prim_kind == RF_PRIM_EDGES ? 2 : 3) >= 2ull * D.n_verts) D.flags |= RF_F_SV;
   D.tex = d->texture ? d->texture->d_data : nullptr;
   D.tex_w = d->texture ? d->texture->w : 0; D.tex_h = d->texture ? d->texture->h : 0;
   std::memcpy(D.vs_u, vs_uniform_override ? vs_uniform_override : d->vs_uniform, sizeof D.vs_u);
@@ -836,7 +843,7 @@ void rf_ctx_destroy(rf_ctx* c) {
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
   }
-  c->cv.release(); c->stris.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->bins2.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
+  c->cv.release(); c->sv.release(); c->stris.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->bins2.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
   for (uint32_t r = 0; r < c->pb.world; r++) if (r != c->pb.self && c->pb_ipc[r]) cudaIpcCloseMemHandle(c->pb.flags[r]);
   c->peer_flags.release();

@@ -21,6 +21,7 @@
 #define RF_F_DTEST_MASK 0x3u
 #define RF_F_CWRITE 0x10u
 #define RF_F_DWRITE 0x20u
+#define RF_F_SV 0x200u      // vertices are shared by enough primitives: k_vertex also stores their screen-space form
 #define RF_F_BBOX 0x100u    // skip the draw when its bounding box is Hidden (scene.rs:81-87)
 #define RF_F_DSORT_SHIFT 6   // Context::depth_sort (ctx.rs:39): RF_SORT_*
 #define RF_F_DSORT_MASK 0x3u
@@ -116,8 +117,10 @@ struct PassParams {
   const uint32_t* pbase;  // [n_draws+1] prefix of n_prims
   const TargetDesc* targets;
   uint32_t n_draws, n_targets, NV, NP, n_tiles;
+  uint32_t use_sv;        // every draw of the pass has RF_F_SV: k_vertex stores screen-space vertices, k_assemble<LT, true> reads them
   uint32_t any_bbox;      // some draw of the pass carries RF_F_BBOX (k_objects ran)
   float* cv;              // clip verts [NV][CVS]
+  float* sv;              // screen verts [NV][SVS]: to_screen of every vertex inside the frustum, plus its outcode
   uint32_t* stris;        // [cap_stris][QW]   compacted screen triangles (k_assemble -> k_setup)
   uint32_t cap_stris;
   uint32_t* sdepth;       // [cap_stris] total-order bits of Render::depth, or null when no draw of the pass is depth-sorted
@@ -152,6 +155,7 @@ struct PassParams {
 // record strides in 32-bit words, as a function of the compile-time lane count LT
 template <int LT> struct Rec {
   static constexpr int CVS = (5 + LT + 3) & ~3;        // clip vert: pos4, oc, attr[LT]            (16 B aligned)
+  static constexpr int SVS = (4 + LT + 3) & ~3;        // screen vert: x, y, z, attr[LT], oc       (16 B aligned)
   static constexpr int SW = (2 + 1 + LT + 1) & ~1;     // span: X0|n<<16, ckpt, z, attr[LT]         (8 B aligned)
   static constexpr int HS = (3 * LT + 8 + 3) & ~3;      // half setup: dv[1+LT], L[2+LT], dl[2+LT], R, dr, y    (16 B aligned)
   static constexpr int TW = 8 + 2 * HS;                // tri: 8 header words + two half setups (see TriRec)

@@ -32,74 +32,6 @@ __global__ void __launch_bounds__(128) k_objects(PassParams P) {
   }
 }
 
-template <int LT>
-__global__ void __launch_bounds__(256) k_vertex(PassParams P) {
-  constexpr int CVS = Rec<LT>::CVS;
-  if (P.cstatus->poison) return;
-  for (uint32_t gv = blockIdx.x * blockDim.x + threadIdx.x; gv < P.NV; gv += gridDim.x * blockDim.x) {
-    const uint32_t d = find_draw(P.vbase, P.n_draws, gv);
-    if (P.any_bbox && P.dstats[d].hidden) continue;  // object culled: its clip vertices are never read
-    const DrawDesc& D = P.draws[d];
-    const float* __restrict__ in = D.verts + (size_t)(gv - __ldg(P.vbase + d)) * D.vstride;
-    const uint32_t L = D.L;
-    const float x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
-    float a[LT];
-#pragma unroll
-    for (int i = 0; i < LT; i++) a[i] = (i < (int)L) ? __ldg(in + 3 + i) : 0.0f;
-
-    float pos[4], out[LT];
-#pragma unroll
-    for (int i = 0; i < LT; i++) out[i] = 0.0f;
-    const float* u = D.vs_u;
-    switch (D.vs) {
-      case RF_VS_MVP:  // mat.rs:968-972 (ProjMat3::apply on a point: [p,1])
-#pragma unroll
-        for (int r = 0; r < 4; r++) pos[r] = dot4p(u + 4 * r, x, y, z, 1.0f);
-#pragma unroll
-        for (int i = 0; i < LT; i++) out[i] = a[i];
-        break;
-      case RF_VS_MVP_LINEARIZE:  // hello_tri.rs:13-17; color.rs:277-285
-#pragma unroll
-        for (int r = 0; r < 4; r++) pos[r] = dot4p(u + 4 * r, x, y, z, 1.0f);
-#pragma unroll
-        for (int i = 0; i < LT; i++) out[i] = (i < (int)L) ? powf(a[i], 2.2f) : 0.0f;
-        break;
-      case RF_VS_SOLIDS: {  // solids.rs:70-79
-        if (LT >= 3) {
-          const float nz = dot4p(u + 16 + 8, a[0], a[1], a[2], 0.0f);  // spin.apply(normal): w = 0
-          const float diffuse = fmaxf(nz + 0.2f, 0.2f) * 0.8f;
-#pragma unroll
-          for (int i = 0; i < 3; i++) out[i] = ((a[i] + 1.1f) * 0.45f) * diffuse;
-        }
-#pragma unroll
-        for (int r = 0; r < 4; r++) pos[r] = dot4p(u + 4 * r, x, y, z, 1.0f);
-        break;
-      }
-      default: {  // RF_VS_SPRITE, sprites.rs:40-45
-        float view[3];
-        const float vp[3] = {a[0] * 0.008f, (LT >= 2 ? a[1] : 0.0f) * 0.008f, 0.0f * 0.008f};
-#pragma unroll
-        for (int r = 0; r < 3; r++) view[r] = dot4p(u + 4 * r, x, y, z, 1.0f) + vp[r];
-#pragma unroll
-        for (int r = 0; r < 4; r++) pos[r] = dot4p(u + 16 + 4 * r, view[0], view[1], view[2], 1.0f);
-        out[0] = a[0];
-        if (LT >= 2) out[1] = a[1];
-        break;
-      }
-    }
-    const uint32_t oc = outcode(pos[0], pos[1], pos[2], pos[3]);
-    float* o = P.cv + (size_t)gv * CVS;
-    *reinterpret_cast<float4*>(o) = make_float4(pos[0], pos[1], pos[2], pos[3]);
-    float rest[CVS - 4];
-    rest[0] = __uint_as_float(oc);
-#pragma unroll
-    for (int i = 0; i < CVS - 5; i++) rest[1 + i] = (i < LT) ? out[i] : 0.0f;
-#pragma unroll
-    for (int q = 0; q < (CVS - 4) / 4; q++)
-      *reinterpret_cast<float4*>(o + 4 + 4 * q) = make_float4(rest[4 * q], rest[4 * q + 1], rest[4 * q + 2], rest[4 * q + 3]);
-  }
-}
-
 // =============================================================================================
 // K2: per primitive — assembly, clip, to_screen, cull, setup, edge walk -> span records.
 // One thread per input primitive; span/half storage is claimed with one warp-aggregated atomic
@@ -187,6 +119,116 @@ __device__ __forceinline__ void to_screen(const CVert<LT>& c, const float* __res
 #pragma unroll
   for (int i = 0; i < LT; i++) s.a[i] = ((persp_mask >> i) & 1u) ? zdiv(c.a[i], w) : c.a[i];
 }
+
+// K1 k_vertex: catalogue vertex shader, outcode, and the screen-space form of inside vertices.
+template <int LT>
+__global__ void __launch_bounds__(256) k_vertex(PassParams P) {
+  constexpr int CVS = Rec<LT>::CVS;
+  if (P.cstatus->poison) return;
+  for (uint32_t gv = blockIdx.x * blockDim.x + threadIdx.x; gv < P.NV; gv += gridDim.x * blockDim.x) {
+    const uint32_t d = find_draw(P.vbase, P.n_draws, gv);
+    if (P.any_bbox && P.dstats[d].hidden) continue;  // object culled: its clip vertices are never read
+    const DrawDesc& D = P.draws[d];
+    const float* __restrict__ in = D.verts + (size_t)(gv - __ldg(P.vbase + d)) * D.vstride;
+    const uint32_t L = D.L;
+    const float x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
+    float a[LT];
+#pragma unroll
+    for (int i = 0; i < LT; i++) a[i] = (i < (int)L) ? __ldg(in + 3 + i) : 0.0f;
+
+    float pos[4], out[LT];
+#pragma unroll
+    for (int i = 0; i < LT; i++) out[i] = 0.0f;
+    const float* u = D.vs_u;
+    switch (D.vs) {
+      case RF_VS_MVP:  // mat.rs:968-972 (ProjMat3::apply on a point: [p,1])
+#pragma unroll
+        for (int r = 0; r < 4; r++) pos[r] = dot4p(u + 4 * r, x, y, z, 1.0f);
+#pragma unroll
+        for (int i = 0; i < LT; i++) out[i] = a[i];
+        break;
+      case RF_VS_MVP_LINEARIZE:  // hello_tri.rs:13-17; color.rs:277-285
+#pragma unroll
+        for (int r = 0; r < 4; r++) pos[r] = dot4p(u + 4 * r, x, y, z, 1.0f);
+#pragma unroll
+        for (int i = 0; i < LT; i++) out[i] = (i < (int)L) ? powf(a[i], 2.2f) : 0.0f;
+        break;
+      case RF_VS_SOLIDS: {  // solids.rs:70-79
+        if (LT >= 3) {
+          const float nz = dot4p(u + 16 + 8, a[0], a[1], a[2], 0.0f);  // spin.apply(normal): w = 0
+          const float diffuse = fmaxf(nz + 0.2f, 0.2f) * 0.8f;
+#pragma unroll
+          for (int i = 0; i < 3; i++) out[i] = ((a[i] + 1.1f) * 0.45f) * diffuse;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) pos[r] = dot4p(u + 4 * r, x, y, z, 1.0f);
+        break;
+      }
+      default: {  // RF_VS_SPRITE, sprites.rs:40-45
+        float view[3];
+        const float vp[3] = {a[0] * 0.008f, (LT >= 2 ? a[1] : 0.0f) * 0.008f, 0.0f * 0.008f};
+#pragma unroll
+        for (int r = 0; r < 3; r++) view[r] = dot4p(u + 4 * r, x, y, z, 1.0f) + vp[r];
+#pragma unroll
+        for (int r = 0; r < 4; r++) pos[r] = dot4p(u + 16 + 4 * r, view[0], view[1], view[2], 1.0f);
+        out[0] = a[0];
+        if (LT >= 2) out[1] = a[1];
+        break;
+      }
+    }
+    const uint32_t oc = outcode(pos[0], pos[1], pos[2], pos[3]);
+    float* o = P.cv + (size_t)gv * CVS;
+    *reinterpret_cast<float4*>(o) = make_float4(pos[0], pos[1], pos[2], pos[3]);
+    float rest[CVS - 4];
+    rest[0] = __uint_as_float(oc);
+#pragma unroll
+    for (int i = 0; i < CVS - 5; i++) rest[1 + i] = (i < LT) ? out[i] : 0.0f;
+#pragma unroll
+    for (int q = 0; q < (CVS - 4) / 4; q++)
+      *reinterpret_cast<float4*>(o + 4 + 4 * q) = make_float4(rest[4 * q], rest[4 * q + 1], rest[4 * q + 2], rest[4 * q + 3]);
+    // Screen-space form of the vertex (prim.rs:62-88), once per vertex instead of once per use: to_screen is a pure function of
+    // the clip vertex and the draw, so a primitive whose three vertices are inside the frustum (no clipping) reads these.
+    constexpr int SVS = Rec<LT>::SVS;
+    float sw[SVS];
+#pragma unroll
+    for (int i = 0; i < SVS; i++) sw[i] = 0.0f;
+    if (!P.use_sv) continue;  // few uses per vertex somewhere in the pass: k_assemble transforms per primitive, nothing is stored here
+    if (oc == 0u) {
+      CVert<LT> c;
+#pragma unroll
+      for (int i = 0; i < 4; i++) c.p[i] = pos[i];
+#pragma unroll
+      for (int i = 0; i < LT; i++) c.a[i] = out[i];
+      c.oc = 0u;
+      SVert<LT> sc;
+      to_screen<LT>(c, D.vp, D.persp_mask, sc);
+      sw[0] = sc.x; sw[1] = sc.y; sw[2] = sc.z;
+#pragma unroll
+      for (int i = 0; i < LT; i++) sw[3 + i] = sc.a[i];
+    }
+    sw[3 + LT] = __uint_as_float(oc);
+    float* so = P.sv + (size_t)gv * SVS;
+#pragma unroll
+    for (int q = 0; q < SVS / 4; q++) *reinterpret_cast<float4*>(so + 4 * q) = make_float4(sw[4 * q], sw[4 * q + 1], sw[4 * q + 2], sw[4 * q + 3]);
+  }
+}
+
+template <int LT>
+__device__ __forceinline__ uint32_t load_sv(const float* __restrict__ sv, uint32_t gv, SVert<LT>& s) {
+  constexpr int SVS = Rec<LT>::SVS;
+  const float4* q = reinterpret_cast<const float4*>(sv + (size_t)gv * SVS);
+  float buf[SVS];
+#pragma unroll
+  for (int i = 0; i < SVS / 4; i++) {
+    float4 t = __ldg(q + i);
+    buf[4 * i] = t.x; buf[4 * i + 1] = t.y; buf[4 * i + 2] = t.z; buf[4 * i + 3] = t.w;
+  }
+  s.x = buf[0]; s.y = buf[1]; s.z = buf[2];
+#pragma unroll
+  for (int i = 0; i < LT; i++) s.a[i] = buf[3 + i];
+  return __float_as_uint(buf[3 + LT]);
+}
+
 
 // One trapezoid half: everything raster.rs:248-302 precomputes, minus the unused y lane.
 // lane order: 0 = x, 1 = z, 2.. = attr
@@ -398,7 +440,7 @@ __device__ __forceinline__ void line_walk(const PassParams& P, const TargetDesc&
 #define RF_CHUNK 32u
 #define RF_LONG_BLOCK 256u
 
-template <int LT>
+template <int LT, bool SV>  // SV: every draw of the pass carries RF_F_SV (k_vertex stored screen-space vertices)
 __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
   constexpr int QW = Rec<LT>::QW;
   if (P.cstatus->poison) return;
@@ -408,10 +450,13 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
     const uint32_t gp = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     const bool have = gp < P.NP;
     uint32_t d = 0, ntri = 0;
-    CVert<LT> c0, c1, c2;
+    CVert<LT> c0, c1;             // edge endpoints while they are clipped
+    SVert<LT> sv0, sv1, sv2;      // screen vertices of an unclipped primitive (from k_vertex)
+    uint32_t gv0 = 0, gv1 = 0, gv2 = 0;
     CVert<LT> poly[10], tmp[10];
-    bool clipped = false;
+    bool clipped = false;   // the primitive's vertices are in poly[] in clip space and go through to_screen at emission
     bool is_edge = false;
+    constexpr bool use_sv = SV;
     if (have) {
       d = find_draw(P.pbase, P.n_draws, gp);
       const DrawDesc& D = P.draws[d];
@@ -428,12 +473,23 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
         atomicOr(&P.status->error, RF_ERRBIT_INDEX_OOB);
       } else {
         const uint32_t vb = __ldg(P.vbase + d);
-        load_cv<LT>(P.cv, vb + i0, c0);
-        load_cv<LT>(P.cv, vb + i1, c1);
-        if ((c0.oc & c1.oc) != 0) ntri = 0;       // both outside one plane
-        else if ((c0.oc | c1.oc) == 0) ntri = 1;  // neither outside
-        else {
+        gv0 = vb + i0; gv1 = vb + i1; gv2 = gv0;
+        uint32_t oc0, oc1;
+        if (use_sv) {
+          oc0 = load_sv<LT>(P.sv, gv0, sv0); oc1 = load_sv<LT>(P.sv, gv1, sv1);
+          sv2 = sv0;  // unused third vertex
+        } else {
+          load_cv<LT>(P.cv, gv0, c0); load_cv<LT>(P.cv, gv1, c1);
+          oc0 = c0.oc; oc1 = c1.oc;
+        }
+        if ((oc0 & oc1) != 0) ntri = 0;       // both outside one plane
+        else if ((oc0 | oc1) == 0) {          // neither outside
           ntri = 1;
+          clipped = !use_sv;                  // with RF_F_SV the screen vertices k_vertex stored are used as they are
+        } else {
+          ntri = 1;
+          clipped = true;
+          if (use_sv) { load_cv<LT>(P.cv, gv0, c0); load_cv<LT>(P.cv, gv1, c1); }
           for (int pl = 0; pl < 6; pl++) {
             const uint32_t bit = 1u << pl;
             const bool a_in = (c0.oc & bit) == 0, b_in = (c1.oc & bit) == 0;
@@ -445,7 +501,7 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
             }
           }
         }
-        c2 = c0;  // unused third vertex
+        if (clipped) { poly[0] = c0; poly[1] = c1; poly[2] = c0; }  // emission reads poly[0], poly[t + 1], poly[t + 2] with t = 0
       }
     } else if (have) {
       const DrawDesc& D = P.draws[d];
@@ -455,15 +511,22 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
         atomicOr(&P.status->error, RF_ERRBIT_INDEX_OOB);  // prim.rs:17-19 panics
       } else {
         const uint32_t vb = __ldg(P.vbase + d);
-        load_cv<LT>(P.cv, vb + i0, c0);
-        load_cv<LT>(P.cv, vb + i1, c1);
-        load_cv<LT>(P.cv, vb + i2, c2);
-        const uint32_t all = c0.oc & c1.oc & c2.oc, any = c0.oc | c1.oc | c2.oc;
+        gv0 = vb + i0; gv1 = vb + i1; gv2 = vb + i2;
+        uint32_t oc0, oc1, oc2;
+        if (use_sv) {
+          oc0 = load_sv<LT>(P.sv, gv0, sv0); oc1 = load_sv<LT>(P.sv, gv1, sv1); oc2 = load_sv<LT>(P.sv, gv2, sv2);
+        } else {
+          load_cv<LT>(P.cv, gv0, poly[0]); load_cv<LT>(P.cv, gv1, poly[1]); load_cv<LT>(P.cv, gv2, poly[2]);
+          oc0 = poly[0].oc; oc1 = poly[1].oc; oc2 = poly[2].oc;
+        }
+        const uint32_t all = oc0 & oc1 & oc2, any = oc0 | oc1 | oc2;
         if (all != 0) ntri = 0;          // Status::Hidden, clip.rs:245-267
-        else if (any == 0) ntri = 1;     // Status::Visible
-        else {
+        else if (any == 0) {             // Status::Visible
+          ntri = 1;
+          clipped = !use_sv;             // with RF_F_SV the screen vertices k_vertex stored are used as they are; else poly[0..2]
+        } else {
           clipped = true;
-          poly[0] = c0; poly[1] = c1; poly[2] = c2;
+          if (use_sv) { load_cv<LT>(P.cv, gv0, poly[0]); load_cv<LT>(P.cv, gv1, poly[1]); load_cv<LT>(P.cv, gv2, poly[2]); }
           const int n = clip_polygon<LT>(poly, tmp);
           ntri = n >= 3 ? (uint32_t)(n - 2) : 0u;  // fan (p0, pk, pk+1), clip.rs:375-394
         }
@@ -484,9 +547,7 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
           to_screen<LT>(poly[t + 1], D.vp, D.persp_mask, s[1]);
           to_screen<LT>(poly[t + 2], D.vp, D.persp_mask, s[2]);
         } else {
-          to_screen<LT>(c0, D.vp, D.persp_mask, s[0]);
-          to_screen<LT>(c1, D.vp, D.persp_mask, s[1]);
-          to_screen<LT>(c2, D.vp, D.persp_mask, s[2]);
+          s[0] = sv0; s[1] = sv1; s[2] = sv2;
         }
         // Tri::winding geom/prim.rs:288-294 ; Context::face_cull ctx.rs:95-101
         const float abx = s[1].x - s[0].x, aby = s[1].y - s[0].y;
@@ -501,8 +562,11 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
         if (emit && P.sdepth != nullptr) {
           // Render::depth: prim.rs:21-23 for triangles (clip-space z, left to right, then / 3.0); f32::INFINITY for edges
           if (is_edge) depth = __int_as_float(0x7F800000);
-          else if (clipped) depth = ((poly[0].p[2] + poly[t + 1].p[2]) + poly[t + 2].p[2]) / 3.0f;
-          else depth = ((c0.p[2] + c1.p[2]) + c2.p[2]) / 3.0f;
+          else if (clipped) depth = ((poly[0].p[2] + poly[t + 1].p[2]) + poly[t + 2].p[2]) / 3.0f;  // also the unclipped triangle without RF_F_SV
+          else {  // unclipped: clip-space z of the three vertices
+            constexpr int CVS = Rec<LT>::CVS;
+            depth = ((__ldg(P.cv + (size_t)gv0 * CVS + 2) + __ldg(P.cv + (size_t)gv1 * CVS + 2)) + __ldg(P.cv + (size_t)gv2 * CVS + 2)) / 3.0f;
+          }
         }
       }
       const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
