@@ -88,6 +88,12 @@ unsafe extern "C" {
     pub fn rf_mesh_destroy(m: *mut rf_mesh);
     pub fn rf_render(ctx: *mut rf_ctx, target: *mut rf_target, draw: *const rf_draw, stats_out: *mut rf_stats) -> rf_status;
     pub fn rf_render_frames(ctx: *mut rf_ctx, targets: *const *mut rf_target, n_frames: u32, draw: *const rf_draw, vs_uniforms: *const f32) -> rf_status;
+    pub fn rf_render_many(ctx: *mut rf_ctx, target: *mut rf_target, draws: *const rf_draw, n_draws: u32) -> rf_status;
+    pub fn rf_ctx_peer_export(ctx: *mut rf_ctx, ipc_handle_out: *mut u8, devptr_out: *mut *mut c_void) -> rf_status;
+    pub fn rf_ctx_peer_attach(ctx: *mut rf_ctx, world: u32, rank: u32, ipc_handles: *const u8, devptrs: *const *mut c_void) -> rf_status;
+    pub fn rf_target_peer_export(ctx: *mut rf_ctx, t: *mut rf_target, ipc_handle_out: *mut u8, devptr_out: *mut *mut c_void) -> rf_status;
+    pub fn rf_target_peer_attach(ctx: *mut rf_ctx, t: *mut rf_target, world: u32, rank: u32, ipc_handles: *const u8, devptrs: *const *mut c_void) -> rf_status;
+    pub fn rf_ctx_replays(ctx: *mut rf_ctx, out: *mut u64) -> rf_status;
     pub fn rf_flush(ctx: *mut rf_ctx) -> rf_status;
     pub fn rf_sync(ctx: *mut rf_ctx) -> rf_status;
     pub fn rf_ctx_stats(ctx: *mut rf_ctx, out: *mut rf_stats, reset: c_int) -> rf_status;
