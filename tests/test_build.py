@@ -23,6 +23,31 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert lib.rf_abi_version() == 1
 
 
+def test_rust_sys_crate_and_ctypes_structs_follow_the_header():
+    """The Rust -sys crate cannot be compiled here (no cargo): at least every header symbol must be declared in it, and the
+    ctypes mirrors of rf_draw / rf_stats must have the header's field order."""
+    header = open(os.path.join(ROOT, "include", "retrofire_b200.h")).read()
+    rust = open(os.path.join(ROOT, "rust", "retrofire-b200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"^(?:rf_status|void\*?|const char\*|uint32_t)\s+(rf_[a-z_0-9]+)\s*\(", header, re.M))
+    assert all(f"fn {name}(" in rust for name in declared), [n for n in declared if f"fn {n}(" not in rust]
+
+    def fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            for part in decl.split(","):
+                m = re.search(r"(\w+)\s*(?:\[[^\]]*\])?\s*$", part.strip())
+                if m and part.strip():
+                    names.append(m.group(1))
+        return names
+
+    assert fields("rf_draw") == [f[0] for f in _ffi.RfDraw._fields_]
+    assert fields("rf_stats") == [f[0] for f in _ffi.RfStats._fields_]
+    for name in fields("rf_draw") + fields("rf_stats"):
+        assert re.search(r"pub %s:" % name, rust), name
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     import torch
     if torch.cuda.is_available():
