@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librf_b200.so")
+LIB_PATH = os.environ.get("RF_B200_LIB") or os.path.join(HERE, "librf_b200.so")   # RF_B200_LIB: a tuning build (build.build_variant)
 
 RF_MAX_ATTR_LANES = 8
 RF_VS_UNIFORM_F32 = 32

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librf_b200.so")
 SOURCES = ["rf_api.cu"]
-HEADERS = ["rf_device.cuh", "rf_geometry.cuh", "rf_raster.cuh", os.path.join("..", "..", "include", "retrofire_b200.h")]
+HEADERS = ["rf_device.cuh", "rf_geometry.cuh", "rf_raster.cuh", "rf_order.cuh", "rf_peer.cuh", os.path.join("..", "..", "include", "retrofire_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -45,6 +45,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
         subprocess.run(cmd, check=True, cwd=CSRC)
     return OUT
+
+
+def build_variant(name: str, defines: dict) -> str:
+    """Tuning aid: the same library with -D overrides of the #ifndef-guarded constants, as retrofire_b200/_variants/<name>.so.
+    `RF_B200_LIB=<path>` makes _ffi load it (A/B timing of two builds inside one GPU session, see scratch/ab.sh)."""
+    vdir = os.path.join(HERE, "_variants")
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, f"{name}.so")
+    cmd = [nvcc()] + NVCC_FLAGS + [f"-D{k}={v}" for k, v in defines.items()] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return out
 
 
 def ptx(path: str) -> str:

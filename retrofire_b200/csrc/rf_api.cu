@@ -275,7 +275,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   auto blocks = [&](size_t n, int bs, int per_sm) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + bs - 1) / bs, (size_t)sm * per_sm)); };
   const int prof = c->profile;
   s.profiled = prof;
-  const unsigned raster_blocks = sm * 7;
+  const unsigned raster_blocks = sm * RF_RASTER_MIN_BLOCKS;
   if (prof == 2) {  // serialised on one stream, an event between every pair of kernels
     int ek = 0;
     auto mark = [&]() { cudaEventRecord(s.ev_k[ek++], st); };

@@ -428,7 +428,9 @@ __device__ __forceinline__ void line_walk(const PassParams& P, const TargetDesc&
 }
 
 // Triangles with at most this many scanlines are walked inline by k_setup; taller ones go to k_walk in chunks.
+#ifndef RF_INLINE_ROWS
 #define RF_INLINE_ROWS 12u
+#endif
 
 // =============================================================================================
 // K2a k_assemble: one thread per input primitive — assembly (render.rs:168-172), status / Sutherland–
@@ -617,8 +619,11 @@ __global__ void __launch_bounds__(128) k_assemble(PassParams P) {
 // sums): a triangle record, its span range, its (triangle x tile) bin entries, and either walks
 // its scanlines inline (few rows) or cuts them into <= 32-row chunks for k_walk.
 // =============================================================================================
+#ifndef RF_SETUP_MIN_BLOCKS
+#define RF_SETUP_MIN_BLOCKS 4
+#endif
 template <int LT>
-__global__ void __launch_bounds__(128, LT == 3 ? 4 : 3) k_setup(PassParams P) {
+__global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setup(PassParams P) {
   constexpr int NL = 2 + LT, NV = 1 + LT;
   constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS, QW = Rec<LT>::QW;
   using TR = TriRec<LT>;

@@ -12,8 +12,12 @@
 // =============================================================================================
 #define RF_SORT_SMALL 1024u   // per-warp shared-memory sort capacity (entries)
 #define RF_SORT_BIG 16384u    // per-block (large smem) sort run; deeper bins are merged from runs of this size
+#ifndef RF_HEAVY_BIN
 #define RF_HEAVY_BIN 64u      // tiles are rasterised longest-first in three classes: >= RF_HEAVIEST_BIN, >= RF_HEAVY_BIN, rest
+#endif
+#ifndef RF_HEAVIEST_BIN
 #define RF_HEAVIEST_BIN 160u
+#endif
 #define RF_SLICES 4u          // row slices of a heaviest tile (RF_TILE / RF_SLICES rows each); task word = tile | (slice+1) << 28
 
 __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
@@ -408,17 +412,30 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
 
 // Average piece length (pixels) above which a batch of pieces is walked one piece per lane;
 // below it the batch is expanded to one FRAGMENT per lane (each lane does k sequential adds).
-#define RF_SPAN_MODE_MIN_AVG 6u
-#define RF_FRAG_QUEUE (RF_SPAN_MODE_MIN_AVG * 32u)  // fragment-mode batches hold fewer fragments than this
+// Measured (scratch/ab.sh): 6 is best at 3 varying lanes (bunny, sprites), 4 at 5 or more (crates: +5.6 %), where a
+// fragment carries more words through the queue.
+#ifndef RF_SPAN_MODE_MIN_AVG_3
+#define RF_SPAN_MODE_MIN_AVG_3 6u
+#endif
+#ifndef RF_SPAN_MODE_MIN_AVG_5
+#define RF_SPAN_MODE_MIN_AVG_5 4u
+#endif
+template <int LT> struct RasterTune {
+  static constexpr uint32_t MIN_AVG = LT == 3 ? RF_SPAN_MODE_MIN_AVG_3 : RF_SPAN_MODE_MIN_AVG_5;
+  static constexpr uint32_t FRAG_QUEUE = MIN_AVG * 32u;  // fragment-mode batches hold fewer fragments than this
+};
 
 template <int LT> struct RasterSmem {
   static constexpr int TILE_WORDS = RF_TILE * RF_TILE_PITCH;
-  static constexpr int WARP_WORDS = TILE_WORDS + (2 + LT) * (int)RF_FRAG_QUEUE;  // depth tile, queue {z, attr[LT], pix}
+  static constexpr int WARP_WORDS = TILE_WORDS + (2 + LT) * (int)RasterTune<LT>::FRAG_QUEUE;  // depth tile, queue {z, attr[LT], pix}
   static constexpr size_t BYTES = (size_t)RF_RASTER_WARPS * WARP_WORDS * 4;
 };
 
+#ifndef RF_RASTER_MIN_BLOCKS
+#define RF_RASTER_MIN_BLOCKS 7   // resident blocks per SM at 3 varying lanes (72 registers); the persistent grid is this many per SM
+#endif
 template <int LT, bool PEER>
-__global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raster(PassParams P) {
+__global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_BLOCKS : 6) k_raster(PassParams P) {
   constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW;
   constexpr int NV = 1 + LT;
   extern __shared__ uint32_t s_raster[];
@@ -428,8 +445,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
   // so passing fragments store their pixel straight to the framebuffer. __syncwarp() between dependency
   // rounds orders two writes to one pixel; untouched pixels are never read or written.
   float* sz = reinterpret_cast<float*>(s_raster + (size_t)warp * RasterSmem<LT>::WARP_WORDS);
-  float* qv = sz + RasterSmem<LT>::TILE_WORDS;                                  // [1+LT][RF_FRAG_QUEUE]
-  uint32_t* qp = reinterpret_cast<uint32_t*>(qv + (1 + LT) * RF_FRAG_QUEUE);    // [RF_FRAG_QUEUE] pixel index | owner lane << 16
+  float* qv = sz + RasterSmem<LT>::TILE_WORDS;                                  // [1+LT][FRAG_QUEUE]
+  uint32_t* qp = reinterpret_cast<uint32_t*>(qv + (1 + LT) * RasterTune<LT>::FRAG_QUEUE);    // [FRAG_QUEUE] pixel index | owner lane << 16
   const uint32_t n_work = P.status->n_work, n_heaviest = P.status->n_work_heaviest, n_heavy = n_heaviest + P.status->n_work_heavy;
 
   for (;;) {
@@ -588,7 +605,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
         const uint32_t f_incl = warp_scan_incl(pn, lane);
         const uint32_t n_frags = __shfl_sync(0xFFFFFFFFu, f_incl, 31);
 
-        if (n_frags >= RF_SPAN_MODE_MIN_AVG * (uint32_t)__popc(vmask)) {
+        if (n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask)) {
           // ================= span mode: one piece per lane, walked serially =================
           // dependencies: earlier lanes on the same row whose x-range overlaps mine
           uint32_t dep = 0;
@@ -664,7 +681,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
               if (k < pn) {
                 const uint32_t q = qstart + k;
 #pragma unroll
-                for (int i = 0; i < NV; i++) { qv[i * RF_FRAG_QUEUE + q] = v[i]; v[i] = v[i] + dv[i]; }
+                for (int i = 0; i < NV; i++) { qv[i * RasterTune<LT>::FRAG_QUEUE + q] = v[i]; v[i] = v[i] + dv[i]; }
                 qp[q] = (pix0 + k) | lane << 16;
               }
             }
@@ -687,7 +704,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? 7 : 6) k_raste
               uint32_t pw = 0;
               if (fvalid) {
 #pragma unroll
-                for (int i = 0; i < NV; i++) fv[i] = qv[i * RF_FRAG_QUEUE + f];
+                for (int i = 0; i < NV; i++) fv[i] = qv[i * RasterTune<LT>::FRAG_QUEUE + f];
                 pw = qp[f];
               } else {
 #pragma unroll
