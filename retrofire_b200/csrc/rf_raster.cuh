@@ -370,12 +370,40 @@ __device__ __forceinline__ uint32_t* color_px(uint32_t* gc, uint32_t gw, uint32_
   return gc + (size_t)row * gw + (idx - row * RF_TILE_PITCH);
 }
 
+// The per-warp shared-memory region (depth tile + fragment queue) addressed by an explicit 32-bit shared-window address.
+// With a generic pointer ptxas re-derives the window base inside the per-fragment loops to save a register (two S2R —
+// SR_CgaCtaId, SR_TID.X — plus address arithmetic per access); the volatile cvta below pins the base in a register.
+#ifndef RF_SMEM_ASM
+#define RF_SMEM_ASM 1
+#endif
+struct WarpSmem {
+#if RF_SMEM_ASM
+  uint32_t a;
+  __device__ __forceinline__ explicit WarpSmem(const void* p) {
+    unsigned long long t;
+    asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(t) : "l"(p));
+    a = (uint32_t)t;
+  }
+  __device__ __forceinline__ float ldf(uint32_t w) const { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a + w * 4u) : "memory"); return v; }
+  __device__ __forceinline__ uint32_t ldu(uint32_t w) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + w * 4u) : "memory"); return v; }
+  __device__ __forceinline__ void stf(uint32_t w, float v) const { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + w * 4u), "f"(v) : "memory"); }
+  __device__ __forceinline__ void stu(uint32_t w, uint32_t v) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + w * 4u), "r"(v) : "memory"); }
+#else
+  float* p;
+  __device__ __forceinline__ explicit WarpSmem(const void* q) : p(reinterpret_cast<float*>(const_cast<void*>(q))) {}
+  __device__ __forceinline__ float ldf(uint32_t w) const { return p[w]; }
+  __device__ __forceinline__ uint32_t ldu(uint32_t w) const { return reinterpret_cast<const uint32_t*>(p)[w]; }
+  __device__ __forceinline__ void stf(uint32_t w, float v) const { p[w] = v; }
+  __device__ __forceinline__ void stu(uint32_t w, uint32_t v) const { reinterpret_cast<uint32_t*>(p)[w] = v; }
+#endif
+};
+
 template <int LT>
-__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t* gc, uint32_t gw, float* sz, uint32_t idx, const float* v,
+__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t* gc, uint32_t gw, WarpSmem sz, uint32_t idx, const float* v,
                                                      uint32_t pmask, uint32_t dtest, bool cwrite, bool dwrite) {
   const float z = v[0];
   if (dtest != RF_DEPTH_NONE) {  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
-    const float curr = sz[idx];
+    const float curr = sz.ldf(idx);
     const bool pass = dtest == RF_DEPTH_LESS ? (curr < z) : (dtest == RF_DEPTH_EQUAL ? (curr == z) : (curr > z));
     if (!pass) return 0u;
   }
@@ -389,7 +417,7 @@ __device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t
   }
   uint32_t r = 0, g = 0, bl = 0, a = 0;
   if (!shade_fragment<LT>(D, fs, var, r, g, bl, a)) return 0u;  // discard: no writes at all
-  if (dwrite) sz[idx] = z;
+  if (dwrite) sz.stf(idx, z);
   if (cwrite) { *color_px(gc, gw, idx) = pack_pixel(fmt, r, g, bl, a); return 1u; }
   return 0u;
 }
@@ -397,15 +425,15 @@ __device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t
 // Specialisation for the default Context (depth test Less, colour and depth writes on, ctx.rs:104-127) and a
 // compile-time fragment shader / perspective mask: straight-line code, no state decoding.
 template <int LT, int FS, uint32_t PMASK>
-__device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, uint32_t fmt, uint32_t* gc, uint32_t gw, float* sz, uint32_t idx, const float* v) {
+__device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, uint32_t fmt, uint32_t* gc, uint32_t gw, WarpSmem sz, uint32_t idx, const float* v) {
   const float z = v[0];
-  if (!(sz[idx] < z)) return 0u;
+  if (!(sz.ldf(idx) < z)) return 0u;
   float var[LT];
 #pragma unroll
   for (int i = 0; i < LT; i++) var[i] = ((PMASK >> i) & 1u) ? zdiv(v[1 + i], z) : v[1 + i];
   uint32_t r = 0, g = 0, bl = 0, a = 0;
   if (!shade_fragment<LT>(D, (uint32_t)FS, var, r, g, bl, a)) return 0u;
-  sz[idx] = z;
+  sz.stf(idx, z);
   *color_px(gc, gw, idx) = pack_pixel(fmt, r, g, bl, a);
   return 1u;
 }
@@ -447,6 +475,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
   float* sz = reinterpret_cast<float*>(s_raster + (size_t)warp * RasterSmem<LT>::WARP_WORDS);
   float* qv = sz + RasterSmem<LT>::TILE_WORDS;                                  // [1+LT][FRAG_QUEUE]
   uint32_t* qp = reinterpret_cast<uint32_t*>(qv + (1 + LT) * RasterTune<LT>::FRAG_QUEUE);    // [FRAG_QUEUE] pixel index | owner lane << 16
+  const WarpSmem wsm(sz);  // the same region for the per-fragment accesses: depth at [idx], queue behind it
+  constexpr uint32_t QV0 = RasterSmem<LT>::TILE_WORDS, QP0 = QV0 + (1 + LT) * RasterTune<LT>::FRAG_QUEUE;
   const uint32_t n_work = P.status->n_work, n_heaviest = P.status->n_work_heaviest, n_heavy = n_heaviest + P.status->n_work_heavy;
 
   for (;;) {
@@ -643,19 +673,19 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
               const uint32_t base = py * RF_TILE_PITCH + pxs;
               if (smode == 4) {  // default Context + FS_TEX_CLAMP_LIT (crates): straight-line fragment code
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, gc, T.w, sz, base + k, v);
+                  my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, gc, T.w, wsm, base + k, v);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                 }
               } else if (smode == 2) {
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, sz, base + k, v);
+                  my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, wsm, base + k, v);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                 }
               } else {
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment<LT>(D, fs, T.fmt, gc, T.w, sz, base + k, v, pmask, dtest, cwrite, dwrite);
+                  my_o += process_fragment<LT>(D, fs, T.fmt, gc, T.w, wsm, base + k, v, pmask, dtest, cwrite, dwrite);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
                 }
@@ -681,8 +711,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
               if (k < pn) {
                 const uint32_t q = qstart + k;
 #pragma unroll
-                for (int i = 0; i < NV; i++) { qv[i * RasterTune<LT>::FRAG_QUEUE + q] = v[i]; v[i] = v[i] + dv[i]; }
-                qp[q] = (pix0 + k) | lane << 16;
+                for (int i = 0; i < NV; i++) { wsm.stf(QV0 + i * RasterTune<LT>::FRAG_QUEUE + q, v[i]); v[i] = v[i] + dv[i]; }
+                wsm.stu(QP0 + q, (pix0 + k) | lane << 16);
               }
             }
           }
@@ -704,8 +734,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
               uint32_t pw = 0;
               if (fvalid) {
 #pragma unroll
-                for (int i = 0; i < NV; i++) fv[i] = qv[i * RasterTune<LT>::FRAG_QUEUE + f];
-                pw = qp[f];
+                for (int i = 0; i < NV; i++) fv[i] = wsm.ldf(QV0 + i * RasterTune<LT>::FRAG_QUEUE + f);
+                pw = wsm.ldu(QP0 + f);
               } else {
 #pragma unroll
                 for (int i = 0; i < NV; i++) fv[i] = 0.0f;
@@ -725,10 +755,10 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
               const DrawDesc& D = UNI ? Du : P.draws[fdraw];
               uint32_t wrote = 0;
               auto one = [&]() -> uint32_t {
-                if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, sz, pix, fv);
-                if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, T.fmt, gc, T.w, sz, pix, fv);
-                if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, gc, T.w, sz, pix, fv);
-                return process_fragment<LT>(D, fs, T.fmt, gc, T.w, sz, pix, fv, pmask, dtest, cwrite, dwrite);
+                if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, wsm, pix, fv);
+                if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, T.fmt, gc, T.w, wsm, pix, fv);
+                if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, gc, T.w, wsm, pix, fv);
+                return process_fragment<LT>(D, fs, T.fmt, gc, T.w, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
               };
               if (__all_sync(0xFFFFFFFFu, earlier == 0)) {
                 if (fvalid) wrote = one();
