@@ -21,6 +21,7 @@
 #define RF_F_DTEST_MASK 0x3u
 #define RF_F_CWRITE 0x10u
 #define RF_F_DWRITE 0x20u
+#define RF_F_RASTER_STATE ((RF_F_DTEST_MASK << RF_F_DTEST_SHIFT) | RF_F_CWRITE | RF_F_DWRITE)  // what the fragment stage reads
 #define RF_F_SV 0x200u      // vertices are shared by enough primitives: k_vertex also stores their screen-space form
 #define RF_F_BBOX 0x100u    // skip the draw when its bounding box is Hidden (scene.rs:81-87)
 #define RF_F_DSORT_SHIFT 6   // Context::depth_sort (ctx.rs:39): RF_SORT_*

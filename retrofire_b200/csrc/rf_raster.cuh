@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
           if (uni) {
             const DrawDesc& Dq = P.draws[d0];
             const uint32_t dflt = RF_DEPTH_LESS << RF_F_DTEST_SHIFT | RF_F_CWRITE | RF_F_DWRITE;
-            const bool is_default = has_depth && (Dq.flags & ~RF_F_CULL_MASK) == dflt;
+            const bool is_default = has_depth && (Dq.flags & RF_F_RASTER_STATE) == dflt;  // the other flag bits concern earlier stages
             if (is_default && Dq.fs == RF_FS_TEX_CLAMP_LIT && Dq.persp_mask == 0x1Fu && LT >= 5) smode = 4;
             else if (is_default && Dq.fs == RF_FS_COLOR3F && Dq.persp_mask == 0u && LT >= 3) smode = 2;
           }
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
           else {
             const DrawDesc& Dq = P.draws[d0];
             const uint32_t dflt = RF_DEPTH_LESS << RF_F_DTEST_SHIFT | RF_F_CWRITE | RF_F_DWRITE;
-            const bool is_default = has_depth && (Dq.flags & ~RF_F_CULL_MASK) == dflt;
+            const bool is_default = has_depth && (Dq.flags & RF_F_RASTER_STATE) == dflt;  // the other flag bits concern earlier stages
             if (is_default && Dq.fs == RF_FS_COLOR3F && Dq.persp_mask == 0u && LT >= 3) frag_loop(std::integral_constant<int, 2>{});
             else if (is_default && Dq.fs == RF_FS_SPRITE_DISC && Dq.persp_mask == 0x3u) frag_loop(std::integral_constant<int, 3>{});
             else if (is_default && Dq.fs == RF_FS_TEX_CLAMP_LIT && Dq.persp_mask == 0x1Fu && LT >= 5) frag_loop(std::integral_constant<int, 4>{});
