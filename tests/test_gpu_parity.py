@@ -270,6 +270,31 @@ def test_wireframe_over_solid_and_front_cull(device, oracle):
     assert_parity(got, run_oracle(oracle, culled), name="front-cull-lines")
 
 
+def test_indexed_mesh_paths_screen_vertices_per_vertex(device, oracle):
+    """Indexed meshes (>= 2 uses per vertex) take the k_vertex -> k_assemble<LT, true> path (to_screen once per vertex):
+    alone, depth-sorted without a depth test (Render::depth of unclipped triangles reads clip-space z), pushed through the
+    near plane so that part of the mesh is clipped, with a bounding box, and mixed with a vertex-per-triangle soup in one
+    pass (which switches the whole pass back to per-primitive to_screen)."""
+    import dataclasses
+    mesh = scenes.bunny(subdiv=0, w=800, h=600)
+    check(device, oracle, mesh)
+    d = mesh.draws[0]
+    nod = rf.Context(depth_sort=rf.DepthSort.BackToFront, depth_test=None, face_cull=None)
+    check(device, oracle, dataclasses.replace(mesh, name="bunny-sorted", ctx=nod, draws=[dataclasses.replace(
+        d, depth_sort=int(rf.DepthSort.BackToFront), depth_test=0, face_cull=0)]))
+    from retrofire_b200 import mathx as mx
+    m0 = np.asarray(d.uniform, np.float32).ravel()[:16].reshape(4, 4)
+    for tz in (2.0, 2.4):    # towards the camera: 2.0 crosses the side planes, 2.4 also the near plane (129 vertices behind it)
+        near = dataclasses.replace(d, uniform=mx.then(mx.translate3(0.0, 0.0, tz), m0))
+        got = run_gpu(device, dataclasses.replace(mesh, name="bunny-near", draws=[near]))
+        assert_parity(got, run_oracle(oracle, dataclasses.replace(mesh, draws=[near])), name=f"bunny-near-{tz}")
+        assert got[2].frags.i > 50000
+    lo, hi = d.verts[:, :3].min(0), d.verts[:, :3].max(0)
+    check(device, oracle, dataclasses.replace(mesh, name="bunny-bbox", draws=[dataclasses.replace(d, bbox=np.stack([lo, hi]))]))
+    soup = scenes.random_soup(1500, 800, 600, seed=3, lanes_kind="color3", big=True)
+    check(device, oracle, dataclasses.replace(mesh, name="bunny+soup", draws=[d] + soup.draws + [d]))
+
+
 def test_object_culling_on_the_device(device, oracle):
     """SURVEY 8f-3: the scene loop of crates.rs:100-131 with `BBox::visibility` (scene.rs:81-87) evaluated on the device.
     All 170 objects are submitted with their bounding boxes; hidden ones are skipped as if render() had not been called
