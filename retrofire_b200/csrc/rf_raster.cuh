@@ -664,6 +664,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
             const bool is_default = has_depth && (Dq.flags & RF_F_RASTER_STATE) == dflt;  // the other flag bits concern earlier stages
             if (is_default && Dq.fs == RF_FS_TEX_CLAMP_LIT && Dq.persp_mask == 0x1Fu && LT >= 5) smode = 4;
             else if (is_default && Dq.fs == RF_FS_COLOR3F && Dq.persp_mask == 0u && LT >= 3) smode = 2;
+            else if (is_default && Dq.fs == RF_FS_CHECKER && Dq.persp_mask == 0x3u && Dq.L == 2u && LT == 5) smode = 5;
           }
           uint32_t done = ~vmask;
           bool pending = valid;
@@ -682,6 +683,12 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
                   my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, wsm, base + k, v);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
+                }
+              } else if (LT == 5 && smode == 5) {  // default Context + FS_CHECKER on two perspective uv lanes (the crates floor): z, u, v only
+                for (uint32_t k = 0; k < pn; k++) {
+                  my_o += process_fragment_fixed<LT, RF_FS_CHECKER, 0x3u>(D, T.fmt, gc, T.w, wsm, base + k, v);
+#pragma unroll
+                  for (int i = 0; i < 3; i++) v[i] = v[i] + dv[i];
                 }
               } else {
                 for (uint32_t k = 0; k < pn; k++) {
