@@ -174,6 +174,11 @@ rf_status rf_target_download_color(rf_ctx* ctx, rf_target* t, void* host, size_t
 rf_status rf_target_upload_depth(rf_ctx* ctx, rf_target* t, const float* host, size_t stride_elems);
 rf_status rf_target_download_depth(rf_ctx* ctx, rf_target* t, float* host, size_t stride_elems);
 /* Pinned host memory for Buf2 storage, so that uploads/downloads DMA directly (no staging copy). */
+/* Opt-in: vertex/index arrays that live in page-locked memory (rf_host_alloc) are read by DMA AFTER rf_render has
+ * returned; the caller must leave them unchanged until the next rf_flush or rf_sync returns (the same contract as
+ * rf_target_download_color_async in the other direction). Default off: rf_render returns only when its arrays
+ * have been read, like the borrows of render(). Pageable arrays are always copied during the call. */
+rf_status rf_ctx_set_geometry_async(rf_ctx* ctx, int on);
 rf_status rf_host_alloc(size_t bytes, void** out);
 void rf_host_free(void* p);
 /* Asynchronous download (4-byte formats): ordered after the queued draws on the ctx stream; the

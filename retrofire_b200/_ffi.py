@@ -85,6 +85,7 @@ SYMBOLS = {
     "rf_ctx_destroy": (None, [_P]),
     "rf_last_error": (C.c_char_p, [_P]),
     "rf_ctx_set_row_band": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "rf_ctx_set_geometry_async": (C.c_int, [_P, C.c_int]),
     "rf_target_create": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(_P)]),
     "rf_target_destroy": (None, [_P]),
     "rf_target_clear": (C.c_int, [_P, _P, C.POINTER(C.c_uint8), C.POINTER(C.c_float)]),

@@ -288,6 +288,10 @@ class Device:
     def __exit__(self, *a):
         self.close()
 
+    def set_geometry_async(self, on: bool = True):
+        """Page-locked geometry arrays (pinned_empty) are read after render() returns: leave them alone until flush()/sync()."""
+        self._check(self.lib.rf_ctx_set_geometry_async(self.h, int(on)))
+
     def set_row_band(self, y0: int, y1: int):
         self._check(self.lib.rf_ctx_set_row_band(self.h, y0, y1))
 

@@ -30,6 +30,7 @@
 
 namespace {
 
+constexpr size_t kTileArrays = 5 + RF_SLICES + 1;  // tile_cnt, tile_off, tile_fill, worklist, worklist_big, worklist_heavy[(RF_SLICES + 1) * n_tiles]
 constexpr int kSlots = 3;          // passes that may be in flight before the oldest is validated
 constexpr uint32_t kMaxTargetDim = 32768;
 
@@ -96,6 +97,8 @@ struct PassSlot {
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   cudaEvent_t ev_k[RF_N_KERNELS + 1] = {};  // boundaries between the pass kernels (profiling mode)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // binning chain runs on the ctx's side stream
+  cudaEvent_t ev_direct = nullptr;  // last asynchronous upload of page-locked caller geometry into d_direct (rf_ctx_set_geometry_async)
+  bool direct_async = false;
   int profiled = 0;
   uint32_t NV = 0, NP = 0, n_tiles = 0, lt = 0;
   uint32_t n_launches = 0;
@@ -138,6 +141,7 @@ struct rf_ctx {
   cudaStream_t copy_in = nullptr; // H2D of page-locked caller geometry during rf_render
   cudaStream_t copy = nullptr;   // asynchronous downloads: D2H overlaps the next pass
   cudaEvent_t ev_copy = nullptr;
+  bool geometry_async = false;  // rf_ctx_set_geometry_async: page-locked caller geometry is not waited for inside rf_render
   cudaStream_t side = nullptr;   // binning chain (k_bin_alloc/scatter/sort) overlaps the span chain (k_edge_ckpt/k_walk/k_ckpt)
   bool own_stream = false;
   int sm_count = 148;
@@ -348,7 +352,7 @@ rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const Aren
     c->cap_chunks = w.chunks;
   }
   if (w.tall > c->cap_tall) { if (!c->talllist.reserve(w.tall * 4)) return fail(c, RF_E_NOMEM, "tall list"); c->cap_tall = w.tall; }
-  if (!c->tiles.reserve(n_tiles * 6 * 4 + 64)) return fail(c, RF_E_NOMEM, "tile arrays");
+  if (!c->tiles.reserve(n_tiles * kTileArrays * 4 + 64)) return fail(c, RF_E_NOMEM, "tile arrays");
   if (!c->cursors.reserve(64)) return fail(c, RF_E_NOMEM, "cursors");
   return RF_OK;
 }
@@ -395,7 +399,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
                   std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), std::max<size_t>(c->capw_stris, (size_t)8 << 20),
                   std::max<size_t>(c->cap_entries, (size_t)1 << 20), std::max<size_t>(c->cap_long, (size_t)1 << 19),
                   std::max<size_t>(c->cap_chunks, (size_t)1 << 20), std::max<size_t>(c->cap_tall, (size_t)1 << 18)};
-  need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->sv.cap < (size_t)nv * words_sv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * 24 + 64 ||
+  need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->sv.cap < (size_t)nv * words_sv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * kTileArrays * 4 + 64 ||
               !arenas_cover(c, want) || c->cursors.cap < 64;
   // Context::depth_sort: bound on the pass's screen triangles (a clipped triangle fans into <= 7) and the sort buffers
   uint64_t order_bound = 0;
@@ -507,6 +511,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
     s.in_flight = true;
     return RF_OK;
   }
+  if (s.direct_async) RF_CUDA(c, cudaStreamWaitEvent(st, s.ev_direct, 0));  // asynchronous uploads of page-locked geometry
   if (s.geom_len) RF_CUDA(c, cudaMemcpyAsync(s.d_geom.p, s.geom.p, s.geom_len, cudaMemcpyHostToDevice, st));
   RF_CUDA(c, cudaMemsetAsync(s.d_status.p, 0, sizeof(PassStatus), st));
   RF_CUDA(c, cudaMemsetAsync(s.d_dstats.p, 0, std::max<size_t>(nd * sizeof(DrawStats), 16), st));
@@ -574,6 +579,7 @@ void reset_slot(PassSlot& s) {
   s.direct_len = 0;
   s.in_flight = false;
   s.peer = false; s.epochs_set = false;
+  s.direct_async = false;
 }
 
 // Wait for every pass in flight, replay overflowed ones with larger arenas, fold Stats.
@@ -742,7 +748,13 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
       uint8_t* db = static_cast<uint8_t*>(s.d_direct.p);
       if (vb) RF_CUDA(c, cudaMemcpyAsync(db + off, d->verts, vb, cudaMemcpyHostToDevice, c->copy_in));
       if (ib) RF_CUDA(c, cudaMemcpyAsync(db + ioff, d->indices, ib, cudaMemcpyHostToDevice, c->copy_in));
-      RF_CUDA(c, cudaStreamSynchronize(c->copy_in));
+      if (c->geometry_async) {  // the caller promised to leave the arrays alone until the next rf_flush / rf_sync returns
+        if (!s.ev_direct) RF_CUDA(c, cudaEventCreateWithFlags(&s.ev_direct, cudaEventDisableTiming));
+        RF_CUDA(c, cudaEventRecord(s.ev_direct, c->copy_in));
+        s.direct_async = true;
+      } else {
+        RF_CUDA(c, cudaStreamSynchronize(c->copy_in));
+      }
       s.direct_len = ioff + ib;
       q.verts_off = off; q.idx_off = ioff; q.direct = true;
     } else {
@@ -834,6 +846,7 @@ void rf_ctx_destroy(rf_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (int k = 0; k < kSlots; k++) {
     PassSlot& s = c->slots[k];
+    if (s.ev_direct) cudaEventDestroy(s.ev_direct);
     s.geom.release(); s.table.release(); s.h_dstats.release();
     s.d_geom.release(); s.d_direct.release(); s.d_table.release(); s.d_dstats.release(); s.d_status.release();
     if (s.h_status) cudaFreeHost(s.h_status);
@@ -859,6 +872,13 @@ void rf_ctx_destroy(rf_ctx* c) {
 }
 
 const char* rf_last_error(const rf_ctx* c) { return c ? c->err.c_str() : "no context"; }
+
+rf_status rf_ctx_set_geometry_async(rf_ctx* c, int on) {
+  if (!c) return RF_E_INVALID;
+  rf_status st = flush_impl(c);
+  c->geometry_async = on != 0;
+  return st;
+}
 
 rf_status rf_ctx_set_row_band(rf_ctx* c, uint32_t y0, uint32_t y1) {
   if (!c || y0 > y1) return fail(c, RF_E_INVALID, "bad band");

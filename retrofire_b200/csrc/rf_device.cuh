@@ -142,7 +142,7 @@ struct PassParams {
   uint32_t* tile_fill;    // [n_tiles]
   uint32_t* worklist;     // [n_tiles] non-empty tiles
   uint32_t* worklist_big; // [n_tiles]
-  uint32_t* worklist_heavy; // [n_tiles] tiles rasterised first
+  uint32_t* worklist_heavy; // [(RF_SLICES + 1) * n_tiles] rasterised first: slice tasks of the heaviest tiles, then the heavy tiles
   uint32_t* cursors;      // [1] raster work cursor
   DrawStats* dstats;      // [n_draws]
   PassStatus* status;

@@ -51,13 +51,14 @@ __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
       P.tile_off[t] = base + (incl - c);
       P.worklist[wbase + __popc(nz & lt)] = t;
       if (c > RF_SORT_SMALL) P.worklist_big[bbase + __popc(big & lt)] = t;
-      // heaviest tiles from the front of the array, heavy ones from its back
+      // worklist_heavy holds (RF_SLICES + 1) * n_tiles words: slice tasks of the heaviest tiles in the first RF_SLICES * n_tiles
+      // (every tile may be one), the heavy tiles behind them
       if (c >= RF_HEAVIEST_BIN) {  // split into RF_SLICES row slices, each rasterised by its own warp
         const uint32_t b = hhbase + __popc(heaviest & lt) * RF_SLICES;
 #pragma unroll
         for (uint32_t sl = 0; sl < RF_SLICES; sl++) P.worklist_heavy[b + sl] = t | (sl + 1u) << 28;
       }
-      else if (c >= RF_HEAVY_BIN) P.worklist_heavy[P.n_tiles - 1 - (hbase + __popc(heavy & lt))] = t;
+      else if (c >= RF_HEAVY_BIN) P.worklist_heavy[(size_t)RF_SLICES * P.n_tiles + hbase + __popc(heavy & lt)] = t;
       atomicMax(&P.status->max_bin, c);
     }
   }
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
     if (lane == 0) wi = atomicAdd(P.cursors + 1, 1u);
     wi = __shfl_sync(0xFFFFFFFFu, wi, 0);
     if (wi >= n_work + n_heavy) break;
-    const uint32_t task = wi < n_heaviest ? P.worklist_heavy[wi] : (wi < n_heavy ? P.worklist_heavy[P.n_tiles - 1 - (wi - n_heaviest)] : P.worklist[wi - n_heavy]);
+    const uint32_t task = wi < n_heaviest ? P.worklist_heavy[wi] : (wi < n_heavy ? P.worklist_heavy[(size_t)RF_SLICES * P.n_tiles + (wi - n_heaviest)] : P.worklist[wi - n_heavy]);
     const uint32_t tile = task & 0x0FFFFFFFu, slice = task >> 28;  // slice 0: whole tile; k+1: rows [k, k+1) * RF_TILE / RF_SLICES
     const uint32_t cnt = P.tile_cnt[tile], off = P.tile_off[tile];
     if (wi >= n_heavy && cnt >= RF_HEAVY_BIN) continue;  // already done from the heavy list

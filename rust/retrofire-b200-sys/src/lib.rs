@@ -94,6 +94,7 @@ unsafe extern "C" {
     pub fn rf_target_peer_export(ctx: *mut rf_ctx, t: *mut rf_target, ipc_handle_out: *mut u8, devptr_out: *mut *mut c_void) -> rf_status;
     pub fn rf_target_peer_attach(ctx: *mut rf_ctx, t: *mut rf_target, world: u32, rank: u32, ipc_handles: *const u8, devptrs: *const *mut c_void) -> rf_status;
     pub fn rf_ctx_replays(ctx: *mut rf_ctx, out: *mut u64) -> rf_status;
+    pub fn rf_ctx_set_geometry_async(ctx: *mut rf_ctx, on: c_int) -> rf_status;
     pub fn rf_flush(ctx: *mut rf_ctx) -> rf_status;
     pub fn rf_sync(ctx: *mut rf_ctx) -> rf_status;
     pub fn rf_ctx_stats(ctx: *mut rf_ctx, out: *mut rf_stats, reset: c_int) -> rf_status;

@@ -207,6 +207,30 @@ def test_page_locked_geometry_is_dmad_directly(device, oracle):
                                                   want.draws[1],
                                                   dataclasses.replace(want.draws[2], prims=pin(want.draws[2].prims), verts=pin(want.draws[2].verts))])
     assert_parity(run_gpu(device, got_scene), run_oracle(oracle, want), name="direct-dma")
+    # opt-in asynchronous form: rf_render does not wait for the DMA; the arrays stay untouched until the sync inside run_gpu
+    device.set_geometry_async(True)
+    try:
+        for _ in range(2):
+            assert_parity(run_gpu(device, got_scene), run_oracle(oracle, want), name="direct-dma-async")
+    finally:
+        device.set_geometry_async(False)
+
+
+def test_every_tile_heaviest_and_repeated_passes(device, oracle):
+    """Big overlapping triangles put >= 160 triangles into nearly every tile, so nearly every tile is split into row-slice
+    tasks (regression: the task list used to hold one word per tile and overflowed, corrupting later passes). The same frame
+    is rendered several times through the same context: every repetition must equal the oracle."""
+    a = scenes.random_soup(4000, 640, 360, seed=51, lanes_kind="lit", big=False)
+    b = scenes.random_soup(4000, 640, 360, seed=52, lanes_kind="color3", big=True)
+    c = scenes.random_soup(4000, 640, 360, seed=53, lanes_kind="lit", big=True)
+    a.draws = a.draws + b.draws + c.draws
+    want = run_oracle(oracle, a)
+    for rep in range(4):
+        assert_parity(run_gpu(device, a), want, name=f"heaviest-everywhere-{rep}")
+    small = scenes.random_soup(6000, 96, 64, seed=54, lanes_kind="color3", big=True)     # 6 tiles, all of them heaviest
+    want = run_oracle(oracle, small)
+    for rep in range(3):
+        assert_parity(run_gpu(device, small), want, name=f"six-heaviest-tiles-{rep}")
 
 
 def test_very_deep_tile_bin(device, oracle):
