@@ -374,6 +374,9 @@ __device__ __forceinline__ uint32_t* color_px(uint32_t* gc, uint32_t gw, uint32_
 // The per-warp shared-memory region (depth tile + fragment queue) addressed by an explicit 32-bit shared-window address.
 // With a generic pointer ptxas re-derives the window base inside the per-fragment loops to save a register (two S2R —
 // SR_CgaCtaId, SR_TID.X — plus address arithmetic per access); the volatile cvta below pins the base in a register.
+#ifndef RF_GROUP_SYNC
+#define RF_GROUP_SYNC 1
+#endif
 #ifndef RF_SMEM_ASM
 #define RF_SMEM_ASM 1
 #endif
@@ -770,6 +773,9 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
               };
               if (__all_sync(0xFFFFFFFFu, earlier == 0)) {
                 if (fvalid) wrote = one();
+#if RF_GROUP_SYNC
+                __syncwarp();  // orders this group's depth/colour writes before the next group's accesses to the same pixels
+#endif
               } else {
                 uint32_t done = ~__ballot_sync(0xFFFFFFFFu, fvalid);
                 bool pending = fvalid;
