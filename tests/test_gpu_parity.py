@@ -502,3 +502,40 @@ def test_row_band_sharding_matches_oracle_band(device, oracle):
     band = lambda r: (r[0][100:260], r[1][100:260], r[2])
     assert_parity(band(got), band(want), name="band")
     assert not got[0][:100].any() and not got[0][260:].any(), "rows outside the band must stay untouched"
+
+
+def test_fuzz_random_frames_through_one_context(device, oracle):
+    """Seeded fuzz: 100 frames of random size (odd sizes included), pixel format, Context flags and draw mix (triangle soups of
+    every lane layout, lines, an indexed mesh, sprites, depth-sorted draws), all through the same context so that arenas,
+    slots and work lists are reused in every state the previous frame left them in."""
+    import dataclasses
+    g = np.random.default_rng(2026)
+    kinds = ["color3", "uv", "disc", "lit", "color4", "checker", "normal", "texclamp", "lanes8"]
+    fmts = [rf.FMT_RGBA8888, rf.FMT_XRGB8888, rf.FMT_ARGB8888, rf.FMT_BGRA8888, rf.FMT_RGB888, rf.FMT_RGB565, rf.FMT_RGBA4444]
+    for frame in range(100):
+        w, h = int(g.integers(33, 700)), int(g.integers(33, 420))
+        ctx = rf.Context(face_cull=[None, rf.FaceCull.Back, rf.FaceCull.Front][g.integers(0, 3)],
+                         depth_test=[None, rf.Ordering.Less, rf.Ordering.Less, rf.Ordering.Greater][g.integers(0, 4)],
+                         depth_write=bool(g.integers(0, 4) > 0), color_write=bool(g.integers(0, 8) > 0),
+                         depth_sort=[None, None, rf.DepthSort.BackToFront, rf.DepthSort.FrontToBack][g.integers(0, 4)])
+        if ctx.depth_test == rf.Ordering.Greater:
+            ctx.depth_clear = 0.001
+        draws = []
+        for _ in range(int(g.integers(1, 5))):
+            what = g.integers(0, 10)
+            seed = int(g.integers(1, 1 << 30))
+            if what < 6:
+                n = int(g.integers(1, 2500))
+                draws += scenes.random_soup(n, w, h, seed=seed, lanes_kind=kinds[g.integers(0, len(kinds))], big=bool(g.integers(0, 2)), ctx=ctx).draws
+            elif what < 8:
+                draws += scenes.random_lines(int(g.integers(1, 800)), w, h, seed=seed, ctx=ctx).draws
+            elif what == 8:
+                d = scenes.bunny(subdiv=0, w=w, h=h).draws[0]
+                draws.append(dataclasses.replace(d, face_cull=ctx.face_cull or 0, depth_test=ctx.depth_test or 0, color_write=ctx.color_write,
+                                                 depth_write=ctx.depth_write, depth_sort=0 if ctx.depth_sort is None else int(ctx.depth_sort)))
+            else:
+                d = scenes.sprites(int(g.integers(10, 400)), w=w, h=h).draws[0]
+                draws.append(dataclasses.replace(d, face_cull=ctx.face_cull or 0, depth_test=ctx.depth_test or 0, color_write=ctx.color_write,
+                                                 depth_write=ctx.depth_write))
+        sc = scenes.Scene(f"fuzz-{frame}", w, h, fmts[g.integers(0, len(fmts))], bool(g.integers(0, 5) > 0), ctx, draws)
+        check(device, oracle, sc)
