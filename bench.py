@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the render() hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload bunny|crates|sprites]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload bunny|crates|sprites|small_tris]
+                    [--frames F] [--sharding frames|tiles] [--exchange peer|peer-root|nccl]
 
 Workload (BASELINE.json configs[1]): the Stanford bunny, 2x midpoint-subdivided to 79,488
 triangles, Gouraud-shaded (VS_SOLIDS/FS_COLOR3F) with depth test at 1920x1080, Xrgb8888 + f32
-depth. One "step" is one frame batch: F frames (theta = 2*pi*f/F), each cleared and drawn into
-its own device-resident target — the frame-sharded batch of SURVEY §8e. With N GPUs every rank
-renders its own F frames (weak scaling, no data-path collective).
+depth. One "step" is one frame batch: F = 128 frames (theta = 2*pi*f/F; BASELINE config 5-ii is 1,024 frames
+over 8 GPUs), each cleared and drawn into its own device-resident target — the frame-sharded batch of
+SURVEY §8e. With N GPUs every rank renders its own F frames (weak scaling, no data-path collective).
+`--sharding tiles` instead renders ONE large frame sort-first (row bands per rank; the band exchange is
+fused into the rasteriser over NVLink peer memory, or `--exchange nccl` gathers the bands afterwards).
 
 `value`   : Mfragments/s (Stats.frags.i per second) with geometry resident in HBM (rf_mesh).
-`e2e`     : same metric through the reference-facing call with HOST vertex/index buffers every
-            frame (H2D inside the timed region) and the colour buffer of every frame downloaded.
+`e2e`     : same metric through the reference-facing calls with HOST (page-locked) vertex/index buffers
+            every frame (H2D inside the timed region) and the colour buffer of every frame downloaded into
+            page-locked Buf2 storage; 16-frame steps into two alternating sets of device targets.
 `roofline`: k_raster, algorithmic bytes 4*frags.i + 8*frags.o per launch over its
             CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth.
 `cpu_baseline`: the CPU oracle (1 thread, like the single-threaded reference) on a bounded
