@@ -272,6 +272,12 @@ void launch_order(rf_ctx* c, PassSlot& s, const PassParams& P, uint32_t QW, cuda
   s.n_launches += 3;  // plus CUB's own kernels
 }
 
+#ifndef RF_SETUP_GRID_PER_SM
+#define RF_SETUP_GRID_PER_SM 16
+#endif
+#ifndef RF_SORT_GRID_PER_SM
+#define RF_SORT_GRID_PER_SM 16
+#endif
 template <int LT>
 void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   const int sm = c->sm_count;
@@ -312,12 +318,12 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
     if (P.use_sv) k_assemble<LT, true><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P); else k_assemble<LT, false><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
     if (s.order_upper) launch_order(c, s, P, Rec<LT>::QW, st);
-    k_setup<LT><<<sm * 8, 128, 0, st>>>(P);
+    k_setup<LT><<<sm * RF_SETUP_GRID_PER_SM, 128, 0, st>>>(P);
     cudaEventRecord(s.ev_fork, st);
     cudaStreamWaitEvent(sd, s.ev_fork, 0);
     k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, sd>>>(P);
     k_bin_scatter<<<sm * 4, 256, 0, sd>>>(P);
-    k_bin_sort_warp<<<sm * 4, RF_SORT_WARPS * 32, 0, sd>>>(P);
+    k_bin_sort_warp<<<sm * RF_SORT_GRID_PER_SM, RF_SORT_WARPS * 32, 0, sd>>>(P);
     k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, sd>>>(P);
     cudaEventRecord(s.ev_join, sd);
     k_edge_ckpt<LT><<<sm * 4, 128, 0, st>>>(P);

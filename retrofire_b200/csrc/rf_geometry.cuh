@@ -442,8 +442,11 @@ __device__ __forceinline__ void line_walk(const PassParams& P, const TargetDesc&
 #define RF_CHUNK 32u
 #define RF_LONG_BLOCK 256u
 
+#ifndef RF_ASSEMBLE_MIN_BLOCKS
+#define RF_ASSEMBLE_MIN_BLOCKS 1
+#endif
 template <int LT, bool SV>  // SV: every draw of the pass carries RF_F_SV (k_vertex stored screen-space vertices)
-__global__ void __launch_bounds__(128) k_assemble(PassParams P) {
+__global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassParams P) {
   constexpr int QW = Rec<LT>::QW;
   if (P.cstatus->poison) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
