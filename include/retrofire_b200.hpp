@@ -37,7 +37,9 @@ struct Stats {  // render/stats.rs:16-40
   }
 };
 
-struct Context {  // render/ctx.rs:11-127 (defaults :104-127)
+struct BBox { std::array<float, 3> low, upp; };  // render/scene.rs:22, model space
+
+struct Context {  // render/ctx.rs:11-127 (defaults :104-127); depth_sort: RF_SORT_* (ctx.rs:39)
   bool has_color_clear = true; std::array<uint8_t, 4> color_clear{0, 0, 0, 0xFF};
   bool has_depth_clear = true; float depth_clear = __builtin_inff();
   uint8_t face_cull = RF_CULL_BACK, depth_test = RF_DEPTH_LESS, depth_sort = 0;
@@ -93,9 +95,14 @@ class Target {  // Framebuf / Colorbuf / Buf2<Color4> resident on the device (re
 // render() — render.rs:134-207. verts: n_verts records of `stride` floats [x,y,z,a0..]; uniform: up to 32 floats
 // (row-major matrices, layout per rf_vs_id); to_screen: row-major 4x4. Synchronous like the reference:
 // when it returns the draw has executed and ctx.stats has been updated (render.rs:206).
+// `edges`: prims are Edge<usize> pairs (render/prim.rs:41-60) instead of Tri<usize> triples. `bbox`: the scene loop's
+// `if obj.bbox.visibility(&model_to_project) == Hidden { continue }` (scene.rs:81-87, crates.rs:100-122) evaluated on the device.
 inline void render(const uint32_t* prims, uint32_t n_prims, const float* verts, uint32_t n_verts, uint32_t stride, const Shader& sh,
-                   const float* uniform, size_t n_uniform, const float to_screen[16], Target& target, const Context& ctx) {
+                   const float* uniform, size_t n_uniform, const float to_screen[16], Target& target, const Context& ctx,
+                   bool edges = false, const BBox* bbox = nullptr) {
   rf_draw d{};
+  d.prim_kind = edges ? RF_PRIM_EDGES : RF_PRIM_TRIS;
+  if (bbox) { d.bbox_cull = 1; std::memcpy(d.bbox, bbox->low.data(), 12); std::memcpy(d.bbox + 3, bbox->upp.data(), 12); }
   d.indices = prims; d.n_prims = n_prims; d.verts = verts; d.n_verts = n_verts; d.vert_stride_f32 = stride;
   d.n_attr_lanes = sh.lanes; d.persp_mask = sh.persp_mask; d.vs = sh.vs; d.fs = sh.fs;
   std::memcpy(d.vs_uniform, uniform, sizeof(float) * (n_uniform < RF_VS_UNIFORM_F32 ? n_uniform : RF_VS_UNIFORM_F32));
@@ -107,6 +114,7 @@ inline void render(const uint32_t* prims, uint32_t n_prims, const float* verts, 
   target.gpu().check(rf_render(target.gpu().raw(), target.raw(), &d, &st));
   Stats s; s.time = st.time_ns * 1e-9; s.calls = (float)st.calls;
   s.prims = {st.prims_i, st.prims_o}; s.verts = {st.verts_i, st.verts_o}; s.frags = {st.frags_i, st.frags_o};
+  s.objs = {st.objs_i, st.objs_o};
   ctx.stats += s;
 }
 
