@@ -81,3 +81,68 @@ def test_band_gather_assembles_the_unsharded_frame_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+class _FakeDev:
+    """Stands in for rf.Device in the peer-exchange helpers: hands out fake handles, records what it was attached to, and
+    reports a replay on the attempts listed in `replay_on` (a pass re-run after arena growth)."""
+
+    def __init__(self, rank, replay_on=()):
+        self.rank, self.replay_on, self._replays, self.attempt, self.attached = rank, set(replay_on), 0, 0, None
+
+    def peer_export(self):
+        return bytes([self.rank + 1]) * 64
+
+    def peer_attach(self, world, rank, table):
+        self.attached = (world, rank, list(table))
+
+    def replays(self):
+        return self._replays
+
+    def sync(self):
+        self.attempt += 1
+        if self.attempt in self.replay_on:
+            self._replays += 1
+
+
+class _FakeFb:
+    def __init__(self, rank, k):
+        self.tag, self.attached = bytes([16 * (k + 1) + rank]) * 64, None
+
+    def peer_export(self):
+        return self.tag
+
+    def peer_attach(self, world, rank, table):
+        self.attached = list(table)
+
+
+def _peer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # handle exchange: every rank sees every rank's handles in rank order; root=0 blanks the entries of the others
+        dev, fbs = _FakeDev(rank), [_FakeFb(rank, 0), _FakeFb(rank, 1)]
+        shard.attach_peers(dev, fbs, rank, world)
+        ok = dev.attached == (world, rank, [bytes([r + 1]) * 64 for r in range(world)])
+        ok = ok and all(fb.attached == [bytes([16 * (k + 1) + r]) * 64 for r in range(world)] for k, fb in enumerate(fbs))
+        dev2, fb2 = _FakeDev(rank), _FakeFb(rank, 0)
+        shard.attach_peers(dev2, [fb2], rank, world, root=0)
+        ok = ok and fb2.attached == [bytes([16 + r]) * 64 if r == 0 else bytes(64) for r in range(world)]
+        # collective retry: only rank 1 replays, on its first attempt -> BOTH ranks render the frame twice
+        dev3 = _FakeDev(rank, replay_on={1} if rank == 1 else ())
+        frames = []
+        tries = shard.render_frame_with_peers(dev3, lambda: frames.append(1))
+        ok = ok and tries == 2 and len(frames) == 2
+        dev4 = _FakeDev(rank)
+        ok = ok and shard.render_frame_with_peers(dev4, lambda: None) == 1
+        out[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_handle_exchange_and_collective_retry_world2():
+    """shard.attach_peers / render_frame_with_peers (the host side of csrc/rf_peer.cuh) over gloo with stand-in devices."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_peer_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert dict(out) == {0: True, 1: True}
