@@ -667,6 +667,17 @@ int64_t rfo_clip_lattice_histogram(int64_t hist[8]) {
 
 uint8_t rfo_outcode(const float pos[4]) { return outcode(pos); }
 
+// ClipPlane::intersect (clip.rs:121-145) on one edge, for the edge_clip_* KATs (clip.rs:455-486): returns 1 and the
+// intersection position if the edge crosses plane `plane` (index into PLANES), else 0.
+int rfo_edge_plane(int plane, const float a[4], const float b[4], float out[4]) {
+  ClipVert va{}, vb{}, vx{};
+  std::memcpy(va.pos, a, 16); std::memcpy(vb.pos, b, 16);
+  va.oc = outcode(va.pos); vb.oc = outcode(vb.pos);
+  if (!intersect(plane, va, vb, 0, vx)) return 0;
+  std::memcpy(out, vx.pos, 16);
+  return 1;
+}
+
 // tri_fill (raster.rs:185-224) with a recording callback: for KATs raster.rs:326-401.
 // lanes_in: 3 x (3+L) floats. For each scanline writes (y, x0, x1) to spans and the
 // z-divided lane-0 varying per fragment to frag_vals (if non-null, up to max_frags).

@@ -56,6 +56,8 @@ def load() -> C.CDLL:
         lib.rfo_clip_lattice_histogram.argtypes = [C.c_void_p]
         lib.rfo_outcode.restype = C.c_uint8
         lib.rfo_outcode.argtypes = [C.c_void_p]
+        lib.rfo_edge_plane.restype = C.c_int
+        lib.rfo_edge_plane.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rfo_tri_fill_spans.restype = C.c_int
         lib.rfo_tri_fill_spans.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(SpanRec), C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         lib.rfo_sample.restype = None
@@ -135,6 +137,13 @@ def clip_lattice_histogram():
 def outcode(pos) -> int:
     p = np.ascontiguousarray(pos, dtype=np.float32).reshape(4)
     return int(load().rfo_outcode(p.ctypes.data))
+
+
+def edge_plane(plane: int, a, b):
+    """ClipPlane::intersect of edge a-b with plane index `plane` (0 near, 1 far, 2 left, 3 right, 4 bottom, 5 top): position or None."""
+    pa, pb = (np.ascontiguousarray(p, dtype=np.float32).reshape(4) for p in (a, b))
+    out = np.zeros(4, dtype=np.float32)
+    return out if load().rfo_edge_plane(plane, pa.ctypes.data, pb.ctypes.data, out.ctypes.data) else None
 
 
 def tri_fill_spans(lanes: np.ndarray, persp_mask: int = 0, max_spans: int = 4096, max_frags: int = 1 << 20):

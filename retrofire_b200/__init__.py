@@ -5,7 +5,7 @@ include/retrofire_b200.h); this package is the thin host-side mirror of retrofir
 render API on top of it. No CPU fallback: using a Device without the built library or
 without a GPU raises.
 """
-from . import _ffi, mathx, scenes, text  # noqa: F401
+from . import _ffi, mathx, scene, scenes, text  # noqa: F401
 from ._ffi import *  # noqa: F401,F403  (enum constants)
 from .api import (Batch, Context, DepthSort, Device, DrawCall, FaceCull, Framebuf, Mesh, Ordering, RetrofireError, Shader, Stats,  # noqa: F401
                   Texture, Throughput, render, shader)

@@ -228,7 +228,8 @@ def crates(grid: str = "1089", w: int = 3840, h: int = 2160, host_cull: bool = T
     import dataclasses
     if device_cull:
         host_cull = False
-    with_bbox = lambda call, verts: dataclasses.replace(call, bbox=np.stack([verts[:, :3].min(0), verts[:, :3].max(0)])) if device_cull else call
+    from .scene import BBox   # Obj::with_transform computes the box from the mesh (scene.rs:29-39)
+    with_bbox = lambda call, verts: dataclasses.replace(call, bbox=BBox.of(verts).as_array()) if device_cull else call
     ctx = Context()
     vw, vh = w - 20, h - 20
     vp = mx.viewport((10, h - 10), (w - 10, 10))

@@ -145,6 +145,15 @@ def test_clip_outcodes_and_single_cases(oracle):
     assert oracle.clip_tri(tri + np.array([3, 0, 0, 0], dtype=np.float32)).shape[0] == 0
 
 
+def test_edge_clip_kats(oracle):
+    """render/clip.rs:455-486 (edge_clip_inside / outside / in_out / out_in): FAR_PLANE against single edges."""
+    FAR = 1
+    assert oracle.edge_plane(FAR, [2, 0, -1, 1], [-1, 1, 1, 1]) is None          # inside (touching the plane): unchanged
+    assert oracle.edge_plane(FAR, [2, 0, 1.5, 1], [-1, 1, 2, 1]) is None         # both outside: nothing to intersect
+    assert np.array_equal(oracle.edge_plane(FAR, [2, 0, 0, 1], [-1, 1, 2, 1]), np.array([0.5, 0.5, 1.0, 1.0], np.float32))
+    assert np.array_equal(oracle.edge_plane(FAR, [2, 0, 4, 1], [-1, 1, 0, 1]), np.array([-0.25, 0.75, 1.0, 1.0], np.float32))
+
+
 def test_clip_exhaustive_lattice_histogram(oracle):
     """render/clip.rs:667-719: 5^9 triangles, all outputs in bounds, output-count histogram."""
     hist, bad = oracle.clip_lattice_histogram()
