@@ -186,6 +186,13 @@ class DrawCall:
     prim_kind: int = _ffi.PRIM_TRIS   # PRIM_EDGES: prims is (n,2) — `Edge<usize>` line primitives
     bbox: Optional[np.ndarray] = None  # (2,3) BBox<Model> low/upp: the draw is skipped when BBox::visibility(uniform) is Hidden
 
+    def __post_init__(self):
+        # `uniform` is copied into rf_draw.vs_uniform as RF_VS_UNIFORM_F32 floats: a shorter array (a caller replacing the
+        # uniform of a two-matrix shader by one 4x4 matrix) is zero-padded here instead of being over-read there
+        u = self.uniform
+        if not (isinstance(u, np.ndarray) and u.dtype == np.float32 and u.size == _ffi.RF_VS_UNIFORM_F32 and u.flags.c_contiguous):
+            self.uniform = _flatten_uniform(u)
+
     @staticmethod
     def make(prims, verts, shd: Shader, uniform, to_screen, ctx: Context = None, mesh: "Mesh" = None, edges: bool = False) -> "DrawCall":
         ctx = ctx or Context()

@@ -459,7 +459,8 @@ rf_status launch_pass(rf_ctx* c, int si) {
     vb += d.n_verts; pb += d.n_prims;
   }
   h_vbase[nd] = vb; h_pbase[nd] = pb;
-  uint32_t tile_base = 0;
+  uint32_t tile_base = 0, tiles_per_target = 0;
+  bool uniform_tiles = nt > 0;
   for (size_t i = 0; i < nt; i++) {
     rf_target* t = s.targets[i];
     TargetDesc& T = h_targets[i];
@@ -467,6 +468,8 @@ rf_status launch_pass(rf_ctx* c, int si) {
     T.w = t->w; T.h = t->h; T.fmt = t->fmt;
     T.tiles_x = (t->w + RF_TILE - 1) / RF_TILE; T.tiles_y = (t->h + RF_TILE - 1) / RF_TILE;
     T.tile_base = tile_base; tile_base += T.tiles_x * T.tiles_y;
+    if (i == 0) tiles_per_target = T.tiles_x * T.tiles_y;
+    else if (T.tiles_x * T.tiles_y != tiles_per_target) uniform_tiles = false;
     T.band_y0 = std::min(c->band_y0, t->h); T.band_y1 = std::min(c->band_y1, t->h);
     T.n_peers = t->n_peers; T._pad = 0;
     for (uint32_t p = 0; p < RF_MAX_PEERS; p++) T.peer_color[p] = p < t->n_peers ? t->peer_color[p] : nullptr;
@@ -531,6 +534,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.pbase = P.vbase + (nd + 1);
   P.targets = reinterpret_cast<const TargetDesc*>(dt + toff);
   P.n_draws = (uint32_t)nd; P.n_targets = (uint32_t)nt; P.NV = nv; P.NP = np; P.n_tiles = ntiles;
+  P.tiles_per_target = uniform_tiles ? tiles_per_target : 0u;  // frame batches: k_raster finds a tile's target by one division
   for (auto& q : s.draws) if (q.desc.flags & RF_F_BBOX) P.any_bbox = 1;
   P.use_sv = 1;
   for (auto& q : s.draws) if (!(q.desc.flags & RF_F_SV)) P.use_sv = 0;

@@ -120,6 +120,7 @@ struct PassParams {
   uint32_t n_draws, n_targets, NV, NP, n_tiles;
   uint32_t use_sv;        // every draw of the pass has RF_F_SV: k_vertex stores screen-space vertices, k_assemble<LT, true> reads them
   uint32_t any_bbox;      // some draw of the pass carries RF_F_BBOX (k_objects ran)
+  uint32_t tiles_per_target;  // every target of the pass has this many tiles (tile / it = target index), or 0 when they differ
   float* cv;              // clip verts [NV][CVS]
   float* sv;              // screen verts [NV][SVS]: to_screen of every vertex inside the frustum, plus its outcode
   uint32_t* stris;        // [cap_stris][QW]   compacted screen triangles (k_assemble -> k_setup)

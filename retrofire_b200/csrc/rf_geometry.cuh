@@ -311,7 +311,7 @@ __device__ __forceinline__ void tile_row_cols(const HalfSetup<LT>& H0, const Hal
 // Serial walk of one trapezoid half by the thread that set it up (ScanlineIter::next, raster.rs:80-114).
 // Used for triangles with few rows, where a separate row-parallel kernel costs more than it saves.
 template <int LT>
-__device__ __forceinline__ void walk_half_inline(const PassParams& P, uint32_t th, uint32_t tw, uint32_t by0, uint32_t by1, HalfSetup<LT>& H,
+__device__ __forceinline__ void walk_half_inline(uint32_t* span_base, uint32_t th, uint32_t tw, uint32_t by0, uint32_t by1, HalfSetup<LT>& H,
                                                  uint32_t& sidx, uint32_t& row, uint32_t& long_rows, unsigned long long& frags_i, bool& oob) {
   constexpr int NL = 2 + LT;
   constexpr int SW = Rec<LT>::SW;
@@ -344,7 +344,7 @@ __device__ __forceinline__ void walk_half_inline(const PassParams& P, uint32_t t
     if (nn && ((X0 + nn - 1) >> RF_TILE_SHIFT) != (X0 >> RF_TILE_SHIFT)) long_rows |= 1u << row;
     w[0] = X0 | nn << 16;
     w[1] = RF_NO_CKPT;
-    uint32_t* sr = P.spans + (size_t)sidx * SW;
+    uint32_t* sr = span_base + (size_t)sidx * SW;  // span record `sidx` of span_base (the global array, or the warp's staging buffer)
 #pragma unroll
     for (int q = 0; q < SW / 2; q++) *reinterpret_cast<uint2*>(sr + 2 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
     sidx++;
@@ -625,6 +625,20 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
 #ifndef RF_SETUP_MIN_BLOCKS
 #define RF_SETUP_MIN_BLOCKS 4
 #endif
+// Triangle records and the span records of inline-walked triangles are staged in shared memory and written out by the
+// whole warp as contiguous runs, every 32-byte sector once. Written by each lane directly (192-byte records at a 192-byte
+// lane stride, 24-byte spans as three 8-byte stores at a stride of rows x 24 bytes) the same data cost 2-3 L2 sector writes
+// per sector of payload: 111 M of the kernel's 135 M L2 write sectors on the bunny batch, 71 M of them excess
+// (profiles/r01_hot_lines.txt), with L2 the busiest unit of the kernel. Only at 3 varying lanes (static shared memory).
+#ifndef RF_SETUP_STAGE
+#define RF_SETUP_STAGE 1
+#endif
+template <int LT> struct SetupStage {
+  static constexpr bool ON = RF_SETUP_STAGE && LT == 3;
+  static constexpr int TWP = Rec<LT>::TW + 4;  // padded record stride in the buffer: 52 words = 20 mod 32 -> 128-bit accesses of 8 lanes hit 32 different banks
+  static constexpr int SPAN_WORDS = 32 * (int)RF_INLINE_ROWS * Rec<LT>::SW, TRI_WORDS = 32 * TWP;
+  static constexpr int WORDS = ON ? (SPAN_WORDS > TRI_WORDS ? SPAN_WORDS : TRI_WORDS) : 4;
+};
 template <int LT>
 __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setup(PassParams P) {
   constexpr int NL = 2 + LT, NV = 1 + LT;
@@ -633,6 +647,8 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
   __shared__ uint32_t s_tot[4][4];
   __shared__ unsigned long long s_base[4];
   __shared__ uint32_t s_fit[4];
+  using SS = SetupStage<LT>;
+  __shared__ uint4 s_stage[4][SS::WORDS / 4];  // uint4: 16-byte aligned for the 128-bit accesses
   if (P.cstatus->poison) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t NT = (uint32_t)min(P.status->stris_needed, (unsigned long long)P.cap_stris);
@@ -805,16 +821,18 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
       if (threadIdx.x == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
       continue;  // keep counting what is needed, write nothing
     }
-    if (emit) {
-      const uint32_t sbase = (uint32_t)sb + (incl_s - nsp);
-      const uint32_t tri_idx = (uint32_t)tb + __popc(emask & lt);
-      uint32_t eidx = (uint32_t)eb + (incl_e - nent);
-      uint32_t cidx = (uint32_t)cb_ + (incl_c - nchunk);
-      const bool inline_walk = !is_line && H0.n + H1.n <= RF_INLINE_ROWS;
-      const uint32_t ch0 = (inline_walk || is_line) ? 0u : (H0.n + RF_CHUNK - 1) / RF_CHUNK, ch1 = (inline_walk || is_line) ? 0u : (H1.n + RF_CHUNK - 1) / RF_CHUNK;
-      const uint32_t eck0 = cidx, eck1 = cidx + ch0;  // edge checkpoints are indexed by chunk position
-      {  // triangle record
-        uint32_t* tr = P.tris + (size_t)tri_idx * TW;
+    const uint32_t sbase = (uint32_t)sb + (incl_s - nsp);  // defined on every lane (nsp = 0 where nothing is emitted)
+    const uint32_t tri_idx = (uint32_t)tb + __popc(emask & lt);
+    uint32_t eidx = (uint32_t)eb + (incl_e - nent);
+    uint32_t cidx = (uint32_t)cb_ + (incl_c - nchunk);
+    const bool inline_walk = emit && !is_line && H0.n + H1.n <= RF_INLINE_ROWS;
+    const bool chunked = emit && !inline_walk && !is_line;
+    const uint32_t ch0 = chunked ? (H0.n + RF_CHUNK - 1) / RF_CHUNK : 0u, ch1 = chunked ? (H1.n + RF_CHUNK - 1) / RF_CHUNK : 0u;
+    const uint32_t eck0 = cidx, eck1 = cidx + ch0;  // edge checkpoints are indexed by chunk position
+    uint32_t* const stg = reinterpret_cast<uint32_t*>(s_stage[wid]);
+    {  // triangle record: into the warp's staging buffer (record = rank among the emitting lanes), or straight to global memory
+      uint32_t* tr = SS::ON ? stg + __popc(emask & lt) * SS::TWP : P.tris + (size_t)tri_idx * TW;
+      if (emit) {
         *reinterpret_cast<uint4*>(tr) = make_uint4(key, d, sbase, Y0);
         *reinterpret_cast<uint4*>(tr + 4) = make_uint4(H0.n, H1.n | (tgt << 16), eck0, eck1);
 #pragma unroll
@@ -832,6 +850,18 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
           for (int q = 0; q < HS / 4; q++) *reinterpret_cast<uint4*>(tr + 8 + hh * HS + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
         }
       }
+      if (SS::ON) {  // the warp's records are consecutive in P.tris: 128-bit stores, consecutive lanes -> consecutive 16 bytes
+        __syncwarp();
+        const uint32_t nq = (uint32_t)__popc(emask) * (TW / 4);
+        uint4* dst = reinterpret_cast<uint4*>(P.tris + (size_t)(uint32_t)tb * TW);
+        for (uint32_t qi = lane; qi < nq; qi += 32) {
+          const uint32_t rec = qi / (TW / 4), part = qi - rec * (TW / 4);
+          dst[qi] = *reinterpret_cast<const uint4*>(stg + rec * SS::TWP + part * 4);
+        }
+        __syncwarp();  // the buffer is reused for the span records below
+      }
+    }
+    if (emit) {
       if (is_line) {  // spans (one run per row, rows without pixels in band keep n = 0) and exact bin entries
         const TargetDesc& T = P.targets[tgt];
         constexpr int SW_ = Rec<LT>::SW;
@@ -856,17 +886,46 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
         P.chunks[cidx++] = make_uint4(tri_idx * 2u, c | min(RF_CHUNK, H0.n - c * RF_CHUNK) << 16, sbase + c * RF_CHUNK, d | tgt << 16);
       for (uint32_t c = 0; c < ch1; c++)
         P.chunks[cidx++] = make_uint4(tri_idx * 2u + 1u, c | min(RF_CHUNK, H1.n - c * RF_CHUNK) << 16, sbase + H0.n + c * RF_CHUNK, d | tgt << 16);
-      if (inline_walk) {  // few rows: walk them here, serially (sequential adds down both edges)
-        uint32_t sidx = sbase, row = 0;
-        bool oob = false;
-        const uint32_t nU = H0.n;
-        walk_half_inline<LT>(P, t_h, t_w, t_by0, t_by1, H0, sidx, row, long_rows, my_frags_i, oob);
-        walk_half_inline<LT>(P, t_h, t_w, t_by0, t_by1, H1, sidx, row, long_rows, my_frags_i, oob);
-        if (oob) atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
-        long_sbase = sbase; long_tri = tri_idx; long_nU = nU;
-      }
       if (ch0 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed, lane); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
       if (ch1 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed, lane); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u + 1u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
+    }
+    // few rows: walk them here, serially (sequential adds down both edges). The span records go to the staging buffer at
+    // the lane's offset among the warp's inline-walked rows (or straight to P.spans).
+    const uint32_t nin = inline_walk ? nsp : 0u;
+    const uint32_t incl_in = SS::ON ? warp_scan_incl(nin, lane) : 0u;
+    if (inline_walk) {
+      uint32_t sidx = SS::ON ? incl_in - nin : sbase, row = 0;
+      uint32_t* const span_base = SS::ON ? stg : P.spans;
+      bool oob = false;
+      const uint32_t nU = H0.n;
+      walk_half_inline<LT>(span_base, t_h, t_w, t_by0, t_by1, H0, sidx, row, long_rows, my_frags_i, oob);
+      walk_half_inline<LT>(span_base, t_h, t_w, t_by0, t_by1, H1, sidx, row, long_rows, my_frags_i, oob);
+      if (oob) atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
+      long_sbase = sbase; long_tri = tri_idx; long_nU = nU;
+    }
+    if (SS::ON) {
+      // Copy-out. The staged spans of consecutive lanes are consecutive in P.spans too, except across a lane whose spans are
+      // written elsewhere (a chunked triangle: k_walk; a line: above): such lanes cut the warp into runs, each one contiguous
+      // copy of 8-byte units (span records are 24 bytes, 8-byte aligned).
+      constexpr int SW_ = Rec<LT>::SW;
+      __syncwarp();
+      const uint32_t total_in = __shfl_sync(0xFFFFFFFFu, incl_in, 31);
+      uint32_t breakers = __ballot_sync(0xFFFFFFFFu, emit && !inline_walk && nsp != 0);
+      uint32_t a = 0;
+      while (total_in != 0 && a < 32) {
+        const uint32_t b = breakers ? (uint32_t)__ffs(breakers) - 1u : 32u;  // the run is lanes [a, b)
+        const uint32_t u0 = __shfl_sync(0xFFFFFFFFu, incl_in - nin, a);
+        const uint32_t u1 = b < 32 ? __shfl_sync(0xFFFFFFFFu, incl_in - nin, b & 31u) : total_in;
+        const uint32_t g0 = __shfl_sync(0xFFFFFFFFu, sbase, a);
+        const uint2* src = reinterpret_cast<const uint2*>(stg + (size_t)u0 * SW_);
+        uint2* dst = reinterpret_cast<uint2*>(P.spans + (size_t)g0 * SW_);
+        const uint32_t nu = (u1 - u0) * (SW_ / 2);
+        for (uint32_t i = lane; i < nu; i += 32) dst[i] = src[i];
+        if (b >= 32) break;
+        breakers &= breakers - 1;
+        a = b + 1;
+      }
+      __syncwarp();  // the buffer is reused by the next iteration
     }
     // ---- long list of the inline walks: one warp-aggregated allocation (warp prefix sum) for all lanes
     {

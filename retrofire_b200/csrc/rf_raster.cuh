@@ -392,6 +392,7 @@ struct WarpSmem {
   __device__ __forceinline__ uint32_t ldu(uint32_t w) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + w * 4u) : "memory"); return v; }
   __device__ __forceinline__ void stf(uint32_t w, float v) const { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + w * 4u), "f"(v) : "memory"); }
   __device__ __forceinline__ void stu(uint32_t w, uint32_t v) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + w * 4u), "r"(v) : "memory"); }
+  __device__ __forceinline__ void oru(uint32_t w, uint32_t v) const { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a + w * 4u), "r"(v) : "memory"); }
 #else
   float* p;
   __device__ __forceinline__ explicit WarpSmem(const void* q) : p(reinterpret_cast<float*>(const_cast<void*>(q))) {}
@@ -399,6 +400,7 @@ struct WarpSmem {
   __device__ __forceinline__ uint32_t ldu(uint32_t w) const { return reinterpret_cast<const uint32_t*>(p)[w]; }
   __device__ __forceinline__ void stf(uint32_t w, float v) const { p[w] = v; }
   __device__ __forceinline__ void stu(uint32_t w, uint32_t v) const { reinterpret_cast<uint32_t*>(p)[w] = v; }
+  __device__ __forceinline__ void oru(uint32_t w, uint32_t v) const { atomicOr(reinterpret_cast<uint32_t*>(p) + w, v); }
 #endif
 };
 
@@ -454,12 +456,14 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
 #endif
 template <int LT> struct RasterTune {
   static constexpr uint32_t MIN_AVG = LT == 3 ? RF_SPAN_MODE_MIN_AVG_3 : RF_SPAN_MODE_MIN_AVG_5;
-  static constexpr uint32_t FRAG_QUEUE = MIN_AVG * 32u;  // fragment-mode batches hold fewer fragments than this
+  // capacity of the fragment queue: fragment-mode batches hold fewer than MIN_AVG * 32 fragments; the last 8 slots were
+  // traded for the 32 row-coverage words (the few batches of 32 pieces with more fragments than this take span mode)
+  static constexpr uint32_t FRAG_QUEUE = MIN_AVG * 32u - 8u;
 };
 
 template <int LT> struct RasterSmem {
   static constexpr int TILE_WORDS = RF_TILE * RF_TILE_PITCH;
-  static constexpr int WARP_WORDS = TILE_WORDS + (2 + LT) * (int)RasterTune<LT>::FRAG_QUEUE;  // depth tile, queue {z, attr[LT], pix}
+  static constexpr int WARP_WORDS = TILE_WORDS + (2 + LT) * (int)RasterTune<LT>::FRAG_QUEUE + RF_TILE;  // depth tile, queue {z, attr[LT], pix}, row coverage
   static constexpr size_t BYTES = (size_t)RF_RASTER_WARPS * WARP_WORDS * 4;
 };
 
@@ -481,6 +485,14 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
   uint32_t* qp = reinterpret_cast<uint32_t*>(qv + (1 + LT) * RasterTune<LT>::FRAG_QUEUE);    // [FRAG_QUEUE] pixel index | owner lane << 16
   const WarpSmem wsm(sz);  // the same region for the per-fragment accesses: depth at [idx], queue behind it
   constexpr uint32_t QV0 = RasterSmem<LT>::TILE_WORDS, QP0 = QV0 + (1 + LT) * RasterTune<LT>::FRAG_QUEUE;
+  // Row coverage [RF_TILE]: bit c of word r = pixel (r, c) is covered by a piece of the current fragment-mode batch. The pieces
+  // OR their pixel runs in; popcount(coverage) == number of fragments <=> no two pieces of the batch share a pixel, and the
+  // batch's fragment groups need no per-group same-pixel search (MATCH.ANY cost 10 % of this kernel's stall samples).
+  constexpr uint32_t RC0 = QP0 + RasterTune<LT>::FRAG_QUEUE;
+  wsm.stu(RC0 + lane, 0u);
+  __syncwarp();
+  // fast-path selectors of the last warp-uniform draw seen (span mode | fragment mode << 4): looked up once per draw, not per batch
+  uint32_t mode_draw = 0xFFFFFFFFu, mode_bits = 0;
   const uint32_t n_work = P.status->n_work, n_heaviest = P.status->n_work_heaviest, n_heavy = n_heaviest + P.status->n_work_heavy;
 
   for (;;) {
@@ -494,7 +506,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
     if (wi >= n_heavy && cnt >= RF_HEAVY_BIN) continue;  // already done from the heavy list
     // which target / tile coordinates
     uint32_t ti = 0;
-    {
+    if (P.tiles_per_target) ti = tile / P.tiles_per_target;  // frame batch: equal targets
+    else {
       uint32_t lo = 0, hi = P.n_targets;
       while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.targets[mid].tile_base <= tile) lo = mid; else hi = mid; }
       ti = lo;
@@ -504,25 +517,41 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
     const uint32_t ty = tl / T.tiles_x, tx = tl - ty * T.tiles_x;
     const uint32_t px0 = tx << RF_TILE_SHIFT, py0 = ty << RF_TILE_SHIFT;
     const uint32_t tw = min((uint32_t)RF_TILE, T.w - px0), th = min((uint32_t)RF_TILE, T.h - py0);
+    // read once: the shared-memory accessors are volatile asm with a memory clobber, so every later T.x would be re-loaded
+    // from global memory inside the fragment loops (the format switch waited on that load: 8 % of the stall samples)
+    const uint32_t t_w = T.w, t_fmt = T.fmt;
     const bool has_depth = T.depth != nullptr;
-    const bool vec = (T.w & 3u) == 0 && tw == RF_TILE;
+    const bool vec = (t_w & 3u) == 0 && tw == RF_TILE;
     // tile rows this task owns (a heaviest tile is shared by RF_SLICES warps, each owning whole rows)
     const uint32_t r0 = slice ? min(th, (slice - 1u) * (RF_TILE / RF_SLICES)) : 0u;
     const uint32_t r1 = slice ? min(th, slice * (RF_TILE / RF_SLICES)) : th;
 
-    uint32_t* gc = T.color + (size_t)py0 * T.w + px0;  // framebuffer address of the tile's first pixel
+    uint32_t* gc = T.color + (size_t)py0 * t_w + px0;  // framebuffer address of the tile's first pixel
+    // the first 32 triangles of the bin: requested before the depth tile so that the two latencies overlap
+    uint32_t nb_tri = lane < cnt ? (uint32_t)P.bins[off + lane] : 0u;
     // ---- stage the depth tile: 128-bit coalesced loads, 8 lanes per row, 4 rows per instruction
     if (has_depth) {
-      if (vec) {
+      const float* t_depth = T.depth;
+      if (vec && r1 - r0 == RF_TILE) {  // whole tile: all eight loads in flight before the first store
+        const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
+        float4 z[RF_TILE / 4];
+#pragma unroll
+        for (int i = 0; i < RF_TILE / 4; i++) z[i] = *reinterpret_cast<const float4*>(t_depth + (size_t)(py0 + rsub + 4 * i) * t_w + px0 + c4);
+#pragma unroll
+        for (int i = 0; i < RF_TILE / 4; i++) {
+          float* e = sz + (rsub + 4 * i) * RF_TILE_PITCH + c4;
+          e[0] = z[i].x; e[1] = z[i].y; e[2] = z[i].z; e[3] = z[i].w;
+        }
+      } else if (vec) {
         const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
         for (uint32_t r = r0 + rsub; r < r1; r += 4) {
-          const float4 z = *reinterpret_cast<const float4*>(T.depth + (size_t)(py0 + r) * T.w + px0 + c4);
+          const float4 z = *reinterpret_cast<const float4*>(t_depth + (size_t)(py0 + r) * t_w + px0 + c4);
           float* e = sz + r * RF_TILE_PITCH + c4;
           e[0] = z.x; e[1] = z.y; e[2] = z.z; e[3] = z.w;
         }
       } else {
         for (uint32_t r = r0; r < r1; r++)
-          if (lane < tw) sz[r * RF_TILE_PITCH + lane] = T.depth[(size_t)(py0 + r) * T.w + px0 + lane];
+          if (lane < tw) sz[r * RF_TILE_PITCH + lane] = t_depth[(size_t)(py0 + r) * t_w + px0 + lane];
       }
     }
     __syncwarp();
@@ -533,8 +562,10 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
     for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
       // ---- lane t: one triangle of this chunk (sorted by submission key)
       uint32_t t_tri = 0, t_sbase = 0, t_Y0 = 0, t_nU = 0, t_ra = 0, t_rows = 0, t_draw = 0;
-      if (c0 + lane < cnt) {
-        t_tri = (uint32_t)P.bins[off + c0 + lane];
+      const bool t_have = c0 + lane < cnt;
+      t_tri = nb_tri;
+      nb_tri = c0 + 32 + lane < cnt ? (uint32_t)P.bins[off + c0 + 32 + lane] : 0u;  // next chunk's triangles, one chunk ahead
+      if (t_have) {
         const uint32_t* tr = P.tris + (size_t)t_tri * TW;
         const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(tr));
         const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(tr + 4));  // nU, nL | target << 16
@@ -639,7 +670,26 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
         const uint32_t f_incl = warp_scan_incl(pn, lane);
         const uint32_t n_frags = __shfl_sync(0xFFFFFFFFu, f_incl, 31);
 
-        if (n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask)) {
+        // warp-uniform fast-path selectors of the batch's draw (0 / 1 = generic)
+        uint32_t smode = 0, fmode = uni ? 1u : 0u;
+        if (uni) {
+          if (d0 != mode_draw) {
+            const DrawDesc& Dq = P.draws[d0];
+            const uint32_t qflags = Dq.flags, qfs = Dq.fs, qpm = Dq.persp_mask, qL = Dq.L;
+            const uint32_t dflt = RF_DEPTH_LESS << RF_F_DTEST_SHIFT | RF_F_CWRITE | RF_F_DWRITE;
+            uint32_t sm = 0, fm = 1;
+            if ((qflags & RF_F_RASTER_STATE) == dflt) {  // default Context (ctx.rs:104-127); the other flag bits concern earlier stages
+              if (qfs == RF_FS_TEX_CLAMP_LIT && qpm == 0x1Fu && LT >= 5) { sm = 4; fm = 4; }
+              else if (qfs == RF_FS_COLOR3F && qpm == 0u && LT >= 3) { sm = 2; fm = 2; }
+              else if (qfs == RF_FS_CHECKER && qpm == 0x3u && qL == 2u && LT == 5) sm = 5;
+              else if (qfs == RF_FS_SPRITE_DISC && qpm == 0x3u) fm = 3;
+            }
+            mode_draw = d0; mode_bits = sm | fm << 4;
+          }
+          if (has_depth) { smode = mode_bits & 15u; fmode = mode_bits >> 4; }
+        }
+
+        if (n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask) || n_frags > RasterTune<LT>::FRAG_QUEUE) {
           // ================= span mode: one piece per lane, walked serially =================
           // dependencies: earlier lanes on the same row whose x-range overlaps mine
           uint32_t dep = 0;
@@ -655,21 +705,6 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
             }
           }
           const DrawDesc& D = P.draws[draw];
-          const uint32_t flags = valid ? D.flags : 0u;
-          const uint32_t pmask = valid ? D.persp_mask : 0u;
-          const uint32_t fs = D.fs;
-          const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
-          const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
-          // warp-uniform specialisation selector (0 = generic)
-          int smode = 0;
-          if (uni) {
-            const DrawDesc& Dq = P.draws[d0];
-            const uint32_t dflt = RF_DEPTH_LESS << RF_F_DTEST_SHIFT | RF_F_CWRITE | RF_F_DWRITE;
-            const bool is_default = has_depth && (Dq.flags & RF_F_RASTER_STATE) == dflt;  // the other flag bits concern earlier stages
-            if (is_default && Dq.fs == RF_FS_TEX_CLAMP_LIT && Dq.persp_mask == 0x1Fu && LT >= 5) smode = 4;
-            else if (is_default && Dq.fs == RF_FS_COLOR3F && Dq.persp_mask == 0u && LT >= 3) smode = 2;
-            else if (is_default && Dq.fs == RF_FS_CHECKER && Dq.persp_mask == 0x3u && Dq.L == 2u && LT == 5) smode = 5;
-          }
           uint32_t done = ~vmask;
           bool pending = valid;
           while (done != 0xFFFFFFFFu) {
@@ -678,25 +713,28 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
               const uint32_t base = py * RF_TILE_PITCH + pxs;
               if (smode == 4) {  // default Context + FS_TEX_CLAMP_LIT (crates): straight-line fragment code
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, gc, T.w, wsm, base + k, v);
+                  my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, gc, t_w, wsm, base + k, v);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                 }
               } else if (smode == 2) {
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, wsm, base + k, v);
+                  my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, gc, t_w, wsm, base + k, v);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                 }
               } else if (LT == 5 && smode == 5) {  // default Context + FS_CHECKER on two perspective uv lanes (the crates floor): z, u, v only
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_CHECKER, 0x3u>(D, T.fmt, gc, T.w, wsm, base + k, v);
+                  my_o += process_fragment_fixed<LT, RF_FS_CHECKER, 0x3u>(D, t_fmt, gc, t_w, wsm, base + k, v);
 #pragma unroll
                   for (int i = 0; i < 3; i++) v[i] = v[i] + dv[i];
                 }
               } else {
+                const uint32_t flags = D.flags, pmask = D.persp_mask, fs = D.fs;
+                const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
+                const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
                 for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment<LT>(D, fs, T.fmt, gc, T.w, wsm, base + k, v, pmask, dtest, cwrite, dwrite);
+                  my_o += process_fragment<LT>(D, fs, t_fmt, gc, t_w, wsm, base + k, v, pmask, dtest, cwrite, dwrite);
 #pragma unroll
                   for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
                 }
@@ -718,6 +756,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xFFFFFFFFu, maxn, o));
             const uint32_t pix0 = py * RF_TILE_PITCH + pxs;
+            if (pn) wsm.oru(RC0 + py, (0xFFFFFFFFu >> (32u - pn)) << pxs);  // this piece's pixels of tile row py
             for (uint32_t k = 0; k < maxn; k++) {
               if (k < pn) {
                 const uint32_t q = qstart + k;
@@ -728,6 +767,10 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
             }
           }
           __syncwarp();
+          // distinct pixels covered by the batch (lane r counts tile row r and clears its word for the next batch)
+          const uint32_t rcov = wsm.ldu(RC0 + lane);
+          wsm.stu(RC0 + lane, 0u);
+          const bool no_overlap = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(rcov)) == n_frags;
           // Phase B. When the whole batch belongs to one draw (the common case) the draw state is
           // warp-uniform and hoisted out of the loop; otherwise every fragment looks its draw up.
           auto frag_loop = [&](auto mode_tag) {
@@ -752,7 +795,13 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
                 for (int i = 0; i < NV; i++) fv[i] = 0.0f;
               }
               const uint32_t pix = fvalid ? (pw & 0xFFFFu) : (0x10000u + lane);
-              const uint32_t earlier = __match_any_sync(0xFFFFFFFFu, pix) & lt;  // same pixel, submitted before me
+              // same pixel, submitted before me: only searched for when two pieces of the batch overlap at all
+              uint32_t earlier = 0;
+              bool clean = true;
+              if (!no_overlap) {
+                earlier = __match_any_sync(0xFFFFFFFFu, pix) & lt;
+                clean = __all_sync(0xFFFFFFFFu, earlier == 0);
+              }
               uint32_t fdraw = d0, pmask = u_pmask, fs = u_fs, dtest = u_dtest;
               bool cwrite = u_cwrite, dwrite = u_dwrite;
               if (!UNI) {
@@ -766,12 +815,12 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
               const DrawDesc& D = UNI ? Du : P.draws[fdraw];
               uint32_t wrote = 0;
               auto one = [&]() -> uint32_t {
-                if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, T.fmt, gc, T.w, wsm, pix, fv);
-                if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, T.fmt, gc, T.w, wsm, pix, fv);
-                if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, T.fmt, gc, T.w, wsm, pix, fv);
-                return process_fragment<LT>(D, fs, T.fmt, gc, T.w, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
+                if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, gc, t_w, wsm, pix, fv);
+                if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, t_fmt, gc, t_w, wsm, pix, fv);
+                if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, gc, t_w, wsm, pix, fv);
+                return process_fragment<LT>(D, fs, t_fmt, gc, t_w, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
               };
-              if (__all_sync(0xFFFFFFFFu, earlier == 0)) {
+              if (clean) {
                 if (fvalid) wrote = one();
 #if RF_GROUP_SYNC
                 __syncwarp();  // orders this group's depth/colour writes before the next group's accesses to the same pixels
@@ -791,16 +840,11 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
               else if (wrote) atomicAdd(&P.dstats[fdraw].frags_o, 1ull);
             }
           };
-          if (!uni) frag_loop(std::integral_constant<int, 0>{});
-          else {
-            const DrawDesc& Dq = P.draws[d0];
-            const uint32_t dflt = RF_DEPTH_LESS << RF_F_DTEST_SHIFT | RF_F_CWRITE | RF_F_DWRITE;
-            const bool is_default = has_depth && (Dq.flags & RF_F_RASTER_STATE) == dflt;  // the other flag bits concern earlier stages
-            if (is_default && Dq.fs == RF_FS_COLOR3F && Dq.persp_mask == 0u && LT >= 3) frag_loop(std::integral_constant<int, 2>{});
-            else if (is_default && Dq.fs == RF_FS_SPRITE_DISC && Dq.persp_mask == 0x3u) frag_loop(std::integral_constant<int, 3>{});
-            else if (is_default && Dq.fs == RF_FS_TEX_CLAMP_LIT && Dq.persp_mask == 0x1Fu && LT >= 5) frag_loop(std::integral_constant<int, 4>{});
-            else frag_loop(std::integral_constant<int, 1>{});
-          }
+          if (fmode == 0) frag_loop(std::integral_constant<int, 0>{});
+          else if (fmode == 2) frag_loop(std::integral_constant<int, 2>{});
+          else if (fmode == 3) frag_loop(std::integral_constant<int, 3>{});
+          else if (fmode == 4) frag_loop(std::integral_constant<int, 4>{});
+          else frag_loop(std::integral_constant<int, 1>{});
           __syncwarp();
         }
       }
@@ -815,15 +859,16 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
 
     // ---- write the depth tile back: 128-bit coalesced stores
     if (has_depth) {
+      float* t_depth = T.depth;
       if (vec) {
         const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
         for (uint32_t r = r0 + rsub; r < r1; r += 4) {
           const float* e = sz + r * RF_TILE_PITCH + c4;
-          *reinterpret_cast<float4*>(T.depth + (size_t)(py0 + r) * T.w + px0 + c4) = make_float4(e[0], e[1], e[2], e[3]);
+          *reinterpret_cast<float4*>(t_depth + (size_t)(py0 + r) * t_w + px0 + c4) = make_float4(e[0], e[1], e[2], e[3]);
         }
       } else {
         for (uint32_t r = r0; r < r1; r++)
-          if (lane < tw) T.depth[(size_t)(py0 + r) * T.w + px0 + lane] = sz[r * RF_TILE_PITCH + lane];
+          if (lane < tw) t_depth[(size_t)(py0 + r) * t_w + px0 + lane] = sz[r * RF_TILE_PITCH + lane];
       }
     }
     __syncwarp();

@@ -56,7 +56,9 @@ def stale() -> bool:
 
 def build(force: bool = False, defines: dict | None = None, out: str | None = None) -> str:
     out = out or OUT
-    if not (force or defines or out != OUT or stale()):
+    if os.environ.get("RF_EMU_CXXFLAGS") and out == OUT:  # debugging builds (sanitizers, -O0 ...) never replace the default library
+        out = OUT.replace(".so", "_custom.so")
+    if not (force or defines or out != OUT or stale() or os.environ.get("RF_EMU_CXXFLAGS")):
         return out
     src = os.path.join(BUILD, "src", "retrofire_b200", "csrc")  # same depth as the original: "../../include/retrofire_b200.h" resolves
     os.makedirs(src, exist_ok=True)
@@ -73,7 +75,7 @@ def build(force: bool = False, defines: dict | None = None, out: str | None = No
     assert not left, f"unhandled inline PTX in {left}"
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing", "-fPIC", "-shared", "-w", "-x", "c++",
            "-DRF_SMEM_ASM=0", f"-I{os.path.join(HERE, 'include')}"] + [f"-D{k}={v}" for k, v in (defines or {}).items()] + \
-          ["-o", out, os.path.join(src, "rf_api.cu.cpp")]
+          os.environ.get("RF_EMU_CXXFLAGS", "").split() + ["-o", out, os.path.join(src, "rf_api.cu.cpp")]
     subprocess.run(cmd, check=True, cwd=src)
     return out
 
