@@ -445,9 +445,16 @@ __device__ __forceinline__ void line_walk(const PassParams& P, const TargetDesc&
 #ifndef RF_ASSEMBLE_MIN_BLOCKS
 #define RF_ASSEMBLE_MIN_BLOCKS 1
 #endif
+// The screen-triangle records a warp appends are consecutive in P.stris: they are staged in shared memory and written
+// by the whole warp, every sector once (as in k_setup; a lane's own 128-bit stores at an 80-byte stride fill half a sector each).
+#ifndef RF_ASSEMBLE_STAGE
+#define RF_ASSEMBLE_STAGE 1
+#endif
 template <int LT, bool SV>  // SV: every draw of the pass carries RF_F_SV (k_vertex stored screen-space vertices)
 __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassParams P) {
   constexpr int QW = Rec<LT>::QW;
+  // record stride QW = 20 / 28 / 36 words: the 128-bit accesses of 8 consecutive lanes fall into 8 different bank groups
+  __shared__ uint4 s_q[RF_ASSEMBLE_STAGE ? 4 : 1][RF_ASSEMBLE_STAGE ? 32 * QW / 4 : 1];
   if (P.cstatus->poison) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t n_iter = (P.NP + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
@@ -583,8 +590,9 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
         if (lane == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
         continue;
       }
+      uint32_t* const qstg = reinterpret_cast<uint32_t*>(s_q[RF_ASSEMBLE_STAGE ? threadIdx.x >> 5 : 0]);
       if (emit) {
-        uint32_t* q = P.stris + (size_t)((uint32_t)base + __popc(emask & lt)) * QW;
+        uint32_t* q = RF_ASSEMBLE_STAGE ? qstg + __popc(emask & lt) * QW : P.stris + (size_t)((uint32_t)base + __popc(emask & lt)) * QW;
         if (P.sdepth != nullptr) P.sdepth[(uint32_t)base + __popc(emask & lt)] = (uint32_t)total_key(depth) ^ 0x80000000u;  // unsigned order == total_cmp
         uint32_t w[QW];
         w[0] = gp * 8u + t; w[1] = is_edge ? (d | RF_STRI_LINE) : d;
@@ -598,6 +606,13 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
         for (int i = 2 + 3 * (3 + LT); i < QW; i++) w[i] = 0u;
 #pragma unroll
         for (int qd = 0; qd < QW / 4; qd++) *reinterpret_cast<uint4*>(q + 4 * qd) = make_uint4(w[4 * qd], w[4 * qd + 1], w[4 * qd + 2], w[4 * qd + 3]);
+      }
+      if (RF_ASSEMBLE_STAGE) {
+        __syncwarp();
+        const uint32_t nq = (uint32_t)__popc(emask) * (QW / 4);
+        uint4* dst = reinterpret_cast<uint4*>(P.stris + (size_t)(uint32_t)base * QW);
+        for (uint32_t qi = lane; qi < nq; qi += 32) dst[qi] = reinterpret_cast<const uint4*>(qstg)[qi];
+        __syncwarp();  // the buffer is reused by the next fan index
       }
     }
     // ---- per-draw prims.o: aggregate over the warp when every lane has the same draw
@@ -633,6 +648,9 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
 #ifndef RF_SETUP_STAGE
 #define RF_SETUP_STAGE 1
 #endif
+#ifndef RF_SETUP_STAGE_IN   // the warp's 32 input records (consecutive in P.stris) are loaded through the same buffer
+#define RF_SETUP_STAGE_IN 1
+#endif
 template <int LT> struct SetupStage {
   static constexpr bool ON = RF_SETUP_STAGE && LT == 3;
   static constexpr int TWP = Rec<LT>::TW + 4;  // padded record stride in the buffer: 52 words = 20 mod 32 -> 128-bit accesses of 8 lanes hit 32 different banks
@@ -644,9 +662,11 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
   constexpr int NL = 2 + LT, NV = 1 + LT;
   constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS, QW = Rec<LT>::QW;
   using TR = TriRec<LT>;
-  __shared__ uint32_t s_tot[4][4];
-  __shared__ unsigned long long s_base[4];
-  __shared__ uint32_t s_fit[4];
+  // allocation scratch, double-buffered by iteration parity: a warp that runs ahead into iteration it + 1 writes the other
+  // copy, and cannot reach iteration it + 2 before every warp has passed the barriers of it + 1 (i.e. finished reading it)
+  __shared__ uint32_t s_tot2[2][4][4];
+  __shared__ unsigned long long s_base2[2][4];
+  __shared__ uint32_t s_fit2[2][4];
   using SS = SetupStage<LT>;
   __shared__ uint4 s_stage[4][SS::WORDS / 4];  // uint4: 16-byte aligned for the 128-bit accesses
   if (P.cstatus->poison) return;
@@ -654,6 +674,9 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
   const uint32_t NT = (uint32_t)min(P.status->stris_needed, (unsigned long long)P.cap_stris);
   const uint32_t n_iter = (NT + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
   for (uint32_t it = 0; it < n_iter; it++) {
+    uint32_t (*const s_tot)[4] = s_tot2[it & 1u];
+    unsigned long long* const s_base = s_base2[it & 1u];
+    uint32_t* const s_fit = s_fit2[it & 1u];
     const uint32_t ti = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     const bool have = ti < NT;
     bool emit = false;
@@ -668,12 +691,21 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
     LineGeom LG{};
     LineMeasure LM{};
     float line_lanes[1 + LT];
+    constexpr bool STAGE_IN = SS::ON && RF_SETUP_STAGE_IN;
+    if (STAGE_IN) {  // consecutive lanes load consecutive 16 bytes; each lane then takes its record from shared memory
+      const uint32_t wbase = ti - lane;
+      const uint32_t nrec = wbase < NT ? min(32u, NT - wbase) : 0u;
+      const uint4* src = reinterpret_cast<const uint4*>(P.stris + (size_t)wbase * QW);
+      uint4* stg4 = s_stage[threadIdx.x >> 5];
+      for (uint32_t qi = lane; qi < nrec * (QW / 4); qi += 32) stg4[qi] = __ldg(src + qi);
+      __syncwarp();
+    }
     if (have) {
-      const uint32_t* q = P.stris + (size_t)ti * QW;
+      const uint32_t* q = STAGE_IN ? reinterpret_cast<const uint32_t*>(s_stage[threadIdx.x >> 5]) + lane * QW : P.stris + (size_t)ti * QW;
       uint32_t w[QW];
 #pragma unroll
       for (int qd = 0; qd < QW / 4; qd++) {
-        const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(q) + qd);
+        const uint4 t4 = STAGE_IN ? reinterpret_cast<const uint4*>(q)[qd] : __ldg(reinterpret_cast<const uint4*>(q) + qd);
         w[4 * qd] = t4.x; w[4 * qd + 1] = t4.y; w[4 * qd + 2] = t4.z; w[4 * qd + 3] = t4.w;
       }
       key = w[0]; d = w[1] & ~RF_STRI_LINE;
@@ -816,7 +848,6 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
     const bool fits = s_fit[0] && s_fit[1] && s_fit[2] && s_fit[3];
     unsigned long long sb = s_base[0], tb = s_base[1], eb = s_base[2], cb_ = s_base[3];
     for (uint32_t w = 0; w < wid; w++) { sb += s_tot[w][0]; tb += s_tot[w][1]; eb += s_tot[w][2]; cb_ += s_tot[w][3]; }
-    __syncthreads();  // s_tot / s_base are reused by the next iteration
     if (!fits) {
       if (threadIdx.x == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
       continue;  // keep counting what is needed, write nothing

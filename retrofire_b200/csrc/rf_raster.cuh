@@ -380,6 +380,17 @@ __device__ __forceinline__ uint32_t* color_px(uint32_t* gc, uint32_t gw, uint32_
 #ifndef RF_SMEM_ASM
 #define RF_SMEM_ASM 1
 #endif
+// L2 prefetch hint (no register result, no dependency): the records a tile's next steps will read — written by k_setup /
+// k_walk long ago, 0.8 GB each on the bunny batch, so mostly out of L2 — are requested a chunk ahead of their use.
+#ifndef RF_RASTER_PREFETCH
+#define RF_RASTER_PREFETCH 1
+#endif
+#if RF_SMEM_ASM
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#endif
+
 struct WarpSmem {
 #if RF_SMEM_ASM
   uint32_t a;
@@ -574,6 +585,12 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
         t_ra = max(t_Y0, py0 + r0);
         const uint32_t rb = min(t_Y0 + nrows, py0 + r1);
         t_rows = rb > t_ra ? rb - t_ra : 0u;
+        if (RF_RASTER_PREFETCH && t_rows) {  // this triangle's span records of the tile's rows: 24-64 bytes each
+          const char* sp0 = reinterpret_cast<const char*>(P.spans + (size_t)(t_sbase + (t_ra - t_Y0)) * SW);
+          prefetch_l2(sp0);
+          if (t_rows * (SW * 4u) > 128u) prefetch_l2(sp0 + 128);
+          if (t_rows * (SW * 4u) > 256u) prefetch_l2(sp0 + 256);
+        }
       }
       const uint32_t t_incl = warp_scan_incl(t_rows, lane);
       const uint32_t n_items = __shfl_sync(0xFFFFFFFFu, t_incl, 31);
@@ -623,6 +640,11 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
       for (uint32_t ib = 0; ib < n_items; ib += 32, cur = nxt) {
         nxt.valid = false;
         if (ib + 32 < n_items) fetch(ib + 32, nxt);
+        if (RF_RASTER_PREFETCH && ib == 32 && c0 + 32 + lane < cnt) {  // header and both dv/dx of the next chunk's triangles
+          const char* tp = reinterpret_cast<const char*>(P.tris + (size_t)nb_tri * TW);
+          prefetch_l2(tp);
+          prefetch_l2(tp + 128);
+        }
         bool valid = cur.valid;
         uint32_t py = 32 + lane, pxs = 0, pn = 0, draw = 0;
         float v[NV], dv[NV];
