@@ -445,10 +445,12 @@ __device__ __forceinline__ void line_walk(const PassParams& P, const TargetDesc&
 #ifndef RF_ASSEMBLE_MIN_BLOCKS
 #define RF_ASSEMBLE_MIN_BLOCKS 1
 #endif
-// The screen-triangle records a warp appends are consecutive in P.stris: they are staged in shared memory and written
-// by the whole warp, every sector once (as in k_setup; a lane's own 128-bit stores at an 80-byte stride fill half a sector each).
+// Optional (off): stage the screen-triangle records a warp appends in shared memory and write them out by the whole warp,
+// every sector once, as k_setup does with its records. Measured on the bunny batch it costs more than it saves here
+// (k_assemble 0.41 -> 0.49 ms, profiles/r01_ab2_assemble_prefetch.txt): the kernel is bound by its IEEE divides and gather
+// latency, not by L2 write sectors, and the two extra warp barriers per fan index sit on its critical path.
 #ifndef RF_ASSEMBLE_STAGE
-#define RF_ASSEMBLE_STAGE 1
+#define RF_ASSEMBLE_STAGE 0
 #endif
 template <int LT, bool SV>  // SV: every draw of the pass carries RF_F_SV (k_vertex stored screen-space vertices)
 __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassParams P) {
@@ -648,8 +650,8 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
 #ifndef RF_SETUP_STAGE
 #define RF_SETUP_STAGE 1
 #endif
-#ifndef RF_SETUP_STAGE_IN   // the warp's 32 input records (consecutive in P.stris) are loaded through the same buffer
-#define RF_SETUP_STAGE_IN 1
+#ifndef RF_SETUP_STAGE_IN   // optional (off): load the warp's 32 input records through the same buffer — measured neutral to +1 %
+#define RF_SETUP_STAGE_IN 0
 #endif
 template <int LT> struct SetupStage {
   static constexpr bool ON = RF_SETUP_STAGE && LT == 3;
@@ -662,11 +664,9 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
   constexpr int NL = 2 + LT, NV = 1 + LT;
   constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS, QW = Rec<LT>::QW;
   using TR = TriRec<LT>;
-  // allocation scratch, double-buffered by iteration parity: a warp that runs ahead into iteration it + 1 writes the other
-  // copy, and cannot reach iteration it + 2 before every warp has passed the barriers of it + 1 (i.e. finished reading it)
-  __shared__ uint32_t s_tot2[2][4][4];
-  __shared__ unsigned long long s_base2[2][4];
-  __shared__ uint32_t s_fit2[2][4];
+  __shared__ uint32_t s_tot[4][4];
+  __shared__ unsigned long long s_base[4];
+  __shared__ uint32_t s_fit[4];
   using SS = SetupStage<LT>;
   __shared__ uint4 s_stage[4][SS::WORDS / 4];  // uint4: 16-byte aligned for the 128-bit accesses
   if (P.cstatus->poison) return;
@@ -674,9 +674,6 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
   const uint32_t NT = (uint32_t)min(P.status->stris_needed, (unsigned long long)P.cap_stris);
   const uint32_t n_iter = (NT + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
   for (uint32_t it = 0; it < n_iter; it++) {
-    uint32_t (*const s_tot)[4] = s_tot2[it & 1u];
-    unsigned long long* const s_base = s_base2[it & 1u];
-    uint32_t* const s_fit = s_fit2[it & 1u];
     const uint32_t ti = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     const bool have = ti < NT;
     bool emit = false;
@@ -848,6 +845,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
     const bool fits = s_fit[0] && s_fit[1] && s_fit[2] && s_fit[3];
     unsigned long long sb = s_base[0], tb = s_base[1], eb = s_base[2], cb_ = s_base[3];
     for (uint32_t w = 0; w < wid; w++) { sb += s_tot[w][0]; tb += s_tot[w][1]; eb += s_tot[w][2]; cb_ += s_tot[w][3]; }
+    __syncthreads();  // s_tot / s_base are reused by the next iteration
     if (!fits) {
       if (threadIdx.x == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
       continue;  // keep counting what is needed, write nothing
