@@ -188,6 +188,47 @@ def test_frame_batch_render_frames(device, oracle):
     assert got_stats.counters() == want_total.counters()
 
 
+def test_targets_of_different_sizes_in_one_pass(device, oracle):
+    """Three targets of different sizes and formats drawn in ONE pass: the rasteriser then finds a tile's target by binary
+    search over the tile bases (frame batches of equal targets use tile / tiles_per_target instead); twice, so that the second
+    pass runs with warm arenas."""
+    scs = [scenes.random_soup(400, 320, 200, seed=21, lanes_kind="color3"), scenes.random_soup(300, 96, 50, seed=22, lanes_kind="uv"),
+           scenes.random_soup(500, 641, 359, seed=23, lanes_kind="color3", big=True)]
+    fbs = [device.framebuf(sc.w, sc.h, sc.fmt, sc.has_depth) for sc in scs]
+    try:
+        for rep in range(2):
+            for sc, fb in zip(scs, fbs):
+                fb.clear(sc.ctx)
+            device.stats(reset=True)
+            for k in range(max(len(sc.draws) for sc in scs)):      # interleaved submission
+                for sc, fb in zip(scs, fbs):
+                    if k < len(sc.draws):
+                        device.render(sc.draws[k], fb)
+            total = device.stats(reset=True)
+            want_total = rf.Stats()
+            for sc, fb in zip(scs, fbs):
+                wc, wd, ws = run_oracle(oracle, sc)
+                want_total += ws
+                assert np.array_equal(fb.download_color(), wc), (sc.name, rep)
+                assert np.array_equal(fb.download_depth().view(np.uint32), wd.view(np.uint32)), (sc.name, rep)
+            assert total.counters() == want_total.counters()
+    finally:
+        for fb in fbs:
+            fb._destroy()
+            device._targets.remove(fb)
+
+
+def test_short_uniform_is_zero_padded(device, oracle):
+    """A uniform shorter than RF_VS_UNIFORM_F32 floats (one matrix given to the two-matrix solids shader) is zero-padded by
+    DrawCall, identically for the device and the oracle: the second matrix is zero, so every normal-derived colour is black."""
+    import dataclasses
+    mesh = scenes.bunny(subdiv=0, w=400, h=300)
+    d = mesh.draws[0]
+    one = dataclasses.replace(d, uniform=np.asarray(d.uniform, np.float32).ravel()[:16].reshape(4, 4))
+    assert one.uniform.shape == (rf.RF_VS_UNIFORM_F32,) and not one.uniform[16:].any()
+    check(device, oracle, dataclasses.replace(mesh, name="bunny-one-matrix", draws=[one]))
+
+
 def test_page_locked_geometry_is_dmad_directly(device, oracle):
     """Vertex/index arrays in rf_host_alloc memory take the direct-DMA path of rf_render (several draws per pass,
     mixed with pageable draws that go through pinned staging); results are identical."""
