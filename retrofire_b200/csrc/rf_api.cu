@@ -446,6 +446,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   toff = (toff + 15) & ~size_t(15);
   TargetDesc* h_targets = reinterpret_cast<TargetDesc*>(tb + toff);
   uint32_t vb = 0, pb = 0;
+  bool uniform_verts = true, uniform_prims = true;  // frame batch: every draw has the same vertex / primitive count
   for (size_t i = 0; i < nd; i++) {
     QueuedDraw& q = s.draws[i];
     DrawDesc d = q.desc;
@@ -457,6 +458,8 @@ rf_status launch_pass(rf_ctx* c, int si) {
     h_draws[i] = d;
     h_vbase[i] = vb; h_pbase[i] = pb;
     vb += d.n_verts; pb += d.n_prims;
+    if (d.n_verts != h_draws[0].n_verts) uniform_verts = false;
+    if (d.n_prims != h_draws[0].n_prims) uniform_prims = false;
   }
   h_vbase[nd] = vb; h_pbase[nd] = pb;
   uint32_t tile_base = 0, tiles_per_target = 0;
@@ -534,6 +537,8 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.pbase = P.vbase + (nd + 1);
   P.targets = reinterpret_cast<const TargetDesc*>(dt + toff);
   P.n_draws = (uint32_t)nd; P.n_targets = (uint32_t)nt; P.NV = nv; P.NP = np; P.n_tiles = ntiles;
+  P.verts_per_draw = nd && uniform_verts ? h_draws[0].n_verts : 0u;  // 0 also when the draws are empty: binary search
+  P.prims_per_draw = nd && uniform_prims ? h_draws[0].n_prims : 0u;
   P.tiles_per_target = uniform_tiles ? tiles_per_target : 0u;  // frame batches: k_raster finds a tile's target by one division
   for (auto& q : s.draws) if (q.desc.flags & RF_F_BBOX) P.any_bbox = 1;
   P.use_sv = 1;

@@ -121,6 +121,7 @@ struct PassParams {
   uint32_t use_sv;        // every draw of the pass has RF_F_SV: k_vertex stores screen-space vertices, k_assemble<LT, true> reads them
   uint32_t any_bbox;      // some draw of the pass carries RF_F_BBOX (k_objects ran)
   uint32_t tiles_per_target;  // every target of the pass has this many tiles (tile / it = target index), or 0 when they differ
+  uint32_t verts_per_draw, prims_per_draw;  // likewise for the draws of a frame batch (one mesh, many frames): index / it = draw, or 0
   float* cv;              // clip verts [NV][CVS]
   float* sv;              // screen verts [NV][SVS]: to_screen of every vertex inside the frustum, plus its outcode
   uint32_t* stris;        // [cap_stris][QW]   compacted screen triangles (k_assemble -> k_setup)
@@ -232,8 +233,10 @@ __device__ __forceinline__ uint32_t pack_pixel(uint32_t fmt, uint32_t r, uint32_
   }
 }
 
-// binary search: largest d with base[d] <= i   (base has n+1 entries, base[0] = 0)
-__device__ __forceinline__ uint32_t find_draw(const uint32_t* __restrict__ base, uint32_t n, uint32_t i) {
+// binary search: largest d with base[d] <= i   (base has n+1 entries, base[0] = 0). `per` != 0: every draw has `per`
+// items (a frame batch), so the draw is one division instead of log2(n) dependent loads.
+__device__ __forceinline__ uint32_t find_draw(const uint32_t* __restrict__ base, uint32_t n, uint32_t i, uint32_t per = 0) {
+  if (per) return i / per;
   uint32_t lo = 0, hi = n;
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;

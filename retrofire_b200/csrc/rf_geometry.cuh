@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_vertex(PassParams P) {
   constexpr int CVS = Rec<LT>::CVS;
   if (P.cstatus->poison) return;
   for (uint32_t gv = blockIdx.x * blockDim.x + threadIdx.x; gv < P.NV; gv += gridDim.x * blockDim.x) {
-    const uint32_t d = find_draw(P.vbase, P.n_draws, gv);
+    const uint32_t d = find_draw(P.vbase, P.n_draws, gv, P.verts_per_draw);
     if (P.any_bbox && P.dstats[d].hidden) continue;  // object culled: its clip vertices are never read
     const DrawDesc& D = P.draws[d];
     const float* __restrict__ in = D.verts + (size_t)(gv - __ldg(P.vbase + d)) * D.vstride;
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
     bool is_edge = false;
     constexpr bool use_sv = SV;
     if (have) {
-      d = find_draw(P.pbase, P.n_draws, gp);
+      d = find_draw(P.pbase, P.n_draws, gp, P.prims_per_draw);
       const DrawDesc& D = P.draws[d];
       is_edge = D.prim_kind == RF_PRIM_EDGES;
     }
