@@ -47,15 +47,86 @@ pub trait GpuShader<Uni> {
     fn texture(&self) -> *const sys::rf_texture { ptr::null() }
 }
 
-/// `|v, mvp| vertex(mvp.apply(&v.pos), v.attrib)` + `|f| f.var.to_color4()` (demos solids/hello_tri non-fp).
-pub struct MvpColor3f;
-impl<B> GpuShader<&retrofire_core::math::ProjMat3<B>> for MvpColor3f {
-    const VS: u32 = 0; // RF_VS_MVP
-    const FS: u32 = 0; // RF_FS_COLOR3F
-    fn vs_uniform(m: &&retrofire_core::math::ProjMat3<B>) -> [f32; 32] { mat_uniform(&m.0, None) }
+type Proj<B> = retrofire_core::math::ProjMat3<B>;
+type M4<S, D> = Mat4<S, D>;
+
+// ---- the catalogue: one value type per (vertex, fragment) shader pair of the demos/tests ----------------
+// The numeric ids are `rf_vs_id` / `rf_fs_id` of include/retrofire_b200.h.
+
+macro_rules! mvp_shader {
+    ($(#[$doc:meta])* $name:ident, $vs:expr, $fs:expr) => {
+        $(#[$doc])*
+        pub struct $name;
+        impl<B> GpuShader<&Proj<B>> for $name {
+            const VS: u32 = $vs;
+            const FS: u32 = $fs;
+            fn vs_uniform(m: &&Proj<B>) -> [f32; 32] { mat_uniform(&m.0, None) }
+        }
+    };
 }
-// ... one unit struct per catalogue entry: MvpTexClamp{tex}, MvpTexClampLit{tex, light_dir}, MvpChecker,
-// SolidsColor3f (uniform (&mvp, &spin)), SpriteDisc (uniform (&modelview, &proj)), MvpNormalVis, ...
+mvp_shader!(
+    /// `|v, mvp| vertex(mvp.apply(&v.pos), v.attrib)` + `|f| f.var.to_color4()` (hello_tri.rs:22-26 non-fp, debug.rs:21-31).
+    MvpColor3f, 0, 0);
+mvp_shader!(
+    /// hello_tri.rs:13-18 with the `fp` feature: attrib -> `powf(c, 2.2)` per vertex, `powf(c, 1/2.2)` per fragment (±1 LSB).
+    MvpLinearizeColor3fSrgb, 1, 1);
+mvp_shader!(
+    /// Four colour lanes passed through (render/debug.rs:34-38, demos/wasm/src/triangle.rs:41).
+    MvpColor4f, 0, 2);
+mvp_shader!(
+    /// Checker floor of crates.rs:32-36: `(uv.x() > 0.5) ^ (uv.y() > 0.5) ? 0.8 : 0.1` gray.
+    MvpChecker, 0, 3);
+mvp_shader!(
+    /// curses.rs:49-56: normal visualisation `n / 2 + 0.5`.
+    MvpNormalVis, 0, 8);
+
+/// solids.rs:70-83: uniform `(&mvp, &spin)`; per-vertex diffuse term from the spun normal, colour from the model normal.
+pub struct SolidsColor3f;
+impl<B, S, D> GpuShader<(&Proj<B>, &M4<S, D>)> for SolidsColor3f {
+    const VS: u32 = 2; // RF_VS_SOLIDS
+    const FS: u32 = 0; // RF_FS_COLOR3F
+    fn vs_uniform(u: &(&Proj<B>, &M4<S, D>)) -> [f32; 32] { mat_uniform(&u.0.0, Some(&u.1.0)) }
+}
+
+/// sprites.rs:40-52: uniform `(&modelview, &project)`; view-space billboard offset 0.008 * corner; disc with `discard`.
+pub struct SpriteDisc;
+impl<S, D, B> GpuShader<(&M4<S, D>, &Proj<B>)> for SpriteDisc {
+    const VS: u32 = 3; // RF_VS_SPRITE
+    const FS: u32 = 7; // RF_FS_SPRITE_DISC
+    fn vs_uniform(u: &(&M4<S, D>, &Proj<B>)) -> [f32; 32] { mat_uniform(&u.0.0, Some(&u.1.0)) }
+}
+
+/// tests/rendering.rs:27-30, square.rs:39-40, hello.rs:33-36: `SamplerClamp.sample(&tex, uv)`.
+pub struct MvpTexClamp<'t> { pub tex: &'t GpuTexture<'t> }
+impl<B> GpuShader<&Proj<B>> for MvpTexClamp<'_> {
+    const VS: u32 = 0;
+    const FS: u32 = 5; // RF_FS_TEX_CLAMP
+    fn vs_uniform(m: &&Proj<B>) -> [f32; 32] { mat_uniform(&m.0, None) }
+    fn texture(&self) -> *const sys::rf_texture { self.tex.t }
+}
+
+/// benches/fill.rs:74-91: `SamplerRepeatPot` (power-of-two sizes only; anything else is RF_E_BAD_TEXTURE = the reference's assert).
+pub struct MvpTexRepeatPot<'t> { pub tex: &'t GpuTexture<'t> }
+impl<B> GpuShader<&Proj<B>> for MvpTexRepeatPot<'_> {
+    const VS: u32 = 0;
+    const FS: u32 = 6; // RF_FS_TEX_REPEAT_POT
+    fn vs_uniform(m: &&Proj<B>) -> [f32; 32] { mat_uniform(&m.0, None) }
+    fn texture(&self) -> *const sys::rf_texture { self.tex.t }
+}
+
+/// crates.rs:39-47: varying `(Normal3, TexCoord)`, `kd = lerp(max(n·l, 0), 0.4, 1.0)`, texel * kd.
+pub struct MvpTexClampLit<'t> { pub tex: &'t GpuTexture<'t>, pub light_dir: Normal3 }
+impl<B> GpuShader<&Proj<B>> for MvpTexClampLit<'_> {
+    const VS: u32 = 0;
+    const FS: u32 = 4; // RF_FS_TEX_CLAMP_LIT
+    fn vs_uniform(m: &&Proj<B>) -> [f32; 32] { mat_uniform(&m.0, None) }
+    fn fs_uniform(&self) -> [f32; sys::RF_FS_UNIFORM_F32] {
+        let mut u = [0.0; sys::RF_FS_UNIFORM_F32];
+        u[..3].copy_from_slice(&self.light_dir.0);
+        u
+    }
+    fn texture(&self) -> *const sys::rf_texture { self.tex.t }
+}
 
 fn mat_uniform(a: &[[f32; 4]; 4], b: Option<&[[f32; 4]; 4]>) -> [f32; 32] {
     let mut u = [0.0f32; 32];
@@ -106,9 +177,66 @@ impl<'g> GpuTarget<'g> {
 }
 impl Drop for GpuTarget<'_> { fn drop(&mut self) { unsafe { sys::rf_target_destroy(self.t) } } }
 
+/// Device copy of a `Texture<Buf2<Color3>>` / `Texture<Buf2<Color4>>` (render/tex.rs:33-37,190-213). Nearest sampling only,
+/// as in the reference; `w`/`h` are the float dimensions the samplers multiply by.
+pub struct GpuTexture<'g> { _gpu: &'g Gpu, t: *mut sys::rf_texture }
+impl<'g> GpuTexture<'g> {
+    /// `texels`: row-major, `stride` elements per row (util/buf.rs:437-439); `fmt` = RF_FMT_RGB888 or RF_FMT_RGBA8888.
+    pub fn new<T>(gpu: &'g Gpu, w: u32, h: u32, fmt: u32, texels: &[T], stride: usize) -> Self {
+        assert!(texels.len() >= stride * (h as usize).saturating_sub(1) + w as usize);
+        let mut t = ptr::null_mut();
+        gpu.check(unsafe { sys::rf_texture_create(gpu.ctx, w, h, fmt, texels.as_ptr().cast(), stride, &mut t) });
+        GpuTexture { _gpu: gpu, t }
+    }
+}
+impl Drop for GpuTexture<'_> { fn drop(&mut self) { unsafe { sys::rf_texture_destroy(self.t) } } }
+
+/// The primitive kinds `render()` accepts (`Render for Tri<usize>` prim.rs:17-39, `Render for Edge<usize>` prim.rs:41-60).
+pub trait GpuPrim: Clone {
+    const KIND: u8;
+    const ARITY: usize;
+    fn indices(&self, out: &mut Vec<u32>);
+}
+fn idx32(i: usize) -> u32 { u32::try_from(i).expect("vertex index >= 2^32") }
+impl GpuPrim for Tri<usize> {
+    const KIND: u8 = 0; // RF_PRIM_TRIS
+    const ARITY: usize = 3;
+    fn indices(&self, out: &mut Vec<u32>) { out.extend(self.0.iter().map(|&i| idx32(i))); }
+}
+impl GpuPrim for retrofire_core::geom::Edge<usize> {
+    const KIND: u8 = 1; // RF_PRIM_EDGES
+    const ARITY: usize = 2;
+    fn indices(&self, out: &mut Vec<u32>) { out.push(idx32(self.0)); out.push(idx32(self.1)); }
+}
+
+/// `render::Batch` (render/batch.rs:31-147): the same public fields and builder methods. The reference changes the type
+/// parameters per setter (typestate); here the primitive/vertex/shader types are fixed when the first setter names them,
+/// which is what every call site in the demos does (`Batch::new().mesh(..).uniform(..).shader(..).viewport(..).target(..).context(..)`).
+pub struct Batch<'a, 'g, Prim, Sp, A, Uni, Shd> {
+    pub prims: Vec<Prim>,
+    pub verts: Vec<Vertex<Point3<Sp>, A>>,
+    pub uniform: Uni,
+    pub shader: Shd,
+    pub viewport: Mat4<Ndc, Screen>,
+    pub target: &'a mut GpuTarget<'g>,
+    pub ctx: &'a Context,
+}
+impl<'a, 'g, Prim: GpuPrim, Sp: Clone, A: Lanes + Clone, Uni: Copy, Shd: GpuShader<Uni>> Batch<'a, 'g, Prim, Sp, A, Uni, Shd> {
+    pub fn primitives(mut self, prims: impl AsRef<[Prim]>) -> Self { self.prims = prims.as_ref().to_vec(); self } // batch.rs:57-64
+    pub fn vertices(mut self, verts: impl AsRef<[Vertex<Point3<Sp>, A>]>) -> Self { self.verts = verts.as_ref().to_vec(); self } // :69-76
+    pub fn uniform(mut self, uniform: Uni) -> Self { self.uniform = uniform; self } // :89-94
+    pub fn shader(mut self, shader: Shd) -> Self { self.shader = shader; self } // :97-102
+    pub fn viewport(mut self, viewport: Mat4<Ndc, Screen>) -> Self { self.viewport = viewport; self } // :105-107
+    pub fn context(mut self, ctx: &'a Context) -> Self { self.ctx = ctx; self } // :116-121
+    /// batch.rs:127-146
+    pub fn render(&mut self) {
+        render(&self.prims, &self.verts, &self.shader, self.uniform, self.viewport, self.target, self.ctx);
+    }
+}
+
 /// `retrofire_core::render::render` (render.rs:134-207) on the GPU.
-pub fn render<A, Uni: Copy, Shd>(
-    prims: impl AsRef<[Tri<usize>]>,
+pub fn render<Prim, A, Uni: Copy, Shd>(
+    prims: impl AsRef<[Prim]>,
     verts: impl AsRef<[Vertex<Point3<impl Sized>, A>]>,
     shader: &Shd,
     uniform: Uni,
@@ -116,6 +244,7 @@ pub fn render<A, Uni: Copy, Shd>(
     target: &mut GpuTarget<'_>,
     ctx: &Context,
 ) where
+    Prim: GpuPrim,
     A: Lanes,
     Shd: GpuShader<Uni>,
 {
@@ -126,7 +255,8 @@ pub fn render<A, Uni: Copy, Shd>(
         o[..3].copy_from_slice(&v.pos.0);
         v.attrib.write(&mut o[3..]);
     }
-    let idx: Vec<u32> = prims.iter().flat_map(|t| t.0).map(|i| u32::try_from(i).expect("vertex index >= 2^32")).collect();
+    let mut idx: Vec<u32> = Vec::with_capacity(prims.len() * Prim::ARITY);
+    for p in prims { p.indices(&mut idx); }
     let mut vp = [0.0f32; 16];
     for r in 0..4 { vp[4 * r..4 * r + 4].copy_from_slice(&to_screen.0[r]); }
     let draw = sys::rf_draw {
@@ -138,7 +268,7 @@ pub fn render<A, Uni: Copy, Shd>(
         face_cull: match ctx.face_cull { None => 0, Some(retrofire_core::render::ctx::FaceCull::Back) => 1, Some(_) => 2 },
         depth_test: match ctx.depth_test { None => 0, Some(core::cmp::Ordering::Less) => 1, Some(core::cmp::Ordering::Equal) => 2, Some(_) => 3 },
         color_write: ctx.color_write as u8, depth_write: ctx.depth_write as u8,
-        depth_sort: match ctx.depth_sort { None => 0, Some(DepthSort::FrontToBack) => 1, Some(DepthSort::BackToFront) => 2 }, prim_kind: 0, bbox_cull: 0, _pad: [0; 1], bbox: [0.0; 6],
+        depth_sort: match ctx.depth_sort { None => 0, Some(DepthSort::FrontToBack) => 1, Some(DepthSort::BackToFront) => 2 }, prim_kind: Prim::KIND, bbox_cull: 0, _pad: [0; 1], bbox: [0.0; 6],
     };
     let mut st = sys::rf_stats::default();
     // stats_out != NULL: flush + wait, i.e. the reference's "done when render() returns" (render.rs:206)
