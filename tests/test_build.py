@@ -48,6 +48,29 @@ def test_rust_sys_crate_and_ctypes_structs_follow_the_header():
         assert re.search(r"pub %s:" % name, rust), name
 
 
+def test_rust_safe_shim_names_every_catalogue_pair_with_the_headers_ids():
+    """rust/retrofire-b200 (not compilable here) must offer one shader value per catalogue fragment shader, with the numeric
+    ids of the header's rf_vs_id / rf_fs_id enums, and set every rf_draw field."""
+    header = open(os.path.join(ROOT, "include", "retrofire_b200.h")).read()
+    shim = open(os.path.join(ROOT, "rust", "retrofire-b200", "src", "lib.rs")).read()
+    ids = {name: int(val) for name, val in re.findall(r"\b(RF_(?:VS|FS)_[A-Z0-9_]+)\s*=\s*(\d+)", header)}
+    fs_ids = {v for k, v in ids.items() if k.startswith("RF_FS_")}
+    vs_ids = {v for k, v in ids.items() if k.startswith("RF_VS_")}
+    used_fs = {int(v) for v in re.findall(r"const FS: u32 = (\d+);", shim)}
+    used_vs = {int(v) for v in re.findall(r"const VS: u32 = (\d+);", shim)}
+    for vs, fs in re.findall(r"mvp_shader!\(.*?(\d+),\s*(\d+)\);", shim, re.S):
+        used_vs.add(int(vs)); used_fs.add(int(fs))
+    assert used_fs == fs_ids, used_fs ^ fs_ids
+    assert used_vs == vs_ids, used_vs ^ vs_ids
+    for name, val in re.findall(r"const (?:VS|FS): u32 = (\d+); // (RF_\w+)", shim):
+        assert ids[val] == int(name), (val, name)   # the id written next to a symbolic comment is that symbol's value
+    rust_sys = open(os.path.join(ROOT, "rust", "retrofire-b200-sys", "src", "lib.rs")).read()
+    draw_fields = re.findall(r"pub (\w+):", re.search(r"pub struct rf_draw \{(.*?)\n\}", rust_sys, re.S).group(1))
+    literal = re.search(r"let draw = sys::rf_draw \{(.*?)\n    \};", shim, re.S).group(1)
+    for f in draw_fields:
+        assert re.search(r"\b%s:" % f, literal), f
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     import torch
     if torch.cuda.is_available():
