@@ -550,10 +550,10 @@ def test_fuzz_random_frames_through_one_context(device, oracle):
     every lane layout, lines, an indexed mesh, sprites, depth-sorted draws), all through the same context so that arenas,
     slots and work lists are reused in every state the previous frame left them in."""
     import dataclasses
-    g = np.random.default_rng(2026)
+    g = np.random.default_rng(int(os.environ.get("RF_FUZZ_SEED", "2026")))  # other seeds: scratch/emu_fuzz.sh
     kinds = ["color3", "uv", "disc", "lit", "color4", "checker", "normal", "texclamp", "lanes8"]
     fmts = [rf.FMT_RGBA8888, rf.FMT_XRGB8888, rf.FMT_ARGB8888, rf.FMT_BGRA8888, rf.FMT_RGB888, rf.FMT_RGB565, rf.FMT_RGBA4444]
-    for frame in range(100):
+    for frame in range(int(os.environ.get("RF_FUZZ_FRAMES", "100"))):
         w, h = int(g.integers(33, 700)), int(g.integers(33, 420))
         ctx = rf.Context(face_cull=[None, rf.FaceCull.Back, rf.FaceCull.Front][g.integers(0, 3)],
                          depth_test=[None, rf.Ordering.Less, rf.Ordering.Less, rf.Ordering.Greater][g.integers(0, 4)],
