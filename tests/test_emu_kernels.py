@@ -49,3 +49,10 @@ if os.environ.get("RF_EMU_FULL") != "1":
 for _name in dir(G):
     if _name.startswith("test_") and _name not in SKIP:
         globals()[_name] = getattr(G, _name)
+
+
+def test_fuzz_first_frames_under_emulation(device, oracle, monkeypatch):
+    """The first 20 frames of the seeded fuzz (the GPU suite runs all 100); scratch/emu_fuzz.sh runs other seeds."""
+    if "RF_FUZZ_FRAMES" not in os.environ:
+        monkeypatch.setenv("RF_FUZZ_FRAMES", "20")
+    G.test_fuzz_random_frames_through_one_context(device, oracle)

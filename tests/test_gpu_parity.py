@@ -579,4 +579,13 @@ def test_fuzz_random_frames_through_one_context(device, oracle):
                 draws.append(dataclasses.replace(d, face_cull=ctx.face_cull or 0, depth_test=ctx.depth_test or 0, color_write=ctx.color_write,
                                                  depth_write=ctx.depth_write))
         sc = scenes.Scene(f"fuzz-{frame}", w, h, fmts[g.integers(0, len(fmts))], bool(g.integers(0, 5) > 0), ctx, draws)
-        check(device, oracle, sc)
+        try:
+            want = run_oracle(oracle, sc)
+        except rf.RetrofireError as e:
+            # a frame the reference would panic on (a span outside the target, render/target.rs:148,173): the same status must
+            # come back from the device path, and the context must keep working for the frames after it
+            with pytest.raises(rf.RetrofireError) as ge:
+                run_gpu(device, sc)
+            assert ge.value.status == e.status, (sc.name, ge.value, e)
+            continue
+        assert_parity(run_gpu(device, sc), want, name=sc.name)
