@@ -10,6 +10,8 @@ import retrofire_b200 as rf
 from retrofire_b200 import scenes
 from tests.parity import assert_parity, run_gpu, run_oracle
 
+f32 = np.float32
+
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -292,6 +294,52 @@ def test_very_deep_tile_bin(device, oracle):
                       [rf.DrawCall.make(tris, verts, rf.shader.new(rf.VS_MVP, rf.FS_COLOR3F), mx.perspective(1.0, w / h, 0.5, 50.0),
                                         mx.viewport((0, h), (w, 0)), ctx)])
     check(device, oracle, sc)
+
+
+@pytest.mark.parametrize("dtest", ["less", "none"])
+@pytest.mark.parametrize("persp", [False, True])
+@pytest.mark.parametrize("size", [(64, 32), (128, 128), (33, 17)])
+def test_lattice_ties(device, oracle, size, persp, dtest):
+    """Every tie the fill rule has to break, thousands of times: vertices on a half-pixel lattice (pixel centres, pixel corners,
+    horizontal and vertical edges through centres), coordinates exactly on and just outside the six clip planes (on-plane =
+    inside, clip.rs:108-111), zero-area and repeated triangles (equal depths: `curr < new` fails the second one, ctx.rs:86-89),
+    w = 0 vertices in the perspective variant. Power-of-two targets make the viewport arithmetic exact; the 33x17 one does not.
+    Without a depth test every fragment is written, so the frame is decided by submission order alone, ≈ 100 layers deep."""
+    w, h = size
+    g = np.random.default_rng(w * 1000 + h + int(persp))
+    n = 3000
+    lx = g.integers(-w - 4, w + 5, (n, 3, 1)).astype(f32) / f32(w)        # screen x = k/2 pixels, a few columns beyond the planes
+    ly = g.integers(-h - 4, h + 5, (n, 3, 1)).astype(f32) / f32(h)
+    c = g.integers(0, 4, (n, 1, 2)).astype(f32) / f32(4)
+    small = g.integers(0, 2, (n, 1, 1)).astype(bool)                       # half of them small: centre + a few lattice steps
+    sx = (g.integers(-w, w, (n, 1, 1)) + g.integers(-6, 7, (n, 3, 1))).astype(f32) / f32(w)
+    sy = (g.integers(-h, h, (n, 1, 1)) + g.integers(-6, 7, (n, 3, 1))).astype(f32) / f32(h)
+    x = np.where(small, sx, lx); y = np.where(small, sy, ly)
+    z = g.choice(np.array([-1.25, -1.0, -0.5, 0.0, 0.25, 0.5, 1.0, 1.25], f32), (n, 3, 1))
+    z = np.where(g.integers(0, 3, (n, 1, 1)) == 0, z[:, :1], z)            # a third of them at constant depth
+    pos = np.concatenate([x, y, z], 2).astype(f32)
+    pos[n // 2:n // 2 + 200] = pos[:200]                                   # exact repeats later in submission order
+    pos[100:140, 2] = pos[100:140, 0]                                      # zero-area: two equal vertices
+    attr = g.integers(0, 5, (n, 3, 3)).astype(f32) / f32(4)
+    verts = np.concatenate([pos, attr], 2).reshape(3 * n, -1).astype(f32)
+    tris = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    mvp = np.eye(4, dtype=f32)
+    if persp:
+        mvp[3] = [0, 0, 1, 1]                                              # w = z + 1: 0 at z = -1, the near plane at z = -0.5
+    ctx = rf.Context(face_cull=None, depth_test=rf.Ordering.Less if dtest == "less" else None)
+    shd = rf.shader.new(rf.VS_MVP, rf.FS_COLOR3F)
+    from retrofire_b200 import mathx as mx
+    sc = scenes.Scene(f"lattice_{w}x{h}_{int(persp)}", w, h, rf.FMT_RGBA8888, True, ctx,
+                      [rf.DrawCall.make(tris, verts, shd, mvp, mx.viewport((0, h), (w, 0)), ctx)])
+    try:
+        want = run_oracle(oracle, sc)
+    except rf.RetrofireError as e:      # the reference would panic (span outside the target): the ABI must report the same
+        with pytest.raises(rf.RetrofireError) as ge:
+            run_gpu(device, sc)
+        assert ge.value.status == e.status
+        return
+    assert want[2].frags.i > 1000, "the lattice scene must actually rasterise"
+    assert_parity(run_gpu(device, sc), want, name=sc.name)
 
 
 def test_nan_and_inf_vertices_behave_like_the_reference(device, oracle):
