@@ -342,6 +342,50 @@ def test_lattice_ties(device, oracle, size, persp, dtest):
     assert_parity(run_gpu(device, sc), want, name=sc.name)
 
 
+@pytest.mark.parametrize("persp", [False, True])
+@pytest.mark.parametrize("size", [(64, 32), (33, 17)])
+def test_lattice_lines(device, oracle, size, persp):
+    """Line segments (raster.rs:122-177) with end points on the half-pixel lattice: exact 45-degree slopes (|dx| == |dy| picks the
+    major axis by a tie), axis-aligned and zero-length segments, end points on and beyond the near/far planes; mixed with lattice
+    triangles submitted before them, no depth test, so submission order decides every pixel."""
+    w, h = size
+    g = np.random.default_rng(w * 77 + h + int(persp))
+    n = 2500
+    # end points stay inside the x/y planes (a segment ending on the right or bottom plane indexes one past the target and panics
+    # in the reference); z crosses the near and far planes
+    x0 = g.integers(-w + 12, w - 11, (n, 1, 1)); y0 = g.integers(-h + 12, h - 11, (n, 1, 1))
+    dx = g.integers(-10, 11, (n, 1, 1)); dy = g.integers(-10, 11, (n, 1, 1))
+    k = n // 5
+    dy[:k] = dx[:k]; dy[k:2 * k] = -dx[k:2 * k]; dy[2 * k:2 * k + 100] = 0; dx[2 * k + 100:2 * k + 200] = 0; dx[2 * k + 200:2 * k + 220] = 0; dy[2 * k + 200:2 * k + 220] = 0
+    x = np.concatenate([x0, x0 + dx], 1).astype(f32) / f32(w)
+    y = np.concatenate([y0, y0 + dy], 1).astype(f32) / f32(h)
+    z = g.choice(np.array([-1.25, -1.0, -0.5, 0.0, 0.25, 0.5, 1.0, 1.25], f32), (n, 2, 1))
+    attr = g.integers(0, 5, (n, 2, 3)).astype(f32) / f32(4)
+    verts = np.concatenate([x, y, z, attr], 2).reshape(2 * n, -1).astype(f32)
+    edges = np.arange(2 * n, dtype=np.uint32).reshape(n, 2)
+    g.shuffle(edges)
+    mvp = np.eye(4, dtype=f32)
+    if persp:
+        mvp[3] = [0, 0, 1, 1]
+    from retrofire_b200 import mathx as mx
+    ctx = rf.Context(face_cull=None, depth_test=None)
+    shd = rf.shader.new(rf.VS_MVP, rf.FS_COLOR3F)
+    vp = mx.viewport((0, h), (w, 0))
+    tri_verts = verts[: 3 * (2 * n // 3)]
+    tris = np.arange(tri_verts.shape[0], dtype=np.uint32).reshape(-1, 3)[:300]
+    sc = scenes.Scene(f"lattice_lines_{w}x{h}_{int(persp)}", w, h, rf.FMT_RGBA8888, True, ctx,
+                      [rf.DrawCall.make(tris, tri_verts, shd, mvp, vp, ctx), rf.DrawCall.make(edges, verts, shd, mvp, vp, ctx, edges=True)])
+    try:
+        want = run_oracle(oracle, sc)
+    except rf.RetrofireError as e:
+        with pytest.raises(rf.RetrofireError) as ge:
+            run_gpu(device, sc)
+        assert ge.value.status == e.status
+        return
+    assert want[2].frags.i > 1000
+    assert_parity(run_gpu(device, sc), want, name=sc.name)
+
+
 def test_nan_and_inf_vertices_behave_like_the_reference(device, oracle):
     """NaN / infinite positions and attributes: outcodes treat NaN as inside (`d > 0.0` is false), saturating
     casts map NaN to 0 rows — the CUDA path must make exactly the oracle's decisions."""
