@@ -343,6 +343,53 @@ def test_lattice_ties(device, oracle, size, persp, dtest):
 
 
 @pytest.mark.parametrize("persp", [False, True])
+@pytest.mark.parametrize("kind", ["checker", "disc", "uv_repeat", "texclamp", "lit"])
+def test_lattice_shader_ties(device, oracle, kind, persp):
+    """Shader decisions on exact ties: attribute values on a quarter lattice over half-pixel lattice triangles, so interpolated
+    values land exactly on the checker's 0.5 (crates.rs:33-36, strict `>`), on the sprite disc's d2 = 1 (sprites.rs:46-52, strict
+    `<` or discard), on texel boundaries of the clamp / repeat samplers (tex.rs:218-304) and on negative coordinates."""
+    w, h = 64, 64
+    g = np.random.default_rng(len(kind) * 10 + int(persp))
+    n = 1500
+    cx = g.integers(-w, w, (n, 1, 1)); cy = g.integers(-h, h, (n, 1, 1))
+    x = (cx + g.integers(-16, 17, (n, 3, 1))).astype(f32) / f32(w)
+    y = (cy + g.integers(-16, 17, (n, 3, 1))).astype(f32) / f32(h)
+    z = g.choice(np.array([-0.5, 0.0, 0.0, 0.25, 0.5, 1.0], f32), (n, 3, 1))
+    z = np.where(g.integers(0, 2, (n, 1, 1)) == 0, z[:, :1], z)
+    uv = g.integers(-4, 9, (n, 3, 2)).astype(f32) / f32(4)                  # -1 .. 2 in quarters
+    if kind == "checker":
+        attr, shd = uv, rf.shader.new(rf.VS_MVP, rf.FS_CHECKER)
+    elif kind == "disc":
+        attr, shd = g.integers(-4, 5, (n, 3, 2)).astype(f32) / f32(4), rf.shader.new(rf.VS_MVP, rf.FS_SPRITE_DISC)
+    elif kind == "uv_repeat":
+        attr, shd = uv, rf.shader.new(rf.VS_MVP, rf.FS_TEX_REPEAT_POT, texture=rf.Texture(g.integers(0, 256, (8, 8, 3), dtype=np.uint8)))
+    elif kind == "texclamp":
+        attr, shd = uv, rf.shader.new(rf.VS_MVP, rf.FS_TEX_CLAMP, texture=rf.Texture(g.integers(0, 256, (8, 4, 4), dtype=np.uint8)))
+    else:
+        nrm = g.integers(-2, 3, (n, 3, 3)).astype(f32) / f32(2)
+        attr = np.concatenate([nrm, uv], 2)
+        shd = rf.shader.new(rf.VS_MVP, rf.FS_TEX_CLAMP_LIT, fs_uniform=[0.0, 0.0, -1.0], texture=rf.Texture(g.integers(0, 256, (16, 16, 3), dtype=np.uint8)))
+    verts = np.concatenate([x, y, z, attr.astype(f32)], 2).reshape(3 * n, -1).astype(f32)
+    tris = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    mvp = np.eye(4, dtype=f32)
+    if persp:
+        mvp[3] = [0, 0, 1, 1]
+    from retrofire_b200 import mathx as mx
+    ctx = rf.Context(face_cull=None, depth_test=rf.Ordering.Less if persp else None)   # w = 1 everywhere: equal depths, shade them all
+    sc = scenes.Scene(f"lattice_{kind}_{int(persp)}", w, h, rf.FMT_RGBA8888, True, ctx,
+                      [rf.DrawCall.make(tris, verts, shd, mvp, mx.viewport((0, h), (w, 0)), ctx)])
+    try:
+        want = run_oracle(oracle, sc)
+    except rf.RetrofireError as e:
+        with pytest.raises(rf.RetrofireError) as ge:
+            run_gpu(device, sc)
+        assert ge.value.status == e.status
+        return
+    assert want[2].frags.i > 1000
+    assert_parity(run_gpu(device, sc), want, name=sc.name)
+
+
+@pytest.mark.parametrize("persp", [False, True])
 @pytest.mark.parametrize("size", [(64, 32), (33, 17)])
 def test_lattice_lines(device, oracle, size, persp):
     """Line segments (raster.rs:122-177) with end points on the half-pixel lattice: exact 45-degree slopes (|dx| == |dy| picks the
