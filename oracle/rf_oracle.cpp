@@ -53,6 +53,10 @@ inline uint8_t sat_u8(float f) {
 }
 
 // math/vec.rs:231-238 — dot() folds from Sc::zero(): (((0 + a0*b0) + a1*b1) + ...)
+// f32::max (used by the demo shaders, solids.rs:75, crates.rs:44): "if one of the arguments is NaN, the other is returned" —
+// std::max(NaN, x) would return the NaN. NaN reaches the shaders through dv_dx = 0 * (1 / 0) on zero-width first rows.
+inline float rust_max(float a, float b) { return a != a ? b : (b != b ? a : (a < b ? b : a)); }
+
 inline float dot4(const float* a, const float* b) {
   float acc = 0.0f;
   for (int i = 0; i < 4; i++) acc = acc + a[i] * b[i];
@@ -161,7 +165,7 @@ void shade_vertex(const rf_draw& d, const float* vin, ClipVert& cv) {
       // Mat4::apply(Vec3): homogeneous w = 0, rows 0..2   (mat.rs:922-926)
       float nh[4] = {a[0], a[1], a[2], 0.0f};
       float nz = dot4(spin + 8, nh);
-      float diffuse = std::max(nz + 0.2f, 0.2f) * 0.8f;
+      float diffuse = rust_max(nz + 0.2f, 0.2f) * 0.8f;
       // 0.45 * (n + splat(1.1)) -> (n + 1.1) * 0.45 ; diffuse * rgb -> c * diffuse
       for (int i = 0; i < 3; i++) cv.attr[i] = ((a[i] + 1.1f) * 0.45f) * diffuse;
       apply_proj(mvp, vin, cv.pos);
@@ -243,7 +247,7 @@ bool shade_fragment(const rf_draw& d, const Tex* tex, const float* var, uint8_t 
       return true;
     }
     case RF_FS_TEX_CLAMP_LIT: {  // crates.rs:42-47
-      float ndl = std::max(dot3(var, d.fs_uniform), 0.0f);
+      float ndl = rust_max(dot3(var, d.fs_uniform), 0.0f);
       float kd = 0.4f + (1.0f - 0.4f) * ndl;  // lerp(t, 0.4, 1.0), math.rs:30-32
       uint8_t c[4];
       sample_clamp(*tex, var[3], var[4], c);

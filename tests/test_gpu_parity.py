@@ -433,6 +433,13 @@ def test_lattice_lines(device, oracle, size, persp):
     assert_parity(run_gpu(device, sc), want, name=sc.name)
 
 
+def test_nan_in_shader_max_is_ignored(device, oracle):
+    """`f32::max` drops a NaN argument (crates.rs:44, solids.rs:75); the oracle side is pinned in tests/test_oracle_golden.py."""
+    from tests.test_oracle_golden import nan_max_scenes
+    for sc in nan_max_scenes():
+        check(device, oracle, sc)
+
+
 def test_nan_and_inf_vertices_behave_like_the_reference(device, oracle):
     """NaN / infinite positions and attributes: outcodes treat NaN as inside (`d > 0.0` is false), saturating
     casts map NaN to 0 rows — the CUDA path must make exactly the oracle's decisions."""

@@ -279,3 +279,39 @@ def test_depth_sort_restatement_equals_presorted_submission(oracle, order):
     assert (c_sorted == c_manual).all() and (z_sorted.view(np.uint32) == z_manual.view(np.uint32)).all()
     assert st_sorted.counters() == st_manual.counters()
     assert (c_sorted != c_plain).any()
+
+
+def nan_max_scenes():
+    """Two one-triangle scenes whose shaders see NaN in a `max` (also rendered on the device by tests/test_gpu_parity.py)."""
+    from retrofire_b200 import mathx as mx
+    f32 = np.float32
+    pos = np.array([[-1, 1, 0], [1, 1, 0], [0, -1, 0]], f32)
+    vp = mx.viewport((0, 32), (32, 0))
+    ctx = rf.Context(face_cull=None, depth_test=None)
+    tris = np.array([[0, 1, 2]], np.uint32)
+    # crates shader: NaN normals, uv = 0 -> texel (0, 0) = (200, 100, 50) scaled by exactly 0.4
+    tex = np.zeros((4, 4, 3), np.uint8); tex[0, 0] = (200, 100, 50)
+    attr = np.concatenate([np.full((3, 3), np.nan, f32), np.zeros((3, 2), f32)], 1)
+    shd = rf.shader.new(rf.VS_MVP, rf.FS_TEX_CLAMP_LIT, fs_uniform=[0.0, 0.0, -1.0], texture=rf.Texture(tex))
+    lit = scenes.Scene("nanmax", 32, 32, rf.FMT_RGBA8888, False, ctx, [rf.DrawCall.make(tris, np.concatenate([pos, attr], 1), shd, np.eye(4, dtype=f32), vp, ctx)])
+    # solids vertex shader: NaN spin matrix -> diffuse = 0.2 * 0.8, colour = ((n + 1.1) * 0.45) * diffuse with n = 0
+    uni = (np.eye(4, dtype=f32), np.full((4, 4), np.nan, f32))
+    shd = rf.shader.new(rf.VS_SOLIDS, rf.FS_COLOR3F)
+    solids = scenes.Scene("nanmax2", 32, 32, rf.FMT_RGBA8888, False, ctx, [rf.DrawCall.make(tris, np.concatenate([pos, np.zeros((3, 3), f32)], 1), shd, uni, vp, ctx)])
+    return lit, solids
+
+
+def test_shader_max_ignores_nan_like_f32_max(oracle):
+    """`f32::max` returns the other argument when one is NaN (Rust std), so `n.dot(&light_dir).max(0.0)` (crates.rs:44) with a NaN
+    normal gives kd = lerp(0, 0.4, 1.0) = 0.4, and `(norm.z() + 0.2).max(0.2)` (solids.rs:75) gives 0.2 — not NaN (black), which is
+    what C's std::max would produce. Found by tests/test_gpu_parity.py::test_lattice_shader_ties (zero-width first rows make
+    dv_dx = 0 * inf = NaN)."""
+    f32 = np.float32
+    lit, solids = nan_max_scenes()
+    tgt, st = run_scene(oracle, lit)
+    img = tgt.host_color()
+    want = [int(f32(256) * ((f32(c) / f32(256)) * f32(0.4))) for c in (200, 100, 50)] + [255]
+    assert st.frags.o > 100 and img[16, 16].tolist() == want, (img[16, 16], want)
+    tgt, st = run_scene(oracle, solids)
+    c = (f32(0) + f32(1.1)) * f32(0.45) * (f32(0.2) * f32(0.8))
+    assert tgt.host_color()[16, 16].tolist() == [int(f32(256) * c)] * 3 + [255], tgt.host_color()[16, 16]
