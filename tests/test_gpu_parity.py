@@ -296,7 +296,7 @@ def test_very_deep_tile_bin(device, oracle):
     check(device, oracle, sc)
 
 
-@pytest.mark.parametrize("dtest", ["less", "none"])
+@pytest.mark.parametrize("dtest", ["less", "none", "none-back-to-front", "none-front-to-back"])
 @pytest.mark.parametrize("persp", [False, True])
 @pytest.mark.parametrize("size", [(64, 32), (128, 128), (33, 17)])
 def test_lattice_ties(device, oracle, size, persp, dtest):
@@ -326,7 +326,10 @@ def test_lattice_ties(device, oracle, size, persp, dtest):
     mvp = np.eye(4, dtype=f32)
     if persp:
         mvp[3] = [0, 0, 1, 1]                                              # w = z + 1: 0 at z = -1, the near plane at z = -0.5
-    ctx = rf.Context(face_cull=None, depth_test=rf.Ordering.Less if dtest == "less" else None)
+    # depth-sorted variants: z comes from eight lattice values, so hundreds of triangles share a sort key and only the defined
+    # tie order (primitive order, DESIGN §4 "Depth sort") keeps the frame deterministic
+    dsort = {"none-back-to-front": rf.DepthSort.BackToFront, "none-front-to-back": rf.DepthSort.FrontToBack}.get(dtest)
+    ctx = rf.Context(face_cull=None, depth_test=rf.Ordering.Less if dtest == "less" else None, depth_sort=dsort)
     shd = rf.shader.new(rf.VS_MVP, rf.FS_COLOR3F)
     from retrofire_b200 import mathx as mx
     sc = scenes.Scene(f"lattice_{w}x{h}_{int(persp)}", w, h, rf.FMT_RGBA8888, True, ctx,
