@@ -341,8 +341,15 @@ def test_lattice_ties(device, oracle, size, persp, dtest):
             run_gpu(device, sc)
         assert ge.value.status == e.status
         return
-    assert want[2].frags.i > 1000, "the lattice scene must actually rasterise"
+    assert want[2].frags.i > min(1000, w * h * 50), "the lattice scene must actually rasterise"
     assert_parity(run_gpu(device, sc), want, name=sc.name)
+
+
+@pytest.mark.parametrize("size", [(1, 1), (2, 3), (7, 5), (31, 33), (32, 32), (65, 1), (1, 70)])
+def test_lattice_ties_tiny_targets(device, oracle, size):
+    """Targets smaller than, equal to and one pixel past a 32x32 tile, and one-pixel-wide strips."""
+    test_lattice_ties(device, oracle, size, True, "less")
+    test_lattice_ties(device, oracle, size, False, "none")
 
 
 @pytest.mark.parametrize("persp", [False, True])
@@ -692,6 +699,31 @@ def test_row_band_sharding_matches_oracle_band(device, oracle):
     band = lambda r: (r[0][100:260], r[1][100:260], r[2])
     assert_parity(band(got), band(want), name="band")
     assert not got[0][:100].any() and not got[0][260:].any(), "rows outside the band must stay untouched"
+
+
+@pytest.mark.parametrize("kind", ["soup", "lines"])
+def test_row_bands_of_any_height_tile_the_frame(device, oracle, kind):
+    """Bands that ignore the 32-row tile grid — one row, a tile boundary minus one, empty tail — each equal to the oracle's band,
+    and together equal to the unsharded frame (pixels and fragment counters)."""
+    w, h = 200, 150
+    sc = scenes.random_soup(1500, w, h, seed=77, lanes_kind="lit", big=True) if kind == "soup" else scenes.random_lines(1500, w, h, seed=78)
+    whole = run_oracle(oracle, sc)
+    cuts = [0, 1, 31, 32, 33, 97, 98, 149, 150]
+    color = np.zeros_like(whole[0]); depth = np.zeros_like(whole[1]); fi = fo = 0
+    for y0, y1 in zip(cuts[:-1], cuts[1:]):
+        device.set_row_band(y0, y1)
+        try:
+            got = run_gpu(device, sc)
+        finally:
+            device.set_row_band(0, 0xFFFFFFFF)
+        want = run_oracle(oracle, sc, band=(y0, y1))
+        band = lambda r: (r[0][y0:y1], r[1][y0:y1], r[2])
+        assert_parity(band(got), band(want), name=f"band {y0}:{y1}")
+        assert not got[0][:y0].any() and not got[0][y1:].any(), "rows outside the band must stay untouched"
+        color[y0:y1] = got[0][y0:y1]; depth[y0:y1] = got[1][y0:y1]
+        fi += got[2].frags.i; fo += got[2].frags.o
+    assert (color == whole[0]).all() and (depth.view(np.uint32) == whole[1].view(np.uint32)).all()
+    assert (fi, fo) == (whole[2].frags.i, whole[2].frags.o)
 
 
 def test_fuzz_random_frames_through_one_context(device, oracle):
