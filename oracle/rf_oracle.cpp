@@ -52,11 +52,11 @@ inline uint8_t sat_u8(float f) {
   return (uint8_t)f;
 }
 
-// math/vec.rs:231-238 — dot() folds from Sc::zero(): (((0 + a0*b0) + a1*b1) + ...)
 // f32::max (used by the demo shaders, solids.rs:75, crates.rs:44): "if one of the arguments is NaN, the other is returned" —
 // std::max(NaN, x) would return the NaN. NaN reaches the shaders through dv_dx = 0 * (1 / 0) on zero-width first rows.
 inline float rust_max(float a, float b) { return a != a ? b : (b != b ? a : (a < b ? b : a)); }
 
+// math/vec.rs:231-238 — dot() folds from Sc::zero(): (((0 + a0*b0) + a1*b1) + ...)
 inline float dot4(const float* a, const float* b) {
   float acc = 0.0f;
   for (int i = 0; i < 4; i++) acc = acc + a[i] * b[i];
