@@ -151,6 +151,24 @@ def test_many_small_draws_one_pass(device, oracle):
     check(device, oracle, base)
 
 
+@pytest.mark.parametrize("vary", ["verts", "prims", "both", "neither"])
+def test_equal_and_unequal_draw_sizes_in_one_pass(device, oracle, vary):
+    """A pass finds a vertex's / primitive's draw by one division when every draw has the same count, by binary search otherwise
+    (`find_draw`): all four combinations, with different data per draw."""
+    import dataclasses
+    draws = []
+    for k in range(37):
+        nt = 20 + (k % 5 if vary in ("prims", "both") else 0)
+        sc = scenes.random_soup(30, 300, 200, seed=500 + k, lanes_kind="color3", big=bool(k & 1))
+        d = sc.draws[0]
+        verts = d.verts if vary in ("neither", "prims") else np.ascontiguousarray(d.verts[: 90 - 3 * (k % 4)])
+        nv = verts.shape[0] // 3
+        prims = np.ascontiguousarray(d.prims[np.arange(nt) % nv])          # triangles reused when the draw has fewer than nt
+        draws.append(dataclasses.replace(d, prims=prims, verts=verts))
+    sc.draws = draws
+    check(device, oracle, sc)
+
+
 def test_render_many_equals_individual_calls(device, oracle):
     """rf_render_many: a frame's list of render() calls in one crossing of the C ABI; re-submitting the same list reuses the
     marshalled array, a changed list does not."""
