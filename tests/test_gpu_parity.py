@@ -461,6 +461,48 @@ def test_lattice_lines(device, oracle, size, persp):
     assert_parity(run_gpu(device, sc), want, name=sc.name)
 
 
+@pytest.mark.parametrize("persp", [False, True])
+@pytest.mark.parametrize("size", [(64, 64), (200, 120)])
+def test_lattice_grid_mesh_shared_edges(device, oracle, size, persp):
+    """An indexed grid mesh (every interior vertex shared by six triangles: the screen-vertex path of k_assemble) whose vertices are
+    jittered on the half-pixel lattice and whose border lies exactly on the clip planes, no depth test. The reference's own
+    "no gaps, no overdraw" KAT (raster.rs:326-368) does NOT generalise to such a mesh: a shared edge is the long edge of one
+    triangle (split at `mid1`, a rounded point, and re-walked from there) and a short edge of its neighbour, so where it passes
+    exactly through pixel centres the two walks can disagree — the oracle covers 4,110 fragments on the 4,096-pixel target. The
+    device path has to reproduce exactly that: same double-covered pixels, same winner by submission order, same counters."""
+    w, h = size
+    cell = 4                                              # pixels per cell
+    nx, ny = w // cell, h // cell
+    g = np.random.default_rng(w + h + int(persp))
+    gx, gy = np.meshgrid(np.arange(nx + 1) * cell * 2, np.arange(ny + 1) * cell * 2)    # in half pixels
+    jx = g.integers(-2, 3, gx.shape); jy = g.integers(-2, 3, gy.shape)                   # ±1 px in 4-px cells: every quad stays convex
+    jx[:, 0] = jx[:, -1] = 0; jy[0, :] = jy[-1, :] = 0
+    x = (gx + jx).astype(f32) / f32(w) - f32(1); y = (gy + jy).astype(f32) / f32(h) - f32(1)
+    z = g.choice(np.array([0.0, 0.25, 0.5, 1.0], f32), gx.shape) if persp else np.zeros(gx.shape, f32)
+    col = g.integers(0, 5, gx.shape + (3,)).astype(f32) / f32(4)
+    if persp:                                             # mvp below makes w_clip = z + 1: pre-multiply so x/w, y/w stay on the lattice
+        x = x * (z + f32(1)); y = y * (z + f32(1))
+    verts = np.concatenate([x[..., None], y[..., None], z[..., None], col], 2).reshape(-1, 6).astype(f32)
+    i = (np.arange(ny)[:, None] * (nx + 1) + np.arange(nx)[None, :]).reshape(-1)
+    flip = g.integers(0, 2, i.shape).astype(bool)         # either diagonal per cell
+    a, b, c, d = i, i + 1, i + nx + 1, i + nx + 2
+    t1 = np.where(flip[:, None], np.stack([a, b, d], 1), np.stack([a, b, c], 1))
+    t2 = np.where(flip[:, None], np.stack([a, d, c], 1), np.stack([b, d, c], 1))
+    tris = np.concatenate([t1, t2]).astype(np.uint32)
+    g.shuffle(tris)
+    mvp = np.eye(4, dtype=f32)
+    if persp:
+        mvp[3] = [0, 0, 1, 1]
+    from retrofire_b200 import mathx as mx
+    ctx = rf.Context(face_cull=None, depth_test=None)
+    sc = scenes.Scene(f"grid_{w}x{h}_{int(persp)}", w, h, rf.FMT_RGBA8888, True, ctx,
+                      [rf.DrawCall.make(tris, verts, rf.shader.new(rf.VS_MVP, rf.FS_COLOR3F), mvp, mx.viewport((0, h), (w, 0)), ctx)])
+    got = run_gpu(device, sc)
+    want = run_oracle(oracle, sc)
+    assert want[2].frags.i >= w * h - 50 and want[2].frags.i != w * h, want[2]   # nearly, but not exactly, once per pixel
+    assert_parity(got, want, name=sc.name)
+
+
 def test_nan_in_shader_max_is_ignored(device, oracle):
     """`f32::max` drops a NaN argument (crates.rs:44, solids.rs:75); the oracle side is pinned in tests/test_oracle_golden.py."""
     from tests.test_oracle_golden import nan_max_scenes
