@@ -503,6 +503,38 @@ def test_lattice_grid_mesh_shared_edges(device, oracle, size, persp):
     assert_parity(got, want, name=sc.name)
 
 
+def ndc_soup(n, w, h, seed, persp, extent=1.0):
+    """Random triangles given directly in NDC (identity matrix, or w = z + 1), spanning up to the whole target whatever its aspect."""
+    from retrofire_b200 import mathx as mx
+    g = np.random.default_rng(seed)
+    c = g.uniform(-1.1, 1.1, (n, 1, 2)).astype(f32)
+    xy = c + g.uniform(-extent, extent, (n, 3, 2)).astype(f32) * g.uniform(0.02, 1.0, (n, 1, 1)).astype(f32)
+    z = g.uniform(-0.6 if persp else -1.1, 1.1, (n, 3, 1)).astype(f32)
+    if persp:
+        xy = xy * (z + f32(1))
+    attr = g.uniform(0, 1, (n, 3, 3)).astype(f32)
+    verts = np.concatenate([xy, z, attr], 2).reshape(3 * n, -1).astype(f32)
+    tris = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    mvp = np.eye(4, dtype=f32)
+    if persp:
+        mvp[3] = [0, 0, 1, 1]
+    ctx = rf.Context(face_cull=None)
+    return scenes.Scene(f"ndc_soup_{w}x{h}_{seed}", w, h, rf.FMT_RGBA8888, True, ctx,
+                        [rf.DrawCall.make(tris, verts, rf.shader.new(rf.VS_MVP, rf.FS_COLOR3F), mvp, mx.viewport((0, h), (w, 0)), ctx)])
+
+
+@pytest.mark.parametrize("persp", [False, True])
+@pytest.mark.parametrize("size", [(3000, 40), (40, 3000), (4099, 33), (1, 2500)])
+def test_extreme_aspect_targets(device, oracle, size, persp):
+    """Very wide targets (spans crossing up to 128 tile columns: one checkpoint per column start) and very tall ones (triangles cut
+    into up to 94 chunks of 32 rows), with triangles up to the size of the target."""
+    w, h = size
+    sc = ndc_soup(300, w, h, seed=w + h + int(persp), persp=persp)
+    want = run_oracle(oracle, sc)
+    assert want[2].frags.i > 4 * w * h, want[2]
+    assert_parity(run_gpu(device, sc), want, name=sc.name)
+
+
 def test_nan_in_shader_max_is_ignored(device, oracle):
     """`f32::max` drops a NaN argument (crates.rs:44, solids.rs:75); the oracle side is pinned in tests/test_oracle_golden.py."""
     from tests.test_oracle_golden import nan_max_scenes
