@@ -208,6 +208,45 @@ def test_frame_batch_render_frames(device, oracle):
     assert got_stats.counters() == want_total.counters()
 
 
+def test_frame_batch_with_empty_and_nan_frames(device, oracle):
+    """A frame batch in which some frames draw nothing (the mesh is behind the camera, or scaled to a point) and one frame's
+    matrix is NaN: every frame must still equal its own oracle frame, and the empty ones must keep their clear values."""
+    import dataclasses
+    verts, faces = scenes.bunny_mesh(0)
+    base = scenes.bunny(subdiv=0, theta=0.3, w=320, h=200)
+    d0 = base.draws[0]
+    uniforms = []
+    for f in range(9):
+        u = scenes.bunny(subdiv=0, theta=0.4 * f, w=320, h=200).draws[0].uniform.copy()
+        if f in (1, 5):
+            u[:16] = -u[:16]            # clip position negated: w < 0, everything outside
+        if f == 3:
+            u[:16] = 0; u[15] = 1       # every vertex at the clip-space origin: zero-area triangles
+        if f == 7:
+            u[:16] = np.nan
+        uniforms.append(u)
+    mesh = device.mesh(faces, verts)
+    call = dataclasses.replace(d0, mesh=mesh)
+    targets = [device.framebuf(320, 200, base.fmt, True) for _ in uniforms]
+    try:
+        for t in targets:
+            t.clear(base.ctx)
+        device.stats(reset=True)
+        device.render_frames(call, targets, np.stack(uniforms))
+        got_stats = device.stats(reset=True)
+        want_total = rf.Stats()
+        for f, (u, t) in enumerate(zip(uniforms, targets)):
+            sc = scenes.Scene(f"frame-{f}", 320, 200, base.fmt, True, base.ctx, [dataclasses.replace(d0, uniform=u)])
+            wc, wd, ws = run_oracle(oracle, sc)
+            want_total += ws
+            assert np.array_equal(t.download_color(), wc), f
+            assert np.array_equal(t.download_depth().view(np.uint32), wd.view(np.uint32)), f
+        assert got_stats.counters() == want_total.counters()
+    finally:
+        for t in targets:
+            t._destroy(); device._targets.remove(t)
+
+
 def test_targets_of_different_sizes_in_one_pass(device, oracle):
     """Three targets of different sizes and formats drawn in ONE pass: the rasteriser then finds a tile's target by binary
     search over the tile bases (frame batches of equal targets use tile / tiles_per_target instead); twice, so that the second
