@@ -673,6 +673,41 @@ def test_object_culling_on_the_device(device, oracle):
     assert e.value.status == rf.RF_E_INVALID
 
 
+@pytest.mark.parametrize("persp", [False, True])
+def test_object_culling_ties(device, oracle, persp):
+    """`BBox::visibility` (scene.rs:59-87) decided on ties: 400 objects whose boxes have corners on a lattice, many touching a
+    clip plane exactly from outside or inside, degenerate (flat or point) boxes, boxes behind w = 0. Frame, Stats and objs.o must
+    equal the oracle's; which objects are skipped is visible in `calls` and `prims.i`."""
+    import dataclasses
+    from retrofire_b200 import mathx as mx
+    g = np.random.default_rng(91 + int(persp))
+    w, h = 96, 64
+    mvp = np.eye(4, dtype=f32)
+    if persp:
+        mvp[3] = [0, 0, 1, 1]
+    ctx = rf.Context(face_cull=None)
+    shd = rf.shader.new(rf.VS_MVP, rf.FS_COLOR3F)
+    vp = mx.viewport((0, h), (w, 0))
+    draws = []
+    for k in range(400):
+        lo = g.integers(-6, 6, 3).astype(f32) / f32(4)                       # -1.5 .. 1.25 in quarters
+        ext = g.integers(0, 4, 3).astype(f32) / f32(4) * g.integers(0, 2, 3).astype(f32)   # some axes flat
+        hi = lo + ext
+        # geometry strictly inside its box (the reference trusts the box), two triangles
+        t = g.uniform(0, 1, (6, 3)).astype(f32)
+        pos = lo + (hi - lo) * t
+        verts = np.concatenate([pos, g.uniform(0, 1, (6, 3)).astype(f32)], 1).astype(f32)
+        d = rf.DrawCall.make(np.array([[0, 1, 2], [3, 4, 5]], np.uint32), verts, shd, mvp, vp, ctx)
+        draws.append(dataclasses.replace(d, bbox=np.stack([lo, hi]).astype(f32)))
+    sc = scenes.Scene(f"bbox_ties_{int(persp)}", w, h, rf.FMT_RGBA8888, True, ctx, draws)
+    got, want = run_gpu(device, sc), run_oracle(oracle, sc)
+    assert 20 < want[2].objs.o < 380, want[2]
+    # independent of the oracle's C++: numpy outcodes of the eight corners (exact on this lattice)
+    assert want[2].objs.o == sum(not scenes._bbox_hidden(d.bbox, mvp) for d in draws)
+    assert (got[2].objs.i, got[2].objs.o) == (want[2].objs.i, want[2].objs.o) == (400, want[2].objs.o)
+    assert_parity(got, want, name=sc.name)
+
+
 def test_text_as_textured_geometry(device, oracle):
     """render/text.rs + tex.rs Atlas: the hello.rs demo — glyph quads sampled with SamplerClamp from a font
     atlas, swinging through the frustum (including frames where the text crosses the near plane and is clipped)."""
