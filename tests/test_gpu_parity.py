@@ -708,6 +708,47 @@ def test_object_culling_ties(device, oracle, persp):
     assert_parity(got, want, name=sc.name)
 
 
+@pytest.mark.parametrize("fmt", [rf.FMT_RGBA8888, rf.FMT_XRGB8888, rf.FMT_RGB888, rf.FMT_RGB565])
+def test_strided_upload_render_download(device, oracle, fmt):
+    """A frontend-owned pixel slice with a row stride larger than the width (front/src/sdl2.rs:208-217, util/buf.rs:437-439):
+    existing colour and depth contents are uploaded with a stride, a frame is rendered over them WITHOUT a clear (the uploaded
+    depth blocks part of it), and colour / depth are downloaded into strided buffers whose padding must stay untouched."""
+    from oracle import rfo
+    w, h, cs, ds = 150, 90, 157, 153
+    g = np.random.default_rng(int(fmt) + 5)
+    sc = scenes.random_soup(600, w, h, seed=31, lanes_kind="color3", big=True)
+    sc.fmt, sc.clear = fmt, False
+    cont = g.integers(0, 1 << 32, (h, w), dtype=np.uint64).astype(np.uint32) & np.uint32(0xFFFF if fmt == rf.FMT_RGB565 else 0xFFFFFF)
+    depth0 = np.where(g.integers(0, 3, (h, w)) == 0, np.float32(np.inf), g.uniform(0, 0.2, (h, w)).astype(f32)).astype(f32)
+    # oracle: a host target that starts with these contents
+    tgt = oracle.HostTarget(w, h, fmt, True)
+    tgt.color[:] = cont; tgt.depth[:] = depth0
+    want_stats = rf.Stats()
+    for d in sc.draws:
+        want_stats += oracle.render(d, tgt)
+    # device: strided upload, render, strided download
+    host0 = rfo.container_to_host(fmt, cont)
+    pad_shape = (h, cs) + host0.shape[2:]
+    hostbuf = np.full(pad_shape, 0xA5, dtype=host0.dtype); hostbuf[:, :w] = host0
+    depthbuf = np.full((h, ds), -7.0, f32); depthbuf[:, :w] = depth0
+    fb = device.framebuf(w, h, fmt, True)
+    try:
+        device._check(device.lib.rf_target_upload_color(device.h, fb.h, hostbuf.ctypes.data, cs))
+        device._check(device.lib.rf_target_upload_depth(device.h, fb.h, depthbuf.ctypes.data, ds))
+        device.stats(reset=True)
+        for d in sc.draws:
+            device.render(d, fb)
+        got_stats = device.stats(reset=True)
+        out = np.full(pad_shape, 0x5A, dtype=host0.dtype); dout = np.full((h, ds), -9.0, f32)
+        device._check(device.lib.rf_target_download_color(device.h, fb.h, out.ctypes.data, cs))
+        device._check(device.lib.rf_target_download_depth(device.h, fb.h, dout.ctypes.data, ds))
+    finally:
+        fb._destroy(); device._targets.remove(fb)
+    assert np.array_equal(out[:, :w], tgt.host_color()) and np.array_equal(dout[:, :w].view(np.uint32), tgt.depth.view(np.uint32))
+    assert (out[:, w:] == 0x5A).all() and (dout[:, w:] == -9.0).all(), "row padding must not be written"
+    assert got_stats.counters() == want_stats.counters() and 0 < want_stats.frags.o < want_stats.frags.i
+
+
 def test_text_as_textured_geometry(device, oracle):
     """render/text.rs + tex.rs Atlas: the hello.rs demo — glyph quads sampled with SamplerClamp from a font
     atlas, swinging through the frustum (including frames where the text crosses the near plane and is clipped)."""
