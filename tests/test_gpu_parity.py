@@ -749,6 +749,46 @@ def test_strided_upload_render_download(device, oracle, fmt):
     assert got_stats.counters() == want_stats.counters() and 0 < want_stats.frags.o < want_stats.frags.i
 
 
+def test_async_download_profiling_and_device_pointers(device, oracle):
+    """The entry points bench.py's end-to-end and per-kernel legs rely on: `rf_target_download_color_async` into page-locked
+    memory (valid after `rf_sync`), `rf_ctx_profile` / `rf_ctx_kernel_times` / `rf_kernel_name`, `rf_ctx_last_pass`, and the raw
+    device pointers of a target. Profiling serialises the pass; the frame must not change."""
+    sc = scenes.random_soup(800, 320, 200, seed=12, lanes_kind="uv", big=True)
+    want = run_oracle(oracle, sc)
+    fb = device.framebuf(sc.w, sc.h, sc.fmt, True)
+    try:
+        for level in (2, 1, 0):
+            device.profile(level)
+            device.kernel_times()                                   # reset the accumulators
+            fb.clear(sc.ctx)
+            device.stats(reset=True)
+            for d in sc.draws:
+                device.render(d, fb)
+            out = device.pinned_empty((sc.h, sc.w, 4), np.uint8)
+            out[:] = 0x5A
+            fb.download_color_async(out)
+            device.sync()
+            stats = device.stats(reset=True)
+            assert np.array_equal(out, want[0]) and np.array_equal(fb.download_color(), want[0]), level
+            assert np.array_equal(fb.download_depth().view(np.uint32), want[1].view(np.uint32)), level
+            assert stats.counters() == want[2].counters(), level
+            times = device.kernel_times()
+            assert len(times) == rf._ffi.RF_N_KERNELS and "k_raster" in times and "k_setup" in times
+            if level:
+                assert times["k_raster"][1] >= 1, times
+            if level == 2:
+                assert all(times[k][1] >= 1 for k in ("k_vertex", "k_assemble", "k_setup")), times
+            if level == 0:
+                assert all(n == 0 for _, n in times.values()), times
+            ns, launches = device.last_pass()
+            assert launches >= 5
+        cp, dp = fb.color_devptr(), fb.depth_devptr()
+        assert cp and dp and cp != dp
+    finally:
+        device.profile(0)
+        fb._destroy(); device._targets.remove(fb)
+
+
 def test_text_as_textured_geometry(device, oracle):
     """render/text.rs + tex.rs Atlas: the hello.rs demo — glyph quads sampled with SamplerClamp from a font
     atlas, swinging through the frustum (including frames where the text crosses the near plane and is clipped)."""
