@@ -789,6 +789,52 @@ def test_async_download_profiling_and_device_pointers(device, oracle):
         fb._destroy(); device._targets.remove(fb)
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_api_sequence_fuzz_persistent_targets(device, oracle, seed):
+    """What a frame loop does to the queue (front/src/minifb.rs:114-152, crates.rs:98-133): three persistent targets of different
+    sizes and formats, and a random sequence of partial clears (colour only, depth only, both), draws into any of them in any
+    interleaving (a clear may follow draws of the same pass), flushes, stats reads and downloads. Each target is mirrored by an
+    oracle target that receives the same operations in submission order; every download must match, and so must the counters."""
+    g = np.random.default_rng(seed)
+    specs = [(96, 64, rf.FMT_RGBA8888, True), (70, 130, rf.FMT_XRGB8888, True), (33, 40, rf.FMT_RGB565, False)]
+    fbs = [device.framebuf(w, h, fmt, dep) for (w, h, fmt, dep) in specs]
+    refs = [oracle.HostTarget(w, h, fmt, dep) for (w, h, fmt, dep) in specs]
+    kinds = ["color3", "uv", "disc", "lit", "checker"]
+    want_stats = rf.Stats()
+    try:
+        device.stats(reset=True)
+        for step in range(120):
+            i = int(g.integers(0, 3)); w, h, fmt, dep = specs[i]
+            op = g.integers(0, 10)
+            if op < 2:
+                ctx = rf.Context(color_clear=None if g.integers(0, 3) == 0 else tuple(int(v) for v in g.integers(0, 256, 4)),
+                                 depth_clear=None if g.integers(0, 3) == 0 else float(g.choice([np.inf, 4.0, 1.0])))
+                fbs[i].clear(ctx)
+                refs[i].clear(ctx.color_clear, ctx.depth_clear)
+            elif op < 8:
+                ctx = rf.Context(face_cull=[None, rf.FaceCull.Back][g.integers(0, 2)], depth_test=[None, rf.Ordering.Less][g.integers(0, 2)] if dep else None,
+                                 depth_write=bool(g.integers(0, 3)), color_write=bool(g.integers(0, 5)))
+                sc = scenes.random_soup(int(g.integers(1, 60)), w, h, seed=int(g.integers(1, 1 << 30)), lanes_kind=kinds[g.integers(0, len(kinds))],
+                                        big=bool(g.integers(0, 2)), ctx=ctx)
+                for d in sc.draws:
+                    device.render(d, fbs[i])
+                    want_stats += oracle.render(d, refs[i])
+            elif op == 8:
+                device.flush() if hasattr(device, "flush") else device.sync()
+            else:
+                assert np.array_equal(fbs[i].download_color(), refs[i].host_color()), (step, i)
+                if dep:
+                    assert np.array_equal(fbs[i].download_depth().view(np.uint32), refs[i].depth.view(np.uint32)), (step, i)
+        for i, (fb, ref) in enumerate(zip(fbs, refs)):
+            assert np.array_equal(fb.download_color(), ref.host_color()), i
+            if specs[i][3]:
+                assert np.array_equal(fb.download_depth().view(np.uint32), ref.depth.view(np.uint32)), i
+        assert device.stats(reset=True).counters() == want_stats.counters()
+    finally:
+        for fb in fbs:
+            fb._destroy(); device._targets.remove(fb)
+
+
 def test_text_as_textured_geometry(device, oracle):
     """render/text.rs + tex.rs Atlas: the hello.rs demo — glyph quads sampled with SamplerClamp from a font
     atlas, swinging through the frustum (including frames where the text crosses the near plane and is clipped)."""
