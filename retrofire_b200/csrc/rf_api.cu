@@ -940,7 +940,16 @@ rf_status rf_target_clear(rf_ctx* c, rf_target* t, const uint8_t* rgba, const fl
   QueuedClear qc{t, rgba != nullptr, depth_recip != nullptr && t->has_depth, 0u, 0u};
   if (rgba) qc.color = pack_pixel_host(t->fmt, rgba);
   if (qc.has_depth) std::memcpy(&qc.zbits, depth_recip, 4);
-  if (qc.has_color || qc.has_depth) c->slots[c->cur].clears.push_back(qc);
+  if (!qc.has_color && !qc.has_depth) return RF_OK;
+  // Every clear of a pass runs in ONE k_clear_multi launch, concurrently: a second clear of the same plane of the same target
+  // (no draw between them, or the pass would have been flushed above) replaces the first — Frame::clear keeps the last value.
+  for (QueuedClear& e : c->slots[c->cur].clears) {
+    if (e.target != t) continue;
+    if (qc.has_color) { e.has_color = true; e.color = qc.color; }
+    if (qc.has_depth) { e.has_depth = true; e.zbits = qc.zbits; }
+    return RF_OK;
+  }
+  c->slots[c->cur].clears.push_back(qc);
   return RF_OK;
 }
 

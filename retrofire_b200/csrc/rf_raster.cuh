@@ -434,7 +434,10 @@ __device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t
   }
   uint32_t r = 0, g = 0, bl = 0, a = 0;
   if (!shade_fragment<LT>(D, fs, var, r, g, bl, a)) return 0u;  // discard: no writes at all
-  if (dwrite) sz.stf(idx, z);
+  // A NaN depth (0 * inf in the setup of a zero-height trapezoid half) can only be written with depth_test = None: every
+  // comparison with a NaN fails (ctx.rs:86-89). The reference's x86-64 host generates the default NaN 0xFFC00000 and
+  // propagates it; CUDA arithmetic generates 0x7FFFFFFF. The bits written are the host's ("NaN contract").
+  if (dwrite) sz.stf(idx, z != z ? __uint_as_float(0xFFC00000u) : z);
   if (cwrite) { *color_px(gc, gw, idx) = pack_pixel(fmt, r, g, bl, a); return 1u; }
   return 0u;
 }

@@ -4,7 +4,7 @@
 # the default bench line and the ncu launch list of the final code.
 mkdir -p gpurun_out
 ( timeout 40 python __graft_entry__.py --smoke; echo "smoke rc $?"
-  timeout 60 python -m pytest tests/test_gpu_parity.py -x -q -k "bunny_x16 or sprites_10k or random_soup or widest or crates_169 or hello_tri or indexed or line_prim or fuzz or heaviest or deep_tile or context_flags or depth_sort or growth" 2>&1 | tail -3 ) > gpurun_out/ab3_tests.txt 2>&1
+  timeout 60 python -m pytest tests/test_gpu_1_configs.py tests/test_gpu_2_api.py tests/test_gpu_3_adversarial.py -x -q -k "bunny_x16 or sprites_10k or random_soup or widest or crates_169 or hello_tri or indexed or line_prim or fuzz or heaviest or deep_tile or context_flags or depth_sort or growth" 2>&1 | tail -3 ) > gpurun_out/ab3_tests.txt 2>&1
 one() {  # variant workload frames steps
   RF_B200_LIB=$PWD/retrofire_b200/_variants/$1.so timeout 40 python bench.py --workload $2 --frames $3 --steps $4 --kernel-only 2>/dev/null | python -c "
 import sys, json

@@ -1,5 +1,5 @@
 #!/bin/bash
-# The seeded fuzz of tests/test_gpu_parity.py through the SIMT emulation of the kernel source (no GPU), with other seeds than the
+# The seeded fuzz of tests/test_gpu_3_adversarial.py through the SIMT emulation of the kernel source (no GPU), with other seeds than the
 # committed one: RF_FUZZ_SEED / RF_FUZZ_FRAMES select the stream. Usage: scratch/emu_fuzz.sh "<seeds>" <frames>
 cd "$(dirname "$0")/.."
 for seed in ${1:-7 8 9}; do
@@ -9,7 +9,7 @@ sys.path.insert(0, os.getcwd()); sys.path.insert(0, "tests/emu")
 import retrofire_b200 as rf
 from retrofire_b200 import _ffi
 from oracle import rfo
-from tests import test_gpu_parity as G
+from tests import test_gpu_3_adversarial as G
 import build_emu
 t = time.time()
 rfo.build(); rfo.load()

@@ -6,7 +6,7 @@ import numpy as np
 import retrofire_b200 as rf
 from retrofire_b200 import _ffi, scenes
 from oracle import rfo
-from tests import test_gpu_parity as G
+from tests import test_gpu_3_adversarial as G
 from tests.parity import run_gpu, run_oracle, assert_parity
 import build_emu
 rfo.build(); rfo.load()

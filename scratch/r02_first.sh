@@ -6,7 +6,7 @@
 #   gpurun --timeout 900 -- 'bash scratch/r02_first.sh'
 mkdir -p gpurun_out
 ( timeout 60 python __graft_entry__.py --smoke; echo "smoke rc $?"
-  timeout 420 python -m pytest tests -m gpu -q 2>&1 | tail -15 ) > gpurun_out/r02_tests.txt 2>&1
+  timeout 600 python -m pytest tests -m gpu -q -rf 2>&1 | tail -40 ) > gpurun_out/r02_tests.txt 2>&1
 timeout 120 python bench.py --steps 300 --cpu-seconds 6 > gpurun_out/r02_bench_bunny_1gpu.json 2> gpurun_out/r02_bench.err; echo "bench rc $?"
 timeout 60 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -k regex:k_ -c 48 --csv \
   --log-file gpurun_out/r02_launches.csv python bench.py --steps 4 --warmup 3 --kernel-only > /dev/null 2>&1; echo "launch list rc $?"

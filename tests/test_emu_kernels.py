@@ -1,5 +1,5 @@
 """The kernel SOURCE of retrofire_b200/csrc, executed on the CPU by the SIMT emulation in tests/emu and compared with
-the oracle — the same test bodies as tests/test_gpu_parity.py, so the warp-level logic (dependency rounds, warp-aggregated
+the oracle — the same test bodies as tests/test_gpu_{1_configs,2_api,3_adversarial}.py, so the warp-level logic (dependency rounds, warp-aggregated
 allocation, bin sort, checkpoints, fast paths, error reporting, arena growth and replay) is checked in a container
 without a GPU. This says nothing about the SASS or about speed: the parity tests proper are the `-m gpu` ones, which run
 the nvcc-built library on a B200. The emulation library lives in tests/emu/_build, is loaded only here, and is unknown to
@@ -13,7 +13,7 @@ import pytest
 
 import retrofire_b200 as rf
 from retrofire_b200 import _ffi
-from tests import test_gpu_parity as G
+from tests import test_gpu_1_configs as G1, test_gpu_2_api as G2, test_gpu_3_adversarial as G3
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 import build_emu  # noqa: E402
@@ -38,7 +38,7 @@ def device():
     dev.close()
 
 
-# Everything in test_gpu_parity.py except the full-size scenes (minutes under emulation; they stay GPU-only) and, unless
+# Everything in the three GPU parity files except the full-size scenes (minutes under emulation; they stay GPU-only) and, unless
 # RF_EMU_FULL=1, the three cases that take more than 30 s each here (all 61 pass: 3.5 min).
 SKIP = {
     "test_bunny_x16", "test_crates_1089_full_4k", "test_sprites_10k_full", "test_small_tris_1m_8k",
@@ -46,13 +46,14 @@ SKIP = {
 }
 if os.environ.get("RF_EMU_FULL") != "1":
     SKIP |= {"test_arena_growth_replays_the_pass", "test_every_tile_heaviest_and_repeated_passes", "test_page_locked_geometry_is_dmad_directly"}
-for _name in dir(G):
-    if _name.startswith("test_") and _name not in SKIP:
-        globals()[_name] = getattr(G, _name)
+for _G in (G1, G2, G3):
+    for _name in dir(_G):
+        if _name.startswith("test_") and _name not in SKIP:
+            globals()[_name] = getattr(_G, _name)
 
 
 def test_fuzz_first_frames_under_emulation(device, oracle, monkeypatch):
     """The first 20 frames of the seeded fuzz (the GPU suite runs all 100); scratch/emu_fuzz.sh runs other seeds."""
     if "RF_FUZZ_FRAMES" not in os.environ:
         monkeypatch.setenv("RF_FUZZ_FRAMES", "20")
-    G.test_fuzz_random_frames_through_one_context(device, oracle)
+    G3.test_fuzz_random_frames_through_one_context(device, oracle)

@@ -282,7 +282,7 @@ def test_depth_sort_restatement_equals_presorted_submission(oracle, order):
 
 
 def nan_max_scenes():
-    """Two one-triangle scenes whose shaders see NaN in a `max` (also rendered on the device by tests/test_gpu_parity.py)."""
+    """Two one-triangle scenes whose shaders see NaN in a `max` (also rendered on the device by tests/test_gpu_3_adversarial.py)."""
     from retrofire_b200 import mathx as mx
     f32 = np.float32
     pos = np.array([[-1, 1, 0], [1, 1, 0], [0, -1, 0]], f32)
@@ -304,7 +304,7 @@ def nan_max_scenes():
 def test_shader_max_ignores_nan_like_f32_max(oracle):
     """`f32::max` returns the other argument when one is NaN (Rust std), so `n.dot(&light_dir).max(0.0)` (crates.rs:44) with a NaN
     normal gives kd = lerp(0, 0.4, 1.0) = 0.4, and `(norm.z() + 0.2).max(0.2)` (solids.rs:75) gives 0.2 — not NaN (black), which is
-    what C's std::max would produce. Found by tests/test_gpu_parity.py::test_lattice_shader_ties (zero-width first rows make
+    what C's std::max would produce. Found by tests/test_gpu_3_adversarial.py::test_lattice_shader_ties (zero-width first rows make
     dv_dx = 0 * inf = NaN)."""
     f32 = np.float32
     lit, solids = nan_max_scenes()
