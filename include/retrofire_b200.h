@@ -243,7 +243,7 @@ rf_status rf_ctx_last_pass(rf_ctx* ctx, uint64_t* time_ns, uint32_t* n_launches)
 
 
 /* ---- measurement (Stats::start/finish analogue, render/stats.rs:57-78, per kernel) ----------- */
-#define RF_N_KERNELS 11 /* kernels launched by one pass, in order; see rf_kernel_name */
+#define RF_N_KERNELS 12 /* kernels launched by one pass, in order; see rf_kernel_name */
 /* level 0: off. 1: CUDA events around k_raster only (the pass keeps its two-stream overlap).
  * 2: events between all pass kernels, which are then serialised on the ctx stream. Resets the sums. */
 rf_status rf_ctx_profile(rf_ctx* ctx, int level);

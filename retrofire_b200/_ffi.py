@@ -118,7 +118,7 @@ SYMBOLS = {
     "rf_ctx_kernel_times": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "rf_kernel_name": (C.c_char_p, [C.c_uint32]),
 }
-RF_N_KERNELS = 11
+RF_N_KERNELS = 12
 
 _lib = None
 

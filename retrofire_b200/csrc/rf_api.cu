@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -96,12 +97,13 @@ struct PassSlot {
   HostStatus* h_status = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   cudaEvent_t ev_k[RF_N_KERNELS + 1] = {};  // boundaries between the pass kernels (profiling mode)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // binning chain runs on the ctx's side stream
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;  // binning chain runs on the ctx's side stream
   cudaEvent_t ev_direct = nullptr;  // last asynchronous upload of page-locked caller geometry into d_direct (rf_ctx_set_geometry_async)
   bool direct_async = false;
   int profiled = 0;
   uint32_t NV = 0, NP = 0, n_tiles = 0, lt = 0;
   uint32_t n_launches = 0;
+  bool first_touch = false;  // some target of the pass is cleared by k_raster / k_clear_untouched (TargetDesc::clear_flags)
   bool peer = false;         // some target of the pass replicates its colour stores into peer GPUs (rf_peer.cuh)
   bool epochs_set = false;   // barrier epochs are assigned at the first launch and reused by replays
   uint32_t epoch1 = 0, epoch2 = 0;
@@ -153,7 +155,7 @@ struct rf_ctx {
   std::vector<int> flight;     // slots launched and not yet validated, oldest first
 
   // scratch arenas shared by all passes (stream order makes reuse safe)
-  DevBuf cv, sv, stris, spans, tris, entries, bins, bins2, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
+  DevBuf cv, sv, stris, largelist, spans, tris, entries, bins, bins2, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
   // capacities: spans/tris/ckpts in 32-bit WORDS (record width depends on the pass's lane count),
   // entries and long spans in records
   size_t capw_stris = 0, capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
@@ -272,6 +274,9 @@ void launch_order(rf_ctx* c, PassSlot& s, const PassParams& P, uint32_t QW, cuda
   s.n_launches += 3;  // plus CUB's own kernels
 }
 
+#ifndef RF_FIRST_TOUCH_CLEAR
+#define RF_FIRST_TOUCH_CLEAR 1
+#endif
 #ifndef RF_SETUP_GRID_PER_SM
 #define RF_SETUP_GRID_PER_SM 16
 #endif
@@ -285,7 +290,8 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   auto blocks = [&](size_t n, int bs, int per_sm) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + bs - 1) / bs, (size_t)sm * per_sm)); };
   const int prof = c->profile;
   s.profiled = prof;
-  const unsigned raster_blocks = sm * RF_RASTER_MIN_BLOCKS;
+  const unsigned raster_blocks = sm * RasterOcc<LT>::BLOCKS;
+  const unsigned clear_blocks = blocks((size_t)s.n_tiles * 32, 256, 8);
   if (prof == 2) {  // serialised on one stream, an event between every pair of kernels
     int ek = 0;
     auto mark = [&]() { cudaEventRecord(s.ev_k[ek++], st); };
@@ -301,6 +307,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     mark(); k_ckpt<LT><<<sm * 8, 256, 0, st>>>(P);
     mark(); k_bin_sort_warp<<<sm * 8, RF_SORT_WARPS * 32, 0, st>>>(P);
     mark(); k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, st>>>(P);
+    mark(); if (s.first_touch) k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
     mark();
     if (s.peer) {
       k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch1);
@@ -325,7 +332,10 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     k_bin_scatter<<<sm * 4, 256, 0, sd>>>(P);
     k_bin_sort_warp<<<sm * RF_SORT_GRID_PER_SM, RF_SORT_WARPS * 32, 0, sd>>>(P);
     k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, sd>>>(P);
+    // the untouched tiles of first-touch-cleared targets: next to k_raster (disjoint tiles), or — with peers — before the barrier
+    if (s.first_touch && s.peer) k_clear_untouched<<<clear_blocks, 256, 0, sd>>>(P);
     cudaEventRecord(s.ev_join, sd);
+    if (s.first_touch && !s.peer) { k_clear_untouched<<<clear_blocks, 256, 0, sd>>>(P); cudaEventRecord(s.ev_join2, sd); }
     k_edge_ckpt<LT><<<sm * 4, 128, 0, st>>>(P);
     k_walk<LT><<<sm * 12, 128, 0, st>>>(P);
     k_ckpt<LT><<<sm * 8, 256, 0, st>>>(P);
@@ -335,16 +345,20 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     if (s.peer) k_raster<LT, true><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
     else k_raster<LT, false><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
     if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS], st);
+    if (s.first_touch && !s.peer) cudaStreamWaitEvent(st, s.ev_join2, 0);
     if (s.peer) { k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch2); s.n_launches++; }  // every peer's stores into this GPU have landed
   }
-  s.n_launches += RF_N_KERNELS;
+  s.n_launches += RF_N_KERNELS - (s.first_touch ? 0 : 1);
 }
 
 // Any growth frees memory that in-flight kernels might still use -> callers guarantee idleness.
 rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const ArenaWants& w) {
   if (!c->cv.reserve(nv * words_cv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "clip-vertex arena");
   if (!c->sv.reserve(nv * words_sv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "screen-vertex arena");
-  if (w.w_stris > c->capw_stris) { if (!c->stris.reserve(w.w_stris * 4)) return fail(c, RF_E_NOMEM, "screen-triangle arena"); c->capw_stris = w.w_stris; }
+  if (w.w_stris > c->capw_stris) {  // the large list names screen triangles: one slot per record of the narrowest layout
+    if (!c->stris.reserve(w.w_stris * 4) || !c->largelist.reserve(w.w_stris / Rec<3>::QW * 4 + 64)) return fail(c, RF_E_NOMEM, "screen-triangle arena");
+    c->capw_stris = w.w_stris;
+  }
   if (w.w_spans > c->capw_spans) { if (!c->spans.reserve(w.w_spans * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->capw_spans = w.w_spans; }
   if (w.w_tris > c->capw_tris) { if (!c->tris.reserve(w.w_tris * 4)) return fail(c, RF_E_NOMEM, "triangle arena"); c->capw_tris = w.w_tris; }
   if (w.w_ckpts > c->capw_ckpts) { if (!c->ckpts.reserve(w.w_ckpts * 4)) return fail(c, RF_E_NOMEM, "checkpoint arena"); c->capw_ckpts = w.w_ckpts; }
@@ -390,8 +404,17 @@ rf_status launch_pass(rf_ctx* c, int si) {
   const int lt = lt_for(maxL);
   s.lt = lt;
 
+  // clears of targets the pass also draws into are first-touch clears (see the target table below): no ClearDesc
+  auto drawn = [&](const rf_target* t) { return RF_FIRST_TOUCH_CLEAR && std::find(s.targets.begin(), s.targets.end(), t) != s.targets.end(); };
   size_t ncl = 0;
-  for (const QueuedClear& qc : s.clears) ncl += (qc.has_color ? 1 : 0) + (qc.has_depth ? 1 : 0);
+  bool first_touch = false;
+  for (const QueuedClear& qc : s.clears) {
+    const bool ft = drawn(qc.target);
+    if (qc.has_color && !(ft && !qc.target->peer_mode)) ncl++;
+    if (qc.has_depth && !ft) ncl++;
+    first_touch = first_touch || (ft && (qc.has_depth || (qc.has_color && !qc.target->peer_mode)));
+  }
+  s.first_touch = first_touch;
   const size_t table_bytes = nd * sizeof(DrawDesc) + 2 * (nd + 1) * 4 + nt * sizeof(TargetDesc) + ncl * sizeof(ClearDesc) + 64;
   if (!s.table.reserve(table_bytes)) return fail(c, RF_E_NOMEM, "pinned table");
   // idle device needed before any reallocation of buffers a previous launch of this slot used
@@ -474,7 +497,16 @@ rf_status launch_pass(rf_ctx* c, int si) {
     if (i == 0) tiles_per_target = T.tiles_x * T.tiles_y;
     else if (T.tiles_x * T.tiles_y != tiles_per_target) uniform_tiles = false;
     T.band_y0 = std::min(c->band_y0, t->h); T.band_y1 = std::min(c->band_y1, t->h);
-    T.n_peers = t->n_peers; T._pad = 0;
+    T.n_peers = t->n_peers;
+    T.clear_flags = 0; T.clear_color = 0; T.clear_zbits = 0;
+    // First-touch clear: a Frame::clear recorded at the head of this pass for a target the pass draws into is carried out by
+    // k_raster (touched tiles) and k_clear_untouched (the others). With peers attached the other GPUs store their bands into
+    // this colour buffer, so its colour plane is still cleared as a whole, before the first cross-GPU barrier.
+    for (const QueuedClear& qc : s.clears) {
+      if (qc.target != t || !RF_FIRST_TOUCH_CLEAR) continue;
+      if (qc.has_color && !t->peer_mode) { T.clear_flags |= RF_CLEAR_COLOR; T.clear_color = qc.color; }
+      if (qc.has_depth) { T.clear_flags |= RF_CLEAR_DEPTH; T.clear_zbits = qc.zbits; }
+    }
     for (uint32_t p = 0; p < RF_MAX_PEERS; p++) T.peer_color[p] = p < t->n_peers ? t->peer_color[p] : nullptr;
     if (t->peer_mode && nd) s.peer = true;
   }
@@ -490,9 +522,10 @@ rf_status launch_pass(rf_ctx* c, int si) {
       const size_t first = (size_t)y0 * qc.target->w;
       const unsigned long long n = (unsigned long long)(y1 > y0 ? y1 - y0 : 0) * qc.target->w;
       // with peers attached the other GPUs store THEIR bands into this buffer: the colour clear covers every row
+      const bool ft = drawn(qc.target);
       if (qc.has_color && qc.target->peer_mode) h_clears[k++] = ClearDesc{qc.target->d_color, (unsigned long long)qc.target->w * qc.target->h, qc.color, 0u};
-      else if (qc.has_color) h_clears[k++] = ClearDesc{qc.target->d_color + first, n, qc.color, 0u};
-      if (qc.has_depth) h_clears[k++] = ClearDesc{reinterpret_cast<uint32_t*>(qc.target->d_depth) + first, n, qc.zbits, 0u};
+      else if (qc.has_color && !ft) h_clears[k++] = ClearDesc{qc.target->d_color + first, n, qc.color, 0u};
+      if (qc.has_depth && !ft) h_clears[k++] = ClearDesc{reinterpret_cast<uint32_t*>(qc.target->d_depth) + first, n, qc.zbits, 0u};
     }
   }
 
@@ -547,6 +580,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.sv = static_cast<float*>(c->sv.p);
   P.stris = static_cast<uint32_t*>(c->stris.p);
   P.cap_stris = (uint32_t)std::min<size_t>(c->capw_stris / words_stri(lt), 0x1FFFFFF0u);
+  P.largelist = static_cast<uint32_t*>(c->largelist.p);
   P.sdepth = s.order_upper ? static_cast<uint32_t*>(c->sdepth.p) : nullptr;
   P.spans = static_cast<uint32_t*>(c->spans.p);
   P.tris = static_cast<uint32_t*>(c->tris.p);
@@ -605,6 +639,10 @@ rf_status validate_all(rf_ctx* c) {
     PassSlot& s = c->slots[si];
     RF_CUDA(c, cudaEventSynchronize(s.ev_stop));
     const PassStatus ps = s.h_status->status;
+    if (getenv("RF_DEBUG_PASS"))
+      fprintf(stderr, "[rf pass] draws %zu stris %llu large %llu tris %llu spans %llu entries %llu chunks %llu long %llu ckpts %llu work %u max_bin %u overflow %u error %u\n",
+              s.draws.size(), ps.stris_needed.v, ps.large_needed.v, ps.tris_needed.v, ps.spans_needed.v, ps.entries_needed.v, ps.chunks_needed.v,
+              ps.long_needed.v, ps.ckpts_needed.v, ps.n_work, ps.max_bin, ps.overflow, ps.error);
     if (ps.overflow) {
       // Every later pass in flight was a no-op (device poison). Grow and replay from here, in order.
       { rf_status st = wait_idle(c); if (st) return st; }
@@ -840,7 +878,8 @@ rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
     PassSlot& s = c->slots[k];
     ok = ok && cudaEventCreate(&s.ev_start) == cudaSuccess && cudaEventCreate(&s.ev_stop) == cudaSuccess;
     for (int e = 0; e <= RF_N_KERNELS && ok; e++) ok = cudaEventCreate(&s.ev_k[e]) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s.ev_join2, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_status), sizeof(HostStatus), cudaHostAllocDefault) == cudaSuccess;
   }
   ok = ok && cudaFuncSetAttribute(k_bin_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
@@ -870,8 +909,9 @@ void rf_ctx_destroy(rf_ctx* c) {
     for (int e = 0; e <= RF_N_KERNELS; e++) if (s.ev_k[e]) cudaEventDestroy(s.ev_k[e]);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
+    if (s.ev_join2) cudaEventDestroy(s.ev_join2);
   }
-  c->cv.release(); c->sv.release(); c->stris.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->bins2.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
+  c->cv.release(); c->sv.release(); c->stris.release(); c->largelist.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->bins2.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
   for (uint32_t r = 0; r < c->pb.world; r++) if (r != c->pb.self && c->pb_ipc[r]) cudaIpcCloseMemHandle(c->pb.flags[r]);
   c->peer_flags.release();
@@ -1180,7 +1220,7 @@ rf_status rf_ctx_kernel_times(rf_ctx* c, uint64_t* ns, uint64_t* launches) {
 }
 
 const char* rf_kernel_name(uint32_t i) {
-  static const char* names[RF_N_KERNELS] = {"k_vertex", "k_assemble", "k_setup", "k_edge_ckpt", "k_walk", "k_bin_alloc", "k_bin_scatter", "k_ckpt", "k_bin_sort_warp", "k_bin_sort_big", "k_raster"};
+  static const char* names[RF_N_KERNELS] = {"k_vertex", "k_assemble", "k_setup", "k_edge_ckpt", "k_walk", "k_bin_alloc", "k_bin_scatter", "k_ckpt", "k_bin_sort_warp", "k_bin_sort_big", "k_clear_untouched", "k_raster"};
   return i < RF_N_KERNELS ? names[i] : "";
 }
 

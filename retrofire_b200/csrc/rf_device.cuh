@@ -61,9 +61,16 @@ struct TargetDesc {
   uint32_t band_y0, band_y1;
   // Sort-first over NVLink peer memory: every colour store of this GPU's band is replicated into the colour buffers of
   // the other GPUs (same layout), so each GPU ends the pass holding the whole frame without a separate gather.
-  uint32_t n_peers, _pad;
+  uint32_t n_peers;
+  // First-touch clear (Frame::clear, front/src/lib.rs:103-120, recorded at the head of this pass): the rasteriser
+  // initialises the tiles it touches itself (depth tile in shared memory from the clear value, colour rows stored
+  // before the first fragment), k_clear_untouched fills the other tiles — every pixel is written once.
+  uint32_t clear_flags;           // RF_CLEAR_COLOR | RF_CLEAR_DEPTH
+  uint32_t clear_color, clear_zbits;
   uint32_t* peer_color[RF_MAX_PEERS];
 };
+#define RF_CLEAR_COLOR 1u
+#define RF_CLEAR_DEPTH 2u
 
 struct DrawStats {
   unsigned long long prims_o, frags_i, frags_o;
@@ -90,6 +97,7 @@ struct PassStatus {
   PaddedCounter long_needed;     // spans that cross a tile-column boundary
   PaddedCounter ckpts_needed;    // checkpoint records for those spans
   PaddedCounter bins_needed;     // total size of all tile bins
+  PaddedCounter large_needed;    // screen triangles that take the k_setup path (tall, wide, near the target's edge, lines)
   uint32_t error;                // RF_ERRBIT_*
   uint32_t overflow;             // a capacity was exceeded: nothing was rasterised
   uint32_t n_work;               // non-empty tiles
@@ -126,6 +134,7 @@ struct PassParams {
   float* sv;              // screen verts [NV][SVS]: to_screen of every vertex inside the frustum, plus its outcode
   uint32_t* stris;        // [cap_stris][QW]   compacted screen triangles (k_assemble -> k_setup)
   uint32_t cap_stris;
+  uint32_t* largelist;    // [cap_stris] indices into stris of the triangles k_setup processes (the others are binned by k_assemble)
   uint32_t* sdepth;       // [cap_stris] total-order bits of Render::depth, or null when no draw of the pass is depth-sorted
   uint32_t* spans;        // [cap_spans][SW]   one per scanline, contiguous per triangle
   uint32_t* tris;         // [cap_tris][TW]    per drawn triangle: key, draw, rows, dv/dx of both halves
@@ -154,6 +163,15 @@ struct PassParams {
 #define RF_NO_CKPT 0xFFFFFFFFu
 #define RF_STRI_LINE 0x80000000u  // flag in the draw word of a screen-triangle record: the record is an Edge (2 vertices)
 #define RF_NO_TILE 0xFFFFFFFFu
+// Bin entries name either a triangle record written by k_setup, or — flag set — a screen-triangle record of k_assemble
+// that the rasteriser sets up and walks itself (a SMALL triangle: few scanlines, narrow, inside the target).
+#define RF_BIN_SMALL 0x80000000u
+#ifndef RF_SMALL_ROWS
+#define RF_SMALL_ROWS 32u      // most scanlines of a SMALL triangle (0 switches the class off)
+#endif
+#ifndef RF_SMALL_WIDTH
+#define RF_SMALL_WIDTH 64.0f   // widest bounding box (pixels) of a SMALL triangle
+#endif
 
 // record strides in 32-bit words, as a function of the compile-time lane count LT
 template <int LT> struct Rec {

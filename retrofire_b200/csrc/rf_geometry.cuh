@@ -272,6 +272,60 @@ __device__ __forceinline__ void half_setup(float y0, float y1, const float* l0, 
   H.n = sat_u32(y1r - y0r);
 }
 
+// tri_fill's vertex order (raster.rs:191): stable sort of the three vertices by y with f32::total_cmp -> top, middle, bottom
+__device__ __forceinline__ void tri_order(float y0, float y1, float y2, int& o0, int& o1, int& o2) {
+  o0 = 0; o1 = 1; o2 = 2;
+  int32_t ka = total_key(y0), kb = total_key(y1), kc = total_key(y2);
+  if (kb < ka) { int t_ = o0; o0 = o1; o1 = t_; int32_t tk = ka; ka = kb; kb = tk; }
+  if (kc < kb) { int t_ = o1; o1 = o2; o2 = t_; int32_t tk = kb; kb = kc; kc = tk; }
+  if (kb < ka) { int t_ = o0; o0 = o1; o1 = t_; }
+}
+
+// Scanline counts of the two trapezoid halves and the first row centre, from the three y alone — the same expressions as
+// half_setup's y0r / y1r / n (raster.rs:262-267), so k_assemble can classify and bin a triangle without setting it up.
+__device__ __forceinline__ void tri_rows(float y0, float y1, float y2, float& yfirst, uint32_t& n0, uint32_t& n1) {
+  int o0, o1, o2;
+  tri_order(y0, y1, y2, o0, o1, o2);
+  const float ty = o0 == 0 ? y0 : (o0 == 1 ? y1 : y2), my = o1 == 0 ? y0 : (o1 == 1 ? y1 : y2), by = o2 == 0 ? y0 : (o2 == 1 ? y1 : y2);
+  const float t = round_up_to_half(ty), m = round_up_to_half(my), b = round_up_to_half(by);
+  n0 = sat_u32(m - t);
+  n1 = sat_u32(b - m);
+  yfirst = n0 ? t : m;
+}
+
+// tri_fill (raster.rs:185-224) on a screen-triangle record (Rec<LT>::QW words: key, draw, 3 x (x, y, z, attr[LT])): vertex
+// order, mid1, left/right, and the `scan` setup of both halves. Used by k_setup and — for SMALL triangles, which have no
+// triangle record — by k_raster: the same instructions in the same order, so both produce the same bits.
+template <int LT>
+__device__ __forceinline__ void tri_setup(const uint32_t* w, HalfSetup<LT>& H0, HalfSetup<LT>& H1, float& xabs) {
+  constexpr int NL = 2 + LT;
+  int o0, o1, o2;
+  tri_order(__uint_as_float(w[3]), __uint_as_float(w[3 + (3 + LT)]), __uint_as_float(w[3 + 2 * (3 + LT)]), o0, o1, o2);
+  float top[NL], mid0[NL], bot[NL], mid1[NL];
+  float ty, my, by;
+#define RF_PICK(dst, yy, idx)                                                                      \
+  {                                                                                                \
+    _Pragma("unroll") for (int k = 0; k < 3; k++) if (k == idx) {                                  \
+      dst[0] = __uint_as_float(w[2 + k * (3 + LT)]); yy = __uint_as_float(w[3 + k * (3 + LT)]);    \
+      dst[1] = __uint_as_float(w[4 + k * (3 + LT)]);                                               \
+      _Pragma("unroll") for (int i = 0; i < LT; i++) dst[2 + i] = __uint_as_float(w[5 + k * (3 + LT) + i]); \
+    }                                                                                              \
+  }
+  RF_PICK(top, ty, o0)
+  RF_PICK(mid0, my, o1)
+  RF_PICK(bot, by, o2)
+#undef RF_PICK
+  const float tt = (my - ty) / (by - ty);
+#pragma unroll
+  for (int i = 0; i < NL; i++) mid1[i] = lerpf(top[i], bot[i], tt);
+  const bool m0left = mid0[0] < mid1[0];
+  const float* left = m0left ? mid0 : mid1;
+  const float* right = m0left ? mid1 : mid0;
+  half_setup<LT>(ty, my, top, left, top, right, H0);
+  half_setup<LT>(my, by, left, bot, right, bot, H1);
+  xabs = fmaxf(fmaxf(fabsf(top[0]), fabsf(mid0[0])), fabsf(bot[0]));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Triangle record (Rec<LT>::TW words), written by k_setup, read by k_edge_ckpt, k_walk, k_ckpt, k_raster:
 //   [0] key  [1] draw  [2] sbase  [3] Y0  [4] nU  [5] nL | target << 16  [6] chunk position of half 0  [7] of half 1
@@ -585,12 +639,64 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
       }
       const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
       if (emask == 0) continue;
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(&P.status->stris_needed, (unsigned long long)__popc(emask));
+      // ---- SMALL or LARGE (see RF_BIN_SMALL). A SMALL triangle has few scanlines, a narrow bounding box and lies inside the
+      // target, so no scanline can leave the target (target.rs:148,173-174 cannot panic) and its pixels lie in the tiles of
+      // its bounding box: it is binned right here and k_raster sets it up and walks it from this record. Everything else —
+      // also anything with a non-finite coordinate — goes to k_setup through the large list.
+      bool small = false;
+      uint32_t s_tr0 = 1, s_tr1 = 0, s_ca = 0, s_cb = 0, s_tbase = 0, s_tx = 1, nent = 0;
+      if (emit && !is_edge && RF_SMALL_ROWS != 0u && P.sdepth == nullptr) {
+        float yfirst;
+        uint32_t n0, n1;
+        tri_rows(s[0].y, s[1].y, s[2].y, yfirst, n0, n1);
+        const uint32_t nrows = n0 + n1;
+        const float xmin = fminf(fminf(s[0].x, s[1].x), s[2].x), xmax = fmaxf(fmaxf(s[0].x, s[1].x), s[2].x);
+        const float ylo = fminf(fminf(s[0].y, s[1].y), s[2].y), yhi = fmaxf(fmaxf(s[0].y, s[1].y), s[2].y);
+        bool finite = true;
+#pragma unroll
+        for (int k = 0; k < 3; k++) finite = finite && fabsf(s[k].x) < 1.0e9f && fabsf(s[k].y) < 1.0e9f;  // false for NaN
+        const TargetDesc& T = P.targets[P.draws[d].target];
+        // the running sums of an edge stay within the bounding box up to rounding drift (|sum_j - (x0 + j * dx)| <= j * 2^-24 * max|x|)
+        const float margin = 1.0f + (float)nrows * fmaxf(fabsf(xmin), fabsf(xmax)) * 1.2e-7f;
+        if (finite && nrows >= 1u && nrows <= RF_SMALL_ROWS && xmax - xmin <= RF_SMALL_WIDTH && ylo >= 0.0f && yhi + 1.0f < (float)T.h &&
+            xmin - margin > 0.0f && xmax + margin < (float)T.w) {
+          small = true;
+          const uint32_t Y0 = sat_u32(yfirst);
+          const uint32_t Ya = max(Y0, T.band_y0), Yb = min(Y0 + nrows, T.band_y1);  // only tile rows of this GPU's row band
+          if (Ya < Yb) {
+            s_tr0 = Ya >> RF_TILE_SHIFT; s_tr1 = (Yb - 1) >> RF_TILE_SHIFT;
+            s_ca = min(sat_u32(floorf(xmin - 0.5f - margin)) >> RF_TILE_SHIFT, T.tiles_x - 1);
+            s_cb = min(sat_u32(floorf(xmax + 0.5f + margin)) >> RF_TILE_SHIFT, T.tiles_x - 1);
+            s_tbase = T.tile_base; s_tx = T.tiles_x;
+            nent = (s_tr1 - s_tr0 + 1) * (s_cb - s_ca + 1);
+          }
+        }
+      }
+      const uint32_t lmask = __ballot_sync(0xFFFFFFFFu, emit && !small);
+      const uint32_t incl_e = warp_scan_incl(nent, lane), tot_e = __shfl_sync(0xFFFFFFFFu, incl_e, 31);
+      unsigned long long base = 0, lbase = 0, ebase = 0;
+      if (lane == 0) {
+        base = atomicAdd(&P.status->stris_needed, (unsigned long long)__popc(emask));
+        if (lmask) lbase = atomicAdd(&P.status->large_needed, (unsigned long long)__popc(lmask));
+        if (tot_e) ebase = atomicAdd(&P.status->entries_needed, (unsigned long long)tot_e);
+      }
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (base + __popc(emask) > P.cap_stris) {
+      lbase = __shfl_sync(0xFFFFFFFFu, lbase, 0);
+      ebase = __shfl_sync(0xFFFFFFFFu, ebase, 0);
+      if (base + __popc(emask) > P.cap_stris || ebase + tot_e > P.cap_entries) {  // the large list has cap_stris slots
         if (lane == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
         continue;
+      }
+      if (emit && !small) P.largelist[(uint32_t)lbase + __popc(lmask & lt)] = (uint32_t)base + __popc(emask & lt);
+      if (nent) {
+        uint32_t eidx = (uint32_t)ebase + (incl_e - nent);
+        const uint32_t ref = ((uint32_t)base + __popc(emask & lt)) | RF_BIN_SMALL, key = gp * 8u + t;
+        for (uint32_t tr = s_tr0; tr <= s_tr1; tr++)
+          for (uint32_t c = s_ca; c <= s_cb; c++) {
+            const uint32_t tile = s_tbase + tr * s_tx + c;
+            P.entries[eidx++] = make_uint4(tile, key, ref, 0u);
+            atomicAdd(P.tile_cnt + tile, 1u);
+          }
       }
       uint32_t* const qstg = reinterpret_cast<uint32_t*>(s_q[RF_ASSEMBLE_STAGE ? threadIdx.x >> 5 : 0]);
       if (emit) {
@@ -650,9 +756,6 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
 #ifndef RF_SETUP_STAGE
 #define RF_SETUP_STAGE 1
 #endif
-#ifndef RF_SETUP_STAGE_IN   // optional (off): load the warp's 32 input records through the same buffer — measured neutral to +1 %
-#define RF_SETUP_STAGE_IN 0
-#endif
 template <int LT> struct SetupStage {
   static constexpr bool ON = RF_SETUP_STAGE && LT == 3;
   static constexpr int TWP = Rec<LT>::TW + 4;  // padded record stride in the buffer: 52 words = 20 mod 32 -> 128-bit accesses of 8 lanes hit 32 different banks
@@ -671,7 +774,8 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
   __shared__ uint4 s_stage[4][SS::WORDS / 4];  // uint4: 16-byte aligned for the 128-bit accesses
   if (P.cstatus->poison) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
-  const uint32_t NT = (uint32_t)min(P.status->stris_needed, (unsigned long long)P.cap_stris);
+  // the triangles k_assemble did not bin itself (see RF_BIN_SMALL): tall or wide ones, those near the target's edges, lines
+  const uint32_t NT = (uint32_t)min(P.status->large_needed, (unsigned long long)P.cap_stris);
   const uint32_t n_iter = (NT + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
   for (uint32_t it = 0; it < n_iter; it++) {
     const uint32_t ti = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
@@ -688,21 +792,12 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
     LineGeom LG{};
     LineMeasure LM{};
     float line_lanes[1 + LT];
-    constexpr bool STAGE_IN = SS::ON && RF_SETUP_STAGE_IN;
-    if (STAGE_IN) {  // consecutive lanes load consecutive 16 bytes; each lane then takes its record from shared memory
-      const uint32_t wbase = ti - lane;
-      const uint32_t nrec = wbase < NT ? min(32u, NT - wbase) : 0u;
-      const uint4* src = reinterpret_cast<const uint4*>(P.stris + (size_t)wbase * QW);
-      uint4* stg4 = s_stage[threadIdx.x >> 5];
-      for (uint32_t qi = lane; qi < nrec * (QW / 4); qi += 32) stg4[qi] = __ldg(src + qi);
-      __syncwarp();
-    }
     if (have) {
-      const uint32_t* q = STAGE_IN ? reinterpret_cast<const uint32_t*>(s_stage[threadIdx.x >> 5]) + lane * QW : P.stris + (size_t)ti * QW;
+      const uint32_t* q = P.stris + (size_t)__ldg(P.largelist + ti) * QW;
       uint32_t w[QW];
 #pragma unroll
       for (int qd = 0; qd < QW / 4; qd++) {
-        const uint4 t4 = STAGE_IN ? reinterpret_cast<const uint4*>(q)[qd] : __ldg(reinterpret_cast<const uint4*>(q) + qd);
+        const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(q) + qd);
         w[4 * qd] = t4.x; w[4 * qd + 1] = t4.y; w[4 * qd + 2] = t4.z; w[4 * qd + 3] = t4.w;
       }
       key = w[0]; d = w[1] & ~RF_STRI_LINE;
@@ -749,37 +844,8 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
           H0.R = H0.dr = H0.y = 0.0f; H1.R = H1.dr = H1.y = 0.0f;
         }
       } else {
-      // tri_fill raster.rs:185-224: stable sort by y (total_cmp)
-      int o0 = 0, o1 = 1, o2 = 2;
-      {
-        const int32_t k0 = total_key(__uint_as_float(w[3])), k1 = total_key(__uint_as_float(w[3 + (3 + LT)])), k2 = total_key(__uint_as_float(w[3 + 2 * (3 + LT)]));
-        int32_t ka = k0, kb = k1, kc = k2;
-        if (kb < ka) { int t_ = o0; o0 = o1; o1 = t_; int32_t tk = ka; ka = kb; kb = tk; }
-        if (kc < kb) { int t_ = o1; o1 = o2; o2 = t_; int32_t tk = kb; kb = kc; kc = tk; }
-        if (kb < ka) { int t_ = o0; o0 = o1; o1 = t_; }
-      }
-      float top[NL], mid0[NL], bot[NL], mid1[NL];
-      float ty, my, by;
-#define RF_PICK(dst, yy, idx)                                                                      \
-  {                                                                                                \
-    _Pragma("unroll") for (int k = 0; k < 3; k++) if (k == idx) {                                  \
-      dst[0] = __uint_as_float(w[2 + k * (3 + LT)]); yy = __uint_as_float(w[3 + k * (3 + LT)]);    \
-      dst[1] = __uint_as_float(w[4 + k * (3 + LT)]);                                               \
-      _Pragma("unroll") for (int i = 0; i < LT; i++) dst[2 + i] = __uint_as_float(w[5 + k * (3 + LT) + i]); \
-    }                                                                                              \
-  }
-      RF_PICK(top, ty, o0)
-      RF_PICK(mid0, my, o1)
-      RF_PICK(bot, by, o2)
-#undef RF_PICK
-      const float tt = (my - ty) / (by - ty);
-#pragma unroll
-      for (int i = 0; i < NL; i++) mid1[i] = lerpf(top[i], bot[i], tt);
-      const bool m0left = mid0[0] < mid1[0];
-      const float* left = m0left ? mid0 : mid1;
-      const float* right = m0left ? mid1 : mid0;
-      half_setup<LT>(ty, my, top, left, top, right, H0);
-      half_setup<LT>(my, by, left, bot, right, bot, H1);
+      float xabs;
+      tri_setup<LT>(w, H0, H1, xabs);  // tri_fill raster.rs:185-224
       const TargetDesc& T = P.targets[D.target];
       tgt = D.target; tiles_x = T.tiles_x;
       t_h = T.h; t_w = T.w; t_by0 = T.band_y0; t_by1 = T.band_y1;
@@ -803,7 +869,6 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
           Y0 = sat_u32(yfirst);
           // only tile rows inside this GPU's row band get bin entries
           const uint32_t Ya = max(Y0, T.band_y0), Yb = min(Y0 + nrows, T.band_y1);
-          const float xabs = fmaxf(fmaxf(fabsf(top[0]), fabsf(mid0[0])), fabsf(bot[0]));
           margin = 1.0f + (float)nrows * xabs * 1.2e-7f;
           if (Ya < Yb) {
             tr0 = Ya >> RF_TILE_SHIFT; tr1 = (Yb - 1) >> RF_TILE_SHIFT;

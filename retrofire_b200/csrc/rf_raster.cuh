@@ -5,6 +5,7 @@
 #include <type_traits>
 
 #include "rf_device.cuh"
+#include "rf_geometry.cuh"
 
 // =============================================================================================
 // K3: give every non-empty tile a contiguous bin (warp prefix sum + one atomic per warp) and
@@ -475,44 +476,79 @@ template <int LT> struct RasterTune {
   static constexpr uint32_t FRAG_QUEUE = MIN_AVG * 32u - 8u;
 };
 
+// Item queue: the (triangle, row) pieces of one round — every span piece of a group of consecutive triangles of the bin
+// that lies inside this tile — as {meta, z, attr[LT]} at the piece's first pixel. SMALL triangles are set up and walked by
+// their lane right here (no triangle record, no span records, no checkpoints: the three screen vertices are all that was
+// stored for them); the pieces of the other triangles are fetched from the span records k_setup / k_walk wrote.
+//   meta = first column | pixels << 6 | tile row << 12 | half << 17 | triangle lane << 18      (0: no pixel in this tile)
+#ifndef RF_ROWQ
+#define RF_ROWQ 128u   // capacity in pieces (a multiple of 32, >= RF_TILE: one triangle's rows in a tile always fit)
+#endif
 template <int LT> struct RasterSmem {
+  static constexpr int NV = 1 + LT;
   static constexpr int TILE_WORDS = RF_TILE * RF_TILE_PITCH;
-  static constexpr int WARP_WORDS = TILE_WORDS + (2 + LT) * (int)RasterTune<LT>::FRAG_QUEUE + RF_TILE;  // depth tile, queue {z, attr[LT], pix}, row coverage
+  static constexpr int FQ = (int)RasterTune<LT>::FRAG_QUEUE;
+  // word offsets inside a warp's region
+  static constexpr int QV0 = TILE_WORDS;           // fragment queue: values [NV][FQ]
+  static constexpr int QP0 = QV0 + NV * FQ;        // fragment queue: pixel index | item lane << 16   [FQ]
+  static constexpr int RC0 = QP0 + FQ;             // row coverage [RF_TILE]
+  static constexpr int IM0 = RC0 + RF_TILE;        // item queue: meta [RF_ROWQ]
+  static constexpr int IV0 = IM0 + (int)RF_ROWQ;   // item queue: values [NV][RF_ROWQ]
+  static constexpr int DV0 = IV0 + NV * (int)RF_ROWQ;  // dv/dx of both halves of the chunk's 32 triangles [32][2][NV]
+  static constexpr int WARP_WORDS = DV0 + 32 * 2 * NV;
   static constexpr size_t BYTES = (size_t)RF_RASTER_WARPS * WARP_WORDS * 4;
 };
 
 #ifndef RF_RASTER_MIN_BLOCKS
-#define RF_RASTER_MIN_BLOCKS 7   // resident blocks per SM at 3 varying lanes (72 registers); the persistent grid is this many per SM
+#define RF_RASTER_MIN_BLOCKS 4   // resident blocks per SM at 3 varying lanes (shared memory: 46 KB per block); the persistent grid is this many per SM
 #endif
+template <int LT> struct RasterOcc { static constexpr int BLOCKS = LT == 3 ? RF_RASTER_MIN_BLOCKS : (LT == 5 ? 4 : 3); };
+
 template <int LT, bool PEER>
-__global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_BLOCKS : 6) k_raster(PassParams P) {
-  constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW;
-  constexpr int NV = 1 + LT;
+__global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k_raster(PassParams P) {
+  constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW, QW = Rec<LT>::QW, HS = Rec<LT>::HS;
+  constexpr int NV = 1 + LT, NL = 2 + LT;
+  using RS = RasterSmem<LT>;
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
   extern __shared__ uint32_t s_raster[];
-  if (P.cstatus->poison || P.status->error) return;
+  if (P.cstatus->poison) return;
+  // A pass with a device-detected error (every check runs before this kernel) rasterises nothing, but the clears recorded
+  // at its head still happen: the tiles this kernel would have touched are initialised and written back, nothing else.
+  const bool clear_only = P.status->error != 0u;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u, warp = threadIdx.x >> 5;
   // Only DEPTH is staged in shared memory: colour is write-only on this path (no blending, target.rs:187-189),
   // so passing fragments store their pixel straight to the framebuffer. __syncwarp() between dependency
   // rounds orders two writes to one pixel; untouched pixels are never read or written.
-  float* sz = reinterpret_cast<float*>(s_raster + (size_t)warp * RasterSmem<LT>::WARP_WORDS);
-  float* qv = sz + RasterSmem<LT>::TILE_WORDS;                                  // [1+LT][FRAG_QUEUE]
-  uint32_t* qp = reinterpret_cast<uint32_t*>(qv + (1 + LT) * RasterTune<LT>::FRAG_QUEUE);    // [FRAG_QUEUE] pixel index | owner lane << 16
-  const WarpSmem wsm(sz);  // the same region for the per-fragment accesses: depth at [idx], queue behind it
-  constexpr uint32_t QV0 = RasterSmem<LT>::TILE_WORDS, QP0 = QV0 + (1 + LT) * RasterTune<LT>::FRAG_QUEUE;
+  float* sz = reinterpret_cast<float*>(s_raster + (size_t)warp * RS::WARP_WORDS);
+  const WarpSmem wsm(sz);  // the same region for the per-fragment accesses: depth at [idx], the queues behind it
+  constexpr uint32_t QV0 = RS::QV0, QP0 = RS::QP0, RC0 = RS::RC0, IM0 = RS::IM0, IV0 = RS::IV0, DV0 = RS::DV0;
+  constexpr uint32_t FQ = RasterTune<LT>::FRAG_QUEUE;
   // Row coverage [RF_TILE]: bit c of word r = pixel (r, c) is covered by a piece of the current fragment-mode batch. The pieces
   // OR their pixel runs in; popcount(coverage) == number of fragments <=> no two pieces of the batch share a pixel, and the
   // batch's fragment groups need no per-group same-pixel search (MATCH.ANY cost 10 % of this kernel's stall samples).
-  constexpr uint32_t RC0 = QP0 + RasterTune<LT>::FRAG_QUEUE;
   wsm.stu(RC0 + lane, 0u);
   __syncwarp();
   // fast-path selectors of the last warp-uniform draw seen (span mode | fragment mode << 4): looked up once per draw, not per batch
   uint32_t mode_draw = 0xFFFFFFFFu, mode_bits = 0;
   const uint32_t n_work = P.status->n_work, n_heaviest = P.status->n_work_heaviest, n_heavy = n_heaviest + P.status->n_work_heavy;
 
+  // per-draw counter update from per-lane partial sums: one atomic per warp when the contributing lanes share a draw
+  auto add_per_draw = [&](uint32_t draw, uint32_t val, bool frags_i) {
+    const uint32_t m = __ballot_sync(FULL, val != 0u);
+    if (m == 0u) return;
+    const uint32_t d0 = __shfl_sync(FULL, draw, __ffs(m) - 1);
+    if (__all_sync(FULL, val == 0u || draw == d0)) {
+      const uint32_t s = __reduce_add_sync(FULL, val);
+      if (lane == 0) atomicAdd(frags_i ? &P.dstats[d0].frags_i : &P.dstats[d0].frags_o, (unsigned long long)s);
+    } else if (val) {
+      atomicAdd(frags_i ? &P.dstats[draw].frags_i : &P.dstats[draw].frags_o, (unsigned long long)val);
+    }
+  };
+
   for (;;) {
     uint32_t wi = 0;
     if (lane == 0) wi = atomicAdd(P.cursors + 1, 1u);
-    wi = __shfl_sync(0xFFFFFFFFu, wi, 0);
+    wi = __shfl_sync(FULL, wi, 0);
     if (wi >= n_work + n_heavy) break;
     const uint32_t task = wi < n_heaviest ? P.worklist_heavy[wi] : (wi < n_heavy ? P.worklist_heavy[(size_t)RF_SLICES * P.n_tiles + (wi - n_heaviest)] : P.worklist[wi - n_heavy]);
     const uint32_t tile = task & 0x0FFFFFFFu, slice = task >> 28;  // slice 0: whole tile; k+1: rows [k, k+1) * RF_TILE / RF_SLICES
@@ -533,9 +569,11 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
     const uint32_t tw = min((uint32_t)RF_TILE, T.w - px0), th = min((uint32_t)RF_TILE, T.h - py0);
     // read once: the shared-memory accessors are volatile asm with a memory clobber, so every later T.x would be re-loaded
     // from global memory inside the fragment loops (the format switch waited on that load: 8 % of the stall samples)
-    const uint32_t t_w = T.w, t_fmt = T.fmt;
+    const uint32_t t_w = T.w, t_fmt = T.fmt, t_by0 = T.band_y0, t_by1 = T.band_y1;
+    const uint32_t t_cflags = T.clear_flags;
     const bool has_depth = T.depth != nullptr;
     const bool vec = (t_w & 3u) == 0 && tw == RF_TILE;
+    if (clear_only && t_cflags == 0u) continue;
     // tile rows this task owns (a heaviest tile is shared by RF_SLICES warps, each owning whole rows)
     const uint32_t r0 = slice ? min(th, (slice - 1u) * (RF_TILE / RF_SLICES)) : 0u;
     const uint32_t r1 = slice ? min(th, slice * (RF_TILE / RF_SLICES)) : th;
@@ -543,8 +581,12 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
     uint32_t* gc = T.color + (size_t)py0 * t_w + px0;  // framebuffer address of the tile's first pixel
     // the first 32 triangles of the bin: requested before the depth tile so that the two latencies overlap
     uint32_t nb_tri = lane < cnt ? (uint32_t)P.bins[off + lane] : 0u;
-    // ---- stage the depth tile: 128-bit coalesced loads, 8 lanes per row, 4 rows per instruction
-    if (has_depth) {
+    // ---- stage the depth tile. First touch after a Frame::clear of this pass: the clear value, no load at all.
+    const bool depth_live = has_depth && !(clear_only && !(t_cflags & RF_CLEAR_DEPTH));
+    if (depth_live && (t_cflags & RF_CLEAR_DEPTH)) {
+      const float cz = __uint_as_float(T.clear_zbits);
+      for (uint32_t r = r0; r < r1; r++) sz[r * RF_TILE_PITCH + lane] = cz;
+    } else if (depth_live) {  // 128-bit coalesced loads, 8 lanes per row, 4 rows per instruction
       const float* t_depth = T.depth;
       if (vec && r1 - r0 == RF_TILE) {  // whole tile: all eight loads in flight before the first store
         const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
@@ -568,310 +610,408 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
           if (lane < tw) sz[r * RF_TILE_PITCH + lane] = t_depth[(size_t)(py0 + r) * t_w + px0 + lane];
       }
     }
+    // ---- first touch of the colour tile: the clear colour goes to the framebuffer before the first fragment (the fragments'
+    // stores to the same lines follow within microseconds, so L2 merges them: DRAM sees each line once)
+    if (t_cflags & RF_CLEAR_COLOR) {
+      const uint32_t cc = T.clear_color;
+      if (vec) {
+        const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
+        const uint4 cc4 = make_uint4(cc, cc, cc, cc);
+        for (uint32_t r = r0 + rsub; r < r1; r += 4) *reinterpret_cast<uint4*>(gc + (size_t)r * t_w + c4) = cc4;
+      } else {
+        for (uint32_t r = r0; r < r1; r++)
+          if (lane < tw) gc[(size_t)r * t_w + lane] = cc;
+      }
+    }
     __syncwarp();
 
     uint32_t acc_draw = 0xFFFFFFFFu;  // warp-uniform draw id of the pending frags.o partial sums
     uint32_t acc_o = 0;               // per-lane partial
 
-    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+    for (uint32_t c0 = 0; c0 < cnt && !clear_only; c0 += 32) {
       // ---- lane t: one triangle of this chunk (sorted by submission key)
-      uint32_t t_tri = 0, t_sbase = 0, t_Y0 = 0, t_nU = 0, t_ra = 0, t_rows = 0, t_draw = 0;
       const bool t_have = c0 + lane < cnt;
-      t_tri = nb_tri;
+      const uint32_t t_ref = nb_tri;
       nb_tri = c0 + 32 + lane < cnt ? (uint32_t)P.bins[off + c0 + 32 + lane] : 0u;  // next chunk's triangles, one chunk ahead
+      const bool t_small = t_have && (t_ref & RF_BIN_SMALL) != 0u;
+      const uint32_t t_tri = t_ref & ~RF_BIN_SMALL;
+      uint32_t t_sbase = 0, t_Y0 = 0, t_nU = 0, t_ra = 0, t_rows = 0, t_draw = 0;
       if (t_have) {
-        const uint32_t* tr = P.tris + (size_t)t_tri * TW;
-        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(tr));
-        const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(tr + 4));  // nU, nL | target << 16
-        t_draw = h0.y; t_sbase = h0.z; t_Y0 = h0.w; t_nU = h1.x;
-        const uint32_t nrows = h1.x + (h1.y & 0xFFFFu);
+        uint32_t nrows;
+        if (t_small) {  // rows from the three y alone; the full setup waits until the triangle's round
+          const uint32_t* q = P.stris + (size_t)t_tri * QW;
+          t_draw = __ldg(q + 1);
+          float yfirst;
+          uint32_t n0, n1;
+          tri_rows(__uint_as_float(__ldg(q + 3)), __uint_as_float(__ldg(q + 3 + (3 + LT))), __uint_as_float(__ldg(q + 3 + 2 * (3 + LT))), yfirst, n0, n1);
+          t_Y0 = sat_u32(yfirst); t_nU = n0; nrows = n0 + n1;
+        } else {
+          const uint32_t* tr = P.tris + (size_t)t_tri * TW;
+          const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(tr));
+          const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(tr + 4));  // nU, nL | target << 16
+          t_draw = h0.y; t_sbase = h0.z; t_Y0 = h0.w; t_nU = h1.x;
+          nrows = h1.x + (h1.y & 0xFFFFu);
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+            for (int i = 0; i < NV; i++) wsm.stu(DV0 + (lane * 2u + hh) * NV + i, __ldg(tr + 8 + hh * HS + i));
+        }
         t_ra = max(t_Y0, py0 + r0);
         const uint32_t rb = min(t_Y0 + nrows, py0 + r1);
         t_rows = rb > t_ra ? rb - t_ra : 0u;
-        if (RF_RASTER_PREFETCH && t_rows) {  // this triangle's span records of the tile's rows: 24-64 bytes each
+        if (RF_RASTER_PREFETCH && t_rows && !t_small) {  // this triangle's span records of the tile's rows: 24-64 bytes each
           const char* sp0 = reinterpret_cast<const char*>(P.spans + (size_t)(t_sbase + (t_ra - t_Y0)) * SW);
           prefetch_l2(sp0);
           if (t_rows * (SW * 4u) > 128u) prefetch_l2(sp0 + 128);
           if (t_rows * (SW * 4u) > 256u) prefetch_l2(sp0 + 256);
         }
       }
+      if (RF_RASTER_PREFETCH && c0 + 32 + lane < cnt) {  // the next chunk's records
+        const bool nsmall = (nb_tri & RF_BIN_SMALL) != 0u;
+        const char* tp = nsmall ? reinterpret_cast<const char*>(P.stris + (size_t)(nb_tri & ~RF_BIN_SMALL) * QW)
+                                : reinterpret_cast<const char*>(P.tris + (size_t)nb_tri * TW);
+        prefetch_l2(tp);
+        if (!nsmall) prefetch_l2(tp + 128);
+      }
       const uint32_t t_incl = warp_scan_incl(t_rows, lane);
-      const uint32_t n_items = __shfl_sync(0xFFFFFFFFu, t_incl, 31);
+      const uint32_t n_items = __shfl_sync(FULL, t_incl, 31);
+      const uint32_t large_mask = __ballot_sync(FULL, t_have && !t_small && t_rows != 0u);
 
-      // Software pipeline: the span record and dv/dx of batch n+1 are requested before batch n is
-      // processed, so their (L2/HBM) latency overlaps the fragment work.
-      struct Pre {
-        bool valid;
-        uint32_t Y, draw;
-        uint32_t w[SW];
-        uint32_t dvw[NV];
-      };
-      auto fetch = [&](uint32_t ib, Pre& p) {
-        const uint32_t item = ib + lane;
-        p.valid = item < n_items;
-        // owner triangle lane: number of lanes whose inclusive end <= item
-        uint32_t ot = 0;
+      // ---- rounds: consecutive triangles whose pieces fit the item queue (t_incl is non-decreasing, a triangle has at most
+      // RF_TILE <= RF_ROWQ rows in the tile: every round takes at least one triangle whole)
+      uint32_t base = 0, ta = 0;
+      while (base < n_items) {
+        const uint32_t fitm = __ballot_sync(FULL, t_incl <= base + RF_ROWQ);
+        const uint32_t tb = fitm == FULL ? 32u : (uint32_t)__ffs(~fitm) - 1u;
+        const uint32_t nround = __shfl_sync(FULL, t_incl, tb - 1u) - base;
+        const uint32_t rmask = (tb == 32u ? FULL : (1u << tb) - 1u) & ~((1u << ta) - 1u);
+
+        // (a) SMALL triangles of the round: tri_fill's setup and ScanlineIter::next for the rows of this tile, by the
+        // triangle's lane — the reference's own sequence of operations (raster.rs:185-302, 80-114), nothing stored in between
+        uint32_t my_fi = 0;
+        if (((rmask >> lane) & 1u) && t_small && t_rows != 0u) {
+          uint32_t w[QW];
+          const uint4* q4 = reinterpret_cast<const uint4*>(P.stris + (size_t)t_tri * QW);
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          const uint32_t cand = ot + step;
-          const uint32_t e = __shfl_sync(0xFFFFFFFFu, t_incl, (cand - 1) & 31);
-          if (cand <= 32 && e <= item) ot = cand;
-        }
-        ot &= 31u;
-        const uint32_t o_incl = __shfl_sync(0xFFFFFFFFu, t_incl, ot), o_rows = __shfl_sync(0xFFFFFFFFu, t_rows, ot);
-        const uint32_t o_ra = __shfl_sync(0xFFFFFFFFu, t_ra, ot), o_Y0 = __shfl_sync(0xFFFFFFFFu, t_Y0, ot);
-        const uint32_t o_sbase = __shfl_sync(0xFFFFFFFFu, t_sbase, ot), o_nU = __shfl_sync(0xFFFFFFFFu, t_nU, ot);
-        const uint32_t o_tri = __shfl_sync(0xFFFFFFFFu, t_tri, ot);
-        p.draw = __shfl_sync(0xFFFFFFFFu, t_draw, ot);
-        p.Y = 0;
-        if (p.valid) {
-          p.Y = o_ra + (item - (o_incl - o_rows));
-          const uint32_t j = p.Y - o_Y0;
-          const uint32_t* sp = P.spans + (size_t)(o_sbase + j) * SW;
-#pragma unroll
-          for (int q = 0; q < SW / 2; q++) {
-            const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp) + q);
-            p.w[2 * q] = t.x; p.w[2 * q + 1] = t.y;
+          for (int qd = 0; qd < QW / 4; qd++) {
+            const uint4 t4 = __ldg(q4 + qd);
+            w[4 * qd] = t4.x; w[4 * qd + 1] = t4.y; w[4 * qd + 2] = t4.z; w[4 * qd + 3] = t4.w;
           }
-          const uint32_t* dp = P.tris + (size_t)o_tri * TW + 8 + (j >= o_nU ? Rec<LT>::HS : 0);
+          HalfSetup<LT> H0, H1;
+          float xabs;
+          tri_setup<LT>(w, H0, H1, xabs);
 #pragma unroll
-          for (int i = 0; i < NV; i++) p.dvw[i] = __ldg(dp + i);
-        }
-      };
-      Pre cur, nxt;
-      fetch(0, cur);
-      for (uint32_t ib = 0; ib < n_items; ib += 32, cur = nxt) {
-        nxt.valid = false;
-        if (ib + 32 < n_items) fetch(ib + 32, nxt);
-        if (RF_RASTER_PREFETCH && ib == 32 && c0 + 32 + lane < cnt) {  // header and both dv/dx of the next chunk's triangles
-          const char* tp = reinterpret_cast<const char*>(P.tris + (size_t)nb_tri * TW);
-          prefetch_l2(tp);
-          prefetch_l2(tp + 128);
-        }
-        bool valid = cur.valid;
-        uint32_t py = 32 + lane, pxs = 0, pn = 0, draw = 0;
-        float v[NV], dv[NV];
+          for (int i = 0; i < NV; i++) { wsm.stf(DV0 + (lane * 2u) * NV + i, H0.dv[1 + i]); wsm.stf(DV0 + (lane * 2u + 1u) * NV + i, H1.dv[1 + i]); }
+          uint32_t slot = (t_incl - t_rows) - base;
+          uint32_t Y = t_Y0;
+          const uint32_t Ya = t_ra, Yb = t_ra + t_rows;
+          auto walk = [&](HalfSetup<LT>& H, uint32_t hh) {
+            for (uint32_t j = 0; j < H.n && Y < Yb; j++, Y++) {
+              float v0[NL];
 #pragma unroll
-        for (int i = 0; i < NV; i++) { v[i] = 0.0f; dv[i] = 0.0f; }
-        if (valid) {
-          const uint32_t X0 = cur.w[0] & 0xFFFFu, n = cur.w[0] >> 16;
-          const uint32_t xs = max(X0, px0), xe = min(X0 + n, px0 + tw);
-          if (n == 0 || xs >= xe) valid = false;
-          else {
-            py = cur.Y - py0; pxs = xs - px0; pn = xe - xs; draw = cur.draw;
-            if (xs > X0) {  // the span started in an earlier tile column: take the checkpoint at this column
-              const uint32_t* ck = P.ckpts + (size_t)(cur.w[1] + (tx - (X0 >> RF_TILE_SHIFT) - 1)) * KW;
+              for (int i = 0; i < NL; i++) { v0[i] = H.L[i]; H.L[i] = H.L[i] + H.dl[i]; }
+              const float x1 = H.R;
+              H.R = H.R + H.dr;
+              if (Y < Ya) continue;  // a row above this tile (or slice): only the running sums advance
+              const float x0r = round_up_to_half(v0[0]), x1r = round_up_to_half(x1);
+              const uint32_t cntp = sat_u32(x1r - x0r);
+              const uint32_t X0 = sat_u32(x0r), X1 = max(sat_u32(x1r), X0);
+              uint32_t nn = min(cntp, X1 - X0);
+              if (Y < t_by0 || Y >= t_by1) nn = 0;  // not this GPU's row band
+              const uint32_t xs = max(X0, px0), xe = min(X0 + nn, px0 + tw);
+              uint32_t meta = 0u;
+              if (xe > xs) {
+                const float tx = x0r - v0[0];
+                float vv[NV];
 #pragma unroll
-              for (int q = 0; q < KW / 2; q++) {
-                const uint2 t = __ldg(reinterpret_cast<const uint2*>(ck) + q);
-                if (2 * q < NV) v[2 * q] = __uint_as_float(t.x);
-                if (2 * q + 1 < NV) v[2 * q + 1] = __uint_as_float(t.y);
+                for (int i = 0; i < NV; i++) vv[i] = v0[1 + i] + ((v0[1 + i] + H.dv[1 + i]) - v0[1 + i]) * tx;
+                for (uint32_t k = X0; k < xs; k++) {  // the span started in an earlier tile column: the pixels before this one
+#pragma unroll
+                  for (int i = 0; i < NV; i++) vv[i] = vv[i] + H.dv[1 + i];
+                }
+#pragma unroll
+                for (int i = 0; i < NV; i++) wsm.stf(IV0 + i * RF_ROWQ + slot, vv[i]);
+                my_fi += xe - xs;
+                meta = (xs - px0) | (xe - xs) << 6 | (Y - py0) << 12 | hh << 17 | lane << 18;
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < NV; i++) v[i] = __uint_as_float(cur.w[2 + i]);
+              wsm.stu(IM0 + slot, meta);
+              slot++;
             }
-#pragma unroll
-            for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(cur.dvw[i]);
-          }
+          };
+          walk(H0, 0u);
+          walk(H1, 1u);
         }
-        const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
-        if (vmask == 0) continue;
-        // ---- frags.o bookkeeping: flush partial sums when the draw changes
-        const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, draw, __ffs(vmask) - 1);
-        const bool uni = __all_sync(0xFFFFFFFFu, !valid || draw == d0);
-        if (!uni || d0 != acc_draw) {
-          if (acc_draw != 0xFFFFFFFFu) {
-            uint32_t s = acc_o;
+        add_per_draw(t_draw, my_fi, true);
+
+        // (b) pieces of the other triangles of the round: span records (and checkpoints) from k_setup / k_walk / k_ckpt
+        if (large_mask & rmask) {
+          for (uint32_t s0 = 0; s0 < nround; s0 += 32) {
+            const uint32_t slot = s0 + lane, item = base + slot;
+            const bool ivalid = slot < nround;
+            // owner triangle lane: number of lanes whose inclusive end <= item
+            uint32_t ot = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-            if (lane == 0 && s) atomicAdd(&P.dstats[acc_draw].frags_o, (unsigned long long)s);
-          }
-          acc_o = 0;
-          acc_draw = uni ? d0 : 0xFFFFFFFFu;
-        }
-        uint32_t my_o = 0;
-
-        const uint32_t f_incl = warp_scan_incl(pn, lane);
-        const uint32_t n_frags = __shfl_sync(0xFFFFFFFFu, f_incl, 31);
-
-        // warp-uniform fast-path selectors of the batch's draw (0 / 1 = generic)
-        uint32_t smode = 0, fmode = uni ? 1u : 0u;
-        if (uni) {
-          if (d0 != mode_draw) {
-            const DrawDesc& Dq = P.draws[d0];
-            const uint32_t qflags = Dq.flags, qfs = Dq.fs, qpm = Dq.persp_mask, qL = Dq.L;
-            const uint32_t dflt = RF_DEPTH_LESS << RF_F_DTEST_SHIFT | RF_F_CWRITE | RF_F_DWRITE;
-            uint32_t sm = 0, fm = 1;
-            if ((qflags & RF_F_RASTER_STATE) == dflt) {  // default Context (ctx.rs:104-127); the other flag bits concern earlier stages
-              if (qfs == RF_FS_TEX_CLAMP_LIT && qpm == 0x1Fu && LT >= 5) { sm = 4; fm = 4; }
-              else if (qfs == RF_FS_COLOR3F && qpm == 0u && LT >= 3) { sm = 2; fm = 2; }
-              else if (qfs == RF_FS_CHECKER && qpm == 0x3u && qL == 2u && LT == 5) sm = 5;
-              else if (qfs == RF_FS_SPRITE_DISC && qpm == 0x3u) fm = 3;
+            for (int step = 16; step > 0; step >>= 1) {
+              const uint32_t cand = ot + step;
+              const uint32_t e = __shfl_sync(FULL, t_incl, (cand - 1) & 31);
+              if (cand <= 32 && e <= item) ot = cand;
             }
-            mode_draw = d0; mode_bits = sm | fm << 4;
+            ot &= 31u;
+            const uint32_t o_incl = __shfl_sync(FULL, t_incl, ot), o_rows = __shfl_sync(FULL, t_rows, ot);
+            const uint32_t o_ra = __shfl_sync(FULL, t_ra, ot), o_Y0 = __shfl_sync(FULL, t_Y0, ot);
+            const uint32_t o_sbase = __shfl_sync(FULL, t_sbase, ot), o_nU = __shfl_sync(FULL, t_nU, ot);
+            const bool o_small = ((__ballot_sync(FULL, t_small) >> ot) & 1u) != 0u;
+            if (ivalid && !o_small) {
+              const uint32_t Y = o_ra + (item - (o_incl - o_rows));
+              const uint32_t j = Y - o_Y0;
+              const uint32_t* sp = P.spans + (size_t)(o_sbase + j) * SW;
+              uint32_t w[SW];
+#pragma unroll
+              for (int q = 0; q < SW / 2; q++) {
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp) + q);
+                w[2 * q] = t.x; w[2 * q + 1] = t.y;
+              }
+              const uint32_t X0 = w[0] & 0xFFFFu, n = w[0] >> 16;
+              const uint32_t xs = max(X0, px0), xe = min(X0 + n, px0 + tw);
+              uint32_t meta = 0u;
+              if (n != 0u && xs < xe) {
+                if (xs > X0) {  // the span started in an earlier tile column: take the checkpoint at this column
+                  const uint32_t* ck = P.ckpts + (size_t)(w[1] + (tx - (X0 >> RF_TILE_SHIFT) - 1)) * KW;
+#pragma unroll
+                  for (int q = 0; q < KW / 2; q++) {
+                    const uint2 t = __ldg(reinterpret_cast<const uint2*>(ck) + q);
+                    if (2 * q < NV) wsm.stu(IV0 + (2 * q) * RF_ROWQ + slot, t.x);
+                    if (2 * q + 1 < NV) wsm.stu(IV0 + (2 * q + 1) * RF_ROWQ + slot, t.y);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < NV; i++) wsm.stu(IV0 + i * RF_ROWQ + slot, w[2 + i]);
+                }
+                meta = (xs - px0) | (xe - xs) << 6 | (Y - py0) << 12 | (j >= o_nU ? 1u : 0u) << 17 | ot << 18;
+              }
+              wsm.stu(IM0 + slot, meta);
+            }
           }
-          if (has_depth) { smode = mode_bits & 15u; fmode = mode_bits >> 4; }
         }
+        __syncwarp();
 
-        if (n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask) || n_frags > RasterTune<LT>::FRAG_QUEUE) {
-          // ================= span mode: one piece per lane, walked serially =================
-          // dependencies: earlier lanes on the same row whose x-range overlaps mine
-          uint32_t dep = 0;
-          {
-            uint32_t m = __match_any_sync(0xFFFFFFFFu, py) & lt;
-            while (__any_sync(0xFFFFFFFFu, m != 0)) {
-              const int jj = m ? (__ffs(m) - 1) : (int)lane;
-              const uint32_t ox = __shfl_sync(0xFFFFFFFFu, pxs, jj), on = __shfl_sync(0xFFFFFFFFu, pn, jj);
-              if (m) {
-                if (pxs < ox + on && ox < pxs + pn) dep |= 1u << jj;
-                m &= m - 1;
+        // (c) the round's pieces, 32 at a time
+        for (uint32_t ib = 0; ib < nround; ib += 32) {
+          const uint32_t slot = ib + lane;
+          const uint32_t meta = slot < nround ? wsm.ldu(IM0 + slot) : 0u;
+          const uint32_t pn = (meta >> 6) & 63u;
+          const bool valid = pn != 0u;
+          const uint32_t pxs = meta & 63u, py = valid ? ((meta >> 12) & 31u) : 32u + lane;
+          const uint32_t draw_o = __shfl_sync(FULL, t_draw, (meta >> 18) & 31u);
+          const uint32_t draw = valid ? draw_o : 0u;
+          float v[NV], dv[NV];
+#pragma unroll
+          for (int i = 0; i < NV; i++) { v[i] = 0.0f; dv[i] = 0.0f; }
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) { v[i] = wsm.ldf(IV0 + i * RF_ROWQ + slot); dv[i] = wsm.ldf(DV0 + ((meta >> 17) & 63u) * NV + i); }
+          }
+          const uint32_t vmask = __ballot_sync(FULL, valid);
+          if (vmask == 0) continue;
+          // ---- frags.o bookkeeping: flush partial sums when the draw changes
+          const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, draw, __ffs(vmask) - 1);
+          const bool uni = __all_sync(0xFFFFFFFFu, !valid || draw == d0);
+          if (!uni || d0 != acc_draw) {
+            if (acc_draw != 0xFFFFFFFFu) {
+              uint32_t s = acc_o;
+  #pragma unroll
+              for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+              if (lane == 0 && s) atomicAdd(&P.dstats[acc_draw].frags_o, (unsigned long long)s);
+            }
+            acc_o = 0;
+            acc_draw = uni ? d0 : 0xFFFFFFFFu;
+          }
+          uint32_t my_o = 0;
+
+          const uint32_t f_incl = warp_scan_incl(pn, lane);
+          const uint32_t n_frags = __shfl_sync(0xFFFFFFFFu, f_incl, 31);
+
+          // warp-uniform fast-path selectors of the batch's draw (0 / 1 = generic)
+          uint32_t smode = 0, fmode = uni ? 1u : 0u;
+          if (uni) {
+            if (d0 != mode_draw) {
+              const DrawDesc& Dq = P.draws[d0];
+              const uint32_t qflags = Dq.flags, qfs = Dq.fs, qpm = Dq.persp_mask, qL = Dq.L;
+              const uint32_t dflt = RF_DEPTH_LESS << RF_F_DTEST_SHIFT | RF_F_CWRITE | RF_F_DWRITE;
+              uint32_t sm = 0, fm = 1;
+              if ((qflags & RF_F_RASTER_STATE) == dflt) {  // default Context (ctx.rs:104-127); the other flag bits concern earlier stages
+                if (qfs == RF_FS_TEX_CLAMP_LIT && qpm == 0x1Fu && LT >= 5) { sm = 4; fm = 4; }
+                else if (qfs == RF_FS_COLOR3F && qpm == 0u && LT >= 3) { sm = 2; fm = 2; }
+                else if (qfs == RF_FS_CHECKER && qpm == 0x3u && qL == 2u && LT == 5) sm = 5;
+                else if (qfs == RF_FS_SPRITE_DISC && qpm == 0x3u) fm = 3;
+              }
+              mode_draw = d0; mode_bits = sm | fm << 4;
+            }
+            if (has_depth) { smode = mode_bits & 15u; fmode = mode_bits >> 4; }
+          }
+
+          if (n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask) || n_frags > RasterTune<LT>::FRAG_QUEUE) {
+            // ================= span mode: one piece per lane, walked serially =================
+            // dependencies: earlier lanes on the same row whose x-range overlaps mine
+            uint32_t dep = 0;
+            {
+              uint32_t m = __match_any_sync(0xFFFFFFFFu, py) & lt;
+              while (__any_sync(0xFFFFFFFFu, m != 0)) {
+                const int jj = m ? (__ffs(m) - 1) : (int)lane;
+                const uint32_t ox = __shfl_sync(0xFFFFFFFFu, pxs, jj), on = __shfl_sync(0xFFFFFFFFu, pn, jj);
+                if (m) {
+                  if (pxs < ox + on && ox < pxs + pn) dep |= 1u << jj;
+                  m &= m - 1;
+                }
               }
             }
-          }
-          const DrawDesc& D = P.draws[draw];
-          uint32_t done = ~vmask;
-          bool pending = valid;
-          while (done != 0xFFFFFFFFu) {
-            const bool ready = pending && (dep & ~done) == 0;
-            if (ready) {
-              const uint32_t base = py * RF_TILE_PITCH + pxs;
-              if (smode == 4) {  // default Context + FS_TEX_CLAMP_LIT (crates): straight-line fragment code
-                for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, gc, t_w, wsm, base + k, v);
-#pragma unroll
-                  for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
+            const DrawDesc& D = P.draws[draw];
+            uint32_t done = ~vmask;
+            bool pending = valid;
+            while (done != 0xFFFFFFFFu) {
+              const bool ready = pending && (dep & ~done) == 0;
+              if (ready) {
+                const uint32_t base = py * RF_TILE_PITCH + pxs;
+                if (smode == 4) {  // default Context + FS_TEX_CLAMP_LIT (crates): straight-line fragment code
+                  for (uint32_t k = 0; k < pn; k++) {
+                    my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, gc, t_w, wsm, base + k, v);
+  #pragma unroll
+                    for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
+                  }
+                } else if (smode == 2) {
+                  for (uint32_t k = 0; k < pn; k++) {
+                    my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, gc, t_w, wsm, base + k, v);
+  #pragma unroll
+                    for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
+                  }
+                } else if (LT == 5 && smode == 5) {  // default Context + FS_CHECKER on two perspective uv lanes (the crates floor): z, u, v only
+                  for (uint32_t k = 0; k < pn; k++) {
+                    my_o += process_fragment_fixed<LT, RF_FS_CHECKER, 0x3u>(D, t_fmt, gc, t_w, wsm, base + k, v);
+  #pragma unroll
+                    for (int i = 0; i < 3; i++) v[i] = v[i] + dv[i];
+                  }
+                } else {
+                  const uint32_t flags = D.flags, pmask = D.persp_mask, fs = D.fs;
+                  const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
+                  const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
+                  for (uint32_t k = 0; k < pn; k++) {
+                    my_o += process_fragment<LT>(D, fs, t_fmt, gc, t_w, wsm, base + k, v, pmask, dtest, cwrite, dwrite);
+  #pragma unroll
+                    for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
+                  }
                 }
-              } else if (smode == 2) {
-                for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, gc, t_w, wsm, base + k, v);
-#pragma unroll
-                  for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
-                }
-              } else if (LT == 5 && smode == 5) {  // default Context + FS_CHECKER on two perspective uv lanes (the crates floor): z, u, v only
-                for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment_fixed<LT, RF_FS_CHECKER, 0x3u>(D, t_fmt, gc, t_w, wsm, base + k, v);
-#pragma unroll
-                  for (int i = 0; i < 3; i++) v[i] = v[i] + dv[i];
-                }
-              } else {
-                const uint32_t flags = D.flags, pmask = D.persp_mask, fs = D.fs;
-                const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
-                const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
-                for (uint32_t k = 0; k < pn; k++) {
-                  my_o += process_fragment<LT>(D, fs, t_fmt, gc, t_w, wsm, base + k, v, pmask, dtest, cwrite, dwrite);
-#pragma unroll
-                  for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
+              }
+              __syncwarp();
+              done |= __ballot_sync(0xFFFFFFFFu, ready);
+              if (ready) pending = false;
+            }
+            if (uni) acc_o += my_o;
+            else if (my_o) atomicAdd(&P.dstats[draw].frags_o, (unsigned long long)my_o);
+          } else {
+            // ================= fragment mode: one fragment per lane =================
+            // Phase A: every piece lane walks its piece (sequential adds, vary.rs:146-154) and queues one
+            // record per fragment in shared memory; phase B: 32 fragments at a time, one per lane.
+            {
+              const uint32_t qstart = f_incl - pn;
+              uint32_t maxn = pn;
+  #pragma unroll
+              for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xFFFFFFFFu, maxn, o));
+              const uint32_t pix0 = py * RF_TILE_PITCH + pxs;
+              if (pn) wsm.oru(RC0 + py, (0xFFFFFFFFu >> (32u - pn)) << pxs);  // this piece's pixels of tile row py
+              for (uint32_t k = 0; k < maxn; k++) {
+                if (k < pn) {
+                  const uint32_t q = qstart + k;
+  #pragma unroll
+                  for (int i = 0; i < NV; i++) { wsm.stf(QV0 + i * RasterTune<LT>::FRAG_QUEUE + q, v[i]); v[i] = v[i] + dv[i]; }
+                  wsm.stu(QP0 + q, (pix0 + k) | lane << 16);
                 }
               }
             }
             __syncwarp();
-            done |= __ballot_sync(0xFFFFFFFFu, ready);
-            if (ready) pending = false;
-          }
-          if (uni) acc_o += my_o;
-          else if (my_o) atomicAdd(&P.dstats[draw].frags_o, (unsigned long long)my_o);
-        } else {
-          // ================= fragment mode: one fragment per lane =================
-          // Phase A: every piece lane walks its piece (sequential adds, vary.rs:146-154) and queues one
-          // record per fragment in shared memory; phase B: 32 fragments at a time, one per lane.
-          {
-            const uint32_t qstart = f_incl - pn;
-            uint32_t maxn = pn;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xFFFFFFFFu, maxn, o));
-            const uint32_t pix0 = py * RF_TILE_PITCH + pxs;
-            if (pn) wsm.oru(RC0 + py, (0xFFFFFFFFu >> (32u - pn)) << pxs);  // this piece's pixels of tile row py
-            for (uint32_t k = 0; k < maxn; k++) {
-              if (k < pn) {
-                const uint32_t q = qstart + k;
-#pragma unroll
-                for (int i = 0; i < NV; i++) { wsm.stf(QV0 + i * RasterTune<LT>::FRAG_QUEUE + q, v[i]); v[i] = v[i] + dv[i]; }
-                wsm.stu(QP0 + q, (pix0 + k) | lane << 16);
-              }
-            }
-          }
-          __syncwarp();
-          // distinct pixels covered by the batch (lane r counts tile row r and clears its word for the next batch)
-          const uint32_t rcov = wsm.ldu(RC0 + lane);
-          wsm.stu(RC0 + lane, 0u);
-          const bool no_overlap = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(rcov)) == n_frags;
-          // Phase B. When the whole batch belongs to one draw (the common case) the draw state is
-          // warp-uniform and hoisted out of the loop; otherwise every fragment looks its draw up.
-          auto frag_loop = [&](auto mode_tag) {
-            // MODE 0: per-lane draw state; 1: warp-uniform state; 2..4: warp-uniform default state with a fixed shader
-            constexpr int MODE = decltype(mode_tag)::value;
-            constexpr bool UNI = MODE >= 1;
-            const DrawDesc& Du = P.draws[d0];
-            const uint32_t u_flags = Du.flags, u_pmask = Du.persp_mask, u_fs = Du.fs;
-            const uint32_t u_dtest = has_depth ? ((u_flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
-            const bool u_cwrite = (u_flags & RF_F_CWRITE) != 0, u_dwrite = has_depth && (u_flags & RF_F_DWRITE) != 0;
-            for (uint32_t fb = 0; fb < n_frags; fb += 32) {
-              const uint32_t f = fb + lane;
-              const bool fvalid = f < n_frags;
-              float fv[NV];
-              uint32_t pw = 0;
-              if (fvalid) {
-#pragma unroll
-                for (int i = 0; i < NV; i++) fv[i] = wsm.ldf(QV0 + i * RasterTune<LT>::FRAG_QUEUE + f);
-                pw = wsm.ldu(QP0 + f);
-              } else {
-#pragma unroll
-                for (int i = 0; i < NV; i++) fv[i] = 0.0f;
-              }
-              const uint32_t pix = fvalid ? (pw & 0xFFFFu) : (0x10000u + lane);
-              // same pixel, submitted before me: only searched for when two pieces of the batch overlap at all
-              uint32_t earlier = 0;
-              bool clean = true;
-              if (!no_overlap) {
-                earlier = __match_any_sync(0xFFFFFFFFu, pix) & lt;
-                clean = __all_sync(0xFFFFFFFFu, earlier == 0);
-              }
-              uint32_t fdraw = d0, pmask = u_pmask, fs = u_fs, dtest = u_dtest;
-              bool cwrite = u_cwrite, dwrite = u_dwrite;
-              if (!UNI) {
-                fdraw = __shfl_sync(0xFFFFFFFFu, draw, (pw >> 16) & 31u);
-                const DrawDesc& Dl = P.draws[fdraw];
-                const uint32_t flags = Dl.flags;
-                pmask = Dl.persp_mask; fs = Dl.fs;
-                dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
-                cwrite = (flags & RF_F_CWRITE) != 0; dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
-              }
-              const DrawDesc& D = UNI ? Du : P.draws[fdraw];
-              uint32_t wrote = 0;
-              auto one = [&]() -> uint32_t {
-                if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, gc, t_w, wsm, pix, fv);
-                if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, t_fmt, gc, t_w, wsm, pix, fv);
-                if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, gc, t_w, wsm, pix, fv);
-                return process_fragment<LT>(D, fs, t_fmt, gc, t_w, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
-              };
-              if (clean) {
-                if (fvalid) wrote = one();
-#if RF_GROUP_SYNC
-                __syncwarp();  // orders this group's depth/colour writes before the next group's accesses to the same pixels
-#endif
-              } else {
-                uint32_t done = ~__ballot_sync(0xFFFFFFFFu, fvalid);
-                bool pending = fvalid;
-                while (done != 0xFFFFFFFFu) {
-                  const bool ready = pending && (earlier & ~done) == 0;
-                  if (ready) wrote = one();
-                  __syncwarp();
-                  done |= __ballot_sync(0xFFFFFFFFu, ready);
-                  if (ready) pending = false;
+            // distinct pixels covered by the batch (lane r counts tile row r and clears its word for the next batch)
+            const uint32_t rcov = wsm.ldu(RC0 + lane);
+            wsm.stu(RC0 + lane, 0u);
+            const bool no_overlap = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(rcov)) == n_frags;
+            // Phase B. When the whole batch belongs to one draw (the common case) the draw state is
+            // warp-uniform and hoisted out of the loop; otherwise every fragment looks its draw up.
+            auto frag_loop = [&](auto mode_tag) {
+              // MODE 0: per-lane draw state; 1: warp-uniform state; 2..4: warp-uniform default state with a fixed shader
+              constexpr int MODE = decltype(mode_tag)::value;
+              constexpr bool UNI = MODE >= 1;
+              const DrawDesc& Du = P.draws[d0];
+              const uint32_t u_flags = Du.flags, u_pmask = Du.persp_mask, u_fs = Du.fs;
+              const uint32_t u_dtest = has_depth ? ((u_flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
+              const bool u_cwrite = (u_flags & RF_F_CWRITE) != 0, u_dwrite = has_depth && (u_flags & RF_F_DWRITE) != 0;
+              for (uint32_t fb = 0; fb < n_frags; fb += 32) {
+                const uint32_t f = fb + lane;
+                const bool fvalid = f < n_frags;
+                float fv[NV];
+                uint32_t pw = 0;
+                if (fvalid) {
+  #pragma unroll
+                  for (int i = 0; i < NV; i++) fv[i] = wsm.ldf(QV0 + i * RasterTune<LT>::FRAG_QUEUE + f);
+                  pw = wsm.ldu(QP0 + f);
+                } else {
+  #pragma unroll
+                  for (int i = 0; i < NV; i++) fv[i] = 0.0f;
                 }
+                const uint32_t pix = fvalid ? (pw & 0xFFFFu) : (0x10000u + lane);
+                // same pixel, submitted before me: only searched for when two pieces of the batch overlap at all
+                uint32_t earlier = 0;
+                bool clean = true;
+                if (!no_overlap) {
+                  earlier = __match_any_sync(0xFFFFFFFFu, pix) & lt;
+                  clean = __all_sync(0xFFFFFFFFu, earlier == 0);
+                }
+                uint32_t fdraw = d0, pmask = u_pmask, fs = u_fs, dtest = u_dtest;
+                bool cwrite = u_cwrite, dwrite = u_dwrite;
+                if (!UNI) {
+                  fdraw = __shfl_sync(0xFFFFFFFFu, draw, (pw >> 16) & 31u);
+                  const DrawDesc& Dl = P.draws[fdraw];
+                  const uint32_t flags = Dl.flags;
+                  pmask = Dl.persp_mask; fs = Dl.fs;
+                  dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
+                  cwrite = (flags & RF_F_CWRITE) != 0; dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
+                }
+                const DrawDesc& D = UNI ? Du : P.draws[fdraw];
+                uint32_t wrote = 0;
+                auto one = [&]() -> uint32_t {
+                  if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, gc, t_w, wsm, pix, fv);
+                  if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, t_fmt, gc, t_w, wsm, pix, fv);
+                  if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, gc, t_w, wsm, pix, fv);
+                  return process_fragment<LT>(D, fs, t_fmt, gc, t_w, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
+                };
+                if (clean) {
+                  if (fvalid) wrote = one();
+  #if RF_GROUP_SYNC
+                  __syncwarp();  // orders this group's depth/colour writes before the next group's accesses to the same pixels
+  #endif
+                } else {
+                  uint32_t done = ~__ballot_sync(0xFFFFFFFFu, fvalid);
+                  bool pending = fvalid;
+                  while (done != 0xFFFFFFFFu) {
+                    const bool ready = pending && (earlier & ~done) == 0;
+                    if (ready) wrote = one();
+                    __syncwarp();
+                    done |= __ballot_sync(0xFFFFFFFFu, ready);
+                    if (ready) pending = false;
+                  }
+                }
+                if (UNI) acc_o += wrote;
+                else if (wrote) atomicAdd(&P.dstats[fdraw].frags_o, 1ull);
               }
-              if (UNI) acc_o += wrote;
-              else if (wrote) atomicAdd(&P.dstats[fdraw].frags_o, 1ull);
-            }
-          };
-          if (fmode == 0) frag_loop(std::integral_constant<int, 0>{});
-          else if (fmode == 2) frag_loop(std::integral_constant<int, 2>{});
-          else if (fmode == 3) frag_loop(std::integral_constant<int, 3>{});
-          else if (fmode == 4) frag_loop(std::integral_constant<int, 4>{});
-          else frag_loop(std::integral_constant<int, 1>{});
-          __syncwarp();
+            };
+            if (fmode == 0) frag_loop(std::integral_constant<int, 0>{});
+            else if (fmode == 2) frag_loop(std::integral_constant<int, 2>{});
+            else if (fmode == 3) frag_loop(std::integral_constant<int, 3>{});
+            else if (fmode == 4) frag_loop(std::integral_constant<int, 4>{});
+            else frag_loop(std::integral_constant<int, 1>{});
+            __syncwarp();
+          }
         }
+        __syncwarp();  // the queues are rewritten by the next round
+        base += nround;
+        ta = tb;
       }
     }
     if (acc_draw != 0xFFFFFFFFu) {
@@ -883,7 +1023,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, LT == 3 ? RF_RASTER_MIN_
     __syncwarp();
 
     // ---- write the depth tile back: 128-bit coalesced stores
-    if (has_depth) {
+    if (depth_live) {
       float* t_depth = T.depth;
       if (vec) {
         const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
@@ -941,4 +1081,50 @@ __global__ void __launch_bounds__(256) k_clear_multi(const ClearDesc* __restrict
   if (tid < head) c.ptr[tid] = c.value;
   for (size_t i = tid; i < n4; i += nth) p4[i] = v4;
   for (size_t i = (n4 << 2) + tid; i < nb; i += nth) body[i] = c.value;
+}
+
+// =============================================================================================
+// First-touch clear, the other half: the tiles of a cleared target that no triangle of the pass
+// was binned into are filled here (one warp per tile, 128-bit stores, whole 128-byte rows); the
+// touched ones are initialised by k_raster. Runs on the side stream next to k_raster: the two
+// write disjoint tiles. Under sort-first sharding only the rows of this GPU's band are cleared.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_clear_untouched(PassParams P) {
+  if (P.cstatus->poison) return;
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t tile = gw; tile < P.n_tiles; tile += nw) {
+    if (P.tile_cnt[tile] != 0u) continue;
+    uint32_t ti = 0;
+    if (P.tiles_per_target) ti = tile / P.tiles_per_target;
+    else {
+      uint32_t lo = 0, hi = P.n_targets;
+      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.targets[mid].tile_base <= tile) lo = mid; else hi = mid; }
+      ti = lo;
+    }
+    const TargetDesc& T = P.targets[ti];
+    const uint32_t cf = T.clear_flags;
+    if (cf == 0u) continue;
+    const uint32_t tl = tile - T.tile_base;
+    const uint32_t ty = tl / T.tiles_x, tx = tl - ty * T.tiles_x;
+    const uint32_t px0 = tx << RF_TILE_SHIFT, py0 = ty << RF_TILE_SHIFT;
+    const uint32_t tw = min((uint32_t)RF_TILE, T.w - px0);
+    const uint32_t ya = max(py0, T.band_y0), yb = min(min(py0 + RF_TILE, T.h), T.band_y1);
+    const bool vec = (T.w & 3u) == 0 && tw == RF_TILE;
+    const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
+#pragma unroll
+    for (int plane = 0; plane < 2; plane++) {
+      if (!(cf & (plane ? RF_CLEAR_DEPTH : RF_CLEAR_COLOR))) continue;
+      uint32_t* buf = plane ? reinterpret_cast<uint32_t*>(T.depth) : T.color;
+      if (buf == nullptr) continue;
+      const uint32_t val = plane ? T.clear_zbits : T.clear_color;
+      if (vec) {
+        const uint4 v4 = make_uint4(val, val, val, val);
+        for (uint32_t y = ya + rsub; y < yb; y += 4) *reinterpret_cast<uint4*>(buf + (size_t)y * T.w + px0 + c4) = v4;
+      } else {
+        for (uint32_t y = ya; y < yb; y++)
+          if (lane < tw) buf[(size_t)y * T.w + px0 + lane] = val;
+      }
+    }
+  }
 }
