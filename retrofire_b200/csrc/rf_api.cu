@@ -155,10 +155,10 @@ struct rf_ctx {
   std::vector<int> flight;     // slots launched and not yet validated, oldest first
 
   // scratch arenas shared by all passes (stream order makes reuse safe)
-  DevBuf cv, sv, stris, largelist, spans, tris, entries, bins, bins2, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
+  DevBuf cv, sv, stris, smalls, spans, tris, entries, bins, bins2, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
   // capacities: spans/tris/ckpts in 32-bit WORDS (record width depends on the pass's lane count),
   // entries and long spans in records
-  size_t capw_stris = 0, capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
+  size_t capw_stris = 0, capw_smalls = 0, capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
   CtxStatus* d_cstatus = nullptr;
   DevBuf sdepth, ord_k32[2], ord_v[2], ord_k64[2], ord_tmp;  // Context::depth_sort (rf_order.cuh), allocated on first use
   DevBuf peer_flags;           // this GPU's barrier slots (rf_peer.cuh), written by the peers
@@ -206,10 +206,11 @@ size_t words_span(int lt) { return lt == 3 ? Rec<3>::SW : lt == 5 ? Rec<5>::SW :
 size_t words_tri(int lt) { return lt == 3 ? Rec<3>::TW : lt == 5 ? Rec<5>::TW : Rec<8>::TW; }
 size_t words_ckpt(int lt) { return lt == 3 ? Rec<3>::KW : lt == 5 ? Rec<5>::KW : Rec<8>::KW; }
 size_t words_stri(int lt) { return lt == 3 ? Rec<3>::QW : lt == 5 ? Rec<5>::QW : Rec<8>::QW; }
+size_t words_small(int lt) { return lt == 3 ? SmallRec<3>::W : lt == 5 ? SmallRec<5>::W : SmallRec<8>::W; }
 size_t words_eck(int lt) { return lt == 3 ? Rec<3>::EW : lt == 5 ? Rec<5>::EW : Rec<8>::EW; }
 
 struct ArenaWants {  // spans/tris/ckpts/ecks in words, the rest in records
-  size_t w_spans, w_tris, w_ckpts, w_stris, entries, longs, chunks, tall;
+  size_t w_spans, w_tris, w_ckpts, w_stris, entries, longs, chunks, tall, w_smalls;
 };
 
 // ---- small utility kernels --------------------------------------------------------------------
@@ -355,10 +356,8 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
 rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const ArenaWants& w) {
   if (!c->cv.reserve(nv * words_cv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "clip-vertex arena");
   if (!c->sv.reserve(nv * words_sv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "screen-vertex arena");
-  if (w.w_stris > c->capw_stris) {  // the large list names screen triangles: one slot per record of the narrowest layout
-    if (!c->stris.reserve(w.w_stris * 4) || !c->largelist.reserve(w.w_stris / Rec<3>::QW * 4 + 64)) return fail(c, RF_E_NOMEM, "screen-triangle arena");
-    c->capw_stris = w.w_stris;
-  }
+  if (w.w_stris > c->capw_stris) { if (!c->stris.reserve(w.w_stris * 4)) return fail(c, RF_E_NOMEM, "screen-triangle arena"); c->capw_stris = w.w_stris; }
+  if (w.w_smalls > c->capw_smalls) { if (!c->smalls.reserve(w.w_smalls * 4)) return fail(c, RF_E_NOMEM, "small-triangle arena"); c->capw_smalls = w.w_smalls; }
   if (w.w_spans > c->capw_spans) { if (!c->spans.reserve(w.w_spans * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->capw_spans = w.w_spans; }
   if (w.w_tris > c->capw_tris) { if (!c->tris.reserve(w.w_tris * 4)) return fail(c, RF_E_NOMEM, "triangle arena"); c->capw_tris = w.w_tris; }
   if (w.w_ckpts > c->capw_ckpts) { if (!c->ckpts.reserve(w.w_ckpts * 4)) return fail(c, RF_E_NOMEM, "checkpoint arena"); c->capw_ckpts = w.w_ckpts; }
@@ -378,7 +377,7 @@ rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const Aren
 }
 
 bool arenas_cover(const rf_ctx* c, const ArenaWants& w) {
-  return w.w_stris <= c->capw_stris && w.w_spans <= c->capw_spans && w.w_tris <= c->capw_tris && w.w_ckpts <= c->capw_ckpts &&
+  return w.w_stris <= c->capw_stris && w.w_smalls <= c->capw_smalls && w.w_spans <= c->capw_spans && w.w_tris <= c->capw_tris && w.w_ckpts <= c->capw_ckpts &&
          w.entries <= c->cap_entries && w.longs <= c->cap_long && w.chunks <= c->cap_chunks && w.tall <= c->cap_tall;
 }
 
@@ -427,7 +426,8 @@ rf_status launch_pass(rf_ctx* c, int si) {
   ArenaWants want{std::max<size_t>(c->capw_spans, (size_t)8 << 20), std::max<size_t>(c->capw_tris, (size_t)8 << 20),
                   std::max<size_t>(c->capw_ckpts, (size_t)2 << 20), std::max<size_t>(c->capw_stris, (size_t)8 << 20),
                   std::max<size_t>(c->cap_entries, (size_t)1 << 20), std::max<size_t>(c->cap_long, (size_t)1 << 19),
-                  std::max<size_t>(c->cap_chunks, (size_t)1 << 20), std::max<size_t>(c->cap_tall, (size_t)1 << 18)};
+                  std::max<size_t>(c->cap_chunks, (size_t)1 << 20), std::max<size_t>(c->cap_tall, (size_t)1 << 18),
+                  std::max<size_t>(c->capw_smalls, (size_t)8 << 20)};
   need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->sv.cap < (size_t)nv * words_sv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * kTileArrays * 4 + 64 ||
               !arenas_cover(c, want) || c->cursors.cap < 64;
   // Context::depth_sort: bound on the pass's screen triangles (a clipped triangle fans into <= 7) and the sort buffers
@@ -580,7 +580,8 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.sv = static_cast<float*>(c->sv.p);
   P.stris = static_cast<uint32_t*>(c->stris.p);
   P.cap_stris = (uint32_t)std::min<size_t>(c->capw_stris / words_stri(lt), 0x1FFFFFF0u);
-  P.largelist = static_cast<uint32_t*>(c->largelist.p);
+  P.smalls = static_cast<uint32_t*>(c->smalls.p);
+  P.cap_smalls = (uint32_t)std::min<size_t>(c->capw_smalls / words_small(lt), 0x7FFFFFF0u);
   P.sdepth = s.order_upper ? static_cast<uint32_t*>(c->sdepth.p) : nullptr;
   P.spans = static_cast<uint32_t*>(c->spans.p);
   P.tris = static_cast<uint32_t*>(c->tris.p);
@@ -640,8 +641,8 @@ rf_status validate_all(rf_ctx* c) {
     RF_CUDA(c, cudaEventSynchronize(s.ev_stop));
     const PassStatus ps = s.h_status->status;
     if (getenv("RF_DEBUG_PASS"))
-      fprintf(stderr, "[rf pass] draws %zu stris %llu large %llu tris %llu spans %llu entries %llu chunks %llu long %llu ckpts %llu work %u max_bin %u overflow %u error %u\n",
-              s.draws.size(), ps.stris_needed.v, ps.large_needed.v, ps.tris_needed.v, ps.spans_needed.v, ps.entries_needed.v, ps.chunks_needed.v,
+      fprintf(stderr, "[rf pass] draws %zu stris %llu small %llu tris %llu spans %llu entries %llu chunks %llu long %llu ckpts %llu work %u max_bin %u overflow %u error %u\n",
+              s.draws.size(), ps.stris_needed.v, ps.small_needed.v, ps.tris_needed.v, ps.spans_needed.v, ps.entries_needed.v, ps.chunks_needed.v,
               ps.long_needed.v, ps.ckpts_needed.v, ps.n_work, ps.max_bin, ps.overflow, ps.error);
     if (ps.overflow) {
       // Every later pass in flight was a no-op (device poison). Grow and replay from here, in order.
@@ -649,13 +650,13 @@ rf_status validate_all(rf_ctx* c) {
       const int lt = (int)s.lt;
       auto grow = [](size_t cap, unsigned long long need) { return need > cap ? (size_t)(need + need / 4 + 4096) : cap; };
       // counters downstream of an overflowed stage are incomplete: guess them from the span count
-      const bool early = ps.stris_needed * words_stri(lt) > c->capw_stris || ps.spans_needed * words_span(lt) > c->capw_spans || ps.tris_needed * words_tri(lt) > c->capw_tris ||
+      const bool early = ps.stris_needed * words_stri(lt) > c->capw_stris || ps.small_needed * words_small(lt) > c->capw_smalls || ps.spans_needed * words_span(lt) > c->capw_spans || ps.tris_needed * words_tri(lt) > c->capw_tris ||
                          ps.chunks_needed > c->cap_chunks || ps.entries_needed > c->cap_entries;
       ArenaWants w{grow(c->capw_spans, ps.spans_needed * words_span(lt)), grow(c->capw_tris, ps.tris_needed * words_tri(lt)),
                    grow(c->capw_ckpts, std::max<unsigned long long>(ps.ckpts_needed, early ? ps.spans_needed / 8 : 0) * words_ckpt(lt)),
                    grow(c->capw_stris, ps.stris_needed * words_stri(lt)), grow(c->cap_entries, ps.entries_needed),
                    grow(c->cap_long, std::max<unsigned long long>(ps.long_needed, early ? ps.spans_needed / 8 : 0)),
-                   grow(c->cap_chunks, ps.chunks_needed), grow(c->cap_tall, ps.tall_needed)};
+                   grow(c->cap_chunks, ps.chunks_needed), grow(c->cap_tall, ps.tall_needed), grow(c->capw_smalls, ps.small_needed * words_small(lt))};
       { rf_status st = ensure_arenas(c, lt, s.NV, s.n_tiles, w); if (st) return st; }
       RF_CUDA(c, cudaMemsetAsync(c->d_cstatus, 0, sizeof(CtxStatus), c->stream));
       std::vector<int> replay = c->flight;
@@ -911,7 +912,7 @@ void rf_ctx_destroy(rf_ctx* c) {
     if (s.ev_join) cudaEventDestroy(s.ev_join);
     if (s.ev_join2) cudaEventDestroy(s.ev_join2);
   }
-  c->cv.release(); c->sv.release(); c->stris.release(); c->largelist.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->bins2.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
+  c->cv.release(); c->sv.release(); c->stris.release(); c->smalls.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->bins2.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
   c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
   for (uint32_t r = 0; r < c->pb.world; r++) if (r != c->pb.self && c->pb_ipc[r]) cudaIpcCloseMemHandle(c->pb.flags[r]);
   c->peer_flags.release();

@@ -97,7 +97,7 @@ struct PassStatus {
   PaddedCounter long_needed;     // spans that cross a tile-column boundary
   PaddedCounter ckpts_needed;    // checkpoint records for those spans
   PaddedCounter bins_needed;     // total size of all tile bins
-  PaddedCounter large_needed;    // screen triangles that take the k_setup path (tall, wide, near the target's edge, lines)
+  PaddedCounter small_needed;    // SMALL triangles: set up by k_assemble, binned there, walked by k_raster (no k_setup, no span records)
   uint32_t error;                // RF_ERRBIT_*
   uint32_t overflow;             // a capacity was exceeded: nothing was rasterised
   uint32_t n_work;               // non-empty tiles
@@ -134,7 +134,8 @@ struct PassParams {
   float* sv;              // screen verts [NV][SVS]: to_screen of every vertex inside the frustum, plus its outcode
   uint32_t* stris;        // [cap_stris][QW]   compacted screen triangles (k_assemble -> k_setup)
   uint32_t cap_stris;
-  uint32_t* largelist;    // [cap_stris] indices into stris of the triangles k_setup processes (the others are binned by k_assemble)
+  uint32_t* smalls;       // [cap_smalls][SmallRec<LT>::W]  SMALL triangles: both trapezoid-half setups, written by k_assemble, walked by k_raster
+  uint32_t cap_smalls;
   uint32_t* sdepth;       // [cap_stris] total-order bits of Render::depth, or null when no draw of the pass is depth-sorted
   uint32_t* spans;        // [cap_spans][SW]   one per scanline, contiguous per triangle
   uint32_t* tris;         // [cap_tris][TW]    per drawn triangle: key, draw, rows, dv/dx of both halves
@@ -163,8 +164,8 @@ struct PassParams {
 #define RF_NO_CKPT 0xFFFFFFFFu
 #define RF_STRI_LINE 0x80000000u  // flag in the draw word of a screen-triangle record: the record is an Edge (2 vertices)
 #define RF_NO_TILE 0xFFFFFFFFu
-// Bin entries name either a triangle record written by k_setup, or — flag set — a screen-triangle record of k_assemble
-// that the rasteriser sets up and walks itself (a SMALL triangle: few scanlines, narrow, inside the target).
+// Bin entries name either a triangle record written by k_setup, or — flag set — a SMALL-triangle record of k_assemble
+// (few scanlines, narrow, inside the target) whose scanlines the rasteriser walks itself.
 #define RF_BIN_SMALL 0x80000000u
 #ifndef RF_SMALL_ROWS
 #define RF_SMALL_ROWS 32u      // most scanlines of a SMALL triangle (0 switches the class off)
@@ -183,6 +184,16 @@ template <int LT> struct Rec {
   static constexpr int EW = (2 + LT + 1 + 1) & ~1;     // edge checkpoint: L[2+LT], R                        (8 B aligned)
   static constexpr int KW = (1 + LT + 1) & ~1;         // checkpoint: z, attr[LT]                   (8 B aligned)
   static constexpr int QW = (2 + 3 * (3 + LT) + 3) & ~3;  // screen triangle: key, draw, 3 x (x,y,z,attr[LT]) (16 B aligned)
+};
+
+// SMALL triangle record (k_assemble -> k_raster): [0] key  [1] draw  [2] first row Y0  [3] rows of the upper half | lower half << 16,
+// then per trapezoid half (HW words, 16-byte aligned): L[2+LT] (x, z, attr at the first row centre), dl[2+LT] (per-row step),
+// R, dr, dv/dx[1+LT] (z, attr) — everything raster.rs:248-302 precomputes, minus the unused y lane. 144 bytes at LT = 3.
+template <int LT> struct SmallRec {
+  static constexpr int NV = 1 + LT, NL = 2 + LT;
+  static constexpr int O_L = 0, O_DL = NL, O_R = 2 * NL, O_DR = 2 * NL + 1, O_DV = 2 * NL + 2;
+  static constexpr int HW = (NV + 2 * NL + 2 + 3) & ~3;
+  static constexpr int W = 4 + 2 * HW;
 };
 
 // ---- Rust `as` casts (saturating, NaN -> 0). PTX cvt.rzi.{u32,s32}.f32 clamps and maps NaN to 0.

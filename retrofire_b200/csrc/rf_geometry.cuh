@@ -637,19 +637,18 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
           }
         }
       }
-      const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
-      if (emask == 0) continue;
+      if (__ballot_sync(0xFFFFFFFFu, emit) == 0u) continue;
       // ---- SMALL or LARGE (see RF_BIN_SMALL). A SMALL triangle has few scanlines, a narrow bounding box and lies inside the
       // target, so no scanline can leave the target (target.rs:148,173-174 cannot panic) and its pixels lie in the tiles of
-      // its bounding box: it is binned right here and k_raster sets it up and walks it from this record. Everything else —
-      // also anything with a non-finite coordinate — goes to k_setup through the large list.
+      // its bounding box: it is set up (tri_fill, raster.rs:185-302) and binned right here, and k_raster walks its scanlines
+      // from that record. Everything else — also anything with a non-finite coordinate — goes to k_setup as a screen triangle.
       bool small = false;
-      uint32_t s_tr0 = 1, s_tr1 = 0, s_ca = 0, s_cb = 0, s_tbase = 0, s_tx = 1, nent = 0;
+      uint32_t s_Y0 = 0, s_n0 = 0, s_n1 = 0, s_tr0 = 1, s_tr1 = 0, s_ca = 0, s_cb = 0, s_tbase = 0, s_tx = 1, nent = 0;
       if (emit && !is_edge && RF_SMALL_ROWS != 0u && P.sdepth == nullptr) {
         float yfirst;
-        uint32_t n0, n1;
-        tri_rows(s[0].y, s[1].y, s[2].y, yfirst, n0, n1);
-        const uint32_t nrows = n0 + n1;
+        tri_rows(s[0].y, s[1].y, s[2].y, yfirst, s_n0, s_n1);
+        const uint32_t nrows = s_n0 + s_n1;
+        if (nrows == 0u) emit = false;  // no pixel-centre row between its vertices: counted above (render.rs:195-196), nothing to draw
         const float xmin = fminf(fminf(s[0].x, s[1].x), s[2].x), xmax = fmaxf(fmaxf(s[0].x, s[1].x), s[2].x);
         const float ylo = fminf(fminf(s[0].y, s[1].y), s[2].y), yhi = fmaxf(fmaxf(s[0].y, s[1].y), s[2].y);
         bool finite = true;
@@ -658,50 +657,41 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
         const TargetDesc& T = P.targets[P.draws[d].target];
         // the running sums of an edge stay within the bounding box up to rounding drift (|sum_j - (x0 + j * dx)| <= j * 2^-24 * max|x|)
         const float margin = 1.0f + (float)nrows * fmaxf(fabsf(xmin), fabsf(xmax)) * 1.2e-7f;
-        if (finite && nrows >= 1u && nrows <= RF_SMALL_ROWS && xmax - xmin <= RF_SMALL_WIDTH && ylo >= 0.0f && yhi + 1.0f < (float)T.h &&
+        if (emit && finite && nrows <= RF_SMALL_ROWS && xmax - xmin <= RF_SMALL_WIDTH && ylo >= 0.0f && yhi + 1.0f < (float)T.h &&
             xmin - margin > 0.0f && xmax + margin < (float)T.w) {
           small = true;
-          const uint32_t Y0 = sat_u32(yfirst);
-          const uint32_t Ya = max(Y0, T.band_y0), Yb = min(Y0 + nrows, T.band_y1);  // only tile rows of this GPU's row band
+          s_Y0 = sat_u32(yfirst);
+          const uint32_t Ya = max(s_Y0, T.band_y0), Yb = min(s_Y0 + nrows, T.band_y1);  // only tile rows of this GPU's row band
           if (Ya < Yb) {
             s_tr0 = Ya >> RF_TILE_SHIFT; s_tr1 = (Yb - 1) >> RF_TILE_SHIFT;
             s_ca = min(sat_u32(floorf(xmin - 0.5f - margin)) >> RF_TILE_SHIFT, T.tiles_x - 1);
             s_cb = min(sat_u32(floorf(xmax + 0.5f + margin)) >> RF_TILE_SHIFT, T.tiles_x - 1);
             s_tbase = T.tile_base; s_tx = T.tiles_x;
             nent = (s_tr1 - s_tr0 + 1) * (s_cb - s_ca + 1);
+          } else {
+            emit = false; small = false;  // sort-first sharding: no scanline in this GPU's row band
           }
         }
       }
-      const uint32_t lmask = __ballot_sync(0xFFFFFFFFu, emit && !small);
+      const uint32_t lmask = __ballot_sync(0xFFFFFFFFu, emit && !small), smask = __ballot_sync(0xFFFFFFFFu, small);
+      if ((lmask | smask) == 0u) continue;
       const uint32_t incl_e = warp_scan_incl(nent, lane), tot_e = __shfl_sync(0xFFFFFFFFu, incl_e, 31);
-      unsigned long long base = 0, lbase = 0, ebase = 0;
+      unsigned long long base = 0, sbase = 0, ebase = 0;
       if (lane == 0) {
-        base = atomicAdd(&P.status->stris_needed, (unsigned long long)__popc(emask));
-        if (lmask) lbase = atomicAdd(&P.status->large_needed, (unsigned long long)__popc(lmask));
+        if (lmask) base = atomicAdd(&P.status->stris_needed, (unsigned long long)__popc(lmask));
+        if (smask) sbase = atomicAdd(&P.status->small_needed, (unsigned long long)__popc(smask));
         if (tot_e) ebase = atomicAdd(&P.status->entries_needed, (unsigned long long)tot_e);
       }
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      lbase = __shfl_sync(0xFFFFFFFFu, lbase, 0);
+      sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
       ebase = __shfl_sync(0xFFFFFFFFu, ebase, 0);
-      if (base + __popc(emask) > P.cap_stris || ebase + tot_e > P.cap_entries) {  // the large list has cap_stris slots
+      if (base + __popc(lmask) > P.cap_stris || sbase + __popc(smask) > P.cap_smalls || ebase + tot_e > P.cap_entries) {
         if (lane == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
         continue;
       }
-      if (emit && !small) P.largelist[(uint32_t)lbase + __popc(lmask & lt)] = (uint32_t)base + __popc(emask & lt);
-      if (nent) {
-        uint32_t eidx = (uint32_t)ebase + (incl_e - nent);
-        const uint32_t ref = ((uint32_t)base + __popc(emask & lt)) | RF_BIN_SMALL, key = gp * 8u + t;
-        for (uint32_t tr = s_tr0; tr <= s_tr1; tr++)
-          for (uint32_t c = s_ca; c <= s_cb; c++) {
-            const uint32_t tile = s_tbase + tr * s_tx + c;
-            P.entries[eidx++] = make_uint4(tile, key, ref, 0u);
-            atomicAdd(P.tile_cnt + tile, 1u);
-          }
-      }
+      const uint32_t emask = lmask;  // screen-triangle records: the LARGE ones only
       uint32_t* const qstg = reinterpret_cast<uint32_t*>(s_q[RF_ASSEMBLE_STAGE ? threadIdx.x >> 5 : 0]);
       if (emit) {
-        uint32_t* q = RF_ASSEMBLE_STAGE ? qstg + __popc(emask & lt) * QW : P.stris + (size_t)((uint32_t)base + __popc(emask & lt)) * QW;
-        if (P.sdepth != nullptr) P.sdepth[(uint32_t)base + __popc(emask & lt)] = (uint32_t)total_key(depth) ^ 0x80000000u;  // unsigned order == total_cmp
         uint32_t w[QW];
         w[0] = gp * 8u + t; w[1] = is_edge ? (d | RF_STRI_LINE) : d;
 #pragma unroll
@@ -712,8 +702,42 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
         }
 #pragma unroll
         for (int i = 2 + 3 * (3 + LT); i < QW; i++) w[i] = 0u;
+        if (small) {
+          using SR = SmallRec<LT>;
+          HalfSetup<LT> H0, H1;
+          float xabs;
+          tri_setup<LT>(w, H0, H1, xabs);
+          const uint32_t sidx = (uint32_t)sbase + __popc(smask & lt);
+          uint32_t* r = P.smalls + (size_t)sidx * SR::W;
+          *reinterpret_cast<uint4*>(r) = make_uint4(w[0], d, s_Y0, s_n0 | s_n1 << 16);
 #pragma unroll
-        for (int qd = 0; qd < QW / 4; qd++) *reinterpret_cast<uint4*>(q + 4 * qd) = make_uint4(w[4 * qd], w[4 * qd + 1], w[4 * qd + 2], w[4 * qd + 3]);
+          for (int hh = 0; hh < 2; hh++) {
+            const HalfSetup<LT>& H = hh ? H1 : H0;
+            uint32_t hw[SR::HW];
+#pragma unroll
+            for (int i = 0; i < SR::HW; i++) hw[i] = 0u;
+#pragma unroll
+            for (int i = 0; i < SR::NV; i++) hw[SR::O_DV + i] = __float_as_uint(H.dv[1 + i]);
+#pragma unroll
+            for (int i = 0; i < SR::NL; i++) { hw[SR::O_L + i] = __float_as_uint(H.L[i]); hw[SR::O_DL + i] = __float_as_uint(H.dl[i]); }
+            hw[SR::O_R] = __float_as_uint(H.R); hw[SR::O_DR] = __float_as_uint(H.dr);
+#pragma unroll
+            for (int qd = 0; qd < SR::HW / 4; qd++) *reinterpret_cast<uint4*>(r + 4 + hh * SR::HW + 4 * qd) = make_uint4(hw[4 * qd], hw[4 * qd + 1], hw[4 * qd + 2], hw[4 * qd + 3]);
+          }
+          // bin entries: every tile of the bounding box (inside this GPU's row band)
+          uint32_t eidx = (uint32_t)ebase + (incl_e - nent);
+          for (uint32_t tr = s_tr0; tr <= s_tr1; tr++)
+            for (uint32_t c = s_ca; c <= s_cb; c++) {
+              const uint32_t tile = s_tbase + tr * s_tx + c;
+              P.entries[eidx++] = make_uint4(tile, w[0], sidx | RF_BIN_SMALL, 0u);
+              atomicAdd(P.tile_cnt + tile, 1u);
+            }
+        } else {
+          uint32_t* q = RF_ASSEMBLE_STAGE ? qstg + __popc(emask & lt) * QW : P.stris + (size_t)((uint32_t)base + __popc(emask & lt)) * QW;
+          if (P.sdepth != nullptr) P.sdepth[(uint32_t)base + __popc(emask & lt)] = (uint32_t)total_key(depth) ^ 0x80000000u;  // unsigned order == total_cmp
+#pragma unroll
+          for (int qd = 0; qd < QW / 4; qd++) *reinterpret_cast<uint4*>(q + 4 * qd) = make_uint4(w[4 * qd], w[4 * qd + 1], w[4 * qd + 2], w[4 * qd + 3]);
+        }
       }
       if (RF_ASSEMBLE_STAGE) {
         __syncwarp();
@@ -774,8 +798,8 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
   __shared__ uint4 s_stage[4][SS::WORDS / 4];  // uint4: 16-byte aligned for the 128-bit accesses
   if (P.cstatus->poison) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
-  // the triangles k_assemble did not bin itself (see RF_BIN_SMALL): tall or wide ones, those near the target's edges, lines
-  const uint32_t NT = (uint32_t)min(P.status->large_needed, (unsigned long long)P.cap_stris);
+  // the triangles k_assemble did not set up and bin itself (see RF_BIN_SMALL): tall or wide ones, those near the target's edges, lines
+  const uint32_t NT = (uint32_t)min(P.status->stris_needed, (unsigned long long)P.cap_stris);
   const uint32_t n_iter = (NT + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
   for (uint32_t it = 0; it < n_iter; it++) {
     const uint32_t ti = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
@@ -793,7 +817,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
     LineMeasure LM{};
     float line_lanes[1 + LT];
     if (have) {
-      const uint32_t* q = P.stris + (size_t)__ldg(P.largelist + ti) * QW;
+      const uint32_t* q = P.stris + (size_t)ti * QW;
       uint32_t w[QW];
 #pragma unroll
       for (int qd = 0; qd < QW / 4; qd++) {

@@ -459,10 +459,9 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
   return 1u;
 }
 
-// Average piece length (pixels) above which a batch of pieces is walked one piece per lane;
-// below it the batch is expanded to one FRAGMENT per lane (each lane does k sequential adds).
-// Measured (scratch/ab.sh): 6 is best at 3 varying lanes (bunny, sprites), 4 at 5 or more (crates: +5.6 %), where a
-// fragment carries more words through the queue.
+// Average piece length (pixels) above which a batch of pieces is walked one piece per lane (span mode);
+// below it the batch is expanded to one FRAGMENT per lane, each lane doing its k sequential adds from the piece start.
+// Measured (scratch/ab.sh): 6 is best at 3 varying lanes (bunny, sprites), 4 at 5 or more (crates: +5.6 %).
 #ifndef RF_SPAN_MODE_MIN_AVG_3
 #define RF_SPAN_MODE_MIN_AVG_3 6u
 #endif
@@ -471,44 +470,37 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
 #endif
 template <int LT> struct RasterTune {
   static constexpr uint32_t MIN_AVG = LT == 3 ? RF_SPAN_MODE_MIN_AVG_3 : RF_SPAN_MODE_MIN_AVG_5;
-  // capacity of the fragment queue: fragment-mode batches hold fewer than MIN_AVG * 32 fragments; the last 8 slots were
-  // traded for the 32 row-coverage words (the few batches of 32 pieces with more fragments than this take span mode)
-  static constexpr uint32_t FRAG_QUEUE = MIN_AVG * 32u - 8u;
 };
 
-// Item queue: the (triangle, row) pieces of one round — every span piece of a group of consecutive triangles of the bin
-// that lies inside this tile — as {meta, z, attr[LT]} at the piece's first pixel. SMALL triangles are set up and walked by
-// their lane right here (no triangle record, no span records, no checkpoints: the three screen vertices are all that was
-// stored for them); the pieces of the other triangles are fetched from the span records k_setup / k_walk wrote.
-//   meta = first column | pixels << 6 | tile row << 12 | half << 17 | triangle lane << 18      (0: no pixel in this tile)
+// Row queue (shared memory, per warp): the edge state {L[2+LT], R} of every scanline of the round's SMALL triangles that
+// lies in this tile, as ScanlineIter::next sees it (raster.rs:84-91) — written by the triangle's lane, which only runs the
+// running sums down both edges (6 dependent adds per row at 3 lanes); rounding to pixel centres, clipping to the tile, the
+// alignment lerp and everything per fragment are done one ROW per lane, with every lane busy.
 #ifndef RF_ROWQ
-#define RF_ROWQ 128u   // capacity in pieces (a multiple of 32, >= RF_TILE: one triangle's rows in a tile always fit)
+#define RF_ROWQ 128u   // capacity in rows (>= RF_TILE: one triangle's rows in a tile always fit)
 #endif
 template <int LT> struct RasterSmem {
-  static constexpr int NV = 1 + LT;
+  static constexpr int NL = 2 + LT;
   static constexpr int TILE_WORDS = RF_TILE * RF_TILE_PITCH;
-  static constexpr int FQ = (int)RasterTune<LT>::FRAG_QUEUE;
   // word offsets inside a warp's region
-  static constexpr int QV0 = TILE_WORDS;           // fragment queue: values [NV][FQ]
-  static constexpr int QP0 = QV0 + NV * FQ;        // fragment queue: pixel index | item lane << 16   [FQ]
-  static constexpr int RC0 = QP0 + FQ;             // row coverage [RF_TILE]
-  static constexpr int IM0 = RC0 + RF_TILE;        // item queue: meta [RF_ROWQ]
-  static constexpr int IV0 = IM0 + (int)RF_ROWQ;   // item queue: values [NV][RF_ROWQ]
-  static constexpr int DV0 = IV0 + NV * (int)RF_ROWQ;  // dv/dx of both halves of the chunk's 32 triangles [32][2][NV]
-  static constexpr int WARP_WORDS = DV0 + 32 * 2 * NV;
+  static constexpr int RC0 = TILE_WORDS;           // row coverage [RF_TILE]
+  static constexpr int IQ0 = RC0 + RF_TILE;        // row queue [NL + 1][RF_ROWQ]
+  static constexpr int WARP_WORDS = IQ0 + (NL + 1) * (int)RF_ROWQ;
   static constexpr size_t BYTES = (size_t)RF_RASTER_WARPS * WARP_WORDS * 4;
 };
 
 #ifndef RF_RASTER_MIN_BLOCKS
-#define RF_RASTER_MIN_BLOCKS 4   // resident blocks per SM at 3 varying lanes (shared memory: 46 KB per block); the persistent grid is this many per SM
+#define RF_RASTER_MIN_BLOCKS 6   // resident blocks per SM at 3 varying lanes; the persistent grid is this many per SM
 #endif
 template <int LT> struct RasterOcc { static constexpr int BLOCKS = LT == 3 ? RF_RASTER_MIN_BLOCKS : (LT == 5 ? 4 : 3); };
 
 template <int LT, bool PEER>
 __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k_raster(PassParams P) {
-  constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW, QW = Rec<LT>::QW, HS = Rec<LT>::HS;
+  constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW, HS = Rec<LT>::HS;
   constexpr int NV = 1 + LT, NL = 2 + LT;
   using RS = RasterSmem<LT>;
+  using SR = SmallRec<LT>;
+  constexpr int WQ = SW > NL + 1 ? SW : NL + 1;  // raw words of a piece: a span record, or a queued edge state
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   extern __shared__ uint32_t s_raster[];
   if (P.cstatus->poison) return;
@@ -520,9 +512,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
   // so passing fragments store their pixel straight to the framebuffer. __syncwarp() between dependency
   // rounds orders two writes to one pixel; untouched pixels are never read or written.
   float* sz = reinterpret_cast<float*>(s_raster + (size_t)warp * RS::WARP_WORDS);
-  const WarpSmem wsm(sz);  // the same region for the per-fragment accesses: depth at [idx], the queues behind it
-  constexpr uint32_t QV0 = RS::QV0, QP0 = RS::QP0, RC0 = RS::RC0, IM0 = RS::IM0, IV0 = RS::IV0, DV0 = RS::DV0;
-  constexpr uint32_t FQ = RasterTune<LT>::FRAG_QUEUE;
+  const WarpSmem wsm(sz);  // the same region for the per-fragment accesses: depth at [idx], coverage and the row queue behind it
+  constexpr uint32_t RC0 = RS::RC0, IQ0 = RS::IQ0;
   // Row coverage [RF_TILE]: bit c of word r = pixel (r, c) is covered by a piece of the current fragment-mode batch. The pieces
   // OR their pixel runs in; popcount(coverage) == number of fragments <=> no two pieces of the batch share a pixel, and the
   // batch's fragment groups need no per-group same-pixel search (MATCH.ANY cost 10 % of this kernel's stall samples).
@@ -531,19 +522,6 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
   // fast-path selectors of the last warp-uniform draw seen (span mode | fragment mode << 4): looked up once per draw, not per batch
   uint32_t mode_draw = 0xFFFFFFFFu, mode_bits = 0;
   const uint32_t n_work = P.status->n_work, n_heaviest = P.status->n_work_heaviest, n_heavy = n_heaviest + P.status->n_work_heavy;
-
-  // per-draw counter update from per-lane partial sums: one atomic per warp when the contributing lanes share a draw
-  auto add_per_draw = [&](uint32_t draw, uint32_t val, bool frags_i) {
-    const uint32_t m = __ballot_sync(FULL, val != 0u);
-    if (m == 0u) return;
-    const uint32_t d0 = __shfl_sync(FULL, draw, __ffs(m) - 1);
-    if (__all_sync(FULL, val == 0u || draw == d0)) {
-      const uint32_t s = __reduce_add_sync(FULL, val);
-      if (lane == 0) atomicAdd(frags_i ? &P.dstats[d0].frags_i : &P.dstats[d0].frags_o, (unsigned long long)s);
-    } else if (val) {
-      atomicAdd(frags_i ? &P.dstats[draw].frags_i : &P.dstats[draw].frags_o, (unsigned long long)val);
-    }
-  };
 
   for (;;) {
     uint32_t wi = 0;
@@ -625,8 +603,16 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
     }
     __syncwarp();
 
-    uint32_t acc_draw = 0xFFFFFFFFu;  // warp-uniform draw id of the pending frags.o partial sums
-    uint32_t acc_o = 0;               // per-lane partial
+    uint32_t acc_draw = 0xFFFFFFFFu;  // warp-uniform draw id of the pending frags.o / frags.i partial sums
+    uint32_t acc_o = 0, acc_i = 0;    // per-lane partials
+    auto flush_acc = [&]() {
+      if (acc_draw != 0xFFFFFFFFu) {
+        const uint32_t so = __reduce_add_sync(FULL, acc_o), si = __reduce_add_sync(FULL, acc_i);
+        if (lane == 0 && so) atomicAdd(&P.dstats[acc_draw].frags_o, (unsigned long long)so);
+        if (lane == 0 && si) atomicAdd(&P.dstats[acc_draw].frags_i, (unsigned long long)si);
+      }
+      acc_o = 0; acc_i = 0;
+    };
 
     for (uint32_t c0 = 0; c0 < cnt && !clear_only; c0 += 32) {
       // ---- lane t: one triangle of this chunk (sorted by submission key)
@@ -635,29 +621,20 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
       nb_tri = c0 + 32 + lane < cnt ? (uint32_t)P.bins[off + c0 + 32 + lane] : 0u;  // next chunk's triangles, one chunk ahead
       const bool t_small = t_have && (t_ref & RF_BIN_SMALL) != 0u;
       const uint32_t t_tri = t_ref & ~RF_BIN_SMALL;
-      uint32_t t_sbase = 0, t_Y0 = 0, t_nU = 0, t_ra = 0, t_rows = 0, t_draw = 0;
+      uint32_t t_sbase = 0, t_Y0 = 0, t_nU = 0, t_nrows = 0, t_ra = 0, t_rows = 0, t_draw = 0;
       if (t_have) {
-        uint32_t nrows;
-        if (t_small) {  // rows from the three y alone; the full setup waits until the triangle's round
-          const uint32_t* q = P.stris + (size_t)t_tri * QW;
-          t_draw = __ldg(q + 1);
-          float yfirst;
-          uint32_t n0, n1;
-          tri_rows(__uint_as_float(__ldg(q + 3)), __uint_as_float(__ldg(q + 3 + (3 + LT))), __uint_as_float(__ldg(q + 3 + 2 * (3 + LT))), yfirst, n0, n1);
-          t_Y0 = sat_u32(yfirst); t_nU = n0; nrows = n0 + n1;
+        if (t_small) {
+          const uint4 h = __ldg(reinterpret_cast<const uint4*>(P.smalls + (size_t)t_tri * SR::W));  // key, draw, Y0, nU | nL << 16
+          t_draw = h.y; t_Y0 = h.z; t_nU = h.w & 0xFFFFu; t_nrows = t_nU + (h.w >> 16);
         } else {
           const uint32_t* tr = P.tris + (size_t)t_tri * TW;
           const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(tr));
           const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(tr + 4));  // nU, nL | target << 16
           t_draw = h0.y; t_sbase = h0.z; t_Y0 = h0.w; t_nU = h1.x;
-          nrows = h1.x + (h1.y & 0xFFFFu);
-#pragma unroll
-          for (int hh = 0; hh < 2; hh++)
-#pragma unroll
-            for (int i = 0; i < NV; i++) wsm.stu(DV0 + (lane * 2u + hh) * NV + i, __ldg(tr + 8 + hh * HS + i));
+          t_nrows = h1.x + (h1.y & 0xFFFFu);
         }
         t_ra = max(t_Y0, py0 + r0);
-        const uint32_t rb = min(t_Y0 + nrows, py0 + r1);
+        const uint32_t rb = min(t_Y0 + t_nrows, py0 + r1);
         t_rows = rb > t_ra ? rb - t_ra : 0u;
         if (RF_RASTER_PREFETCH && t_rows && !t_small) {  // this triangle's span records of the tile's rows: 24-64 bytes each
           const char* sp0 = reinterpret_cast<const char*>(P.spans + (size_t)(t_sbase + (t_ra - t_Y0)) * SW);
@@ -668,168 +645,203 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
       }
       if (RF_RASTER_PREFETCH && c0 + 32 + lane < cnt) {  // the next chunk's records
         const bool nsmall = (nb_tri & RF_BIN_SMALL) != 0u;
-        const char* tp = nsmall ? reinterpret_cast<const char*>(P.stris + (size_t)(nb_tri & ~RF_BIN_SMALL) * QW)
+        const char* tp = nsmall ? reinterpret_cast<const char*>(P.smalls + (size_t)(nb_tri & ~RF_BIN_SMALL) * SR::W)
                                 : reinterpret_cast<const char*>(P.tris + (size_t)nb_tri * TW);
         prefetch_l2(tp);
-        if (!nsmall) prefetch_l2(tp + 128);
+        prefetch_l2(tp + 128);
       }
       const uint32_t t_incl = warp_scan_incl(t_rows, lane);
       const uint32_t n_items = __shfl_sync(FULL, t_incl, 31);
-      const uint32_t large_mask = __ballot_sync(FULL, t_have && !t_small && t_rows != 0u);
+      const uint32_t small_mask = __ballot_sync(FULL, t_small);
+      const uint32_t s_rows = t_small ? t_rows : 0u;
+      const uint32_t s_incl = small_mask ? warp_scan_incl(s_rows, lane) : 0u;  // row-queue slots
 
-      // ---- rounds: consecutive triangles whose pieces fit the item queue (t_incl is non-decreasing, a triangle has at most
-      // RF_TILE <= RF_ROWQ rows in the tile: every round takes at least one triangle whole)
-      uint32_t base = 0, ta = 0;
+      // ---- rounds: consecutive triangles whose SMALL rows fit the row queue (s_incl is non-decreasing, a triangle has at
+      // most RF_TILE <= RF_ROWQ rows in the tile: every round takes at least one triangle whole)
+      uint32_t base = 0, sbase = 0;
       while (base < n_items) {
-        const uint32_t fitm = __ballot_sync(FULL, t_incl <= base + RF_ROWQ);
+        const uint32_t fitm = __ballot_sync(FULL, s_incl <= sbase + RF_ROWQ);
         const uint32_t tb = fitm == FULL ? 32u : (uint32_t)__ffs(~fitm) - 1u;
-        const uint32_t nround = __shfl_sync(FULL, t_incl, tb - 1u) - base;
-        const uint32_t rmask = (tb == 32u ? FULL : (1u << tb) - 1u) & ~((1u << ta) - 1u);
+        const uint32_t round_end = __shfl_sync(FULL, t_incl, tb - 1u);
+        const uint32_t nround = round_end - base;
 
-        // (a) SMALL triangles of the round: tri_fill's setup and ScanlineIter::next for the rows of this tile, by the
-        // triangle's lane — the reference's own sequence of operations (raster.rs:185-302, 80-114), nothing stored in between
-        uint32_t my_fi = 0;
-        if (((rmask >> lane) & 1u) && t_small && t_rows != 0u) {
-          uint32_t w[QW];
-          const uint4* q4 = reinterpret_cast<const uint4*>(P.stris + (size_t)t_tri * QW);
-#pragma unroll
-          for (int qd = 0; qd < QW / 4; qd++) {
-            const uint4 t4 = __ldg(q4 + qd);
-            w[4 * qd] = t4.x; w[4 * qd + 1] = t4.y; w[4 * qd + 2] = t4.z; w[4 * qd + 3] = t4.w;
-          }
-          HalfSetup<LT> H0, H1;
-          float xabs;
-          tri_setup<LT>(w, H0, H1, xabs);
-#pragma unroll
-          for (int i = 0; i < NV; i++) { wsm.stf(DV0 + (lane * 2u) * NV + i, H0.dv[1 + i]); wsm.stf(DV0 + (lane * 2u + 1u) * NV + i, H1.dv[1 + i]); }
-          uint32_t slot = (t_incl - t_rows) - base;
+        // (a) SMALL triangles of the round: the running sums down both edges (ScanlineIter::next, raster.rs:84-91), by the
+        // triangle's lane, from the first row of each half (the two halves start from their own setup) to the last row of this
+        // tile; the state of every row inside the tile is queued
+        if (t_small && s_rows != 0u && s_incl > sbase && s_incl <= sbase + RF_ROWQ) {
+          const uint32_t* rec = P.smalls + (size_t)t_tri * SR::W + 4;
+          uint32_t slot = (s_incl - s_rows) - sbase;
           uint32_t Y = t_Y0;
           const uint32_t Ya = t_ra, Yb = t_ra + t_rows;
-          auto walk = [&](HalfSetup<LT>& H, uint32_t hh) {
-            for (uint32_t j = 0; j < H.n && Y < Yb; j++, Y++) {
-              float v0[NL];
+#pragma unroll 1
+          for (uint32_t hh = 0; hh < 2u; hh++) {
+            const uint32_t n = hh ? t_nrows - t_nU : t_nU;
+            if (Y + n <= Ya) { Y += n; continue; }  // this half lies above the tile: nothing of it is needed
+            if (Y >= Yb) break;
+            constexpr int EWD = 2 * NL + 2;  // L[NL], dl[NL], R, dr
+            uint32_t e[(EWD + 3) & ~3];
+            const uint4* e4 = reinterpret_cast<const uint4*>(rec + hh * SR::HW + SR::O_L);
 #pragma unroll
-              for (int i = 0; i < NL; i++) { v0[i] = H.L[i]; H.L[i] = H.L[i] + H.dl[i]; }
-              const float x1 = H.R;
-              H.R = H.R + H.dr;
-              if (Y < Ya) continue;  // a row above this tile (or slice): only the running sums advance
-              const float x0r = round_up_to_half(v0[0]), x1r = round_up_to_half(x1);
-              const uint32_t cntp = sat_u32(x1r - x0r);
-              const uint32_t X0 = sat_u32(x0r), X1 = max(sat_u32(x1r), X0);
-              uint32_t nn = min(cntp, X1 - X0);
-              if (Y < t_by0 || Y >= t_by1) nn = 0;  // not this GPU's row band
-              const uint32_t xs = max(X0, px0), xe = min(X0 + nn, px0 + tw);
-              uint32_t meta = 0u;
-              if (xe > xs) {
-                const float tx = x0r - v0[0];
-                float vv[NV];
-#pragma unroll
-                for (int i = 0; i < NV; i++) vv[i] = v0[1 + i] + ((v0[1 + i] + H.dv[1 + i]) - v0[1 + i]) * tx;
-                for (uint32_t k = X0; k < xs; k++) {  // the span started in an earlier tile column: the pixels before this one
-#pragma unroll
-                  for (int i = 0; i < NV; i++) vv[i] = vv[i] + H.dv[1 + i];
-                }
-#pragma unroll
-                for (int i = 0; i < NV; i++) wsm.stf(IV0 + i * RF_ROWQ + slot, vv[i]);
-                my_fi += xe - xs;
-                meta = (xs - px0) | (xe - xs) << 6 | (Y - py0) << 12 | hh << 17 | lane << 18;
-              }
-              wsm.stu(IM0 + slot, meta);
-              slot++;
+            for (int q = 0; q < (EWD + 3) / 4; q++) {
+              const uint4 t4 = __ldg(e4 + q);
+              e[4 * q] = t4.x; e[4 * q + 1] = t4.y; e[4 * q + 2] = t4.z; e[4 * q + 3] = t4.w;
             }
-          };
-          walk(H0, 0u);
-          walk(H1, 1u);
-        }
-        add_per_draw(t_draw, my_fi, true);
-
-        // (b) pieces of the other triangles of the round: span records (and checkpoints) from k_setup / k_walk / k_ckpt
-        if (large_mask & rmask) {
-          for (uint32_t s0 = 0; s0 < nround; s0 += 32) {
-            const uint32_t slot = s0 + lane, item = base + slot;
-            const bool ivalid = slot < nround;
-            // owner triangle lane: number of lanes whose inclusive end <= item
-            uint32_t ot = 0;
+            float L[NL], dl[NL];
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-              const uint32_t cand = ot + step;
-              const uint32_t e = __shfl_sync(FULL, t_incl, (cand - 1) & 31);
-              if (cand <= 32 && e <= item) ot = cand;
-            }
-            ot &= 31u;
-            const uint32_t o_incl = __shfl_sync(FULL, t_incl, ot), o_rows = __shfl_sync(FULL, t_rows, ot);
-            const uint32_t o_ra = __shfl_sync(FULL, t_ra, ot), o_Y0 = __shfl_sync(FULL, t_Y0, ot);
-            const uint32_t o_sbase = __shfl_sync(FULL, t_sbase, ot), o_nU = __shfl_sync(FULL, t_nU, ot);
-            const bool o_small = ((__ballot_sync(FULL, t_small) >> ot) & 1u) != 0u;
-            if (ivalid && !o_small) {
-              const uint32_t Y = o_ra + (item - (o_incl - o_rows));
-              const uint32_t j = Y - o_Y0;
-              const uint32_t* sp = P.spans + (size_t)(o_sbase + j) * SW;
-              uint32_t w[SW];
+            for (int i = 0; i < NL; i++) { L[i] = __uint_as_float(e[i]); dl[i] = __uint_as_float(e[NL + i]); }
+            float R = __uint_as_float(e[2 * NL]);
+            const float dr = __uint_as_float(e[2 * NL + 1]);
+            const uint32_t yend = min(Y + n, Yb);
+            for (; Y < yend; Y++) {
+              if (Y >= Ya) {
 #pragma unroll
-              for (int q = 0; q < SW / 2; q++) {
-                const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp) + q);
-                w[2 * q] = t.x; w[2 * q + 1] = t.y;
+                for (int i = 0; i < NL; i++) wsm.stf(IQ0 + i * RF_ROWQ + slot, L[i]);
+                wsm.stf(IQ0 + NL * RF_ROWQ + slot, R);
+                slot++;
               }
-              const uint32_t X0 = w[0] & 0xFFFFu, n = w[0] >> 16;
-              const uint32_t xs = max(X0, px0), xe = min(X0 + n, px0 + tw);
-              uint32_t meta = 0u;
-              if (n != 0u && xs < xe) {
-                if (xs > X0) {  // the span started in an earlier tile column: take the checkpoint at this column
-                  const uint32_t* ck = P.ckpts + (size_t)(w[1] + (tx - (X0 >> RF_TILE_SHIFT) - 1)) * KW;
 #pragma unroll
-                  for (int q = 0; q < KW / 2; q++) {
-                    const uint2 t = __ldg(reinterpret_cast<const uint2*>(ck) + q);
-                    if (2 * q < NV) wsm.stu(IV0 + (2 * q) * RF_ROWQ + slot, t.x);
-                    if (2 * q + 1 < NV) wsm.stu(IV0 + (2 * q + 1) * RF_ROWQ + slot, t.y);
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < NV; i++) wsm.stu(IV0 + i * RF_ROWQ + slot, w[2 + i]);
-                }
-                meta = (xs - px0) | (xe - xs) << 6 | (Y - py0) << 12 | (j >= o_nU ? 1u : 0u) << 17 | ot << 18;
-              }
-              wsm.stu(IM0 + slot, meta);
+              for (int i = 0; i < NL; i++) L[i] = L[i] + dl[i];
+              R = R + dr;
             }
           }
         }
         __syncwarp();
 
-        // (c) the round's pieces, 32 at a time
-        for (uint32_t ib = 0; ib < nround; ib += 32) {
-          const uint32_t slot = ib + lane;
-          const uint32_t meta = slot < nround ? wsm.ldu(IM0 + slot) : 0u;
-          const uint32_t pn = (meta >> 6) & 63u;
-          const bool valid = pn != 0u;
-          const uint32_t pxs = meta & 63u, py = valid ? ((meta >> 12) & 31u) : 32u + lane;
-          const uint32_t draw_o = __shfl_sync(FULL, t_draw, (meta >> 18) & 31u);
-          const uint32_t draw = valid ? draw_o : 0u;
+        // (b) the round's pieces, 32 at a time, one (triangle, row) per lane. Software pipeline: the raw words of batch n+1 (a
+        // queued edge state, or the span record k_setup / k_walk wrote) and its dv/dx are requested before batch n is processed.
+        struct Pre {
+          bool valid, small;
+          uint32_t Y, draw, aux;  // aux: SMALL: unused; otherwise the span's checkpoint base
+          uint32_t w[WQ];
+          uint32_t dvw[NV];
+        };
+        auto fetch = [&](uint32_t ib, Pre& p) {
+          const uint32_t item = base + ib + lane;
+          p.valid = ib + lane < nround;
+          // owner triangle lane: number of lanes whose inclusive end <= item
+          uint32_t ot = 0;
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t cand = ot + step;
+            const uint32_t e = __shfl_sync(FULL, t_incl, (cand - 1) & 31);
+            if (cand <= 32 && e <= item) ot = cand;
+          }
+          ot &= 31u;
+          const uint32_t o_incl = __shfl_sync(FULL, t_incl, ot), o_rows = __shfl_sync(FULL, t_rows, ot);
+          const uint32_t o_ra = __shfl_sync(FULL, t_ra, ot), o_Y0 = __shfl_sync(FULL, t_Y0, ot);
+          const uint32_t o_sbase = __shfl_sync(FULL, t_sbase, ot), o_nU = __shfl_sync(FULL, t_nU, ot);
+          const uint32_t o_tri = __shfl_sync(FULL, t_tri, ot), o_sincl = __shfl_sync(FULL, s_incl, ot);
+          p.draw = __shfl_sync(FULL, t_draw, ot);
+          p.small = ((small_mask >> ot) & 1u) != 0u;
+          p.Y = 0; p.aux = 0;
+          if (p.valid) {
+            const uint32_t rit = item - (o_incl - o_rows);  // row among the triangle's rows in this tile
+            p.Y = o_ra + rit;
+            const uint32_t hh = (p.Y - o_Y0) >= o_nU ? 1u : 0u;
+            if (p.small) {
+              const uint32_t slot = (o_sincl - o_rows) - sbase + rit;
+#pragma unroll
+              for (int i = 0; i < NL + 1; i++) p.w[i] = wsm.ldu(IQ0 + i * RF_ROWQ + slot);
+              const uint32_t* dp = P.smalls + (size_t)o_tri * SR::W + 4 + hh * SR::HW + SR::O_DV;
+              if (SR::O_DV % 4 == 0) {
+#pragma unroll
+                for (int q = 0; q < (NV + 3) / 4; q++) {
+                  const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(dp) + q);
+                  if (4 * q < NV) p.dvw[4 * q] = t4.x;
+                  if (4 * q + 1 < NV) p.dvw[4 * q + 1] = t4.y;
+                  if (4 * q + 2 < NV) p.dvw[4 * q + 2] = t4.z;
+                  if (4 * q + 3 < NV) p.dvw[4 * q + 3] = t4.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < NV; i++) p.dvw[i] = __ldg(dp + i);
+              }
+            } else {
+              const uint32_t* sp = P.spans + (size_t)(o_sbase + (p.Y - o_Y0)) * SW;
+#pragma unroll
+              for (int q = 0; q < SW / 2; q++) {
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp) + q);
+                p.w[2 * q] = t.x; p.w[2 * q + 1] = t.y;
+              }
+              const uint32_t* dp = P.tris + (size_t)o_tri * TW + 8 + hh * HS;
+#pragma unroll
+              for (int i = 0; i < NV; i++) p.dvw[i] = __ldg(dp + i);
+            }
+          }
+        };
+        Pre cur, nxt;
+        fetch(0, cur);
+        for (uint32_t ib = 0; ib < nround; ib += 32, cur = nxt) {
+          nxt.valid = false;
+          if (ib + 32 < nround) fetch(ib + 32, nxt);
+          bool valid = cur.valid;
+          uint32_t py = 32 + lane, pxs = 0, pn = 0, draw = 0;
           float v[NV], dv[NV];
 #pragma unroll
           for (int i = 0; i < NV; i++) { v[i] = 0.0f; dv[i] = 0.0f; }
-          if (valid) {
+          if (valid && cur.small) {
+            // ScanlineIter::next for this row (raster.rs:91-112): round both ends up to pixel centres, align the varyings to the
+            // first centre, clip the span to this tile's columns (a SMALL triangle lies inside the target: no bounds to check)
 #pragma unroll
-            for (int i = 0; i < NV; i++) { v[i] = wsm.ldf(IV0 + i * RF_ROWQ + slot); dv[i] = wsm.ldf(DV0 + ((meta >> 17) & 63u) * NV + i); }
+            for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(cur.dvw[i]);
+            const float v0x = __uint_as_float(cur.w[0]), x1 = __uint_as_float(cur.w[NL]);
+            const float x0r = round_up_to_half(v0x), x1r = round_up_to_half(x1);
+            const uint32_t cntp = sat_u32(x1r - x0r);
+            const uint32_t X0 = sat_u32(x0r), X1 = max(sat_u32(x1r), X0);
+            uint32_t nn = min(cntp, X1 - X0);
+            if (cur.Y < t_by0 || cur.Y >= t_by1) nn = 0;  // not this GPU's row band
+            const uint32_t xs = max(X0, px0), xe = min(X0 + nn, px0 + tw);
+            if (xe > xs) {
+              const float tx_ = x0r - v0x;
+#pragma unroll
+              for (int i = 0; i < NV; i++) { const float a = __uint_as_float(cur.w[1 + i]); v[i] = a + ((a + dv[i]) - a) * tx_; }
+              for (uint32_t k = X0; k < xs; k++) {  // the span started in an earlier tile column: the pixels before this one
+#pragma unroll
+                for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
+              }
+              py = cur.Y - py0; pxs = xs - px0; pn = xe - xs; draw = cur.draw;
+              acc_i += pn;  // frags.i (render/stats.rs): every span pixel, passed or not; the tiles' pieces add up to X1 - X0
+            } else valid = false;
+          } else if (valid) {
+            const uint32_t X0 = cur.w[0] & 0xFFFFu, n = cur.w[0] >> 16;
+            const uint32_t xs = max(X0, px0), xe = min(X0 + n, px0 + tw);
+            if (n == 0 || xs >= xe) valid = false;
+            else {
+              py = cur.Y - py0; pxs = xs - px0; pn = xe - xs; draw = cur.draw;
+              if (xs > X0) {  // the span started in an earlier tile column: take the checkpoint at this column
+                const uint32_t* ck = P.ckpts + (size_t)(cur.w[1] + (tx - (X0 >> RF_TILE_SHIFT) - 1)) * KW;
+#pragma unroll
+                for (int q = 0; q < KW / 2; q++) {
+                  const uint2 t = __ldg(reinterpret_cast<const uint2*>(ck) + q);
+                  if (2 * q < NV) v[2 * q] = __uint_as_float(t.x);
+                  if (2 * q + 1 < NV) v[2 * q + 1] = __uint_as_float(t.y);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < NV; i++) v[i] = __uint_as_float(cur.w[2 + i]);
+              }
+#pragma unroll
+              for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(cur.dvw[i]);
+            }
           }
           const uint32_t vmask = __ballot_sync(FULL, valid);
           if (vmask == 0) continue;
-          // ---- frags.o bookkeeping: flush partial sums when the draw changes
-          const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, draw, __ffs(vmask) - 1);
-          const bool uni = __all_sync(0xFFFFFFFFu, !valid || draw == d0);
+          // ---- frags.o / frags.i bookkeeping: flush the partial sums when the draw changes
+          const uint32_t d0 = __shfl_sync(FULL, draw, __ffs(vmask) - 1);
+          const bool uni = __all_sync(FULL, !valid || draw == d0);
+          uint32_t my_i = 0;
           if (!uni || d0 != acc_draw) {
-            if (acc_draw != 0xFFFFFFFFu) {
-              uint32_t s = acc_o;
-  #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-              if (lane == 0 && s) atomicAdd(&P.dstats[acc_draw].frags_o, (unsigned long long)s);
-            }
-            acc_o = 0;
+            my_i = (valid && cur.small) ? pn : 0u;  // this batch's share, added above, belongs to the new draw(s)
+            acc_i -= my_i;
+            flush_acc();
             acc_draw = uni ? d0 : 0xFFFFFFFFu;
+            if (uni) { acc_i = my_i; my_i = 0; }
           }
+          if (!uni && my_i) atomicAdd(&P.dstats[draw].frags_i, (unsigned long long)my_i);
           uint32_t my_o = 0;
 
           const uint32_t f_incl = warp_scan_incl(pn, lane);
-          const uint32_t n_frags = __shfl_sync(0xFFFFFFFFu, f_incl, 31);
+          const uint32_t n_frags = __shfl_sync(FULL, f_incl, 31);
 
           // warp-uniform fast-path selectors of the batch's draw (0 / 1 = generic)
           uint32_t smode = 0, fmode = uni ? 1u : 0u;
@@ -850,15 +862,15 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
             if (has_depth) { smode = mode_bits & 15u; fmode = mode_bits >> 4; }
           }
 
-          if (n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask) || n_frags > RasterTune<LT>::FRAG_QUEUE) {
+          if (n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask)) {
             // ================= span mode: one piece per lane, walked serially =================
             // dependencies: earlier lanes on the same row whose x-range overlaps mine
             uint32_t dep = 0;
             {
-              uint32_t m = __match_any_sync(0xFFFFFFFFu, py) & lt;
-              while (__any_sync(0xFFFFFFFFu, m != 0)) {
+              uint32_t m = __match_any_sync(FULL, py) & lt;
+              while (__any_sync(FULL, m != 0)) {
                 const int jj = m ? (__ffs(m) - 1) : (int)lane;
-                const uint32_t ox = __shfl_sync(0xFFFFFFFFu, pxs, jj), on = __shfl_sync(0xFFFFFFFFu, pn, jj);
+                const uint32_t ox = __shfl_sync(FULL, pxs, jj), on = __shfl_sync(FULL, pn, jj);
                 if (m) {
                   if (pxs < ox + on && ox < pxs + pn) dep |= 1u << jj;
                   m &= m - 1;
@@ -868,26 +880,26 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
             const DrawDesc& D = P.draws[draw];
             uint32_t done = ~vmask;
             bool pending = valid;
-            while (done != 0xFFFFFFFFu) {
+            while (done != FULL) {
               const bool ready = pending && (dep & ~done) == 0;
               if (ready) {
-                const uint32_t base = py * RF_TILE_PITCH + pxs;
+                const uint32_t pbase = py * RF_TILE_PITCH + pxs;
                 if (smode == 4) {  // default Context + FS_TEX_CLAMP_LIT (crates): straight-line fragment code
                   for (uint32_t k = 0; k < pn; k++) {
-                    my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, gc, t_w, wsm, base + k, v);
-  #pragma unroll
+                    my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, gc, t_w, wsm, pbase + k, v);
+#pragma unroll
                     for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                   }
                 } else if (smode == 2) {
                   for (uint32_t k = 0; k < pn; k++) {
-                    my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, gc, t_w, wsm, base + k, v);
-  #pragma unroll
+                    my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, gc, t_w, wsm, pbase + k, v);
+#pragma unroll
                     for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                   }
                 } else if (LT == 5 && smode == 5) {  // default Context + FS_CHECKER on two perspective uv lanes (the crates floor): z, u, v only
                   for (uint32_t k = 0; k < pn; k++) {
-                    my_o += process_fragment_fixed<LT, RF_FS_CHECKER, 0x3u>(D, t_fmt, gc, t_w, wsm, base + k, v);
-  #pragma unroll
+                    my_o += process_fragment_fixed<LT, RF_FS_CHECKER, 0x3u>(D, t_fmt, gc, t_w, wsm, pbase + k, v);
+#pragma unroll
                     for (int i = 0; i < 3; i++) v[i] = v[i] + dv[i];
                   }
                 } else {
@@ -895,45 +907,31 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                   const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
                   const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
                   for (uint32_t k = 0; k < pn; k++) {
-                    my_o += process_fragment<LT>(D, fs, t_fmt, gc, t_w, wsm, base + k, v, pmask, dtest, cwrite, dwrite);
-  #pragma unroll
+                    my_o += process_fragment<LT>(D, fs, t_fmt, gc, t_w, wsm, pbase + k, v, pmask, dtest, cwrite, dwrite);
+#pragma unroll
                     for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
                   }
                 }
               }
               __syncwarp();
-              done |= __ballot_sync(0xFFFFFFFFu, ready);
+              done |= __ballot_sync(FULL, ready);
               if (ready) pending = false;
             }
             if (uni) acc_o += my_o;
             else if (my_o) atomicAdd(&P.dstats[draw].frags_o, (unsigned long long)my_o);
           } else {
             // ================= fragment mode: one fragment per lane =================
-            // Phase A: every piece lane walks its piece (sequential adds, vary.rs:146-154) and queues one
-            // record per fragment in shared memory; phase B: 32 fragments at a time, one per lane.
-            {
-              const uint32_t qstart = f_incl - pn;
-              uint32_t maxn = pn;
-  #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xFFFFFFFFu, maxn, o));
-              const uint32_t pix0 = py * RF_TILE_PITCH + pxs;
-              if (pn) wsm.oru(RC0 + py, (0xFFFFFFFFu >> (32u - pn)) << pxs);  // this piece's pixels of tile row py
-              for (uint32_t k = 0; k < maxn; k++) {
-                if (k < pn) {
-                  const uint32_t q = qstart + k;
-  #pragma unroll
-                  for (int i = 0; i < NV; i++) { wsm.stf(QV0 + i * RasterTune<LT>::FRAG_QUEUE + q, v[i]); v[i] = v[i] + dv[i]; }
-                  wsm.stu(QP0 + q, (pix0 + k) | lane << 16);
-                }
-              }
-            }
+            // Fragment f of the batch belongs to the piece whose running pixel count covers f; its lane takes the piece's
+            // start values and steps over shuffles and performs the k adds of vary.rs:146-154 that bring them to pixel k.
+            const uint32_t pix0 = py * RF_TILE_PITCH + pxs;
+            if (pn) wsm.oru(RC0 + py, (0xFFFFFFFFu >> (32u - pn)) << pxs);  // this piece's pixels of tile row py
             __syncwarp();
             // distinct pixels covered by the batch (lane r counts tile row r and clears its word for the next batch)
             const uint32_t rcov = wsm.ldu(RC0 + lane);
             wsm.stu(RC0 + lane, 0u);
-            const bool no_overlap = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(rcov)) == n_frags;
-            // Phase B. When the whole batch belongs to one draw (the common case) the draw state is
-            // warp-uniform and hoisted out of the loop; otherwise every fragment looks its draw up.
+            const bool no_overlap = __reduce_add_sync(FULL, (uint32_t)__popc(rcov)) == n_frags;
+            // When the whole batch belongs to one draw (the common case) the draw state is warp-uniform and hoisted out of
+            // the loop; otherwise every fragment looks its draw up.
             auto frag_loop = [&](auto mode_tag) {
               // MODE 0: per-lane draw state; 1: warp-uniform state; 2..4: warp-uniform default state with a fixed shader
               constexpr int MODE = decltype(mode_tag)::value;
@@ -945,28 +943,39 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
               for (uint32_t fb = 0; fb < n_frags; fb += 32) {
                 const uint32_t f = fb + lane;
                 const bool fvalid = f < n_frags;
-                float fv[NV];
-                uint32_t pw = 0;
-                if (fvalid) {
-  #pragma unroll
-                  for (int i = 0; i < NV; i++) fv[i] = wsm.ldf(QV0 + i * RasterTune<LT>::FRAG_QUEUE + f);
-                  pw = wsm.ldu(QP0 + f);
-                } else {
-  #pragma unroll
-                  for (int i = 0; i < NV; i++) fv[i] = 0.0f;
+                // owner piece: number of lanes whose inclusive pixel count <= f
+                uint32_t oi = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                  const uint32_t cand = oi + step;
+                  const uint32_t e = __shfl_sync(FULL, f_incl, (cand - 1) & 31);
+                  if (cand <= 32 && e <= f) oi = cand;
                 }
-                const uint32_t pix = fvalid ? (pw & 0xFFFFu) : (0x10000u + lane);
+                oi &= 31u;
+                const uint32_t o_end = __shfl_sync(FULL, f_incl, oi), o_pn = __shfl_sync(FULL, pn, oi), o_pix = __shfl_sync(FULL, pix0, oi);
+                const uint32_t k = fvalid ? f - (o_end - o_pn) : 0u;
+                float fv[NV], fdv[NV];
+#pragma unroll
+                for (int i = 0; i < NV; i++) { fv[i] = __shfl_sync(FULL, v[i], oi); fdv[i] = __shfl_sync(FULL, dv[i], oi); }
+                const uint32_t maxk = __reduce_max_sync(FULL, k);
+                for (uint32_t kk = 0; kk < maxk; kk++) {
+                  if (kk < k) {
+#pragma unroll
+                    for (int i = 0; i < NV; i++) fv[i] = fv[i] + fdv[i];
+                  }
+                }
+                const uint32_t pix = fvalid ? o_pix + k : (0x10000u + lane);
                 // same pixel, submitted before me: only searched for when two pieces of the batch overlap at all
                 uint32_t earlier = 0;
                 bool clean = true;
                 if (!no_overlap) {
-                  earlier = __match_any_sync(0xFFFFFFFFu, pix) & lt;
-                  clean = __all_sync(0xFFFFFFFFu, earlier == 0);
+                  earlier = __match_any_sync(FULL, pix) & lt;
+                  clean = __all_sync(FULL, earlier == 0);
                 }
                 uint32_t fdraw = d0, pmask = u_pmask, fs = u_fs, dtest = u_dtest;
                 bool cwrite = u_cwrite, dwrite = u_dwrite;
                 if (!UNI) {
-                  fdraw = __shfl_sync(0xFFFFFFFFu, draw, (pw >> 16) & 31u);
+                  fdraw = __shfl_sync(FULL, draw, oi);
                   const DrawDesc& Dl = P.draws[fdraw];
                   const uint32_t flags = Dl.flags;
                   pmask = Dl.persp_mask; fs = Dl.fs;
@@ -983,17 +992,17 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                 };
                 if (clean) {
                   if (fvalid) wrote = one();
-  #if RF_GROUP_SYNC
+#if RF_GROUP_SYNC
                   __syncwarp();  // orders this group's depth/colour writes before the next group's accesses to the same pixels
-  #endif
+#endif
                 } else {
-                  uint32_t done = ~__ballot_sync(0xFFFFFFFFu, fvalid);
+                  uint32_t done = ~__ballot_sync(FULL, fvalid);
                   bool pending = fvalid;
-                  while (done != 0xFFFFFFFFu) {
+                  while (done != FULL) {
                     const bool ready = pending && (earlier & ~done) == 0;
                     if (ready) wrote = one();
                     __syncwarp();
-                    done |= __ballot_sync(0xFFFFFFFFu, ready);
+                    done |= __ballot_sync(FULL, ready);
                     if (ready) pending = false;
                   }
                 }
@@ -1009,17 +1018,12 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
             __syncwarp();
           }
         }
-        __syncwarp();  // the queues are rewritten by the next round
-        base += nround;
-        ta = tb;
+        __syncwarp();  // the row queue is rewritten by the next round
+        base = round_end;
+        sbase = __shfl_sync(FULL, s_incl, tb - 1u);
       }
     }
-    if (acc_draw != 0xFFFFFFFFu) {
-      uint32_t s = acc_o;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-      if (lane == 0 && s) atomicAdd(&P.dstats[acc_draw].frags_o, (unsigned long long)s);
-    }
+    flush_acc();
     __syncwarp();
 
     // ---- write the depth tile back: 128-bit coalesced stores

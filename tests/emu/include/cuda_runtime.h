@@ -333,6 +333,13 @@ inline uint32_t __reduce_add_sync(uint32_t mask, uint32_t v) {  // REDUX.SUM
     return r;
   });
 }
+inline uint32_t __reduce_max_sync(uint32_t mask, uint32_t v) {  // REDUX.MAX
+  return emu::exchange(mask, v, [&](emu::WarpState& w) {
+    uint32_t r = 0;
+    for (unsigned l = 0; l < 32; l++) if ((mask >> l & 1u) && !(w.exited >> l & 1u)) r = std::max(r, (uint32_t)w.buf[l]);
+    return r;
+  });
+}
 template <class T> inline uint32_t __match_any_sync(uint32_t mask, T v) {
   const uint64_t mine = emu::to_bits(v);
   return emu::exchange(mask, v, [&](emu::WarpState& w) {
