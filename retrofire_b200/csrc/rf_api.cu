@@ -103,6 +103,8 @@ struct PassSlot {
   int profiled = 0;
   uint32_t NV = 0, NP = 0, n_tiles = 0, lt = 0;
   uint32_t n_launches = 0;
+  uint32_t seq = 0;          // sequence number of the current launch of this pass
+  cudaEvent_t ev_geo = nullptr;  // geometry + binning of the pass complete (geo stream)
   bool first_touch = false;  // some target of the pass is cleared by k_raster / k_clear_untouched (TargetDesc::clear_flags)
   bool peer = false;         // some target of the pass replicates its colour stores into peer GPUs (rf_peer.cuh)
   bool epochs_set = false;   // barrier epochs are assigned at the first launch and reused by replays
@@ -154,8 +156,17 @@ struct rf_ctx {
   int cur = 0;                 // slot collecting queued draws
   std::vector<int> flight;     // slots launched and not yet validated, oldest first
 
-  // scratch arenas shared by all passes (stream order makes reuse safe)
-  DevBuf cv, sv, stris, smalls, spans, tris, entries, bins, bins2, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
+  // Scratch arenas of a pass, TWO sets: consecutive passes alternate, so that the geometry stage of pass k + 1 (geo stream) can
+  // run next to the rasteriser of pass k (ctx stream); a set is reused once the rasteriser that read it has finished (ev_set_done).
+  struct ArenaSet {
+    DevBuf cv, sv, stris, smalls, spans, tris, entries, bins, bins2, longlist, ckpts, chunks, talllist, ecks, tiles, cursors;
+  } sets[2];
+  cudaEvent_t ev_set_done[2] = {nullptr, nullptr};
+  bool set_busy[2] = {false, false};
+  uint32_t pass_seq = 0;         // sequence number of the last pass launched (device poison compares against it)
+  cudaStream_t geo = nullptr;    // vertex / assembly / setup / span chain of a pass
+  cudaStream_t side2 = nullptr;  // k_clear_untouched next to k_raster
+  cudaEvent_t ev_pre = nullptr;
   // capacities: spans/tris/ckpts in 32-bit WORDS (record width depends on the pass's lane count),
   // entries and long spans in records
   size_t capw_stris = 0, capw_smalls = 0, capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
@@ -214,8 +225,7 @@ struct ArenaWants {  // spans/tris/ckpts/ecks in words, the rest in records
 };
 
 // ---- small utility kernels --------------------------------------------------------------------
-__global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n, const CtxStatus* cs) {
-  if (cs->poison) return;
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n) {
   const size_t n4 = n >> 2;
   uint4* p4 = reinterpret_cast<uint4*>(p);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p4[i] = make_uint4(v, v, v, v);
@@ -278,6 +288,14 @@ void launch_order(rf_ctx* c, PassSlot& s, const PassParams& P, uint32_t QW, cuda
 #ifndef RF_FIRST_TOUCH_CLEAR
 #define RF_FIRST_TOUCH_CLEAR 1
 #endif
+// Blocks of the persistent rasteriser grid per SM. Below the kernel's occupancy limit the SMs keep room (registers, shared
+// memory, issue slots) for the geometry kernels of the NEXT pass, which run concurrently on the geo stream.
+#ifndef RF_RASTER_GRID_PER_SM
+#define RF_RASTER_GRID_PER_SM 0   // 0: the occupancy limit (RasterOcc)
+#endif
+#ifndef RF_ASSEMBLE_THREADS
+#define RF_ASSEMBLE_THREADS 128
+#endif
 #ifndef RF_SETUP_GRID_PER_SM
 #define RF_SETUP_GRID_PER_SM 16
 #endif
@@ -291,7 +309,8 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
   auto blocks = [&](size_t n, int bs, int per_sm) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + bs - 1) / bs, (size_t)sm * per_sm)); };
   const int prof = c->profile;
   s.profiled = prof;
-  const unsigned raster_blocks = sm * RasterOcc<LT>::BLOCKS;
+  const unsigned raster_blocks = sm * (RF_RASTER_GRID_PER_SM && LT == 3 ? RF_RASTER_GRID_PER_SM : RasterOcc<LT>::BLOCKS);
+  constexpr int AT = RF_ASSEMBLE_THREADS;
   const unsigned clear_blocks = blocks((size_t)s.n_tiles * 32, 256, 8);
   if (prof == 2) {  // serialised on one stream, an event between every pair of kernels
     int ek = 0;
@@ -320,27 +339,36 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     }
     mark();
   } else {
-    // two dependent chains after k_setup: spans (main stream) and bins (side stream), joined before k_raster
-    cudaStream_t sd = c->side;
-    if (P.any_bbox) { k_objects<<<blocks(P.n_draws, 128, 8), 128, 0, st>>>(P); s.n_launches++; }
-    k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, st>>>(P);
-    if (P.use_sv) k_assemble<LT, true><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P); else k_assemble<LT, false><<<blocks(s.NP, 128, 16), 128, 0, st>>>(P);
-    if (s.order_upper) launch_order(c, s, P, Rec<LT>::QW, st);
-    k_setup<LT><<<sm * RF_SETUP_GRID_PER_SM, 128, 0, st>>>(P);
-    cudaEventRecord(s.ev_fork, st);
+    // Geometry of the pass on the geo stream — two dependent chains after k_setup, spans (geo) and bins (side), joined at
+    // ev_geo — then the rasteriser on the ctx stream: while it runs, the geo stream already works on the next pass.
+    cudaStream_t gs = c->geo, sd = c->side;
+    if (P.any_bbox) { k_objects<<<blocks(P.n_draws, 128, 8), 128, 0, gs>>>(P); s.n_launches++; }
+    k_vertex<LT><<<blocks(s.NV, 256, 8), 256, 0, gs>>>(P);
+    if (P.use_sv) k_assemble<LT, true><<<blocks(s.NP, AT, 16 * 128 / AT), AT, 0, gs>>>(P); else k_assemble<LT, false><<<blocks(s.NP, AT, 16 * 128 / AT), AT, 0, gs>>>(P);
+    if (s.order_upper) launch_order(c, s, P, Rec<LT>::QW, gs);
+    k_setup<LT><<<sm * RF_SETUP_GRID_PER_SM, 128, 0, gs>>>(P);
+    cudaEventRecord(s.ev_fork, gs);
     cudaStreamWaitEvent(sd, s.ev_fork, 0);
     k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, sd>>>(P);
     k_bin_scatter<<<sm * 4, 256, 0, sd>>>(P);
     k_bin_sort_warp<<<sm * RF_SORT_GRID_PER_SM, RF_SORT_WARPS * 32, 0, sd>>>(P);
     k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, sd>>>(P);
-    // the untouched tiles of first-touch-cleared targets: next to k_raster (disjoint tiles), or — with peers — before the barrier
-    if (s.first_touch && s.peer) k_clear_untouched<<<clear_blocks, 256, 0, sd>>>(P);
     cudaEventRecord(s.ev_join, sd);
-    if (s.first_touch && !s.peer) { k_clear_untouched<<<clear_blocks, 256, 0, sd>>>(P); cudaEventRecord(s.ev_join2, sd); }
-    k_edge_ckpt<LT><<<sm * 4, 128, 0, st>>>(P);
-    k_walk<LT><<<sm * 12, 128, 0, st>>>(P);
-    k_ckpt<LT><<<sm * 8, 256, 0, st>>>(P);
-    cudaStreamWaitEvent(st, s.ev_join, 0);
+    k_edge_ckpt<LT><<<sm * 4, 128, 0, gs>>>(P);
+    k_walk<LT><<<sm * 12, 128, 0, gs>>>(P);
+    k_ckpt<LT><<<sm * 8, 256, 0, gs>>>(P);
+    cudaStreamWaitEvent(gs, s.ev_join, 0);
+    cudaEventRecord(s.ev_geo, gs);
+    cudaStreamWaitEvent(st, s.ev_geo, 0);
+    // the untouched tiles of first-touch-cleared targets: next to k_raster (disjoint tiles; after everything earlier on the ctx
+    // stream, i.e. the previous rasteriser of the same targets), or — with peers — before the barrier
+    if (s.first_touch && s.peer) k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
+    if (s.first_touch && !s.peer) {
+      cudaEventRecord(c->ev_pre, st);
+      cudaStreamWaitEvent(c->side2, c->ev_pre, 0);
+      k_clear_untouched<<<clear_blocks, 256, 0, c->side2>>>(P);
+      cudaEventRecord(s.ev_join2, c->side2);
+    }
     if (s.peer) { k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch1); s.n_launches++; }  // every peer has cleared its copy of the frame
     if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS - 1], st);
     if (s.peer) k_raster<LT, true><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
@@ -354,25 +382,24 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
 
 // Any growth frees memory that in-flight kernels might still use -> callers guarantee idleness.
 rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const ArenaWants& w) {
-  if (!c->cv.reserve(nv * words_cv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "clip-vertex arena");
-  if (!c->sv.reserve(nv * words_sv(lt) * 4 + 64)) return fail(c, RF_E_NOMEM, "screen-vertex arena");
-  if (w.w_stris > c->capw_stris) { if (!c->stris.reserve(w.w_stris * 4)) return fail(c, RF_E_NOMEM, "screen-triangle arena"); c->capw_stris = w.w_stris; }
-  if (w.w_smalls > c->capw_smalls) { if (!c->smalls.reserve(w.w_smalls * 4)) return fail(c, RF_E_NOMEM, "small-triangle arena"); c->capw_smalls = w.w_smalls; }
-  if (w.w_spans > c->capw_spans) { if (!c->spans.reserve(w.w_spans * 4)) return fail(c, RF_E_NOMEM, "span arena"); c->capw_spans = w.w_spans; }
-  if (w.w_tris > c->capw_tris) { if (!c->tris.reserve(w.w_tris * 4)) return fail(c, RF_E_NOMEM, "triangle arena"); c->capw_tris = w.w_tris; }
-  if (w.w_ckpts > c->capw_ckpts) { if (!c->ckpts.reserve(w.w_ckpts * 4)) return fail(c, RF_E_NOMEM, "checkpoint arena"); c->capw_ckpts = w.w_ckpts; }
-  if (w.entries > c->cap_entries) {
-    if (!c->entries.reserve(w.entries * 16) || !c->bins.reserve(w.entries * 8) || !c->bins2.reserve(w.entries * 8)) return fail(c, RF_E_NOMEM, "bin arena");
-    c->cap_entries = w.entries;
+  for (auto& a : c->sets) {
+    bool ok = a.cv.reserve(nv * words_cv(lt) * 4 + 64) && a.sv.reserve(nv * words_sv(lt) * 4 + 64) &&
+              a.tiles.reserve(n_tiles * kTileArrays * 4 + 64) && a.cursors.reserve(64);
+    if (w.w_stris > c->capw_stris) ok = ok && a.stris.reserve(w.w_stris * 4);
+    if (w.w_smalls > c->capw_smalls) ok = ok && a.smalls.reserve(w.w_smalls * 4);
+    if (w.w_spans > c->capw_spans) ok = ok && a.spans.reserve(w.w_spans * 4);
+    if (w.w_tris > c->capw_tris) ok = ok && a.tris.reserve(w.w_tris * 4);
+    if (w.w_ckpts > c->capw_ckpts) ok = ok && a.ckpts.reserve(w.w_ckpts * 4);
+    if (w.entries > c->cap_entries) ok = ok && a.entries.reserve(w.entries * 16) && a.bins.reserve(w.entries * 8) && a.bins2.reserve(w.entries * 8);
+    if (w.longs > c->cap_long) ok = ok && a.longlist.reserve(w.longs * 8);
+    if (w.chunks > c->cap_chunks) ok = ok && a.chunks.reserve(w.chunks * 16) && a.ecks.reserve(w.chunks * Rec<8>::EW * 4);
+    if (w.tall > c->cap_tall) ok = ok && a.talllist.reserve(w.tall * 4);
+    if (!ok) return fail(c, RF_E_NOMEM, "pass arenas");
   }
-  if (w.longs > c->cap_long) { if (!c->longlist.reserve(w.longs * 8)) return fail(c, RF_E_NOMEM, "long-span list"); c->cap_long = w.longs; }
-  if (w.chunks > c->cap_chunks) {
-    if (!c->chunks.reserve(w.chunks * 16) || !c->ecks.reserve(w.chunks * Rec<8>::EW * 4)) return fail(c, RF_E_NOMEM, "chunk list");
-    c->cap_chunks = w.chunks;
-  }
-  if (w.tall > c->cap_tall) { if (!c->talllist.reserve(w.tall * 4)) return fail(c, RF_E_NOMEM, "tall list"); c->cap_tall = w.tall; }
-  if (!c->tiles.reserve(n_tiles * kTileArrays * 4 + 64)) return fail(c, RF_E_NOMEM, "tile arrays");
-  if (!c->cursors.reserve(64)) return fail(c, RF_E_NOMEM, "cursors");
+  c->capw_stris = std::max(c->capw_stris, w.w_stris); c->capw_smalls = std::max(c->capw_smalls, w.w_smalls);
+  c->capw_spans = std::max(c->capw_spans, w.w_spans); c->capw_tris = std::max(c->capw_tris, w.w_tris);
+  c->capw_ckpts = std::max(c->capw_ckpts, w.w_ckpts); c->cap_entries = std::max(c->cap_entries, w.entries);
+  c->cap_long = std::max(c->cap_long, w.longs); c->cap_chunks = std::max(c->cap_chunks, w.chunks); c->cap_tall = std::max(c->cap_tall, w.tall);
   return RF_OK;
 }
 
@@ -382,7 +409,11 @@ bool arenas_cover(const rf_ctx* c, const ArenaWants& w) {
 }
 
 rf_status wait_idle(rf_ctx* c) {
+  RF_CUDA(c, cudaStreamSynchronize(c->geo));
+  RF_CUDA(c, cudaStreamSynchronize(c->side));
   RF_CUDA(c, cudaStreamSynchronize(c->stream));
+  RF_CUDA(c, cudaStreamSynchronize(c->side2));
+  c->set_busy[0] = c->set_busy[1] = false;
   return RF_OK;
 }
 
@@ -428,8 +459,10 @@ rf_status launch_pass(rf_ctx* c, int si) {
                   std::max<size_t>(c->cap_entries, (size_t)1 << 20), std::max<size_t>(c->cap_long, (size_t)1 << 19),
                   std::max<size_t>(c->cap_chunks, (size_t)1 << 20), std::max<size_t>(c->cap_tall, (size_t)1 << 18),
                   std::max<size_t>(c->capw_smalls, (size_t)8 << 20)};
-  need_idle = need_idle || c->cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || c->sv.cap < (size_t)nv * words_sv(lt) * 4 + 64 || c->tiles.cap < (size_t)ntiles * kTileArrays * 4 + 64 ||
-              !arenas_cover(c, want) || c->cursors.cap < 64;
+  for (auto& a : c->sets)
+    need_idle = need_idle || a.cv.cap < (size_t)nv * words_cv(lt) * 4 + 64 || a.sv.cap < (size_t)nv * words_sv(lt) * 4 + 64 ||
+                a.tiles.cap < (size_t)ntiles * kTileArrays * 4 + 64 || a.cursors.cap < 64;
+  need_idle = need_idle || !arenas_cover(c, want);
   // Context::depth_sort: bound on the pass's screen triangles (a clipped triangle fans into <= 7) and the sort buffers
   uint64_t order_bound = 0;
   bool any_sort = false;
@@ -530,38 +563,43 @@ rf_status launch_pass(rf_ctx* c, int si) {
   }
 
   cudaStream_t st = c->stream;
+  // Streams. Everything that touches a TARGET (clears, k_raster, k_clear_untouched) is ordered on the ctx stream; the geometry
+  // of the pass — table / geometry uploads included — runs on the geo stream and only has to wait until the rasteriser that
+  // last read this arena set is done. In the serialised profiling mode everything is on the ctx stream.
+  s.seq = ++c->pass_seq;
+  const int set = (int)(s.seq & 1u);
+  rf_ctx::ArenaSet& A = c->sets[set];
+  cudaStream_t gs = c->profile == 2 ? st : c->geo;
   // a target that is still being downloaded on the copy stream must not be overwritten yet
   for (rf_target* t : s.targets) if (t->dl_pending) { RF_CUDA(c, cudaStreamWaitEvent(st, t->dl_done, 0)); t->dl_pending = false; }
   for (const QueuedClear& qc : s.clears) if (qc.target->dl_pending) { RF_CUDA(c, cudaStreamWaitEvent(st, qc.target->dl_done, 0)); qc.target->dl_pending = false; }
-  RF_CUDA(c, cudaEventRecord(s.ev_start, st));
+  if (c->set_busy[set] && gs != st) RF_CUDA(c, cudaStreamWaitEvent(gs, c->ev_set_done[set], 0));
+  RF_CUDA(c, cudaEventRecord(s.ev_start, gs));
   s.n_launches = 0;
-  RF_CUDA(c, cudaMemcpyAsync(s.d_table.p, tb, coff + ncl * sizeof(ClearDesc), cudaMemcpyHostToDevice, st));
-  if (ncl) {
-    // The clears are only needed by k_raster: with draws in the pass (and not in the serialised profiling mode) they run on
-    // the side stream, concurrently with the latency-bound geometry kernels, and are joined with the binning chain.
-    const bool overlap = nd != 0 && c->profile != 2;
-    cudaStream_t cs = overlap ? c->side : st;
-    if (overlap) {
-      RF_CUDA(c, cudaEventRecord(s.ev_fork, st));        // after the table upload and everything earlier on the ctx stream
-      RF_CUDA(c, cudaStreamWaitEvent(cs, s.ev_fork, 0));
+  RF_CUDA(c, cudaMemcpyAsync(s.d_table.p, tb, coff + ncl * sizeof(ClearDesc), cudaMemcpyHostToDevice, gs));
+  if (ncl || nd == 0) {
+    if (gs != st) { RF_CUDA(c, cudaEventRecord(s.ev_fork, gs)); RF_CUDA(c, cudaStreamWaitEvent(st, s.ev_fork, 0)); }  // the table
+    if (ncl) {
+      const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)c->sm_count * 8 / ncl + 1, 1024));
+      k_clear_multi<<<dim3(gx, (unsigned)ncl), 256, 0, st>>>(reinterpret_cast<const ClearDesc*>(static_cast<uint8_t*>(s.d_table.p) + coff), c->d_cstatus, s.seq);
+      s.n_launches++;
     }
-    const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)c->sm_count * 8 / ncl + 1, 1024));
-    k_clear_multi<<<dim3(gx, (unsigned)ncl), 256, 0, cs>>>(reinterpret_cast<const ClearDesc*>(static_cast<uint8_t*>(s.d_table.p) + coff), c->d_cstatus);
-    s.n_launches++;
   }
   if (nd == 0) {
     RF_CUDA(c, cudaMemsetAsync(s.d_status.p, 0, sizeof(PassStatus), st));
     RF_CUDA(c, cudaMemcpyAsync(&s.h_status->status, s.d_status.p, sizeof(PassStatus), cudaMemcpyDeviceToHost, st));
     RF_CUDA(c, cudaEventRecord(s.ev_stop, st));
+    RF_CUDA(c, cudaEventRecord(c->ev_set_done[set], st));
+    c->set_busy[set] = true;
     s.in_flight = true;
     return RF_OK;
   }
-  if (s.direct_async) RF_CUDA(c, cudaStreamWaitEvent(st, s.ev_direct, 0));  // asynchronous uploads of page-locked geometry
-  if (s.geom_len) RF_CUDA(c, cudaMemcpyAsync(s.d_geom.p, s.geom.p, s.geom_len, cudaMemcpyHostToDevice, st));
-  RF_CUDA(c, cudaMemsetAsync(s.d_status.p, 0, sizeof(PassStatus), st));
-  RF_CUDA(c, cudaMemsetAsync(s.d_dstats.p, 0, std::max<size_t>(nd * sizeof(DrawStats), 16), st));
-  RF_CUDA(c, cudaMemsetAsync(c->tiles.p, 0, (size_t)ntiles * 20, st));
-  RF_CUDA(c, cudaMemsetAsync(c->cursors.p, 0, 64, st));
+  if (s.direct_async) RF_CUDA(c, cudaStreamWaitEvent(gs, s.ev_direct, 0));  // asynchronous uploads of page-locked geometry
+  if (s.geom_len) RF_CUDA(c, cudaMemcpyAsync(s.d_geom.p, s.geom.p, s.geom_len, cudaMemcpyHostToDevice, gs));
+  RF_CUDA(c, cudaMemsetAsync(s.d_status.p, 0, sizeof(PassStatus), gs));
+  RF_CUDA(c, cudaMemsetAsync(s.d_dstats.p, 0, std::max<size_t>(nd * sizeof(DrawStats), 16), gs));
+  RF_CUDA(c, cudaMemsetAsync(A.tiles.p, 0, (size_t)ntiles * 20, gs));
+  RF_CUDA(c, cudaMemsetAsync(A.cursors.p, 0, 64, gs));
 
   PassParams P{};
   uint8_t* dt = static_cast<uint8_t*>(s.d_table.p);
@@ -569,6 +607,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   P.vbase = reinterpret_cast<const uint32_t*>(dt + nd * sizeof(DrawDesc));
   P.pbase = P.vbase + (nd + 1);
   P.targets = reinterpret_cast<const TargetDesc*>(dt + toff);
+  P.seq = s.seq;
   P.n_draws = (uint32_t)nd; P.n_targets = (uint32_t)nt; P.NV = nv; P.NP = np; P.n_tiles = ntiles;
   P.verts_per_draw = nd && uniform_verts ? h_draws[0].n_verts : 0u;  // 0 also when the draws are empty: binary search
   P.prims_per_draw = nd && uniform_prims ? h_draws[0].n_prims : 0u;
@@ -576,36 +615,36 @@ rf_status launch_pass(rf_ctx* c, int si) {
   for (auto& q : s.draws) if (q.desc.flags & RF_F_BBOX) P.any_bbox = 1;
   P.use_sv = 1;
   for (auto& q : s.draws) if (!(q.desc.flags & RF_F_SV)) P.use_sv = 0;
-  P.cv = static_cast<float*>(c->cv.p);
-  P.sv = static_cast<float*>(c->sv.p);
-  P.stris = static_cast<uint32_t*>(c->stris.p);
+  P.cv = static_cast<float*>(A.cv.p);
+  P.sv = static_cast<float*>(A.sv.p);
+  P.stris = static_cast<uint32_t*>(A.stris.p);
   P.cap_stris = (uint32_t)std::min<size_t>(c->capw_stris / words_stri(lt), 0x1FFFFFF0u);
-  P.smalls = static_cast<uint32_t*>(c->smalls.p);
+  P.smalls = static_cast<uint32_t*>(A.smalls.p);
   P.cap_smalls = (uint32_t)std::min<size_t>(c->capw_smalls / words_small(lt), 0x7FFFFFF0u);
   P.sdepth = s.order_upper ? static_cast<uint32_t*>(c->sdepth.p) : nullptr;
-  P.spans = static_cast<uint32_t*>(c->spans.p);
-  P.tris = static_cast<uint32_t*>(c->tris.p);
-  P.entries = static_cast<uint4*>(c->entries.p);
-  P.bins = static_cast<unsigned long long*>(c->bins.p);
-  P.bins2 = static_cast<unsigned long long*>(c->bins2.p);
-  P.longlist = static_cast<uint2*>(c->longlist.p);
-  P.ckpts = static_cast<uint32_t*>(c->ckpts.p);
+  P.spans = static_cast<uint32_t*>(A.spans.p);
+  P.tris = static_cast<uint32_t*>(A.tris.p);
+  P.entries = static_cast<uint4*>(A.entries.p);
+  P.bins = static_cast<unsigned long long*>(A.bins.p);
+  P.bins2 = static_cast<unsigned long long*>(A.bins2.p);
+  P.longlist = static_cast<uint2*>(A.longlist.p);
+  P.ckpts = static_cast<uint32_t*>(A.ckpts.p);
   // capacities in records of THIS pass's width
   P.cap_spans = (uint32_t)std::min<size_t>(c->capw_spans / words_span(lt), 0xFFFFFFF0u);
   P.cap_tris = (uint32_t)std::min<size_t>(c->capw_tris / words_tri(lt), 0x7FFFFFF0u);
   P.cap_ckpts = (uint32_t)std::min<size_t>(c->capw_ckpts / words_ckpt(lt), 0xFFFFFFF0u);
   P.cap_entries = (uint32_t)std::min<size_t>(c->cap_entries, 0xFFFFFFF0u);
   P.cap_long = (uint32_t)std::min<size_t>(c->cap_long, 0xFFFFFFF0u);
-  P.chunks = static_cast<uint4*>(c->chunks.p);
-  P.talllist = static_cast<uint32_t*>(c->talllist.p);
-  P.ecks = static_cast<uint32_t*>(c->ecks.p);
+  P.chunks = static_cast<uint4*>(A.chunks.p);
+  P.talllist = static_cast<uint32_t*>(A.talllist.p);
+  P.ecks = static_cast<uint32_t*>(A.ecks.p);
   P.cap_chunks = (uint32_t)std::min<size_t>(c->cap_chunks, 0xFFFFFFF0u);
   P.cap_tall = (uint32_t)std::min<size_t>(c->cap_tall, 0xFFFFFFF0u);
   P.cap_ecks = P.cap_chunks;
-  uint32_t* ta = static_cast<uint32_t*>(c->tiles.p);
+  uint32_t* ta = static_cast<uint32_t*>(A.tiles.p);
   P.tile_cnt = ta; P.tile_off = ta + ntiles; P.tile_fill = ta + 2 * (size_t)ntiles;
   P.worklist = ta + 3 * (size_t)ntiles; P.worklist_big = ta + 4 * (size_t)ntiles; P.worklist_heavy = ta + 5 * (size_t)ntiles;
-  P.cursors = static_cast<uint32_t*>(c->cursors.p);
+  P.cursors = static_cast<uint32_t*>(A.cursors.p);
   P.dstats = static_cast<DrawStats*>(s.d_dstats.p);
   P.status = static_cast<PassStatus*>(s.d_status.p);
   P.cstatus = c->d_cstatus;
@@ -618,6 +657,8 @@ rf_status launch_pass(rf_ctx* c, int si) {
   RF_CUDA(c, cudaMemcpyAsync(&s.h_status->status, s.d_status.p, sizeof(PassStatus), cudaMemcpyDeviceToHost, st));
   if (nd) RF_CUDA(c, cudaMemcpyAsync(s.h_dstats.p, s.d_dstats.p, nd * sizeof(DrawStats), cudaMemcpyDeviceToHost, st));
   RF_CUDA(c, cudaEventRecord(s.ev_stop, st));
+  RF_CUDA(c, cudaEventRecord(c->ev_set_done[set], st));
+  c->set_busy[set] = true;
   s.in_flight = true;
   return RF_OK;
 }
@@ -658,7 +699,8 @@ rf_status validate_all(rf_ctx* c) {
                    grow(c->cap_long, std::max<unsigned long long>(ps.long_needed, early ? ps.spans_needed / 8 : 0)),
                    grow(c->cap_chunks, ps.chunks_needed), grow(c->cap_tall, ps.tall_needed), grow(c->capw_smalls, ps.small_needed * words_small(lt))};
       { rf_status st = ensure_arenas(c, lt, s.NV, s.n_tiles, w); if (st) return st; }
-      RF_CUDA(c, cudaMemsetAsync(c->d_cstatus, 0, sizeof(CtxStatus), c->stream));
+      RF_CUDA(c, cudaMemsetAsync(c->d_cstatus, 0xFF, sizeof(CtxStatus), c->stream));
+      RF_CUDA(c, cudaStreamSynchronize(c->stream));
       std::vector<int> replay = c->flight;
       c->replays += replay.size();
       for (int r : replay) { rf_status st = launch_pass(c, r); if (st) return st; }
@@ -872,15 +914,19 @@ rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
     c->own_stream = true;
   }
   if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->geo, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_set_done[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_set_done[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) { rf_ctx_destroy(c); return RF_E_CUDA; }
-  bool ok = cudaMalloc(&c->d_cstatus, sizeof(CtxStatus)) == cudaSuccess && cudaMemset(c->d_cstatus, 0, sizeof(CtxStatus)) == cudaSuccess;
+  bool ok = cudaMalloc(&c->d_cstatus, sizeof(CtxStatus)) == cudaSuccess && cudaMemset(c->d_cstatus, 0xFF, sizeof(CtxStatus)) == cudaSuccess;  // RF_NO_POISON
   for (int k = 0; k < kSlots && ok; k++) {
     PassSlot& s = c->slots[k];
     ok = ok && cudaEventCreate(&s.ev_start) == cudaSuccess && cudaEventCreate(&s.ev_stop) == cudaSuccess;
     for (int e = 0; e <= RF_N_KERNELS && ok; e++) ok = cudaEventCreate(&s.ev_k[e]) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&s.ev_join2, cudaEventDisableTiming) == cudaSuccess;
+         cudaEventCreateWithFlags(&s.ev_join2, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s.ev_geo, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_status), sizeof(HostStatus), cudaHostAllocDefault) == cudaSuccess;
   }
   ok = ok && cudaFuncSetAttribute(k_bin_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SORT_BIG * 8) == cudaSuccess;
@@ -898,7 +944,10 @@ rf_status rf_ctx_create(int device, void* stream, rf_ctx** out) {
 void rf_ctx_destroy(rf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->geo) cudaStreamSynchronize(c->geo);
+  if (c->side) cudaStreamSynchronize(c->side);
   cudaStreamSynchronize(c->stream);
+  if (c->side2) cudaStreamSynchronize(c->side2);
   for (int k = 0; k < kSlots; k++) {
     PassSlot& s = c->slots[k];
     if (s.ev_direct) cudaEventDestroy(s.ev_direct);
@@ -911,9 +960,17 @@ void rf_ctx_destroy(rf_ctx* c) {
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
     if (s.ev_join2) cudaEventDestroy(s.ev_join2);
+    if (s.ev_geo) cudaEventDestroy(s.ev_geo);
   }
-  c->cv.release(); c->sv.release(); c->stris.release(); c->smalls.release(); c->spans.release(); c->tris.release(); c->entries.release(); c->bins.release(); c->bins2.release(); c->longlist.release(); c->ckpts.release(); c->chunks.release(); c->talllist.release(); c->ecks.release();
-  c->tiles.release(); c->cursors.release(); c->bounce.release(); c->h_bounce.release();
+  for (auto& a : c->sets) {
+    a.cv.release(); a.sv.release(); a.stris.release(); a.smalls.release(); a.spans.release(); a.tris.release(); a.entries.release(); a.bins.release(); a.bins2.release();
+    a.longlist.release(); a.ckpts.release(); a.chunks.release(); a.talllist.release(); a.ecks.release(); a.tiles.release(); a.cursors.release();
+  }
+  c->bounce.release(); c->h_bounce.release();
+  for (int k = 0; k < 2; k++) if (c->ev_set_done[k]) cudaEventDestroy(c->ev_set_done[k]);
+  if (c->ev_pre) cudaEventDestroy(c->ev_pre);
+  if (c->geo) cudaStreamDestroy(c->geo);
+  if (c->side2) cudaStreamDestroy(c->side2);
   for (uint32_t r = 0; r < c->pb.world; r++) if (r != c->pb.self && c->pb_ipc[r]) cudaIpcCloseMemHandle(c->pb.flags[r]);
   c->peer_flags.release();
   c->sdepth.release(); c->ord_tmp.release();

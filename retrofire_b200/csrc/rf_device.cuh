@@ -108,7 +108,10 @@ struct PassStatus {
   uint32_t _pad;
 };
 
-// persistent across passes: once set, every later pass is a no-op until the host clears it
+// Persistent across passes: the sequence number of the first pass that exceeded an arena capacity (RF_NO_POISON: none). That
+// pass and every later one are no-ops until the host has grown the arenas and replayed them in order; EARLIER passes still
+// in flight (the rasteriser of pass k runs next to the geometry stage of pass k + 1) are not disturbed.
+#define RF_NO_POISON 0xFFFFFFFFu
 struct CtxStatus {
   uint32_t poison;
 };
@@ -126,6 +129,7 @@ struct PassParams {
   const uint32_t* pbase;  // [n_draws+1] prefix of n_prims
   const TargetDesc* targets;
   uint32_t n_draws, n_targets, NV, NP, n_tiles;
+  uint32_t seq;           // pass sequence number (see CtxStatus)
   uint32_t use_sv;        // every draw of the pass has RF_F_SV: k_vertex stores screen-space vertices, k_assemble<LT, true> reads them
   uint32_t any_bbox;      // some draw of the pass carries RF_F_BBOX (k_objects ran)
   uint32_t tiles_per_target;  // every target of the pass has this many tiles (tile / it = target index), or 0 when they differ
@@ -160,6 +164,9 @@ struct PassParams {
   PassStatus* status;
   CtxStatus* cstatus;
 };
+
+__device__ __forceinline__ bool rf_poisoned(const PassParams& P) { return P.cstatus->poison <= P.seq; }
+__device__ __forceinline__ void rf_overflow(const PassParams& P) { P.status->overflow = 1; atomicMin(&P.cstatus->poison, P.seq); }
 
 #define RF_NO_CKPT 0xFFFFFFFFu
 #define RF_STRI_LINE 0x80000000u  // flag in the draw word of a screen-triangle record: the record is an Edge (2 vertices)

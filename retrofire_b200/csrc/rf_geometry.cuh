@@ -15,7 +15,7 @@
 // (ProjMat3::apply, mat.rs:968-972), get their outcodes (ClipVert::new, clip.rs:180-190) and the box is Hidden when all
 // corners are outside one plane (view_frustum::status, clip.rs:245-267). A hidden draw is skipped by k_vertex/k_assemble.
 __global__ void __launch_bounds__(128) k_objects(PassParams P) {
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < P.n_draws; d += gridDim.x * blockDim.x) {
     const DrawDesc& D = P.draws[d];
     if (!(D.flags & RF_F_BBOX)) continue;
@@ -124,7 +124,7 @@ __device__ __forceinline__ void to_screen(const CVert<LT>& c, const float* __res
 template <int LT>
 __global__ void __launch_bounds__(256) k_vertex(PassParams P) {
   constexpr int CVS = Rec<LT>::CVS;
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   for (uint32_t gv = blockIdx.x * blockDim.x + threadIdx.x; gv < P.NV; gv += gridDim.x * blockDim.x) {
     const uint32_t d = find_draw(P.vbase, P.n_draws, gv, P.verts_per_draw);
     if (P.any_bbox && P.dstats[d].hidden) continue;  // object culled: its clip vertices are never read
@@ -464,7 +464,7 @@ __device__ __forceinline__ void line_walk(const PassParams& P, const TargetDesc&
       if (nn && ((run_x0 + nn - 1) >> RF_TILE_SHIFT) != (run_x0 >> RF_TILE_SHIFT)) {
         const unsigned long long slot = agg_atomic_inc(&P.status->long_needed, lane);
         if (slot < P.cap_long) P.longlist[slot] = make_uint2(sidx, tri_idx * 2u);
-        else { P.status->overflow = 1; P.cstatus->poison = 1; }
+        else rf_overflow(P);
       }
     }
     run_n = 0;
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
   constexpr int QW = Rec<LT>::QW;
   // record stride QW = 20 / 28 / 36 words: the 128-bit accesses of 8 consecutive lanes fall into 8 different bank groups
   __shared__ uint4 s_q[RF_ASSEMBLE_STAGE ? 4 : 1][RF_ASSEMBLE_STAGE ? 32 * QW / 4 : 1];
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t n_iter = (P.NP + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
   for (uint32_t it = 0; it < n_iter; it++) {
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
       sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
       ebase = __shfl_sync(0xFFFFFFFFu, ebase, 0);
       if (base + __popc(lmask) > P.cap_stris || sbase + __popc(smask) > P.cap_smalls || ebase + tot_e > P.cap_entries) {
-        if (lane == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
+        if (lane == 0) rf_overflow(P);
         continue;
       }
       const uint32_t emask = lmask;  // screen-triangle records: the LARGE ones only
@@ -796,7 +796,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
   __shared__ uint32_t s_fit[4];
   using SS = SetupStage<LT>;
   __shared__ uint4 s_stage[4][SS::WORDS / 4];  // uint4: 16-byte aligned for the 128-bit accesses
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   // the triangles k_assemble did not set up and bin itself (see RF_BIN_SMALL): tall or wide ones, those near the target's edges, lines
   const uint32_t NT = (uint32_t)min(P.status->stris_needed, (unsigned long long)P.cap_stris);
@@ -936,7 +936,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
     for (uint32_t w = 0; w < wid; w++) { sb += s_tot[w][0]; tb += s_tot[w][1]; eb += s_tot[w][2]; cb_ += s_tot[w][3]; }
     __syncthreads();  // s_tot / s_base are reused by the next iteration
     if (!fits) {
-      if (threadIdx.x == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
+      if (threadIdx.x == 0) rf_overflow(P);
       continue;  // keep counting what is needed, write nothing
     }
     const uint32_t sbase = (uint32_t)sb + (incl_s - nsp);  // defined on every lane (nsp = 0 where nothing is emitted)
@@ -1004,8 +1004,8 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
         P.chunks[cidx++] = make_uint4(tri_idx * 2u, c | min(RF_CHUNK, H0.n - c * RF_CHUNK) << 16, sbase + c * RF_CHUNK, d | tgt << 16);
       for (uint32_t c = 0; c < ch1; c++)
         P.chunks[cidx++] = make_uint4(tri_idx * 2u + 1u, c | min(RF_CHUNK, H1.n - c * RF_CHUNK) << 16, sbase + H0.n + c * RF_CHUNK, d | tgt << 16);
-      if (ch0 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed, lane); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
-      if (ch1 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed, lane); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u + 1u; else { P.status->overflow = 1; P.cstatus->poison = 1; } }
+      if (ch0 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed, lane); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u; else rf_overflow(P); }
+      if (ch1 > 1) { const unsigned long long sl = agg_atomic_inc(&P.status->tall_needed, lane); if (sl < P.cap_tall) P.talllist[sl] = tri_idx * 2u + 1u; else rf_overflow(P); }
     }
     // few rows: walk them here, serially (sequential adds down both edges). The span records go to the staging buffer at
     // the lane's offset among the warp's inline-walked rows (or straight to P.spans).
@@ -1062,7 +1062,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
             m &= m - 1;
             P.longlist[slot++] = make_uint2(long_sbase + r, long_tri * 2u + (r >= long_nU ? 1u : 0u));
           }
-        } else if (lane == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
+        } else if (lane == 0) rf_overflow(P);
       }
     }
     // ---- per-draw frags.i of the inline walks
@@ -1091,7 +1091,7 @@ __global__ void __launch_bounds__(128) k_edge_ckpt(PassParams P) {
   constexpr int NL = 2 + LT;
   constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS, EW = Rec<LT>::EW;
   using TR = TriRec<LT>;
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t nt = (uint32_t)min(P.status->tall_needed, (unsigned long long)P.cap_tall);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) {
     const uint32_t own = P.talllist[i];
@@ -1135,7 +1135,7 @@ __global__ void __launch_bounds__(128) k_walk(PassParams P) {
   constexpr int NL = 2 + LT;
   constexpr int TW = Rec<LT>::TW, HS = Rec<LT>::HS, EW = Rec<LT>::EW, SW = Rec<LT>::SW;
   using TR = TriRec<LT>;
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t nch = (uint32_t)min(P.status->chunks_needed, (unsigned long long)P.cap_chunks);
   const uint32_t wpb = blockDim.x >> 5;
@@ -1281,7 +1281,7 @@ __global__ void __launch_bounds__(128) k_walk(PassParams P) {
               __syncwarp();
               ll_next = base; ll_end = base + RF_LONG_BLOCK;
             } else {
-              if (lane == 0) { P.status->overflow = 1; P.cstatus->poison = 1; }
+              if (lane == 0) rf_overflow(P);
               ll_next = ll_end = 0;
             }
           }

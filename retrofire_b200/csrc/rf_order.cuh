@@ -15,7 +15,7 @@
 #include "rf_device.cuh"
 
 __global__ void __launch_bounds__(256) k_order_init(PassParams P, uint32_t QW, uint32_t upper, uint32_t* __restrict__ k32, uint32_t* __restrict__ vals) {
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t n = (uint32_t)min(P.status->stris_needed.v, (unsigned long long)P.cap_stris);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < upper; i += gridDim.x * blockDim.x) {
     const bool live = i < n;
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) k_order_init(PassParams P, uint32_t QW, u
 }
 
 __global__ void __launch_bounds__(256) k_order_keys(PassParams P, uint32_t QW, uint32_t upper, const uint32_t* __restrict__ vals, unsigned long long* __restrict__ k64) {
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < upper; i += gridDim.x * blockDim.x) {
     const uint32_t v = vals[i];
     unsigned long long k = ~0ull;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_order_keys(PassParams P, uint32_t QW, u
 }
 
 __global__ void __launch_bounds__(256) k_order_apply(PassParams P, uint32_t QW, uint32_t upper, const uint32_t* __restrict__ vals) {
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < upper; r += gridDim.x * blockDim.x) {
     const uint32_t v = vals[r];
     if (v != 0xFFFFFFFFu) P.stris[(size_t)v * QW] = r;

@@ -22,7 +22,7 @@
 #define RF_SLICES 4u          // row slices of a heaviest tile (RF_TILE / RF_SLICES rows each); task word = tile | (slice+1) << 28
 
 __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t n_iter = (P.n_tiles + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
   for (uint32_t it = 0; it < n_iter; it++) {
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k_bin_alloc(PassParams P) {
 // K4: scatter the (triangle x tile) entries written by k_prim into the tile bins.
 // =============================================================================================
 __global__ void __launch_bounds__(256) k_bin_scatter(PassParams P) {
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t ne = (uint32_t)min(P.status->entries_needed, (unsigned long long)P.cap_entries);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += gridDim.x * blockDim.x) {
     const uint4 e = __ldg(P.entries + i);
@@ -89,7 +89,7 @@ template <int LT>
 __global__ void __launch_bounds__(256) k_ckpt(PassParams P) {
   constexpr int SW = Rec<LT>::SW, TW = Rec<LT>::TW, KW = Rec<LT>::KW;
   constexpr int NV = 1 + LT;
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t nl = (uint32_t)min(P.status->long_needed, (unsigned long long)P.cap_long);
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t n_iter = (nl + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_ckpt(PassParams P) {
     if (lane == 0 && total) base = atomicAdd(&P.status->ckpts_needed, (unsigned long long)total);
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (base + total > P.cap_ckpts) {
-      if (lane == 0 && total) { P.status->overflow = 1; P.cstatus->poison = 1; }
+      if (lane == 0 && total) rf_overflow(P);
       continue;
     }
     if (!have || nck == 0) continue;
@@ -158,7 +158,7 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 #define RF_SORT_WARPS 4
 __global__ void __launch_bounds__(RF_SORT_WARPS * 32) k_bin_sort_warp(PassParams P) {
   __shared__ unsigned long long sk_all[RF_SORT_WARPS][RF_SORT_SMALL];
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u, warp = threadIdx.x >> 5;
   unsigned long long* sk = sk_all[warp];
   const uint32_t n_work = P.status->n_work;
@@ -225,7 +225,7 @@ __device__ __forceinline__ void block_bitonic(unsigned long long* sk, uint32_t n
 // (every element finds its output slot by binary search in the other run), so there is no depth limit.
 __global__ void __launch_bounds__(256) k_bin_sort_big(PassParams P) {
   extern __shared__ unsigned long long skb[];
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t n_work = P.status->n_work_big;
   for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
     const uint32_t tile = P.worklist_big[wi];
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
   constexpr int WQ = SW > NL + 1 ? SW : NL + 1;  // raw words of a piece: a span record, or a queued edge state
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   extern __shared__ uint32_t s_raster[];
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   // A pass with a device-detected error (every check runs before this kernel) rasterises nothing, but the clears recorded
   // at its head still happen: the tiles this kernel would have touched are initialised and written back, nothing else.
   const bool clear_only = P.status->error != 0u;
@@ -1072,8 +1072,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
 // Frame::clear (front/src/lib.rs:103-120) for every target cleared at the head of a pass, in one
 // launch: blockIdx.y selects the buffer, 128-bit stores.
 // =============================================================================================
-__global__ void __launch_bounds__(256) k_clear_multi(const ClearDesc* __restrict__ cl, const CtxStatus* cs) {
-  if (cs->poison) return;
+__global__ void __launch_bounds__(256) k_clear_multi(const ClearDesc* __restrict__ cl, const CtxStatus* cs, uint32_t seq) {
+  if (cs->poison <= seq) return;
   const ClearDesc c = cl[blockIdx.y];
   // scalar head up to 16-byte alignment (a row band may start at any row of an odd-width target), 128-bit body, scalar tail
   const size_t head = min((size_t)c.n, (size_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(c.ptr) & 15u)) & 15u) >> 2);
@@ -1094,7 +1094,7 @@ __global__ void __launch_bounds__(256) k_clear_multi(const ClearDesc* __restrict
 // write disjoint tiles. Under sort-first sharding only the rows of this GPU's band are cleared.
 // =============================================================================================
 __global__ void __launch_bounds__(256) k_clear_untouched(PassParams P) {
-  if (P.cstatus->poison) return;
+  if (rf_poisoned(P)) return;
   const uint32_t lane = lane_id();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t tile = gw; tile < P.n_tiles; tile += nw) {
