@@ -10,6 +10,11 @@
 
 #include "../../include/retrofire_b200.h"
 
+// Inline PTX (laneid aside) can be switched off: the SIMT emulation of tests/emu compiles the C++ equivalents instead.
+#ifndef RF_SMEM_ASM
+#define RF_SMEM_ASM 1
+#endif
+
 #define RF_TILE 32          // framebuffer tile: RF_TILE rows x RF_TILE columns, one warp owns one tile
 #define RF_TILE_SHIFT 5
 #define RF_TILE_PITCH 33    // smem row pitch in words (bank = (row + col) % 32)
@@ -206,7 +211,16 @@ template <int LT> struct SmallRec {
 // ---- Rust `as` casts (saturating, NaN -> 0). PTX cvt.rzi.{u32,s32}.f32 clamps and maps NaN to 0.
 __device__ __forceinline__ uint32_t sat_u32(float f) { return __float2uint_rz(f); }
 __device__ __forceinline__ int32_t sat_i32(float f) { return __float2int_rz(f); }
-__device__ __forceinline__ uint32_t sat_u8(float f) { return min(__float2uint_rz(f), 255u); }
+// `f as u8` (color.rs:253-263): truncate, clamp to 0..255, NaN -> 0 — one F2I.U8 instead of F2I.U32 + IMNMX
+__device__ __forceinline__ uint32_t sat_u8(float f) {
+#if RF_SMEM_ASM
+  uint32_t r;
+  asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(f));
+  return r;
+#else
+  return min(__float2uint_rz(f), 255u);
+#endif
+}
 
 // math/vec.rs:231-238: left fold from 0.0
 __device__ __forceinline__ float dot4(float a0, float a1, float a2, float a3, float b0, float b1, float b2, float b3) {
@@ -267,6 +281,23 @@ __device__ __forceinline__ uint32_t pack_pixel(uint32_t fmt, uint32_t r, uint32_
     case RF_FMT_RGB565: return ((r >> 3) & 0x1Fu) << 11 | ((g >> 2) & 0x3Fu) << 5 | ((b >> 3) & 0x1Fu);
     default: return (r >> 4) << 12 | (g >> 4) << 8 | (b >> 4) << 4 | (a >> 4);  // RGBA4444
   }
+}
+
+// The four 8888 layouts and RGB888 are byte permutations of r | g << 8 | b << 16 | a << 24: one PRMT with a per-target
+// selector (0: not such a format, use pack_pixel). Index 4 selects a zero byte from the second PRMT operand.
+__host__ __device__ __forceinline__ uint32_t pack_selector(uint32_t fmt) {
+  switch (fmt) {
+    case RF_FMT_RGBA8888: return 0x3210u;
+    case RF_FMT_XRGB8888: return 0x4012u;
+    case RF_FMT_ARGB8888: return 0x2103u;
+    case RF_FMT_BGRA8888: return 0x3012u;
+    case RF_FMT_RGB888: return 0x4210u;
+    default: return 0u;
+  }
+}
+__device__ __forceinline__ uint32_t pack_pixel_sel(uint32_t sel, uint32_t fmt, uint32_t r, uint32_t g, uint32_t b, uint32_t a) {
+  if (sel) return __byte_perm(r | g << 8 | b << 16 | a << 24, 0u, sel);
+  return pack_pixel(fmt, r, g, b, a);
 }
 
 // binary search: largest d with base[d] <= i   (base has n+1 entries, base[0] = 0). `per` != 0: every draw has `per`

@@ -365,21 +365,13 @@ __device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, c
 }
 
 // One fragment (target.rs:163-198): depth test -> fragment shader -> colour/depth write.
-// v[0] = interpolated 1/w (the depth value), v[1..] = interpolated varyings. Returns 1 if colour was written.
-// colour pixel of tile-local index idx (= row * RF_TILE_PITCH + col) in the framebuffer
-__device__ __forceinline__ uint32_t* color_px(uint32_t* gc, uint32_t gw, uint32_t idx) {
-  const uint32_t row = idx / RF_TILE_PITCH;
-  return gc + (size_t)row * gw + (idx - row * RF_TILE_PITCH);
-}
-
+// v[0] = interpolated 1/w (the depth value), v[1..] = interpolated varyings; idx = tile-local depth index (row * RF_TILE_PITCH
+// + col), gp = the pixel in the framebuffer. Returns 1 if colour was written.
 // The per-warp shared-memory region (depth tile + fragment queue) addressed by an explicit 32-bit shared-window address.
 // With a generic pointer ptxas re-derives the window base inside the per-fragment loops to save a register (two S2R —
 // SR_CgaCtaId, SR_TID.X — plus address arithmetic per access); the volatile cvta below pins the base in a register.
 #ifndef RF_GROUP_SYNC
 #define RF_GROUP_SYNC 1
-#endif
-#ifndef RF_SMEM_ASM
-#define RF_SMEM_ASM 1
 #endif
 // L2 prefetch hint (no register result, no dependency): the records a tile's next steps will read — written by k_setup /
 // k_walk long ago, 0.8 GB each on the bunny batch, so mostly out of L2 — are requested a chunk ahead of their use.
@@ -417,7 +409,7 @@ struct WarpSmem {
 };
 
 template <int LT>
-__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t* gc, uint32_t gw, WarpSmem sz, uint32_t idx, const float* v,
+__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t sel, uint32_t* gp, WarpSmem sz, uint32_t idx, const float* v,
                                                      uint32_t pmask, uint32_t dtest, bool cwrite, bool dwrite) {
   const float z = v[0];
   if (dtest != RF_DEPTH_NONE) {  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
@@ -439,14 +431,14 @@ __device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t
   // comparison with a NaN fails (ctx.rs:86-89). The reference's x86-64 host generates the default NaN 0xFFC00000 and
   // propagates it; CUDA arithmetic generates 0x7FFFFFFF. The bits written are the host's ("NaN contract").
   if (dwrite) sz.stf(idx, z != z ? __uint_as_float(0xFFC00000u) : z);
-  if (cwrite) { *color_px(gc, gw, idx) = pack_pixel(fmt, r, g, bl, a); return 1u; }
+  if (cwrite) { *gp = pack_pixel_sel(sel, fmt, r, g, bl, a); return 1u; }
   return 0u;
 }
 
 // Specialisation for the default Context (depth test Less, colour and depth writes on, ctx.rs:104-127) and a
 // compile-time fragment shader / perspective mask: straight-line code, no state decoding.
 template <int LT, int FS, uint32_t PMASK>
-__device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, uint32_t fmt, uint32_t* gc, uint32_t gw, WarpSmem sz, uint32_t idx, const float* v) {
+__device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, uint32_t fmt, uint32_t sel, uint32_t* gp, WarpSmem sz, uint32_t idx, const float* v) {
   const float z = v[0];
   if (!(sz.ldf(idx) < z)) return 0u;
   float var[LT];
@@ -455,7 +447,7 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
   uint32_t r = 0, g = 0, bl = 0, a = 0;
   if (!shade_fragment<LT>(D, (uint32_t)FS, var, r, g, bl, a)) return 0u;
   sz.stf(idx, z);
-  *color_px(gc, gw, idx) = pack_pixel(fmt, r, g, bl, a);
+  *gp = pack_pixel_sel(sel, fmt, r, g, bl, a);
   return 1u;
 }
 
@@ -484,8 +476,8 @@ template <int LT> struct RasterSmem {
   static constexpr int TILE_WORDS = RF_TILE * RF_TILE_PITCH;
   // word offsets inside a warp's region
   static constexpr int RC0 = TILE_WORDS;           // row coverage [RF_TILE]
-  static constexpr int IQ0 = RC0 + RF_TILE;        // row queue [NL + 1][RF_ROWQ]
-  static constexpr int WARP_WORDS = IQ0 + (NL + 1) * (int)RF_ROWQ;
+  static constexpr int IQ0 = RC0 + RF_TILE;        // row queue [NL + 2][RF_ROWQ]: L[NL], R, meta = tile row | half << 5 | triangle lane << 6
+  static constexpr int WARP_WORDS = IQ0 + (NL + 2) * (int)RF_ROWQ;
   static constexpr size_t BYTES = (size_t)RF_RASTER_WARPS * WARP_WORDS * 4;
 };
 
@@ -548,6 +540,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
     // read once: the shared-memory accessors are volatile asm with a memory clobber, so every later T.x would be re-loaded
     // from global memory inside the fragment loops (the format switch waited on that load: 8 % of the stall samples)
     const uint32_t t_w = T.w, t_fmt = T.fmt, t_by0 = T.band_y0, t_by1 = T.band_y1;
+    const uint32_t t_sel = pack_selector(t_fmt);
     const uint32_t t_cflags = T.clear_flags;
     const bool has_depth = T.depth != nullptr;
     const bool vec = (t_w & 3u) == 0 && tw == RF_TILE;
@@ -653,6 +646,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
       const uint32_t t_incl = warp_scan_incl(t_rows, lane);
       const uint32_t n_items = __shfl_sync(FULL, t_incl, 31);
       const uint32_t small_mask = __ballot_sync(FULL, t_small);
+      // no other kind of triangle with rows here: the pieces of the chunk are exactly the queued rows, in order (item == queue slot)
+      const bool all_small = __ballot_sync(FULL, t_have && !t_small && t_rows != 0u) == 0u;
       const uint32_t s_rows = t_small ? t_rows : 0u;
       const uint32_t s_incl = small_mask ? warp_scan_incl(s_rows, lane) : 0u;  // row-queue slots
 
@@ -697,6 +692,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
 #pragma unroll
                 for (int i = 0; i < NL; i++) wsm.stf(IQ0 + i * RF_ROWQ + slot, L[i]);
                 wsm.stf(IQ0 + NL * RF_ROWQ + slot, R);
+                wsm.stu(IQ0 + (NL + 1) * RF_ROWQ + slot, (Y - py0) | hh << 5 | lane << 6);
                 slot++;
               }
 #pragma unroll
@@ -714,6 +710,39 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
           uint32_t Y, draw, aux;  // aux: SMALL: unused; otherwise the span's checkpoint base
           uint32_t w[WQ];
           uint32_t dvw[NV];
+        };
+        auto load_small_dv = [&](uint32_t tri, uint32_t hh, Pre& p) {
+          const uint32_t* dp = P.smalls + (size_t)tri * SR::W + 4 + hh * SR::HW + SR::O_DV;
+          if (SR::O_DV % 4 == 0) {
+#pragma unroll
+            for (int q = 0; q < (NV + 3) / 4; q++) {
+              const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(dp) + q);
+              if (4 * q < NV) p.dvw[4 * q] = t4.x;
+              if (4 * q + 1 < NV) p.dvw[4 * q + 1] = t4.y;
+              if (4 * q + 2 < NV) p.dvw[4 * q + 2] = t4.z;
+              if (4 * q + 3 < NV) p.dvw[4 * q + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < NV; i++) p.dvw[i] = __ldg(dp + i);
+          }
+        };
+        // all-SMALL chunk: the row's own meta word names its triangle lane — no search, two shuffles
+        auto fetch_small = [&](uint32_t ib, Pre& p) {
+          const uint32_t slot = ib + lane;
+          p.valid = slot < nround;
+          p.small = true;
+          p.aux = 0;
+          const uint32_t meta = p.valid ? wsm.ldu(IQ0 + (NL + 1) * RF_ROWQ + slot) : 0u;
+          const uint32_t ow = (meta >> 6) & 31u;
+          p.draw = __shfl_sync(FULL, t_draw, ow);
+          const uint32_t o_tri = __shfl_sync(FULL, t_tri, ow);
+          p.Y = py0 + (meta & 31u);
+          if (p.valid) {
+#pragma unroll
+            for (int i = 0; i < NL + 1; i++) p.w[i] = wsm.ldu(IQ0 + i * RF_ROWQ + slot);
+            load_small_dv(o_tri, (meta >> 5) & 1u, p);
+          }
         };
         auto fetch = [&](uint32_t ib, Pre& p) {
           const uint32_t item = base + ib + lane;
@@ -742,20 +771,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
               const uint32_t slot = (o_sincl - o_rows) - sbase + rit;
 #pragma unroll
               for (int i = 0; i < NL + 1; i++) p.w[i] = wsm.ldu(IQ0 + i * RF_ROWQ + slot);
-              const uint32_t* dp = P.smalls + (size_t)o_tri * SR::W + 4 + hh * SR::HW + SR::O_DV;
-              if (SR::O_DV % 4 == 0) {
-#pragma unroll
-                for (int q = 0; q < (NV + 3) / 4; q++) {
-                  const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(dp) + q);
-                  if (4 * q < NV) p.dvw[4 * q] = t4.x;
-                  if (4 * q + 1 < NV) p.dvw[4 * q + 1] = t4.y;
-                  if (4 * q + 2 < NV) p.dvw[4 * q + 2] = t4.z;
-                  if (4 * q + 3 < NV) p.dvw[4 * q + 3] = t4.w;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < NV; i++) p.dvw[i] = __ldg(dp + i);
-              }
+              load_small_dv(o_tri, hh, p);
             } else {
               const uint32_t* sp = P.spans + (size_t)(o_sbase + (p.Y - o_Y0)) * SW;
 #pragma unroll
@@ -770,10 +786,15 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
           }
         };
         Pre cur, nxt;
-        fetch(0, cur);
-        for (uint32_t ib = 0; ib < nround; ib += 32, cur = nxt) {
-          nxt.valid = false;
-          if (ib + 32 < nround) fetch(ib + 32, nxt);
+        nxt.valid = false;
+        if (!all_small) fetch(0, nxt);
+        for (uint32_t ib = 0; ib < nround; ib += 32) {
+          if (all_small) fetch_small(ib, cur);  // shared-memory latency only: no pipeline, no register copies
+          else {
+            cur = nxt;
+            nxt.valid = false;
+            if (ib + 32 < nround) fetch(ib + 32, nxt);
+          }
           bool valid = cur.valid;
           uint32_t py = 32 + lane, pxs = 0, pn = 0, draw = 0;
           float v[NV], dv[NV];
@@ -884,21 +905,22 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
               const bool ready = pending && (dep & ~done) == 0;
               if (ready) {
                 const uint32_t pbase = py * RF_TILE_PITCH + pxs;
+                uint32_t* const gp0 = gc + (size_t)py * t_w + pxs;
                 if (smode == 4) {  // default Context + FS_TEX_CLAMP_LIT (crates): straight-line fragment code
                   for (uint32_t k = 0; k < pn; k++) {
-                    my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, gc, t_w, wsm, pbase + k, v);
+                    my_o += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, t_sel, gp0 + k, wsm, pbase + k, v);
 #pragma unroll
                     for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                   }
                 } else if (smode == 2) {
                   for (uint32_t k = 0; k < pn; k++) {
-                    my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, gc, t_w, wsm, pbase + k, v);
+                    my_o += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, t_sel, gp0 + k, wsm, pbase + k, v);
 #pragma unroll
                     for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
                   }
                 } else if (LT == 5 && smode == 5) {  // default Context + FS_CHECKER on two perspective uv lanes (the crates floor): z, u, v only
                   for (uint32_t k = 0; k < pn; k++) {
-                    my_o += process_fragment_fixed<LT, RF_FS_CHECKER, 0x3u>(D, t_fmt, gc, t_w, wsm, pbase + k, v);
+                    my_o += process_fragment_fixed<LT, RF_FS_CHECKER, 0x3u>(D, t_fmt, t_sel, gp0 + k, wsm, pbase + k, v);
 #pragma unroll
                     for (int i = 0; i < 3; i++) v[i] = v[i] + dv[i];
                   }
@@ -907,7 +929,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                   const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
                   const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
                   for (uint32_t k = 0; k < pn; k++) {
-                    my_o += process_fragment<LT>(D, fs, t_fmt, gc, t_w, wsm, pbase + k, v, pmask, dtest, cwrite, dwrite);
+                    my_o += process_fragment<LT>(D, fs, t_fmt, t_sel, gp0 + k, wsm, pbase + k, v, pmask, dtest, cwrite, dwrite);
 #pragma unroll
                     for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
                   }
@@ -923,7 +945,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
             // ================= fragment mode: one fragment per lane =================
             // Fragment f of the batch belongs to the piece whose running pixel count covers f; its lane takes the piece's
             // start values and steps over shuffles and performs the k adds of vary.rs:146-154 that bring them to pixel k.
-            const uint32_t pix0 = py * RF_TILE_PITCH + pxs;
+            const uint32_t pix0 = py * RF_TILE_PITCH + pxs, gofs0 = py * t_w + pxs;
             if (pn) wsm.oru(RC0 + py, (0xFFFFFFFFu >> (32u - pn)) << pxs);  // this piece's pixels of tile row py
             __syncwarp();
             // distinct pixels covered by the batch (lane r counts tile row r and clears its word for the next batch)
@@ -952,7 +974,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                   if (cand <= 32 && e <= f) oi = cand;
                 }
                 oi &= 31u;
-                const uint32_t o_end = __shfl_sync(FULL, f_incl, oi), o_pn = __shfl_sync(FULL, pn, oi), o_pix = __shfl_sync(FULL, pix0, oi);
+                const uint32_t o_end = __shfl_sync(FULL, f_incl, oi), o_pn = __shfl_sync(FULL, pn, oi), o_pix = __shfl_sync(FULL, pix0, oi), o_gofs = __shfl_sync(FULL, gofs0, oi);
                 const uint32_t k = fvalid ? f - (o_end - o_pn) : 0u;
                 float fv[NV], fdv[NV];
 #pragma unroll
@@ -965,6 +987,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                   }
                 }
                 const uint32_t pix = fvalid ? o_pix + k : (0x10000u + lane);
+                uint32_t* const gp = gc + (o_gofs + k);
                 // same pixel, submitted before me: only searched for when two pieces of the batch overlap at all
                 uint32_t earlier = 0;
                 bool clean = true;
@@ -985,10 +1008,10 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                 const DrawDesc& D = UNI ? Du : P.draws[fdraw];
                 uint32_t wrote = 0;
                 auto one = [&]() -> uint32_t {
-                  if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, gc, t_w, wsm, pix, fv);
-                  if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, t_fmt, gc, t_w, wsm, pix, fv);
-                  if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, gc, t_w, wsm, pix, fv);
-                  return process_fragment<LT>(D, fs, t_fmt, gc, t_w, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
+                  if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, t_sel, gp, wsm, pix, fv);
+                  if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, t_fmt, t_sel, gp, wsm, pix, fv);
+                  if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, t_sel, gp, wsm, pix, fv);
+                  return process_fragment<LT>(D, fs, t_fmt, t_sel, gp, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
                 };
                 if (clean) {
                   if (fvalid) wrote = one();

@@ -356,6 +356,12 @@ inline int32_t __float_as_int(float f) { return emu::from_bits<int32_t>(emu::to_
 inline float __uint_as_float(uint32_t u) { return emu::from_bits<float>(emu::to_bits(u)); }
 inline float __int_as_float(int32_t u) { return emu::from_bits<float>(emu::to_bits(u)); }
 // PTX cvt.rzi: round towards zero, clamp to the destination range, NaN -> 0
+inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {  // PRMT, default mode
+  const uint64_t src = (uint64_t)b << 32 | a;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= (uint32_t)((src >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+  return r;
+}
 inline uint32_t __float2uint_rz(float f) { return !(f == f) ? 0u : (f <= 0.0f ? 0u : (f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)f)); }
 inline int32_t __float2int_rz(float f) { return !(f == f) ? 0 : (f <= -2147483648.0f ? INT32_MIN : (f >= 2147483648.0f ? INT32_MAX : (int32_t)f)); }
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }
