@@ -31,7 +31,7 @@ for r in csv.reader(out.splitlines()):
 
     def num(name):
         try:
-            return int(r[ix[name]] or 0)
+            return int(r[ix[name]] or 0) if name in ix else 0
         except ValueError:
             return 0
 

@@ -11,7 +11,9 @@
 // K3: give every non-empty tile a contiguous bin (warp prefix sum + one atomic per warp) and
 // build the work lists. tile_cnt was accumulated by k_prim.
 // =============================================================================================
+#ifndef RF_SORT_SMALL
 #define RF_SORT_SMALL 1024u   // per-warp shared-memory sort capacity (entries)
+#endif
 #define RF_SORT_BIG 16384u    // per-block (large smem) sort run; deeper bins are merged from runs of this size
 #ifndef RF_HEAVY_BIN
 #define RF_HEAVY_BIN 64u      // tiles are rasterised longest-first in three classes: >= RF_HEAVIEST_BIN, >= RF_HEAVY_BIN, rest
@@ -460,6 +462,14 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
 #ifndef RF_SPAN_MODE_MIN_AVG_5
 #define RF_SPAN_MODE_MIN_AVG_5 4u
 #endif
+// Cost model (instructions per warp, measured from ncu source counters): span mode runs max(pn) iterations of one fragment
+// per lane, fragment mode runs ceil(n_frags / 32) groups, each paying the piece search, the shuffles and the k adds.
+#ifndef RF_SPAN_ITER_COST
+#define RF_SPAN_ITER_COST 0u   // 0: decide by the average piece length alone
+#endif
+#ifndef RF_FRAG_GROUP_COST
+#define RF_FRAG_GROUP_COST 150u
+#endif
 template <int LT> struct RasterTune {
   static constexpr uint32_t MIN_AVG = LT == 3 ? RF_SPAN_MODE_MIN_AVG_3 : RF_SPAN_MODE_MIN_AVG_5;
 };
@@ -883,11 +893,20 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
             if (has_depth) { smode = mode_bits & 15u; fmode = mode_bits >> 4; }
           }
 
-          if (n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask)) {
+          // distinct pixels covered by the batch: every piece ORs its pixel run into the coverage word of its tile row (lane r then
+          // counts row r and clears the word for the next batch); equal to the fragment count <=> no two pieces share a pixel
+          if (pn) wsm.oru(RC0 + py, (0xFFFFFFFFu >> (32u - pn)) << pxs);
+          __syncwarp();
+          const uint32_t rcov = wsm.ldu(RC0 + lane);
+          wsm.stu(RC0 + lane, 0u);
+          const bool no_overlap = __reduce_add_sync(FULL, (uint32_t)__popc(rcov)) == n_frags;
+          bool span_mode = n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask);
+          if (RF_SPAN_ITER_COST != 0u && !span_mode) span_mode = __reduce_max_sync(FULL, pn) * RF_SPAN_ITER_COST <= ((n_frags + 31u) >> 5) * RF_FRAG_GROUP_COST;
+          if (span_mode) {
             // ================= span mode: one piece per lane, walked serially =================
             // dependencies: earlier lanes on the same row whose x-range overlaps mine
             uint32_t dep = 0;
-            {
+            if (!no_overlap) {
               uint32_t m = __match_any_sync(FULL, py) & lt;
               while (__any_sync(FULL, m != 0)) {
                 const int jj = m ? (__ffs(m) - 1) : (int)lane;
@@ -946,12 +965,6 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
             // Fragment f of the batch belongs to the piece whose running pixel count covers f; its lane takes the piece's
             // start values and steps over shuffles and performs the k adds of vary.rs:146-154 that bring them to pixel k.
             const uint32_t pix0 = py * RF_TILE_PITCH + pxs, gofs0 = py * t_w + pxs;
-            if (pn) wsm.oru(RC0 + py, (0xFFFFFFFFu >> (32u - pn)) << pxs);  // this piece's pixels of tile row py
-            __syncwarp();
-            // distinct pixels covered by the batch (lane r counts tile row r and clears its word for the next batch)
-            const uint32_t rcov = wsm.ldu(RC0 + lane);
-            wsm.stu(RC0 + lane, 0u);
-            const bool no_overlap = __reduce_add_sync(FULL, (uint32_t)__popc(rcov)) == n_frags;
             // When the whole batch belongs to one draw (the common case) the draw state is warp-uniform and hoisted out of
             // the loop; otherwise every fragment looks its draw up.
             auto frag_loop = [&](auto mode_tag) {
