@@ -177,6 +177,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": desc,
         "frames_per_s": tot_n / tot_t, "Mtriangles_per_s": tot_p / tot_t / 1e6,
+        "frames_sampled": len(sample), "threads": cores,
         "cpu_baseline": {"value": val, "unit": "Mfragments/s", "cores": cores, "kind": "port",
                          "sample": f"{len(sample)} of {args.frames} frames per step, frames spread over {cores} host threads (oracle port; the Rust reference cannot be built here)"},
         "e2e": {"value": val, "unit": "Mfragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,30 +186,69 @@ def run_reference(args):
 
 
 # ---- B200 arm ------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
+def csrc_sha() -> str:
+    """Hash of the kernel sources: a committed ncu traffic figure is only printed for the tree it was captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "retrofire_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
+
+def committed_traffic(workload: str, frames: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE k_raster launch of this command, from the committed capture
+    (profiles/r02_raster_traffic.json, written by profiles/make_traffic.py from an ncu run) — or None when the capture is of
+    another tree (csrc hash), workload or batch size: a stale figure is never printed."""
+    tp = os.path.join(ROOT, "profiles", "r02_raster_traffic.json")
+    if not os.path.exists(tp):
+        return None, None
+    tj = json.load(open(tp))
+    e = tj.get("captures", {}).get(f"{workload}:{frames}")
+    if not e or tj.get("csrc_sha") != csrc_sha():
+        return None, None
+    return int(e["dram_bytes_read"] + e["dram_bytes_write"]), e.get("pass_dram_bytes")
+
+
+def measure_pcie(torch, dist, world, seconds: float = 0.6):
+    """Device-to-host DMA ceiling of this box with all `world` ranks copying at once (page-locked destination), GB/s per rank
+    and aggregate: the denominator of the end-to-end leg, whose every frame ends with one colour buffer crossing PCIe."""
+    n = 256 << 20
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dst = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.Stream(device=local)
+        dist.barrier()
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < seconds:
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        reps += 1
+    dt = time.perf_counter() - t0
+    mine = reps * n / dt / 1e9
+    tot = mine
+    if world > 1:
+        t = torch.tensor([mine], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot = float(t[0])
+    return mine, tot
 
-    base, per_frame, desc = make_workload(args.workload, args.frames)
-    F = args.frames
-    dev = rf.Device(local, stream=stream.cuda_stream)
+
+def measure(ctx, workload: str, F: int, steps: int, warmup: int, e2e: bool, cpu_seconds: float, latency: bool):
+    """One workload through the device path. Returns the fields of a bench line for it (rank-local; reduce() folds ranks)."""
+    import dataclasses
+    torch, dev, stream, barrier = ctx["torch"], ctx["dev"], ctx["stream"], ctx["barrier"]
+    base, per_frame, desc = make_workload(workload, F)
     targets = [dev.framebuf(base.w, base.h, base.fmt, base.has_depth) for _ in range(F)]
-    # resident geometry: one rf_mesh per distinct (prims, verts) pair
-    mesh_cache = {}
+    mesh_cache = ctx["mesh_cache"]
 
-    def resident(d: rf.DrawCall) -> rf.DrawCall:
+    def resident(d: rf.DrawCall) -> rf.DrawCall:  # resident geometry: one rf_mesh per distinct (prims, verts) pair
         key = (d.prims.ctypes.data, d.verts.ctypes.data)
         if key not in mesh_cache:
             mesh_cache[key] = dev.mesh(d.prims, d.verts)
-        import dataclasses
         return dataclasses.replace(d, mesh=mesh_cache[key])
 
     res_frames = [[resident(d) for d in draws] for draws in per_frame]
@@ -225,30 +265,26 @@ def run_b200(args):
                 dev.render_many(draws, t)    # the frame's render() calls in one crossing of the C ABI
         dev.flush()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ---- warm-up (also grows the arenas so the timed region never replays a pass)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_resident()
         dev.sync()
     dev.stats(reset=True)
     dev.profile(1)   # CUDA events around k_raster only: the timed passes keep their normal stream overlap
-    torch.cuda.cudart().cudaProfilerStart()  # ncu --profile-from-start off: capture only the timed region
-
-    sampler = ClockSampler(local)
+    if ctx["primary"]:
+        torch.cuda.cudart().cudaProfilerStart()  # ncu --profile-from-start off: capture only the timed region
+    sampler = ClockSampler(ctx["local"])
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_resident()
     ev1.record(stream)
     dev.sync()
     barrier()
-    torch.cuda.cudart().cudaProfilerStop()
+    if ctx["primary"]:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = ev0.elapsed_time(ev1)
     sampler.stop_flag.set()
     st = dev.stats(reset=True)
@@ -260,10 +296,11 @@ def run_b200(args):
     kall = dev.kernel_times()
     dev.profile(0)
     _, launches_per_pass = dev.last_pass()
+    out = {"base": base, "desc": desc, "F": F, "steps": steps, "ms": ms, "stats": st, "ktimes": ktimes, "kall": kall,
+           "launches_per_pass": launches_per_pass, "clocks": sampler.summary(), "single": single, "per_frame": per_frame}
 
     # ---- single-frame latency, reported separately: clear + draw + wait, one frame per pass
-    lat_ms = None
-    if not args.kernel_only:
+    if latency:
         one = res_frames[0]
         ts = []
         for k in range(30):
@@ -273,157 +310,182 @@ def run_b200(args):
             dev.render_many(one, targets[0])
             dev.sync()
             ts.append(time.perf_counter() - t0)
-        lat_ms = 1e3 * sorted(ts[5:])[len(ts[5:]) // 2]
+        out["latency_ms"] = 1e3 * sorted(ts[5:])[len(ts[5:]) // 2]
 
-    # ---- end to end: host geometry in (rf_render with host pointers: staged through pinned memory and
-    # copied H2D inside the timed region), colour buffer of every frame out (D2H into page-locked Buf2 storage)
-    Fe = min(F // 2, 16) if F >= 2 else 1   # frames per end-to-end step; two sets of device targets alternate (a swap chain)
-    dt, shape = (np.uint32, (base.h, base.w)) if base.fmt == rf.FMT_XRGB8888 else (np.uint8, (base.h, base.w, 4))
-    host_color = [[dev.pinned_empty(shape, dt) for _ in range(Fe)] for _ in range(2)]  # double-buffered Buf2 storage
+    # ---- end to end: host geometry in (rf_render with HOST pointers to page-locked arrays: DMA'd inside the timed region),
+    # colour buffer of every frame out (D2H into page-locked Buf2 storage). Two halves of the step's targets alternate (a swap
+    # chain), so that the downloads of one half overlap the rendering of the other.
+    if e2e:
+        Fe = max(1, F // 2)
+        dt, shape = (np.uint32, (base.h, base.w)) if base.fmt == rf.FMT_XRGB8888 else (np.uint8, (base.h, base.w, 4))
+        host_color = [[dev.pinned_empty(shape, dt) for _ in range(Fe)] for _ in range(2)]  # double-buffered Buf2 storage
+        pin_cache = {}
 
-    # the caller's vertex / index arrays live in page-locked memory (rf_host_alloc), as the bench contract asks
-    import dataclasses as _dc
-    pin_cache = {}
+        def pinned_copy(a):
+            key = a.ctypes.data
+            if key not in pin_cache:
+                b = dev.pinned_empty(a.shape, a.dtype)
+                b[...] = a
+                pin_cache[key] = b
+            return pin_cache[key]
 
-    def pinned_copy(a):
-        key = a.ctypes.data
-        if key not in pin_cache:
-            b = dev.pinned_empty(a.shape, a.dtype)
-            b[...] = a
-            pin_cache[key] = b
-        return pin_cache[key]
+        e2e_frames = [[dataclasses.replace(d, prims=pinned_copy(d.prims), verts=pinned_copy(d.verts)) for d in per_frame[f]] for f in range(Fe)]
 
-    e2e_frames = [[_dc.replace(d, prims=pinned_copy(d.prims), verts=pinned_copy(d.verts)) for d in per_frame[f]] for f in range(Fe)]
+        def step_e2e(k=0):
+            tg = targets[(k & 1) * Fe: (k & 1) * Fe + Fe] if F >= 2 * Fe else targets[:Fe]
+            for f in range(Fe):
+                tg[f].clear(base.ctx)
+                dev.render_many(e2e_frames[f], tg[f])
+            for f in range(Fe):
+                tg[f].download_color_async(host_color[k & 1][f])
 
-    def step_e2e(k=0):
-        """One step through the reference-facing calls: clear + render() with host geometry for every frame,
-        then the colour buffer of every frame is read back. Downloads run on the library's copy stream and
-        overlap the next step's rendering; dev.sync() at the end of the timed region waits for all of them."""
-        tg = targets[(k & 1) * Fe: (k & 1) * Fe + Fe] if F >= 2 * Fe else targets[:Fe]
-        for f in range(Fe):
-            tg[f].clear(base.ctx)
-            dev.render_many(e2e_frames[f], tg[f])
-        for f in range(Fe):
-            tg[f].download_color_async(host_color[k & 1][f])
-
-    e_steps = 0 if args.kernel_only else max(2, min(args.steps, 20))
-    for k in range(2 if e_steps else 0):
-        step_e2e(k)
-    dev.sync()
-    # wall-clock (host work is part of the end-to-end path): median of three repetitions of e_steps steps
-    e_runs = []
-    for rep in range(3 if e_steps else 1):
-        dev.stats(reset=True)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(e_steps):
+        e_steps = max(4, min(2 * steps, 12))
+        for k in range(2):
             step_e2e(k)
-        dev.sync()   # every queued pass and every download has completed: the pixels are in host memory
-        barrier()
-        e_runs.append(max(time.perf_counter() - t0, 1e-9))
-    e_dt = sorted(e_runs)[len(e_runs) // 2]
-    e_st = dev.stats(reset=True)
-    h2d = sum(d.verts.nbytes + d.prims.nbytes for f in range(Fe) for d in per_frame[f])
-    d2h = Fe * base.w * base.h * 4
-
-    # ---- second metric configuration (BASELINE "crates 4K"): a short resident-geometry run, reported under "crates_4k"
-    crates_info = None
-    if args.workload == "bunny" and not args.kernel_only:
-        cb, cpf, _ = make_workload("crates", 2)
-        ct = [dev.framebuf(cb.w, cb.h, cb.fmt, cb.has_depth) for _ in range(2)]
-        cres = [[resident(d) for d in draws] for draws in cpf]
-
-        def step_crates():
-            for t, draws in zip(ct, cres):
-                t.clear(cb.ctx)
-                dev.render_many(draws, t)
-            dev.flush()
-
-        for _ in range(3):
-            step_crates()
-            dev.sync()
-        dev.stats(reset=True)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record(stream)
-        csteps = 10
-        for _ in range(csteps):
-            step_crates()
-        c1.record(stream)
         dev.sync()
-        cms = c0.elapsed_time(c1)
-        cst = dev.stats(reset=True)
-        crates_info = {"workload": "crates 1,089 cubes + floor 3840x2160 Rgba8888, one draw per visible cube", "draws_per_frame": len(cres[0]),
-                       "frames_per_s": 2 * csteps / (cms * 1e-3), "Mfragments_per_s": cst.frags.i / (cms * 1e-3) / 1e6,
-                       "ms_per_frame": cms / (2 * csteps), "frags_i_per_frame": cst.frags.i // (2 * csteps), "n_gpus": 1}
+        e_runs = []   # wall clock (host work is part of the end-to-end path): median of three repetitions
+        for rep in range(3):
+            dev.stats(reset=True)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(e_steps):
+                step_e2e(k)
+            dev.sync()   # every queued pass and every download has completed: the pixels are in host memory
+            barrier()
+            e_runs.append(max(time.perf_counter() - t0, 1e-9))
+        out["e2e"] = {"seconds": sorted(e_runs)[1], "stats": dev.stats(reset=True), "steps": e_steps, "Fe": Fe,
+                      "h2d": sum(d.verts.nbytes + d.prims.nbytes for f in range(Fe) for d in per_frame[f]), "d2h": Fe * base.w * base.h * 4}
 
-    # ---- reduce over ranks
-    t_ms, e_s = ms, e_dt
+    if cpu_seconds > 0:  # CPU baseline: oracle, 1 thread (the reference is single-threaded), bounded sample
+        n = 0
+        t_used = fi_tot = 0.0
+        while t_used < cpu_seconds and n < 100000:
+            dt_, fi, _, _ = oracle_frames(base, per_frame, [n % F], 1)
+            t_used += dt_; fi_tot += fi; n += 1
+        out["cpu"] = {"value": fi_tot / t_used / 1e6, "unit": "Mfragments/s", "cores": 1, "kind": "port",
+                      "sample": f"{n} frames (cycling the step's {F}), CPU oracle single-threaded, {t_used:.1f} s", "frames_per_s": n / t_used}
+    for t in targets:
+        t._destroy()
+        dev._targets.remove(t)
+    return out
+
+
+def fold(ctx, m, workload: str, pcie):
+    """Fold a measure() result over the ranks (max of times, sum of counters) into bench-line fields (valid on rank 0)."""
+    torch, dist, world = ctx["torch"], ctx["dist"], ctx["world"]
+    base, F, steps, st = m["base"], m["F"], m["steps"], m["stats"]
+    t_ms = m["ms"]
     frags_i, frags_o, prims_i = st.frags.i, st.frags.o, st.prims.i
-    e_frags = e_st.frags.i
+    e = m.get("e2e")
+    e_s, e_frags = (e["seconds"], e["stats"].frags.i) if e else (0.0, 0)
     if world > 1:
-        tt = torch.tensor([ms, e_dt], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_ms, e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_ms, e_s = float(tt[0]), float(tt[1])
         cc = torch.tensor([frags_i, frags_o, prims_i, e_frags], device="cuda", dtype=torch.int64)
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
         frags_i, frags_o, prims_i, e_frags = (int(x) for x in cc)
+    peak, peak_src = peaks()
+    r_ns, r_n = m["ktimes"]["k_raster"]
+    alg_bytes_launch = (4 * st.frags.i + 8 * st.frags.o) / max(r_n, 1)   # rank-0 kernel: algorithmic bytes of ITS launches
+    r_avg_s = r_ns * 1e-9 / max(r_n, 1)
+    achieved = alg_bytes_launch / r_avg_s / 1e9 if r_avg_s > 0 else 0.0
+    kall = m["kall"]
+    kshare = {k: round(v[0] / max(sum(x[0] for x in kall.values()), 1), 4) for k, v in kall.items()}
+    # whole-frame algorithmic bytes (SURVEY §8d B_alg: geometry in + clear + 4 B per input fragment + 8 B per written one) of
+    # one rank's step over that step's time: BASELINE.md's "% of HBM peak"
+    geom = sum(d.verts.shape[0] * 4 * (3 + d.shader.lanes) + d.prims.shape[0] * 12 for d in m["per_frame"][0])
+    b_alg_step = F * (geom + (8 if base.has_depth else 4) * base.w * base.h) + (4 * st.frags.i + 8 * st.frags.o) / steps
+    pass_gbps = b_alg_step / (t_ms * 1e-3 / steps) / 1e9
+    traffic, pass_traffic = committed_traffic(workload, F)
+    f = {
+        "value": frags_i / (t_ms * 1e-3) / 1e6, "ms_per_step": t_ms / steps,
+        "config": dict(m["desc"], l2="inputs larger than L2: %d targets x %.1f MB colour+depth per step" % (F, base.w * base.h * 8 / 1e6),
+                       parallelism=f"frame-sharded x{world}"),
+        "frames_per_s": world * F * steps / (t_ms * 1e-3), "Mtriangles_per_s": prims_i / (t_ms * 1e-3) / 1e6,
+        "frags_i_per_step": frags_i // steps, "frags_o_per_step": frags_o // steps,
+        "gpu_launches": int(steps * m["launches_per_pass"]),
+        "roofline": {"bound": "hbm", "kernel": "k_raster", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": "profiles/r02_raster_traffic.json (ncu capture of this tree, csrc hash checked)" if traffic else None,
+                     "peak_source": peak_src, "kernel_ms_avg": r_avg_s * 1e3, "alg_bytes_per_launch": alg_bytes_launch,
+                     "kernel_time_share": kshare,
+                     "pass_alg_GBps": pass_gbps, "frac_pass": pass_gbps / peak, "pass_alg_bytes": b_alg_step, "pass_traffic": pass_traffic},
+        "clocks": m["clocks"],
+    }
+    if e:
+        frames_s = world * e["Fe"] * e["steps"] / e_s
+        f["e2e"] = {"value": e_frags / e_s / 1e6, "unit": "Mfragments/s", "h2d_bytes_per_step": int(e["h2d"]), "d2h_bytes_per_step": int(e["d2h"]),
+                    "frames_per_step": e["Fe"], "frames_per_s": frames_s}
+        if pcie:
+            d2h_gbps = frames_s * base.w * base.h * 4 / 1e9
+            f["e2e"].update({"d2h_GBps": d2h_gbps, "pcie_d2h_GBps_all_ranks": pcie[1], "frac_of_pcie": d2h_gbps / pcie[1],
+                             "bound": "host link: every frame ends with its colour buffer crossing PCIe"})
+    if "latency_ms" in m:
+        f["single_frame_latency_ms"] = m["latency_ms"]  # wall clock of clear + render + sync for ONE frame (not batched)
+    if "cpu" in m:
+        f["cpu_baseline"] = m["cpu"]
+    return f
 
-    if rank == 0:
-        peak, peak_src = peaks()
-        r_ns, r_n = ktimes["k_raster"]
-        # rank-0 kernel: algorithmic bytes of ITS launches
-        alg_bytes_launch = (4 * st.frags.i + 8 * st.frags.o) / max(r_n, 1)
-        r_avg_s = r_ns * 1e-9 / max(r_n, 1)
-        achieved = alg_bytes_launch / r_avg_s / 1e9 if r_avg_s > 0 else 0.0
-        kshare = {k: round(v[0] / max(sum(x[0] for x in kall.values()), 1), 4) for k, v in kall.items()}
-        # whole-frame algorithmic bytes (SURVEY §8d B_alg) over the whole step time, for context
-        geom = base.geometry_bytes() if single else sum(d.verts.shape[0] * 4 * (3 + d.shader.lanes) + d.prims.shape[0] * 12 for d in per_frame[0])
-        b_alg_step = F * (geom + 8 * base.w * base.h) + (4 * st.frags.i + 8 * st.frags.o) / args.steps
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_raster_traffic.json")
-        if os.path.exists(tp):  # dram bytes of one k_raster launch from the committed ncu --set full capture of this command
-            tj = json.load(open(tp))
-            if tj.get("workload") == args.workload and tj.get("frames_per_pass") == F:
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        line = {
-            "metric": "Mfragments/s", "value": frags_i / (t_ms * 1e-3) / 1e6, "unit": "Mfragments/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(desc, l2="inputs larger than L2: %d targets x %.1f MB colour+depth per step" % (F, base.w * base.h * 8 / 1e6),
-                           parallelism=f"frame-sharded x{world}"),
-            "frames_per_s": world * F * args.steps / (t_ms * 1e-3), "Mtriangles_per_s": prims_i / (t_ms * 1e-3) / 1e6,
-            "frags_i_per_step": frags_i // args.steps, "frags_o_per_step": frags_o // args.steps,
-            "e2e": {"value": e_frags / e_s / 1e6, "unit": "Mfragments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "frames_per_step": Fe, "frames_per_s": world * Fe * e_steps / e_s},
-            "gpu_launches": int(args.steps * (launches_per_pass)),
-            "roofline": {"bound": "hbm", "kernel": "k_raster", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel_ms_avg": r_avg_s * 1e3,
-                         "alg_bytes_per_launch": alg_bytes_launch, "kernel_time_share": kshare,
-                         "pass_alg_GBps": b_alg_step / (t_ms * 1e-3 / args.steps) / 1e9},
-            "clocks": sampler.summary(),
-        }
-        if crates_info is not None:
-            line["crates_4k"] = crates_info
-        if lat_ms is not None:
-            line["single_frame_latency_ms"] = lat_ms  # wall clock of clear + render + sync for ONE frame (not batched)
-        if world == 1 and not args.kernel_only:
-            # CPU baseline: oracle, 1 thread (the reference is single-threaded), bounded sample
-            n = 0
-            t_used = fi_tot = 0.0
-            while t_used < args.cpu_seconds and n < 100000:
-                dt, fi, _, _ = oracle_frames(base, per_frame, [n % F], 1)
-                t_used += dt; fi_tot += fi; n += 1
-            line["cpu_baseline"] = {"value": fi_tot / t_used / 1e6, "unit": "Mfragments/s", "cores": 1, "kind": "port",
-                                    "sample": f"{n} frames (cycling the step's {F}), CPU oracle single-threaded, {t_used:.1f} s",
-                                    "frames_per_s": n / t_used}
-        print(json.dumps(line), flush=True)
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream(device=local)
+    dev = rf.Device(local, stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = {"torch": torch, "dist": dist, "dev": dev, "stream": stream, "barrier": barrier, "world": world, "rank": rank, "local": local,
+           "mesh_cache": {}, "primary": True}
+    full = not args.kernel_only
+    pcie = measure_pcie(torch, dist, world) if full else None
+    m = measure(ctx, args.workload, args.frames, args.steps, args.warmup, e2e=full, cpu_seconds=args.cpu_seconds if full and world == 1 else 0.0, latency=full)
+    f = fold(ctx, m, args.workload, pcie)
+    line = {"metric": "Mfragments/s", "value": f.pop("value"), "unit": "Mfragments/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": f.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic"}
+    line.update(f)
+    # ---- the second configuration BASELINE.json's metric names, "crates 4K", measured the same way (value, roofline, e2e,
+    # cpu_baseline) on an 8-frame batch
+    if args.workload == "bunny" and full:
+        ctx["primary"] = False
+        mc = measure(ctx, "crates", 8, 10, 3, e2e=True, cpu_seconds=min(args.cpu_seconds, 4.0) if world == 1 else 0.0, latency=True)
+        fc = fold(ctx, mc, "crates", pcie)
+        fc["unit"] = "Mfragments/s"
+        fc["draws_per_frame"] = len(mc["per_frame"][0])
+        line["crates_4k"] = fc
     dev.close()
+    # ---- N > 1: the other way the path shards (SURVEY 8e, north_star config 5-i): ONE 8K frame of 1 M small triangles,
+    # sort-first over the ranks, so that the scaling record carries the mode that has an exchange step
+    if world > 1 and full and args.workload == "bunny":
+        a2 = argparse.Namespace(**vars(args))
+        a2.workload, a2.steps, a2.warmup = "small_tris", 20, 3
+        sf = {}
+        for ex in ("peer", "nccl"):
+            a2.exchange = ex
+            r = run_tiles(a2, emit=False, init=False)
+            if rank == 0 and r:
+                sf[ex] = {k: r[k] for k in ("value", "ms_per_step", "frames_per_s", "exchange", "gather_bytes_per_step", "nccl_gather_ms_alone", "kernel_ms_rank0")}
+                sf["workload"] = r["config"]["workload"]
+        if rank == 0:
+            line["sort_first_8k"] = sf
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_tiles(args):
+def run_tiles(args, emit: bool = True, init: bool = True):
     """Sort-first: geometry replicated, rank r rasterises its row band of one large frame, bands gathered with NCCL."""
     import torch
     import torch.distributed as dist
@@ -432,7 +494,7 @@ def run_tiles(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and init:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream(device=local)
     base, per_frame, desc = make_workload(args.workload, 1)
@@ -502,8 +564,9 @@ def run_tiles(args):
         cc = torch.tensor([fi], device="cuda", dtype=torch.int64)
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
         fi = int(cc[0])
+    result = None
     if rank == 0:
-        print(json.dumps({
+        result = ({
             "metric": "Mfragments/s", "value": fi / (ms * 1e-3) / 1e6, "unit": "Mfragments/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -513,10 +576,13 @@ def run_tiles(args):
             "frames_per_s": args.steps / (ms * 1e-3), "Mtriangles_per_s": pi / (ms * 1e-3) / 1e6,
             "exchange": "none" if world == 1 else args.exchange,
             "gather_bytes_per_step": 0 if world == 1 or peer else base.w * base.h * 4 * (world - 1) // world,
-            "nccl_gather_ms_alone": gather_ms, "kernel_ms_rank0": kernel_ms}), flush=True)
+            "nccl_gather_ms_alone": gather_ms, "kernel_ms_rank0": kernel_ms})
+        if emit:
+            print(json.dumps(result), flush=True)
     dev.close()
-    if world > 1:
+    if world > 1 and init:
         dist.destroy_process_group()
+    return result
 
 
 def main():

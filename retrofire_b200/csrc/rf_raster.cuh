@@ -462,13 +462,17 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
 #ifndef RF_SPAN_MODE_MIN_AVG_5
 #define RF_SPAN_MODE_MIN_AVG_5 4u
 #endif
-// Cost model (instructions per warp, measured from ncu source counters): span mode runs max(pn) iterations of one fragment
-// per lane, fragment mode runs ceil(n_frags / 32) groups, each paying the piece search, the shuffles and the k adds.
+// Cost model: span mode runs max(pn) iterations of one fragment per lane, fragment mode runs ceil(n_frags / 32) groups, each
+// paying the piece search, the shuffles and the k adds. The constants are fitted to A/B timings on the four bench workloads
+// (profiles/r02_ab_span_model.txt: span mode iff max(pn) <= 7 x groups; -5 % bunny, -16 % sprites, +1.5 % small triangles).
 #ifndef RF_SPAN_ITER_COST
-#define RF_SPAN_ITER_COST 0u   // 0: decide by the average piece length alone
+#define RF_SPAN_ITER_COST 20u   // one span-mode iteration (0: decide by the average piece length alone)
 #endif
 #ifndef RF_FRAG_GROUP_COST
-#define RF_FRAG_GROUP_COST 150u
+#define RF_FRAG_GROUP_COST 150u  // one fragment-mode group, plus RF_FRAG_K_COST per step of its k loop
+#endif
+#ifndef RF_FRAG_K_COST
+#define RF_FRAG_K_COST 0u
 #endif
 template <int LT> struct RasterTune {
   static constexpr uint32_t MIN_AVG = LT == 3 ? RF_SPAN_MODE_MIN_AVG_3 : RF_SPAN_MODE_MIN_AVG_5;
@@ -901,7 +905,10 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
           wsm.stu(RC0 + lane, 0u);
           const bool no_overlap = __reduce_add_sync(FULL, (uint32_t)__popc(rcov)) == n_frags;
           bool span_mode = n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask);
-          if (RF_SPAN_ITER_COST != 0u && !span_mode) span_mode = __reduce_max_sync(FULL, pn) * RF_SPAN_ITER_COST <= ((n_frags + 31u) >> 5) * RF_FRAG_GROUP_COST;
+          if (RF_SPAN_ITER_COST != 0u && !span_mode) {
+            const uint32_t maxpn = __reduce_max_sync(FULL, pn);
+            span_mode = 10u + maxpn * RF_SPAN_ITER_COST <= ((n_frags + 31u) >> 5) * (RF_FRAG_GROUP_COST + RF_FRAG_K_COST * maxpn);
+          }
           if (span_mode) {
             // ================= span mode: one piece per lane, walked serially =================
             // dependencies: earlier lanes on the same row whose x-range overlaps mine
