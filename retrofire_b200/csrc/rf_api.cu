@@ -720,7 +720,6 @@ rf_status validate_all(rf_ctx* c) {
     if (ps.error) {
       if (ps.error & RF_ERRBIT_INDEX_OOB) result = fail(c, RF_E_INDEX_OOB, "vertex index out of bounds (render/prim.rs:17-19 panics)");
       else if (ps.error & RF_ERRBIT_TARGET_OOB) result = fail(c, RF_E_TARGET_OOB, "scanline outside the render target (render/target.rs:148,173 panics)");
-      else if (ps.error & RF_ERRBIT_NEG_ROW) result = fail(c, RF_E_TARGET_OOB, "scanline above the render target (viewport outside the target)");
       else if (ps.error & RF_ERRBIT_INTERNAL) result = fail(c, RF_E_CUDA, "internal: span outside its triangle's tile bounding box");
       else result = fail(c, RF_E_NOMEM, "a 32x32 tile is overlapped by more than %u triangles of one pass (max_bin=%u)", RF_SORT_BIG, ps.max_bin);
     } else {

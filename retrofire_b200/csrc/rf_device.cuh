@@ -38,7 +38,6 @@
 #define RF_ERRBIT_INDEX_OOB 0x1u
 #define RF_ERRBIT_TARGET_OOB 0x2u
 #define RF_ERRBIT_BIN_TOO_DEEP 0x4u
-#define RF_ERRBIT_NEG_ROW 0x8u
 #define RF_ERRBIT_INTERNAL 0x10u
 
 struct DrawDesc {

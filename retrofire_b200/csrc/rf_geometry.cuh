@@ -328,7 +328,7 @@ __device__ __forceinline__ void tri_setup(const uint32_t* w, HalfSetup<LT>& H0, 
 
 // ---------------------------------------------------------------------------------------------
 // Triangle record (Rec<LT>::TW words), written by k_setup, read by k_edge_ckpt, k_walk, k_ckpt, k_raster:
-//   [0] key  [1] draw  [2] sbase  [3] Y0  [4] nU  [5] nL | target << 16  [6] chunk position of half 0  [7] of half 1
+//   [0] key  [1] draw  [2] sbase  [3] Yf0 (int32: first scanline's row, negative above the target)  [4] nU  [5] nL | target << 16  [6] chunk position of half 0  [7] of half 1
 //   [8 + h*HS ...] half h: dv[1+LT] (dz/dx, dattr/dx), L[2+LT], dl[2+LT], R, dr, y
 // ---------------------------------------------------------------------------------------------
 template <int LT> struct TriRec {
@@ -340,19 +340,29 @@ template <int LT> struct TriRec {
 // Conservative tile-column range of a triangle in one tile row, from the closed-form edge lines
 // widened by a margin that bounds the drift of the reference's running sums (|sum_j - (x0 + j*dx)|
 // <= j * 2^-24 * max|x|) plus the half-pixel rounding of round_up_to_half.
+// Scanline j of a triangle whose first row centre is Yf0 + 0.5 lands on framebuffer row max(0, Yf0 + j): `self.y as usize`
+// saturates (raster.rs:106), so every scanline above the target is drawn at row 0. The scanlines of framebuffer rows [ra, rb]:
+__device__ __forceinline__ void rows_to_scanlines(int32_t Yf0, uint32_t nrows, uint32_t ra, uint32_t rb, uint32_t& ja, uint32_t& jb_excl) {
+  const int32_t a = (int32_t)ra - Yf0;
+  ja = (ra == 0u || a < 0) ? 0u : (uint32_t)a;  // row 0 also takes every scanline above it
+  const int32_t e = (int32_t)rb + 1 - Yf0;
+  jb_excl = e <= 0 ? 0u : min(nrows, (uint32_t)e);
+  if (ja > jb_excl) ja = jb_excl;
+}
 template <int LT>
-__device__ __forceinline__ void tile_row_cols(const HalfSetup<LT>& H0, const HalfSetup<LT>& H1, uint32_t Y0, uint32_t nrows, uint32_t trow,
+__device__ __forceinline__ void tile_row_cols(const HalfSetup<LT>& H0, const HalfSetup<LT>& H1, int32_t Yf0, uint32_t nrows, uint32_t trow,
                                               float margin, uint32_t tiles_x, uint32_t& ca, uint32_t& cb) {
-  const uint32_t Ya = max(Y0, trow << RF_TILE_SHIFT), Yb = min(Y0 + nrows - 1, (trow << RF_TILE_SHIFT) + RF_TILE - 1);
+  uint32_t j0, j1;  // scanlines [j0, j1) of this tile row
+  rows_to_scanlines(Yf0, nrows, trow << RF_TILE_SHIFT, (trow << RF_TILE_SHIFT) + RF_TILE - 1, j0, j1);
   float lo = 3.0e38f, hi = -3.0e38f;
   const uint32_t nU = H0.n;
-  if (Ya < Y0 + nU) {  // rows of the upper half
-    const float ja = (float)(Ya - Y0), jb = (float)(min(Yb, Y0 + nU - 1) - Y0);
+  if (j0 < j1 && j0 < nU) {  // rows of the upper half
+    const float ja = (float)j0, jb = (float)(min(j1, nU) - 1u);
     lo = fminf(lo, fminf(H0.L[0] + H0.dl[0] * ja, H0.L[0] + H0.dl[0] * jb));
     hi = fmaxf(hi, fmaxf(H0.R + H0.dr * ja, H0.R + H0.dr * jb));
   }
-  if (Yb >= Y0 + nU) {  // rows of the lower half
-    const float ja = (float)(max(Ya, Y0 + nU) - (Y0 + nU)), jb = (float)(Yb - (Y0 + nU));
+  if (j0 < j1 && j1 > nU) {  // rows of the lower half
+    const float ja = (float)(max(j0, nU) - nU), jb = (float)(j1 - 1u - nU);
     lo = fminf(lo, fminf(H1.L[0] + H1.dl[0] * ja, H1.L[0] + H1.dl[0] * jb));
     hi = fmaxf(hi, fmaxf(H1.R + H1.dr * ja, H1.R + H1.dr * jb));
   }
@@ -807,7 +817,8 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
     bool emit = false;
     HalfSetup<LT> H0, H1;
     H0.n = H1.n = 0;
-    uint32_t key = 0, d = 0, tgt = 0, Y0 = 0, tr0 = 0, tr1 = 0, tiles_x = 1, nent = 0, nchunk = 0;
+    int32_t Yf0 = 0;  // first scanline's framebuffer row, signed (see rows_to_scanlines)
+    uint32_t key = 0, d = 0, tgt = 0, tr0 = 0, tr1 = 0, tiles_x = 1, nent = 0, nchunk = 0;
     float margin = 0.0f;
     unsigned long long my_frags_i = 0;
     uint32_t long_rows = 0, long_sbase = 0, long_tri = 0, long_nU = 0;  // inline-walked rows that cross a tile column
@@ -860,7 +871,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
         if (LM.oob) { atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB); }
         else if (LM.ymin <= LM.ymax) {
           emit = true;
-          Y0 = LM.ymin;
+          Yf0 = (int32_t)LM.ymin;
           H0.n = LM.ymax - LM.ymin + 1; H1.n = 0;
           nent = LM.nent;
 #pragma unroll
@@ -873,32 +884,29 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
       const TargetDesc& T = P.targets[D.target];
       tgt = D.target; tiles_x = T.tiles_x;
       t_h = T.h; t_w = T.w; t_by0 = T.band_y0; t_by1 = T.band_y1;
-      // Row-range sanity. A scanline at y >= h panics in the reference (target.rs:148,173);
-      // RF_MAX_ROWS bounds the work against absurd coordinates; a negative first row can only
-      // come from a viewport outside the target and is rejected (the reference would draw it at row 0).
+      // Row-range sanity. A scanline at y >= h panics in the reference (target.rs:148,173). Scanlines ABOVE the target (a
+      // viewport partly outside it) are drawn at row 0, one after the other, as `self.y as usize` does (raster.rs:106); a
+      // trapezoid half is bounded at 65,535 scanlines (record field width) — more than 32,767 rows above the largest target.
       uint32_t nrows = H0.n + H1.n;
       if (nrows != 0) {
         const float yfirst = H0.n ? H0.y : H1.y;
         const float ylast = yfirst + (float)(nrows - 1);
-        if (H0.n > RF_MAX_ROWS || H1.n > RF_MAX_ROWS || sat_u32(ylast) >= T.h) {
+        if (H0.n > 65535u || H1.n > 65535u || sat_u32(ylast) >= T.h) {
           atomicOr(&P.status->error, RF_ERRBIT_TARGET_OOB);
-          nrows = 0;
-        } else if (yfirst < 0.0f) {
-          atomicOr(&P.status->error, RF_ERRBIT_NEG_ROW);
           nrows = 0;
         }
         if (nrows == 0) H0.n = H1.n = 0;
         else {
           emit = true;
-          Y0 = sat_u32(yfirst);
-          // only tile rows inside this GPU's row band get bin entries
-          const uint32_t Ya = max(Y0, T.band_y0), Yb = min(Y0 + nrows, T.band_y1);
+          Yf0 = (int32_t)floorf(yfirst);  // row centres are k + 0.5; |yfirst| < 2^17 here
+          // framebuffer rows [max(Yf0, 0), max(Yf0 + nrows, 1)); only tile rows inside this GPU's row band get bin entries
+          const uint32_t Ya = max((uint32_t)max(Yf0, 0), T.band_y0), Yb = min((uint32_t)max(Yf0 + (int32_t)nrows, 1), T.band_y1);
           margin = 1.0f + (float)nrows * xabs * 1.2e-7f;
           if (Ya < Yb) {
             tr0 = Ya >> RF_TILE_SHIFT; tr1 = (Yb - 1) >> RF_TILE_SHIFT;
             for (uint32_t tr = tr0; tr <= tr1; tr++) {
               uint32_t ca, cb;
-              tile_row_cols<LT>(H0, H1, Y0, nrows, tr, margin, tiles_x, ca, cb);
+              tile_row_cols<LT>(H0, H1, Yf0, nrows, tr, margin, tiles_x, ca, cb);
               nent += cb - ca + 1;
             }
           } else {
@@ -951,7 +959,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
     {  // triangle record: into the warp's staging buffer (record = rank among the emitting lanes), or straight to global memory
       uint32_t* tr = SS::ON ? stg + __popc(emask & lt) * SS::TWP : P.tris + (size_t)tri_idx * TW;
       if (emit) {
-        *reinterpret_cast<uint4*>(tr) = make_uint4(key, d, sbase, Y0);
+        *reinterpret_cast<uint4*>(tr) = make_uint4(key, d, sbase, (uint32_t)Yf0);
         *reinterpret_cast<uint4*>(tr + 4) = make_uint4(H0.n, H1.n | (tgt << 16), eck0, eck1);
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
@@ -991,7 +999,7 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
         const TargetDesc& T = P.targets[tgt];
         for (uint32_t tr = tr0; tr <= tr1; tr++) {
           uint32_t ca, cb;
-          tile_row_cols<LT>(H0, H1, Y0, H0.n + H1.n, tr, margin, tiles_x, ca, cb);
+          tile_row_cols<LT>(H0, H1, Yf0, H0.n + H1.n, tr, margin, tiles_x, ca, cb);
           const uint32_t tbase = T.tile_base + tr * tiles_x;
           for (uint32_t c = ca; c <= cb; c++) {
             P.entries[eidx++] = make_uint4(tbase + c, key, tri_idx, 0u);

@@ -628,7 +628,9 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
       nb_tri = c0 + 32 + lane < cnt ? (uint32_t)P.bins[off + c0 + 32 + lane] : 0u;  // next chunk's triangles, one chunk ahead
       const bool t_small = t_have && (t_ref & RF_BIN_SMALL) != 0u;
       const uint32_t t_tri = t_ref & ~RF_BIN_SMALL;
-      uint32_t t_sbase = 0, t_Y0 = 0, t_nU = 0, t_nrows = 0, t_ra = 0, t_rows = 0, t_draw = 0;
+      // t_Y0: the first scanline's framebuffer row — signed for the other kind: scanlines above the target are drawn at row 0
+      // (rows_to_scanlines); t_j0: the first scanline of this tile (or slice), t_rows: how many
+      uint32_t t_sbase = 0, t_Y0 = 0, t_nU = 0, t_nrows = 0, t_j0 = 0, t_rows = 0, t_draw = 0;
       if (t_have) {
         if (t_small) {
           const uint4 h = __ldg(reinterpret_cast<const uint4*>(P.smalls + (size_t)t_tri * SR::W));  // key, draw, Y0, nU | nL << 16
@@ -640,11 +642,13 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
           t_draw = h0.y; t_sbase = h0.z; t_Y0 = h0.w; t_nU = h1.x;
           t_nrows = h1.x + (h1.y & 0xFFFFu);
         }
-        t_ra = max(t_Y0, py0 + r0);
-        const uint32_t rb = min(t_Y0 + t_nrows, py0 + r1);
-        t_rows = rb > t_ra ? rb - t_ra : 0u;
+        if (py0 + r1 > py0 + r0) {
+          uint32_t j1;
+          rows_to_scanlines((int32_t)t_Y0, t_nrows, py0 + r0, py0 + r1 - 1u, t_j0, j1);
+          t_rows = j1 - t_j0;
+        }
         if (RF_RASTER_PREFETCH && t_rows && !t_small) {  // this triangle's span records of the tile's rows: 24-64 bytes each
-          const char* sp0 = reinterpret_cast<const char*>(P.spans + (size_t)(t_sbase + (t_ra - t_Y0)) * SW);
+          const char* sp0 = reinterpret_cast<const char*>(P.spans + (size_t)(t_sbase + t_j0) * SW);
           prefetch_l2(sp0);
           if (t_rows * (SW * 4u) > 128u) prefetch_l2(sp0 + 128);
           if (t_rows * (SW * 4u) > 256u) prefetch_l2(sp0 + 256);
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
           const uint32_t* rec = P.smalls + (size_t)t_tri * SR::W + 4;
           uint32_t slot = (s_incl - s_rows) - sbase;
           uint32_t Y = t_Y0;
-          const uint32_t Ya = t_ra, Yb = t_ra + t_rows;
+          const uint32_t Ya = t_Y0 + t_j0, Yb = Ya + t_rows;  // a SMALL triangle lies inside the target: row = t_Y0 + scanline
 #pragma unroll 1
           for (uint32_t hh = 0; hh < 2u; hh++) {
             const uint32_t n = hh ? t_nrows - t_nU : t_nU;
@@ -771,23 +775,24 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
           }
           ot &= 31u;
           const uint32_t o_incl = __shfl_sync(FULL, t_incl, ot), o_rows = __shfl_sync(FULL, t_rows, ot);
-          const uint32_t o_ra = __shfl_sync(FULL, t_ra, ot), o_Y0 = __shfl_sync(FULL, t_Y0, ot);
+          const uint32_t o_j0 = __shfl_sync(FULL, t_j0, ot), o_Y0 = __shfl_sync(FULL, t_Y0, ot);
           const uint32_t o_sbase = __shfl_sync(FULL, t_sbase, ot), o_nU = __shfl_sync(FULL, t_nU, ot);
           const uint32_t o_tri = __shfl_sync(FULL, t_tri, ot), o_sincl = __shfl_sync(FULL, s_incl, ot);
           p.draw = __shfl_sync(FULL, t_draw, ot);
           p.small = ((small_mask >> ot) & 1u) != 0u;
           p.Y = 0; p.aux = 0;
           if (p.valid) {
-            const uint32_t rit = item - (o_incl - o_rows);  // row among the triangle's rows in this tile
-            p.Y = o_ra + rit;
-            const uint32_t hh = (p.Y - o_Y0) >= o_nU ? 1u : 0u;
+            const uint32_t rit = item - (o_incl - o_rows);  // scanline among the triangle's scanlines in this tile
+            const uint32_t j = o_j0 + rit;
+            p.Y = (uint32_t)max((int32_t)o_Y0 + (int32_t)j, 0);
+            const uint32_t hh = j >= o_nU ? 1u : 0u;
             if (p.small) {
               const uint32_t slot = (o_sincl - o_rows) - sbase + rit;
 #pragma unroll
               for (int i = 0; i < NL + 1; i++) p.w[i] = wsm.ldu(IQ0 + i * RF_ROWQ + slot);
               load_small_dv(o_tri, hh, p);
             } else {
-              const uint32_t* sp = P.spans + (size_t)(o_sbase + (p.Y - o_Y0)) * SW;
+              const uint32_t* sp = P.spans + (size_t)(o_sbase + j) * SW;
 #pragma unroll
               for (int q = 0; q < SW / 2; q++) {
                 const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp) + q);

@@ -4,6 +4,7 @@ pixel format, the shader catalogue, lines, object culling, depth sort and row ba
 CPU oracle on identical inputs. Bit-exact depth (coverage and depth-test winners), bit-exact colour except where a shader uses powf
 (±1 LSB), equal Stats counters. The adversarial families live in test_gpu_3_adversarial.py so that one failure there
 cannot hide these."""
+import dataclasses
 import os
 
 import numpy as np
@@ -302,3 +303,22 @@ def test_row_band_sharding_matches_oracle_band(device, oracle):
     band = lambda r: (r[0][100:260], r[1][100:260], r[2])
     assert_parity(band(got), band(want), name="band")
     assert not got[0][:100].any() and not got[0][260:].any(), "rows outside the band must stay untouched"
+
+
+@pytest.mark.parametrize("dtest", ["less", "none"])
+@pytest.mark.parametrize("shift", [40.0, 300.0])
+def test_scanlines_above_the_target_are_drawn_at_row_0(device, oracle, dtest, shift):
+    """`let y = self.y as usize` (raster.rs:106) saturates: with a viewport that reaches above the target, every scanline with a
+    negative y is drawn at row 0, one after the other, in scanline order. Large and small triangles, lit and colour lanes, with
+    and without a depth test (without one the last scanline drawn wins row 0); Stats count those fragments like any others."""
+    from retrofire_b200 import mathx as mx
+    w, h = 160, 96
+    for kind in ("color3", "lit"):
+        sc0 = scenes.random_soup(400, w, h, seed=21, lanes_kind=kind, big=(kind == "lit"))
+        ctx = rf.Context(face_cull=None, depth_test=rf.Ordering.Less if dtest == "less" else None)
+        vp = mx.viewport((0, h - shift), (w, -shift))   # the whole picture moved up by `shift` rows
+        draws = [dataclasses.replace(d, viewport=np.asarray(vp, dtype=f32).reshape(4, 4), face_cull=0, depth_test=rf.Ordering.Less if dtest == "less" else 0) for d in sc0.draws]
+        sc = scenes.Scene(f"above_{kind}_{dtest}_{int(shift)}", w, h, sc0.fmt, True, ctx, draws)
+        want = run_oracle(oracle, sc)
+        assert want[2].frags.i > 1000
+        assert_parity(run_gpu(device, sc), want, name=sc.name)
