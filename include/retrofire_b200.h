@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RF_ABI_VERSION 1
+#define RF_ABI_VERSION 2   /* 2: rf_mesh_create takes the primitive kind; RF_N_KERNELS 12 */
 #define RF_MAX_ATTR_LANES 8   /* varying lanes besides position (x,y,z) */
 #define RF_VS_UNIFORM_F32 32  /* e.g. two row-major 4x4 matrices */
 #define RF_FS_UNIFORM_F32 8
@@ -195,10 +195,12 @@ rf_status rf_texture_create(rf_ctx* ctx, uint32_t w, uint32_t h, uint32_t texel_
                             const void* data, size_t stride_elems, rf_texture** out);
 void rf_texture_destroy(rf_texture* t);
 
-/* ---- persistent geometry (Batch clones prims/verts per call, batch.rs:62-84; this avoids it) */
+/* ---- persistent geometry (Batch clones prims/verts per call, batch.rs:62-84; this avoids it).
+ * prim_kind: RF_PRIM_TRIS (indices = n_prims x 3) or RF_PRIM_EDGES (n_prims x 2); a draw that names the mesh
+ * with another rf_draw.prim_kind is rejected with RF_E_INVALID. */
 rf_status rf_mesh_create(rf_ctx* ctx, const float* verts, uint32_t n_verts,
                          uint32_t vert_stride_f32, const uint32_t* indices, uint32_t n_prims,
-                         rf_mesh** out);
+                         uint32_t prim_kind, rf_mesh** out);
 void rf_mesh_destroy(rf_mesh* m);
 
 /* ---- the hot path ------------------------------------------------------------------------ */

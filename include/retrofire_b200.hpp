@@ -129,6 +129,7 @@ struct Batch {
   Batch& viewport(const float m[16]) { std::memcpy(viewport_.data(), m, 64); return *this; }
   Batch& target(Target& t) { target_ = &t; return *this; }
   Batch& context(const Context& c) { ctx_ = &c; return *this; }
+  Batch clone() const { return *this; }  // #[derive(Clone)], batch.rs:31: crates.rs clones one configured batch per object
   void render() { re::render(prims.data(), (uint32_t)(prims.size() / 3), verts.data(), (uint32_t)(verts.size() / stride), stride, shader_, uniform_.data(), uniform_.size(), viewport_.data(), *target_, *ctx_); }
 };
 

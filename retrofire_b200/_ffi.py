@@ -100,7 +100,7 @@ SYMBOLS = {
     "rf_target_depth_devptr": (_P, [_P]),
     "rf_texture_create": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_size_t, C.POINTER(_P)]),
     "rf_texture_destroy": (None, [_P]),
-    "rf_mesh_create": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.POINTER(_P)]),
+    "rf_mesh_create": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "rf_mesh_destroy": (None, [_P]),
     "rf_render_many": (C.c_int, [_P, _P, _P, C.c_uint32]),
     "rf_ctx_peer_export": (C.c_int, [_P, _P, C.POINTER(_P)]),

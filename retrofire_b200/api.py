@@ -147,13 +147,14 @@ class Texture:
         self._dev = {}
 
     def handle(self, dev: "Device") -> int:
-        h = self._dev.get(id(dev))
+        h = self._dev.get(dev.token)  # one token per Device instance, never reused: a closed Device's handles cannot be hit again
         if h is None:
             out = C.c_void_p()
             dev._check(dev.lib.rf_texture_create(dev.h, self.w, self.h, self.fmt, self.data.ctypes.data, self.w, C.byref(out)))
             h = out.value
-            self._dev[id(dev)] = h
+            self._dev[dev.token] = h
             dev._textures.append(h)
+            dev._texture_objs.append(self)
         return h
 
 
@@ -169,9 +170,10 @@ def _flatten_uniform(uniform) -> np.ndarray:
     return out
 
 
-@dataclass
+@dataclass(frozen=True, eq=False)
 class DrawCall:
-    """Arguments of one `render()` call in ABI form. Keeps the numpy buffers alive."""
+    """Arguments of one `render()` call in ABI form. Keeps the numpy buffers alive. Immutable (the marshalled rf_draw is
+    memoised per Device): a changed uniform or array is a new DrawCall — `dataclasses.replace(d, uniform=...)`."""
     prims: np.ndarray      # (n,3) uint32
     verts: np.ndarray      # (n, stride) float32 : [x,y,z,a0..]
     shader: Shader
@@ -191,7 +193,8 @@ class DrawCall:
         # uniform of a two-matrix shader by one 4x4 matrix) is zero-padded here instead of being over-read there
         u = self.uniform
         if not (isinstance(u, np.ndarray) and u.dtype == np.float32 and u.size == _ffi.RF_VS_UNIFORM_F32 and u.flags.c_contiguous):
-            self.uniform = _flatten_uniform(u)
+            object.__setattr__(self, "uniform", _flatten_uniform(u))
+        object.__setattr__(self, "_cache", {})
 
     @staticmethod
     def make(prims, verts, shd: Shader, uniform, to_screen, ctx: Context = None, mesh: "Mesh" = None, edges: bool = False) -> "DrawCall":
@@ -208,7 +211,7 @@ class DrawCall:
 
     def cached_struct(self, key, texture_handle, mesh_handle) -> RfDraw:
         """to_struct() memoised per device: the marshalling costs more than the rf_render call."""
-        c = self.__dict__.setdefault("_cache", {})
+        c = self._cache
         st = c.get(key)
         if st is None:
             st = c[key] = self.to_struct(texture_handle, mesh_handle)
@@ -264,7 +267,9 @@ class Device:
         if st != _ffi.RF_OK:
             raise RetrofireError(st, "rf_ctx_create failed (is an sm_100 GPU visible?)")
         self.h = out.value
+        self.token = object()   # identity of this Device for the caches of Texture / DrawCall (id() values are reused)
         self._textures = []
+        self._texture_objs = []
         self._targets = []
         self._meshes = []
         self._pinned = []
@@ -283,6 +288,9 @@ class Device:
                 m._destroy()
             for t in self._textures:
                 self.lib.rf_texture_destroy(t)
+            for tx in self._texture_objs:
+                tx._dev.pop(self.token, None)
+            self._many.clear()
             self.lib.rf_ctx_destroy(self.h)
             for p in self._pinned:
                 self.lib.rf_host_free(p)
@@ -359,13 +367,13 @@ class Device:
     def framebuf(self, w: int, h: int, fmt: int = _ffi.FMT_RGBA8888, depth: bool = True) -> "Framebuf":
         return Framebuf(self, w, h, fmt, depth)
 
-    def mesh(self, prims, verts) -> "Mesh":
-        return Mesh(self, prims, verts)
+    def mesh(self, prims, verts, edges: bool = False) -> "Mesh":
+        return Mesh(self, prims, verts, edges)
 
     # -- the hot path
     def render(self, call: DrawCall, target: "Framebuf", want_stats: bool = False) -> Optional[Stats]:
         tex = call.shader.texture.handle(self) if call.shader.texture is not None else None
-        d = call.cached_struct(id(self), tex, call.mesh.h if call.mesh is not None else None)
+        d = call.cached_struct(self.token, tex, call.mesh.h if call.mesh is not None else None)
         if want_stats:
             s = RfStats()
             self._check(self.lib.rf_render(self.h, target.h, C.byref(d), C.byref(s)))
@@ -401,14 +409,14 @@ class Device:
 class Mesh:
     """Persistent device copy of (prims, verts) — avoids Batch's per-call clones (batch.rs:62-84)."""
 
-    def __init__(self, dev: Device, prims, verts):
+    def __init__(self, dev: Device, prims, verts, edges: bool = False):
         self.dev = dev
-        prims = np.ascontiguousarray(np.asarray(prims, dtype=np.uint32).reshape(-1, 3))
+        prims = np.ascontiguousarray(np.asarray(prims, dtype=np.uint32).reshape(-1, 2 if edges else 3))
         verts = np.ascontiguousarray(np.asarray(verts, dtype=np.float32))
         self.n_prims, self.n_verts, self.stride = prims.shape[0], verts.shape[0], verts.shape[1]
         out = C.c_void_p()
         dev._check(dev.lib.rf_mesh_create(dev.h, verts.ctypes.data, self.n_verts, self.stride, prims.ctypes.data,
-                                          self.n_prims, C.byref(out)))
+                                          self.n_prims, _ffi.PRIM_EDGES if edges else _ffi.PRIM_TRIS, C.byref(out)))
         self.h = out.value
         dev._meshes.append(self)
 

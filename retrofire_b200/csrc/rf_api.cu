@@ -136,7 +136,7 @@ struct rf_mesh {
   rf_ctx* ctx;
   float* d_verts;
   uint32_t* d_idx;
-  uint32_t n_verts, stride, n_prims;
+  uint32_t n_verts, stride, n_prims, prim_kind;
 };
 
 struct rf_ctx {
@@ -179,6 +179,12 @@ struct rf_ctx {
   uint64_t replays = 0;        // passes re-launched after an arena overflow
   DevBuf bounce;               // upload/download staging on the device
   PinnedBuf h_bounce;
+
+  // Asynchronous downloads taken since the last synchronisation: {target, host, stride, slot of the pass flushed just before}.
+  // A pass replayed after arena growth re-issues the downloads that followed it, so the host buffer never keeps the frame of
+  // a poisoned (no-op) pass.
+  struct PendingDl { rf_target* t; void* host; size_t stride; int slot; };
+  std::vector<PendingDl> pending_dl;
 
   rf_stats accum{};
   rf_stats last_draw{};        // stats of the last draw of the last validated pass
@@ -673,6 +679,17 @@ void reset_slot(PassSlot& s) {
   s.direct_async = false;
 }
 
+// The D2H copy of rf_target_download_color_async: on the copy stream, after everything queued so far on the ctx stream.
+rf_status issue_download(rf_ctx* c, rf_target* t, void* host, size_t stride) {
+  RF_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
+  RF_CUDA(c, cudaStreamWaitEvent(c->copy, c->ev_copy, 0));
+  RF_CUDA(c, cudaMemcpy2DAsync(host, stride * 4, t->d_color, (size_t)t->w * 4, (size_t)t->w * 4, t->h, cudaMemcpyDeviceToHost, c->copy));
+  if (!t->dl_done) RF_CUDA(c, cudaEventCreateWithFlags(&t->dl_done, cudaEventDisableTiming));
+  RF_CUDA(c, cudaEventRecord(t->dl_done, c->copy));
+  t->dl_pending = true;
+  return RF_OK;
+}
+
 // Wait for every pass in flight, replay overflowed ones with larger arenas, fold Stats.
 rf_status validate_all(rf_ctx* c) {
   rf_status result = RF_OK;
@@ -703,7 +720,11 @@ rf_status validate_all(rf_ctx* c) {
       RF_CUDA(c, cudaStreamSynchronize(c->stream));
       std::vector<int> replay = c->flight;
       c->replays += replay.size();
-      for (int r : replay) { rf_status st = launch_pass(c, r); if (st) return st; }
+      for (int r : replay) {
+        rf_status st = launch_pass(c, r);
+        if (st) return st;
+        for (const rf_ctx::PendingDl& d : c->pending_dl) if (d.slot == r) { st = issue_download(c, d.t, d.host, d.stride); if (st) return st; }
+      }
       continue;  // re-validate the same front slot
     }
     float ms = 0.f;
@@ -745,6 +766,7 @@ rf_status validate_all(rf_ctx* c) {
       c->accum.time_ns += ns;
     }
     reset_slot(s);
+    c->pending_dl.erase(std::remove_if(c->pending_dl.begin(), c->pending_dl.end(), [&](const rf_ctx::PendingDl& d) { return d.slot == si; }), c->pending_dl.end());
     c->flight.erase(c->flight.begin());
   }
   return result;
@@ -812,6 +834,7 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
   if (d->mesh) {
     if (d->verts || d->indices) return fail(c, RF_E_INVALID, "give either mesh or host pointers");
     if (d->mesh->stride < 3 + d->n_attr_lanes) return fail(c, RF_E_INVALID, "mesh stride too small");
+    if (d->mesh->prim_kind != d->prim_kind) return fail(c, RF_E_INVALID, "rf_draw.prim_kind differs from the mesh's");
     D.verts = d->mesh->d_verts; D.indices = d->mesh->d_idx;
     D.vstride = d->mesh->stride; D.n_verts = d->mesh->n_verts; D.n_prims = d->mesh->n_prims;
     q.verts_off = q.idx_off = SIZE_MAX; q.direct = false;
@@ -1146,18 +1169,19 @@ void rf_texture_destroy(rf_texture* t) {
   delete t;
 }
 
-rf_status rf_mesh_create(rf_ctx* c, const float* verts, uint32_t n_verts, uint32_t stride, const uint32_t* indices, uint32_t n_prims, rf_mesh** out) {
-  if (!c || !out || !verts || !indices || stride < 3) return fail(c, RF_E_INVALID, "bad mesh arguments");
+rf_status rf_mesh_create(rf_ctx* c, const float* verts, uint32_t n_verts, uint32_t stride, const uint32_t* indices, uint32_t n_prims, uint32_t prim_kind, rf_mesh** out) {
+  if (!c || !out || !verts || !indices || stride < 3 || prim_kind > RF_PRIM_EDGES) return fail(c, RF_E_INVALID, "bad mesh arguments");
   cudaSetDevice(c->device);
-  rf_mesh* m = new rf_mesh{c, nullptr, nullptr, n_verts, stride, n_prims};
-  const size_t vb = std::max<size_t>((size_t)n_verts * stride * 4, 16), ib = std::max<size_t>((size_t)n_prims * 12, 16);
+  rf_mesh* m = new rf_mesh{c, nullptr, nullptr, n_verts, stride, n_prims, prim_kind};
+  const size_t arity = prim_kind == RF_PRIM_EDGES ? 2 : 3;
+  const size_t vb = std::max<size_t>((size_t)n_verts * stride * 4, 16), ib = std::max<size_t>((size_t)n_prims * arity * 4, 16);
   if (cudaMalloc(&m->d_verts, vb) != cudaSuccess || cudaMalloc(&m->d_idx, ib) != cudaSuccess) {
     if (m->d_verts) cudaFree(m->d_verts);
     delete m;
     return fail(c, RF_E_NOMEM, "mesh");
   }
   RF_CUDA(c, cudaMemcpyAsync(m->d_verts, verts, (size_t)n_verts * stride * 4, cudaMemcpyHostToDevice, c->stream));
-  RF_CUDA(c, cudaMemcpyAsync(m->d_idx, indices, (size_t)n_prims * 12, cudaMemcpyHostToDevice, c->stream));
+  RF_CUDA(c, cudaMemcpyAsync(m->d_idx, indices, (size_t)n_prims * arity * 4, cudaMemcpyHostToDevice, c->stream));
   RF_CUDA(c, cudaStreamSynchronize(c->stream));
   *out = m;
   return RF_OK;
@@ -1248,13 +1272,9 @@ rf_status rf_target_download_color_async(rf_ctx* c, rf_target* t, void* host, si
   rf_status st = flush_impl(c);
   if (st) return st;
   // the copy runs on its own stream, after everything queued so far, and overlaps later passes
-  RF_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
-  RF_CUDA(c, cudaStreamWaitEvent(c->copy, c->ev_copy, 0));
-  RF_CUDA(c, cudaMemcpy2DAsync(host, stride * 4, t->d_color, (size_t)t->w * 4, (size_t)t->w * 4, t->h, cudaMemcpyDeviceToHost, c->copy));
-  if (!t->dl_done) RF_CUDA(c, cudaEventCreateWithFlags(&t->dl_done, cudaEventDisableTiming));
-  RF_CUDA(c, cudaEventRecord(t->dl_done, c->copy));
-  t->dl_pending = true;
-  return RF_OK;
+  const int last = c->flight.empty() ? -1 : c->flight.back();
+  if (last >= 0) c->pending_dl.push_back(rf_ctx::PendingDl{t, host, stride, last});  // re-issued if that pass has to be replayed
+  return issue_download(c, t, host, stride);
 }
 
 rf_status rf_ctx_profile(rf_ctx* c, int enable) {

@@ -1,4 +1,4 @@
-//! Raw bindings, one item per declaration of `include/retrofire_b200.h` (ABI version 1).
+//! Raw bindings, one item per declaration of `include/retrofire_b200.h` (ABI version 2).
 //! NOT compiled in the build container (no cargo/rustc there); kept in lock-step with the header.
 #![allow(non_camel_case_types)]
 use core::ffi::{c_char, c_int, c_void};
@@ -6,7 +6,46 @@ use core::ffi::{c_char, c_int, c_void};
 pub const RF_MAX_ATTR_LANES: usize = 8;
 pub const RF_VS_UNIFORM_F32: usize = 32;
 pub const RF_FS_UNIFORM_F32: usize = 8;
-pub const RF_N_KERNELS: usize = 11;
+pub const RF_N_KERNELS: usize = 12;
+pub const RF_ABI_VERSION: u32 = 2;
+
+// rf_vs_id / rf_fs_id: the shader catalogue
+pub const RF_VS_MVP: u32 = 0;
+pub const RF_VS_MVP_LINEARIZE: u32 = 1;
+pub const RF_VS_SOLIDS: u32 = 2;
+pub const RF_VS_SPRITE: u32 = 3;
+pub const RF_FS_COLOR3F: u32 = 0;
+pub const RF_FS_COLOR3F_SRGB: u32 = 1;
+pub const RF_FS_COLOR4F: u32 = 2;
+pub const RF_FS_CHECKER: u32 = 3;
+pub const RF_FS_TEX_CLAMP_LIT: u32 = 4;
+pub const RF_FS_TEX_CLAMP: u32 = 5;
+pub const RF_FS_TEX_REPEAT_POT: u32 = 6;
+pub const RF_FS_SPRITE_DISC: u32 = 7;
+pub const RF_FS_NORMAL_VIS: u32 = 8;
+// rf_pixel_fmt: the colour layout of a TARGET (rf_target_create)
+pub const RF_FMT_RGBA8888: u32 = 0;
+pub const RF_FMT_XRGB8888: u32 = 1;
+pub const RF_FMT_ARGB8888: u32 = 2;
+pub const RF_FMT_BGRA8888: u32 = 3;
+pub const RF_FMT_RGB888: u32 = 4;
+pub const RF_FMT_RGB565: u32 = 5;
+pub const RF_FMT_RGBA4444: u32 = 6;
+// rf_texel_fmt: the texel layout of a TEXTURE (rf_texture_create) — a different enumeration from rf_pixel_fmt
+pub const RF_TEXEL_RGB888: u32 = 0;
+pub const RF_TEXEL_RGBA8888: u32 = 1;
+pub const RF_PRIM_TRIS: u8 = 0;
+pub const RF_PRIM_EDGES: u8 = 1;
+pub const RF_SORT_NONE: u8 = 0;
+pub const RF_SORT_FRONT_TO_BACK: u8 = 1;
+pub const RF_SORT_BACK_TO_FRONT: u8 = 2;
+pub const RF_CULL_NONE: u8 = 0;
+pub const RF_CULL_BACK: u8 = 1;
+pub const RF_CULL_FRONT: u8 = 2;
+pub const RF_DEPTH_NONE: u8 = 0;
+pub const RF_DEPTH_LESS: u8 = 1;
+pub const RF_DEPTH_EQUAL: u8 = 2;
+pub const RF_DEPTH_GREATER: u8 = 3;
 
 #[repr(C)] pub struct rf_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct rf_target { _p: [u8; 0] }
@@ -84,7 +123,7 @@ unsafe extern "C" {
     pub fn rf_target_depth_devptr(t: *mut rf_target) -> *mut c_void;
     pub fn rf_texture_create(ctx: *mut rf_ctx, w: u32, h: u32, texel_fmt: u32, data: *const c_void, stride_elems: usize, out: *mut *mut rf_texture) -> rf_status;
     pub fn rf_texture_destroy(t: *mut rf_texture);
-    pub fn rf_mesh_create(ctx: *mut rf_ctx, verts: *const f32, n_verts: u32, vert_stride_f32: u32, indices: *const u32, n_prims: u32, out: *mut *mut rf_mesh) -> rf_status;
+    pub fn rf_mesh_create(ctx: *mut rf_ctx, verts: *const f32, n_verts: u32, vert_stride_f32: u32, indices: *const u32, n_prims: u32, prim_kind: u32, out: *mut *mut rf_mesh) -> rf_status;
     pub fn rf_mesh_destroy(m: *mut rf_mesh);
     pub fn rf_render(ctx: *mut rf_ctx, target: *mut rf_target, draw: *const rf_draw, stats_out: *mut rf_stats) -> rf_status;
     pub fn rf_render_frames(ctx: *mut rf_ctx, targets: *const *mut rf_target, n_frames: u32, draw: *const rf_draw, vs_uniforms: *const f32) -> rf_status;

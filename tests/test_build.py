@@ -20,7 +20,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_ffi.SYMBOLS), declared ^ set(_ffi.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.rf_abi_version() == 1
+    assert lib.rf_abi_version() == 2
 
 
 def test_rust_sys_crate_and_ctypes_structs_follow_the_header():
@@ -124,3 +124,14 @@ def test_cpp_host_mirror_renders_hello_tri(tmp_path):
     exe = _compile_cpp_smoke(str(tmp_path / "cpp_host_smoke"))
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/retrofire_b200.h compiles as C99 with -pedantic -Werror (tests/c_header_check.c): what cgo, the Rust -sys crate or a
+    C host bind is a C header, not a C++ one."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = tmp_path / "c_header_check.o"
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(os.path.dirname(here), "include"), "-c",
+                        os.path.join(here, "c_header_check.c"), "-o", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -1,12 +1,13 @@
 """GPU parity, part 2: the C-ABI surface around render() — queued passes, rf_render_many, targets of different sizes, page-locked
 geometry, strided upload/download, asynchronous downloads, profiling entry points, error statuses."""
+import dataclasses
 import os
 
 import numpy as np
 import pytest
 
 import retrofire_b200 as rf
-from retrofire_b200 import scenes
+from retrofire_b200 import _ffi, scenes
 from tests.parity import assert_parity, depth_equal, run_gpu, run_oracle
 
 f32 = np.float32
@@ -309,3 +310,36 @@ def test_batch_builder_mirrors_render(device, oracle):
     assert got.prims.i == 2 * want[2].prims.i and got.frags.i == 2 * want[2].frags.i
     assert np.array_equal(fb.download_color(), want[0]) and depth_equal(fb.download_depth(), want[1])
     fb._destroy(); device._targets.remove(fb)
+
+
+def test_resident_mesh_remembers_its_primitive_kind(device, oracle):
+    """rf_mesh_create records RF_PRIM_TRIS / RF_PRIM_EDGES (ABI 2): an Edge mesh draws like host-pointer edges, and naming a mesh
+    with the other rf_draw.prim_kind is RF_E_INVALID instead of reinterpreting the index list."""
+    sc = scenes.random_lines(300, 320, 200, seed=5, lanes_kind="color3")
+    d = sc.draws[0]
+    want = run_oracle(oracle, sc)
+    m = device.mesh(d.prims, d.verts, edges=True)
+    res = dataclasses.replace(d, mesh=m)
+    got = run_gpu(device, dataclasses.replace(sc, draws=[res]))
+    assert_parity(got, want, name="edge mesh")
+    fb = device.framebuf(sc.w, sc.h, sc.fmt, sc.has_depth)
+    with pytest.raises(rf.RetrofireError) as e:
+        device.render(dataclasses.replace(res, prim_kind=_ffi.PRIM_TRIS), fb)
+    assert e.value.status == _ffi.RF_E_INVALID
+    tri = scenes.random_soup(100, 320, 200, seed=3, lanes_kind="color3", big=False).draws[0]
+    mt = device.mesh(tri.prims, tri.verts)
+    with pytest.raises(rf.RetrofireError) as e:
+        device.render(dataclasses.replace(tri, mesh=mt, prim_kind=_ffi.PRIM_EDGES), fb)
+    assert e.value.status == _ffi.RF_E_INVALID
+    device.sync()
+    fb._destroy(); device._targets.remove(fb)
+
+
+def test_closed_device_handles_are_not_reused(oracle):
+    """Texture / DrawCall caches are keyed on the Device instance, not on id(): a second Device created after the first was
+    closed must upload its own texture and marshal its own rf_draw (use-after-free through a recycled id)."""
+    sc = scenes.textured_quad()
+    want = run_oracle(oracle, sc)
+    for _ in range(3):
+        with rf.Device(0) as dev:
+            assert_parity(run_gpu(dev, sc), want, name=sc.name)
