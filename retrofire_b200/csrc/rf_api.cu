@@ -355,6 +355,13 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     k_setup<LT><<<sm * RF_SETUP_GRID_PER_SM, 128, 0, gs>>>(P);
     cudaEventRecord(s.ev_fork, gs);
     cudaStreamWaitEvent(sd, s.ev_fork, 0);
+    // The untouched tiles of first-touch-cleared targets are known once k_setup has counted the bins: they are filled on the
+    // ctx stream (after the previous rasteriser of the same targets) WHILE the bins are sorted — a bandwidth-bound kernel next
+    // to latency-bound ones — and not next to k_raster, which it slowed by 14 % (profiles/r02_ab_clear_placement.txt).
+    if (s.first_touch) {
+      cudaStreamWaitEvent(st, s.ev_fork, 0);
+      k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
+    }
     k_bin_alloc<<<blocks(s.n_tiles, 256, 8), 256, 0, sd>>>(P);
     k_bin_scatter<<<sm * 4, 256, 0, sd>>>(P);
     k_bin_sort_warp<<<sm * RF_SORT_GRID_PER_SM, RF_SORT_WARPS * 32, 0, sd>>>(P);
@@ -366,21 +373,11 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     cudaStreamWaitEvent(gs, s.ev_join, 0);
     cudaEventRecord(s.ev_geo, gs);
     cudaStreamWaitEvent(st, s.ev_geo, 0);
-    // the untouched tiles of first-touch-cleared targets: next to k_raster (disjoint tiles; after everything earlier on the ctx
-    // stream, i.e. the previous rasteriser of the same targets), or — with peers — before the barrier
-    if (s.first_touch && s.peer) k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
-    if (s.first_touch && !s.peer) {
-      cudaEventRecord(c->ev_pre, st);
-      cudaStreamWaitEvent(c->side2, c->ev_pre, 0);
-      k_clear_untouched<<<clear_blocks, 256, 0, c->side2>>>(P);
-      cudaEventRecord(s.ev_join2, c->side2);
-    }
     if (s.peer) { k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch1); s.n_launches++; }  // every peer has cleared its copy of the frame
     if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS - 1], st);
     if (s.peer) k_raster<LT, true><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
     else k_raster<LT, false><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
     if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS], st);
-    if (s.first_touch && !s.peer) cudaStreamWaitEvent(st, s.ev_join2, 0);
     if (s.peer) { k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch2); s.n_launches++; }  // every peer's stores into this GPU have landed
   }
   s.n_launches += RF_N_KERNELS - (s.first_touch ? 0 : 1);

@@ -157,6 +157,49 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return __shfl_xor_sync(0xFFFFFFFFu, v, m);
 }
 
+// Bitonic sort of R * 32 keys held R per lane (element r * 32 + lane in register r): the exchanges at distance < 32 are
+// shuffles, those at distance >= 32 stay inside the lane. No shared memory, no bank conflicts, no warp barriers — the
+// shared-memory version spent 34 % of its stall samples on conflicting accesses (profiles/r02_s5_sort_lines.txt).
+template <int R>
+__device__ __forceinline__ void warp_bitonic_regs(unsigned long long (&v)[R], uint32_t lane) {
+#pragma unroll
+  for (int k = 2; k <= R * 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const int q = r ^ (j >> 5);
+          if (q > r) {
+            const bool up = ((r << 5) & k) == 0;
+            const unsigned long long a = v[r], b = v[q];
+            if ((a > b) == up) { v[r] = b; v[q] = a; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const unsigned long long o = shfl_xor_u64(v[r], j);
+          const bool up = (((r << 5) | lane) & k) == 0, lower = (lane & j) == 0;
+          v[r] = (up == lower) ? (o < v[r] ? o : v[r]) : (o > v[r] ? o : v[r]);
+        }
+      }
+    }
+  }
+}
+template <int R>
+__device__ __forceinline__ void sort_bin_regs(unsigned long long* bin, uint32_t cnt, uint32_t lane) {
+  unsigned long long v[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) v[r] = (uint32_t)(r * 32) + lane < cnt ? bin[r * 32 + lane] : ~0ull;
+  warp_bitonic_regs<R>(v, lane);
+#pragma unroll
+  for (int r = 0; r < R; r++) if ((uint32_t)(r * 32) + lane < cnt) bin[r * 32 + lane] = v[r];
+}
+
+#ifndef RF_SORT_REGS
+#define RF_SORT_REGS 1   // bins of 33..256 entries are sorted in registers
+#endif
 #define RF_SORT_WARPS 4
 __global__ void __launch_bounds__(RF_SORT_WARPS * 32) k_bin_sort_warp(PassParams P) {
   __shared__ unsigned long long sk_all[RF_SORT_WARPS][RF_SORT_SMALL];
@@ -183,6 +226,12 @@ __global__ void __launch_bounds__(RF_SORT_WARPS * 32) k_bin_sort_warp(PassParams
         }
       }
       if (lane < cnt) bin[lane] = v;
+      continue;
+    }
+    if (RF_SORT_REGS && cnt <= 256) {
+      if (cnt <= 64) sort_bin_regs<2>(bin, cnt, lane);
+      else if (cnt <= 128) sort_bin_regs<4>(bin, cnt, lane);
+      else sort_bin_regs<8>(bin, cnt, lane);
       continue;
     }
     uint32_t n2 = 64;
