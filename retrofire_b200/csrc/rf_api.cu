@@ -105,6 +105,7 @@ struct PassSlot {
   uint32_t n_launches = 0;
   uint32_t seq = 0;          // sequence number of the current launch of this pass
   cudaEvent_t ev_geo = nullptr;  // geometry + binning of the pass complete (geo stream)
+  cudaEvent_t ev_geo_t = nullptr;  // the same instant as a timing event (RF_DEBUG_PASS timeline)
   bool first_touch = false;  // some target of the pass is cleared by k_raster / k_clear_untouched (TargetDesc::clear_flags)
   bool peer = false;         // some target of the pass replicates its colour stores into peer GPUs (rf_peer.cuh)
   bool epochs_set = false;   // barrier epochs are assigned at the first launch and reused by replays
@@ -167,6 +168,7 @@ struct rf_ctx {
   cudaStream_t geo = nullptr;    // vertex / assembly / setup / span chain of a pass
   cudaStream_t side2 = nullptr;  // k_clear_untouched next to k_raster
   cudaEvent_t ev_pre = nullptr;
+  cudaEvent_t ev_base = nullptr;  // RF_DEBUG_PASS: origin of the printed timeline
   // capacities: spans/tris/ckpts in 32-bit WORDS (record width depends on the pass's lane count),
   // entries and long spans in records
   size_t capw_stris = 0, capw_smalls = 0, capw_spans = 0, capw_tris = 0, capw_ckpts = 0, capw_ecks = 0, cap_entries = 0, cap_long = 0, cap_chunks = 0, cap_tall = 0;
@@ -299,6 +301,9 @@ void launch_order(rf_ctx* c, PassSlot& s, const PassParams& P, uint32_t QW, cuda
 #ifndef RF_RASTER_GRID_PER_SM
 #define RF_RASTER_GRID_PER_SM 0   // 0: the occupancy limit (RasterOcc)
 #endif
+#ifndef RF_CLEAR_PLACE
+#define RF_CLEAR_PLACE 1
+#endif
 #ifndef RF_ASSEMBLE_THREADS
 #define RF_ASSEMBLE_THREADS 128
 #endif
@@ -355,10 +360,11 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     k_setup<LT><<<sm * RF_SETUP_GRID_PER_SM, 128, 0, gs>>>(P);
     cudaEventRecord(s.ev_fork, gs);
     cudaStreamWaitEvent(sd, s.ev_fork, 0);
-    // The untouched tiles of first-touch-cleared targets are known once k_setup has counted the bins: they are filled on the
-    // ctx stream (after the previous rasteriser of the same targets) WHILE the bins are sorted — a bandwidth-bound kernel next
-    // to latency-bound ones — and not next to k_raster, which it slowed by 14 % (profiles/r02_ab_clear_placement.txt).
-    if (s.first_touch) {
+    // The untouched tiles of first-touch-cleared targets are known once k_setup has counted the bins. RF_CLEAR_PLACE 1: they
+    // are filled on the ctx stream while the bins are sorted; 2: after k_raster, i.e. next to the geometry stage of the NEXT
+    // pass (latency-bound kernels on the geo stream) — never next to k_raster itself, which that slowed by 14 %
+    // (profiles/r02_ab_clear_placement.txt). With peers the clear must precede the cross-GPU barrier: always placement 1.
+    if (s.first_touch && (RF_CLEAR_PLACE == 1 || s.peer)) {
       cudaStreamWaitEvent(st, s.ev_fork, 0);
       k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
     }
@@ -372,12 +378,14 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     k_ckpt<LT><<<sm * 8, 256, 0, gs>>>(P);
     cudaStreamWaitEvent(gs, s.ev_join, 0);
     cudaEventRecord(s.ev_geo, gs);
+    if (s.ev_geo_t) cudaEventRecord(s.ev_geo_t, gs);
     cudaStreamWaitEvent(st, s.ev_geo, 0);
     if (s.peer) { k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch1); s.n_launches++; }  // every peer has cleared its copy of the frame
     if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS - 1], st);
     if (s.peer) k_raster<LT, true><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
     else k_raster<LT, false><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
     if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS], st);
+    if (s.first_touch && RF_CLEAR_PLACE == 2 && !s.peer) k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
     if (s.peer) { k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch2); s.n_launches++; }  // every peer's stores into this GPU have landed
   }
   s.n_launches += RF_N_KERNELS - (s.first_touch ? 0 : 1);
@@ -577,6 +585,10 @@ rf_status launch_pass(rf_ctx* c, int si) {
   for (rf_target* t : s.targets) if (t->dl_pending) { RF_CUDA(c, cudaStreamWaitEvent(st, t->dl_done, 0)); t->dl_pending = false; }
   for (const QueuedClear& qc : s.clears) if (qc.target->dl_pending) { RF_CUDA(c, cudaStreamWaitEvent(st, qc.target->dl_done, 0)); qc.target->dl_pending = false; }
   if (c->set_busy[set] && gs != st) RF_CUDA(c, cudaStreamWaitEvent(gs, c->ev_set_done[set], 0));
+  if (getenv("RF_DEBUG_PASS")) {
+    if (!c->ev_base) { cudaEventCreate(&c->ev_base); cudaEventRecord(c->ev_base, st); }
+    if (!s.ev_geo_t) cudaEventCreate(&s.ev_geo_t);
+  }
   RF_CUDA(c, cudaEventRecord(s.ev_start, gs));
   s.n_launches = 0;
   RF_CUDA(c, cudaMemcpyAsync(s.d_table.p, tb, coff + ncl * sizeof(ClearDesc), cudaMemcpyHostToDevice, gs));
@@ -688,9 +700,11 @@ rf_status issue_download(rf_ctx* c, rf_target* t, void* host, size_t stride) {
 }
 
 // Wait for every pass in flight, replay overflowed ones with larger arenas, fold Stats.
-rf_status validate_all(rf_ctx* c) {
+// `only_oldest`: stop once the oldest pass has been validated (the others stay in flight: the pipeline is not drained).
+rf_status validate_all(rf_ctx* c, bool only_oldest = false) {
   rf_status result = RF_OK;
-  while (!c->flight.empty()) {
+  const size_t stop_at = only_oldest && !c->flight.empty() ? c->flight.size() - 1 : 0;
+  while (c->flight.size() > stop_at) {
     const int si = c->flight.front();
     PassSlot& s = c->slots[si];
     RF_CUDA(c, cudaEventSynchronize(s.ev_stop));
@@ -699,6 +713,12 @@ rf_status validate_all(rf_ctx* c) {
       fprintf(stderr, "[rf pass] draws %zu stris %llu small %llu tris %llu spans %llu entries %llu chunks %llu long %llu ckpts %llu work %u max_bin %u overflow %u error %u\n",
               s.draws.size(), ps.stris_needed.v, ps.small_needed.v, ps.tris_needed.v, ps.spans_needed.v, ps.entries_needed.v, ps.chunks_needed.v,
               ps.long_needed.v, ps.ckpts_needed.v, ps.n_work, ps.max_bin, ps.overflow, ps.error);
+    if (getenv("RF_DEBUG_PASS") && c->ev_base && s.ev_geo_t && !s.draws.empty()) {
+      float a = 0, b = 0, r0 = 0, r1 = 0, e = 0;
+      cudaEventElapsedTime(&a, c->ev_base, s.ev_start); cudaEventElapsedTime(&b, c->ev_base, s.ev_geo_t); cudaEventElapsedTime(&e, c->ev_base, s.ev_stop);
+      if (s.profiled == 1) { cudaEventElapsedTime(&r0, c->ev_base, s.ev_k[RF_N_KERNELS - 1]); cudaEventElapsedTime(&r1, c->ev_base, s.ev_k[RF_N_KERNELS]); }
+      fprintf(stderr, "[rf timeline] seq %u: geometry %.3f .. %.3f ms, raster %.3f .. %.3f, done %.3f\n", s.seq, a, b, r0, r1, e);
+    }
     if (ps.overflow) {
       // Every later pass in flight was a no-op (device poison). Grow and replay from here, in order.
       { rf_status st = wait_idle(c); if (st) return st; }
@@ -780,7 +800,7 @@ rf_status flush_impl(rf_ctx* c) {
   int next = -1;
   for (int k = 0; k < kSlots; k++) if (!c->slots[k].in_flight && c->slots[k].draws.empty() && c->slots[k].clears.empty()) { next = k; break; }
   if (next < 0) {
-    st = validate_all(c);
+    st = validate_all(c, true);
     next = 0;
     for (int k = 0; k < kSlots; k++) if (!c->slots[k].in_flight) { next = k; break; }
   }

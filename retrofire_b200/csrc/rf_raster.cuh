@@ -198,8 +198,9 @@ __device__ __forceinline__ void sort_bin_regs(unsigned long long* bin, uint32_t 
 }
 
 #ifndef RF_SORT_REGS
-#define RF_SORT_REGS 1   // bins of 33..256 entries are sorted in registers
-#endif
+#define RF_SORT_REGS 0   // 1: bins of 33..256 entries are sorted in registers — measured +3 % on the bunny step (78 registers, three
+#endif                  // unrolled networks in the instruction cache), profiles/r02_ab_clear_placement.txt: off
+
 #define RF_SORT_WARPS 4
 __global__ void __launch_bounds__(RF_SORT_WARPS * 32) k_bin_sort_warp(PassParams P) {
   __shared__ unsigned long long sk_all[RF_SORT_WARPS][RF_SORT_SMALL];
