@@ -449,6 +449,8 @@ struct WarpSmem {
   __device__ __forceinline__ void stf(uint32_t w, float v) const { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + w * 4u), "f"(v) : "memory"); }
   __device__ __forceinline__ void stu(uint32_t w, uint32_t v) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + w * 4u), "r"(v) : "memory"); }
   __device__ __forceinline__ void oru(uint32_t w, uint32_t v) const { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a + w * 4u), "r"(v) : "memory"); }
+  __device__ __forceinline__ void stb(uint32_t b, uint32_t v) const { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a + b), "r"(v) : "memory"); }  // byte offset
+  __device__ __forceinline__ uint32_t ldb(uint32_t b) const { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a + b) : "memory"); return v; }
 #else
   float* p;
   __device__ __forceinline__ explicit WarpSmem(const void* q) : p(reinterpret_cast<float*>(const_cast<void*>(q))) {}
@@ -457,6 +459,8 @@ struct WarpSmem {
   __device__ __forceinline__ void stf(uint32_t w, float v) const { p[w] = v; }
   __device__ __forceinline__ void stu(uint32_t w, uint32_t v) const { reinterpret_cast<uint32_t*>(p)[w] = v; }
   __device__ __forceinline__ void oru(uint32_t w, uint32_t v) const { atomicOr(reinterpret_cast<uint32_t*>(p) + w, v); }
+  __device__ __forceinline__ void stb(uint32_t b, uint32_t v) const { reinterpret_cast<uint8_t*>(p)[b] = (uint8_t)v; }
+  __device__ __forceinline__ uint32_t ldb(uint32_t b) const { return reinterpret_cast<const uint8_t*>(p)[b]; }
 #endif
 };
 
@@ -528,20 +532,17 @@ template <int LT> struct RasterTune {
   static constexpr uint32_t MIN_AVG = LT == 3 ? RF_SPAN_MODE_MIN_AVG_3 : RF_SPAN_MODE_MIN_AVG_5;
 };
 
-// Row queue (shared memory, per warp): the edge state {L[2+LT], R} of every scanline of the round's SMALL triangles that
-// lies in this tile, as ScanlineIter::next sees it (raster.rs:84-91) — written by the triangle's lane, which only runs the
-// running sums down both edges (6 dependent adds per row at 3 lanes); rounding to pixel centres, clipping to the tile, the
-// alignment lerp and everything per fragment are done one ROW per lane, with every lane busy.
-#ifndef RF_ROWQ
-#define RF_ROWQ 128u   // capacity in rows (>= RF_TILE: one triangle's rows in a tile always fit)
-#endif
+// SMALL triangles have no span records: a (triangle, row) item takes the trapezoid half's setup {L, dl, R, dr, dv/dx} from the
+// record k_assemble wrote and performs the j running-sum steps of ScanlineIter::next that lead to its row (raster.rs:84-91) —
+// one ROW per lane, every lane busy (walking the rows per triangle lane ran at 21 % lane efficiency: 20 % of this kernel's
+// instructions, profiles/r02_s14_raster_regions.txt). The owner table maps an item of the chunk to its triangle lane.
+#define RF_OWNER_ITEMS 1024u   // items of a chunk the owner table covers (32 triangles x 32 rows); beyond that a search
 template <int LT> struct RasterSmem {
-  static constexpr int NL = 2 + LT;
   static constexpr int TILE_WORDS = RF_TILE * RF_TILE_PITCH;
   // word offsets inside a warp's region
   static constexpr int RC0 = TILE_WORDS;           // row coverage [RF_TILE]
-  static constexpr int IQ0 = RC0 + RF_TILE;        // row queue [NL + 2][RF_ROWQ]: L[NL], R, meta = tile row | half << 5 | triangle lane << 6
-  static constexpr int WARP_WORDS = IQ0 + (NL + 2) * (int)RF_ROWQ;
+  static constexpr int OW0 = RC0 + RF_TILE;        // owner table: one byte per item of the chunk
+  static constexpr int WARP_WORDS = OW0 + (int)RF_OWNER_ITEMS / 4;
   static constexpr size_t BYTES = (size_t)RF_RASTER_WARPS * WARP_WORDS * 4;
 };
 
@@ -556,7 +557,6 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
   constexpr int NV = 1 + LT, NL = 2 + LT;
   using RS = RasterSmem<LT>;
   using SR = SmallRec<LT>;
-  constexpr int WQ = SW > NL + 1 ? SW : NL + 1;  // raw words of a piece: a span record, or a queued edge state
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   extern __shared__ uint32_t s_raster[];
   if (rf_poisoned(P)) return;
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
   // rounds orders two writes to one pixel; untouched pixels are never read or written.
   float* sz = reinterpret_cast<float*>(s_raster + (size_t)warp * RS::WARP_WORDS);
   const WarpSmem wsm(sz);  // the same region for the per-fragment accesses: depth at [idx], coverage and the row queue behind it
-  constexpr uint32_t RC0 = RS::RC0, IQ0 = RS::IQ0;
+  constexpr uint32_t RC0 = RS::RC0, OW0 = RS::OW0;
   // Row coverage [RF_TILE]: bit c of word r = pixel (r, c) is covered by a piece of the current fragment-mode batch. The pieces
   // OR their pixel runs in; popcount(coverage) == number of fragments <=> no two pieces of the batch share a pixel, and the
   // batch's fragment groups need no per-group same-pixel search (MATCH.ANY cost 10 % of this kernel's stall samples).
@@ -714,120 +714,42 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
       const uint32_t t_incl = warp_scan_incl(t_rows, lane);
       const uint32_t n_items = __shfl_sync(FULL, t_incl, 31);
       const uint32_t small_mask = __ballot_sync(FULL, t_small);
-      // no other kind of triangle with rows here: the pieces of the chunk are exactly the queued rows, in order (item == queue slot)
-      const bool all_small = __ballot_sync(FULL, t_have && !t_small && t_rows != 0u) == 0u;
-      const uint32_t s_rows = t_small ? t_rows : 0u;
-      const uint32_t s_incl = small_mask ? warp_scan_incl(s_rows, lane) : 0u;  // row-queue slots
-
-      // ---- rounds: consecutive triangles whose SMALL rows fit the row queue (s_incl is non-decreasing, a triangle has at
-      // most RF_TILE <= RF_ROWQ rows in the tile: every round takes at least one triangle whole)
-      uint32_t base = 0, sbase = 0;
-      while (base < n_items) {
-        const uint32_t fitm = __ballot_sync(FULL, s_incl <= sbase + RF_ROWQ);
-        const uint32_t tb = fitm == FULL ? 32u : (uint32_t)__ffs(~fitm) - 1u;
-        const uint32_t round_end = __shfl_sync(FULL, t_incl, tb - 1u);
-        const uint32_t nround = round_end - base;
-
-        // (a) SMALL triangles of the round: the running sums down both edges (ScanlineIter::next, raster.rs:84-91), by the
-        // triangle's lane, from the first row of each half (the two halves start from their own setup) to the last row of this
-        // tile; the state of every row inside the tile is queued
-        if (t_small && s_rows != 0u && s_incl > sbase && s_incl <= sbase + RF_ROWQ) {
-          const uint32_t* rec = P.smalls + (size_t)t_tri * SR::W + 4;
-          uint32_t slot = (s_incl - s_rows) - sbase;
-          uint32_t Y = t_Y0;
-          const uint32_t Ya = t_Y0 + t_j0, Yb = Ya + t_rows;  // a SMALL triangle lies inside the target: row = t_Y0 + scanline
-#pragma unroll 1
-          for (uint32_t hh = 0; hh < 2u; hh++) {
-            const uint32_t n = hh ? t_nrows - t_nU : t_nU;
-            if (Y + n <= Ya) { Y += n; continue; }  // this half lies above the tile: nothing of it is needed
-            if (Y >= Yb) break;
-            constexpr int EWD = 2 * NL + 2;  // L[NL], dl[NL], R, dr
-            uint32_t e[(EWD + 3) & ~3];
-            const uint4* e4 = reinterpret_cast<const uint4*>(rec + hh * SR::HW + SR::O_L);
-#pragma unroll
-            for (int q = 0; q < (EWD + 3) / 4; q++) {
-              const uint4 t4 = __ldg(e4 + q);
-              e[4 * q] = t4.x; e[4 * q + 1] = t4.y; e[4 * q + 2] = t4.z; e[4 * q + 3] = t4.w;
-            }
-            float L[NL], dl[NL];
-#pragma unroll
-            for (int i = 0; i < NL; i++) { L[i] = __uint_as_float(e[i]); dl[i] = __uint_as_float(e[NL + i]); }
-            float R = __uint_as_float(e[2 * NL]);
-            const float dr = __uint_as_float(e[2 * NL + 1]);
-            const uint32_t yend = min(Y + n, Yb);
-            for (; Y < yend; Y++) {
-              if (Y >= Ya) {
-#pragma unroll
-                for (int i = 0; i < NL; i++) wsm.stf(IQ0 + i * RF_ROWQ + slot, L[i]);
-                wsm.stf(IQ0 + NL * RF_ROWQ + slot, R);
-                wsm.stu(IQ0 + (NL + 1) * RF_ROWQ + slot, (Y - py0) | hh << 5 | lane << 6);
-                slot++;
-              }
-#pragma unroll
-              for (int i = 0; i < NL; i++) L[i] = L[i] + dl[i];
-              R = R + dr;
-            }
-          }
-        }
-        __syncwarp();
-
+      // owner table: item -> triangle lane (a byte each); chunks with more items than it holds search the prefix sums instead
+      const bool use_table = n_items <= RF_OWNER_ITEMS;
+      if (use_table) {
+        const uint32_t i0 = t_incl - t_rows;
+        for (uint32_t r = 0; r < t_rows; r++) wsm.stb(OW0 * 4u + i0 + r, lane);
+      }
+      __syncwarp();
+      {
+        const uint32_t base = 0, nround = n_items;
         // (b) the round's pieces, 32 at a time, one (triangle, row) per lane. Software pipeline: the raw words of batch n+1 (a
         // queued edge state, or the span record k_setup / k_walk wrote) and its dv/dx are requested before batch n is processed.
         struct Pre {
           bool valid, small;
           uint32_t Y, draw, aux;  // aux: SMALL: unused; otherwise the span's checkpoint base
-          uint32_t w[WQ];
+          uint32_t w[SW];
           uint32_t dvw[NV];
-        };
-        auto load_small_dv = [&](uint32_t tri, uint32_t hh, Pre& p) {
-          const uint32_t* dp = P.smalls + (size_t)tri * SR::W + 4 + hh * SR::HW + SR::O_DV;
-          if (SR::O_DV % 4 == 0) {
-#pragma unroll
-            for (int q = 0; q < (NV + 3) / 4; q++) {
-              const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(dp) + q);
-              if (4 * q < NV) p.dvw[4 * q] = t4.x;
-              if (4 * q + 1 < NV) p.dvw[4 * q + 1] = t4.y;
-              if (4 * q + 2 < NV) p.dvw[4 * q + 2] = t4.z;
-              if (4 * q + 3 < NV) p.dvw[4 * q + 3] = t4.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < NV; i++) p.dvw[i] = __ldg(dp + i);
-          }
-        };
-        // all-SMALL chunk: the row's own meta word names its triangle lane — no search, two shuffles
-        auto fetch_small = [&](uint32_t ib, Pre& p) {
-          const uint32_t slot = ib + lane;
-          p.valid = slot < nround;
-          p.small = true;
-          p.aux = 0;
-          const uint32_t meta = p.valid ? wsm.ldu(IQ0 + (NL + 1) * RF_ROWQ + slot) : 0u;
-          const uint32_t ow = (meta >> 6) & 31u;
-          p.draw = __shfl_sync(FULL, t_draw, ow);
-          const uint32_t o_tri = __shfl_sync(FULL, t_tri, ow);
-          p.Y = py0 + (meta & 31u);
-          if (p.valid) {
-#pragma unroll
-            for (int i = 0; i < NL + 1; i++) p.w[i] = wsm.ldu(IQ0 + i * RF_ROWQ + slot);
-            load_small_dv(o_tri, (meta >> 5) & 1u, p);
-          }
         };
         auto fetch = [&](uint32_t ib, Pre& p) {
           const uint32_t item = base + ib + lane;
           p.valid = ib + lane < nround;
-          // owner triangle lane: number of lanes whose inclusive end <= item
+          // owner triangle lane: from the table, or the number of lanes whose inclusive end <= item
           uint32_t ot = 0;
+          if (use_table) ot = p.valid ? wsm.ldb(OW0 * 4u + item) : 0u;
+          else {
 #pragma unroll
-          for (int step = 16; step > 0; step >>= 1) {
-            const uint32_t cand = ot + step;
-            const uint32_t e = __shfl_sync(FULL, t_incl, (cand - 1) & 31);
-            if (cand <= 32 && e <= item) ot = cand;
+            for (int step = 16; step > 0; step >>= 1) {
+              const uint32_t cand = ot + step;
+              const uint32_t e = __shfl_sync(FULL, t_incl, (cand - 1) & 31);
+              if (cand <= 32 && e <= item) ot = cand;
+            }
+            ot &= 31u;
           }
-          ot &= 31u;
           const uint32_t o_incl = __shfl_sync(FULL, t_incl, ot), o_rows = __shfl_sync(FULL, t_rows, ot);
           const uint32_t o_j0 = __shfl_sync(FULL, t_j0, ot), o_Y0 = __shfl_sync(FULL, t_Y0, ot);
           const uint32_t o_sbase = __shfl_sync(FULL, t_sbase, ot), o_nU = __shfl_sync(FULL, t_nU, ot);
-          const uint32_t o_tri = __shfl_sync(FULL, t_tri, ot), o_sincl = __shfl_sync(FULL, s_incl, ot);
+          const uint32_t o_tri = __shfl_sync(FULL, t_tri, ot);
           p.draw = __shfl_sync(FULL, t_draw, ot);
           p.small = ((small_mask >> ot) & 1u) != 0u;
           p.Y = 0; p.aux = 0;
@@ -836,11 +758,9 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
             const uint32_t j = o_j0 + rit;
             p.Y = (uint32_t)max((int32_t)o_Y0 + (int32_t)j, 0);
             const uint32_t hh = j >= o_nU ? 1u : 0u;
-            if (p.small) {
-              const uint32_t slot = (o_sincl - o_rows) - sbase + rit;
-#pragma unroll
-              for (int i = 0; i < NL + 1; i++) p.w[i] = wsm.ldu(IQ0 + i * RF_ROWQ + slot);
-              load_small_dv(o_tri, hh, p);
+            if (p.small) {  // the record is read when the item is processed (L1 / L2 hits: ~7 rows share a half)
+              p.w[0] = o_tri;
+              p.w[1] = (hh ? j - o_nU : j) | hh << 16;
             } else {
               const uint32_t* sp = P.spans + (size_t)(o_sbase + j) * SW;
 #pragma unroll
@@ -854,11 +774,13 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
             }
           }
         };
+        // chunks without span-record triangles need no software pipeline (and no register copies): their items only carry indices
+        const bool pipelined = __ballot_sync(FULL, t_have && !t_small && t_rows != 0u) != 0u;
         Pre cur, nxt;
         nxt.valid = false;
-        if (!all_small) fetch(0, nxt);
+        if (pipelined) fetch(0, nxt);
         for (uint32_t ib = 0; ib < nround; ib += 32) {
-          if (all_small) fetch_small(ib, cur);  // shared-memory latency only: no pipeline, no register copies
+          if (!pipelined) fetch(ib, cur);
           else {
             cur = nxt;
             nxt.valid = false;
@@ -869,12 +791,44 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
           float v[NV], dv[NV];
 #pragma unroll
           for (int i = 0; i < NV; i++) { v[i] = 0.0f; dv[i] = 0.0f; }
-          if (valid && cur.small) {
-            // ScanlineIter::next for this row (raster.rs:91-112): round both ends up to pixel centres, align the varyings to the
-            // first centre, clip the span to this tile's columns (a SMALL triangle lies inside the target: no bounds to check)
+          // ScanlineIter::next for the rows of SMALL triangles (raster.rs:84-112): the half's setup, jj steps of the running sums down
+          // both edges (the same additions in the same order as the reference's iterator), then round both ends up to pixel centres,
+          // align the varyings to the first centre and clip the span to this tile's columns (a SMALL triangle lies inside the
+          // target: no bounds to check). The step loop runs to the largest jj of the batch.
+          const bool is_small = valid && cur.small;
+          float eL[NL], eR = 0.0f;
+          if (__any_sync(FULL, is_small)) {
+            float dl[NL], dr = 0.0f;
+            uint32_t jj = 0;
 #pragma unroll
-            for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(cur.dvw[i]);
-            const float v0x = __uint_as_float(cur.w[0]), x1 = __uint_as_float(cur.w[NL]);
+            for (int i = 0; i < NL; i++) { eL[i] = 0.0f; dl[i] = 0.0f; }
+            if (is_small) {
+              jj = cur.w[1] & 0xFFFFu;
+              const uint32_t* rec = P.smalls + (size_t)cur.w[0] * SR::W + 4 + (cur.w[1] >> 16) * SR::HW;
+              constexpr int EWD = 2 * NL + 2 + NV;  // L[NL], dl[NL], R, dr, dv[NV]: contiguous in the record
+              uint32_t e[(EWD + 3) & ~3];
+#pragma unroll
+              for (int q = 0; q < (EWD + 3) / 4; q++) {
+                const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(rec) + q);
+                e[4 * q] = t4.x; e[4 * q + 1] = t4.y; e[4 * q + 2] = t4.z; e[4 * q + 3] = t4.w;
+              }
+#pragma unroll
+              for (int i = 0; i < NL; i++) { eL[i] = __uint_as_float(e[SR::O_L + i]); dl[i] = __uint_as_float(e[SR::O_DL + i]); }
+              eR = __uint_as_float(e[SR::O_R]); dr = __uint_as_float(e[SR::O_DR]);
+#pragma unroll
+              for (int i = 0; i < NV; i++) dv[i] = __uint_as_float(e[SR::O_DV + i]);
+            }
+            const uint32_t maxj = __reduce_max_sync(FULL, jj);
+            for (uint32_t q = 0; q < maxj; q++) {
+              if (q < jj) {
+#pragma unroll
+                for (int i = 0; i < NL; i++) eL[i] = eL[i] + dl[i];
+                eR = eR + dr;
+              }
+            }
+          }
+          if (is_small) {
+            const float v0x = eL[0], x1 = eR;
             const float x0r = round_up_to_half(v0x), x1r = round_up_to_half(x1);
             const uint32_t cntp = sat_u32(x1r - x0r);
             const uint32_t X0 = sat_u32(x0r), X1 = max(sat_u32(x1r), X0);
@@ -884,7 +838,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
             if (xe > xs) {
               const float tx_ = x0r - v0x;
 #pragma unroll
-              for (int i = 0; i < NV; i++) { const float a = __uint_as_float(cur.w[1 + i]); v[i] = a + ((a + dv[i]) - a) * tx_; }
+              for (int i = 0; i < NV; i++) { const float a = eL[1 + i]; v[i] = a + ((a + dv[i]) - a) * tx_; }
               for (uint32_t k = X0; k < xs; k++) {  // the span started in an earlier tile column: the pixels before this one
 #pragma unroll
                 for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];
@@ -1116,10 +1070,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
             __syncwarp();
           }
         }
-        __syncwarp();  // the row queue is rewritten by the next round
-        base = round_end;
-        sbase = __shfl_sync(FULL, s_incl, tb - 1u);
       }
+      __syncwarp();  // the owner table is rewritten by the next chunk
     }
     flush_acc();
     __syncwarp();
