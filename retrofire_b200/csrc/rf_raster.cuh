@@ -528,19 +528,6 @@ __device__ __forceinline__ uint32_t process_fragment_fixed(const DrawDesc& D, ui
 #ifndef RF_FRAG_K_COST
 #define RF_FRAG_K_COST 0u
 #endif
-// chunked mode (see k_raster): taken when RF_CHUNK_FIXED + RF_CHUNK_ITER * T < 10 + RF_SPAN_ITER_COST_REAL * max(pn)
-#ifndef RF_CHUNKED
-#define RF_CHUNKED 1
-#endif
-#ifndef RF_CHUNK_FIXED
-#define RF_CHUNK_FIXED 90u
-#endif
-#ifndef RF_CHUNK_ITER
-#define RF_CHUNK_ITER 38u
-#endif
-#ifndef RF_SPAN_ITER_COST_REAL
-#define RF_SPAN_ITER_COST_REAL 35u
-#endif
 template <int LT> struct RasterTune {
   static constexpr uint32_t MIN_AVG = LT == 3 ? RF_SPAN_MODE_MIN_AVG_3 : RF_SPAN_MODE_MIN_AVG_5;
 };
@@ -926,92 +913,11 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
           const uint32_t rcov = wsm.ldu(RC0 + lane);
           wsm.stu(RC0 + lane, 0u);
           const bool no_overlap = __reduce_add_sync(FULL, (uint32_t)__popc(rcov)) == n_frags;
-          const uint32_t maxpn = __reduce_max_sync(FULL, pn);
-          // ================= chunked mode: pieces cut into runs of at most T pixels, one run per lane =================
-          // Span mode runs max(pn) iterations with the short pieces' lanes idle (32 % lane efficiency on the bunny batch,
-          // profiles/r02_s16_raster_regions.txt). When no two pieces of the batch share a pixel, the runs are independent: a
-          // lane takes run `sub` of a piece — the piece's start values and steps over shuffles, sub * T running-sum steps to its
-          // first pixel (the same additions in the same order, vary.rs:146-154) — and T iterations finish the batch.
-          if (RF_CHUNKED && no_overlap && uni && maxpn > 2u) {
-            uint32_t lg = 0;  // T = 1 << lg: the smallest power of two with at most 32 runs
-            while ((1u << lg) < ((n_frags + 31u) >> 5)) lg++;
-            while (__reduce_add_sync(FULL, (pn + (1u << lg) - 1u) >> lg) > 32u) lg++;
-            const uint32_t T = 1u << lg;
-            if (RF_CHUNK_FIXED + RF_CHUNK_ITER * T < 10u + RF_SPAN_ITER_COST_REAL * maxpn) {
-              const uint32_t nsub = (pn + T - 1u) >> lg;
-              const uint32_t r_incl = warp_scan_incl(nsub, lane);
-              // owner piece of run `lane`: number of lanes whose inclusive run count <= lane
-              uint32_t oi = 0;
-#pragma unroll
-              for (int step = 16; step > 0; step >>= 1) {
-                const uint32_t cand = oi + step;
-                const uint32_t e = __shfl_sync(FULL, r_incl, (cand - 1) & 31);
-                if (cand <= 32 && e <= lane) oi = cand;
-              }
-              oi &= 31u;
-              const uint32_t o_end = __shfl_sync(FULL, r_incl, oi), o_nsub = __shfl_sync(FULL, nsub, oi), o_pn = __shfl_sync(FULL, pn, oi);
-              const uint32_t o_pix = __shfl_sync(FULL, py * RF_TILE_PITCH + pxs, oi), o_gofs = __shfl_sync(FULL, py * t_w + pxs, oi);
-              const bool rvalid = lane < __shfl_sync(FULL, r_incl, 31);
-              const uint32_t k0 = rvalid ? (lane - (o_end - o_nsub)) << lg : 0u;
-              const uint32_t len = rvalid ? min(T, o_pn - k0) : 0u;
-              float fv[NV], fdv[NV];
-#pragma unroll
-              for (int i = 0; i < NV; i++) { fv[i] = __shfl_sync(FULL, v[i], oi); fdv[i] = __shfl_sync(FULL, dv[i], oi); }
-              const uint32_t maxk0 = __reduce_max_sync(FULL, k0);
-              for (uint32_t q = 0; q < maxk0; q++) {
-                if (q < k0) {
-#pragma unroll
-                  for (int i = 0; i < NV; i++) fv[i] = fv[i] + fdv[i];
-                }
-              }
-              const DrawDesc& D = P.draws[d0];
-              const uint32_t pbase = o_pix + k0;
-              uint32_t* const gp0 = gc + (o_gofs + k0);
-              uint32_t wrote = 0;
-              if (smode == 2) {
-                for (uint32_t k = 0; k < T; k++) {
-                  if (k < len) {
-                    wrote += process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, t_sel, gp0 + k, wsm, pbase + k, fv);
-#pragma unroll
-                    for (int i = 0; i < NV; i++) fv[i] = fv[i] + fdv[i];
-                  }
-                }
-              } else if (fmode == 3) {
-                for (uint32_t k = 0; k < T; k++) {
-                  if (k < len) {
-                    wrote += process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, t_fmt, t_sel, gp0 + k, wsm, pbase + k, fv);
-#pragma unroll
-                    for (int i = 0; i < NV; i++) fv[i] = fv[i] + fdv[i];
-                  }
-                }
-              } else if (smode == 4) {
-                for (uint32_t k = 0; k < T; k++) {
-                  if (k < len) {
-                    wrote += process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, t_sel, gp0 + k, wsm, pbase + k, fv);
-#pragma unroll
-                    for (int i = 0; i < NV; i++) fv[i] = fv[i] + fdv[i];
-                  }
-                }
-              } else {
-                const uint32_t flags = D.flags, pmask = D.persp_mask, fs = D.fs;
-                const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
-                const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
-                for (uint32_t k = 0; k < T; k++) {
-                  if (k < len) {
-                    wrote += process_fragment<LT>(D, fs, t_fmt, t_sel, gp0 + k, wsm, pbase + k, fv, pmask, dtest, cwrite, dwrite);
-#pragma unroll
-                    for (int i = 0; i < NV; i++) fv[i] = fv[i] + fdv[i];
-                  }
-                }
-              }
-              acc_o += wrote;
-              __syncwarp();  // orders this batch's depth / colour writes before the next batch's accesses to the same pixels
-              continue;
-            }
-          }
           bool span_mode = n_frags >= RasterTune<LT>::MIN_AVG * (uint32_t)__popc(vmask);
-          if (RF_SPAN_ITER_COST != 0u && !span_mode)
+          if (RF_SPAN_ITER_COST != 0u && !span_mode) {
+            const uint32_t maxpn = __reduce_max_sync(FULL, pn);
             span_mode = 10u + maxpn * RF_SPAN_ITER_COST <= ((n_frags + 31u) >> 5) * (RF_FRAG_GROUP_COST + RF_FRAG_K_COST * maxpn);
+          }
           if (span_mode) {
             // ================= span mode: one piece per lane, walked serially =================
             // dependencies: earlier lanes on the same row whose x-range overlaps mine
