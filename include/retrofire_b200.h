@@ -77,7 +77,9 @@ typedef enum rf_fs_id {
   RF_FS_TEX_CLAMP = 5,      /* 2 lanes uv, SamplerClamp                 tests/rendering.rs:30 */
   RF_FS_TEX_REPEAT_POT = 6, /* 2 lanes uv, SamplerRepeatPot             benches/fill.rs:74-91 */
   RF_FS_SPRITE_DISC = 7,    /* 2 lanes; d2<1 ? 1-d2*(.25,.5,1) : discard sprites.rs:46-52     */
-  RF_FS_NORMAL_VIS = 8      /* 3 lanes; n/2+0.5                         curses.rs:53-56       */
+  RF_FS_NORMAL_VIS = 8,     /* 3 lanes; n/2+0.5                         curses.rs:53-56       */
+  RF_FS_TEX_ONCE = 9        /* 2 lanes uv, SamplerOnce: texel (w*u as u32, h*v as u32), unchecked; a coordinate outside the
+                               texture panics in the reference (tex.rs:313-357) = RF_E_BAD_TEXTURE here */
 } rf_fs_id;
 
 /* Colour element of the target (util/pixfmt.rs:20-142, render/target.rs:99-136).

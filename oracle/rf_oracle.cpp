@@ -215,6 +215,15 @@ inline void sample_clamp(const Tex& t, float tu, float tv, uint8_t rgba[4]) {
   uint32_t v = sat_u32(floorf(rust_clamp(sv, 0.0f, h - 1.0f)));
   texel(t, u, v, rgba);
 }
+// tex.rs:313-357 SamplerOnce: `tc.u() as u32` of the scaled coordinate, no wrapping or clamping; `d[[u, v]]` panics when the
+// texel is outside the texture (util/buf.rs Index) -> false
+inline bool sample_once(const Tex& t, float tu, float tv, uint8_t rgba[4]) {
+  float w = (float)t.w, h = (float)t.h;
+  uint32_t u = sat_u32(w * tu), v = sat_u32(h * tv);
+  if (u >= t.w || v >= t.h) return false;
+  texel(t, u, v, rgba);
+  return true;
+}
 // tex.rs:218-267
 inline void sample_repeat_pot(const Tex& t, float tu, float tv, uint8_t rgba[4]) {
   float w = (float)t.w, h = (float)t.h;
@@ -226,8 +235,11 @@ inline void sample_repeat_pot(const Tex& t, float tu, float tv, uint8_t rgba[4])
 
 // ---- fragment shaders (catalogue) ----------------------------------------------------------
 // returns false = discard (shader.rs:48-55). var[] is already perspective-corrected.
-bool shade_fragment(const rf_draw& d, const Tex* tex, const float* var, uint8_t rgba[4]) {
+bool shade_fragment(const rf_draw& d, const Tex* tex, const float* var, uint8_t rgba[4], bool* panicked) {
   switch (d.fs) {
+    case RF_FS_TEX_ONCE:
+      if (!sample_once(*tex, var[0], var[1], rgba)) { *panicked = true; return false; }
+      return true;
     case RF_FS_COLOR3F:  // color.rs:246-263  to_color4: (256*c) as u8, a = 0xFF
       for (int i = 0; i < 3; i++) rgba[i] = sat_u8(256.0f * var[i]);
       rgba[3] = 0xFF;
@@ -315,6 +327,7 @@ struct Raster {
   rf_stats& st;
   int NL;  // 3 + L
   bool oob = false;
+  bool tex_oob = false;  // SamplerOnce indexed outside the texture (the reference panics)
 
   // render/target.rs:138-198 on one Scanline (raster.rs:80-114 produced it)
   void scanline(uint64_t Y, uint64_t X0, uint64_t X1e, uint32_t cnt, Lanes v, const Lanes& dvdx) {
@@ -343,7 +356,7 @@ struct Raster {
       }
       if (pass) {
         uint8_t c[4];
-        if (shade_fragment(d, tex, var, c)) {
+        if (shade_fragment(d, tex, var, c, &tex_oob)) {
           if (d.color_write) {
             st.frags_o += 1;
             crow[X0 + k] = pack_pixel(tg.fmt, c);
@@ -492,7 +505,7 @@ int rfo_render(const rf_draw* dp, const rfo_texture* texp, rfo_target* tp, rf_st
   }
   Tex tex{};
   if (texp) tex = Tex{texp->w, texp->h, texp->fmt, texp->data, (size_t)texp->stride};
-  const bool needs_tex = d.fs == RF_FS_TEX_CLAMP_LIT || d.fs == RF_FS_TEX_CLAMP || d.fs == RF_FS_TEX_REPEAT_POT;
+  const bool needs_tex = d.fs == RF_FS_TEX_CLAMP_LIT || d.fs == RF_FS_TEX_CLAMP || d.fs == RF_FS_TEX_REPEAT_POT || d.fs == RF_FS_TEX_ONCE;
   if (needs_tex && !texp) return RF_E_INVALID;
   if (d.fs == RF_FS_TEX_REPEAT_POT && ((tex.w & (tex.w - 1)) || (tex.h & (tex.h - 1)) || !tex.w || !tex.h))
     return RF_E_BAD_TEXTURE;  // tex.rs:230-231
@@ -552,6 +565,7 @@ int rfo_render(const rf_draw* dp, const rfo_texture* texp, rfo_target* tp, rf_st
       s.verts_o += 3;  // render.rs:196 adds 3 whatever the primitive
       R.line(sa, sb);
       if (R.oob) { status = RF_E_TARGET_OOB; break; }
+      if (R.tex_oob) { status = RF_E_BAD_TEXTURE; break; }
     }
     auto t1e = std::chrono::steady_clock::now();
     s.time_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1e - t0).count();
@@ -608,6 +622,7 @@ int rfo_render(const rf_draw* dp, const rfo_texture* texp, rfo_target* tp, rf_st
     s.verts_o += 3;
     R.tri_fill(scr);
     if (R.oob) { status = RF_E_TARGET_OOB; break; }
+    if (R.tex_oob) { status = RF_E_BAD_TEXTURE; break; }
   }
   auto t1 = std::chrono::steady_clock::now();
   s.time_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
@@ -748,10 +763,11 @@ int rfo_tri_fill_spans(const float* lanes_in, int L, uint32_t persp_mask, SpanRe
   return rec.n;
 }
 
-// Sampler KATs (tex.rs:381-418): kind 0 clamp, 1 repeat_pot
+// Sampler KATs (tex.rs:381-418): kind 0 clamp, 1 repeat_pot, 2 once (a texel outside the texture, where the reference panics, gives 4 x 0xEE)
 void rfo_sample(const rfo_texture* t, int kind, float u, float v, uint8_t rgba[4]) {
   Tex tex{t->w, t->h, t->fmt, t->data, (size_t)t->stride};
   if (kind == 0) sample_clamp(tex, u, v, rgba);
+  else if (kind == 2) { if (!sample_once(tex, u, v, rgba)) rgba[0] = rgba[1] = rgba[2] = rgba[3] = 0xEE; }
   else sample_repeat_pot(tex, u, v, rgba);
 }
 

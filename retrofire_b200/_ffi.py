@@ -26,7 +26,7 @@ STATUS_NAMES = {
 # rf_vs_id / rf_fs_id
 VS_MVP, VS_MVP_LINEARIZE, VS_SOLIDS, VS_SPRITE = 0, 1, 2, 3
 (FS_COLOR3F, FS_COLOR3F_SRGB, FS_COLOR4F, FS_CHECKER, FS_TEX_CLAMP_LIT, FS_TEX_CLAMP,
- FS_TEX_REPEAT_POT, FS_SPRITE_DISC, FS_NORMAL_VIS) = range(9)
+ FS_TEX_REPEAT_POT, FS_SPRITE_DISC, FS_NORMAL_VIS, FS_TEX_ONCE) = range(10)
 
 # rf_color_fmt
 FMT_RGBA8888, FMT_XRGB8888, FMT_ARGB8888, FMT_BGRA8888, FMT_RGB888, FMT_RGB565, FMT_RGBA4444 = range(7)

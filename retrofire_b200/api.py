@@ -112,6 +112,7 @@ _FS_LANES = {  # fs id -> (lanes, persp_mask) implied by the varying's Rust type
     _ffi.FS_COLOR3F: (3, 0b000), _ffi.FS_COLOR3F_SRGB: (3, 0b000), _ffi.FS_COLOR4F: (4, 0b0000),
     _ffi.FS_CHECKER: (2, 0b11), _ffi.FS_TEX_CLAMP_LIT: (5, 0b11111), _ffi.FS_TEX_CLAMP: (2, 0b11),
     _ffi.FS_TEX_REPEAT_POT: (2, 0b11), _ffi.FS_SPRITE_DISC: (2, 0b11), _ffi.FS_NORMAL_VIS: (3, 0b111),
+    _ffi.FS_TEX_ONCE: (2, 0b11),
 }
 
 

@@ -758,6 +758,7 @@ rf_status validate_all(rf_ctx* c, bool only_oldest = false) {
     if (ps.error) {
       if (ps.error & RF_ERRBIT_INDEX_OOB) result = fail(c, RF_E_INDEX_OOB, "vertex index out of bounds (render/prim.rs:17-19 panics)");
       else if (ps.error & RF_ERRBIT_TARGET_OOB) result = fail(c, RF_E_TARGET_OOB, "scanline outside the render target (render/target.rs:148,173 panics)");
+      else if (ps.error & RF_ERRBIT_TEXEL_OOB) result = fail(c, RF_E_BAD_TEXTURE, "SamplerOnce: texture coordinate outside the texture (render/tex.rs:343-356 panics)");
       else if (ps.error & RF_ERRBIT_INTERNAL) result = fail(c, RF_E_CUDA, "internal: span outside its triangle's tile bounding box");
       else result = fail(c, RF_E_NOMEM, "a 32x32 tile is overlapped by more than %u triangles of one pass (max_bin=%u)", RF_SORT_BIG, ps.max_bin);
     } else {
@@ -817,7 +818,7 @@ rf_status sync_impl(rf_ctx* c) {
   return st;
 }
 
-bool fs_needs_tex(uint32_t fs) { return fs == RF_FS_TEX_CLAMP_LIT || fs == RF_FS_TEX_CLAMP || fs == RF_FS_TEX_REPEAT_POT; }
+bool fs_needs_tex(uint32_t fs) { return fs == RF_FS_TEX_CLAMP_LIT || fs == RF_FS_TEX_CLAMP || fs == RF_FS_TEX_REPEAT_POT || fs == RF_FS_TEX_ONCE; }
 uint32_t fs_min_lanes(uint32_t fs) {
   switch (fs) {
     case RF_FS_COLOR3F: case RF_FS_COLOR3F_SRGB: case RF_FS_NORMAL_VIS: return 3;
@@ -832,7 +833,7 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
   if (target->ctx != c) return fail(c, RF_E_INVALID, "target belongs to another ctx");
   if (d->depth_sort > RF_SORT_BACK_TO_FRONT) return fail(c, RF_E_INVALID, "bad depth_sort");
   if (d->bbox_cull > 1 || (d->bbox_cull && d->vs == RF_VS_SPRITE)) return fail(c, RF_E_INVALID, "bbox_cull needs a vertex shader whose u[0..16] is the model-to-projection matrix");
-  if (d->vs > RF_VS_SPRITE || d->fs > RF_FS_NORMAL_VIS) return fail(c, RF_E_UNSUPPORTED_SHADER, "shader id not in the catalogue");
+  if (d->vs > RF_VS_SPRITE || d->fs > RF_FS_TEX_ONCE) return fail(c, RF_E_UNSUPPORTED_SHADER, "shader id not in the catalogue");
   if (d->n_attr_lanes > RF_MAX_ATTR_LANES || d->n_attr_lanes < fs_min_lanes(d->fs))
     return fail(c, RF_E_UNSUPPORTED_SHADER, "fragment shader %u needs >= %u varying lanes, got %u", d->fs, fs_min_lanes(d->fs), d->n_attr_lanes);
   if ((d->vs == RF_VS_SOLIDS && d->n_attr_lanes < 3) || (d->vs == RF_VS_SPRITE && d->n_attr_lanes < 2))

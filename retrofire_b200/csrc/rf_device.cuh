@@ -39,6 +39,7 @@
 #define RF_ERRBIT_TARGET_OOB 0x2u
 #define RF_ERRBIT_BIN_TOO_DEEP 0x4u
 #define RF_ERRBIT_INTERNAL 0x10u
+#define RF_ERRBIT_TEXEL_OOB 0x20u   // SamplerOnce indexed outside its texture (tex.rs:343-356 panics); raised by k_raster itself
 
 struct DrawDesc {
   const float* verts;       // [n_verts][vstride]

@@ -396,6 +396,14 @@ __device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, c
       r = c & 0xFFu; g = (c >> 8) & 0xFFu; b = (c >> 16) & 0xFFu; a = c >> 24;
       return true;
     }
+    case RF_FS_TEX_ONCE: {  // tex.rs:313-357 SamplerOnce: no wrapping, no clamping; outside the texture the reference panics
+      const float w = (float)D.tex_w, h = (float)D.tex_h;
+      const uint32_t u = sat_u32(w * var[0]), v = sat_u32(h * var[LT >= 2 ? 1 : 0]);
+      if (u >= D.tex_w || v >= D.tex_h) { r = 0x100u; return false; }  // flagged to the caller through r
+      const uint32_t c = __ldg(D.tex + (size_t)v * D.tex_w + u);
+      r = c & 0xFFu; g = (c >> 8) & 0xFFu; b = (c >> 16) & 0xFFu; a = c >> 24;
+      return true;
+    }
     case RF_FS_SPRITE_DISC: {  // sprites.rs:46-52
       float d2 = 0.0f;
       d2 = d2 + var[0] * var[0];
@@ -482,7 +490,7 @@ __device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t
       if ((pmask >> i) & 1u) var[i] = zdiv(v[1 + i], z);
   }
   uint32_t r = 0, g = 0, bl = 0, a = 0;
-  if (!shade_fragment<LT>(D, fs, var, r, g, bl, a)) return 0u;  // discard: no writes at all
+  if (!shade_fragment<LT>(D, fs, var, r, g, bl, a)) return r == 0x100u ? 0x80000000u : 0u;  // discard: no writes at all (bit 31: SamplerOnce left its texture)
   // A NaN depth (0 * inf in the setup of a zero-height trapezoid half) can only be written with depth_test = None: every
   // comparison with a NaN fails (ctx.rs:86-89). The reference's x86-64 host generates the default NaN 0xFFC00000 and
   // propagates it; CUDA arithmetic generates 0x7FFFFFFF. The bits written are the host's ("NaN contract").
@@ -964,7 +972,9 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                   const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
                   const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
                   for (uint32_t k = 0; k < pn; k++) {
-                    my_o += process_fragment<LT>(D, fs, t_fmt, t_sel, gp0 + k, wsm, pbase + k, v, pmask, dtest, cwrite, dwrite);
+                    const uint32_t pf = process_fragment<LT>(D, fs, t_fmt, t_sel, gp0 + k, wsm, pbase + k, v, pmask, dtest, cwrite, dwrite);
+                    if (pf & 0x80000000u) atomicOr(&P.status->error, RF_ERRBIT_TEXEL_OOB);
+                    my_o += pf & 1u;
 #pragma unroll
                     for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
                   }
@@ -1040,7 +1050,9 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                   if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, t_sel, gp, wsm, pix, fv);
                   if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, t_fmt, t_sel, gp, wsm, pix, fv);
                   if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, t_sel, gp, wsm, pix, fv);
-                  return process_fragment<LT>(D, fs, t_fmt, t_sel, gp, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
+                  const uint32_t pf = process_fragment<LT>(D, fs, t_fmt, t_sel, gp, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
+                  if (pf & 0x80000000u) atomicOr(&P.status->error, RF_ERRBIT_TEXEL_OOB);
+                  return pf & 1u;
                 };
                 if (clean) {
                   if (fvalid) wrote = one();

@@ -23,6 +23,7 @@ pub const RF_FS_TEX_CLAMP: u32 = 5;
 pub const RF_FS_TEX_REPEAT_POT: u32 = 6;
 pub const RF_FS_SPRITE_DISC: u32 = 7;
 pub const RF_FS_NORMAL_VIS: u32 = 8;
+pub const RF_FS_TEX_ONCE: u32 = 9;
 // rf_pixel_fmt: the colour layout of a TARGET (rf_target_create)
 pub const RF_FMT_RGBA8888: u32 = 0;
 pub const RF_FMT_XRGB8888: u32 = 1;

@@ -115,6 +115,16 @@ impl<B> GpuShader<&Proj<B>> for MvpTexRepeatPot<'_> {
     fn texture(&self) -> *const sys::rf_texture { self.tex.t }
 }
 
+/// `SamplerOnce.sample(&tex, uv)` (render/tex.rs:313-357): coordinates are assumed inside the texture; outside it the
+/// reference panics (slice index) and this path reports RF_E_BAD_TEXTURE, which `check` turns into the same panic.
+pub struct MvpTexOnce<'t> { pub tex: &'t GpuTexture<'t> }
+impl<B> GpuShader<&Proj<B>> for MvpTexOnce<'_> {
+    const VS: u32 = sys::RF_VS_MVP;
+    const FS: u32 = sys::RF_FS_TEX_ONCE;
+    fn vs_uniform(m: &&Proj<B>) -> [f32; 32] { mat_uniform(&m.0, None) }
+    fn texture(&self) -> *const sys::rf_texture { self.tex.t }
+}
+
 /// crates.rs:39-47: varying `(Normal3, TexCoord)`, `kd = lerp(max(n·l, 0), 0.4, 1.0)`, texel * kd.
 pub struct MvpTexClampLit<'t> { pub tex: &'t GpuTexture<'t>, pub light_dir: Normal3 }
 impl<B> GpuShader<&Proj<B>> for MvpTexClampLit<'_> {

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import retrofire_b200 as rf
-from retrofire_b200 import scenes
+from retrofire_b200 import _ffi, scenes
 from tests.parity import assert_parity, depth_equal, run_gpu, run_oracle
 
 f32 = np.float32
@@ -322,3 +322,29 @@ def test_scanlines_above_the_target_are_drawn_at_row_0(device, oracle, dtest, sh
         want = run_oracle(oracle, sc)
         assert want[2].frags.i > 1000
         assert_parity(run_gpu(device, sc), want, name=sc.name)
+
+
+def test_sampler_once(device, oracle):
+    """`SamplerOnce` (tex.rs:313-357, catalogue id RF_FS_TEX_ONCE): unchecked texel fetch. Inside the texture it is a plain lookup; a
+    coordinate outside it panics in the reference (slice index) and is RF_E_BAD_TEXTURE on both sides."""
+    from retrofire_b200 import mathx as mx
+    g = np.random.default_rng(3)
+    tex = rf.Texture(g.integers(0, 256, (16, 8, 4), dtype=np.uint8))   # 8 wide, 16 high, Color4 texels
+    w, h = 128, 96
+    for uvmax, ok in ((0.999, True), (1.25, False)):
+        verts = np.array([[-0.9, -0.9, 0.5, 0.0, 0.0], [0.9, -0.9, 0.5, uvmax, 0.0], [0.9, 0.9, 0.5, uvmax, uvmax], [-0.9, 0.9, 0.5, 0.0, uvmax]], dtype=f32)
+        tris = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.uint32)
+        ctx = rf.Context(face_cull=None)
+        shd = rf.shader.new(rf.VS_MVP, rf.FS_TEX_ONCE, texture=tex)
+        sc = scenes.Scene(f"once_{uvmax}", w, h, rf.FMT_RGBA8888, True, ctx,
+                          [rf.DrawCall.make(tris, verts, shd, np.eye(4, dtype=f32), mx.viewport((0, h), (w, 0)), ctx)])
+        if ok:
+            want = run_oracle(oracle, sc)
+            assert want[2].frags.o > 5000
+            assert_parity(run_gpu(device, sc), want, name=sc.name)
+        else:
+            with pytest.raises(rf.RetrofireError) as eo:
+                run_oracle(oracle, sc)
+            with pytest.raises(rf.RetrofireError) as eg:
+                run_gpu(device, sc)
+            assert eo.value.status == eg.value.status == _ffi.RF_E_BAD_TEXTURE

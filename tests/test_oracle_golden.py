@@ -177,6 +177,13 @@ def test_sampler_kats(oracle):
     assert cl(1.5, 0.0) == (0, 0xFF, 0)
     assert cl(0.0, 1.5) == (0, 0, 0xFF)
     assert cl(1.5, 1.5) == (0xFF, 0xFF, 0)
+    on = lambda u, v: oracle.sample(tex, 2, u, v)[:3]   # SamplerOnce, tex.rs:410-418
+    assert on(0.0, 0.0) == (0xFF, 0, 0)
+    assert on(0.5, 0.0) == (0, 0xFF, 0)
+    assert on(0.0, 0.5) == (0, 0, 0xFF)
+    assert on(0.5, 0.5) == (0xFF, 0xFF, 0)
+    assert on(1.0, 0.0) == (0xEE, 0xEE, 0xEE) and on(0.0, 1.5) == (0xEE, 0xEE, 0xEE)   # outside: the reference's slice index panics
+    assert on(-0.4, 0.0) == (0xFF, 0, 0)                                              # `as u32` saturates a negative coordinate to 0
 
 
 def test_xorshift64_kats():
