@@ -60,6 +60,11 @@ def test_rust_safe_shim_names_every_catalogue_pair_with_the_headers_ids():
     used_vs = {int(v) for v in re.findall(r"const VS: u32 = (\d+);", shim)}
     for vs, fs in re.findall(r"mvp_shader!\(.*?(\d+),\s*(\d+)\);", shim, re.S):
         used_vs.add(int(vs)); used_fs.add(int(fs))
+    # ids written symbolically (`sys::RF_FS_TEX_ONCE`) resolve through the -sys crate, whose constants must equal the header's
+    rust_consts = {n: int(v) for n, v in re.findall(r"pub const (RF_(?:VS|FS)_[A-Z0-9_]+): u32 = (\d+);", open(os.path.join(ROOT, "rust", "retrofire-b200-sys", "src", "lib.rs")).read())}
+    assert rust_consts == ids, set(rust_consts.items()) ^ set(ids.items())
+    used_fs |= {rust_consts[n] for n in re.findall(r"const FS: u32 = sys::(RF_FS_\w+);", shim)}
+    used_vs |= {rust_consts[n] for n in re.findall(r"const VS: u32 = sys::(RF_VS_\w+);", shim)}
     assert used_fs == fs_ids, used_fs ^ fs_ids
     assert used_vs == vs_ids, used_vs ^ vs_ids
     for name, val in re.findall(r"const (?:VS|FS): u32 = (\d+); // (RF_\w+)", shim):
