@@ -17,7 +17,16 @@
 
 #define RF_TILE 32          // framebuffer tile: RF_TILE rows x RF_TILE columns, one warp owns one tile
 #define RF_TILE_SHIFT 5
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) move the depth tile between HBM and shared memory, one 128-byte row per lane:
+// rows must then start on 16-byte boundaries, i.e. a pitch of 36 words instead of the conflict-free 33.
+#ifndef RF_TMA_DEPTH
+#define RF_TMA_DEPTH 1
+#endif
+#if RF_TMA_DEPTH
+#define RF_TILE_PITCH 36    // smem row pitch in words: 144-byte rows (bank = (4 * row + col) % 32)
+#else
 #define RF_TILE_PITCH 33    // smem row pitch in words (bank = (row + col) % 32)
+#endif
 #define RF_MAX_ROWS (1u << 20)
 
 // per-draw flag bits

@@ -341,7 +341,7 @@ __device__ __forceinline__ float rust_clampf(float x, float lo, float hi) {
 
 // Catalogue fragment shaders. var[] already perspective-corrected. false = discard.
 template <int LT>
-__device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, const float* var, uint32_t& r, uint32_t& g, uint32_t& b, uint32_t& a) {
+__device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, const float* var, uint32_t& r, uint32_t& g, uint32_t& b, uint32_t& a, uint32_t* err = nullptr) {
   a = 0xFFu;
   switch (fs) {
     case RF_FS_COLOR3F:  // color.rs:246-263
@@ -399,7 +399,7 @@ __device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, c
     case RF_FS_TEX_ONCE: {  // tex.rs:313-357 SamplerOnce: no wrapping, no clamping; outside the texture the reference panics
       const float w = (float)D.tex_w, h = (float)D.tex_h;
       const uint32_t u = sat_u32(w * var[0]), v = sat_u32(h * var[LT >= 2 ? 1 : 0]);
-      if (u >= D.tex_w || v >= D.tex_h) { r = 0x100u; return false; }  // flagged to the caller through r
+      if (u >= D.tex_w || v >= D.tex_h) { if (err) atomicOr(err, RF_ERRBIT_TEXEL_OOB); return false; }  // the pass reports RF_E_BAD_TEXTURE
       const uint32_t c = __ldg(D.tex + (size_t)v * D.tex_w + u);
       r = c & 0xFFu; g = (c >> 8) & 0xFFu; b = (c >> 16) & 0xFFu; a = c >> 24;
       return true;
@@ -444,6 +444,37 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ void prefetch_l2(const void*) {}
 #endif
 
+// ---- TMA bulk copies of one tile row (cp.async.bulk: SASS UBLKCP), issued per lane -------------------------------------------
+#if RF_SMEM_ASM && RF_TMA_DEPTH
+#define RF_TMA_ON 1
+__device__ __forceinline__ void tma_mbar_init(uint32_t mbar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_mbar_expect(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_row(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tma_store_row(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_fence_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#else
+#define RF_TMA_ON 0
+#endif
+
 struct WarpSmem {
 #if RF_SMEM_ASM
   uint32_t a;
@@ -473,7 +504,7 @@ struct WarpSmem {
 };
 
 template <int LT>
-__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t sel, uint32_t* gp, WarpSmem sz, uint32_t idx, const float* v,
+__device__ __forceinline__ uint32_t process_fragment(const PassParams& P, const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t sel, uint32_t* gp, WarpSmem sz, uint32_t idx, const float* v,
                                                      uint32_t pmask, uint32_t dtest, bool cwrite, bool dwrite) {
   const float z = v[0];
   if (dtest != RF_DEPTH_NONE) {  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
@@ -490,7 +521,7 @@ __device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t
       if ((pmask >> i) & 1u) var[i] = zdiv(v[1 + i], z);
   }
   uint32_t r = 0, g = 0, bl = 0, a = 0;
-  if (!shade_fragment<LT>(D, fs, var, r, g, bl, a)) return r == 0x100u ? 0x80000000u : 0u;  // discard: no writes at all (bit 31: SamplerOnce left its texture)
+  if (!shade_fragment<LT>(D, fs, var, r, g, bl, a, &P.status->error)) return 0u;  // discard: no writes at all
   // A NaN depth (0 * inf in the setup of a zero-height trapezoid half) can only be written with depth_test = None: every
   // comparison with a NaN fails (ctx.rs:86-89). The reference's x86-64 host generates the default NaN 0xFFC00000 and
   // propagates it; CUDA arithmetic generates 0x7FFFFFFF. The bits written are the host's ("NaN contract").
@@ -550,7 +581,8 @@ template <int LT> struct RasterSmem {
   // word offsets inside a warp's region
   static constexpr int RC0 = TILE_WORDS;           // row coverage [RF_TILE]
   static constexpr int OW0 = RC0 + RF_TILE;        // owner table: one byte per item of the chunk
-  static constexpr int WARP_WORDS = OW0 + (int)RF_OWNER_ITEMS / 4;
+  static constexpr int MB0 = OW0 + (int)RF_OWNER_ITEMS / 4;  // mbarrier of the bulk loads (8 bytes), padded to keep warp regions 16-byte aligned
+  static constexpr int WARP_WORDS = MB0 + 4;
   static constexpr size_t BYTES = (size_t)RF_RASTER_WARPS * WARP_WORDS * 4;
 };
 
@@ -582,6 +614,11 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
   // OR their pixel runs in; popcount(coverage) == number of fragments <=> no two pieces of the batch share a pixel, and the
   // batch's fragment groups need no per-group same-pixel search (MATCH.ANY cost 10 % of this kernel's stall samples).
   wsm.stu(RC0 + lane, 0u);
+#if RF_TMA_ON
+#define RF_MBAR (wsm.a + RS::MB0 * 4u)  /* this warp's mbarrier for bulk loads of the depth tile */
+  uint32_t mb_parity = 0;
+  if (lane == 0) tma_mbar_init(RF_MBAR);
+#endif
   __syncwarp();
   // fast-path selectors of the last warp-uniform draw seen (span mode | fragment mode << 4): looked up once per draw, not per batch
   uint32_t mode_draw = 0xFFFFFFFFu, mode_bits = 0;
@@ -629,8 +666,18 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
     if (depth_live && (t_cflags & RF_CLEAR_DEPTH)) {
       const float cz = __uint_as_float(T.clear_zbits);
       for (uint32_t r = r0; r < r1; r++) sz[r * RF_TILE_PITCH + lane] = cz;
-    } else if (depth_live) {  // 128-bit coalesced loads, 8 lanes per row, 4 rows per instruction
+    } else if (depth_live) {
       const float* t_depth = T.depth;
+#if RF_TMA_ON
+      if (vec) {  // TMA: every lane asks for one 128-byte row; the warp's mbarrier counts the bytes in
+        tma_fence_proxy();  // earlier generic-proxy accesses to the tile region precede the async-proxy writes
+        if (lane == 0) tma_mbar_expect(RF_MBAR, (r1 - r0) * (RF_TILE * 4u));
+        __syncwarp();
+        if (lane >= r0 && lane < r1) tma_load_row(wsm.a + lane * (RF_TILE_PITCH * 4u), t_depth + (size_t)(py0 + lane) * t_w + px0, RF_TILE * 4u, RF_MBAR);
+        if (r1 > r0) { tma_mbar_wait(RF_MBAR, mb_parity); mb_parity ^= 1u; }
+      } else
+#endif
+      // 128-bit coalesced loads, 8 lanes per row, 4 rows per instruction
       if (vec && r1 - r0 == RF_TILE) {  // whole tile: all eight loads in flight before the first store
         const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
         float4 z[RF_TILE / 4];
@@ -972,9 +1019,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                   const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
                   const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
                   for (uint32_t k = 0; k < pn; k++) {
-                    const uint32_t pf = process_fragment<LT>(D, fs, t_fmt, t_sel, gp0 + k, wsm, pbase + k, v, pmask, dtest, cwrite, dwrite);
-                    if (pf & 0x80000000u) atomicOr(&P.status->error, RF_ERRBIT_TEXEL_OOB);
-                    my_o += pf & 1u;
+                    my_o += process_fragment<LT>(P, D, fs, t_fmt, t_sel, gp0 + k, wsm, pbase + k, v, pmask, dtest, cwrite, dwrite);
 #pragma unroll
                     for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
                   }
@@ -1050,9 +1095,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                   if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, t_sel, gp, wsm, pix, fv);
                   if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, t_fmt, t_sel, gp, wsm, pix, fv);
                   if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, t_sel, gp, wsm, pix, fv);
-                  const uint32_t pf = process_fragment<LT>(D, fs, t_fmt, t_sel, gp, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
-                  if (pf & 0x80000000u) atomicOr(&P.status->error, RF_ERRBIT_TEXEL_OOB);
-                  return pf & 1u;
+                  return process_fragment<LT>(P, D, fs, t_fmt, t_sel, gp, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
                 };
                 if (clean) {
                   if (fvalid) wrote = one();
@@ -1091,6 +1134,14 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
     // ---- write the depth tile back: 128-bit coalesced stores
     if (depth_live) {
       float* t_depth = T.depth;
+#if RF_TMA_ON
+      if (vec) {  // TMA: every lane stores one 128-byte row from shared memory; the region is reusable once the rows have been read
+        tma_fence_proxy();  // the fragments' st.shared are visible to the async proxy
+        __syncwarp();
+        if (lane >= r0 && lane < r1) tma_store_row(t_depth + (size_t)(py0 + lane) * t_w + px0, wsm.a + lane * (RF_TILE_PITCH * 4u), RF_TILE * 4u);
+        tma_store_commit_wait_read();
+      } else
+#endif
       if (vec) {
         const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
         for (uint32_t r = r0 + rsub; r < r1; r += 4) {
