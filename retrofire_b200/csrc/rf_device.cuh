@@ -20,7 +20,7 @@
 // TMA bulk copies (cp.async.bulk, SASS UBLKCP) move the depth tile between HBM and shared memory, one 128-byte row per lane:
 // rows must then start on 16-byte boundaries, i.e. a pitch of 36 words instead of the conflict-free 33.
 #ifndef RF_TMA_DEPTH
-#define RF_TMA_DEPTH 1
+#define RF_TMA_DEPTH 0   // opt-in build variant: measured 2-8 % slower than the LDG/STG path at pitch 33 (profiles/r02_ab_tma_depth.txt)
 #endif
 #if RF_TMA_DEPTH
 #define RF_TILE_PITCH 36    // smem row pitch in words: 144-byte rows (bank = (4 * row + col) % 32)

@@ -341,7 +341,7 @@ __device__ __forceinline__ float rust_clampf(float x, float lo, float hi) {
 
 // Catalogue fragment shaders. var[] already perspective-corrected. false = discard.
 template <int LT>
-__device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, const float* var, uint32_t& r, uint32_t& g, uint32_t& b, uint32_t& a, uint32_t* err = nullptr) {
+__device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, const float* var, uint32_t& r, uint32_t& g, uint32_t& b, uint32_t& a) {
   a = 0xFFu;
   switch (fs) {
     case RF_FS_COLOR3F:  // color.rs:246-263
@@ -380,10 +380,16 @@ __device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, c
       }
       return true;
     }
-    case RF_FS_TEX_CLAMP: {  // tests/rendering.rs:30
+    case RF_FS_TEX_ONCE:     // tex.rs:313-357 SamplerOnce: `(w * u) as u32`, no wrapping, no clamping; outside the texture the reference
+    case RF_FS_TEX_CLAMP: {  // panics (slice index) -> the pass reports RF_E_BAD_TEXTURE.   SamplerClamp: tests/rendering.rs:30
       const float w = (float)D.tex_w, h = (float)D.tex_h;
-      const uint32_t u = sat_u32(floorf(rust_clampf(var[0] * w, 0.0f, w - 1.0f)));
-      const uint32_t v = sat_u32(floorf(rust_clampf(var[LT >= 2 ? 1 : 0] * h, 0.0f, h - 1.0f)));
+      const float su = var[0] * w, sv = var[LT >= 2 ? 1 : 0] * h;  // Once multiplies as w * u: the product is the same
+      uint32_t u = sat_u32(floorf(rust_clampf(su, 0.0f, w - 1.0f)));
+      uint32_t v = sat_u32(floorf(rust_clampf(sv, 0.0f, h - 1.0f)));
+      if (fs == RF_FS_TEX_ONCE) {
+        u = sat_u32(su); v = sat_u32(sv);
+        if (u >= D.tex_w || v >= D.tex_h) return false;  // the only way this shader returns false: the caller raises the error
+      }
       const uint32_t c = __ldg(D.tex + (size_t)v * D.tex_w + u);
       r = c & 0xFFu; g = (c >> 8) & 0xFFu; b = (c >> 16) & 0xFFu; a = c >> 24;
       return true;
@@ -392,14 +398,6 @@ __device__ __forceinline__ bool shade_fragment(const DrawDesc& D, uint32_t fs, c
       const float w = (float)D.tex_w, h = (float)D.tex_h;
       const uint32_t u = (uint32_t)sat_i32(floorf(w * var[0])) & (D.tex_w - 1);
       const uint32_t v = (uint32_t)sat_i32(floorf(h * var[LT >= 2 ? 1 : 0])) & (D.tex_h - 1);
-      const uint32_t c = __ldg(D.tex + (size_t)v * D.tex_w + u);
-      r = c & 0xFFu; g = (c >> 8) & 0xFFu; b = (c >> 16) & 0xFFu; a = c >> 24;
-      return true;
-    }
-    case RF_FS_TEX_ONCE: {  // tex.rs:313-357 SamplerOnce: no wrapping, no clamping; outside the texture the reference panics
-      const float w = (float)D.tex_w, h = (float)D.tex_h;
-      const uint32_t u = sat_u32(w * var[0]), v = sat_u32(h * var[LT >= 2 ? 1 : 0]);
-      if (u >= D.tex_w || v >= D.tex_h) { if (err) atomicOr(err, RF_ERRBIT_TEXEL_OOB); return false; }  // the pass reports RF_E_BAD_TEXTURE
       const uint32_t c = __ldg(D.tex + (size_t)v * D.tex_w + u);
       r = c & 0xFFu; g = (c >> 8) & 0xFFu; b = (c >> 16) & 0xFFu; a = c >> 24;
       return true;
@@ -503,8 +501,11 @@ struct WarpSmem {
 #endif
 };
 
+// word (relative to the warp's shared-memory region) where a warp notes that SamplerOnce left its texture: the spare half of the
+// mbarrier slot, the same offset for every lane count
+#define RF_TEXERR_WORD (RF_TILE * RF_TILE_PITCH + RF_TILE + 1024u / 4u + 2u)
 template <int LT>
-__device__ __forceinline__ uint32_t process_fragment(const PassParams& P, const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t sel, uint32_t* gp, WarpSmem sz, uint32_t idx, const float* v,
+__device__ __forceinline__ uint32_t process_fragment(const DrawDesc& D, uint32_t fs, uint32_t fmt, uint32_t sel, uint32_t* gp, WarpSmem sz, uint32_t idx, const float* v,
                                                      uint32_t pmask, uint32_t dtest, bool cwrite, bool dwrite) {
   const float z = v[0];
   if (dtest != RF_DEPTH_NONE) {  // ctx.rs:86-89: curr.partial_cmp(&new) == Some(test)
@@ -521,7 +522,12 @@ __device__ __forceinline__ uint32_t process_fragment(const PassParams& P, const 
       if ((pmask >> i) & 1u) var[i] = zdiv(v[1 + i], z);
   }
   uint32_t r = 0, g = 0, bl = 0, a = 0;
-  if (!shade_fragment<LT>(D, fs, var, r, g, bl, a, &P.status->error)) return 0u;  // discard: no writes at all
+  if (!shade_fragment<LT>(D, fs, var, r, g, bl, a)) {  // discard: no writes at all
+    // SamplerOnce never discards: false means it indexed outside its texture, where the reference panics. The warp notes it in
+    // shared memory (an atomic here cost the whole kernel 330 bytes of register spills) and reports it after the tile.
+    if (fs == RF_FS_TEX_ONCE) sz.stu(RF_TEXERR_WORD, 1u);
+    return 0u;
+  }
   // A NaN depth (0 * inf in the setup of a zero-height trapezoid half) can only be written with depth_test = None: every
   // comparison with a NaN fails (ctx.rs:86-89). The reference's x86-64 host generates the default NaN 0xFFC00000 and
   // propagates it; CUDA arithmetic generates 0x7FFFFFFF. The bits written are the host's ("NaN contract").
@@ -614,6 +620,8 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
   // OR their pixel runs in; popcount(coverage) == number of fragments <=> no two pieces of the batch share a pixel, and the
   // batch's fragment groups need no per-group same-pixel search (MATCH.ANY cost 10 % of this kernel's stall samples).
   wsm.stu(RC0 + lane, 0u);
+  static_assert(RF_TEXERR_WORD == RS::MB0 + 2, "RF_TEXERR_WORD follows the RasterSmem layout");
+  if (lane == 0) wsm.stu(RF_TEXERR_WORD, 0u);
 #if RF_TMA_ON
 #define RF_MBAR (wsm.a + RS::MB0 * 4u)  /* this warp's mbarrier for bulk loads of the depth tile */
   uint32_t mb_parity = 0;
@@ -1019,7 +1027,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                   const uint32_t dtest = has_depth ? ((flags >> RF_F_DTEST_SHIFT) & RF_F_DTEST_MASK) : (uint32_t)RF_DEPTH_NONE;
                   const bool cwrite = (flags & RF_F_CWRITE) != 0, dwrite = has_depth && (flags & RF_F_DWRITE) != 0;
                   for (uint32_t k = 0; k < pn; k++) {
-                    my_o += process_fragment<LT>(P, D, fs, t_fmt, t_sel, gp0 + k, wsm, pbase + k, v, pmask, dtest, cwrite, dwrite);
+                    my_o += process_fragment<LT>(D, fs, t_fmt, t_sel, gp0 + k, wsm, pbase + k, v, pmask, dtest, cwrite, dwrite);
 #pragma unroll
                     for (int i = 0; i < NV; i++) v[i] = v[i] + dv[i];  // vary.rs:146-154
                   }
@@ -1095,7 +1103,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
                   if (MODE == 2) return process_fragment_fixed<LT, RF_FS_COLOR3F, 0u>(D, t_fmt, t_sel, gp, wsm, pix, fv);
                   if (MODE == 3) return process_fragment_fixed<LT, RF_FS_SPRITE_DISC, 0x3u>(D, t_fmt, t_sel, gp, wsm, pix, fv);
                   if (MODE == 4) return process_fragment_fixed<LT, RF_FS_TEX_CLAMP_LIT, 0x1Fu>(D, t_fmt, t_sel, gp, wsm, pix, fv);
-                  return process_fragment<LT>(P, D, fs, t_fmt, t_sel, gp, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
+                  return process_fragment<LT>(D, fs, t_fmt, t_sel, gp, wsm, pix, fv, pmask, dtest, cwrite, dwrite);
                 };
                 if (clean) {
                   if (fvalid) wrote = one();
@@ -1130,6 +1138,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
     }
     flush_acc();
     __syncwarp();
+    if (lane == 0 && wsm.ldu(RF_TEXERR_WORD) != 0u) { atomicOr(&P.status->error, RF_ERRBIT_TEXEL_OOB); wsm.stu(RF_TEXERR_WORD, 0u); }
 
     // ---- write the depth tile back: 128-bit coalesced stores
     if (depth_live) {

@@ -140,3 +140,18 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(os.path.dirname(here), "include"), "-c",
                         os.path.join(here, "c_header_check.c"), "-o", str(out)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_hot_kernels_do_not_spill():
+    """Register budget of the hot kernels as built (cuobjdump --dump-resource-usage of the shipped library). k_raster<3> is capped at
+    80 registers by its launch bounds (6 blocks per SM): one innocent-looking atomic in a fragment shader once pushed it from 48 to 378
+    bytes of spills and the bunny step from 2.50 to 3.13 ms (profiles/r02_ab_tma_depth.txt) — this keeps such a change from going unseen."""
+    rfbuild.build()
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {}
+    for fn, res in re.findall(r"Function (\w+):\s*\n\s*(REG:[^\n]*)", out):
+        usage[fn] = {k: int(v) for k, v in re.findall(r"(\w+):(\d+)", res)}
+    ras = usage["_Z8k_rasterILi3ELb0EEv10PassParams"]
+    assert ras["REG"] <= 80 and ras["STACK"] <= 64, ras
+    asm_ = usage["_Z10k_assembleILi3ELb1EEv10PassParams"]
+    assert asm_["REG"] <= 128, asm_
