@@ -27,7 +27,6 @@
 #include "rf_order.cuh"
 #include "rf_peer.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
 
 namespace {
 
@@ -274,6 +273,22 @@ uint32_t pack_pixel_host(uint32_t fmt, const uint8_t c[4]) {
 }
 
 // ---- pass launch ----------------------------------------------------------------------------------
+// Stable LSD radix sort of n (key, value) pairs on bits [0, end_bit) (rf_order.cuh): ping-pongs between the two buffer pairs,
+// returns the index (0 / 1) of the pair that holds the result.
+template <class K>
+int rsort_pairs(rf_ctx* c, PassSlot& s, const PassParams& P, K* const k[2], uint32_t* const v[2], uint32_t n, int end_bit, cudaStream_t st) {
+  const uint32_t nblk = (n + RF_RSORT_CHUNK - 1) / RF_RSORT_CHUNK;
+  uint32_t* hist = static_cast<uint32_t*>(c->ord_tmp.p);
+  int cur = 0;
+  for (int shift = 0; shift < end_bit; shift += 8, cur ^= 1) {
+    k_rsort_hist<K><<<nblk, 32, 0, st>>>(P, k[cur], n, (uint32_t)shift, hist, nblk);
+    k_rsort_scan<<<1, 256, 0, st>>>(P, hist, 256u * nblk);
+    k_rsort_scatter<K><<<nblk, 32, 0, st>>>(P, k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], n, (uint32_t)shift, hist, nblk);
+    s.n_launches += 3;
+  }
+  return cur;
+}
+
 // Context::depth_sort: replace the submission keys of the pass by ranks (rf_order.cuh). Runs between k_assemble and k_setup.
 void launch_order(rf_ctx* c, PassSlot& s, const PassParams& P, uint32_t QW, cudaStream_t st) {
   const uint32_t n = s.order_upper;
@@ -281,16 +296,15 @@ void launch_order(rf_ctx* c, PassSlot& s, const PassParams& P, uint32_t QW, cuda
   uint32_t* k32[2] = {static_cast<uint32_t*>(c->ord_k32[0].p), static_cast<uint32_t*>(c->ord_k32[1].p)};
   uint32_t* v[2] = {static_cast<uint32_t*>(c->ord_v[0].p), static_cast<uint32_t*>(c->ord_v[1].p)};
   unsigned long long* k64[2] = {static_cast<unsigned long long*>(c->ord_k64[0].p), static_cast<unsigned long long*>(c->ord_k64[1].p)};
-  size_t tmp = c->ord_tmp.cap;
   k_order_init<<<g, 256, 0, st>>>(P, QW, n, k32[0], v[0]);
-  cub::DeviceRadixSort::SortPairs(c->ord_tmp.p, tmp, k32[0], k32[1], v[0], v[1], (int)n, 0, 32, st);
-  k_order_keys<<<g, 256, 0, st>>>(P, QW, n, v[1], k64[0]);
+  const int a = rsort_pairs<uint32_t>(c, s, P, k32, v, n, 32, st);  // by submission key: restores primitive order
+  uint32_t* va[2] = {v[a], v[a ^ 1]};                               // the sorted indices are the input of the second sort
+  k_order_keys<<<g, 256, 0, st>>>(P, QW, n, va[0], k64[0]);
   int dbits = 1;
   while ((1ull << dbits) <= P.n_draws) dbits++;  // the padding key (all ones) stays above every draw index
-  tmp = c->ord_tmp.cap;
-  cub::DeviceRadixSort::SortPairs(c->ord_tmp.p, tmp, k64[0], k64[1], v[1], v[0], (int)n, 0, 32 + dbits, st);
-  k_order_apply<<<g, 256, 0, st>>>(P, QW, n, v[0]);
-  s.n_launches += 3;  // plus CUB's own kernels
+  const int b = rsort_pairs<unsigned long long>(c, s, P, k64, va, n, 32 + dbits, st);  // stable by (draw, depth bits)
+  k_order_apply<<<g, 256, 0, st>>>(P, QW, n, va[b]);
+  s.n_launches += 3;
 }
 
 #ifndef RF_FIRST_TOUCH_CLEAR
@@ -485,10 +499,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
   const uint32_t order_upper = any_sort ? (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(order_bound, cap_stris_el)) : 0u;
   size_t order_tmp = 0;
   if (order_upper) {
-    size_t t32 = 0, t64 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t32, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)order_upper, 0, 32);
-    cub::DeviceRadixSort::SortPairs(nullptr, t64, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)order_upper, 0, 64);
-    order_tmp = std::max(t32, t64) + 256;
+    order_tmp = (size_t)((order_upper + RF_RSORT_CHUNK - 1) / RF_RSORT_CHUNK) * 256 * 4 + 256;  // digit histograms of the radix sort
     need_idle = need_idle || c->sdepth.cap < cap_stris_el * 4 || c->ord_k32[0].cap < (size_t)order_upper * 4 || c->ord_tmp.cap < order_tmp;
   }
   s.order_upper = order_upper;

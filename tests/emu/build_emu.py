@@ -50,7 +50,7 @@ def stale() -> bool:
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, f) for f in FILES] + [os.path.join(ROOT, "include", "retrofire_b200.h"), os.path.abspath(__file__),
-                                                     os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(HERE, "include", "cub", "device", "device_radix_sort.cuh")]
+                                                     os.path.join(HERE, "include", "cuda_runtime.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
