@@ -506,12 +506,6 @@ __device__ __forceinline__ void line_walk(const PassParams& P, const TargetDesc&
 #define RF_CHUNK 32u
 #define RF_LONG_BLOCK 256u
 
-#ifndef RF_ASM_CHUNK_SMALL
-#define RF_ASM_CHUNK_SMALL 256u    // SMALL records a warp reserves at a time (0 entries wasted: holes are never referenced)
-#endif
-#ifndef RF_ASM_CHUNK_ENTRIES
-#define RF_ASM_CHUNK_ENTRIES 512u  // bin entries a warp reserves at a time
-#endif
 #ifndef RF_ASSEMBLE_MIN_BLOCKS
 #define RF_ASSEMBLE_MIN_BLOCKS 4   // <= 128 registers: measured -2 % on the bunny step against the unconstrained 147
 #endif
@@ -530,7 +524,6 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
   if (rf_poisoned(P)) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   const uint32_t n_iter = (P.NP + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
-  uint32_t sm_next = 0, sm_end = 0, en_next = 0, en_end = 0;  // the warp's reserved ranges of SMALL records / bin entries (warp-uniform)
   for (uint32_t it = 0; it < n_iter; it++) {
     const uint32_t gp = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     const bool have = gp < P.NP;
@@ -693,38 +686,19 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
       const uint32_t lmask = __ballot_sync(0xFFFFFFFFu, emit && !small), smask = __ballot_sync(0xFFFFFFFFu, small);
       if ((lmask | smask) == 0u) continue;
       const uint32_t incl_e = warp_scan_incl(nent, lane), tot_e = __shfl_sync(0xFFFFFFFFu, incl_e, 31);
-      // Allocation. SMALL records and bin entries come from ranges the warp reserves RF_ASM_CHUNK_* at a time: one same-address
-      // atomic per ~20 iterations instead of two per iteration (the counters are single words every warp of the grid hits, and
-      // same-address atomics serialise in L2 — 640 k of them per bunny pass). Unused entry slots are marked RF_NO_TILE (when
-      // the warp moves on to a new range, and at the end of the kernel); holes among the SMALL records are never referenced.
-      unsigned long long base = 0;
-      if (lane == 0 && lmask) base = atomicAdd(&P.status->stris_needed, (unsigned long long)__popc(lmask));
-      if (lmask) base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      bool over = base + __popc(lmask) > P.cap_stris;
-      const uint32_t ns = (uint32_t)__popc(smask);
-      if (ns != 0u && sm_next + ns > sm_end) {
-        unsigned long long b = 0;
-        if (lane == 0) b = atomicAdd(&P.status->small_needed, (unsigned long long)RF_ASM_CHUNK_SMALL);
-        b = __shfl_sync(0xFFFFFFFFu, b, 0);
-        if (b + RF_ASM_CHUNK_SMALL > P.cap_smalls) { over = true; sm_next = sm_end = 0; }
-        else { sm_next = (uint32_t)b; sm_end = sm_next + RF_ASM_CHUNK_SMALL; }
+      unsigned long long base = 0, sbase = 0, ebase = 0;
+      if (lane == 0) {
+        if (lmask) base = atomicAdd(&P.status->stris_needed, (unsigned long long)__popc(lmask));
+        if (smask) sbase = atomicAdd(&P.status->small_needed, (unsigned long long)__popc(smask));
+        if (tot_e) ebase = atomicAdd(&P.status->entries_needed, (unsigned long long)tot_e);
       }
-      if (tot_e != 0u && en_next + tot_e > en_end) {
-        for (uint32_t i = en_next + lane; i < en_end; i += 32) P.entries[i] = make_uint4(RF_NO_TILE, 0u, 0u, 0u);
-        const uint32_t want = max(tot_e, (uint32_t)RF_ASM_CHUNK_ENTRIES);
-        unsigned long long b = 0;
-        if (lane == 0) b = atomicAdd(&P.status->entries_needed, (unsigned long long)want);
-        b = __shfl_sync(0xFFFFFFFFu, b, 0);
-        if (b + want > P.cap_entries) { over = true; en_next = en_end = 0; }
-        else { en_next = (uint32_t)b; en_end = en_next + want; }
-      }
-      if (over) {
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
+      ebase = __shfl_sync(0xFFFFFFFFu, ebase, 0);
+      if (base + __popc(lmask) > P.cap_stris || sbase + __popc(smask) > P.cap_smalls || ebase + tot_e > P.cap_entries) {
         if (lane == 0) rf_overflow(P);
         continue;
       }
-      const uint32_t sbase = sm_next, ebase = en_next;
-      sm_next += ns;
-      en_next += tot_e;
       const uint32_t emask = lmask;  // screen-triangle records: the LARGE ones only
       uint32_t* const qstg = reinterpret_cast<uint32_t*>(s_q[RF_ASSEMBLE_STAGE ? threadIdx.x >> 5 : 0]);
       if (emit) {
@@ -797,7 +771,6 @@ __global__ void __launch_bounds__(128, RF_ASSEMBLE_MIN_BLOCKS) k_assemble(PassPa
       }
     }
   }
-  for (uint32_t i = en_next + lane; i < en_end; i += 32) P.entries[i] = make_uint4(RF_NO_TILE, 0u, 0u, 0u);  // the unused rest of the last range
 }
 
 // =============================================================================================
