@@ -94,33 +94,76 @@ def make_workload(name: str, frames: int):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line). NVML in-process (a sample
+    costs microseconds, so even a 50 ms region of 20 steps gets dozens); `nvidia-smi` as a subprocess only when NVML cannot be loaded
+    (a subprocess takes longer than a short timed region: round 1's 8-rank line had no sample at all)."""
 
-    def __init__(self, index: int):
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index: int, uuid: str | None = None):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+        self.index, self.uuid, self.stop_flag, self.rows = index, uuid, threading.Event(), []   # rows: (sm_mhz, max_mhz, [reason flags])
+        self.source = None
 
-    def run(self):
+    def _nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = None
+        if self.uuid:
+            try:
+                h = nv.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+            except Exception:
+                h = None
+        if h is None:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            h = nv.nvmlDeviceGetHandleByIndex(int(ids[self.index]) if self.index < len(ids) else self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        masks = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+
+        def sample():
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            return nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, [bool(r & m) for m in masks]
+        sample()
+        return sample
+
+    def _smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag.is_set():
+
+        def sample():
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            r = [s.strip() for s in out.split(",")]
+            return int(r[0]), int(r[1]), [x.lower().startswith("active") for x in r[2:6]]
+        return sample
+
+    def prepare(self):
+        """Open NVML before the timed region starts (library load is not part of the sampling)."""
+        try:
+            self.sample, self.source = self._nvml(), "nvml"
+        except Exception:
+            self.sample, self.source = self._smi(), "nvidia-smi"
+        return self
+
+    def run(self):
+        period = 0.002 if self.source == "nvml" else 0.1
+        while True:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([s.strip() for s in out.split(",")])
+                self.rows.append(self.sample())
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            if self.stop_flag.wait(period):   # the last sample is taken before the stop is seen: at least one lies in the region
+                break
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2][i] for r in self.rows if len(r[2]) > i)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows),
+                "source": self.source}
 
 
 def peaks():
@@ -273,9 +316,13 @@ def measure(ctx, workload: str, F: int, steps: int, warmup: int, e2e: bool, cpu_
     dev.profile(1)   # CUDA events around k_raster only: the timed passes keep their normal stream overlap
     if ctx["primary"]:
         torch.cuda.cudart().cudaProfilerStart()  # ncu --profile-from-start off: capture only the timed region
-    sampler = ClockSampler(ctx["local"])
-    sampler.start()
+    try:
+        uuid = str(torch.cuda.get_device_properties(torch.cuda.current_device()).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(ctx["local"], uuid).prepare()
     barrier()
+    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(steps):

@@ -85,6 +85,7 @@ struct PassSlot {
   bool in_flight = false;
   std::vector<QueuedClear> clears;
   std::vector<QueuedDraw> draws;
+  uint64_t prims_queued = 0;  // sum of draws[i].desc.n_prims (a pass addresses prims with 29 bits)
   std::vector<rf_target*> targets;
   PinnedBuf geom;       // pinned copy of host-pointer geometry
   size_t geom_len = 0;
@@ -692,6 +693,7 @@ rf_status launch_pass(rf_ctx* c, int si) {
 void reset_slot(PassSlot& s) {
   s.clears.clear();
   s.draws.clear();
+  s.prims_queued = 0;
   s.geom_len = 0;
   s.direct_len = 0;
   s.in_flight = false;
@@ -929,14 +931,15 @@ rf_status queue_draw(rf_ctx* c, rf_target* target, const rf_draw* d, const float
   std::memcpy(D.vp, d->viewport, sizeof D.vp);
   q.target = target;
   // a pass addresses targets with 16 bits and prims with 29 (key = prim*8 + fan index)
-  uint64_t np = D.n_prims;
-  for (auto& e : s.draws) np += e.desc.n_prims;
-  if (np >= (1u << 29) || s.draws.size() >= 60000) {
+  // (a running total: summing the queue here made a pass of n draws cost n^2 / 2 on the host — 447 ms for the 33,024 draws of a
+  // 128-frame crates batch, profiles/r02_bench_crates_1gpu.json before the fix)
+  if (s.prims_queued + D.n_prims >= (1u << 29) || s.draws.size() >= 60000) {
     rf_status st = flush_impl(c);
     if (st) return st;
     return queue_draw(c, target, d, vs_uniform_override);
   }
   s.draws.push_back(q);
+  s.prims_queued += D.n_prims;
   return RF_OK;
 }
 
