@@ -319,6 +319,10 @@ void launch_order(rf_ctx* c, PassSlot& s, const PassParams& P, uint32_t QW, cuda
 #ifndef RF_CLEAR_PLACE
 #define RF_CLEAR_PLACE 1
 #endif
+#ifndef RF_FUSED_CLEAR
+#define RF_FUSED_CLEAR 0   // 1: the untouched tiles of a first-touch clear are filled by k_raster's warps between their tiles (no k_clear_untouched
+#endif                     // launch). Measured: k_raster grows by exactly the clear kernel's time (1.25 -> 1.50 ms, step 2.553 -> 2.546 ms; sprites and
+                           // small triangles +2-3 %): the 1.5 GB of stores cost their HBM time wherever they are issued (profiles/r02_ab_fused_clear.txt)
 #ifndef RF_ASSEMBLE_THREADS
 #define RF_ASSEMBLE_THREADS 128
 #endif
@@ -329,7 +333,11 @@ void launch_order(rf_ctx* c, PassSlot& s, const PassParams& P, uint32_t QW, cuda
 #define RF_SORT_GRID_PER_SM 16
 #endif
 template <int LT>
-void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
+void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P0) {
+  PassParams P = P0;
+  const bool fused_clear = RF_FUSED_CLEAR && s.first_touch && !s.peer;
+  const bool clear_kernel = s.first_touch && !fused_clear;
+  P.fused_clear = fused_clear ? 1u : 0u;
   const int sm = c->sm_count;
   cudaStream_t st = c->stream;
   auto blocks = [&](size_t n, int bs, int per_sm) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + bs - 1) / bs, (size_t)sm * per_sm)); };
@@ -353,7 +361,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     mark(); k_ckpt<LT><<<sm * 8, 256, 0, st>>>(P);
     mark(); k_bin_sort_warp<<<sm * 8, RF_SORT_WARPS * 32, 0, st>>>(P);
     mark(); k_bin_sort_big<<<sm, 256, RF_SORT_BIG * 8, st>>>(P);
-    mark(); if (s.first_touch) k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
+    mark(); if (clear_kernel) k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
     mark();
     if (s.peer) {
       k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch1);
@@ -379,7 +387,7 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     // are filled on the ctx stream while the bins are sorted; 2: after k_raster, i.e. next to the geometry stage of the NEXT
     // pass (latency-bound kernels on the geo stream) — never next to k_raster itself, which that slowed by 14 %
     // (profiles/r02_ab_clear_placement.txt). With peers the clear must precede the cross-GPU barrier: always placement 1.
-    if (s.first_touch && (RF_CLEAR_PLACE == 1 || s.peer)) {
+    if (clear_kernel && (RF_CLEAR_PLACE == 1 || s.peer)) {
       cudaStreamWaitEvent(st, s.ev_fork, 0);
       k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
     }
@@ -400,10 +408,10 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P) {
     if (s.peer) k_raster<LT, true><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
     else k_raster<LT, false><<<raster_blocks, RF_RASTER_WARPS * 32, RasterSmem<LT>::BYTES, st>>>(P);
     if (prof == 1) cudaEventRecord(s.ev_k[RF_N_KERNELS], st);
-    if (s.first_touch && RF_CLEAR_PLACE == 2 && !s.peer) k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
+    if (clear_kernel && RF_CLEAR_PLACE == 2 && !s.peer) k_clear_untouched<<<clear_blocks, 256, 0, st>>>(P);
     if (s.peer) { k_peer_barrier<<<1, 32, 0, st>>>(c->pb, s.epoch2); s.n_launches++; }  // every peer's stores into this GPU have landed
   }
-  s.n_launches += RF_N_KERNELS - (s.first_touch ? 0 : 1);
+  s.n_launches += RF_N_KERNELS - (clear_kernel ? 0 : 1);
 }
 
 // Any growth frees memory that in-flight kernels might still use -> callers guarantee idleness.

@@ -147,6 +147,7 @@ struct PassParams {
   uint32_t use_sv;        // every draw of the pass has RF_F_SV: k_vertex stores screen-space vertices, k_assemble<LT, true> reads them
   uint32_t any_bbox;      // some draw of the pass carries RF_F_BBOX (k_objects ran)
   uint32_t tiles_per_target;  // every target of the pass has this many tiles (tile / it = target index), or 0 when they differ
+  uint32_t fused_clear;   // the first-touch clear of the tiles WITHOUT bin entries is done by k_raster's warps (no k_clear_untouched launch)
   uint32_t verts_per_draw, prims_per_draw;  // likewise for the draws of a frame batch (one mesh, many frames): index / it = draw, or 0
   float* cv;              // clip verts [NV][CVS]
   float* sv;              // screen verts [NV][SVS]: to_screen of every vertex inside the frustum, plus its outcode
@@ -173,7 +174,7 @@ struct PassParams {
   uint32_t* worklist;     // [n_tiles] non-empty tiles
   uint32_t* worklist_big; // [n_tiles]
   uint32_t* worklist_heavy; // [(RF_SLICES + 1) * n_tiles] rasterised first: slice tasks of the heaviest tiles, then the heavy tiles
-  uint32_t* cursors;      // [1] raster work cursor
+  uint32_t* cursors;      // [1] raster work cursor, [2] tile cursor of the fused first-touch clear
   DrawStats* dstats;      // [n_draws]
   PassStatus* status;
   CtxStatus* cstatus;

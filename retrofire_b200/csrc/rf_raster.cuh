@@ -323,6 +323,44 @@ __global__ void __launch_bounds__(256) k_bin_sort_big(PassParams P) {
   }
 }
 
+// The first-touch clear of ONE tile without bin entries, by one warp (128-bit stores, 8 lanes per row). Under sort-first sharding
+// only the rows of this GPU's band are cleared. Called by k_clear_untouched and, when the pass fuses the clear (PassParams::
+// fused_clear), by the rasteriser's warps between their tiles.
+__device__ __forceinline__ void clear_untouched_tile(const PassParams& P, uint32_t tile, uint32_t lane) {
+  uint32_t ti = 0;
+  if (P.tiles_per_target) ti = tile / P.tiles_per_target;
+  else {
+    uint32_t lo = 0, hi = P.n_targets;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.targets[mid].tile_base <= tile) lo = mid; else hi = mid; }
+    ti = lo;
+  }
+  const TargetDesc& T = P.targets[ti];
+  const uint32_t cf = T.clear_flags;
+  if (cf == 0u) return;
+  const uint32_t t_w = T.w;
+  const uint32_t tl = tile - T.tile_base;
+  const uint32_t ty = tl / T.tiles_x, tx = tl - ty * T.tiles_x;
+  const uint32_t px0 = tx << RF_TILE_SHIFT, py0 = ty << RF_TILE_SHIFT;
+  const uint32_t tw = min((uint32_t)RF_TILE, t_w - px0);
+  const uint32_t ya = max(py0, T.band_y0), yb = min(min(py0 + RF_TILE, T.h), T.band_y1);
+  const bool vec = (t_w & 3u) == 0 && tw == RF_TILE;
+  const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
+#pragma unroll
+  for (int plane = 0; plane < 2; plane++) {
+    if (!(cf & (plane ? RF_CLEAR_DEPTH : RF_CLEAR_COLOR))) continue;
+    uint32_t* buf = plane ? reinterpret_cast<uint32_t*>(T.depth) : T.color;
+    if (buf == nullptr) continue;
+    const uint32_t val = plane ? T.clear_zbits : T.clear_color;
+    if (vec) {
+      const uint4 v4 = make_uint4(val, val, val, val);
+      for (uint32_t y = ya + rsub; y < yb; y += 4) *reinterpret_cast<uint4*>(buf + (size_t)y * t_w + px0 + c4) = v4;
+    } else {
+      for (uint32_t y = ya; y < yb; y++)
+        if (lane < tw) buf[(size_t)y * t_w + px0 + lane] = val;
+    }
+  }
+}
+
 // =============================================================================================
 // K7: tile rasteriser. One warp owns one 32x32 tile: colour and depth are staged in shared
 // memory; the tile's triangles are taken in submission order, 32 at a time, and expanded into
@@ -632,11 +670,32 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
   uint32_t mode_draw = 0xFFFFFFFFu, mode_bits = 0;
   const uint32_t n_work = P.status->n_work, n_heaviest = P.status->n_work_heaviest, n_heavy = n_heaviest + P.status->n_work_heavy;
 
+  // Fused first-touch clear (PassParams::fused_clear, build knob RF_FUSED_CLEAR, off): the tiles WITHOUT bin entries are filled by
+  // this kernel's warps, a quota of tile ids per rasterised tile taken from a second cursor, instead of by k_clear_untouched.
+  const uint32_t n_tasks = n_work + n_heavy;
+  const uint32_t clear_quota = P.fused_clear ? (P.n_tiles + max(n_tasks, 1u) - 1u) / max(n_tasks, 1u) : 0u;
+  auto clear_some = [&](uint32_t q) -> bool {   // false: every tile id has been handed out
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(P.cursors + 2, q);
+    b = __shfl_sync(FULL, b, 0);
+    if (b >= P.n_tiles) return false;
+    const uint32_t e = min(b + q, P.n_tiles);
+    for (uint32_t t0 = b; t0 < e; t0 += 32) {
+      uint32_t m = __ballot_sync(FULL, t0 + lane < e && P.tile_cnt[t0 + lane] == 0u);
+      while (m) {
+        clear_untouched_tile(P, t0 + (uint32_t)__ffs(m) - 1u, lane);
+        m &= m - 1u;
+      }
+    }
+    return true;
+  };
+
   for (;;) {
     uint32_t wi = 0;
     if (lane == 0) wi = atomicAdd(P.cursors + 1, 1u);
     wi = __shfl_sync(FULL, wi, 0);
-    if (wi >= n_work + n_heavy) break;
+    if (wi >= n_tasks) break;
+    if (clear_quota) clear_some(clear_quota);
     const uint32_t task = wi < n_heaviest ? P.worklist_heavy[wi] : (wi < n_heavy ? P.worklist_heavy[(size_t)RF_SLICES * P.n_tiles + (wi - n_heaviest)] : P.worklist[wi - n_heavy]);
     const uint32_t tile = task & 0x0FFFFFFFu, slice = task >> 28;  // slice 0: whole tile; k+1: rows [k, k+1) * RF_TILE / RF_SLICES
     const uint32_t cnt = P.tile_cnt[tile], off = P.tile_off[tile];
@@ -1188,6 +1247,7 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
       }
     }
   }
+  if (P.fused_clear) while (clear_some(32u)) {}   // tile ids the quotas did not reach (all of them when the pass rasterises nothing)
 }
 
 // =============================================================================================
@@ -1221,36 +1281,6 @@ __global__ void __launch_bounds__(256) k_clear_untouched(PassParams P) {
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t tile = gw; tile < P.n_tiles; tile += nw) {
     if (P.tile_cnt[tile] != 0u) continue;
-    uint32_t ti = 0;
-    if (P.tiles_per_target) ti = tile / P.tiles_per_target;
-    else {
-      uint32_t lo = 0, hi = P.n_targets;
-      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.targets[mid].tile_base <= tile) lo = mid; else hi = mid; }
-      ti = lo;
-    }
-    const TargetDesc& T = P.targets[ti];
-    const uint32_t cf = T.clear_flags;
-    if (cf == 0u) continue;
-    const uint32_t tl = tile - T.tile_base;
-    const uint32_t ty = tl / T.tiles_x, tx = tl - ty * T.tiles_x;
-    const uint32_t px0 = tx << RF_TILE_SHIFT, py0 = ty << RF_TILE_SHIFT;
-    const uint32_t tw = min((uint32_t)RF_TILE, T.w - px0);
-    const uint32_t ya = max(py0, T.band_y0), yb = min(min(py0 + RF_TILE, T.h), T.band_y1);
-    const bool vec = (T.w & 3u) == 0 && tw == RF_TILE;
-    const uint32_t rsub = lane >> 3, c4 = (lane & 7u) << 2;
-#pragma unroll
-    for (int plane = 0; plane < 2; plane++) {
-      if (!(cf & (plane ? RF_CLEAR_DEPTH : RF_CLEAR_COLOR))) continue;
-      uint32_t* buf = plane ? reinterpret_cast<uint32_t*>(T.depth) : T.color;
-      if (buf == nullptr) continue;
-      const uint32_t val = plane ? T.clear_zbits : T.clear_color;
-      if (vec) {
-        const uint4 v4 = make_uint4(val, val, val, val);
-        for (uint32_t y = ya + rsub; y < yb; y += 4) *reinterpret_cast<uint4*>(buf + (size_t)y * T.w + px0 + c4) = v4;
-      } else {
-        for (uint32_t y = ya; y < yb; y++)
-          if (lane < tw) buf[(size_t)y * T.w + px0 + lane] = val;
-      }
-    }
+    clear_untouched_tile(P, tile, lane);
   }
 }
