@@ -1275,12 +1275,54 @@ __global__ void __launch_bounds__(256) k_clear_multi(const ClearDesc* __restrict
 // touched ones are initialised by k_raster. Runs on the side stream next to k_raster: the two
 // write disjoint tiles. Under sort-first sharding only the rows of this GPU's band are cleared.
 // =============================================================================================
+#ifndef RF_CLEAR_RUN
+#define RF_CLEAR_RUN 4   // k_clear_untouched: a warp takes this many consecutive tile ids; when all are untouched tiles of one tile row its stores
+#endif                   // cover 128 * RF_CLEAR_RUN contiguous bytes of a framebuffer row instead of four 128-byte pieces of four rows (1: per tile)
 __global__ void __launch_bounds__(256) k_clear_untouched(PassParams P) {
   if (rf_poisoned(P)) return;
   const uint32_t lane = lane_id();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t tile = gw; tile < P.n_tiles; tile += nw) {
-    if (P.tile_cnt[tile] != 0u) continue;
-    clear_untouched_tile(P, tile, lane);
+  constexpr uint32_t G = RF_CLEAR_RUN;
+  static_assert(G == 1 || G == 2 || G == 4, "RF_CLEAR_RUN: 32 lanes x 16 bytes cover at most four tiles of a row");
+  for (uint32_t t0 = gw * G; t0 < P.n_tiles; t0 += nw * G) {
+    const uint32_t cnt = lane < G && t0 + lane < P.n_tiles ? P.tile_cnt[t0 + lane] : 1u;
+    uint32_t um = __ballot_sync(0xFFFFFFFFu, cnt == 0u);
+    if (um == 0u) continue;
+    if (G > 1 && um == (1u << G) - 1u) {  // the whole group: one run if it lies in one tile row of one target, full tiles only
+      uint32_t ti = 0;
+      if (P.tiles_per_target) ti = t0 / P.tiles_per_target;
+      else {
+        uint32_t lo = 0, hi = P.n_targets;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.targets[mid].tile_base <= t0) lo = mid; else hi = mid; }
+        ti = lo;
+      }
+      const TargetDesc& T = P.targets[ti];
+      const uint32_t t_w = T.w, tiles_x = T.tiles_x;
+      const uint32_t tl = t0 - T.tile_base;
+      const uint32_t ty = tl / tiles_x, tx = tl - ty * tiles_x;
+      const uint32_t n_target_tiles = tiles_x * T.tiles_y;
+      if (tl + G <= n_target_tiles && tx + G <= tiles_x && ((tx + G) << RF_TILE_SHIFT) <= t_w && (t_w & 3u) == 0u) {
+        const uint32_t cf = T.clear_flags;
+        if (cf == 0u) continue;
+        const uint32_t px0 = tx << RF_TILE_SHIFT, py0 = ty << RF_TILE_SHIFT;
+        const uint32_t ya = max(py0, T.band_y0), yb = min(min(py0 + RF_TILE, T.h), T.band_y1);
+        constexpr uint32_t LPR = G * 8u;  // lanes per framebuffer row of the run
+        const uint32_t rsub = lane / LPR, c4 = (lane % LPR) << 2;
+#pragma unroll
+        for (int plane = 0; plane < 2; plane++) {
+          if (!(cf & (plane ? RF_CLEAR_DEPTH : RF_CLEAR_COLOR))) continue;
+          uint32_t* buf = plane ? reinterpret_cast<uint32_t*>(T.depth) : T.color;
+          if (buf == nullptr) continue;
+          const uint32_t val = plane ? T.clear_zbits : T.clear_color;
+          const uint4 v4 = make_uint4(val, val, val, val);
+          for (uint32_t y = ya + rsub; y < yb; y += 32u / LPR) *reinterpret_cast<uint4*>(buf + (size_t)y * t_w + px0 + c4) = v4;
+        }
+        continue;
+      }
+    }
+    while (um) {
+      clear_untouched_tile(P, t0 + (uint32_t)__ffs(um) - 1u, lane);
+      um &= um - 1u;
+    }
   }
 }

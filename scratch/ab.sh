@@ -10,7 +10,7 @@ for rep in 1 2; do
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        j = json.loads(l); print('$v', '$n', round(j['ms_per_step'], 4), 'ms/step', round(j['frames_per_s']), 'fps', 'raster', round(j['roofline']['kernel_ms_avg'], 4))
+        j = json.loads(l); print('$v', '$n', round(j['ms_per_step'], 4), 'ms/step', round(j['frames_per_s']), 'fps', 'raster', round(j['roofline']['kernel_ms_avg'], 4), 'shares', {k[2:]: v for k, v in j['roofline']['kernel_time_share'].items() if v >= 0.02})
 "
     done
   done
