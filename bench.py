@@ -254,24 +254,32 @@ def committed_traffic(workload: str, frames: int):
     return int(e["dram_bytes_read"] + e["dram_bytes_write"]), e.get("pass_dram_bytes")
 
 
-def measure_pcie(torch, dist, world, seconds: float = 0.6):
+def measure_pcie(torch, dist, world, seconds: float = 1.0):
     """Device-to-host DMA ceiling of this box with all `world` ranks copying at once (page-locked destination), GB/s per rank
-    and aggregate: the denominator of the end-to-end leg, whose every frame ends with one colour buffer crossing PCIe."""
-    n = 256 << 20
+    and aggregate: the denominator of the end-to-end leg, whose every frame ends with one colour buffer crossing PCIe.
+    Copies of 64 MB are timed one by one with CUDA events for `seconds`; the first third is warm-up (the link leaves its idle
+    state under load — a ceiling read during the ramp came out BELOW the rate the end-to-end leg then reached), the figure is
+    the median rate of the rest."""
+    n = 64 << 20
     src = torch.empty(n, dtype=torch.uint8, device="cuda")
     dst = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     dst.copy_(src, non_blocking=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    rates = []
     t0 = time.perf_counter()
-    reps = 0
     while time.perf_counter() - t0 < seconds:
-        dst.copy_(src, non_blocking=True)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(9)]
+        evs[0].record()
+        for k in range(8):
+            dst.copy_(src, non_blocking=True)
+            evs[k + 1].record()
         torch.cuda.synchronize()
-        reps += 1
-    dt = time.perf_counter() - t0
-    mine = reps * n / dt / 1e9
+        now = time.perf_counter() - t0
+        rates += [(now, n / (evs[k].elapsed_time(evs[k + 1]) * 1e-3) / 1e9) for k in range(8)]
+    late = sorted(r for t, r in rates if t >= seconds / 3) or sorted(r for t, r in rates)
+    mine = late[len(late) // 2]
     tot = mine
     if world > 1:
         t = torch.tensor([mine], device="cuda", dtype=torch.float64)

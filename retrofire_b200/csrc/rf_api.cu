@@ -127,6 +127,8 @@ struct rf_target {
   uint32_t n_peers = 0;           // colour buffers of the same target on the other GPUs that this GPU pushes its tiles into
   uint32_t* peer_color[RF_MAX_PEERS] = {};
   bool peer_ipc[RF_MAX_PEERS] = {};  // opened with cudaIpcOpenMemHandle (closed on destroy)
+  uint32_t* d_lazy = nullptr;     // lazy depth clear: RF_LAZY_WORDS words per tile (TargetDesc::lazy), zero = no tile is lazy
+  bool lazy_off = false;          // the depth plane's device pointer was handed out: its memory is kept materialised from then on
 };
 struct rf_texture {
   rf_ctx* ctx;
@@ -323,6 +325,9 @@ void launch_order(rf_ctx* c, PassSlot& s, const PassParams& P, uint32_t QW, cuda
 #define RF_FUSED_CLEAR 0   // 1: the untouched tiles of a first-touch clear are filled by k_raster's warps between their tiles (no k_clear_untouched
 #endif                     // launch). Measured: k_raster grows by exactly the clear kernel's time (1.25 -> 1.50 ms, step 2.553 -> 2.546 ms; sprites and
                            // small triangles +2-3 %): the 1.5 GB of stores cost their HBM time wherever they are issued (profiles/r02_ab_fused_clear.txt)
+#ifndef RF_LAZY_DEPTH
+#define RF_LAZY_DEPTH 1    // a first-touch depth clear marks the untouched tiles (TargetDesc::lazy) instead of filling them
+#endif
 #ifndef RF_ASSEMBLE_THREADS
 #define RF_ASSEMBLE_THREADS 128
 #endif
@@ -452,6 +457,18 @@ rf_status wait_idle(rf_ctx* c) {
 }
 
 // Launch (or re-launch) the pass stored in slot `si`.
+// ---- lazy depth clear (TargetDesc::lazy)
+uint32_t lazy_tiles(const rf_target* t) { return ((t->w + RF_TILE - 1) >> RF_TILE_SHIFT) * ((t->h + RF_TILE - 1) >> RF_TILE_SHIFT); }
+uint32_t lazy_words(const rf_target* t) { return lazy_tiles(t) * RF_LAZY_WORDS; }
+// writes the marked tiles of the target out, on the ctx stream (ordered after every pass launched so far)
+void lazy_materialize(rf_ctx* c, rf_target* t) {
+  if (!t->d_lazy || t->lazy_off) return;
+  const uint32_t nt = lazy_tiles(t);
+  const unsigned grid = std::max(1u, std::min((nt + 7u) / 8u, (uint32_t)c->sm_count * 8u));
+  const uint32_t tiles_x = (t->w + RF_TILE - 1) >> RF_TILE_SHIFT;
+  k_lazy_materialize<<<grid, 256, 0, c->stream>>>(t->d_depth, t->d_lazy, t->w, t->h, tiles_x, nt);
+}
+
 rf_status launch_pass(rf_ctx* c, int si) {
   PassSlot& s = c->slots[si];
   const size_t nd = s.draws.size();
@@ -563,13 +580,16 @@ rf_status launch_pass(rf_ctx* c, int si) {
     T.band_y0 = std::min(c->band_y0, t->h); T.band_y1 = std::min(c->band_y1, t->h);
     T.n_peers = t->n_peers;
     T.clear_flags = 0; T.clear_color = 0; T.clear_zbits = 0;
+    T.lazy = (t->has_depth && t->d_lazy && !t->lazy_off) ? t->d_lazy : nullptr;
+    // new lazy marks: not under sort-first sharding (a band owns part of a tile's rows; peers gather depth planes as memory)
+    const bool lazy_ok = T.lazy != nullptr && !t->peer_mode && c->band_y0 == 0 && c->band_y1 >= t->h;
     // First-touch clear: a Frame::clear recorded at the head of this pass for a target the pass draws into is carried out by
     // k_raster (touched tiles) and k_clear_untouched (the others). With peers attached the other GPUs store their bands into
     // this colour buffer, so its colour plane is still cleared as a whole, before the first cross-GPU barrier.
     for (const QueuedClear& qc : s.clears) {
       if (qc.target != t || !RF_FIRST_TOUCH_CLEAR) continue;
       if (qc.has_color && !t->peer_mode) { T.clear_flags |= RF_CLEAR_COLOR; T.clear_color = qc.color; }
-      if (qc.has_depth) { T.clear_flags |= RF_CLEAR_DEPTH; T.clear_zbits = qc.zbits; }
+      if (qc.has_depth) { T.clear_flags |= RF_CLEAR_DEPTH | (lazy_ok ? RF_CLEAR_LAZY : 0u); T.clear_zbits = qc.zbits; }
     }
     for (uint32_t p = 0; p < RF_MAX_PEERS; p++) T.peer_color[p] = p < t->n_peers ? t->peer_color[p] : nullptr;
     if (t->peer_mode && nd) s.peer = true;
@@ -587,9 +607,15 @@ rf_status launch_pass(rf_ctx* c, int si) {
       const unsigned long long n = (unsigned long long)(y1 > y0 ? y1 - y0 : 0) * qc.target->w;
       // with peers attached the other GPUs store THEIR bands into this buffer: the colour clear covers every row
       const bool ft = drawn(qc.target);
-      if (qc.has_color && qc.target->peer_mode) h_clears[k++] = ClearDesc{qc.target->d_color, (unsigned long long)qc.target->w * qc.target->h, qc.color, 0u};
-      else if (qc.has_color && !ft) h_clears[k++] = ClearDesc{qc.target->d_color + first, n, qc.color, 0u};
-      if (qc.has_depth && !ft) h_clears[k++] = ClearDesc{reinterpret_cast<uint32_t*>(qc.target->d_depth) + first, n, qc.zbits, 0u};
+      if (qc.has_color && qc.target->peer_mode) h_clears[k++] = ClearDesc{qc.target->d_color, (unsigned long long)qc.target->w * qc.target->h, qc.color, 0u, nullptr};
+      else if (qc.has_color && !ft) h_clears[k++] = ClearDesc{qc.target->d_color + first, n, qc.color, 0u, nullptr};
+      if (qc.has_depth && !ft) {
+        // the plane is written as memory: no tile of it stays lazy (a band clears only its rows: the marked tiles are written out first)
+        rf_target* qt = qc.target;
+        const bool lazy = qt->d_lazy && !qt->lazy_off, whole = y0 == 0 && y1 >= qt->h;
+        if (lazy && !whole) lazy_materialize(c, qt);
+        h_clears[k++] = ClearDesc{reinterpret_cast<uint32_t*>(qt->d_depth) + first, n, qc.zbits, lazy && whole ? lazy_words(qt) : 0u, qt->d_lazy};
+      }
     }
   }
 
@@ -1072,6 +1098,10 @@ rf_status rf_target_create(rf_ctx* c, uint32_t w, uint32_t h, uint32_t fmt, int 
   if (has_depth && cudaMalloc(&t->d_depth, n * 4) != cudaSuccess) { cudaFree(t->d_color); delete t; return fail(c, RF_E_NOMEM, "depth buffer"); }
   cudaMemsetAsync(t->d_color, 0, n * 4, c->stream);  // Buf2::new zero-fills (util/buf.rs:155-161)
   if (has_depth) cudaMemsetAsync(t->d_depth, 0, n * 4, c->stream);
+  if (has_depth && RF_LAZY_DEPTH) {
+    if (cudaMalloc(&t->d_lazy, (size_t)lazy_words(t) * 4) != cudaSuccess) { cudaFree(t->d_color); cudaFree(t->d_depth); delete t; return fail(c, RF_E_NOMEM, "lazy tile table"); }
+    cudaMemsetAsync(t->d_lazy, 0, (size_t)lazy_words(t) * 4, c->stream);
+  }
   *out = t;
   return RF_OK;
 }
@@ -1083,6 +1113,7 @@ void rf_target_destroy(rf_target* t) {
   for (uint32_t p = 0; p < t->n_peers; p++) if (t->peer_ipc[p]) cudaIpcCloseMemHandle(t->peer_color[p]);
   cudaFree(t->d_color);
   if (t->d_depth) cudaFree(t->d_depth);
+  if (t->d_lazy) cudaFree(t->d_lazy);
   delete t;
 }
 
@@ -1164,6 +1195,7 @@ rf_status rf_target_upload_depth(rf_ctx* c, rf_target* t, const float* host, siz
   if (!c || !t || !host || stride < t->w || !t->has_depth) return fail(c, RF_E_INVALID, "bad upload arguments");
   rf_status st = sync_impl(c);
   if (st) return st;
+  lazy_materialize(c, t);  // clears the marks: the plane is memory again before it is overwritten
   RF_CUDA(c, cudaMemcpy2DAsync(t->d_depth, (size_t)t->w * 4, host, stride * 4, (size_t)t->w * 4, t->h, cudaMemcpyHostToDevice, c->stream));
   RF_CUDA(c, cudaStreamSynchronize(c->stream));
   return RF_OK;
@@ -1173,13 +1205,25 @@ rf_status rf_target_download_depth(rf_ctx* c, rf_target* t, float* host, size_t 
   if (!c || !t || !host || stride < t->w || !t->has_depth) return fail(c, RF_E_INVALID, "bad download arguments");
   rf_status st = sync_impl(c);
   if (st) return st;
+  lazy_materialize(c, t);
   RF_CUDA(c, cudaMemcpy2DAsync(host, stride * 4, t->d_depth, (size_t)t->w * 4, (size_t)t->w * 4, t->h, cudaMemcpyDeviceToHost, c->stream));
   RF_CUDA(c, cudaStreamSynchronize(c->stream));
   return RF_OK;
 }
 
 void* rf_target_color_devptr(rf_target* t) { return t ? t->d_color : nullptr; }
-void* rf_target_depth_devptr(rf_target* t) { return t ? t->d_depth : nullptr; }
+void* rf_target_depth_devptr(rf_target* t) {
+  if (!t) return nullptr;
+  // The caller is about to read or write the plane as plain memory, with its own ordering on the ctx stream: write the lazy
+  // tiles out now (stream-ordered after the passes launched so far — queued ones are flushed first) and keep the plane
+  // materialised from here on.
+  if (t->d_lazy && !t->lazy_off) {
+    flush_impl(t->ctx);
+    lazy_materialize(t->ctx, t);
+    t->lazy_off = true;
+  }
+  return t->d_depth;
+}
 
 rf_status rf_texture_create(rf_ctx* c, uint32_t w, uint32_t h, uint32_t fmt, const void* data, size_t stride, rf_texture** out) {
   if (!c || !out || !data || !w || !h || fmt > RF_TEXEL_RGBA8888 || stride < w) return fail(c, RF_E_INVALID, "bad texture arguments");

@@ -81,10 +81,17 @@ struct TargetDesc {
   // before the first fragment), k_clear_untouched fills the other tiles — every pixel is written once.
   uint32_t clear_flags;           // RF_CLEAR_COLOR | RF_CLEAR_DEPTH
   uint32_t clear_color, clear_zbits;
+  // Lazy depth clear (RF_LAZY_DEPTH): three words per tile of the target — {lazy, zbits, slices done}. lazy != 0: every depth value
+  // of the tile equals zbits and has NOT been written to `depth` (a first-touch clear marked the untouched tile instead of
+  // filling it); the rasteriser that next touches the tile starts from zbits without a load and writes the tile back, after
+  // which the tile is ordinary memory again; every host-visible read of the depth plane materialises first. nullptr: off.
+  uint32_t* lazy;
   uint32_t* peer_color[RF_MAX_PEERS];
 };
+#define RF_LAZY_WORDS 3u
 #define RF_CLEAR_COLOR 1u
 #define RF_CLEAR_DEPTH 2u
+#define RF_CLEAR_LAZY 4u    // with RF_CLEAR_DEPTH: the untouched tiles are marked in TargetDesc::lazy instead of being filled
 
 struct DrawStats {
   unsigned long long prims_o, frags_i, frags_o;
@@ -134,7 +141,8 @@ struct ClearDesc {
   uint32_t* ptr;
   unsigned long long n;
   uint32_t value;
-  uint32_t _pad;
+  uint32_t n_lazy;   // depth plane of a target with lazy tiles: the words of `lazy` to zero (the plane is written as a whole)
+  uint32_t* lazy;
 };
 
 struct PassParams {

@@ -351,6 +351,13 @@ __device__ __forceinline__ void clear_untouched_tile(const PassParams& P, uint32
     uint32_t* buf = plane ? reinterpret_cast<uint32_t*>(T.depth) : T.color;
     if (buf == nullptr) continue;
     const uint32_t val = plane ? T.clear_zbits : T.clear_color;
+    if (plane && T.lazy != nullptr) {
+      if (cf & RF_CLEAR_LAZY) {  // lazy depth clear: mark the tile, write nothing
+        if (lane == 0) { T.lazy[tl * RF_LAZY_WORDS + 1u] = val; T.lazy[tl * RF_LAZY_WORDS] = 1u; }
+        continue;
+      }
+      if (lane == 0) T.lazy[tl * RF_LAZY_WORDS] = 0u;  // filled as memory below: an older mark ends here
+    }
     if (vec) {
       const uint4 v4 = make_uint4(val, val, val, val);
       for (uint32_t y = ya + rsub; y < yb; y += 4) *reinterpret_cast<uint4*>(buf + (size_t)y * t_w + px0 + c4) = v4;
@@ -730,8 +737,11 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
     uint32_t nb_tri = lane < cnt ? (uint32_t)P.bins[off + lane] : 0u;
     // ---- stage the depth tile. First touch after a Frame::clear of this pass: the clear value, no load at all.
     const bool depth_live = has_depth && !(clear_only && !(t_cflags & RF_CLEAR_DEPTH));
-    if (depth_live && (t_cflags & RF_CLEAR_DEPTH)) {
-      const float cz = __uint_as_float(T.clear_zbits);
+    // lazy tile (TargetDesc::lazy): an earlier first-touch clear marked it instead of filling it — start from its value, no load
+    uint32_t* const lz = depth_live && T.lazy != nullptr ? T.lazy + (size_t)tl * RF_LAZY_WORDS : nullptr;
+    const bool was_lazy = lz != nullptr && !(t_cflags & RF_CLEAR_DEPTH) && lz[0] != 0u;
+    if (depth_live && ((t_cflags & RF_CLEAR_DEPTH) || was_lazy)) {
+      const float cz = __uint_as_float(was_lazy ? lz[1] : T.clear_zbits);
       for (uint32_t r = r0; r < r1; r++) sz[r * RF_TILE_PITCH + lane] = cz;
     } else if (depth_live) {
       const float* t_depth = T.depth;
@@ -1220,6 +1230,15 @@ __global__ void __launch_bounds__(RF_RASTER_WARPS * 32, RasterOcc<LT>::BLOCKS) k
         for (uint32_t r = r0; r < r1; r++)
           if (lane < tw) t_depth[(size_t)(py0 + r) * t_w + px0 + lane] = sz[r * RF_TILE_PITCH + lane];
       }
+      // the rows this task owns are real depth values now: the tile stops being lazy once every task of the tile has written
+      // (a heaviest tile is RF_SLICES tasks, and a slice that starts late must still see the mark)
+      if (lz != nullptr && lane == 0) {
+        if (slice == 0u) lz[0] = 0u;
+        else {
+          __threadfence();
+          if (atomicAdd(lz + 2, 1u) == RF_SLICES - 1u) { lz[2] = 0u; lz[0] = 0u; }
+        }
+      }
     }
     __syncwarp();
 
@@ -1265,6 +1284,7 @@ __global__ void __launch_bounds__(256) k_clear_multi(const ClearDesc* __restrict
   const uint4 v4 = make_uint4(c.value, c.value, c.value, c.value);
   const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
   if (tid < head) c.ptr[tid] = c.value;
+  for (size_t i = tid; i < c.n_lazy; i += nth) c.lazy[i] = 0u;  // the whole depth plane is written: no tile stays lazy
   for (size_t i = tid; i < n4; i += nth) p4[i] = v4;
   for (size_t i = (n4 << 2) + tid; i < nb; i += nth) body[i] = c.value;
 }
@@ -1314,6 +1334,13 @@ __global__ void __launch_bounds__(256) k_clear_untouched(PassParams P) {
           uint32_t* buf = plane ? reinterpret_cast<uint32_t*>(T.depth) : T.color;
           if (buf == nullptr) continue;
           const uint32_t val = plane ? T.clear_zbits : T.clear_color;
+          if (plane && T.lazy != nullptr) {
+            if (cf & RF_CLEAR_LAZY) {  // lazy depth clear: mark the G tiles, write nothing
+              if (lane < G) { T.lazy[(tl + lane) * RF_LAZY_WORDS + 1u] = val; T.lazy[(tl + lane) * RF_LAZY_WORDS] = 1u; }
+              continue;
+            }
+            if (lane < G) T.lazy[(tl + lane) * RF_LAZY_WORDS] = 0u;
+          }
           const uint4 v4 = make_uint4(val, val, val, val);
           for (uint32_t y = ya + rsub; y < yb; y += 32u / LPR) *reinterpret_cast<uint4*>(buf + (size_t)y * t_w + px0 + c4) = v4;
         }
@@ -1324,5 +1351,25 @@ __global__ void __launch_bounds__(256) k_clear_untouched(PassParams P) {
       clear_untouched_tile(P, t0 + (uint32_t)__ffs(um) - 1u, lane);
       um &= um - 1u;
     }
+  }
+}
+
+// =============================================================================================
+// Lazy depth clear: write the marked tiles of ONE target out (before a download / upload of its depth plane or before its
+// device pointer is handed out). One warp per tile.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_lazy_materialize(float* depth, uint32_t* lazy, uint32_t w, uint32_t h, uint32_t tiles_x, uint32_t n_tiles) {
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t tl = gw; tl < n_tiles; tl += nw) {
+    if (lazy[tl * RF_LAZY_WORDS] == 0u) continue;
+    const float z = __uint_as_float(lazy[tl * RF_LAZY_WORDS + 1u]);
+    const uint32_t ty = tl / tiles_x, tx = tl - ty * tiles_x;
+    const uint32_t px0 = tx << RF_TILE_SHIFT, py0 = ty << RF_TILE_SHIFT;
+    const uint32_t tw = min((uint32_t)RF_TILE, w - px0), th = min((uint32_t)RF_TILE, h - py0);
+    for (uint32_t r = 0; r < th; r++)
+      if (lane < tw) depth[(size_t)(py0 + r) * w + px0 + lane] = z;
+    __syncwarp();
+    if (lane == 0) { lazy[tl * RF_LAZY_WORDS] = 0u; lazy[tl * RF_LAZY_WORDS + 2u] = 0u; }
   }
 }

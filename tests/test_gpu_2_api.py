@@ -285,6 +285,66 @@ def test_two_clears_without_a_draw_keep_the_last_value(device):
     assert (c == np.array([1, 2, 3, 4], np.uint8)).all() and (d == np.float32(0.125)).all()
 
 
+def test_lazy_depth_tiles_through_later_passes(device, oracle):
+    """Lazy depth clear: a clear recorded with draws marks the tiles the pass does not touch instead of filling their
+    depth. Every way such a tile is used afterwards must see the clear value: a later pass without a clear (one warp per tile, and a
+    heaviest tile cut into row slices), a download, a second clear with another value, a clear without draws (the plane is written
+    as memory), an upload over marked tiles, and the raw device pointer (which ends laziness for the target). One device target
+    and one oracle target go through the same sequence; colour, depth and Stats are compared after every step."""
+    w, h = 256, 192
+    few = scenes.random_soup(40, w, h, seed=61, lanes_kind="color3", big=False)       # most of the 48 tiles stay untouched
+    some = scenes.random_soup(300, w, h, seed=63, lanes_kind="uv", big=True)
+    many = scenes.random_soup(6000, w, h, seed=62, lanes_kind="color3", big=True)     # >= 160 triangles per tile: row-slice tasks
+    fb = device.framebuf(w, h, few.fmt, True)
+    ref = oracle.HostTarget(w, h, few.fmt, True)
+    dstat, rstat = rf.Stats(), rf.Stats()
+
+    def draw(sc):
+        nonlocal rstat
+        for d in sc.draws:
+            device.render(d, fb)
+            rstat += oracle.render(d, ref)
+
+    def clear(color, depth):
+        fb.clear(rf.Context(color_clear=color, depth_clear=depth))
+        ref.clear(color, depth)
+
+    def same(step, depth=True):
+        nonlocal dstat
+        dstat += device.stats(reset=True)
+        assert np.array_equal(fb.download_color(), ref.host_color()), step
+        if depth:
+            assert depth_equal(fb.download_depth(), ref.depth), step
+        assert dstat.counters() == rstat.counters(), step
+
+    try:
+        device.stats(reset=True)
+        clear((10, 20, 30, 255), 8.0); draw(few); device.flush()
+        draw(some); device.flush()                                   # no clear: marked tiles are first touched here
+        same("later pass, one warp per tile")
+        clear(None, 4.0); draw(few); device.flush()                  # marked again, with another value
+        draw(many); device.flush()                                   # no clear: marked tiles rasterised as row slices
+        same("later pass, row slices", depth=False)                  # colour first: the depth download below materialises
+        draw(few)
+        same("after the slices")
+        clear((1, 2, 3, 4), 2.0); draw(few); device.flush()          # marked
+        clear((5, 6, 7, 8), 16.0); device.flush()                    # a clear without draws writes the whole plane
+        draw(some)
+        same("clear without draws over marked tiles")
+        clear(None, 2.0); draw(few); device.flush()                  # marked
+        up = np.random.default_rng(7).uniform(0.05, 0.6, (h, w)).astype(f32)
+        fb.upload_depth(up); ref.depth[:] = up
+        draw(some)
+        same("upload over marked tiles")
+        clear((9, 9, 9, 255), 32.0); draw(few); device.flush()       # marked
+        assert fb.depth_devptr()                                      # handed out: written out, and kept as memory from here on
+        draw(some); device.flush()
+        clear(None, 8.0); draw(few); device.flush(); draw(some)
+        same("after the device pointer was handed out")
+    finally:
+        fb._destroy(); device._targets.remove(fb)
+
+
 def test_batch_builder_mirrors_render(device, oracle):
     """`Batch` (batch.rs:31-147): the builder's render() is render() with the same arguments; clone() leaves the original usable
     (crates.rs:103-130 clones one batch per crate). Stats accumulate in the Context like render.rs:206."""

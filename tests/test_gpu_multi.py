@@ -66,6 +66,20 @@ def test_two_gpu_sort_first_with_nccl_gather():
     assert dict(out) == {0: True, 1: True}
 
 
+def test_all_gpus_sort_first_with_nccl_gather():
+    """The same frame cut into as many row bands as the box has GPUs (4 or 8): bands of 192 / 96 rows, gathered frame and summed
+    Stats equal to the unsharded oracle frame."""
+    import torch
+    world = min(torch.cuda.device_count(), 8)
+    if world < 4:
+        pytest.skip("needs >= 4 GPUs (the 2-GPU case is the test above)")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {r: True for r in range(world)}
+
+
 def _peer_worker(rank, world, port, out):
     import torch
     import torch.distributed as dist
@@ -171,3 +185,16 @@ def test_peer_stores_between_two_contexts_on_one_gpu(oracle):
         finally:
             for dev in devs:
                 dev.close()
+
+
+def test_all_gpus_sort_first_fused_peer_stores():
+    """The fused exchange with every GPU of the box (4 or 8 ranks, each pushing its band into all the others)."""
+    import torch
+    world = min(torch.cuda.device_count(), 8)
+    if world < 4:
+        pytest.skip("needs >= 4 GPUs (the 2-GPU case is the test above)")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_peer_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {r: True for r in range(world)}
