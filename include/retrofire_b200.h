@@ -188,7 +188,11 @@ void rf_host_free(void* p);
  * callers that use this must have warmed the arenas up, or use the synchronous download. */
 rf_status rf_target_download_color_async(rf_ctx* ctx, rf_target* t, void* host, size_t stride_elems);
 /* Device pointers of the uint32 colour containers / float depth (row-major, stride = w),
- * for NCCL gathers done by the host layer. */
+ * for NCCL gathers done by the host layer. The depth plane is scratch state of the rasteriser: a
+ * Frame::clear recorded with draws only MARKS the 32x32 tiles the pass does not touch ("lazy depth
+ * clear"), and every read through this API sees the cleared values. rf_target_depth_devptr flushes
+ * the queued draws, writes the marked tiles out on the ctx stream and keeps the plane materialised
+ * from then on, so the pointer can be used like any device buffer ordered on that stream. */
 void* rf_target_color_devptr(rf_target* t);
 void* rf_target_depth_devptr(rf_target* t);
 
