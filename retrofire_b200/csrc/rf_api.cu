@@ -421,24 +421,38 @@ void launch_kernels(rf_ctx* c, PassSlot& s, const PassParams& P0) {
 
 // Any growth frees memory that in-flight kernels might still use -> callers guarantee idleness.
 rf_status ensure_arenas(rf_ctx* c, int lt, size_t nv, size_t n_tiles, const ArenaWants& w) {
-  for (auto& a : c->sets) {
-    bool ok = a.cv.reserve(nv * words_cv(lt) * 4 + 64) && a.sv.reserve(nv * words_sv(lt) * 4 + 64) &&
-              a.tiles.reserve(n_tiles * kTileArrays * 4 + 64) && a.cursors.reserve(64);
-    if (w.w_stris > c->capw_stris) ok = ok && a.stris.reserve(w.w_stris * 4);
-    if (w.w_smalls > c->capw_smalls) ok = ok && a.smalls.reserve(w.w_smalls * 4);
-    if (w.w_spans > c->capw_spans) ok = ok && a.spans.reserve(w.w_spans * 4);
-    if (w.w_tris > c->capw_tris) ok = ok && a.tris.reserve(w.w_tris * 4);
-    if (w.w_ckpts > c->capw_ckpts) ok = ok && a.ckpts.reserve(w.w_ckpts * 4);
-    if (w.entries > c->cap_entries) ok = ok && a.entries.reserve(w.entries * 16) && a.bins.reserve(w.entries * 8) && a.bins2.reserve(w.entries * 8);
-    if (w.longs > c->cap_long) ok = ok && a.longlist.reserve(w.longs * 8);
-    if (w.chunks > c->cap_chunks) ok = ok && a.chunks.reserve(w.chunks * 16) && a.ecks.reserve(w.chunks * Rec<8>::EW * 4);
-    if (w.tall > c->cap_tall) ok = ok && a.talllist.reserve(w.tall * 4);
-    if (!ok) return fail(c, RF_E_NOMEM, "pass arenas");
+  // every buffer at the larger of its present capacity and the wanted one (reserve() is a no-op for a buffer that is large enough)
+  const size_t stris = std::max(c->capw_stris, w.w_stris), smalls = std::max(c->capw_smalls, w.w_smalls), spans = std::max(c->capw_spans, w.w_spans),
+               tris = std::max(c->capw_tris, w.w_tris), ckpts = std::max(c->capw_ckpts, w.w_ckpts), entries = std::max(c->cap_entries, w.entries),
+               longs = std::max(c->cap_long, w.longs), chunks = std::max(c->cap_chunks, w.chunks), tall = std::max(c->cap_tall, w.tall);
+  auto reserve_set = [&](rf_ctx::ArenaSet& a) {
+    return a.cv.reserve(nv * words_cv(lt) * 4 + 64) && a.sv.reserve(nv * words_sv(lt) * 4 + 64) && a.tiles.reserve(n_tiles * kTileArrays * 4 + 64) &&
+           a.cursors.reserve(64) && a.stris.reserve(stris * 4) && a.smalls.reserve(smalls * 4) && a.spans.reserve(spans * 4) && a.tris.reserve(tris * 4) &&
+           a.ckpts.reserve(ckpts * 4) && a.entries.reserve(entries * 16) && a.bins.reserve(entries * 8) && a.bins2.reserve(entries * 8) &&
+           a.longlist.reserve(longs * 8) && a.chunks.reserve(chunks * 16) && a.ecks.reserve(chunks * Rec<8>::EW * 4) && a.talllist.reserve(tall * 4);
+  };
+  bool ok = reserve_set(c->sets[0]) && reserve_set(c->sets[1]);
+  if (!ok) {
+    // A buffer is freed before its larger replacement is allocated, so the peak is the new footprint; a failure here was seen
+    // once on a 2-GPU box right after other CUDA processes had exited. Let the device settle, give everything back, start over.
+    cudaGetLastError();
+    cudaDeviceSynchronize();
+    for (auto& a : c->sets) {
+      a.cv.release(); a.sv.release(); a.stris.release(); a.smalls.release(); a.spans.release(); a.tris.release(); a.entries.release(); a.bins.release();
+      a.bins2.release(); a.longlist.release(); a.ckpts.release(); a.chunks.release(); a.talllist.release(); a.ecks.release(); a.tiles.release(); a.cursors.release();
+    }
+    ok = reserve_set(c->sets[0]) && reserve_set(c->sets[1]);
   }
-  c->capw_stris = std::max(c->capw_stris, w.w_stris); c->capw_smalls = std::max(c->capw_smalls, w.w_smalls);
-  c->capw_spans = std::max(c->capw_spans, w.w_spans); c->capw_tris = std::max(c->capw_tris, w.w_tris);
-  c->capw_ckpts = std::max(c->capw_ckpts, w.w_ckpts); c->cap_entries = std::max(c->cap_entries, w.entries);
-  c->cap_long = std::max(c->cap_long, w.longs); c->cap_chunks = std::max(c->cap_chunks, w.chunks); c->cap_tall = std::max(c->cap_tall, w.tall);
+  if (!ok) {
+    size_t fr = 0, tot = 0;
+    const cudaError_t le = cudaGetLastError();
+    cudaMemGetInfo(&fr, &tot);
+    c->capw_stris = c->capw_smalls = c->capw_spans = c->capw_tris = c->capw_ckpts = c->cap_entries = c->cap_long = c->cap_chunks = c->cap_tall = 0;  // nothing is certain now
+    return fail(c, RF_E_NOMEM, "pass arenas (%s; free %zu of %zu MiB; want spans %zu tris %zu ckpts %zu stris %zu smalls %zu MiB, entries %zu, verts %zu)", cudaGetErrorString(le),
+                fr >> 20, tot >> 20, spans >> 18, tris >> 18, ckpts >> 18, stris >> 18, smalls >> 18, entries, nv);
+  }
+  c->capw_stris = stris; c->capw_smalls = smalls; c->capw_spans = spans; c->capw_tris = tris; c->capw_ckpts = ckpts;
+  c->cap_entries = entries; c->cap_long = longs; c->cap_chunks = chunks; c->cap_tall = tall;
   return RF_OK;
 }
 

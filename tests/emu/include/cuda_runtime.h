@@ -440,6 +440,8 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return c
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaMemGetInfo(size_t* fr, size_t* tot) { *fr = *tot = 0; return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
 inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
   std::memset(a, 0, sizeof *a);
