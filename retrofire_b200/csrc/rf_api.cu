@@ -779,6 +779,7 @@ rf_status validate_all(rf_ctx* c, bool only_oldest = false) {
       cudaEventElapsedTime(&a, c->ev_base, s.ev_start); cudaEventElapsedTime(&b, c->ev_base, s.ev_geo_t); cudaEventElapsedTime(&e, c->ev_base, s.ev_stop);
       if (s.profiled == 1) { cudaEventElapsedTime(&r0, c->ev_base, s.ev_k[RF_N_KERNELS - 1]); cudaEventElapsedTime(&r1, c->ev_base, s.ev_k[RF_N_KERNELS]); }
       fprintf(stderr, "[rf timeline] seq %u: geometry %.3f .. %.3f ms, raster %.3f .. %.3f, done %.3f\n", s.seq, a, b, r0, r1, e);
+      cudaGetLastError();  // an event of this debug printout that was never recorded must not surface as the next call's error
     }
     if (ps.overflow) {
       // Every later pass in flight was a no-op (device poison). Grow and replay from here, in order.

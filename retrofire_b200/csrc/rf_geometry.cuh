@@ -806,7 +806,15 @@ __global__ void __launch_bounds__(128, LT == 3 ? RF_SETUP_MIN_BLOCKS : 3) k_setu
   __shared__ uint32_t s_fit[4];
   using SS = SetupStage<LT>;
   __shared__ uint4 s_stage[4][SS::WORDS / 4];  // uint4: 16-byte aligned for the 128-bit accesses
-  if (rf_poisoned(P)) return;
+  // The poison test must be ONE decision per block: other blocks of this very kernel set the poison when they overflow, and a block
+  // whose warps read it on either side of that moment lost some warps while the rest went on to the block-wide allocation below with
+  // the missing warps' s_tot entries uninitialised — garbage counters (arena requests of hundreds of GB) and triangle records
+  // written far outside the arena (compute-sanitizer: profiles/r02_memcheck.txt). Seen when a 32-frame crates batch followed the
+  // bunny batch in one context.
+  __shared__ uint32_t s_poisoned;
+  if (threadIdx.x == 0) s_poisoned = rf_poisoned(P) ? 1u : 0u;
+  __syncthreads();
+  if (s_poisoned) return;
   const uint32_t lane = lane_id(), lt = (1u << lane) - 1u;
   // the triangles k_assemble did not set up and bin itself (see RF_BIN_SMALL): tall or wide ones, those near the target's edges, lines
   const uint32_t NT = (uint32_t)min(P.status->stris_needed, (unsigned long long)P.cap_stris);

@@ -277,7 +277,11 @@ __device__ __forceinline__ void block_bitonic(unsigned long long* sk, uint32_t n
 // (every element finds its output slot by binary search in the other run), so there is no depth limit.
 __global__ void __launch_bounds__(256) k_bin_sort_big(PassParams P) {
   extern __shared__ unsigned long long skb[];
-  if (rf_poisoned(P)) return;
+  // one decision per block (the span chain on the geo stream may set the poison while this kernel runs on the side stream)
+  __shared__ uint32_t s_poisoned;
+  if (threadIdx.x == 0) s_poisoned = rf_poisoned(P) ? 1u : 0u;
+  __syncthreads();
+  if (s_poisoned) return;
   const uint32_t n_work = P.status->n_work_big;
   for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
     const uint32_t tile = P.worklist_big[wi];
