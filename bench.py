@@ -15,11 +15,14 @@ fused into the rasteriser over NVLink peer memory, or `--exchange nccl` gathers 
 `value`   : Mfragments/s (Stats.frags.i per second) with geometry resident in HBM (rf_mesh).
 `e2e`     : same metric through the reference-facing calls with HOST (page-locked) vertex/index buffers
             every frame (H2D inside the timed region) and the colour buffer of every frame downloaded into
-            page-locked Buf2 storage; 16-frame steps into two alternating sets of device targets.
+            page-locked Buf2 storage; steps of F/2 frames into two alternating halves of the device targets; `frac_of_pcie` = its D2H
+            rate over the device-to-host ceiling measured in the same run with every rank copying at once.
 `roofline`: k_raster, algorithmic bytes 4*frags.i + 8*frags.o per launch over its
             CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth.
 `cpu_baseline`: the CPU oracle (1 thread, like the single-threaded reference) on a bounded
             sample of the same frames.
+`crates_4k`: the second configuration BASELINE.json's metric names (crates 3840x2160, 32-frame batches), same objects.
+`sort_first_8k` (N > 1): one 8K frame of 1 M small triangles, sort-first over the ranks, both exchange forms.
 `--impl reference`: the oracle port on all host cores (frames are independent), same metric.
 """
 from __future__ import annotations
