@@ -44,6 +44,7 @@ SKIP = {
     "test_bunny_x16", "test_crates_1089_full_4k", "test_sprites_10k_full", "test_small_tris_1m_8k",
     "test_small_tris_8k_row_bands_cover_the_frame", "test_fuzz_random_frames_through_one_context",
     "test_closed_device_handles_are_not_reused",  # creates its own Device: needs the real library and a GPU
+    "test_overflowing_pass_after_a_small_one_in_a_fresh_context",  # likewise (and a race between blocks is not reproducible here)
 }
 if os.environ.get("RF_EMU_FULL") != "1":
     SKIP |= {"test_arena_growth_replays_the_pass", "test_every_tile_heaviest_and_repeated_passes", "test_page_locked_geometry_is_dmad_directly"}

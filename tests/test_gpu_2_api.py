@@ -403,3 +403,35 @@ def test_closed_device_handles_are_not_reused(oracle):
     for _ in range(3):
         with rf.Device(0) as dev:
             assert_parity(run_gpu(dev, sc), want, name=sc.name)
+
+
+def test_overflowing_pass_after_a_small_one_in_a_fresh_context(oracle):
+    """The flow that exposed the k_setup poison race (profiles/r02_memcheck.txt): a context whose arenas were sized by a small pass of
+    3-lane triangles gets a pass of four 4K crates frames (5 lanes, 500,000 span records) — k_setup overflows the arenas while its own
+    blocks are still starting, the pass is replayed several times with larger arenas. Every frame must equal the oracle's, the
+    arena requests must stay sane (the race produced requests of hundreds of GB -> RF_E_NOMEM) and nothing may be written out of
+    bounds (it also produced triangle records far outside the arena: a sticky launch failure). Three fresh contexts."""
+    small = scenes.bunny(subdiv=0, w=400, h=300)
+    big = scenes.crates("1089")
+    want_small, want_big = run_oracle(oracle, small), run_oracle(oracle, big)
+    for rep in range(3):
+        with rf.Device(0) as dev:
+            assert_parity(run_gpu(dev, small), want_small, name=f"{small.name}-{rep}")
+            fbs = [dev.framebuf(big.w, big.h, big.fmt, True) for _ in range(4)]
+            try:
+                dev.stats(reset=True)
+                for fb in fbs:
+                    fb.clear(big.ctx)
+                for fb in fbs:
+                    dev.render_many(big.draws, fb)
+                dev.flush()
+                dev.sync()
+                assert dev.replays() >= 1, "the second pass was meant to overflow the arenas of the first"
+                stats = dev.stats(reset=True)
+                assert stats.frags.i == 4 * want_big[2].frags.i and stats.frags.o == 4 * want_big[2].frags.o
+                for k, fb in enumerate(fbs):
+                    got = (fb.download_color(), fb.download_depth(), want_big[2])
+                    assert_parity(got, want_big, name=f"{big.name}-{rep}-{k}")
+            finally:
+                for fb in fbs:
+                    fb._destroy(); dev._targets.remove(fb)
