@@ -395,6 +395,10 @@ class Device:
                 C.memmove(C.byref(arr, i * C.sizeof(RfDraw)), C.byref(d), C.sizeof(RfDraw))
                 keep.append(call)
             memo = (calls, len(calls), arr, keep)
+            # the memo keeps the list (and through it the caller's arrays) alive: bound it, oldest entries first, so that a loop
+            # which builds a new list every frame does not grow it without end (a frame batch re-submits a few hundred lists)
+            while len(self._many) >= 4096:
+                self._many.pop(next(iter(self._many)))
             self._many[id(calls)] = memo
         self._check(self.lib.rf_render_many(self.h, target.h, memo[2], memo[1]))
 
