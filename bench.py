@@ -517,7 +517,7 @@ def run_b200(args):
     # cpu_baseline) on a 32-frame batch (8-frame batches leave the pass pipeline half empty: 4,580 vs 5,250 frames/s)
     if args.workload == "bunny" and full:
         ctx["primary"] = False
-        mc = measure(ctx, "crates", 32, 10, 3, e2e=True, cpu_seconds=min(args.cpu_seconds, 4.0) if world == 1 else 0.0, latency=True)
+        mc = measure(ctx, "crates", 32, 20, 3, e2e=True, cpu_seconds=min(args.cpu_seconds, 4.0) if world == 1 else 0.0, latency=True)
         fc = fold(ctx, mc, "crates", pcie)
         fc["unit"] = "Mfragments/s"
         fc["draws_per_frame"] = len(mc["per_frame"][0])
